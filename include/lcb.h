@@ -1,0 +1,103 @@
+/* lcb.h -- C ABI of liblcb.so: B200 (sm_100a) kernels for lightcurver's STARRED hot path.
+ *
+ * Every entry point replaces one group of calls that lightcurver makes into the third-party
+ * `starred` package (paths relative to the lightcurver checkout, v1.2.3):
+ *
+ *   lcb_phot_fit_batch     star_photometry.py:66-128  setup_model / Loss / Optimizer('adabelief').minimize /
+ *                                                      model.model  (fixed-PSF amplitude+shift fit)
+ *                          + starred_utilities.py:10-39 get_flux_uncertainties (closed form, sigma_a)
+ *   lcb_psf_fit_batch      psf_modelling.py:164-171    starred.procedures.psf_routines.build_psf
+ *   lcb_psf_loss_grad      (same Loss object, one evaluation; used by parity tests)
+ *   lcb_noise_weights      star_photometry.py:108, roi_modelling.py:299  propagate_noise(method='SLIT')
+ *   lcb_deconv_*           roi_modelling.py:213-335    setup_model / Loss / Optimizer('adabelief').minimize
+ *
+ * Conventions: all arrays are C-contiguous float32, row-major [item][y][x]; positions are in data
+ * pixels with the origin at the stamp centre (n-1)/2 (roi_modelling.py:207-210).  `mem` selects
+ * where EVERY pointer of a call lives: LCB_MEM_DEVICE (device pointers, work is enqueued on
+ * `stream`, the call does not synchronise) or LCB_MEM_HOST (host pointers; the library stages
+ * through its own device arena, H2D and D2H copies included, and returns after synchronising).
+ * The caller owns every buffer; nothing is retained after return except explicit handles.
+ * Return value: 0 on success, negative lcb_status otherwise; lcb_last_error() gives the text.
+ * There is no CPU fallback: without a CUDA device every compute entry returns LCB_ERR_CUDA.
+ */
+#ifndef LCB_H
+#define LCB_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum lcb_status {
+    LCB_OK = 0,
+    LCB_ERR_ARG = -1,     /* bad argument / unsupported shape */
+    LCB_ERR_CUDA = -2,    /* CUDA runtime error (text in lcb_last_error) */
+    LCB_ERR_NOMEM = -3
+};
+
+enum lcb_mem { LCB_MEM_DEVICE = 0, LCB_MEM_HOST = 1 };
+
+/* per-item status flags written to status[] */
+enum lcb_item_status { LCB_ITEM_OK = 0, LCB_ITEM_NONFINITE = 1 };
+
+/* every recalled STARRED constant, switchable at run time. */
+typedef struct {
+    float gauss_fwhm_up;     /* FWHM of the target-resolution Gaussian, upsampled px (2.0) */
+    int   gauss_taps;        /* G, even, one of 8/12/16 (12) */
+    int   downsample_mean;   /* 1: D_k is the block mean, 0: block sum */
+    int   chi2_half;         /* 1: chi2 term is 1/2 sum w r^2 */
+    float clip_global_norm;  /* optax.clip_by_global_norm when scheduled (1.0) */
+    float lr_decay_rate;     /* exponential_decay rate over max_iterations (0.99) */
+    float belief_b1, belief_b2, belief_eps, belief_eps_root;
+} lcb_conventions;
+
+int lcb_conventions_get(lcb_conventions* out);
+int lcb_conventions_set(const lcb_conventions* in);
+const char* lcb_last_error(void);
+int lcb_version(void);
+/* number of visible CUDA devices (0 when none); never fails */
+int lcb_device_count(void);
+
+/* Optimiser options (starred Optimizer.minimize(**opts), star_photometry.py:115-120) */
+typedef struct {
+    int   n_iter;     /* max_iterations; loss history has exactly n_iter entries */
+    float lr;         /* init_learning_rate */
+    int   schedule;   /* schedule_learning_rate: 1 = clip_by_global_norm + exponential decay */
+} lcb_fit_opts;
+
+/* ---------------- K2: fixed-PSF amplitude + shift photometry ---------------------------------- */
+typedef struct {
+    int B;                  /* number of (frame,star) items */
+    int n, k;               /* stamp side (data px), subsampling factor; PSF side is n*k */
+    const float* data;      /* [B][n][n] */
+    const float* weight;    /* [B][n][n]  1/sigma^2 (0 = ignored pixel) */
+    const float* psf;       /* [Fp][n*k][n*k] narrow PSFs */
+    const int*   psf_index; /* [B] index into psf */
+    int Fp;                 /* number of PSFs */
+    const float* a0;        /* [B] initial amplitude */
+    const float* dx0;       /* [B] initial shifts, may be NULL (= 0) */
+    const float* dy0;
+} lcb_phot_batch;
+
+typedef struct {
+    float* a; float* dx; float* dy;   /* [B] fitted parameters */
+    float* sigma_a;                   /* [B] Fisher sigma of a (may be NULL) */
+    float* chi2;                      /* [B] sum w r^2 / n^2 at the final parameters (may be NULL) */
+    float* residuals;                 /* [B][n][n] data - model (may be NULL) */
+    float* loss_hist;                 /* [B][n_iter] (may be NULL) */
+    float* loss0;                     /* [B] loss at the initial parameters (may be NULL) */
+    float* grad0;                     /* [B][3] d loss / d (a,dx,dy) at the initial parameters (may be NULL) */
+    int*   status;                    /* [B] lcb_item_status (may be NULL) */
+} lcb_phot_out;
+
+int lcb_phot_fit_batch(const lcb_phot_batch* in, const lcb_fit_opts* opt, lcb_phot_out* out,
+                       int mem, void* stream);
+
+/* ---------------- measurement helper ---------------------------------------------------------- */
+/* FP32 FMA micro-benchmark: runs `iters` dependent-chain FFMA loops on every SM and returns the
+ * achieved TFLOP/s in *tflops (used as the measured roofline denominator by bench.py). */
+int lcb_fp32_peak(int iters, float* tflops, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LCB_H */

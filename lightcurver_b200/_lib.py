@@ -1,0 +1,162 @@
+"""ctypes binding of liblcb.so (the C ABI declared in include/lcb.h).
+
+The product has NO CPU fallback: importing this module without the built library raises, and every
+compute entry returns LCB_ERR_CUDA (-> RuntimeError) when no CUDA device is visible.
+"""
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = Path(os.environ.get('LCB_LIBRARY', _HERE / 'liblcb.so'))
+
+if not LIB_PATH.exists():
+    raise ImportError(
+        f"{LIB_PATH} is missing: build the sm_100a kernels first "
+        f"(python -m lightcurver_b200.build, or __graft_entry__.build()). "
+        f"lightcurver_b200 has no CPU fallback.")
+
+lib = C.CDLL(str(LIB_PATH))
+
+MEM_DEVICE, MEM_HOST = 0, 1
+c_fp = C.POINTER(C.c_float)
+c_ip = C.POINTER(C.c_int)
+
+
+class Conventions(C.Structure):
+    _fields_ = [('gauss_fwhm_up', C.c_float), ('gauss_taps', C.c_int), ('downsample_mean', C.c_int),
+                ('chi2_half', C.c_int), ('clip_global_norm', C.c_float), ('lr_decay_rate', C.c_float),
+                ('belief_b1', C.c_float), ('belief_b2', C.c_float), ('belief_eps', C.c_float),
+                ('belief_eps_root', C.c_float)]
+
+
+class FitOpts(C.Structure):
+    _fields_ = [('n_iter', C.c_int), ('lr', C.c_float), ('schedule', C.c_int)]
+
+
+class PhotBatch(C.Structure):
+    _fields_ = [('B', C.c_int), ('n', C.c_int), ('k', C.c_int),
+                ('data', C.c_void_p), ('weight', C.c_void_p), ('psf', C.c_void_p), ('psf_index', C.c_void_p),
+                ('Fp', C.c_int), ('a0', C.c_void_p), ('dx0', C.c_void_p), ('dy0', C.c_void_p)]
+
+
+class PhotOut(C.Structure):
+    _fields_ = [(nm, C.c_void_p) for nm in ('a', 'dx', 'dy', 'sigma_a', 'chi2', 'residuals', 'loss_hist',
+                                            'loss0', 'grad0', 'status')]
+
+
+lib.lcb_last_error.restype = C.c_char_p
+lib.lcb_version.restype = C.c_int
+lib.lcb_device_count.restype = C.c_int
+lib.lcb_conventions_get.argtypes = [C.POINTER(Conventions)]
+lib.lcb_conventions_set.argtypes = [C.POINTER(Conventions)]
+lib.lcb_phot_fit_batch.argtypes = [C.POINTER(PhotBatch), C.POINTER(FitOpts), C.POINTER(PhotOut), C.c_int, C.c_void_p]
+lib.lcb_phot_fit_batch.restype = C.c_int
+lib.lcb_fp32_peak.argtypes = [C.c_int, c_fp, c_fp]
+lib.lcb_fp32_peak.restype = C.c_int
+
+
+class LcbError(RuntimeError):
+    pass
+
+
+def check(rc, what):
+    if rc != 0:
+        raise LcbError(f"{what} failed (status {rc}): {lib.lcb_last_error().decode(errors='replace')}")
+
+
+def device_count():
+    return int(lib.lcb_device_count())
+
+
+def require_device():
+    if device_count() == 0:
+        raise LcbError("lightcurver_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+# ------------------------------------------------------------------ array plumbing
+def is_torch(x):
+    return type(x).__module__.startswith('torch')
+
+
+def ptr(x):
+    """Raw address of a C-contiguous numpy array or torch tensor (None -> NULL)."""
+    if x is None:
+        return None
+    if is_torch(x):
+        assert x.is_contiguous()
+        return C.c_void_p(x.data_ptr())
+    assert x.flags['C_CONTIGUOUS']
+    return C.c_void_p(x.ctypes.data)
+
+
+def as_f32(x, like_torch=None):
+    """C-contiguous float32 view/copy; numpy stays numpy, torch stays torch."""
+    if x is None:
+        return None
+    if is_torch(x):
+        import torch
+        return x.to(torch.float32).contiguous()
+    return np.ascontiguousarray(x, dtype=np.float32)
+
+
+def as_i32(x):
+    if x is None:
+        return None
+    if is_torch(x):
+        import torch
+        return x.to(torch.int32).contiguous()
+    return np.ascontiguousarray(x, dtype=np.int32)
+
+
+def empty_like_kind(ref, shape, dtype='f'):
+    """Uninitialised output of the same kind (numpy / torch device) as ``ref``."""
+    if is_torch(ref):
+        import torch
+        return torch.empty(shape, dtype=torch.float32 if dtype == 'f' else torch.int32, device=ref.device)
+    return np.empty(shape, dtype=np.float32 if dtype == 'f' else np.int32)
+
+
+def mem_kind(*arrays):
+    kinds = set()
+    for a in arrays:
+        if a is None:
+            continue
+        if is_torch(a):
+            kinds.add(MEM_DEVICE if a.is_cuda else MEM_HOST)
+        else:
+            kinds.add(MEM_HOST)
+    if len(kinds) != 1:
+        raise ValueError("all arrays of one call must live in the same memory (all host or all device)")
+    return kinds.pop()
+
+
+def current_stream(ref):
+    if is_torch(ref) and ref.is_cuda:
+        import torch
+        return C.c_void_p(torch.cuda.current_stream(ref.device).cuda_stream)
+    return None
+
+
+def get_conventions():
+    c = Conventions()
+    check(lib.lcb_conventions_get(C.byref(c)), 'lcb_conventions_get')
+    return c
+
+
+def set_conventions(**kw):
+    c = get_conventions()
+    for k, v in kw.items():
+        if not hasattr(c, k):
+            raise KeyError(k)
+        setattr(c, k, v)
+    check(lib.lcb_conventions_set(C.byref(c)), 'lcb_conventions_set')
+
+
+def fp32_peak(iters=4096):
+    require_device()
+    t, ms = C.c_float(0), C.c_float(0)
+    check(lib.lcb_fp32_peak(iters, C.byref(t), C.byref(ms)), 'lcb_fp32_peak')
+    return float(t.value), float(ms.value)

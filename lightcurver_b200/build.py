@@ -1,0 +1,60 @@
+"""Builds lightcurver_b200/liblcb.so (sm_100a only) with nvcc, in-tree.
+
+``python -m lightcurver_b200.build`` or ``__graft_entry__.build()``.  nvcc cross-compiles without a
+GPU; the resulting .so is git-ignored but travels to the GPU box with the repo snapshot.
+"""
+import concurrent.futures
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+CSRC = HERE / 'csrc'
+OUT = HERE / 'liblcb.so'
+OBJ = HERE / 'build'
+
+NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
+         '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr', '--extended-lambda']
+
+
+def _needs(target: Path, deps):
+    if not target.exists():
+        return True
+    t = target.stat().st_mtime
+    return any(Path(d).stat().st_mtime > t for d in deps)
+
+
+def build(verbose=False, force=False, ptxas_info=False):
+    OBJ.mkdir(exist_ok=True)
+    sources = sorted(CSRC.glob('*.cu'))
+    headers = sorted(CSRC.glob('*.cuh')) + [HERE.parent / 'include' / 'lcb.h']
+    jobs = []
+    for src in sources:
+        obj = OBJ / (src.stem + '.o')
+        if force or _needs(obj, [src] + headers):
+            cmd = [NVCC] + FLAGS + (['-Xptxas', '-v'] if ptxas_info else []) + ['-c', str(src), '-o', str(obj)]
+            jobs.append((src, cmd))
+    if jobs:
+        with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+            futs = {ex.submit(subprocess.run, cmd, capture_output=True, text=True): src for src, cmd in jobs}
+            for fut in concurrent.futures.as_completed(futs):
+                r = fut.result()
+                if verbose or r.returncode != 0 or ptxas_info:
+                    sys.stderr.write(r.stdout + r.stderr)
+                if r.returncode != 0:
+                    raise RuntimeError(f'nvcc failed on {futs[fut]}')
+    objs = [str(OBJ / (s.stem + '.o')) for s in sources]
+    if jobs or not OUT.exists():
+        cmd = [NVCC, '-shared', '-o', str(OUT)] + objs + ['-lcudart']
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError('link failed')
+    return OUT
+
+
+if __name__ == '__main__':
+    p = build(verbose='-v' in sys.argv, force='-f' in sys.argv, ptxas_info='--ptxas' in sys.argv)
+    print(p)

@@ -1,0 +1,127 @@
+// lcb_api.cu -- library-wide state of liblcb: last error, conventions, staging arena, FP32 peak probe.
+#include "lcb_common.cuh"
+
+static thread_local char g_err[512] = "";
+static lcb_conventions g_conv = {2.0f, 12, 1, 1, 1.0f, 0.99f, 0.9f, 0.999f, 1e-16f, 1e-16f};
+
+void lcb_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+const lcb_conventions& lcb_conv() { return g_conv; }
+
+DevConv lcb_devconv() {
+    const lcb_conventions& c = g_conv;
+    DevConv d;
+    const double sig = (double)c.gauss_fwhm_up / (2.0 * sqrt(2.0 * log(2.0)));
+    d.G = c.gauss_taps;
+    d.inv2s2 = (float)(1.0 / (2.0 * sig * sig));
+    d.invs2 = (float)(1.0 / (sig * sig));
+    d.gnorm = (float)(1.0 / (sqrt(2.0 * M_PI) * sig));
+    d.mean = c.downsample_mean;
+    d.half = c.chi2_half ? 0.5f : 1.0f;
+    d.clip = c.clip_global_norm;
+    d.decay = c.lr_decay_rate;
+    d.b1 = c.belief_b1; d.b2 = c.belief_b2; d.eps = c.belief_eps; d.eps_root = c.belief_eps_root;
+    return d;
+}
+
+static LcbArena g_arena;
+LcbArena& lcb_arena() { return g_arena; }
+
+int LcbArena::reserve(size_t bytes) {
+    int d = 0;
+    LCB_CUDA(cudaGetDevice(&d));
+    if (base && d == dev && cap >= bytes) return LCB_OK;
+    if (base) { cudaSetDevice(dev); cudaFree(base); cudaSetDevice(d); base = nullptr; cap = 0; }
+    size_t want = bytes + (bytes >> 2) + (1u << 20);
+    cudaError_t e = cudaMalloc((void**)&base, want);
+    if (e != cudaSuccess) {
+        lcb_set_error("arena cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        base = nullptr;
+        return LCB_ERR_NOMEM;
+    }
+    cap = want; dev = d; off = 0;
+    return LCB_OK;
+}
+
+void* LcbArena::take(size_t bytes) {
+    size_t a = (off + 255) & ~(size_t)255;
+    if (a + bytes > cap) return nullptr;
+    off = a + bytes;
+    return base + a;
+}
+
+extern "C" {
+
+const char* lcb_last_error(void) { return g_err; }
+int lcb_version(void) { return 100; }
+
+int lcb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int lcb_conventions_get(lcb_conventions* out) {
+    LCB_REQUIRE(out != nullptr, "lcb_conventions_get: NULL");
+    *out = g_conv;
+    return LCB_OK;
+}
+
+int lcb_conventions_set(const lcb_conventions* in) {
+    LCB_REQUIRE(in != nullptr, "lcb_conventions_set: NULL");
+    LCB_REQUIRE(in->gauss_taps == 8 || in->gauss_taps == 12 || in->gauss_taps == 16,
+                "gauss_taps must be 8, 12 or 16 (got %d)", in->gauss_taps);
+    LCB_REQUIRE(in->gauss_fwhm_up > 0.f, "gauss_fwhm_up must be > 0");
+    g_conv = *in;
+    return LCB_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------- FP32 FMA peak probe
+// 8 independent FFMA chains per thread, 1024 threads/CTA, 2 CTAs/SM: measures the SIMT FP32 issue
+// ceiling that the stencil kernels are bounded by.
+__global__ void __launch_bounds__(1024) k_fp32_peak(int iters, float* sink) {
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
+    float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float m = 0.999f, c = 1e-3f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+            a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+        }
+    }
+    float s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 123.456f) sink[0] = s;
+}
+
+extern "C" int lcb_fp32_peak(int iters, float* tflops, float* ms_out) {
+    LCB_REQUIRE(iters > 0 && tflops != nullptr, "lcb_fp32_peak: bad arguments");
+    int dev = 0, sms = 0;
+    LCB_CUDA(cudaGetDevice(&dev));
+    LCB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    float* sink = nullptr;
+    LCB_CUDA(cudaMalloc(&sink, 4));
+    cudaEvent_t e0, e1;
+    LCB_CUDA(cudaEventCreate(&e0));
+    LCB_CUDA(cudaEventCreate(&e1));
+    const int grid = sms * 2;
+    k_fp32_peak<<<grid, 1024>>>(iters / 8 + 1, sink);   // warm-up
+    LCB_CUDA(cudaEventRecord(e0));
+    k_fp32_peak<<<grid, 1024>>>(iters, sink);
+    LCB_CUDA(cudaEventRecord(e1));
+    LCB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    LCB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 8.0 * 16.0 * (double)iters * 1024.0 * (double)grid;
+    *tflops = (float)(flops / (ms * 1e-3) / 1e12);
+    if (ms_out) *ms_out = ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    return LCB_OK;
+}

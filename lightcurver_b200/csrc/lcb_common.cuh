@@ -1,0 +1,90 @@
+// lcb_common.cuh -- shared host/device helpers of liblcb (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <cmath>
+#include "../../include/lcb.h"
+
+// ---------------------------------------------------------------- host side: errors, conventions
+void lcb_set_error(const char* fmt, ...);
+const lcb_conventions& lcb_conv();
+
+#define LCB_CUDA(call)                                                                   \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess) {                                                        \
+            lcb_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,                  \
+                          cudaGetErrorString(e__));                                      \
+            return LCB_ERR_CUDA;                                                         \
+        }                                                                                \
+    } while (0)
+
+#define LCB_REQUIRE(cond, ...)                                                           \
+    do {                                                                                 \
+        if (!(cond)) { lcb_set_error(__VA_ARGS__); return LCB_ERR_ARG; }                 \
+    } while (0)
+
+// Device staging arena for LCB_MEM_HOST calls: one growing allocation per process and device.
+// h2d()/alloc() hand out 256-byte aligned slices; release() rewinds (no free between calls).
+struct LcbArena {
+    char* base = nullptr; size_t cap = 0; size_t off = 0; int dev = -1;
+    int reserve(size_t bytes);
+    void* take(size_t bytes);
+    void rewind() { off = 0; }
+};
+LcbArena& lcb_arena();
+
+// ---------------------------------------------------------------- device side
+struct DevConv {              // conventions in the form kernels consume
+    int G;                    // taps
+    float inv2s2;             // 1/(2 sigma^2)
+    float invs2;              // 1/sigma^2
+    float gnorm;              // 1/(sqrt(2pi) sigma)
+    int mean;                 // downsample mean
+    float half;               // 0.5 or 1.0 factor on chi2
+    float clip, decay, b1, b2, eps, eps_root;
+};
+DevConv lcb_devconv();
+
+#define LCB_GE_MAX 20        // G + k - 1 <= 16 + 4 - 1
+
+// Effective decimating taps for one axis (DESIGN.md "taps"): for shift c (upsampled px),
+//   ic = floor(c + 0.5), fr = c - ic,
+//   out[X] = sum_{p=0}^{GE-1} e[p] * in[k*X - ic - G/2 + p],   GE = G + k - 1
+//   e[p]  = (1/k) sum_{kap<k} g(kap - (p-G/2) - fr) [tau = kap-(p-G/2) in (-G/2, G/2]]
+//   de[p] = d e[p] / d c  (window held fixed)
+__device__ __forceinline__ void lcb_tap(const DevConv& cv, int k, float fr, int pidx, float& e, float& de) {
+    const int G2 = cv.G / 2;
+    const int p = pidx - G2;
+    float s = 0.f, d = 0.f;
+    for (int kap = 0; kap < k; ++kap) {
+        const int tau = kap - p;
+        if (tau >= -G2 + 1 && tau <= G2) {
+            const float x = (float)tau - fr;
+            const float g = cv.gnorm * expf(-x * x * cv.inv2s2);
+            s += g;
+            d += x * cv.invs2 * g;
+        }
+    }
+    const float sc = cv.mean ? 1.f / (float)k : 1.f;
+    e = s * sc;
+    de = d * sc;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// AdaBelief (optax.scale_by_belief) on one scalar parameter; g already clipped.
+struct BeliefCoef { float lr, b1, b2, omb1, omb2, inv_bc1, inv_bc2, eps, eps_root; };
+
+__device__ __forceinline__ void belief_update(const BeliefCoef& c, float g, float& p, float& mu, float& nu) {
+    mu = c.b1 * mu + c.omb1 * g;
+    const float d = g - mu;
+    nu = c.b2 * nu + c.omb2 * d * d + c.eps_root;
+    p -= c.lr * (mu * c.inv_bc1) / (sqrtf(nu * c.inv_bc2) + c.eps);
+}

@@ -1,0 +1,252 @@
+// lcb_phot.cu -- K2: fixed-PSF amplitude + shift photometry, one CTA per (frame, star) item.
+//
+// Replaces, per item, the STARRED calls of lightcurver/processes/star_photometry.py:66-128
+// (setup_model / Loss / Optimizer('adabelief').minimize / model.model) in the per-frame form of
+// SURVEY.md section 7 "hard part 2" (c fixed at 0, h = 0, mean = 0, clip per item), plus the closed
+// form of lightcurver/utilities/starred_utilities.py:10-39 (sigma_a).
+//
+// The whole fit (all n_iter AdaBelief iterations) runs inside one kernel: the narrow PSF, the
+// stamp, the weights and the intermediate planes stay in shared memory; per iteration
+//   taps -> pass 1 (rows, g and dg/dy) -> pass 2 (columns, g and dg/dx) + weighted residual
+//        -> block reduction (warp shuffles) of loss, dL/da, dL/ddx, dL/ddy -> AdaBelief in registers.
+#include "lcb_passes.cuh"
+
+struct PhotArgs {
+    int B, n, k, nu, n_iter, schedule, s_in_smem;
+    float lr;
+    const float *data, *weight, *psf, *a0, *dx0, *dy0;
+    const int* psf_index;
+    float *a, *dx, *dy, *sigma_a, *chi2, *residuals, *loss_hist, *loss0, *grad0;
+    int* status;
+    DevConv cv;
+};
+
+#define PHOT_THREADS 256
+
+template <int K, int G>
+__global__ void __launch_bounds__(PHOT_THREADS) k_phot_fit(PhotArgs A) {
+    using P = LcbPass<K, G>;
+    extern __shared__ __align__(16) float sm[];
+    const int n = A.n, nu = A.nu, tid = threadIdx.x;
+    const int ldv = n + 1, ldt = n + 1;
+    const int item = blockIdx.x;
+    // shared layout
+    float* taps = sm;                              // ey, dey, ex, dex  [4][LCB_GE_MAX]
+    float* red = taps + 4 * LCB_GE_MAX;            // [2][8 warps][4] double-buffered partials
+    float* dT = red + 2 * 8 * 4;                   // [n][ldt]  data, stored [X][Y]
+    float* wT = dT + n * ldt;                      // [n][ldt]
+    float* Vg = wT + n * ldt;                      // [nu][ldv]
+    float* Vd = Vg + nu * ldv;                     // [nu][ldv]
+    float* s_sm = Vd + nu * ldv;                   // [nu][nu] when it fits
+    const float* psf_g = A.psf + (size_t)A.psf_index[item] * nu * nu;
+    const float* s = A.s_in_smem ? s_sm : psf_g;
+
+    // ---- load: stamp + weight transposed, PSF tile (coalesced float loads; 16 KB at n=32,k=2)
+    const float* dg = A.data + (size_t)item * n * n;
+    const float* wg = A.weight + (size_t)item * n * n;
+    for (int i = tid; i < n * n; i += PHOT_THREADS) {
+        const int Y = i / n, X = i % n;
+        dT[X * ldt + Y] = dg[i];
+        wT[X * ldt + Y] = wg[i];
+    }
+    if (A.s_in_smem) {
+        const float4* src = reinterpret_cast<const float4*>(psf_g);
+        float4* dst = reinterpret_cast<float4*>(s_sm);
+        for (int i = tid; i < nu * nu / 4; i += PHOT_THREADS) dst[i] = __ldg(src + i);
+    }
+
+    __syncthreads();
+    float a = A.a0[item];
+    float dx = A.dx0 ? A.dx0[item] : 0.f;
+    float dy = A.dy0 ? A.dy0[item] : 0.f;
+    float mu[3] = {0.f, 0.f, 0.f}, nv[3] = {0.f, 0.f, 0.f};
+    float b1t = 1.f, b2t = 1.f;
+    int bad = 0;
+    const DevConv cv = A.cv;
+    const float fk = (float)K;
+
+    // iteration n_iter is the final evaluation (outputs only, no update)
+    for (int it = 0; it <= A.n_iter; ++it) {
+        const bool last = (it == A.n_iter);
+        const float cx = fk * dx, cy = fk * dy;
+        const int icx = (int)floorf(cx + 0.5f), icy = (int)floorf(cy + 0.5f);
+        if (tid < 2 * P::GE) {                      // (readers of the previous taps passed the reduce barrier)
+            const int which = tid / P::GE, p = tid % P::GE;
+            float e, de;
+            lcb_tap(cv, K, which ? (cx - (float)icx) : (cy - (float)icy), p, e, de);
+            taps[(which ? 2 : 0) * LCB_GE_MAX + p] = e;
+            taps[(which ? 3 : 1) * LCB_GE_MAX + p] = de;
+        }
+        __syncthreads();
+        lcb_pass1<K, G>(s, nu, nu, n, icy, taps, taps + LCB_GE_MAX, Vg, Vd, ldv, tid, PHOT_THREADS);
+        __syncthreads();
+        float loss = 0.f, ga = 0.f, gx = 0.f, gy = 0.f;   // on the last pass: chi2, H, -, -
+        float* resid = (last && A.residuals) ? A.residuals + (size_t)item * n * n : nullptr;
+        lcb_pass2<K, G>(Vg, Vd, ldv, nu, n, icx, taps + 2 * LCB_GE_MAX, taps + 3 * LCB_GE_MAX, tid,
+                        PHOT_THREADS, [&](int Y, int X, float m0, float mx, float my) {
+                            const float d = dT[X * ldt + Y], w = wT[X * ldt + Y];
+                            const float diff = fmaf(a, m0, -d);
+                            const float r = w * diff;
+                            if (!last) {
+                                loss = fmaf(r, diff, loss);
+                                ga = fmaf(r, m0, ga);
+                                gx = fmaf(r, mx, gx);
+                                gy = fmaf(r, my, gy);
+                            } else {
+                                loss = fmaf(r, diff, loss);
+                                ga = fmaf(w * m0, m0, ga);
+                                if (resid) resid[Y * n + X] = -diff;
+                            }
+                        });
+        loss = warp_sum(loss); ga = warp_sum(ga); gx = warp_sum(gx); gy = warp_sum(gy);
+        float* rbuf = red + (it & 1) * 32;
+        if ((tid & 31) == 0) {
+            float4 v = make_float4(loss, ga, gx, gy);
+            reinterpret_cast<float4*>(rbuf)[tid >> 5] = v;
+        }
+        __syncthreads();
+        float L = 0.f, Ga = 0.f, Gx = 0.f, Gy = 0.f;
+#pragma unroll
+        for (int w = 0; w < PHOT_THREADS / 32; ++w) {
+            const float4 v = reinterpret_cast<const float4*>(rbuf)[w];
+            L += v.x; Ga += v.y; Gx += v.z; Gy += v.w;
+        }
+        if (last) {
+            if (tid == 0) {
+                if (A.chi2) A.chi2[item] = L / (float)(n * n);
+                if (A.sigma_a) A.sigma_a[item] = rsqrtf((cv.half == 0.5f ? 1.f : 2.f) * Ga);
+            }
+            break;
+        }
+        L *= cv.half;
+        const float sc = (cv.half == 0.5f) ? 1.f : 2.f;   // d/dp of (half * sum w diff^2) = 2*half * sum r dm/dp
+        Ga *= sc;
+        float Gdx = sc * a * fk * Gx, Gdy = sc * a * fk * Gy;
+        if (tid == 0) {
+            if (A.loss_hist) A.loss_hist[(size_t)item * A.n_iter + it] = L;
+            if (it == 0) {
+                if (A.loss0) A.loss0[item] = L;
+                if (A.grad0) { A.grad0[item * 3] = Ga; A.grad0[item * 3 + 1] = Gdx; A.grad0[item * 3 + 2] = Gdy; }
+            }
+        }
+        if (!isfinite(L)) bad = 1;
+        // ---- optimiser (every thread redundantly; 3 parameters)
+        float lr = A.lr;
+        if (A.schedule) {
+            const float gn = sqrtf(Ga * Ga + Gdx * Gdx + Gdy * Gdy);
+            const float cs = (gn < cv.clip) ? 1.f : cv.clip / gn;
+            Ga *= cs; Gdx *= cs; Gdy *= cs;
+            lr = A.lr * powf(cv.decay, (float)it / (float)A.n_iter);
+        }
+        b1t *= cv.b1; b2t *= cv.b2;
+        BeliefCoef bc = {lr, cv.b1, cv.b2, 1.f - cv.b1, 1.f - cv.b2, 1.f / (1.f - b1t), 1.f / (1.f - b2t),
+                         cv.eps, cv.eps_root};
+        belief_update(bc, Ga, a, mu[0], nv[0]);
+        belief_update(bc, Gdx, dx, mu[1], nv[1]);
+        belief_update(bc, Gdy, dy, mu[2], nv[2]);
+        // keep the G-tap windows inside what the halo logic supports
+        const float lim = 0.25f * (float)n;
+        dx = fminf(fmaxf(dx, -lim), lim);
+        dy = fminf(fmaxf(dy, -lim), lim);
+    }
+    if (tid == 0) {
+        A.a[item] = a; A.dx[item] = dx; A.dy[item] = dy;
+        if (A.status) A.status[item] = bad ? LCB_ITEM_NONFINITE : LCB_ITEM_OK;
+    }
+}
+
+template <int K, int G>
+static int launch_phot(const PhotArgs& A, size_t smem, cudaStream_t st) {
+    LCB_CUDA(cudaFuncSetAttribute(k_phot_fit<K, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_phot_fit<K, G><<<A.B, PHOT_THREADS, smem, st>>>(A);
+    LCB_CUDA(cudaGetLastError());
+    return LCB_OK;
+}
+
+static int dispatch_phot(const PhotArgs& A, size_t smem, cudaStream_t st) {
+    const int G = A.cv.G;
+#define CASE(KK, GG) if (A.k == KK && G == GG) return launch_phot<KK, GG>(A, smem, st);
+    CASE(1, 12) CASE(2, 12) CASE(3, 12) CASE(4, 12)
+    CASE(1, 8) CASE(2, 8) CASE(3, 8)
+    CASE(1, 16) CASE(2, 16) CASE(3, 16)
+#undef CASE
+    lcb_set_error("photometry: unsupported (subsampling_factor=%d, gauss_taps=%d)", A.k, G);
+    return LCB_ERR_ARG;
+}
+
+extern "C" int lcb_phot_fit_batch(const lcb_phot_batch* in, const lcb_fit_opts* opt, lcb_phot_out* out,
+                                  int mem, void* stream) {
+    LCB_REQUIRE(in && opt && out, "lcb_phot_fit_batch: NULL argument");
+    LCB_REQUIRE(in->B >= 0 && in->n >= 4 && in->k >= 1 && in->Fp >= 1, "lcb_phot_fit_batch: bad sizes B=%d n=%d k=%d Fp=%d",
+                in->B, in->n, in->k, in->Fp);
+    LCB_REQUIRE(opt->n_iter >= 0, "n_iter must be >= 0");
+    LCB_REQUIRE(in->data && in->weight && in->psf && in->psf_index && in->a0, "lcb_phot_fit_batch: NULL input array");
+    LCB_REQUIRE(out->a && out->dx && out->dy, "lcb_phot_fit_batch: a/dx/dy outputs are mandatory");
+    LCB_REQUIRE(((size_t)in->n * in->k * in->n * in->k) % 4 == 0, "PSF plane must be a multiple of 4 floats");
+    if (in->B == 0) return LCB_OK;
+    if (lcb_device_count() == 0) { lcb_set_error("no CUDA device: liblcb has no CPU fallback"); return LCB_ERR_CUDA; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int B = in->B, n = in->n, k = in->k, nu = n * k, T = opt->n_iter;
+    PhotArgs A;
+    memset(&A, 0, sizeof(A));
+    A.B = B; A.n = n; A.k = k; A.nu = nu; A.n_iter = T; A.schedule = opt->schedule; A.lr = opt->lr;
+    A.cv = lcb_devconv();
+    const size_t fixed = (size_t)(4 * LCB_GE_MAX + 64 + 2 * n * (n + 1) + 2 * nu * (n + 1)) * 4;
+    const size_t with_s = fixed + (size_t)nu * nu * 4;
+    int dev = 0, maxsm = 0;
+    LCB_CUDA(cudaGetDevice(&dev));
+    LCB_CUDA(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    LCB_REQUIRE(fixed <= (size_t)maxsm, "photometry: stamp %dx%d (k=%d) needs %zu B of shared memory (> %d)", n, n, k, fixed, maxsm);
+    A.s_in_smem = (with_s <= (size_t)maxsm) ? 1 : 0;
+    const size_t smem = A.s_in_smem ? with_s : fixed;
+
+    if (mem == LCB_MEM_DEVICE) {
+        A.data = in->data; A.weight = in->weight; A.psf = in->psf; A.psf_index = in->psf_index;
+        A.a0 = in->a0; A.dx0 = in->dx0; A.dy0 = in->dy0;
+        A.a = out->a; A.dx = out->dx; A.dy = out->dy; A.sigma_a = out->sigma_a; A.chi2 = out->chi2;
+        A.residuals = out->residuals; A.loss_hist = out->loss_hist; A.loss0 = out->loss0; A.grad0 = out->grad0;
+        A.status = out->status;
+        return dispatch_phot(A, smem, st);
+    }
+    LCB_REQUIRE(mem == LCB_MEM_HOST, "mem must be LCB_MEM_DEVICE or LCB_MEM_HOST");
+    // ---- host pointers: stage through the arena
+    LcbArena& ar = lcb_arena();
+    const size_t nn = (size_t)n * n, pp = (size_t)nu * nu;
+    size_t need = 2 * B * nn * 4 + (size_t)in->Fp * pp * 4 + (size_t)B * 4 * 16 + (size_t)B * nn * 4 +
+                  (size_t)B * T * 4 + 64 * 256;
+    int rc = ar.reserve(need);
+    if (rc) return rc;
+    ar.rewind();
+    auto up = [&](const void* h, size_t bytes, const void** d) -> int {
+        if (!h) { *d = nullptr; return LCB_OK; }
+        void* p = ar.take(bytes);
+        if (!p) { lcb_set_error("arena overflow"); return LCB_ERR_NOMEM; }
+        LCB_CUDA(cudaMemcpyAsync(p, h, bytes, cudaMemcpyHostToDevice, st));
+        *d = p;
+        return LCB_OK;
+    };
+    auto dn = [&](void* h, size_t bytes, void** d) -> int {
+        if (!h) { *d = nullptr; return LCB_OK; }
+        *d = ar.take(bytes);
+        if (!*d) { lcb_set_error("arena overflow"); return LCB_ERR_NOMEM; }
+        return LCB_OK;
+    };
+#define UP(f, bytes) if ((rc = up(in->f, bytes, (const void**)&A.f))) return rc;
+    UP(data, B * nn * 4) UP(weight, B * nn * 4) UP(psf, in->Fp * pp * 4) UP(psf_index, (size_t)B * 4)
+    UP(a0, (size_t)B * 4) UP(dx0, (size_t)B * 4) UP(dy0, (size_t)B * 4)
+#undef UP
+#define DN(f, bytes) if ((rc = dn(out->f, bytes, (void**)&A.f))) return rc;
+    DN(a, (size_t)B * 4) DN(dx, (size_t)B * 4) DN(dy, (size_t)B * 4) DN(sigma_a, (size_t)B * 4) DN(chi2, (size_t)B * 4)
+    DN(residuals, B * nn * 4) DN(loss_hist, (size_t)B * T * 4) DN(loss0, (size_t)B * 4) DN(grad0, (size_t)B * 12)
+    DN(status, (size_t)B * 4)
+#undef DN
+    rc = dispatch_phot(A, smem, st);
+    if (rc) return rc;
+#define BACK(f, bytes) if (out->f) LCB_CUDA(cudaMemcpyAsync(out->f, A.f, bytes, cudaMemcpyDeviceToHost, st));
+    BACK(a, (size_t)B * 4) BACK(dx, (size_t)B * 4) BACK(dy, (size_t)B * 4) BACK(sigma_a, (size_t)B * 4) BACK(chi2, (size_t)B * 4)
+    BACK(residuals, B * nn * 4) BACK(loss_hist, (size_t)B * T * 4) BACK(loss0, (size_t)B * 4) BACK(grad0, (size_t)B * 12)
+    BACK(status, (size_t)B * 4)
+#undef BACK
+    LCB_CUDA(cudaStreamSynchronize(st));
+    return LCB_OK;
+}
