@@ -92,6 +92,49 @@ typedef struct {
 int lcb_phot_fit_batch(const lcb_phot_batch* in, const lcb_fit_opts* opt, lcb_phot_out* out,
                        int mem, void* stream);
 
+/* ---------------- K1: per-frame PSF fit (starred build_psf) ------------------------------------ */
+/* Ragged batch: frame f owns stars star_off[f] .. star_off[f+1]-1 of every per-star array. */
+typedef struct {
+    int F;                   /* frames */
+    const int* star_off;     /* [F+1] */
+    int n, k;                /* stamp side, subsampling factor (nu = n*k) */
+    const float* data;       /* [sumN][n][n] stamps, already normalised by the caller */
+    const float* weight;     /* [sumN][n][n] mask / sigma^2 */
+    const float* noisemap;   /* [sumN][n][n] sigma; only read when opts.noise_weights = 1 */
+    const float* W;          /* [F][J][nu*nu] starlet-space weights supplied by the caller, or NULL */
+} lcb_psf_batch;
+
+typedef struct {
+    int   n_iter_analytic;   /* stage 1 iterations (reference: L-BFGS-B maxiter; here LM, early stop) ; 0 = skip */
+    int   n_iter_adabelief;  /* stage 2 iterations */
+    float lr;                /* stage 2 init_learning_rate (scheduled, clipped) */
+    float lam_scales, lam_hf;/* regularization_strength_scales / _hf */
+    int   noise_weights;     /* 0: W from batch (NULL -> 1);  1: SLIT-style propagation of noisemap */
+    float fwhm_min, fwhm_max, beta_min, beta_max;   /* bounds of the analytic stage */
+} lcb_psf_opts;
+
+typedef struct {
+    float* moffat;           /* [F][5] fwhm_x, fwhm_y, phi, beta, C   in: guess, out: fitted */
+    float* a; float* x0; float* y0;   /* [sumN]                       in: guess, out: fitted */
+    float* background;       /* [F][nu*nu]                            in: initial grid, out: fitted */
+    float* narrow_psf;       /* [F][nu*nu] (may be NULL) */
+    float* full_psf;         /* [F][nu*nu] (may be NULL) */
+    float* residuals;        /* [sumN][n][n] data - model (may be NULL) */
+    float* chi2;             /* [F] sum w r^2 / #(w>0) (may be NULL) */
+    float* loss_hist;        /* [F][n_iter_adabelief] (may be NULL) */
+    float* loss_hist_analytic; /* [F][n_iter_analytic] (may be NULL) */
+    float* W_out;            /* [F][J][nu*nu] the weights used (may be NULL) */
+    float* loss0;            /* [F] stage-2 loss at its initial point (may be NULL) */
+    float* grad_b0;          /* [F][nu*nu] d loss / d background at the initial point (may be NULL) */
+    float* grad_s0;          /* [sumN][3] d loss / d (a, x0, y0) at the initial point (may be NULL) */
+    int*   status;           /* [F] (may be NULL) */
+} lcb_psf_out;
+
+/* number of starlet scales used for a grid of side nu: int(log2(nu)) */
+int lcb_starlet_scales(int nu);
+int lcb_psf_fit_batch(const lcb_psf_batch* in, const lcb_psf_opts* opt, lcb_psf_out* out,
+                      int mem, void* stream);
+
 /* ---------------- measurement helper ---------------------------------------------------------- */
 /* FP32 FMA micro-benchmark: runs `iters` dependent-chain FFMA loops on every SM and returns the
  * achieved TFLOP/s in *tflops (used as the measured roofline denominator by bench.py). */

@@ -160,3 +160,28 @@ def fp32_peak(iters=4096):
     t, ms = C.c_float(0), C.c_float(0)
     check(lib.lcb_fp32_peak(iters, C.byref(t), C.byref(ms)), 'lcb_fp32_peak')
     return float(t.value), float(ms.value)
+
+
+class PsfBatch(C.Structure):
+    _fields_ = [('F', C.c_int), ('star_off', C.c_void_p), ('n', C.c_int), ('k', C.c_int),
+                ('data', C.c_void_p), ('weight', C.c_void_p), ('noisemap', C.c_void_p), ('W', C.c_void_p)]
+
+
+class PsfOpts(C.Structure):
+    _fields_ = [('n_iter_analytic', C.c_int), ('n_iter_adabelief', C.c_int), ('lr', C.c_float),
+                ('lam_scales', C.c_float), ('lam_hf', C.c_float), ('noise_weights', C.c_int),
+                ('fwhm_min', C.c_float), ('fwhm_max', C.c_float), ('beta_min', C.c_float), ('beta_max', C.c_float)]
+
+
+PSF_OUT_FIELDS = ('moffat', 'a', 'x0', 'y0', 'background', 'narrow_psf', 'full_psf', 'residuals', 'chi2',
+                  'loss_hist', 'loss_hist_analytic', 'W_out', 'loss0', 'grad_b0', 'grad_s0', 'status')
+
+
+class PsfOut(C.Structure):
+    _fields_ = [(nm, C.c_void_p) for nm in PSF_OUT_FIELDS]
+
+
+lib.lcb_starlet_scales.argtypes = [C.c_int]
+lib.lcb_starlet_scales.restype = C.c_int
+lib.lcb_psf_fit_batch.argtypes = [C.POINTER(PsfBatch), C.POINTER(PsfOpts), C.POINTER(PsfOut), C.c_int, C.c_void_p]
+lib.lcb_psf_fit_batch.restype = C.c_int

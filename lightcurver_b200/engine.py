@@ -48,3 +48,58 @@ def phot_fit_batch(data, weight, psf, psf_index, a0, k, n_iter, lr=1e-3, schedul
     rc = _lib.lib.lcb_phot_fit_batch(C.byref(bi), C.byref(opts), C.byref(bo), mem, current_stream(data))
     _lib.check(rc, 'lcb_phot_fit_batch')
     return out
+
+
+def starlet_scales(nu):
+    return int(_lib.lib.lcb_starlet_scales(int(nu)))
+
+
+def _clone_f32(x, ref):
+    """float32 C-contiguous private copy of the same kind as ``ref`` (in/out arrays of the ABI)."""
+    if _lib.is_torch(ref):
+        import torch
+        return torch.as_tensor(x, dtype=torch.float32, device=ref.device).contiguous().clone()
+    return np.array(x, dtype=np.float32, order='C', copy=True)
+
+
+def psf_fit_batch(data, weight, star_off, k, moffat0, a0, x00=None, y00=None, background0=None,
+                  noisemap=None, W=None, n_iter_analytic=100, n_iter_adabelief=3000, lr=1e-3,
+                  lam_scales=1.0, lam_hf=1.0, noise_weights=False, bounds=None,
+                  want=('narrow_psf', 'full_psf', 'residuals', 'chi2', 'loss_hist', 'status')):
+    """K1: ragged batch of per-frame PSF fits (lcb_psf_fit_batch).
+
+    data, weight (sumN,n,n); star_off (F+1,) CSR offsets; moffat0 (F,5) = fwhm_x, fwhm_y, phi, beta, C
+    guesses; a0 (sumN,).  ``want`` lists optional outputs (see lcb_psf_out in include/lcb.h).
+    Returns a dict with moffat, a, x0, y0, background and the requested outputs.
+    """
+    _lib.require_device()
+    data, weight = as_f32(data), as_f32(weight)
+    noisemap, W = as_f32(noisemap), as_f32(W)
+    star_off = as_i32(star_off)
+    mem = mem_kind(data, weight, star_off, noisemap, W)
+    sumN, n = int(data.shape[0]), int(data.shape[-1])
+    F = int(star_off.shape[0]) - 1
+    nu = n * k
+    J = starlet_scales(nu)
+    if W is not None and tuple(W.shape) != (F, J, nu, nu):
+        raise ValueError(f"W must be ({F},{J},{nu},{nu}); got {tuple(W.shape)}")
+    out = dict(moffat=_clone_f32(moffat0, data), a=_clone_f32(a0, data),
+               x0=_clone_f32(np.zeros(sumN) if x00 is None else x00, data),
+               y0=_clone_f32(np.zeros(sumN) if y00 is None else y00, data),
+               background=_clone_f32(np.zeros((F, nu, nu)) if background0 is None else background0, data))
+    if tuple(out['moffat'].shape) != (F, 5) or tuple(out['a'].shape) != (sumN,):
+        raise ValueError("moffat0 must be (F,5) and a0 (sumN,)")
+    shapes = dict(narrow_psf=(F, nu, nu), full_psf=(F, nu, nu), residuals=(sumN, n, n), chi2=(F,),
+                  loss_hist=(F, n_iter_adabelief), loss_hist_analytic=(F, n_iter_analytic),
+                  W_out=(F, J, nu, nu), loss0=(F,), grad_b0=(F, nu, nu), grad_s0=(sumN, 3), status=(F,))
+    for nm in want:
+        out[nm] = empty_like_kind(data, shapes[nm], 'i' if nm == 'status' else 'f')
+    b = bounds or {}
+    opts = _lib.PsfOpts(int(n_iter_analytic), int(n_iter_adabelief), float(lr), float(lam_scales), float(lam_hf),
+                        int(bool(noise_weights)), float(b.get('fwhm_min', 1.0)), float(b.get('fwhm_max', n / 2.0)),
+                        float(b.get('beta_min', 1.1)), float(b.get('beta_max', 12.0)))
+    bi = _lib.PsfBatch(F, ptr(star_off), n, k, ptr(data), ptr(weight), ptr(noisemap), ptr(W))
+    bo = _lib.PsfOut(*[ptr(out.get(nm)) for nm in _lib.PSF_OUT_FIELDS])
+    rc = _lib.lib.lcb_psf_fit_batch(C.byref(bi), C.byref(opts), C.byref(bo), mem, current_stream(data))
+    _lib.check(rc, 'lcb_psf_fit_batch')
+    return out

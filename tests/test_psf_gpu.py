@@ -1,0 +1,143 @@
+"""K1 parity: CUDA per-frame PSF fit (through the C ABI) vs the CPU oracle.
+
+Tolerances are BASELINE.json's: loss and gradient at identical parameters within 1e-5 relative;
+after a fixed iteration count fitted fluxes within 1e-4 relative and PSF pixels within 1e-3 of the
+peak.
+"""
+import numpy as np
+import pytest
+
+from lightcurver_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def _frames(F, N, n, k, seed, norm=True):
+    d = synthetic.make_psf_frames(F, N, n, k, seed=seed)
+    data = d['data'].astype(np.float64)
+    nm = d['noisemap'].astype(np.float64)
+    if norm:
+        sc = data.max() / 100.0
+        data, nm = data / sc, nm / sc
+    weight = d['masks'] / nm ** 2
+    a0 = (data * d['masks']).sum((-1, -2)) * k * k
+    off = np.arange(F + 1, dtype=np.int32) * N
+    return d, data.astype(np.float32), nm.astype(np.float32), weight.astype(np.float32), a0.astype(np.float32), off
+
+
+def _flat(x):
+    return x.reshape(-1, *x.shape[2:])
+
+
+@pytest.mark.parametrize("n,k,N", [(32, 2, 5), (16, 1, 3), (24, 2, 2), (18, 3, 4)])
+def test_psf_loss_grad_parity(cuda_device, n, k, N):
+    """Loss and full gradient (grid, a, x0, y0) at an arbitrary point, with W != 1."""
+    from lightcurver_b200 import engine
+    from oracle import starred_model as sm
+    F = 2
+    d, data, nm, weight, a0, off = _frames(F, N, n, k, seed=100 + n)
+    nu = n * k
+    rng = np.random.default_rng(1)
+    moffat = np.stack([np.full(F, 3.2), np.full(F, 3.6), np.full(F, 0.4), np.full(F, 2.8), np.ones(F)], -1)
+    J = engine.starlet_scales(nu)
+    W = rng.uniform(0.5, 2.0, (F, J, nu, nu)).astype(np.float32)
+    b0 = (1e-4 * rng.standard_normal((F, nu, nu))).astype(np.float32)
+    x00 = rng.uniform(-0.7, 0.7, (F, N)).astype(np.float32)
+    y00 = rng.uniform(-0.7, 0.7, (F, N)).astype(np.float32)
+    a00 = (a0 * rng.uniform(0.9, 1.1, (F, N))).astype(np.float32)
+    out = engine.psf_fit_batch(_flat(data), _flat(weight), off, k, moffat, a00.ravel(), x00.ravel(), y00.ravel(),
+                               background0=b0, W=W, n_iter_analytic=0, n_iter_adabelief=1, lr=1e-3,
+                               lam_scales=0.7, lam_hf=1.3, want=('loss0', 'grad_b0', 'grad_s0', 'status'))
+    s_fixed = sm.moffat_image(moffat[:, 0], moffat[:, 1], moffat[:, 2], moffat[:, 3], n, k).numpy()
+    L, (gb, ga, gx, gy) = sm.psf_loss_grad(s_fixed, b0, a00, x00, y00, data, weight, W, n, k, 0.7, 1.3)
+    np.testing.assert_allclose(out['loss0'], L, rtol=1e-5)
+    np.testing.assert_allclose(out['grad_b0'], gb, rtol=1e-5, atol=1e-5 * np.abs(gb).max())
+    gs = np.stack([ga, gx, gy], -1).reshape(-1, 3)
+    np.testing.assert_allclose(out['grad_s0'], gs, rtol=2e-5, atol=1e-5 * np.abs(gs).max(0).max())
+
+
+def test_psf_stage2_fit_parity(cuda_device):
+    """Fixed iteration count from the same start: fluxes 1e-4 rel, PSF pixels 1e-3 of the peak."""
+    from lightcurver_b200 import engine
+    from oracle import starred_model as sm
+    n, k, N, F, T = 32, 2, 6, 2, 200
+    d, data, nm, weight, a0, off = _frames(F, N, n, k, seed=7)
+    nu = n * k
+    moffat = np.stack([d['fwhm'], d['fwhm'], np.zeros(F), np.full(F, 3.0), np.ones(F)], -1)
+    W = np.stack([sm.propagate_noise_slit(nm[f], k).numpy() for f in range(F)]).astype(np.float32)
+    out = engine.psf_fit_batch(_flat(data), _flat(weight), off, k, moffat, a0.ravel(), W=W,
+                               n_iter_analytic=0, n_iter_adabelief=T, lr=1e-3, lam_scales=1.0, lam_hf=1.0)
+    s_fixed = sm.moffat_image(moffat[:, 0], moffat[:, 1], moffat[:, 2], moffat[:, 3], n, k).numpy()
+    z = np.zeros((F, N))
+    ref = sm.fit_psf_stage2(s_fixed, np.zeros((F, nu, nu)), a0, z, z, data, weight, W, n, k, T, lr=1e-3,
+                            lam_scales=1.0, lam_hf=1.0)
+    np.testing.assert_allclose(out['a'].reshape(F, N), ref['a'], rtol=1e-4)
+    np.testing.assert_allclose(out['loss_hist'], ref['loss_hist'], rtol=1e-4)
+    s_ref = s_fixed + ref['b']
+    s_ref /= s_ref.sum((-1, -2), keepdims=True)
+    assert np.abs(out['narrow_psf'] - s_ref).max() <= 1e-3 * s_ref.max()
+    for f in range(F):
+        pr = sm.psf_products(s_fixed[f] + out['background'][f], out['a'].reshape(F, N)[f], out['x0'].reshape(F, N)[f],
+                             out['y0'].reshape(F, N)[f], data[f], weight[f], n, k)
+        np.testing.assert_allclose(out['full_psf'][f], pr['full_psf'], atol=1e-6 * pr['full_psf'].max() + 1e-9, rtol=1e-4)
+        np.testing.assert_allclose(out['residuals'].reshape(F, N, n, n)[f], pr['residuals'], atol=2e-4 * np.abs(data).max())
+        np.testing.assert_allclose(out['chi2'][f], pr['chi2'], rtol=1e-3)
+    assert (out['status'] == 0).all()
+
+
+def test_psf_noise_weights_parity(cuda_device):
+    from lightcurver_b200 import engine
+    from oracle import starred_model as sm
+    n, k, N, F = 32, 2, 4, 3
+    d, data, nm, weight, a0, off = _frames(F, N, n, k, seed=9)
+    moffat = np.stack([d['fwhm'], d['fwhm'], np.zeros(F), np.full(F, 3.0), np.ones(F)], -1)
+    out = engine.psf_fit_batch(_flat(data), _flat(weight), off, k, moffat, a0.ravel(), noisemap=_flat(nm),
+                               noise_weights=True, n_iter_analytic=0, n_iter_adabelief=1, want=('W_out',))
+    for f in range(F):
+        W = sm.propagate_noise_slit(nm[f], k).numpy()
+        np.testing.assert_allclose(out['W_out'][f], W, rtol=2e-4, atol=1e-6 * W.max())
+
+
+def test_psf_stage1_converges_like_lbfgsb(cuda_device):
+    """Analytic stage: LM in the kernel vs scipy L-BFGS-B in the oracle, compared on the converged
+    loss and parameters (the trajectories differ by construction)."""
+    from lightcurver_b200 import engine
+    from oracle import starred_model as sm
+    n, k, N, F = 32, 2, 6, 3
+    d, data, nm, weight, a0, off = _frames(F, N, n, k, seed=21)
+    moffat = np.stack([np.full(F, 3.0), np.full(F, 3.0), np.zeros(F), np.full(F, 2.5), np.ones(F)], -1)
+    out = engine.psf_fit_batch(_flat(data), _flat(weight), off, k, moffat, a0.ravel(), n_iter_analytic=100,
+                               n_iter_adabelief=0, want=('loss_hist_analytic', 'status', 'narrow_psf'))
+    for f in range(F):
+        ref = sm.fit_psf_stage1(data[f], weight[f], n, k, 3.0, a0[f], 400)
+        L_gpu = out['loss_hist_analytic'][f, -1]
+        assert L_gpu <= ref['loss'] * (1 + 2e-4), (L_gpu, ref['loss'])
+        assert abs(L_gpu - ref['loss']) <= 2e-3 * ref['loss']
+        np.testing.assert_allclose(out['a'].reshape(F, N)[f], ref['a'], rtol=2e-3)
+        fw_gpu = np.sort(out['moffat'][f, :2])
+        fw_ref = np.sort([ref['fwhm_x'], ref['fwhm_y']])
+        np.testing.assert_allclose(fw_gpu, fw_ref, rtol=5e-3)
+        np.testing.assert_allclose(out['moffat'][f, 3], ref['beta'], rtol=2e-2)
+        s_ref = sm.moffat_image(ref['fwhm_x'], ref['fwhm_y'], ref['phi'], ref['beta'], n, k).numpy()
+        assert np.abs(out['narrow_psf'][f] - s_ref).max() <= 2e-3 * s_ref.max()
+
+
+def test_psf_ragged_batch_matches_single_frames(cuda_device):
+    """Frames with different star counts in one batch give bit-identical results to separate calls."""
+    from lightcurver_b200 import engine
+    n, k = 16, 2
+    d, data, nm, weight, a0, off = _frames(3, 5, n, k, seed=33)
+    keep = [[0, 1, 2, 3, 4], [1, 3], [0, 2, 4]]
+    dat = np.concatenate([data[f][kk] for f, kk in enumerate(keep)])
+    wgt = np.concatenate([weight[f][kk] for f, kk in enumerate(keep)])
+    a00 = np.concatenate([a0[f][kk] for f, kk in enumerate(keep)])
+    off = np.cumsum([0] + [len(kk) for kk in keep]).astype(np.int32)
+    moffat = np.tile(np.array([3.0, 3.0, 0.0, 2.5, 1.0]), (3, 1))
+    kw = dict(n_iter_analytic=20, n_iter_adabelief=30, lr=1e-3)
+    out = engine.psf_fit_batch(dat, wgt, off, k, moffat, a00, **kw)
+    for f in range(3):
+        s = slice(off[f], off[f + 1])
+        one = engine.psf_fit_batch(dat[s], wgt[s], np.array([0, off[f + 1] - off[f]], np.int32), k, moffat[f:f + 1], a00[s], **kw)
+        assert np.array_equal(one['narrow_psf'][0], out['narrow_psf'][f])
+        assert np.array_equal(one['a'], out['a'][s])
+        assert np.array_equal(one['loss_hist'][0], out['loss_hist'][f])
