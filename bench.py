@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of the PSF + photometry fits on synthetic stamp stacks (BASELINE.json cfg2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One step = one pass of the hot path over the cfg2 batch: 1,000 frames x 10 stars x 32x32 stamps,
+subsampling 2: per-frame PSF fit (analytic Moffat stage <=100 its, noise weights, 3000 AdaBelief
+iterations on the 64x64 pixel grid) followed by the fixed-PSF photometry of the same 10 stars
+(2000 AdaBelief iterations) with the PSFs just fitted.  N > 1 (torchrun): every rank owns its own
+1,000 frames (weak scaling, no data-path collective); value = all frames / max-over-ranks time.
+
+JSON keys: see the task contract.  `value` is timed with inputs resident in HBM (device pointers
+through the C ABI); `e2e` is the same step through the public Python API with pinned HOST buffers
+(host preparation, H2D, kernels, D2H inside the timed region).  `roofline` refers to k_psf_fit (the
+dominant kernel), timed live with CUDA events on its launch stream (lcb_profile_*); the bound is the
+FP32 SIMT FMA pipe, peak measured live by lcb_fp32_peak.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+CFG = dict(F=1000, N=10, n=32, k=2, T1=100, T2=3000, Tphot=2000, G=12)
+METRIC = "frames/sec PSF+photometry fit (cfg2: 1000 frames x 10 stars x 32x32, ss2, Moffat+grid)"
+
+
+# ------------------------------------------------------------------ algorithmic work
+def algorithmic_flops():
+    F, N, n, k, G = CFG['F'], CFG['N'], CFG['n'], CFG['k'], CFG['G']
+    nu = n * k
+    J = int(np.log2(nu))
+    per_it = 14 * G * nu * nu * N + N * (2 * nu * nu + 12 * n * n) + 2 * J * 21 * nu * nu + 16 * (nu * nu + 3 * N)
+    psf = per_it * CFG['T2']
+    phot_it = 10 * G * nu * nu + 3 * nu * nu + 18 * n * n
+    phot = phot_it * CFG['Tphot'] * N
+    return dict(psf_per_frame=psf, phot_per_frame=phot, psf_per_it=per_it, phot_per_it_item=phot_it)
+
+
+def algorithmic_bytes_per_frame():
+    N, n, k = CFG['N'], CFG['n'], CFG['k']
+    nu = n * k
+    return 2 * N * n * n * 4 + (2 * nu * nu + N * n * n + 3 * N + 5 + CFG['T2']) * 4
+
+
+# ------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw"
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            p = [x.strip() for x in r.split(',')]
+            if len(p) < 6:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ CPU baseline (oracle port)
+def cpu_baseline_run(sample_frames=4, t1=10, t2=20, tphot=20):
+    """Times the oracle (restated STARRED model, PyTorch CPU float32, all host threads) on a bounded
+    sample of cfg2 and scales linearly in the iteration counts to (T1, T2, Tphot)."""
+    import torch
+    from oracle import starred_model as sm
+    from lightcurver_b200 import synthetic
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n, k, N = CFG['n'], CFG['k'], CFG['N']
+    d = synthetic.make_psf_frames(sample_frames, N, n, k, seed=synthetic.SEEDS['cfg2'])
+    sc = d['data'].reshape(sample_frames, -1).max(1)[:, None, None, None] / 100.0
+    data = d['data'] / sc
+    nm = d['noisemap'] / sc
+    weight = d['masks'] / nm ** 2
+    a0 = (data * d['masks']).sum((-1, -2)) * k * k
+    nu = n * k
+    sm.fit_psf_stage1(data[0], weight[0], n, k, float(d['fwhm'][0]), a0[0], 1)   # untimed: first-call overheads
+    t0 = time.perf_counter()
+    st1 = [sm.fit_psf_stage1(data[f], weight[f], n, k, float(d['fwhm'][f]), a0[f], t1) for f in range(sample_frames)]
+    t_stage1 = time.perf_counter() - t0
+    s_fixed = np.stack([sm.moffat_image(r['fwhm_x'], r['fwhm_y'], r['phi'], r['beta'], n, k).numpy() for r in st1])
+    a1 = np.stack([r['a'] for r in st1]); x1 = np.stack([r['x0'] for r in st1]); y1 = np.stack([r['y0'] for r in st1])
+    t0 = time.perf_counter()
+    W = np.stack([sm.psf_noise_weights(weight[f], a1[f], x1[f], y1[f], n, k).numpy() for f in range(sample_frames)])
+    t_w = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    r2 = sm.fit_psf_stage2(s_fixed, np.zeros((sample_frames, nu, nu)), a1, x1, y1, data, weight, W, n, k, t2,
+                           lr=1e-5, dtype=torch.float32)
+    t_stage2 = time.perf_counter() - t0
+    s = s_fixed + r2['b']
+    psf = (s / s.sum((-1, -2), keepdims=True)).astype(np.float32)
+    t0 = time.perf_counter()
+    sm.fit_phot(np.repeat(psf, N, 0), data.reshape(-1, n, n), (1.0 / nm ** 2).reshape(-1, n, n),
+                a1.reshape(-1), n, k, tphot, dtype=torch.float32)
+    t_phot = time.perf_counter() - t0
+    n_lbfgs = max(1, int(np.mean([len(r['loss_hist']) for r in st1])))
+    per_frame = (t_stage1 * CFG['T1'] / n_lbfgs + t_w + t_stage2 * CFG['T2'] / t2 + t_phot * CFG['Tphot'] / tphot) / sample_frames
+    return dict(value=1.0 / per_frame, unit="frames/s", cores=cores, kind="port",
+                sample=f"{sample_frames} frames x {N} stars of cfg2; oracle (restated STARRED model, PyTorch CPU f32 + autograd, "
+                       f"scipy L-BFGS-B f64): stage1 {n_lbfgs} its {t_stage1:.2f}s, W {t_w:.2f}s, stage2 {t2} its {t_stage2:.2f}s, "
+                       f"phot {tphot} its {t_phot:.2f}s; scaled linearly to {CFG['T1']}/{CFG['T2']}/{CFG['Tphot']} iterations",
+                seconds=t_stage1 + t_w + t_stage2 + t_phot)
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    vals, secs = [], []
+    for i in range(args.warmup + args.steps):
+        r = cpu_baseline_run(sample_frames=2, t1=6, t2=10, tphot=10)
+        if i >= args.warmup:
+            vals.append(r['value']); secs.append(r['seconds'])
+    v = float(np.mean(vals))
+    r['value'] = v
+    line = {"metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "cfg2 PSF+photometry fit, bounded sample per step (see cpu_baseline.sample)", **CFG},
+            "cpu_baseline": r,
+            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--frames', type=int, default=CFG['F'], help=argparse.SUPPRESS)
+    ap.add_argument('--no-cpu-baseline', action='store_true', help=argparse.SUPPRESS)
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from lightcurver_b200 import _lib, engine, synthetic
+    from lightcurver_b200.procedures.psf_routines import build_psf_batch
+    from lightcurver_b200.processes.star_photometry import star_photometry_batch
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    dev = torch.device('cuda', local)
+    F, N, n, k = args.frames, CFG['N'], CFG['n'], CFG['k']
+    nu = n * k
+
+    # ---- synthetic workload (seed differs per rank: every rank owns its own frames)
+    d = synthetic.make_psf_frames(F, N, n, k, seed=synthetic.SEEDS['cfg2'] + rank)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h_data, h_nm, h_mask = pin(d['data']), pin(d['noisemap']), pin(d['masks'])
+    fwhm_guess = d['fwhm'] * np.random.default_rng(1).uniform(0.9, 1.1, F)
+
+    # device-resident, already-prepared inputs for the `value` arm
+    sc = torch.from_numpy(d['data']).reshape(F, -1).max(1).values[:, None, None, None] / 100.0
+    g_data = (torch.from_numpy(d['data']) / sc).reshape(F * N, n, n).to(dev)
+    g_nm = (torch.from_numpy(d['noisemap']) / sc).reshape(F * N, n, n).to(dev)
+    g_w = (torch.from_numpy(d['masks']).reshape(F * N, n, n).to(dev) / g_nm ** 2).contiguous()
+    g_wphot = (1.0 / g_nm ** 2).contiguous()
+    g_off = (torch.arange(F + 1, dtype=torch.int32) * N).to(dev)
+    g_a0 = ((g_data * (g_w > 0)).sum((-1, -2)) * (k * k)).contiguous()
+    g_mof = torch.tensor(np.stack([fwhm_guess, fwhm_guess, np.zeros(F), np.full(F, 2.5), np.ones(F)], -1), dtype=torch.float32).to(dev)
+    g_idx = torch.arange(F, dtype=torch.int32).repeat_interleave(N).to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def step_device():
+        out = engine.psf_fit_batch(g_data, g_w, g_off, k, g_mof, g_a0, n_iter_analytic=CFG['T1'],
+                                   n_iter_adabelief=CFG['T2'], lr=1e-5, lam_scales=1.0, lam_hf=1.0, noise_weights=True,
+                                   want=('narrow_psf', 'full_psf', 'residuals', 'chi2', 'loss_hist', 'status'))
+        ph = engine.phot_fit_batch(g_data, g_wphot, out['narrow_psf'], g_idx, out['a'], k, CFG['Tphot'], lr=1e-3,
+                                   schedule=True, want_residuals=False, want_loss_hist=True)
+        return out, ph
+
+    def step_e2e():
+        res = build_psf_batch(h_data.numpy(), h_nm.numpy(), k, masks=h_mask.numpy(), n_iter_analytic=CFG['T1'],
+                              n_iter_adabelief=CFG['T2'], guess_method_star_position='center',
+                              guess_fwhm_pixels=fwhm_guess, return_dicts=False)
+        ph = star_photometry_batch(h_data.numpy(), h_nm.numpy(), res['narrow_psf'], k, n_iter=CFG['Tphot'],
+                                   masks=h_mask.numpy(), want_loss_hist=False)
+        return res, ph
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- FP32 peak (roofline denominator), before the run heats the chip
+    fp32_peak, _ = _lib.fp32_peak(8192)
+
+    for _ in range(args.warmup):
+        step_device()
+        flush.fill_(1)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.profile_enable(True)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        ev[i][0].record()
+        out, ph = step_device()
+        ev[i][1].record()
+        flush.fill_(i)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    prof = _lib.profile_summary()
+    _lib.profile_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_steps = [a.elapsed_time(b) for a, b in ev]
+    ms_step = float(np.mean(ms_steps))
+    t = torch.tensor([ms_step], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step_max = float(t.item())
+    value = world * F / (ms_step_max * 1e-3)
+    chi2_med = float(out['chi2'].median())
+    phot_chi2_med = float(ph['chi2'].median())
+
+    # ---- e2e through the public API with pinned host buffers
+    e2e_steps = max(1, min(args.steps, 2))
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res, ph2 = step_e2e()
+    barrier()
+    t_e2e = (time.perf_counter() - t0) / e2e_steps
+    te = torch.tensor([t_e2e], device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * F / float(te.item())
+    h2d = 2 * F * N * n * n * 4 + (F + 1) * 4 + F * 20 + 3 * F * N * 4 + F * nu * nu * 4 \
+        + 2 * F * N * n * n * 4 + F * nu * nu * 4 + 4 * F * N * 4
+    d2h = (2 * F * nu * nu + F * N * n * n + F * (CFG['T1'] + CFG['T2']) + 3 * F * N + 8 * F) * 4 + F * nu * nu * 4 \
+        + 6 * F * N * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    fl = algorithmic_flops()
+    kfit = prof.get('k_psf_fit', {'ms': 0.0, 'launches': 0})
+    launches = sum(v['launches'] for v in prof.values())
+    fit_ms_per_launch = kfit['ms'] / max(kfit['launches'], 1)
+    achieved = fl['psf_per_frame'] * F / (fit_ms_per_launch * 1e-3) / 1e12 if fit_ms_per_launch > 0 else 0.0
+    hbm_peak = None
+    try:
+        hbm_peak = json.load(open(ROOT / 'MEASURED_PEAKS.json'))['hbm_gbs']
+    except Exception:
+        pass
+    traffic = None
+    try:
+        traffic = json.load(open(ROOT / 'profiles' / 'k_psf_fit_traffic.json'))['dram_bytes_per_launch']
+    except Exception:
+        pass
+    hbm_ach = algorithmic_bytes_per_frame() * F / (fit_ms_per_launch * 1e-3) / 1e9 if fit_ms_per_launch > 0 else 0.0
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step_max, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"cfg2: {F} frames x {N} stars x {n}x{n} per GPU, subsampling {k}: PSF fit (Moffat LM<= {CFG['T1']} its, "
+                               f"SLIT noise weights, {CFG['T2']} AdaBelief its on the {nu}x{nu} grid) + photometry of the same stars "
+                               f"({CFG['Tphot']} AdaBelief its)", **{kk: (F if kk == 'F' else v) for kk, v in CFG.items()},
+                   "l2": "256 MiB buffer written between timed steps (L2 flush)", "seed": synthetic.SEEDS['cfg2'],
+                   "quality": {"psf_chi2_median": chi2_med, "phot_chi2_median": phot_chi2_med}},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "build_psf_batch + star_photometry_batch, pinned host numpy in, numpy out", "steps": e2e_steps},
+        "gpu_launches": launches,
+        "kernels": prof,
+        "roofline": {"bound": "fp32", "kernel": "k_psf_fit", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                     "frac": achieved / fp32_peak if fp32_peak else None, "traffic": traffic,
+                     "peak_source": "lcb_fp32_peak measured live (FFMA chains on all SMs); MEASURED_PEAKS.json has no FP32 SIMT figure",
+                     "algorithmic_flop_per_launch": fl['psf_per_frame'] * F, "ms_per_launch": fit_ms_per_launch,
+                     "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": (hbm_ach / hbm_peak) if hbm_peak else None, "peak_source": "MEASURED_PEAKS.json (of measured)"}},
+        "wall_s_timed_region": t_wall,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline_run()
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -100,7 +100,6 @@ typedef struct {
     int n, k;                /* stamp side, subsampling factor (nu = n*k) */
     const float* data;       /* [sumN][n][n] stamps, already normalised by the caller */
     const float* weight;     /* [sumN][n][n] mask / sigma^2 */
-    const float* noisemap;   /* [sumN][n][n] sigma; only read when opts.noise_weights = 1 */
     const float* W;          /* [F][J][nu*nu] starlet-space weights supplied by the caller, or NULL */
 } lcb_psf_batch;
 
@@ -109,7 +108,7 @@ typedef struct {
     int   n_iter_adabelief;  /* stage 2 iterations */
     float lr;                /* stage 2 init_learning_rate (scheduled, clipped) */
     float lam_scales, lam_hf;/* regularization_strength_scales / _hf */
-    int   noise_weights;     /* 0: W from batch (NULL -> 1);  1: SLIT-style propagation of noisemap */
+    int   noise_weights;     /* 0: W from batch (NULL -> 1);  1: SLIT propagation of the weights through the stage-1 model */
     float fwhm_min, fwhm_max, beta_min, beta_max;   /* bounds of the analytic stage */
 } lcb_psf_opts;
 
@@ -139,6 +138,12 @@ int lcb_psf_fit_batch(const lcb_psf_batch* in, const lcb_psf_opts* opt, lcb_psf_
 /* FP32 FMA micro-benchmark: runs `iters` dependent-chain FFMA loops on every SM and returns the
  * achieved TFLOP/s in *tflops (used as the measured roofline denominator by bench.py). */
 int lcb_fp32_peak(int iters, float* tflops, float* ms);
+
+/* Per-kernel device timing: after lcb_profile_enable(1) every kernel launched by the library is
+ * bracketed by CUDA events on its launch stream; lcb_profile_summary() synchronises on them and
+ * writes a JSON object {"kernel": {"ms": total, "launches": count}, ...} into buf. */
+int lcb_profile_enable(int on);
+int lcb_profile_summary(char* buf, int buflen);
 
 #ifdef __cplusplus
 }

@@ -164,7 +164,7 @@ def fp32_peak(iters=4096):
 
 class PsfBatch(C.Structure):
     _fields_ = [('F', C.c_int), ('star_off', C.c_void_p), ('n', C.c_int), ('k', C.c_int),
-                ('data', C.c_void_p), ('weight', C.c_void_p), ('noisemap', C.c_void_p), ('W', C.c_void_p)]
+                ('data', C.c_void_p), ('weight', C.c_void_p), ('W', C.c_void_p)]
 
 
 class PsfOpts(C.Structure):
@@ -185,3 +185,18 @@ lib.lcb_starlet_scales.argtypes = [C.c_int]
 lib.lcb_starlet_scales.restype = C.c_int
 lib.lcb_psf_fit_batch.argtypes = [C.POINTER(PsfBatch), C.POINTER(PsfOpts), C.POINTER(PsfOut), C.c_int, C.c_void_p]
 lib.lcb_psf_fit_batch.restype = C.c_int
+
+
+lib.lcb_profile_enable.argtypes = [C.c_int]
+lib.lcb_profile_summary.argtypes = [C.c_char_p, C.c_int]
+
+
+def profile_enable(on=True):
+    check(lib.lcb_profile_enable(int(bool(on))), 'lcb_profile_enable')
+
+
+def profile_summary():
+    import json
+    buf = C.create_string_buffer(1 << 16)
+    check(lib.lcb_profile_summary(buf, len(buf)), 'lcb_profile_summary')
+    return json.loads(buf.value.decode())

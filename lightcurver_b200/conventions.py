@@ -28,7 +28,7 @@ class Conventions:
     # build_psf: stamps are divided by max(image)/psf_norm_scale before fitting
     psf_norm_scale: float = 100.0
     # build_psf stage 2 (AdaBelief on the pixel grid) initial learning rate
-    psf_stage2_lr: float = 1e-3
+    psf_stage2_lr: float = 1e-5
     # Moffat initial beta and bounds used by the analytic stage
     moffat_beta_init: float = 2.5
     moffat_beta_min: float = 1.1

@@ -55,6 +55,54 @@ void* LcbArena::take(size_t bytes) {
     return base + a;
 }
 
+// ---------------------------------------------------------------- profiling
+#include <vector>
+#include <string>
+#include <map>
+struct ProfRec { const char* name; cudaEvent_t e0, e1; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+
+LcbProfScope::LcbProfScope(const char* name, cudaStream_t s) : idx(-1), st(s) {
+    if (!g_prof_on) return;
+    ProfRec r; r.name = name;
+    if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+    cudaEventRecord(r.e0, st);
+    g_prof.push_back(r);
+    idx = (int)g_prof.size() - 1;
+}
+LcbProfScope::~LcbProfScope() { if (idx >= 0) cudaEventRecord(g_prof[idx].e1, st); }
+
+extern "C" int lcb_profile_enable(int on) {
+    for (ProfRec& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    g_prof.clear();
+    g_prof_on = (on != 0);
+    return LCB_OK;
+}
+
+extern "C" int lcb_profile_summary(char* buf, int buflen) {
+    LCB_REQUIRE(buf && buflen > 2, "lcb_profile_summary: bad buffer");
+    std::map<std::string, std::pair<double, int>> agg;
+    for (ProfRec& r : g_prof) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(r.e1) == cudaSuccess && cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+            auto& a = agg[r.name]; a.first += ms; a.second += 1;
+        }
+    }
+    std::string out = "{";
+    bool first = true;
+    for (auto& kv : agg) {
+        char tmp[256];
+        snprintf(tmp, sizeof(tmp), "%s\"%s\": {\"ms\": %.6f, \"launches\": %d}", first ? "" : ", ", kv.first.c_str(),
+                 kv.second.first, kv.second.second);
+        out += tmp; first = false;
+    }
+    out += "}";
+    LCB_REQUIRE((int)out.size() + 1 <= buflen, "lcb_profile_summary: buffer too small (%zu needed)", out.size() + 1);
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return LCB_OK;
+}
+
 extern "C" {
 
 const char* lcb_last_error(void) { return g_err; }

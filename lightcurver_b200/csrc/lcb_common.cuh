@@ -36,6 +36,14 @@ struct LcbArena {
 };
 LcbArena& lcb_arena();
 
+// Optional per-kernel timing (lcb_profile_enable): CUDA events recorded on the launch stream around
+// every kernel launch of the library; lcb_profile_summary() synchronises and aggregates by name.
+struct LcbProfScope {
+    int idx; cudaStream_t st;
+    LcbProfScope(const char* name, cudaStream_t s);
+    ~LcbProfScope();
+};
+
 // ---------------------------------------------------------------- device side
 struct DevConv {              // conventions in the form kernels consume
     int G;                    // taps

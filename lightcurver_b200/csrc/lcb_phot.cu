@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(PHOT_THREADS) k_phot_fit(PhotArgs A) {
 template <int K, int G>
 static int launch_phot(const PhotArgs& A, size_t smem, cudaStream_t st) {
     LCB_CUDA(cudaFuncSetAttribute(k_phot_fit<K, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_phot_fit<K, G><<<A.B, PHOT_THREADS, smem, st>>>(A);
+    { LcbProfScope ps("k_phot_fit", st); k_phot_fit<K, G><<<A.B, PHOT_THREADS, smem, st>>>(A); }
     LCB_CUDA(cudaGetLastError());
     return LCB_OK;
 }

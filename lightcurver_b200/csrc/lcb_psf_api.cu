@@ -9,8 +9,9 @@ size_t lcb_psf_lm_smem_small(int n, int nu, int Nmax);
 int lcb_psf_fit_dispatch(const PsfArgs& A, size_t smem, cudaStream_t st);
 int lcb_psf_lm_dispatch(const PsfArgs& A, size_t smem, cudaStream_t st);
 int lcb_moffat_image_launch(const PsfArgs& A, cudaStream_t st);
-int lcb_noise_weights_launch(int F, int nu, int n, int k, int J, const int* star_off, const float* noisemap,
-                             const float* tab, float* W, float* work, size_t work_per_frame, cudaStream_t st);
+int lcb_noise_var_dispatch(const PsfArgs& A, cudaStream_t st);
+int lcb_noise_weights_launch(int F, int nu, int J, const float* tab, float* W, float* work,
+                             size_t work_per_frame, cudaStream_t st);
 
 extern "C" int lcb_starlet_scales(int nu) {
     int J = 0;
@@ -83,7 +84,6 @@ static int psf_run_device(const lcb_psf_batch* in, const lcb_psf_opts* opt, lcb_
     float* Wuse = nullptr;
     const bool do_reg = (opt->lam_scales != 0.f || opt->lam_hf != 0.f);
     if (opt->noise_weights && do_reg) {
-        LCB_REQUIRE(in->noisemap != nullptr, "noise_weights=1 needs batch.noisemap");
         if (out->W_out) Wuse = out->W_out;
         else { if ((rc = Wtmp.alloc((size_t)F * J * pp * 4))) return rc; Wuse = (float*)Wtmp.p; }
         std::vector<float> tab;
@@ -131,8 +131,9 @@ static int psf_run_device(const lcb_psf_batch* in, const lcb_psf_opts* opt, lcb_
             if ((rc = lcb_moffat_image_launch(A, st))) return rc;
         }
         if (opt->noise_weights && do_reg) {
-            if ((rc = lcb_noise_weights_launch(Fc, nu, n, k, J, A.star_off, in->noisemap, (const float*)tabd.p,
-                                               Wuse + (size_t)f0 * J * pp, (float*)work.p, wpf, st))) return rc;
+            if ((rc = lcb_noise_var_dispatch(A, st))) return rc;
+            if ((rc = lcb_noise_weights_launch(Fc, nu, J, (const float*)tabd.p, Wuse + (size_t)f0 * J * pp,
+                                               (float*)work.p, wpf, st))) return rc;
         }
         A.planes_in_smem = fit_planes_sm;
         if ((rc = lcb_psf_fit_dispatch(A, fit_small + (fit_planes_sm ? (size_t)7 * pp * 4 : 0), st))) return rc;
@@ -178,7 +179,7 @@ extern "C" int lcb_psf_fit_batch(const lcb_psf_batch* in, const lcb_psf_opts* op
 
     // ---- host pointers: stage everything through the arena
     const int T1 = opt->n_iter_analytic, T2 = opt->n_iter_adabelief;
-    size_t need = (size_t)(F + 1) * 4 + 3 * sumN * nn * 4 + (in->W || out->W_out ? (size_t)F * J * pp * 4 : 0) +
+    size_t need = (size_t)(F + 1) * 4 + 2 * sumN * nn * 4 + (in->W || out->W_out ? (size_t)F * J * pp * 4 : 0) +
                   (size_t)F * 5 * 4 + 3 * (size_t)sumN * 4 + 4 * F * pp * 4 + sumN * nn * 4 + (size_t)F * 4 * 3 +
                   (size_t)F * (T1 + T2) * 4 + (size_t)sumN * 12 + 64 * 256;
     LcbArena& ar = lcb_arena();
@@ -211,7 +212,6 @@ extern "C" int lcb_psf_fit_batch(const lcb_psf_batch* in, const lcb_psf_opts* op
     };
 #define UP(f, bytes) if ((rc = up(in->f, bytes, (const void**)&din.f))) return rc;
     UP(star_off, (size_t)(F + 1) * 4) UP(data, sumN * nn * 4) UP(weight, sumN * nn * 4)
-    if (opt->noise_weights) { UP(noisemap, sumN * nn * 4) }
     UP(W, (size_t)F * J * pp * 4)
 #undef UP
 #define IO(f, bytes, upl) if ((rc = io(out->f, bytes, (void**)&dout.f, upl))) return rc;

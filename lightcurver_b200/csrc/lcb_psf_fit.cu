@@ -338,7 +338,7 @@ size_t lcb_psf_fit_smem_small(int n, int nu, int Nmax) {
 template <int K, int G>
 static int launch_psf_fit(const PsfArgs& A, size_t smem, cudaStream_t st) {
     LCB_CUDA(cudaFuncSetAttribute(k_psf_fit<K, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_psf_fit<K, G><<<A.F, PSF_THREADS, smem, st>>>(A);
+    { LcbProfScope ps("k_psf_fit", st); k_psf_fit<K, G><<<A.F, PSF_THREADS, smem, st>>>(A); }
     LCB_CUDA(cudaGetLastError());
     return LCB_OK;
 }

@@ -352,7 +352,7 @@ size_t lcb_psf_lm_smem_small(int n, int nu, int Nmax) {
 template <int K, int G>
 static int launch_lm(const PsfArgs& A, size_t smem, cudaStream_t st) {
     LCB_CUDA(cudaFuncSetAttribute(k_psf_moffat_lm<K, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_psf_moffat_lm<K, G><<<A.F, PSF_THREADS, smem, st>>>(A);
+    { LcbProfScope ps("k_psf_moffat_lm", st); k_psf_moffat_lm<K, G><<<A.F, PSF_THREADS, smem, st>>>(A); }
     LCB_CUDA(cudaGetLastError());
     return LCB_OK;
 }
@@ -369,29 +369,82 @@ int lcb_psf_lm_dispatch(const PsfArgs& A, size_t smem, cudaStream_t st) {
 }
 
 int lcb_moffat_image_launch(const PsfArgs& A, cudaStream_t st) {
-    k_moffat_image<<<A.F, PSF_THREADS, 0, st>>>(A);
+    { LcbProfScope ps("k_moffat_image", st); k_moffat_image<<<A.F, PSF_THREADS, 0, st>>>(A); }
     LCB_CUDA(cudaGetLastError());
     return LCB_OK;
 }
 
 // ---------------------------------------------------------------- K5 noise weights
+// Restates propagate_noise(model, noisemap, kwargs, ['starlet'], method='SLIT', likelihood_type='chi2')
+// for the PSF grid: var_grad(p) = sum_i a_i^2 sum_q A_i[q,p]^2 w_i[q]  (diagonal of J^T C^-1 J, i.e. the
+// transposed passes with SQUARED taps applied to the weights), then W_j = sqrt(var_grad (*) psi_j^2).
+template <int K, int G>
+__global__ void __launch_bounds__(PSF_THREADS) k_noise_var(PsfArgs A) {
+    using P = LcbPass<K, G>;
+    extern __shared__ __align__(16) float sm[];
+    const int n = A.n, nu = A.nu, nn = n * n, pp = nu * nu, tid = threadIdx.x;
+    const int ldt = n + 1, ldb = nu + 1;
+    const int f = blockIdx.x;
+    const int i0 = A.star_off[f], N = A.star_off[f + 1] - i0;
+    const float fk = (float)K;
+    float* taps2 = sm;                               // [Nmax][2][GE_MAX]  ey^2, ex^2
+    float* wT = taps2 + A.Nmax * 2 * LCB_GE_MAX;     // [n][ldt]
+    float* Vbar = wT + n * ldt;                      // [n][ldb]
+    float* var = A.work + (size_t)f * A.work_per_frame;
+    for (int idx = tid; idx < N * 2 * P::GE; idx += PSF_THREADS) {
+        const int st = idx / (2 * P::GE), rem = idx % (2 * P::GE), which = rem / P::GE, p = rem % P::GE;
+        const float c = fk * (which ? A.x0[i0 + st] : A.y0[i0 + st]);
+        const float ic = floorf(c + 0.5f);
+        float e, de;
+        lcb_tap(A.cv, K, c - ic, p, e, de);
+        taps2[(st * 2 + which) * LCB_GE_MAX + p] = e * e;
+    }
+    for (int i = tid; i < pp; i += PSF_THREADS) var[i] = 0.f;
+    __syncthreads();
+    for (int st = 0; st < N; ++st) {
+        const float a = A.a[i0 + st];
+        const float cx = fk * A.x0[i0 + st], cy = fk * A.y0[i0 + st];
+        const int icx = (int)floorf(cx + 0.5f), icy = (int)floorf(cy + 0.5f);
+        const float* ws = A.weight + (size_t)(i0 + st) * nn;
+        for (int i = tid; i < nn; i += PSF_THREADS) wT[(i % n) * ldt + i / n] = ws[i];
+        __syncthreads();
+        lcb_pass2T<K, G>(wT, ldt, nu, n, icx, taps2 + (st * 2 + 1) * LCB_GE_MAX, Vbar, ldb, tid, PSF_THREADS);
+        __syncthreads();
+        lcb_pass1T<K, G>(Vbar, ldb, nu, n, icy, taps2 + (st * 2) * LCB_GE_MAX, tid, PSF_THREADS,
+                         [&](int v, int u, float val) { var[v * nu + u] = fmaf(a * a, val, var[v * nu + u]); });
+        __syncthreads();
+    }
+}
+
+template <int K, int G>
+static int launch_nvar(const PsfArgs& A, cudaStream_t st) {
+    const size_t smem = (size_t)(A.Nmax * 2 * LCB_GE_MAX + A.n * (A.n + 1) + A.n * (A.nu + 1)) * 4;
+    LCB_CUDA(cudaFuncSetAttribute(k_noise_var<K, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { LcbProfScope ps("k_noise_var", st); k_noise_var<K, G><<<A.F, PSF_THREADS, smem, st>>>(A); }
+    LCB_CUDA(cudaGetLastError());
+    return LCB_OK;
+}
+
+int lcb_noise_var_dispatch(const PsfArgs& A, cudaStream_t st) {
+    const int G = A.cv.G;
+#define CASE(KK, GG) if (A.k == KK && G == GG) return launch_nvar<KK, GG>(A, st);
+    CASE(1, 12) CASE(2, 12) CASE(3, 12) CASE(4, 12)
+    CASE(1, 8) CASE(2, 8) CASE(3, 8)
+    CASE(1, 16) CASE(2, 16) CASE(3, 16)
+#undef CASE
+    lcb_set_error("noise weights: unsupported (subsampling_factor=%d, gauss_taps=%d)", A.k, G);
+    return LCB_ERR_ARG;
+}
+
 // tab: [J][3][nu] 1-D kernels f_j^2, f_j f_{j+1}, f_{j+1}^2 (host-computed, clamped cascade of a
-// Dirac at nu/2).  W[f][j] = sqrt(max(0, sep(f_j^2) - 2 sep(f_j f_j+1) + sep(f_j+1^2))) of var_up.
-__global__ void __launch_bounds__(PSF_THREADS) k_noise_weights(int nu, int n, int k, int J, const int* star_off,
-                                                               const float* noisemap, const float* tab,
+// Dirac at nu/2).  W[f][j] = sqrt(max(0, sep(f_j^2) - 2 sep(f_j f_j+1) + sep(f_j+1^2))) of the
+// variance plane at work[f] (written by k_noise_var or by the caller).
+__global__ void __launch_bounds__(PSF_THREADS) k_noise_weights(int nu, int J, const float* tab,
                                                                float* W, float* work, size_t work_per_frame) {
-    const int f = blockIdx.x, tid = threadIdx.x, pp = nu * nu, nn = n * n;
-    const int i0 = star_off[f], N = star_off[f + 1] - i0;
+    const int f = blockIdx.x, tid = threadIdx.x, pp = nu * nu;
     float* var = work + (size_t)f * work_per_frame;   // [pp]
     float* tmp = var + pp;                            // [pp]
     const int a0 = nu / 2;
-    for (int i = tid; i < pp; i += PSF_THREADS) {
-        const int Y = (i / nu) / k, X = (i % nu) / k;
-        float s = 0.f;
-        for (int st = 0; st < N; ++st) { const float v = noisemap[(size_t)(i0 + st) * nn + Y * n + X]; s = fmaf(v, v, s); }
-        var[i] = s / (float)max(N, 1);
-    }
-    __syncthreads();
     float* Wf = W + (size_t)f * J * pp;
     for (int j = 0; j < J; ++j) {
         for (int term = 0; term < 3; ++term) {
@@ -423,9 +476,9 @@ __global__ void __launch_bounds__(PSF_THREADS) k_noise_weights(int nu, int n, in
     }
 }
 
-int lcb_noise_weights_launch(int F, int nu, int n, int k, int J, const int* star_off, const float* noisemap,
-                             const float* tab, float* W, float* work, size_t work_per_frame, cudaStream_t st) {
-    k_noise_weights<<<F, PSF_THREADS, 0, st>>>(nu, n, k, J, star_off, noisemap, tab, W, work, work_per_frame);
+int lcb_noise_weights_launch(int F, int nu, int J, const float* tab, float* W, float* work,
+                             size_t work_per_frame, cudaStream_t st) {
+    { LcbProfScope ps("k_noise_weights", st); k_noise_weights<<<F, PSF_THREADS, 0, st>>>(nu, J, tab, W, work, work_per_frame); }
     LCB_CUDA(cudaGetLastError());
     return LCB_OK;
 }

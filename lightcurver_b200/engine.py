@@ -63,7 +63,7 @@ def _clone_f32(x, ref):
 
 
 def psf_fit_batch(data, weight, star_off, k, moffat0, a0, x00=None, y00=None, background0=None,
-                  noisemap=None, W=None, n_iter_analytic=100, n_iter_adabelief=3000, lr=1e-3,
+                  W=None, n_iter_analytic=100, n_iter_adabelief=3000, lr=1e-3,
                   lam_scales=1.0, lam_hf=1.0, noise_weights=False, bounds=None,
                   want=('narrow_psf', 'full_psf', 'residuals', 'chi2', 'loss_hist', 'status')):
     """K1: ragged batch of per-frame PSF fits (lcb_psf_fit_batch).
@@ -74,9 +74,9 @@ def psf_fit_batch(data, weight, star_off, k, moffat0, a0, x00=None, y00=None, ba
     """
     _lib.require_device()
     data, weight = as_f32(data), as_f32(weight)
-    noisemap, W = as_f32(noisemap), as_f32(W)
+    W = as_f32(W)
     star_off = as_i32(star_off)
-    mem = mem_kind(data, weight, star_off, noisemap, W)
+    mem = mem_kind(data, weight, star_off, W)
     sumN, n = int(data.shape[0]), int(data.shape[-1])
     F = int(star_off.shape[0]) - 1
     nu = n * k
@@ -98,7 +98,7 @@ def psf_fit_batch(data, weight, star_off, k, moffat0, a0, x00=None, y00=None, ba
     opts = _lib.PsfOpts(int(n_iter_analytic), int(n_iter_adabelief), float(lr), float(lam_scales), float(lam_hf),
                         int(bool(noise_weights)), float(b.get('fwhm_min', 1.0)), float(b.get('fwhm_max', n / 2.0)),
                         float(b.get('beta_min', 1.1)), float(b.get('beta_max', 12.0)))
-    bi = _lib.PsfBatch(F, ptr(star_off), n, k, ptr(data), ptr(weight), ptr(noisemap), ptr(W))
+    bi = _lib.PsfBatch(F, ptr(star_off), n, k, ptr(data), ptr(weight), ptr(W))
     bo = _lib.PsfOut(*[ptr(out.get(nm)) for nm in _lib.PSF_OUT_FIELDS])
     rc = _lib.lib.lcb_psf_fit_batch(C.byref(bi), C.byref(opts), C.byref(bo), mem, current_stream(data))
     _lib.check(rc, 'lcb_psf_fit_batch')

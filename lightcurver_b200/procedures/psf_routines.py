@@ -1,0 +1,126 @@
+"""``build_psf``: the call lightcurver makes at lightcurver/processes/psf_modelling.py:164-171
+(``starred.procedures.psf_routines.build_psf``), served by the sm_100a kernels of liblcb.
+
+``build_psf`` keeps the reference's signature, argument meaning and result keys (those consumed at
+psf_modelling.py:177-210 and pinned by tests/test_starred_calls/test_starred_calls.py:66-80) for ONE
+frame; ``build_psf_batch`` is the batched form used by the patched ``model_all_psfs`` driver: gather
+every pending frame, ONE library call, scatter the per-frame dicts.
+"""
+import numpy as np
+
+from .. import engine
+from ..conventions import Conventions, DEFAULT
+
+
+def _guess_positions(img, mask, method):
+    """x0, y0 (data px, origin at the stamp centre) per star.  'center' is what lightcurver uses."""
+    N, n, _ = img.shape
+    if method == 'center':
+        return np.zeros(N), np.zeros(N)
+    ctr = (n - 1) / 2.0
+    if method == 'max':
+        flat = np.where(mask > 0, img, -np.inf).reshape(N, -1).argmax(-1)
+        return (flat % n) - ctr, (flat // n) - ctr
+    if method == 'barycenter':
+        w = np.clip(np.where(mask > 0, img, 0.0), 0.0, None)
+        tot = np.maximum(w.sum((-1, -2)), 1e-30)
+        ax = np.arange(n) - ctr
+        return (w.sum(-2) * ax).sum(-1) / tot, (w.sum(-1) * ax).sum(-1) / tot
+    raise ValueError(f"guess_method_star_position must be 'center', 'max' or 'barycenter' (got {method!r})")
+
+
+def build_psf_batch(images, noisemaps, subsampling_factor, masks=None, n_iter_analytic=40,
+                    n_iter_adabelief=2000, guess_method_star_position='barycenter', guess_fwhm_pixels=3.,
+                    field_distortion=False, stamp_coordinates=None, regularization_strength_scales=None,
+                    regularization_strength_hf=None, adabelief_learning_rate=None,
+                    conventions: Conventions = DEFAULT, return_dicts=True):
+    """Fits F frames in one library call.
+
+    images / noisemaps / masks: sequences (length F) of arrays (N_f, n, n) -- N_f may differ per
+    frame (psf_modelling.py:144-153 drops stars per frame).  guess_fwhm_pixels: scalar or (F,).
+    Returns a list of per-frame result dicts shaped like STARRED's (``return_dicts``), or the raw
+    batched arrays.
+    """
+    if field_distortion:
+        raise NotImplementedError("field_distortion=True is a 'next' row (SURVEY.md section 8f rank 3); "
+                                  "run with field_distortion: false")
+    cv = conventions
+    F = len(images)
+    k = int(subsampling_factor)
+    counts = [int(np.shape(im)[0]) for im in images]
+    if F == 0:
+        return []
+    if min(counts) < 1:
+        raise ValueError("every frame needs at least one star (psf_modelling.py:154-160 skips empty frames)")
+    n = int(np.shape(images[0])[-1])
+    off = np.zeros(F + 1, np.int32)
+    off[1:] = np.cumsum(counts)
+    sumN = int(off[-1])
+    cat = lambda seq: (np.asarray(seq).reshape(sumN, n, n) if isinstance(seq, np.ndarray)
+                       else np.concatenate([np.asarray(x) for x in seq]))
+    img = cat(images).astype(np.float32)
+    nm = cat(noisemaps).astype(np.float32)
+    mk = np.ones((sumN, n, n), bool) if masks is None else (cat(masks) > 0)
+    counts_a = np.asarray(counts)
+    # global normalisation per frame (A.4): stamps / (max(image) / psf_norm_scale)
+    star_max = np.nanmax(np.where(np.isfinite(img), img, -np.inf).reshape(sumN, -1), axis=1)
+    norms = np.maximum.reduceat(star_max, off[:-1]).astype(np.float64) / cv.psf_norm_scale
+    norms[~np.isfinite(norms) | (norms <= 0)] = 1.0
+    inv = np.repeat(1.0 / norms, counts_a).astype(np.float32)[:, None, None]
+    data = img * inv
+    nm = nm * inv
+    good = mk & (nm > 0) & np.isfinite(nm) & np.isfinite(data)
+    weight = np.zeros_like(data)
+    np.divide(1.0, nm * nm, out=weight, where=good)
+    data[~np.isfinite(data)] = 0.0
+    flux = np.where(good, data, 0.0).sum((-1, -2), dtype=np.float64)
+    a0 = (np.maximum(flux, 1e-6) * (k * k if cv.downsample_mean else 1.0)).astype(np.float32)
+    x00, y00 = _guess_positions(data, good, guess_method_star_position)
+    fwhm = np.broadcast_to(np.asarray(3.0 if guess_fwhm_pixels is None else guess_fwhm_pixels, dtype=np.float64), (F,))
+    moffat0 = np.stack([fwhm, fwhm, np.zeros(F), np.full(F, cv.moffat_beta_init), np.ones(F)], -1)
+    lam_s = cv.psf_lambda_scales if regularization_strength_scales is None else regularization_strength_scales
+    lam_h = cv.psf_lambda_hf if regularization_strength_hf is None else regularization_strength_hf
+    out = engine.psf_fit_batch(
+        data, weight, off, k, moffat0, a0, x00, y00, n_iter_analytic=n_iter_analytic,
+        n_iter_adabelief=n_iter_adabelief, lr=cv.psf_stage2_lr if adabelief_learning_rate is None else adabelief_learning_rate,
+        lam_scales=lam_s, lam_hf=lam_h, noise_weights=True,
+        bounds=dict(fwhm_min=cv.moffat_fwhm_min, fwhm_max=n / 2.0, beta_min=cv.moffat_beta_min, beta_max=cv.moffat_beta_max),
+        want=('narrow_psf', 'full_psf', 'residuals', 'chi2', 'loss_hist', 'loss_hist_analytic', 'status'))
+    out['norms'] = norms
+    out['star_off'] = off
+    if not return_dicts:
+        return out
+    res = []
+    nu = n * k
+    for f in range(F):
+        sl = slice(off[f], off[f + 1])
+        mo = out['moffat'][f]
+        res.append({
+            'full_psf': out['full_psf'][f],
+            'narrow_psf': out['narrow_psf'][f],
+            'chi2': float(out['chi2'][f]),
+            'residuals': out['residuals'][sl] * norms[f],
+            'kwargs_psf': {
+                'kwargs_moffat': {'fwhm_x': np.array([mo[0]]), 'fwhm_y': np.array([mo[1]]), 'phi': np.array([mo[2]]),
+                                  'beta': np.array([mo[3]]), 'C': np.array([mo[4]])},
+                'kwargs_gaussian': {'a': out['a'][sl], 'x0': out['x0'][sl], 'y0': out['y0'][sl]},
+                'kwargs_background': {'background': out['background'][f].reshape(nu * nu)},
+                'kwargs_distortion': {},
+            },
+            'adabelief_extra_fields': {'loss_history': out['loss_hist'][f]},
+            'analytical_extra_fields': {'loss_history': out['loss_hist_analytic'][f]},
+            'norm': float(norms[f]),
+            'status': int(out['status'][f]),
+        })
+    return res
+
+
+def build_psf(image, noisemap, subsampling_factor, masks=None, n_iter_analytic=40, n_iter_adabelief=2000,
+              guess_method_star_position='barycenter', guess_fwhm_pixels=3., field_distortion=False,
+              stamp_coordinates=None, **kwargs):
+    """One frame; same call as psf_modelling.py:164-171.  image, noisemap, masks: (N, n, n)."""
+    return build_psf_batch([image], [noisemap], subsampling_factor, None if masks is None else [masks],
+                           n_iter_analytic=n_iter_analytic, n_iter_adabelief=n_iter_adabelief,
+                           guess_method_star_position=guess_method_star_position,
+                           guess_fwhm_pixels=guess_fwhm_pixels, field_distortion=field_distortion,
+                           stamp_coordinates=stamp_coordinates, **kwargs)[0]

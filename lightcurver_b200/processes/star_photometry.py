@@ -1,0 +1,155 @@
+"""``do_one_star_forward_modelling`` of lightcurver/processes/star_photometry.py:23-151, served by
+liblcb (K2 for the default pipeline configuration, the joint-deconvolution engine when a shared
+starlet background or per-epoch constants are requested).
+
+Same signature, same in-place rescaling of the caller's arrays (:47-49), same result keys (:139-150)
+and types (tests/test_starred_calls/test_starred_calls.py:20-64).  In the north-star formulation the
+epochs of one star are independent fits (c fixed at the stamp centre, per-epoch gradient clip; see
+DESIGN.md "reference-coupled mode"), which is what makes frames shard across GPUs with no collective.
+"""
+import math
+
+import numpy as np
+
+from .. import engine
+from ..conventions import Conventions, DEFAULT
+
+
+def _initial_flux_guess(data):
+    """star_photometry.py:55-64: sum of pixels minus n^2 * (mean over the 4 edges AND all epochs of the
+    edge medians) -- one scalar background for the whole stack."""
+    with np.errstate(all='ignore'):
+        background_values = np.nanmean([
+            np.nanmedian(data[:, :1, :], axis=(1, 2)),
+            np.nanmedian(data[:, :, :1], axis=(1, 2)),
+            np.nanmedian(data[:, -1:, :], axis=(1, 2)),
+            np.nanmedian(data[:, :, -1:], axis=(1, 2))
+        ])
+    background_values = np.nan_to_num(background_values, nan=0)
+    return np.nansum(data, axis=(1, 2)) - data[0].size * background_values
+
+
+def point_source_image(a, x, y, n, k, cv: Conventions = DEFAULT):
+    """a * G(.; k x, k y) on the nu x nu grid (what model.getDeconvolved shows for a point source)."""
+    nu = n * k
+    sig = cv.gauss_fwhm_up / (2.0 * math.sqrt(2.0 * math.log(2.0)))
+    u = np.arange(nu) - (nu - 1) / 2.0
+    gx = np.exp(-(u - k * x) ** 2 / (2 * sig * sig)) / (math.sqrt(2 * math.pi) * sig)
+    gy = np.exp(-(u - k * y) ** 2 / (2 * sig * sig)) / (math.sqrt(2 * math.pi) * sig)
+    return a * np.outer(gy, gx)
+
+
+def do_one_star_forward_modelling(data, noisemap, psf, subsampling_factor, n_iter=2000,
+                                  uniform_background_per_epoch=False, starlet_global_background=True,
+                                  conventions: Conventions = DEFAULT):
+    """See lightcurver/processes/star_photometry.py:23-151.  data, noisemap (E,n,n); psf (E,n*k,n*k)."""
+    cv = conventions
+    k = int(subsampling_factor)
+    E, n = data.shape[0], data.shape[-1]
+    # star_photometry.py:47-49 -- IN PLACE on the caller's arrays, like the reference
+    scale = float(np.nanmax(data))
+    data /= scale
+    noisemap /= scale
+    a_est = _initial_flux_guess(data)
+    if cv.downsample_mean:
+        a_est = a_est * (k * k)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        weight = np.where(np.isfinite(noisemap) & (noisemap > 0), 1.0 / noisemap.astype(np.float64) ** 2, 0.0)
+    d32 = np.nan_to_num(np.asarray(data, dtype=np.float32), nan=0.0)
+    psf = np.ascontiguousarray(psf, dtype=np.float32)
+    if starlet_global_background or uniform_background_per_epoch:
+        from .roi_modelling import joint_deconvolution
+        res = joint_deconvolution(
+            d32, weight.astype(np.float32), psf, k, xs=np.zeros(1), ys=np.zeros(1), initial_a=a_est,
+            n_iter=n_iter, lr=1e-3, schedule=True, free_h=bool(starlet_global_background),
+            free_mean=bool(uniform_background_per_epoch), free_c=True,
+            regularization_strength_scales=3.0, regularization_strength_hf=3.0,
+            regularization_strength_positivity=0.0, conventions=cv)
+        kw = res['kwargs_final']
+        a = np.asarray(kw['kwargs_analytic']['a'])
+        model = res['model']
+        sigma = res['flux_sigma']
+        loss_curve = res['loss_history']
+        deconv, bkg = res['deconvolved_epoch0']
+    else:
+        out = engine.phot_fit_batch(d32, weight.astype(np.float32), psf, np.arange(E, dtype=np.int32),
+                                    a_est.astype(np.float32), k, n_iter, lr=1e-3, schedule=True)
+        a = out['a'].astype(np.float64)
+        kw = {
+            'kwargs_analytic': {'c_x': np.zeros(1), 'c_y': np.zeros(1), 'dx': out['dx'].astype(np.float64),
+                                'dy': out['dy'].astype(np.float64), 'a': a, 'alpha': np.zeros(E)},
+            'kwargs_background': {'h': np.zeros((n * k) ** 2), 'mean': np.zeros(E)},
+            'kwargs_sersic': {},
+        }
+        model = d32 - out['residuals']
+        sigma = out['sigma_a'].astype(np.float64)
+        loss_curve = out['loss_hist'].astype(np.float64).sum(0)   # the joint loss is the sum over epochs
+        deconv = point_source_image(a[0], out['dx'][0], out['dy'][0], n, k, cv)
+        bkg = np.zeros((n * k, n * k))
+    residuals = data - model
+    sigma_2 = noisemap ** 2
+    with np.errstate(divide='ignore', invalid='ignore'):
+        chi2_per_frame = np.nansum(residuals ** 2 / sigma_2, axis=(1, 2)) / n ** 2   # :127 (image_size^2, not dof)
+    chi2 = np.nanmean(chi2_per_frame)
+    return {
+        'scale': scale,
+        'kwargs_final': kw,
+        'fluxes': scale * a,
+        'fluxes_uncertainties': scale * np.asarray(sigma),
+        'chi2': float(chi2),
+        'chi2_per_frame': np.array(chi2_per_frame),
+        'loss_curve': list(np.asarray(loss_curve)),
+        'residuals': scale * residuals,
+        'deconvolved_image': scale * np.asarray(deconv),
+        'starlet_background': scale * np.asarray(bkg),
+    }
+
+
+def star_photometry_batch(data, noisemap, psfs, subsampling_factor, n_iter=2000, masks=None,
+                          conventions: Conventions = DEFAULT, want_residuals=False, want_loss_hist=True):
+    """Batched driver replacing the serial loop of do_star_photometry (star_photometry.py:257-366):
+    every (frame, star) item of a footprint in ONE library call.
+
+    data, noisemap (F,S,n,n) [frame, star]; psfs (F,nu,nu) the narrow PSF of each frame; masks
+    optional (F,S,n,n) bool, True = good (handled like star_photometry.py:309-316: NaN -> data 0 /
+    noise 1e7, and the noise of an epoch with ANY masked pixel is multiplied by 1000).
+    Per star the stack is scaled by its nanmax over all frames (:47-49) and a single background
+    scalar enters the initial flux guess (:55-64).  Arrays are NOT modified in place.
+    Returns dict(fluxes, fluxes_uncertainties, chi2_per_frame (F,S), dx, dy, scale (S,), loss_curve (S,T)).
+    """
+    cv = conventions
+    k = int(subsampling_factor)
+    F, S, n, _ = data.shape
+    d = np.array(data, dtype=np.float32)
+    nm = np.array(noisemap, dtype=np.float32)
+    isnan = np.isnan(d) | np.isnan(nm)
+    d[isnan] = 0.0
+    nm[isnan] = 1e7
+    if masks is not None:
+        bad_epoch = (~np.asarray(masks, bool)).any((-1, -2))
+        nm[bad_epoch] *= 1000.0
+    scale = np.nanmax(d, axis=(0, 2, 3))                      # (S,)
+    d /= scale[None, :, None, None]
+    nm /= scale[None, :, None, None]
+    a_est = np.stack([_initial_flux_guess(d[:, s]) for s in range(S)], 1)   # (F,S)
+    if cv.downsample_mean:
+        a_est = a_est * (k * k)
+    weight = 1.0 / (nm.astype(np.float64) ** 2)
+    idx = np.repeat(np.arange(F, dtype=np.int32), S)
+    out = engine.phot_fit_batch(d.reshape(F * S, n, n), weight.astype(np.float32).reshape(F * S, n, n),
+                                np.ascontiguousarray(psfs, np.float32), idx, a_est.reshape(-1).astype(np.float32),
+                                k, n_iter, lr=1e-3, schedule=True, want_residuals=want_residuals,
+                                want_loss_hist=want_loss_hist)
+    res = {
+        'scale': scale,
+        'fluxes': out['a'].reshape(F, S) * scale[None],
+        'fluxes_uncertainties': out['sigma_a'].reshape(F, S) * scale[None],
+        'chi2_per_frame': out['chi2'].reshape(F, S),
+        'dx': out['dx'].reshape(F, S), 'dy': out['dy'].reshape(F, S),
+        'status': out['status'].reshape(F, S),
+    }
+    if want_loss_hist:
+        res['loss_curve'] = out['loss_hist'].reshape(F, S, -1).sum(0)
+    if want_residuals:
+        res['residuals'] = out['residuals'].reshape(F, S, n, n) * scale[None, :, None, None]
+    return res

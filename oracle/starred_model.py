@@ -145,26 +145,39 @@ def starlet_dirac_planes(nu, dtype=torch.float64):
     return al
 
 
-def propagate_noise_slit(noisemaps, k, dtype=torch.float64):
-    """W (J, nu, nu): SLIT-style analytic propagation of the noise into starlet space.
-
-    Restates ``propagate_noise(..., method='SLIT')`` (star_photometry.py:108, roi_modelling.py:299)
-    [R]: sigma_bar^2 = mean over stamps of noisemap^2, repeated k x k onto the upsampled grid,
-    W_j = sqrt( sigma_bar^2_up (*) psi_j^2 ) with psi_j the j-th starlet plane of a centred Dirac
-    ('same' convolution, zero padded, anchored at the Dirac position nu//2).
-    """
-    nm = torch.as_tensor(noisemaps, dtype=dtype)
-    var = (nm * nm).mean(0)
-    var_up = var.repeat_interleave(k, 0).repeat_interleave(k, 1)
-    nu = var_up.shape[-1]
+def starlet_noise_levels(var_grad):
+    """W (J, nu, nu) = sqrt( var_grad (*) psi_j^2 ): std of the starlet coefficients of a white-ish
+    field of per-pixel variance var_grad; psi_j = j-th starlet plane of a centred Dirac ('same'
+    convolution, zero padded, anchored at the Dirac position nu//2)."""
+    nu = var_grad.shape[-1]
+    dtype = var_grad.dtype
     psi2 = starlet_dirac_planes(nu, dtype) ** 2       # (J, nu, nu)
     L = 2 * nu
-    F = torch.fft.rfft2(var_up, s=(L, L))
+    F = torch.fft.rfft2(var_grad, s=(L, L))
     K = torch.fft.rfft2(psi2, s=(L, L))
     full = torch.fft.irfft2(F[None] * K, s=(L, L))
     a0 = nu // 2
     out = full[:, a0:a0 + nu, a0:a0 + nu]
     return torch.sqrt(torch.clamp(out, min=0.0))
+
+
+def psf_noise_weights(weight, a, x0, y0, n, k, cv: Conventions = DEFAULT, dtype=torch.float64):
+    """Restates ``propagate_noise(model, noisemap, kwargs, ['starlet'], method='SLIT',
+    likelihood_type='chi2')`` for the PSF grid (star_photometry.py:108, roi_modelling.py:299 show
+    the call shape; build_psf makes the same call with the stage-1 kwargs) [R].
+
+    For a chi2 likelihood the quantity thresholded by the weighted L1 term is the gradient of the
+    chi2 in starlet space, whose noise is J^T C^-1 n.  SLIT's diagonal propagation gives per grid
+    pixel  var_grad(p) = sum_i a_i^2 sum_q A_i[q,p]^2 w_i[q]  (A_i = shift+smooth+decimate operator of
+    star i, w = mask/sigma^2), and W_j = sqrt(var_grad (*) psi_j^2).  One frame: weight (N,n,n).
+    """
+    weight = _const(weight, dtype)
+    a, x0, y0 = _const(a, dtype), _const(x0, dtype), _const(y0, dtype)
+    Ay = shift_matrix(k * y0, n, k, cv)               # (N, n, nu)
+    Ax = shift_matrix(k * x0, n, k, cv)
+    var = ((Ay * Ay).transpose(-1, -2) @ weight @ (Ax * Ax))      # (N, nu, nu)
+    var = (a[:, None, None] ** 2 * var).sum(0)
+    return starlet_noise_levels(var)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -505,6 +518,8 @@ def fit_psf_stage1(data, weight, n, k, fwhm_guess, a0, n_iter, cv: Conventions =
     def unpack(x):
         return x[0], x[1], x[2], x[3], x[4:4 + N], x[4 + N:4 + 2 * N], x[4 + 2 * N:]
 
+    last = {}
+
     def fun(xv):
         x = torch.tensor(xv, dtype=dtype, requires_grad=True)
         fx, fy, ph, be, a, x0, y0 = unpack(x)
@@ -514,12 +529,13 @@ def fit_psf_stage1(data, weight, n, k, fwhm_guess, a0, n_iter, cv: Conventions =
         if cv.chi2_half:
             L = 0.5 * L
         L.backward()
-        return float(L), x.grad.numpy().copy()
+        last['L'] = float(L.detach())
+        return last['L'], x.grad.numpy().copy()
 
     hist = []
     res = minimize(fun, x_init, jac=True, method='L-BFGS-B', bounds=list(zip(lo, hi)),
                    options={'maxiter': n_iter, 'maxfun': 20 * n_iter, 'ftol': 1e-15, 'gtol': 1e-10},
-                   callback=lambda xk: hist.append(fun(xk)[0]))
+                   callback=lambda xk: hist.append(last['L']))
     fx, fy, ph, be, a, x0, y0 = unpack(res.x)
     return dict(fwhm_x=fx, fwhm_y=fy, phi=ph, beta=be, C=1.0, a=a, x0=x0, y0=y0,
                 loss=float(res.fun), loss_hist=np.array(hist))

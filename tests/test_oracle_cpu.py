@@ -1,0 +1,127 @@
+"""CPU tests of the oracle itself (no GPU): internal consistency of the restated STARRED model.
+
+The reference holds no golden vector for this path (parity unpinned, see oracle/__init__.py); what
+can be pinned on CPU is that the restatement is self-consistent: banded form == general
+deconvolution form, FFT == direct convolution, starlet reconstruction, optimiser semantics of
+optax.scale_by_belief on a known-answer case, and the committed golden vectors under tests/golden.
+"""
+import json
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from oracle import starred_model as sm
+from oracle.conventions import Conventions, DEFAULT
+
+GOLD = Path(__file__).parent / 'golden'
+
+
+def test_conventions_twins_identical():
+    from lightcurver_b200.conventions import Conventions as P
+    assert P().as_dict() == Conventions().as_dict()
+
+
+def test_banded_equals_general_deconvolution_model():
+    n, k, E = 16, 2, 3
+    nu = n * k
+    psf = sm.moffat_image(torch.tensor([3.0] * E), torch.tensor([3.3] * E), torch.tensor([0.3] * E), torch.tensor([2.5] * E), n, k)
+    a = torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64)
+    dx = torch.tensor([0.2, -0.7, 1.3], dtype=torch.float64)
+    dy = torch.tensor([-0.4, 0.1, 0.6], dtype=torch.float64)
+    z1, zE = torch.zeros(1, dtype=torch.float64), torch.zeros(E, dtype=torch.float64)
+    m1 = sm.phot_models(psf, a, dx, dy, n, k)
+    m2 = sm.deconv_model(torch.zeros(nu, nu, dtype=torch.float64), zE, a[:, None], z1, z1, dx, dy, zE, psf, n, k, with_h=False)
+    m3 = sm.deconv_model(torch.zeros(nu, nu, dtype=torch.float64), zE, a[:, None], z1, z1, dx, dy, zE, psf, n, k, with_h=False, direct=True)
+    assert (m1 - m2).abs().max() < 1e-14 and (m2 - m3).abs().max() < 1e-14
+    # mean-downsample convention: sum of the model = a / k^2 when nothing falls off the stamp
+    np.testing.assert_allclose(m1.sum((-1, -2)).numpy(), a.numpy() / k ** 2, rtol=2e-2)
+
+
+def test_fft_equals_direct_with_background_and_rotation():
+    n, k, E = 12, 2, 2
+    nu = n * k
+    torch.manual_seed(0)
+    h = torch.rand(nu, nu, dtype=torch.float64)
+    psf = sm.moffat_image(torch.tensor([3.0] * E), torch.tensor([2.7] * E), torch.tensor([0.1] * E), torch.tensor([3.0] * E), n, k)[:, 2:-2, 2:-2]
+    args = (h, torch.tensor([0.1, -0.2], dtype=torch.float64), torch.tensor([[1.0, 2.0], [1.5, 0.5]], dtype=torch.float64),
+            torch.tensor([-2.0, 2.5], dtype=torch.float64), torch.tensor([1.0, -1.5], dtype=torch.float64),
+            torch.tensor([0.3, -0.6], dtype=torch.float64), torch.tensor([-0.2, 0.9], dtype=torch.float64),
+            torch.tensor([0.0, 0.15], dtype=torch.float64), psf, n, k)
+    assert (sm.deconv_model(*args) - sm.deconv_model(*args, direct=True)).abs().max() < 1e-13
+
+
+def test_starlet_reconstruction_and_adjoint_identity():
+    torch.manual_seed(1)
+    b = torch.rand(24, 24, dtype=torch.float64, requires_grad=True)
+    al, c = sm.starlet(b)
+    assert al.shape[0] == 4
+    assert (al.sum(0) + c - b).abs().max() < 1e-14
+    # <Phi b, y> == <b, Phi^T y> with Phi^T from autograd
+    y = torch.rand_like(al)
+    (g,) = torch.autograd.grad((al * y).sum(), b)
+    b2 = torch.rand(24, 24, dtype=torch.float64)
+    al2, _ = sm.starlet(b2)
+    assert abs(float((al2 * y).sum()) - float((b2 * g).sum())) < 1e-10
+
+
+def test_adabelief_matches_optax_formulas_known_answer():
+    """Two steps of scale_by_belief (b1=.9, b2=.999, eps=eps_root=1e-16) worked by hand."""
+    p = torch.tensor([1.0], dtype=torch.float64)
+    opt = sm.AdaBelief([p], lr=0.1, n_iter=10, schedule=False)
+    g1 = torch.tensor([2.0], dtype=torch.float64)
+    opt.step([g1])
+    mu = 0.2; s = 0.001 * (2.0 - 0.2) ** 2 + 1e-16
+    exp1 = 1.0 - 0.1 * (mu / 0.1) / (np.sqrt(s / 0.001) + 1e-16)
+    assert abs(float(p) - exp1) < 1e-12
+    g2 = torch.tensor([-1.0], dtype=torch.float64)
+    opt.step([g2])
+    mu2 = 0.9 * mu + 0.1 * -1.0
+    s2 = 0.999 * s + 0.001 * (-1.0 - mu2) ** 2 + 1e-16
+    exp2 = exp1 - 0.1 * (mu2 / (1 - 0.81)) / (np.sqrt(s2 / (1 - 0.999 ** 2)) + 1e-16)
+    assert abs(float(p) - exp2) < 1e-12
+
+
+def test_clip_and_schedule():
+    p = torch.zeros(3, dtype=torch.float64)
+    opt = sm.AdaBelief([p], lr=1e-3, n_iter=100, schedule=True)
+    g = torch.tensor([3.0, 4.0, 0.0], dtype=torch.float64)       # norm 5 -> clipped to norm 1
+    opt.step([g])
+    # first step of AdaBelief is -lr * g/(0.9|g|): independent of the clip scale, schedule gives lr0 at t=0
+    np.testing.assert_allclose(p.numpy()[:2], [-1e-3 / 0.9, -1e-3 / 0.9], rtol=1e-9)
+
+
+def test_phot_fit_recovers_flux_cpu():
+    from lightcurver_b200 import synthetic
+    n, k = 16, 2
+    d = synthetic.make_phot_frames(2, 2, n, k, seed=5)
+    data = d['data'].reshape(-1, n, n)
+    sc = data.max()
+    w = sc ** 2 / d['noisemap'].reshape(-1, n, n).astype(np.float64) ** 2
+    a0 = data.sum((-1, -2)) * k * k / sc
+    r = sm.fit_phot(np.repeat(d['psf'], 2, 0), data / sc, w, a0, n, k, 300, dtype=torch.float64)
+    truth = (d['transparency'][:, None] * d['star_flux'][None]).reshape(-1)
+    flux = r['a'] * sc / k ** 2
+    assert np.all(np.abs(flux - truth) < 6 * r['sigma_a'] * sc / k ** 2)
+    assert r['loss_hist'][:, -1].sum() < r['loss_hist'][:, 0].sum()
+
+
+def test_golden_vectors():
+    """Committed golden vectors (tests/golden/*.npz, generated by tools/make_golden.py from the oracle
+    in float64) pin the oracle against silent edits."""
+    files = sorted(GOLD.glob('*.npz'))
+    assert files, "tests/golden is empty"
+    for f in files:
+        g = np.load(f)
+        kind = str(g['kind'])
+        n, k = int(g['n']), int(g['k'])
+        if kind == 'phot':
+            L, gr = sm.phot_loss_grad(g['psf'], g['data'], g['weight'], g['a'], g['dx'], g['dy'], n, k)
+            np.testing.assert_allclose(L, g['loss'], rtol=1e-12)
+            np.testing.assert_allclose(np.stack(gr, -1), g['grad'], rtol=1e-10, atol=1e-12)
+        elif kind == 'psf':
+            L, gr = sm.psf_loss_grad(g['s_fixed'], g['b'], g['a'], g['x0'], g['y0'], g['data'], g['weight'], g['W'], n, k,
+                                     float(g['lam_scales']), float(g['lam_hf']))
+            np.testing.assert_allclose(L, g['loss'], rtol=1e-12)
+            np.testing.assert_allclose(gr[0], g['grad_b'], rtol=1e-9, atol=1e-12)
+            np.testing.assert_allclose(np.stack(gr[1:], -1), g['grad_s'], rtol=1e-9, atol=1e-12)

@@ -28,11 +28,11 @@ def main():
     a0 = (data.sum((-1, -2)) * k * k)
     mof = torch.tensor([[3.0, 3.0, 0.0, 2.5, 1.0]]).repeat(F, 1).cuda()
     for (t1, t2, nw, lam) in [(0, T2, False, 1.0), (0, T2, False, 0.0), (100, 0, False, 1.0), (0, 1, True, 1.0), (100, T2, True, 1.0)]:
-        ms = ev_time(lambda: engine.psf_fit_batch(data, w, off, k, mof, a0, noisemap=nm, n_iter_analytic=t1,
+        ms = ev_time(lambda: engine.psf_fit_batch(data, w, off, k, mof, a0, n_iter_analytic=t1,
                                                    n_iter_adabelief=t2, noise_weights=nw, lam_scales=lam, lam_hf=lam,
                                                    want=('narrow_psf', 'chi2')))
         print(f"psf F={F} N={N} T1={t1} T2={t2} W={nw} lam={lam}: {ms:.2f} ms  -> {ms / max(t2, 1) / F * 148 * 1e3:.2f} us/iter/frame-slot", flush=True)
-    out = engine.psf_fit_batch(data, w, off, k, mof, a0, noisemap=nm, n_iter_analytic=100, n_iter_adabelief=T2, noise_weights=True,
+    out = engine.psf_fit_batch(data, w, off, k, mof, a0, n_iter_analytic=100, n_iter_adabelief=T2, noise_weights=True,
                                want=('narrow_psf', 'chi2', 'loss_hist_analytic'))
     print('chi2 median', float(out['chi2'].median()), 'fwhm', out['moffat'][:3].cpu().numpy())
     # photometry
