@@ -134,6 +134,59 @@ int lcb_starlet_scales(int nu);
 int lcb_psf_fit_batch(const lcb_psf_batch* in, const lcb_psf_opts* opt, lcb_psf_out* out,
                       int mem, void* stream);
 
+/* ---------------- K3: joint multi-epoch deconvolution (roi_modelling.py:213-335) ----------------- */
+typedef struct {
+    int E, n, k;            /* epochs (local to this rank), stamp side, subsampling factor */
+    int P;                  /* narrow PSF side (upsampled px), any parity */
+    int M;                  /* point sources (<= 8) */
+    const float* data;      /* [E][n][n]  (already scaled, roi_modelling.py:162-164) */
+    const float* weight;    /* [E][n][n]  1/sigma^2 */
+    const float* psf;       /* [E][P][P] */
+} lcb_deconv_problem;
+
+/* kwargs of the STARRED model (roi_modelling.py:221-263): a is epoch-major a[e*M+m] (:462) */
+typedef struct {
+    const float* h;         /* [nu*nu] shared background (NULL keeps the current one; initial 0) */
+    const float* mean;      /* [E] */
+    const float* a;         /* [E*M] */
+    const float* c_x; const float* c_y;   /* [M] */
+    const float* dx; const float* dy;     /* [E] */
+    const float* alpha;     /* [E] fixed rotation of each epoch (radians) */
+    int free_h, free_mean, free_a, free_c, free_d;   /* which groups the optimiser moves */
+} lcb_deconv_params;
+
+typedef struct {
+    float lam_scales, lam_hf, lam_pos;    /* regularization_strength_{scales,hf,positivity} */
+    const float* W;                       /* [J][nu*nu] or NULL (== 1) */
+    const float* prior_mu_x; const float* prior_sig_x;   /* [M] Gaussian prior on c_x (Prior(prior_analytic=...)), or NULL */
+    const float* prior_mu_y; const float* prior_sig_y;
+} lcb_deconv_reg;
+
+typedef struct {           /* gradient of the loss at the current parameters */
+    float* loss;            /* [1] */
+    float* h;               /* [nu*nu] */
+    float* mean; float* a; float* c_x; float* c_y; float* dx; float* dy;
+} lcb_deconv_grad;
+
+int lcb_deconv_create(const lcb_deconv_problem* p, int mem, void* stream, void** handle);
+int lcb_deconv_set_params(void* handle, const lcb_deconv_params* q, int mem);   /* also restarts the optimiser state */
+int lcb_deconv_set_reg(void* handle, const lcb_deconv_reg* r, int mem);
+/* single-rank driver: n_iter AdaBelief iterations; loss_hist [n_iter] may be NULL */
+int lcb_deconv_run(void* handle, const lcb_fit_opts* opt, float* loss_hist, int mem);
+/* multi-rank driver, one iteration = step_local ; all-reduce(sum) of reduce_buffer ; step_update.
+ * After the last iteration call step_local once more to apply the pending per-epoch update. */
+int lcb_deconv_step_local(void* handle, int want_model);
+int lcb_deconv_reduce_buffer(void* handle, float** device_ptr, int* count);
+int lcb_deconv_step_update(void* handle, int it, int n_iter, float lr, int schedule);
+int lcb_deconv_loss_grad(void* handle, lcb_deconv_grad* g, int mem);
+/* current parameters; model [E][n][n] and loss [1] are evaluated when non-NULL */
+int lcb_deconv_get(void* handle, lcb_deconv_params* q, float* model, float* loss, int mem);
+/* starlet-space noise weights of h: stage 0 fills the reduce buffer with the local variance plane
+ * (all-reduce it when epochs are sharded), stage 1 builds W [J][nu*nu], installs it for the
+ * regulariser and copies it to W_out when non-NULL */
+int lcb_deconv_noise_weights(void* handle, int stage, float* W_out, int mem);
+int lcb_deconv_destroy(void* handle);
+
 /* ---------------- measurement helper ---------------------------------------------------------- */
 /* FP32 FMA micro-benchmark: runs `iters` dependent-chain FFMA loops on every SM and returns the
  * achieved TFLOP/s in *tflops (used as the measured roofline denominator by bench.py). */

@@ -200,3 +200,35 @@ def profile_summary():
     buf = C.create_string_buffer(1 << 16)
     check(lib.lcb_profile_summary(buf, len(buf)), 'lcb_profile_summary')
     return json.loads(buf.value.decode())
+
+
+class DeconvProblem(C.Structure):
+    _fields_ = [('E', C.c_int), ('n', C.c_int), ('k', C.c_int), ('P', C.c_int), ('M', C.c_int),
+                ('data', C.c_void_p), ('weight', C.c_void_p), ('psf', C.c_void_p)]
+
+
+class DeconvParams(C.Structure):
+    _fields_ = [(nm, C.c_void_p) for nm in ('h', 'mean', 'a', 'c_x', 'c_y', 'dx', 'dy', 'alpha')] + \
+               [(nm, C.c_int) for nm in ('free_h', 'free_mean', 'free_a', 'free_c', 'free_d')]
+
+
+class DeconvReg(C.Structure):
+    _fields_ = [('lam_scales', C.c_float), ('lam_hf', C.c_float), ('lam_pos', C.c_float), ('W', C.c_void_p),
+                ('prior_mu_x', C.c_void_p), ('prior_sig_x', C.c_void_p), ('prior_mu_y', C.c_void_p), ('prior_sig_y', C.c_void_p)]
+
+
+class DeconvGrad(C.Structure):
+    _fields_ = [(nm, C.c_void_p) for nm in ('loss', 'h', 'mean', 'a', 'c_x', 'c_y', 'dx', 'dy')]
+
+
+lib.lcb_deconv_create.argtypes = [C.POINTER(DeconvProblem), C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+lib.lcb_deconv_set_params.argtypes = [C.c_void_p, C.POINTER(DeconvParams), C.c_int]
+lib.lcb_deconv_set_reg.argtypes = [C.c_void_p, C.POINTER(DeconvReg), C.c_int]
+lib.lcb_deconv_run.argtypes = [C.c_void_p, C.POINTER(FitOpts), C.c_void_p, C.c_int]
+lib.lcb_deconv_step_local.argtypes = [C.c_void_p, C.c_int]
+lib.lcb_deconv_reduce_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
+lib.lcb_deconv_step_update.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int]
+lib.lcb_deconv_loss_grad.argtypes = [C.c_void_p, C.POINTER(DeconvGrad), C.c_int]
+lib.lcb_deconv_get.argtypes = [C.c_void_p, C.POINTER(DeconvParams), C.c_void_p, C.c_void_p, C.c_int]
+lib.lcb_deconv_destroy.argtypes = [C.c_void_p]
+lib.lcb_deconv_noise_weights.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]

@@ -1,0 +1,847 @@
+// lcb_deconv.cu -- K3: joint multi-epoch deconvolution with a shared high-resolution background.
+//
+// Replaces the STARRED calls of lightcurver/processes/roi_modelling.py:213-335 (setup_model, Loss,
+// Optimizer('adabelief').minimize, model.model, model.getDeconvolved) and, with M = 1, the
+// reference-coupled form of star_photometry.py:66-137.  Model:
+//     f_e = Warp_{dx_e,dy_e,alpha_e}[h] + sum_m a_em G(. ; k (R_alpha c_m + d_e))        (nu x nu)
+//     m_e = D_k[ s_e (*) f_e ] + mean_e                                                  (n x n)
+// Loss (A.7): 1/2 sum w (m-d)^2 + starlet-L1(h; W) + positivity(h) + Gaussian prior on (c_x, c_y).
+//
+// One iteration =
+//   k_deconv_epoch   one CTA per epoch: apply the pending AdaBelief update of the per-epoch parameters,
+//                    build f_e in shared memory (polyphase layout), direct FP32 convolution with the
+//                    k-box-folded PSF fused with the decimation, weighted residual, adjoint convolution,
+//                    point-source / shift / mean gradients, transposed warp -> partial dL/dh of the epoch
+//   k_deconv_reduce  deterministic sum over the local epochs -> red[nu^2 + 2M + 2]
+//   (multi-GPU: ONE all-reduce of red over NVLink, issued by the caller between the two entries)
+//   k_deconv_update  starlet / positivity / prior gradients, global norm, AdaBelief on h, c_x, c_y.
+//
+// Decimation is folded into the PSF: m[Y][X] = mean + 1/k^2 sum_phase sum_{av,au} S_ph[av][au] f_ph[Y+av][X+au]
+// with f_ph[Y'][X'] = f[kY'+pv][kX'+pu] and S_ph the polyphase components of s (*) box_k; each phase is a
+// plain 2-D correlation of an n x n plane with an NA x NA kernel (NA ~ P/k + 1): 4x fewer MACs than
+// convolving at full resolution, and lanes <-> rows with an odd leading dimension is conflict free.
+#include "lcb_common.cuh"
+#include <vector>
+
+void lcb_build_noise_table(int nu, int J, std::vector<float>& tab);
+int lcb_noise_weights_launch(int F, int nu, int J, const float* tab, float* W, float* work,
+                             size_t work_per_frame, cudaStream_t st);
+
+#define DC_THREADS 256
+#define DC_XB 8
+#define DC_MMAX 8
+
+struct DeconvDev {
+    int E, n, k, nu, P, M, NA, A0, J, G;
+    int free_h, free_mean, free_a, free_c, free_d;
+    // inputs
+    float *data, *weight, *S;            // [E][n][n], [E][n][n], [E][k*k][NA][NA]
+    float *W;                            // [J][nu^2] or NULL
+    float lam_scales, lam_hf, lam_pos;
+    int has_prior; float *prior;         // [4][M] mu_x, sig_x, mu_y, sig_y
+    // parameters + AdaBelief state
+    float *h, *h_mu, *h_nu;              // [nu^2]
+    float *c, *c_mu, *c_nu;              // [2M] c_x then c_y
+    float *ep, *ep_mu, *ep_nu, *ep_g;    // [E][M+3]: a[M], dx, dy, mean  (value, moments, pending gradient)
+    float *alpha;                        // [E]
+    // per-iteration scratch
+    float *Gh;                           // [E][nu^2] per-epoch partial dL/dh
+    float *gc;                           // [E][2M]
+    float *eloss;                        // [E]
+    float *red;                          // [nu^2 + 2M + 2] reduced: dL/dh, dL/dc, loss, |g_epoch|^2
+    float *ctl;                          // [8] clip scale, lr, 1/bc1, 1/bc2, pending flag, loss
+    float *planes;                       // [3][nu^2] starlet scratch + Tj [J][nu^2]
+    float *model;                        // [E][n][n] (written when requested)
+    float *loss_hist;                    // [cap]
+    DevConv cv;
+};
+
+__device__ __forceinline__ int fdiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+// ---------------------------------------------------------------- setup: polyphase box-folded PSF
+// S[e][pv*k+pu][av-A0][au-A0] = stilde(tv = j0 - k av - pv, tu = j0 - k au - pu),
+// stilde(tv,tu) = sum_{kv,ku<k} s[tv+kv][tu+ku]   (zero outside the P x P array).
+__global__ void k_deconv_fold_psf(const float* psf, float* S, int E, int P, int k, int NA, int A0) {
+    const int e = blockIdx.x;
+    const int j0 = (P - 1) / 2;
+    const float* s = psf + (size_t)e * P * P;
+    float* out = S + (size_t)e * k * k * NA * NA;
+    for (int i = threadIdx.x; i < k * k * NA * NA; i += blockDim.x) {
+        const int ph = i / (NA * NA), r = i % (NA * NA), av = r / NA + A0, au = r % NA + A0;
+        const int pv = ph / k, pu = ph % k;
+        const int tv = j0 - k * av - pv, tu = j0 - k * au - pu;
+        float acc = 0.f;
+        for (int kv = 0; kv < k; ++kv)
+            for (int ku = 0; ku < k; ++ku) {
+                const int jv = tv + kv, ju = tu + ku;
+                if (jv >= 0 && jv < P && ju >= 0 && ju < P) acc += s[jv * P + ju];
+            }
+        out[i] = acc;
+    }
+}
+
+// ---------------------------------------------------------------- geometry helpers
+struct Geo { float ca, sa, tx, ty, ctr; };   // q = R^-1 (p - ctr - k d) + ctr
+
+__device__ __forceinline__ void geo_src(const Geo& g, float u, float v, float& qu, float& qv) {
+    const float pu = u - g.ctr - g.tx, pv = v - g.ctr - g.ty;
+    qu = g.ca * pu + g.sa * pv + g.ctr;
+    qv = -g.sa * pu + g.ca * pv + g.ctr;
+}
+
+__device__ __forceinline__ float h_at(const float* __restrict__ h, int nu, int v, int u) {
+    return (v >= 0 && v < nu && u >= 0 && u < nu) ? __ldg(h + v * nu + u) : 0.f;
+}
+
+// correlation of one phase plane with its NA x NA kernel for XB consecutive outputs of row Y:
+//   acc[x] += sum_{av,au} Sph[av-A0][au-A0] * src[Y+av][X0+x+au]      (zero outside [0,n))
+__device__ __forceinline__ void corr_row(const float* __restrict__ src, int ld, int n, const float* __restrict__ Sph,
+                                         int NA, int A0, int Y, int X0, float (&acc)[DC_XB]) {
+    for (int ia = 0; ia < NA; ++ia) {
+        const int row = Y + A0 + ia;
+        if (row < 0 || row >= n) continue;
+        const float* fr = src + row * ld;
+        const float* sr = Sph + ia * NA;
+        float buf[2 * DC_XB];
+#pragma unroll
+        for (int i = 0; i < DC_XB; ++i) {
+            const int c = X0 + A0 + i;
+            buf[i] = (c >= 0 && c < n) ? fr[c] : 0.f;
+        }
+        for (int t0 = 0; t0 < NA; t0 += DC_XB) {
+#pragma unroll
+            for (int i = 0; i < DC_XB; ++i) {
+                const int c = X0 + A0 + t0 + DC_XB + i;
+                buf[DC_XB + i] = (c >= 0 && c < n) ? fr[c] : 0.f;
+            }
+#pragma unroll
+            for (int t = 0; t < DC_XB; ++t) {
+                const float sv = (t0 + t < NA) ? sr[t0 + t] : 0.f;
+#pragma unroll
+                for (int x = 0; x < DC_XB; ++x) acc[x] = fmaf(sv, buf[t + x], acc[x]);
+            }
+#pragma unroll
+            for (int i = 0; i < DC_XB; ++i) buf[i] = buf[DC_XB + i];
+        }
+    }
+}
+
+// transposed: acc[x] += sum_{av,au} Sph[av-A0][au-A0] * r[Y'-av][X0+x-au]
+__device__ __forceinline__ void conv_row_T(const float* __restrict__ src, int ld, int n, const float* __restrict__ Sph,
+                                           int NA, int A0, int Y, int X0, float (&acc)[DC_XB], bool squared) {
+    for (int ia = 0; ia < NA; ++ia) {
+        const int row = Y - A0 - ia;
+        if (row < 0 || row >= n) continue;
+        const float* fr = src + row * ld;
+        const float* sr = Sph + ia * NA;
+        // index c = X0 + x - A0 - t ; walk t upwards => c downwards.  window base b(t) = X0 - A0 - t
+        float buf[2 * DC_XB];              // buf[j] holds fr[base_hi - j] with base_hi = X0 - A0 + DC_XB - 1
+#pragma unroll
+        for (int i = 0; i < DC_XB; ++i) {
+            const int c = X0 - A0 + DC_XB - 1 - i;
+            buf[i] = (c >= 0 && c < n) ? fr[c] : 0.f;
+        }
+        for (int t0 = 0; t0 < NA; t0 += DC_XB) {
+#pragma unroll
+            for (int i = 0; i < DC_XB; ++i) {
+                const int c = X0 - A0 - 1 - t0 - i;
+                buf[DC_XB + i] = (c >= 0 && c < n) ? fr[c] : 0.f;
+            }
+#pragma unroll
+            for (int t = 0; t < DC_XB; ++t) {
+                float sv = (t0 + t < NA) ? sr[t0 + t] : 0.f;
+                if (squared) sv *= sv;
+                // output x needs fr[X0 + x - A0 - t0 - t] = buf[DC_XB - 1 - x + t]
+#pragma unroll
+                for (int x = 0; x < DC_XB; ++x) acc[x] = fmaf(sv, buf[DC_XB - 1 - x + t], acc[x]);
+            }
+#pragma unroll
+            for (int i = 0; i < DC_XB; ++i) buf[i] = buf[DC_XB + i];
+        }
+    }
+}
+
+__device__ __forceinline__ float block_sum(float v, float* red, int tid) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    float s = 0.f;
+    for (int w = 0; w < DC_THREADS / 32; ++w) s += red[w];
+    return s;
+}
+
+// ---------------------------------------------------------------- per-epoch kernel
+__global__ void __launch_bounds__(DC_THREADS) k_deconv_epoch(DeconvDev D, int flags) {
+    const int want_model = flags & 1;
+    const bool noise = (flags & 2) != 0;   // propagate the weights instead of the residuals (lcb_deconv_noise_weights)
+    extern __shared__ __align__(16) float sm[];
+    const int e = blockIdx.x, tid = threadIdx.x;
+    const int n = D.n, k = D.k, nu = D.nu, M = D.M, NA = D.NA, A0 = D.A0, G = D.G;
+    const int ldf = n + 1, ldr = n + 1, kk = k * k;
+    const int np = M + 3;
+    float* Ssm = sm;                                  // [kk][NA][NA]
+    float* fpl = Ssm + kk * NA * NA;                  // [kk][n][ldf]   f, later dL/df
+    float* rsm = fpl + kk * n * ldf;                  // [n][ldr]
+    float* gx = rsm + n * ldr;                        // [M][G] and derivative [M][G]
+    float* gy = gx + 2 * DC_MMAX * 16;
+    float* par = gy + 2 * DC_MMAX * 16;               // [np]
+    float* red = par + 16;                            // [8 + 4*DC_MMAX]
+    __shared__ int iwin[2 * DC_MMAX];
+
+    // ---- pending AdaBelief update of the per-epoch parameters (gradients of the previous iteration)
+    float* ep = D.ep + (size_t)e * np;
+    if (tid < np) {
+        float p = ep[tid];
+        if (D.ctl[4] != 0.f && !noise) {
+            const bool is_free = (tid < M) ? D.free_a : (tid < M + 2) ? D.free_d : D.free_mean;
+            if (is_free) {
+                const BeliefCoef bc = {D.ctl[1], D.cv.b1, D.cv.b2, 1.f - D.cv.b1, 1.f - D.cv.b2, D.ctl[2], D.ctl[3],
+                                       D.cv.eps, D.cv.eps_root};
+                float mu = D.ep_mu[(size_t)e * np + tid], nv = D.ep_nu[(size_t)e * np + tid];
+                belief_update(bc, D.ctl[0] * D.ep_g[(size_t)e * np + tid], p, mu, nv);
+                D.ep_mu[(size_t)e * np + tid] = mu; D.ep_nu[(size_t)e * np + tid] = nv;
+                ep[tid] = p;
+            }
+        }
+        par[tid] = p;
+    }
+    for (int i = tid; i < kk * NA * NA; i += DC_THREADS) Ssm[i] = __ldg(D.S + (size_t)e * kk * NA * NA + i);
+    __syncthreads();
+
+    const int j0 = (D.P - 1) / 2;
+    const float delta = 0.5f * (float)(D.P - 1) - (float)j0;
+    const float ctr = 0.5f * (float)(nu - 1) - delta;
+    const float al = D.alpha[e];
+    float sa, ca;
+    sincosf(al, &sa, &ca);
+    const float dx = par[M], dy = par[M + 1], mean = par[M + 2];
+    const Geo geo = {ca, sa, (float)k * dx, (float)k * dy, ctr};
+
+    // ---- point-source windows and taps
+    if (tid < 2 * M * G) {
+        const int m = (tid / G) % M, t = tid % G, axis = tid / (M * G);
+        const float cxm = D.c[m], cym = D.c[M + m];
+        const float pc = axis == 0 ? ctr + (float)k * (ca * cxm - sa * cym + dx) : ctr + (float)k * (sa * cxm + ca * cym + dy);
+        const int ic = (int)floorf(pc + 0.5f);
+        const int u = ic - G / 2 + 1 + t;
+        const float x = (float)u - pc;
+        const float g = D.cv.gnorm * expf(-x * x * D.cv.inv2s2);
+        float* dst = axis == 0 ? gx : gy;
+        dst[m * 16 + t] = g;
+        dst[DC_MMAX * 16 + m * 16 + t] = x * D.cv.invs2 * g;     // d g / d pc
+        if (t == 0) iwin[axis * DC_MMAX + m] = ic - G / 2 + 1;
+    }
+    // ---- f = warp(h) in polyphase layout
+    for (int i = tid; i < nu * nu; i += DC_THREADS) {
+        const int v = i / nu, u = i % nu;
+        float val = 0.f;
+        if (D.free_h || D.h != nullptr) {
+            float qu, qv;
+            geo_src(geo, (float)u, (float)v, qu, qv);
+            const float fu0 = floorf(qu), fv0 = floorf(qv);
+            const float fu = qu - fu0, fv = qv - fv0;
+            const int u0 = (int)fu0, v0 = (int)fv0;
+            val = (1.f - fv) * ((1.f - fu) * h_at(D.h, nu, v0, u0) + fu * h_at(D.h, nu, v0, u0 + 1)) +
+                  fv * ((1.f - fu) * h_at(D.h, nu, v0 + 1, u0) + fu * h_at(D.h, nu, v0 + 1, u0 + 1));
+        }
+        fpl[(((v % k) * k + (u % k)) * n + v / k) * ldf + u / k] = val;
+    }
+    __syncthreads();
+    for (int m = 0; m < M; ++m) {          // serially per source: windows of different sources may overlap
+        for (int i = tid; i < G * G; i += DC_THREADS) {
+            const int tv = i / G, tu = i % G;
+            const int v = iwin[DC_MMAX + m] + tv, u = iwin[m] + tu;
+            if (v >= 0 && v < nu && u >= 0 && u < nu)
+                fpl[(((v % k) * k + (u % k)) * n + v / k) * ldf + u / k] += par[m] * gy[m * 16 + tv] * gx[m * 16 + tu];
+        }
+        __syncthreads();
+    }
+
+    // ---- forward: m = mean + 1/k^2 sum_ph corr(f_ph, S_ph);  r = w (m - d)
+    const float dscale = D.cv.mean ? 1.f / (float)kk : 1.f;
+    const float* dat = D.data + (size_t)e * n * n;
+    const float* wgt = D.weight + (size_t)e * n * n;
+    float loss = 0.f, gmean = 0.f;
+    const int nxb = (n + DC_XB - 1) / DC_XB;
+    if (noise) for (int i = tid; i < n * n; i += DC_THREADS) rsm[(i / n) * ldr + i % n] = __ldg(wgt + i);
+    for (int task = tid; task < (noise ? 0 : n * nxb); task += DC_THREADS) {
+        const int Y = task % n, X0 = (task / n) * DC_XB;
+        float acc[DC_XB];
+#pragma unroll
+        for (int x = 0; x < DC_XB; ++x) acc[x] = 0.f;
+        for (int ph = 0; ph < kk; ++ph) corr_row(fpl + ph * n * ldf, ldf, n, Ssm + ph * NA * NA, NA, A0, Y, X0, acc);
+#pragma unroll
+        for (int x = 0; x < DC_XB; ++x) {
+            const int X = X0 + x;
+            if (X < n) {
+                const float mval = fmaf(dscale, acc[x], mean);
+                const float d = __ldg(dat + Y * n + X), w = __ldg(wgt + Y * n + X);
+                const float diff = mval - d, r = w * diff;
+                rsm[Y * ldr + X] = r;
+                loss = fmaf(r, diff, loss);
+                gmean += r;
+                if (want_model) D.model[(size_t)e * n * n + Y * n + X] = mval;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- adjoint: dL/df_ph[Y'][X'] = 1/k^2 sum S_ph[av][au] r[Y'-av][X'-au]   (overwrites f)
+    for (int task = tid; task < kk * n * nxb; task += DC_THREADS) {
+        const int ph = task / (n * nxb), rem = task % (n * nxb), Y = rem % n, X0 = (rem / n) * DC_XB;
+        float acc[DC_XB];
+#pragma unroll
+        for (int x = 0; x < DC_XB; ++x) acc[x] = 0.f;
+        conv_row_T(rsm, ldr, n, Ssm + ph * NA * NA, NA, A0, Y, X0, acc, noise);
+#pragma unroll
+        for (int x = 0; x < DC_XB; ++x)
+            if (X0 + x < n) fpl[(ph * n + Y) * ldf + X0 + x] = (noise ? dscale * dscale : dscale) * acc[x];
+    }
+    __syncthreads();
+    auto dfat = [&](int v, int u) -> float {
+        return (v >= 0 && v < nu && u >= 0 && u < nu) ? fpl[(((v % k) * k + (u % k)) * n + v / k) * ldf + u / k] : 0.f;
+    };
+    // ---- point-source gradients: one warp per source (M <= 8 warps)
+    const float sc = (D.cv.half == 0.5f) ? 1.f : 2.f;
+    const int warp = tid >> 5, lane = tid & 31;
+    float* epg = D.ep_g + (size_t)e * np;
+    if (warp < M && !noise) {
+        const int m = warp;
+        float ga = 0.f, gu = 0.f, gv = 0.f;
+        for (int i = lane; i < G * G; i += 32) {
+            const int tv = i / G, tu = i % G;
+            const float df = dfat(iwin[DC_MMAX + m] + tv, iwin[m] + tu);
+            const float gyv = gy[m * 16 + tv], gxv = gx[m * 16 + tu];
+            ga = fmaf(df, gyv * gxv, ga);
+            gu = fmaf(df, gyv * gx[DC_MMAX * 16 + m * 16 + tu], gu);
+            gv = fmaf(df, gy[DC_MMAX * 16 + m * 16 + tv] * gxv, gv);
+        }
+        ga = warp_sum(ga); gu = warp_sum(gu); gv = warp_sum(gv);
+        if (lane == 0) {
+            const float a = par[m];
+            epg[m] = sc * ga;
+            red[8 + m * 4] = a * gu;            // dL/d uc_m
+            red[8 + m * 4 + 1] = a * gv;        // dL/d vc_m
+        }
+    }
+    // ---- shift gradient through the warp: dL/dd = sum_p dL/df[p] * grad h(q(p)) . dq/dd
+    float gwx = 0.f, gwy = 0.f;
+    if (D.free_d && !noise) {
+        for (int i = tid; i < nu * nu; i += DC_THREADS) {
+            const int v = i / nu, u = i % nu;
+            float qu, qv;
+            geo_src(geo, (float)u, (float)v, qu, qv);
+            const float fu0 = floorf(qu), fv0 = floorf(qv);
+            const float fu = qu - fu0, fv = qv - fv0;
+            const int u0 = (int)fu0, v0 = (int)fv0;
+            const float h00 = h_at(D.h, nu, v0, u0), h01 = h_at(D.h, nu, v0, u0 + 1);
+            const float h10 = h_at(D.h, nu, v0 + 1, u0), h11 = h_at(D.h, nu, v0 + 1, u0 + 1);
+            const float dhu = (1.f - fv) * (h01 - h00) + fv * (h11 - h10);
+            const float dhv = (1.f - fu) * (h10 - h00) + fu * (h11 - h01);
+            const float df = fpl[(((v % k) * k + (u % k)) * n + v / k) * ldf + u / k];
+            // dq/ddx = -k (ca, -sa),  dq/ddy = -k (sa, ca)
+            gwx = fmaf(df, -(float)k * (ca * dhu - sa * dhv), gwx);
+            gwy = fmaf(df, -(float)k * (sa * dhu + ca * dhv), gwy);
+        }
+    }
+    loss = block_sum(loss, red, tid);
+    gmean = block_sum(gmean, red, tid);
+    gwx = block_sum(gwx, red, tid);
+    gwy = block_sum(gwy, red, tid);
+    if (tid == 0 && !noise) {
+        float gdx = sc * gwx, gdy = sc * gwy;
+        for (int m = 0; m < M; ++m) {
+            const float gu = sc * red[8 + m * 4], gv = sc * red[8 + m * 4 + 1];
+            gdx += (float)k * gu; gdy += (float)k * gv;
+            D.gc[(size_t)e * 2 * M + m] = (float)k * (ca * gu + sa * gv);
+            D.gc[(size_t)e * 2 * M + M + m] = (float)k * (-sa * gu + ca * gv);
+        }
+        epg[M] = gdx; epg[M + 1] = gdy; epg[M + 2] = sc * gmean;
+        D.eloss[e] = D.cv.half * loss;
+    }
+    // ---- transposed warp as an exact gather: dL/dh[q] = sum_p dL/df[p] * hat(q - q(p))
+    if (D.free_h || noise) {
+        float* Gh = D.Gh + (size_t)e * nu * nu;
+        for (int i = tid; i < nu * nu; i += DC_THREADS) {
+            const int qv_i = i / nu, qu_i = i % nu;
+            // forward image of q: p_c = R (q - ctr) + ctr + k d
+            const float ru = (float)qu_i - ctr, rv = (float)qv_i - ctr;
+            const float pcu = ca * ru - sa * rv + ctr + geo.tx, pcv = sa * ru + ca * rv + ctr + geo.ty;
+            const int pu0 = (int)floorf(pcu) - 1, pv0 = (int)floorf(pcv) - 1;
+            float acc = 0.f;
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+#pragma unroll
+                for (int a2 = 0; a2 < 4; ++a2) {
+                    const int pv = pv0 + b, pu = pu0 + a2;
+                    if (pv < 0 || pv >= nu || pu < 0 || pu >= nu) continue;
+                    float qu, qv;
+                    geo_src(geo, (float)pu, (float)pv, qu, qv);
+                    // bilinear weight of tap q for source position (qu,qv): taps are floor(q), floor(q)+1
+                    const float fu0 = floorf(qu), fv0 = floorf(qv);
+                    float wu = 0.f, wv = 0.f;
+                    if ((int)fu0 == qu_i) wu = 1.f - (qu - fu0); else if ((int)fu0 + 1 == qu_i) wu = qu - fu0;
+                    if ((int)fv0 == qv_i) wv = 1.f - (qv - fv0); else if ((int)fv0 + 1 == qv_i) wv = qv - fv0;
+                    if (noise) { wu *= wu; wv *= wv; }
+                    if (wu != 0.f && wv != 0.f) acc = fmaf(wu * wv, fpl[(((pv % k) * k + (pu % k)) * n + pv / k) * ldf + pu / k], acc);
+                }
+            Gh[i] = noise ? acc : sc * acc;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- reduction over the local epochs
+__global__ void __launch_bounds__(256) k_deconv_reduce(DeconvDev D, int force_h) {
+    const int nu2 = D.nu * D.nu, M = D.M, np = D.M + 3;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nu2) {
+        float s = 0.f;
+        if (D.free_h || force_h) for (int e = 0; e < D.E; ++e) s += D.Gh[(size_t)e * nu2 + i];
+        D.red[i] = s;
+    } else if (i < nu2 + 2 * M) {
+        float s = 0.f;
+        for (int e = 0; e < D.E; ++e) s += D.gc[(size_t)e * 2 * M + (i - nu2)];
+        D.red[i] = s;
+    } else if (i == nu2 + 2 * M) {
+        float s = 0.f;
+        for (int e = 0; e < D.E; ++e) s += D.eloss[e];
+        D.red[i] = s;
+    } else if (i == nu2 + 2 * M + 1) {
+        float s = 0.f;
+        for (int e = 0; e < D.E; ++e)
+            for (int p = 0; p < np; ++p) {
+                const bool is_free = (p < M) ? D.free_a : (p < M + 2) ? D.free_d : D.free_mean;
+                const float g = D.ep_g[(size_t)e * np + p];
+                if (is_free) s = fmaf(g, g, s);
+            }
+        D.red[i] = s;
+    }
+}
+
+// ---------------------------------------------------------------- shared-parameter update (one CTA)
+__device__ __forceinline__ float atrous_g(const float* __restrict__ c, int nu, int v, int u, int Dd, int axis) {
+    const float h0 = 1.f / 16.f, h1 = 4.f / 16.f, h2 = 6.f / 16.f;
+    if (axis == 0) {
+        const float* row = c + v * nu;
+        return h0 * (row[max(u - 2 * Dd, 0)] + row[min(u + 2 * Dd, nu - 1)]) + h1 * (row[max(u - Dd, 0)] + row[min(u + Dd, nu - 1)]) + h2 * row[u];
+    }
+    return h0 * (c[max(v - 2 * Dd, 0) * nu + u] + c[min(v + 2 * Dd, nu - 1) * nu + u]) +
+           h1 * (c[max(v - Dd, 0) * nu + u] + c[min(v + Dd, nu - 1) * nu + u]) + h2 * c[v * nu + u];
+}
+
+__device__ __forceinline__ float atrous_adj(const float* __restrict__ base, int stride, int nu, int i, int Dd) {
+    const float h[5] = {1.f / 16.f, 4.f / 16.f, 6.f / 16.f, 4.f / 16.f, 1.f / 16.f};
+    float acc = 0.f;
+    if (i > 0 && i < nu - 1) {
+#pragma unroll
+        for (int t = 0; t < 5; ++t) {
+            const int ip = i - (t - 2) * Dd;
+            if (ip >= 0 && ip < nu) acc = fmaf(h[t], base[ip * stride], acc);
+        }
+    } else if (i == 0) {
+#pragma unroll
+        for (int t = 0; t < 5; ++t) {
+            const int hi = min(-(t - 2) * Dd, nu - 1);
+            float s = 0.f;
+            for (int ip = 0; ip <= hi; ++ip) s += base[ip * stride];
+            if (hi >= 0) acc = fmaf(h[t], s, acc);
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < 5; ++t) {
+            const int lo = max(nu - 1 - (t - 2) * Dd, 0);
+            float s = 0.f;
+            for (int ip = lo; ip < nu; ++ip) s += base[ip * stride];
+            if (lo < nu) acc = fmaf(h[t], s, acc);
+        }
+    }
+    return acc;
+}
+
+#define DU_THREADS 1024
+__device__ __forceinline__ float block_sum_u(float v, float* red, int tid) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    float s = 0.f;
+    for (int w = 0; w < DU_THREADS / 32; ++w) s += red[w];
+    return s;
+}
+
+// it < 0: evaluation only (loss + full gradient into red / planes, no update)
+__global__ void __launch_bounds__(DU_THREADS) k_deconv_update(DeconvDev D, int it, int n_iter, float lr0, int schedule,
+                                                              float* grad_h_out, float* grad_c_out, float* loss_out) {
+    __shared__ float red[DU_THREADS / 32];
+    const int tid = threadIdx.x, nu = D.nu, pp = nu * nu, M = D.M, J = D.J;
+    float* C0 = D.planes;
+    float* C1 = C0 + pp;
+    float* GT = C1 + pp;                 // total gradient wrt h
+    float* Tj = GT + pp;                 // [J][pp]
+    float reg = 0.f;
+    const bool do_reg = D.free_h && (D.lam_scales != 0.f || D.lam_hf != 0.f);
+    if (do_reg) {
+        for (int j = 0; j < J; ++j) {
+            const int Dd = 1 << j;
+            const float* cur = (j == 0) ? D.h : C0;
+            for (int i = tid; i < pp; i += DU_THREADS) C1[i] = atrous_g(cur, nu, i / nu, i % nu, Dd, 0);
+            __syncthreads();
+            const float lam = (j == 0) ? D.lam_hf : D.lam_scales;
+            for (int i = tid; i < pp; i += DU_THREADS) {
+                const float nxt = atrous_g(C1, nu, i / nu, i % nu, Dd, 1);
+                const float al = cur[i] - nxt;
+                const float lw = lam * (D.W ? D.W[(size_t)j * pp + i] : 1.f);
+                reg = fmaf(lw, fabsf(al), reg);
+                Tj[(size_t)j * pp + i] = (al > 0.f) ? lw : (al < 0.f) ? -lw : 0.f;
+                C0[i] = nxt;
+            }
+            __syncthreads();
+        }
+        for (int j = J - 1; j >= 0; --j) {
+            const int Dd = 1 << j;
+            for (int i = tid; i < pp; i += DU_THREADS) C0[i] = ((j == J - 1) ? 0.f : C0[i]) - Tj[(size_t)j * pp + i];
+            __syncthreads();
+            for (int i = tid; i < pp; i += DU_THREADS) C1[i] = atrous_adj(C0 + (i % nu), nu, nu, i / nu, Dd);
+            __syncthreads();
+            for (int i = tid; i < pp; i += DU_THREADS) C0[i] = Tj[(size_t)j * pp + i] + atrous_adj(C1 + (i / nu) * nu, 1, nu, i % nu, Dd);
+            __syncthreads();
+        }
+    }
+    float gn2 = 0.f, pos = 0.f;
+    if (D.free_h) {
+        for (int i = tid; i < pp; i += DU_THREADS) {
+            const float hv = D.h[i];
+            float g = D.red[i] + (do_reg ? C0[i] : 0.f);
+            if (D.lam_pos != 0.f && hv < 0.f) { g -= D.lam_pos; pos -= D.lam_pos * hv; }
+            GT[i] = g;
+            gn2 = fmaf(g, g, gn2);
+            if (grad_h_out) grad_h_out[i] = g;
+        }
+    }
+    // c_x, c_y gradients (+ prior)
+    float prior_loss = 0.f;
+    __shared__ float gcs[2 * DC_MMAX];
+    if (tid < 2 * M) {
+        float g = D.red[pp + tid];
+        if (D.has_prior) {
+            const int ax = tid / M, m = tid % M;
+            const float mu = D.prior[(2 * ax) * M + m], sg = D.prior[(2 * ax + 1) * M + m];
+            const float z = (D.c[tid] - mu) / sg;
+            g += z / sg;
+            prior_loss = 0.5f * z * z;
+        }
+        gcs[tid] = g;
+        if (grad_c_out) grad_c_out[tid] = g;
+        if (D.free_c) gn2 = fmaf(g, g, gn2);
+    }
+    reg = block_sum_u(reg, red, tid);
+    pos = block_sum_u(pos, red, tid);
+    prior_loss = block_sum_u(prior_loss, red, tid);
+    gn2 = block_sum_u(gn2, red, tid) + D.red[pp + 2 * M + 1];
+    const float L = D.red[pp + 2 * M] + reg + pos + prior_loss;
+    if (tid == 0) {
+        if (loss_out) loss_out[0] = L;
+        if (it >= 0 && D.loss_hist) D.loss_hist[it] = L;
+        D.ctl[5] = L;
+    }
+    if (it < 0) return;
+    // ---- optimiser coefficients; per-epoch parameters are updated by the next k_deconv_epoch launch
+    float cs = 1.f, lr = lr0;
+    if (schedule) {
+        const float gn = sqrtf(gn2);
+        cs = (gn < D.cv.clip) ? 1.f : D.cv.clip / gn;
+        lr = lr0 * powf(D.cv.decay, (float)it / (float)n_iter);
+    }
+    const float b1t = powf(D.cv.b1, (float)(it + 1)), b2t = powf(D.cv.b2, (float)(it + 1));
+    const BeliefCoef bc = {lr, D.cv.b1, D.cv.b2, 1.f - D.cv.b1, 1.f - D.cv.b2, 1.f / (1.f - b1t), 1.f / (1.f - b2t),
+                           D.cv.eps, D.cv.eps_root};
+    if (D.free_h) {
+        for (int i = tid; i < pp; i += DU_THREADS) {
+            float hv = D.h[i], mu = D.h_mu[i], nv = D.h_nu[i];
+            belief_update(bc, cs * GT[i], hv, mu, nv);
+            D.h[i] = hv; D.h_mu[i] = mu; D.h_nu[i] = nv;
+        }
+    }
+    if (D.free_c && tid < 2 * M) {
+        float cvv = D.c[tid], mu = D.c_mu[tid], nv = D.c_nu[tid];
+        belief_update(bc, cs * gcs[tid], cvv, mu, nv);
+        D.c[tid] = cvv; D.c_mu[tid] = mu; D.c_nu[tid] = nv;
+    }
+    if (tid == 0) { D.ctl[0] = cs; D.ctl[1] = lr; D.ctl[2] = bc.inv_bc1; D.ctl[3] = bc.inv_bc2; D.ctl[4] = 1.f; }
+}
+
+// ================================================================= host side: handle-based ABI
+struct DeconvHandle {
+    DeconvDev D;
+    std::vector<void*> owned;
+    cudaStream_t st;
+    int loss_cap;
+    size_t smem_epoch;
+};
+
+static int dalloc(DeconvHandle* H, void** p, size_t bytes, bool zero) {
+    cudaError_t e = cudaMalloc(p, bytes ? bytes : 4);
+    if (e != cudaSuccess) { lcb_set_error("deconv cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); return LCB_ERR_NOMEM; }
+    H->owned.push_back(*p);
+    if (zero) LCB_CUDA(cudaMemsetAsync(*p, 0, bytes ? bytes : 4, H->st));
+    return LCB_OK;
+}
+
+static int put(DeconvHandle* H, float* dst, const float* src, size_t count, int mem) {
+    if (!src) return LCB_OK;
+    LCB_CUDA(cudaMemcpyAsync(dst, src, count * 4, mem == LCB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, H->st));
+    if (mem == LCB_MEM_HOST) LCB_CUDA(cudaStreamSynchronize(H->st));
+    return LCB_OK;
+}
+
+static int get(DeconvHandle* H, float* dst, const float* src, size_t count, int mem) {
+    if (!dst) return LCB_OK;
+    LCB_CUDA(cudaMemcpyAsync(dst, src, count * 4, mem == LCB_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, H->st));
+    if (mem == LCB_MEM_HOST) LCB_CUDA(cudaStreamSynchronize(H->st));
+    return LCB_OK;
+}
+
+extern "C" {
+
+int lcb_deconv_destroy(void* handle) {
+    DeconvHandle* H = (DeconvHandle*)handle;
+    if (!H) return LCB_OK;
+    cudaStreamSynchronize(H->st);
+    for (void* p : H->owned) cudaFree(p);
+    delete H;
+    return LCB_OK;
+}
+
+int lcb_deconv_create(const lcb_deconv_problem* p, int mem, void* stream, void** handle) {
+    LCB_REQUIRE(p && handle, "lcb_deconv_create: NULL argument");
+    LCB_REQUIRE(p->E >= 1 && p->n >= 4 && p->k >= 1 && p->k <= 4 && p->P >= 1 && p->M >= 0 && p->M <= DC_MMAX,
+                "lcb_deconv_create: bad sizes E=%d n=%d k=%d P=%d M=%d (M <= %d)", p->E, p->n, p->k, p->P, p->M, DC_MMAX);
+    LCB_REQUIRE(p->data && p->weight && p->psf, "lcb_deconv_create: NULL input array");
+    if (lcb_device_count() == 0) { lcb_set_error("no CUDA device: liblcb has no CPU fallback"); return LCB_ERR_CUDA; }
+    DeconvHandle* H = new DeconvHandle();
+    H->st = (cudaStream_t)stream;
+    DeconvDev& D = H->D;
+    memset(&D, 0, sizeof(D));
+    D.E = p->E; D.n = p->n; D.k = p->k; D.nu = p->n * p->k; D.P = p->P; D.M = p->M;
+    D.cv = lcb_devconv();
+    D.G = D.cv.G;
+    LCB_REQUIRE(D.G <= 16, "gauss_taps must be <= 16");
+    const int j0 = (p->P - 1) / 2;
+    D.A0 = (j0 - p->P + 1 >= 0) ? (j0 - p->P + 1) / p->k : -((-(j0 - p->P + 1) + p->k - 1) / p->k);
+    const int A1 = (j0 + p->k - 1) / p->k;
+    D.NA = A1 - D.A0 + 1;
+    int J = 0; while ((1 << (J + 1)) <= D.nu) ++J;
+    D.J = J;
+    const size_t E = D.E, nn = (size_t)D.n * D.n, pp = (size_t)D.nu * D.nu, np = D.M + 3, kk = (size_t)D.k * D.k;
+    int rc = 0;
+#define AL(field, count, zero) if ((rc = dalloc(H, (void**)&D.field, (count) * 4, zero))) { lcb_deconv_destroy(H); return rc; }
+    AL(data, E * nn, false) AL(weight, E * nn, false) AL(S, E * kk * D.NA * D.NA, false)
+    AL(h, pp, true) AL(h_mu, pp, true) AL(h_nu, pp, true)
+    AL(c, 2 * (size_t)DC_MMAX, true) AL(c_mu, 2 * (size_t)DC_MMAX, true) AL(c_nu, 2 * (size_t)DC_MMAX, true)
+    AL(ep, E * np, true) AL(ep_mu, E * np, true) AL(ep_nu, E * np, true) AL(ep_g, E * np, true)
+    AL(alpha, E, true) AL(Gh, E * pp, true) AL(gc, E * 2 * (size_t)DC_MMAX, true) AL(eloss, E, true)
+    AL(red, pp + 2 * DC_MMAX + 2, true) AL(ctl, 8, true) AL(planes, (3 + (size_t)J) * pp, true)
+    AL(model, E * nn, true) AL(prior, 4 * (size_t)DC_MMAX, true)
+#undef AL
+    D.W = nullptr;                                    // allocated by lcb_deconv_set_reg when weights are given
+    H->loss_cap = 0; D.loss_hist = nullptr;
+    // inputs
+    float* psf_d = nullptr;
+    if ((rc = dalloc(H, (void**)&psf_d, E * (size_t)p->P * p->P * 4, false))) { lcb_deconv_destroy(H); return rc; }
+    if ((rc = put(H, D.data, p->data, E * nn, mem)) || (rc = put(H, D.weight, p->weight, E * nn, mem)) ||
+        (rc = put(H, psf_d, p->psf, E * (size_t)p->P * p->P, mem))) { lcb_deconv_destroy(H); return rc; }
+    k_deconv_fold_psf<<<D.E, 256, 0, H->st>>>(psf_d, D.S, D.E, D.P, D.k, D.NA, D.A0);
+    if (cudaGetLastError() != cudaSuccess) { lcb_set_error("k_deconv_fold_psf launch failed"); lcb_deconv_destroy(H); return LCB_ERR_CUDA; }
+    D.free_h = D.free_mean = D.free_a = D.free_c = D.free_d = 1;
+    H->smem_epoch = (kk * D.NA * D.NA + kk * D.n * (D.n + 1) + (size_t)D.n * (D.n + 1) + 4 * DC_MMAX * 16 + 16 + 8 + 4 * DC_MMAX) * 4;
+    int dev = 0, maxsm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (H->smem_epoch > (size_t)maxsm) {
+        lcb_set_error("deconvolution: n=%d k=%d P=%d needs %zu B of shared memory per epoch (> %d)", D.n, D.k, D.P, H->smem_epoch, maxsm);
+        lcb_deconv_destroy(H);
+        return LCB_ERR_ARG;
+    }
+    cudaFuncSetAttribute(k_deconv_epoch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H->smem_epoch);
+    *handle = H;
+    return LCB_OK;
+}
+
+int lcb_deconv_set_params(void* handle, const lcb_deconv_params* q, int mem) {
+    DeconvHandle* H = (DeconvHandle*)handle;
+    LCB_REQUIRE(H && q, "lcb_deconv_set_params: NULL argument");
+    DeconvDev& D = H->D;
+    const size_t E = D.E, pp = (size_t)D.nu * D.nu, np = D.M + 3;
+    int rc;
+    if ((rc = put(H, D.h, q->h, pp, mem))) return rc;
+    if ((rc = put(H, D.c, q->c_x, D.M, mem)) || (rc = put(H, D.c + D.M, q->c_y, D.M, mem))) return rc;
+    if ((rc = put(H, D.alpha, q->alpha, E, mem))) return rc;
+    // per-epoch block [E][M+3] is assembled on the host side of the copy: strided device copies
+    if (q->a) LCB_CUDA(cudaMemcpy2DAsync(D.ep, np * 4, q->a, D.M * 4, D.M * 4, E, mem == LCB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, H->st));
+    const float* cols[3] = {q->dx, q->dy, q->mean};
+    for (int c = 0; c < 3; ++c)
+        if (cols[c]) LCB_CUDA(cudaMemcpy2DAsync(D.ep + D.M + c, np * 4, cols[c], 4, 4, E, mem == LCB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, H->st));
+    // restart the optimiser
+    LCB_CUDA(cudaMemsetAsync(D.h_mu, 0, pp * 4, H->st)); LCB_CUDA(cudaMemsetAsync(D.h_nu, 0, pp * 4, H->st));
+    LCB_CUDA(cudaMemsetAsync(D.c_mu, 0, 2 * DC_MMAX * 4, H->st)); LCB_CUDA(cudaMemsetAsync(D.c_nu, 0, 2 * DC_MMAX * 4, H->st));
+    LCB_CUDA(cudaMemsetAsync(D.ep_mu, 0, E * np * 4, H->st)); LCB_CUDA(cudaMemsetAsync(D.ep_nu, 0, E * np * 4, H->st));
+    LCB_CUDA(cudaMemsetAsync(D.ctl, 0, 8 * 4, H->st));
+    D.free_h = q->free_h; D.free_mean = q->free_mean; D.free_a = q->free_a; D.free_c = q->free_c; D.free_d = q->free_d;
+    LCB_CUDA(cudaStreamSynchronize(H->st));
+    return LCB_OK;
+}
+
+int lcb_deconv_set_reg(void* handle, const lcb_deconv_reg* r, int mem) {
+    DeconvHandle* H = (DeconvHandle*)handle;
+    LCB_REQUIRE(H && r, "lcb_deconv_set_reg: NULL argument");
+    DeconvDev& D = H->D;
+    const size_t pp = (size_t)D.nu * D.nu;
+    D.lam_scales = r->lam_scales; D.lam_hf = r->lam_hf; D.lam_pos = r->lam_pos;
+    int rc;
+    if (r->W) {
+        if (!D.W) { if ((rc = dalloc(H, (void**)&D.W, (size_t)D.J * pp * 4, false))) return rc; }
+        if ((rc = put(H, D.W, r->W, (size_t)D.J * pp, mem))) return rc;
+    } else D.W = nullptr;
+    D.has_prior = (r->prior_mu_x && r->prior_sig_x && r->prior_mu_y && r->prior_sig_y) ? 1 : 0;
+    if (D.has_prior) {
+        if ((rc = put(H, D.prior, r->prior_mu_x, D.M, mem)) || (rc = put(H, D.prior + D.M, r->prior_sig_x, D.M, mem)) ||
+            (rc = put(H, D.prior + 2 * D.M, r->prior_mu_y, D.M, mem)) || (rc = put(H, D.prior + 3 * D.M, r->prior_sig_y, D.M, mem))) return rc;
+    }
+    return LCB_OK;
+}
+
+// local half of one iteration: per-epoch kernel + reduction over the local epochs into red[]
+int lcb_deconv_step_local(void* handle, int want_model) {
+    DeconvHandle* H = (DeconvHandle*)handle;
+    LCB_REQUIRE(H, "lcb_deconv_step_local: NULL handle");
+    DeconvDev& D = H->D;
+    { LcbProfScope ps("k_deconv_epoch", H->st); k_deconv_epoch<<<D.E, DC_THREADS, H->smem_epoch, H->st>>>(D, want_model); }
+    LCB_CUDA(cudaGetLastError());
+    const int tot = D.nu * D.nu + 2 * D.M + 2;
+    { LcbProfScope ps("k_deconv_reduce", H->st); k_deconv_reduce<<<(tot + 255) / 256, 256, 0, H->st>>>(D, 0); }
+    LCB_CUDA(cudaGetLastError());
+    return LCB_OK;
+}
+
+// device pointer and length of the buffer to all-reduce (sum) across ranks between the two halves
+int lcb_deconv_reduce_buffer(void* handle, float** ptr, int* count) {
+    DeconvHandle* H = (DeconvHandle*)handle;
+    LCB_REQUIRE(H && ptr && count, "lcb_deconv_reduce_buffer: NULL argument");
+    *ptr = H->D.red; *count = H->D.nu * H->D.nu + 2 * H->D.M + 2;
+    return LCB_OK;
+}
+
+// replicated half: regularisers, global norm, AdaBelief on the shared parameters; it < 0 = evaluate only
+int lcb_deconv_step_update(void* handle, int it, int n_iter, float lr, int schedule) {
+    DeconvHandle* H = (DeconvHandle*)handle;
+    LCB_REQUIRE(H, "lcb_deconv_step_update: NULL handle");
+    { LcbProfScope ps("k_deconv_update", H->st);
+      k_deconv_update<<<1, DU_THREADS, 0, H->st>>>(H->D, it, n_iter, lr, schedule, nullptr, nullptr, nullptr); }
+    LCB_CUDA(cudaGetLastError());
+    return LCB_OK;
+}
+
+int lcb_deconv_run(void* handle, const lcb_fit_opts* opt, float* loss_hist, int mem) {
+    DeconvHandle* H = (DeconvHandle*)handle;
+    LCB_REQUIRE(H && opt && opt->n_iter >= 0, "lcb_deconv_run: bad arguments");
+    DeconvDev& D = H->D;
+    int rc;
+    if (opt->n_iter > H->loss_cap) {
+        if ((rc = dalloc(H, (void**)&D.loss_hist, (size_t)opt->n_iter * 4, true))) return rc;
+        H->loss_cap = opt->n_iter;
+    }
+    for (int it = 0; it < opt->n_iter; ++it) {
+        if ((rc = lcb_deconv_step_local(H, 0))) return rc;
+        if ((rc = lcb_deconv_step_update(H, it, opt->n_iter, opt->lr, opt->schedule))) return rc;
+    }
+    // flush the pending per-epoch update so that get() sees the final parameters
+    if (opt->n_iter > 0) { if ((rc = lcb_deconv_step_local(H, 0))) return rc; LCB_CUDA(cudaMemsetAsync(D.ctl + 4, 0, 4, H->st)); }
+    if (loss_hist) { if ((rc = get(H, loss_hist, D.loss_hist, opt->n_iter, mem))) return rc; }
+    return LCB_OK;
+}
+
+// loss and gradient at the current parameters (no update)
+int lcb_deconv_loss_grad(void* handle, lcb_deconv_grad* g, int mem) {
+    DeconvHandle* H = (DeconvHandle*)handle;
+    LCB_REQUIRE(H && g, "lcb_deconv_loss_grad: NULL argument");
+    DeconvDev& D = H->D;
+    const size_t E = D.E, pp = (size_t)D.nu * D.nu, np = D.M + 3;
+    int rc;
+    LCB_CUDA(cudaMemsetAsync(D.ctl + 4, 0, 4, H->st));
+    if ((rc = lcb_deconv_step_local(H, 0))) return rc;
+    float *gh = nullptr, *gcx = nullptr, *ls = nullptr;
+    if ((rc = dalloc(H, (void**)&gh, pp * 4, true)) || (rc = dalloc(H, (void**)&gcx, 2 * DC_MMAX * 4, true)) ||
+        (rc = dalloc(H, (void**)&ls, 4, true))) return rc;
+    k_deconv_update<<<1, DU_THREADS, 0, H->st>>>(D, -1, 1, 0.f, 0, gh, gcx, ls);
+    LCB_CUDA(cudaGetLastError());
+    if ((rc = get(H, g->loss, ls, 1, mem)) || (rc = get(H, g->h, gh, pp, mem)) || (rc = get(H, g->c_x, gcx, D.M, mem)) ||
+        (rc = get(H, g->c_y, gcx + D.M, D.M, mem))) return rc;
+    const cudaMemcpyKind kd = mem == LCB_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    if (g->a) LCB_CUDA(cudaMemcpy2DAsync(g->a, D.M * 4, D.ep_g, np * 4, D.M * 4, E, kd, H->st));
+    float* cols[3] = {g->dx, g->dy, g->mean};
+    for (int c = 0; c < 3; ++c)
+        if (cols[c]) LCB_CUDA(cudaMemcpy2DAsync(cols[c], 4, D.ep_g + D.M + c, np * 4, 4, E, kd, H->st));
+    LCB_CUDA(cudaStreamSynchronize(H->st));
+    return LCB_OK;
+}
+
+int lcb_deconv_get(void* handle, lcb_deconv_params* q, float* model, float* loss, int mem) {
+    DeconvHandle* H = (DeconvHandle*)handle;
+    LCB_REQUIRE(H && q, "lcb_deconv_get: NULL argument");
+    DeconvDev& D = H->D;
+    const size_t E = D.E, pp = (size_t)D.nu * D.nu, np = D.M + 3, nn = (size_t)D.n * D.n;
+    int rc;
+    if (model || loss) {
+        LCB_CUDA(cudaMemsetAsync(D.ctl + 4, 0, 4, H->st));
+        if ((rc = lcb_deconv_step_local(H, 1))) return rc;
+        if (loss) {
+            float* ls = nullptr;
+            if ((rc = dalloc(H, (void**)&ls, 4, true))) return rc;
+            k_deconv_update<<<1, DU_THREADS, 0, H->st>>>(D, -1, 1, 0.f, 0, nullptr, nullptr, ls);
+            LCB_CUDA(cudaGetLastError());
+            if ((rc = get(H, loss, ls, 1, mem))) return rc;
+        }
+        if ((rc = get(H, model, D.model, E * nn, mem))) return rc;
+    }
+    if ((rc = get(H, (float*)q->h, D.h, pp, mem)) || (rc = get(H, (float*)q->c_x, D.c, D.M, mem)) ||
+        (rc = get(H, (float*)q->c_y, D.c + D.M, D.M, mem)) || (rc = get(H, (float*)q->alpha, D.alpha, E, mem))) return rc;
+    const cudaMemcpyKind kd = mem == LCB_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    if (q->a) LCB_CUDA(cudaMemcpy2DAsync((float*)q->a, D.M * 4, D.ep, np * 4, D.M * 4, E, kd, H->st));
+    float* cols[3] = {(float*)q->dx, (float*)q->dy, (float*)q->mean};
+    for (int c = 0; c < 3; ++c)
+        if (cols[c]) LCB_CUDA(cudaMemcpy2DAsync(cols[c], 4, D.ep + D.M + c, np * 4, 4, E, kd, H->st));
+    LCB_CUDA(cudaStreamSynchronize(H->st));
+    return LCB_OK;
+}
+
+// Noise weights for the starlet regulariser of h (roi_modelling.py:299, star_photometry.py:108), same
+// definition as for the PSF grid: var(p) = sum_e sum_q A_e[q,p]^2 w_e[q] (A_e = warp, PSF, decimation),
+// W_j = sqrt(var (*) psi_j^2).  stage 0: local var into the reduce buffer (all-reduce it when sharded);
+// stage 1: W from the reduce buffer, installed in the handle (and copied to W_out when non-NULL).
+int lcb_deconv_noise_weights(void* handle, int stage, float* W_out, int mem) {
+    DeconvHandle* H = (DeconvHandle*)handle;
+    LCB_REQUIRE(H, "lcb_deconv_noise_weights: NULL handle");
+    DeconvDev& D = H->D;
+    const size_t pp = (size_t)D.nu * D.nu;
+    int rc;
+    if (stage == 0) {
+        k_deconv_epoch<<<D.E, DC_THREADS, H->smem_epoch, H->st>>>(D, 2);
+        LCB_CUDA(cudaGetLastError());
+        const int tot = D.nu * D.nu + 2 * D.M + 2;
+        k_deconv_reduce<<<(tot + 255) / 256, 256, 0, H->st>>>(D, 1);
+        LCB_CUDA(cudaGetLastError());
+        return LCB_OK;
+    }
+    std::vector<float> tab;
+    lcb_build_noise_table(D.nu, D.J, tab);
+    float* tabd = nullptr;
+    if ((rc = dalloc(H, (void**)&tabd, tab.size() * 4, false))) return rc;
+    LCB_CUDA(cudaMemcpyAsync(tabd, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, H->st));
+    LCB_CUDA(cudaStreamSynchronize(H->st));
+    if (!D.W) { if ((rc = dalloc(H, (void**)&D.W, (size_t)D.J * pp * 4, false))) return rc; }
+    LCB_CUDA(cudaMemcpyAsync(D.planes, D.red, pp * 4, cudaMemcpyDeviceToDevice, H->st));
+    if ((rc = lcb_noise_weights_launch(1, D.nu, D.J, tabd, D.W, D.planes, 2 * pp, H->st))) return rc;
+    return get(H, W_out, D.W, (size_t)D.J * pp, mem);
+}
+
+}  // extern "C"

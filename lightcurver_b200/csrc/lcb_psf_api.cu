@@ -21,7 +21,7 @@ extern "C" int lcb_starlet_scales(int nu) {
 
 // 1-D kernels of the starlet-space noise propagation: f_j = H_{j-1}..H_0 delta_{nu/2} (clamped a-trous
 // cascade, double precision), table [J][3][nu] = f_j^2, f_j f_{j+1}, f_{j+1}^2.
-static void build_noise_table(int nu, int J, std::vector<float>& tab) {
+void lcb_build_noise_table(int nu, int J, std::vector<float>& tab) {
     std::vector<double> f(nu, 0.0), g(nu, 0.0);
     f[nu / 2] = 1.0;
     tab.assign((size_t)J * 3 * nu, 0.f);
@@ -87,7 +87,7 @@ static int psf_run_device(const lcb_psf_batch* in, const lcb_psf_opts* opt, lcb_
         if (out->W_out) Wuse = out->W_out;
         else { if ((rc = Wtmp.alloc((size_t)F * J * pp * 4))) return rc; Wuse = (float*)Wtmp.p; }
         std::vector<float> tab;
-        build_noise_table(nu, J, tab);
+        lcb_build_noise_table(nu, J, tab);
         if ((rc = tabd.alloc(tab.size() * 4))) return rc;
         LCB_CUDA(cudaMemcpyAsync(tabd.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, st));
         LCB_CUDA(cudaStreamSynchronize(st));                 // tab is a host temporary

@@ -1,0 +1,226 @@
+"""Joint multi-epoch deconvolution: the STARRED calls of lightcurver/processes/roi_modelling.py:213-335
+(``setup_model``, ``Prior``, ``Loss``, ``propagate_noise``, ``Optimizer('adabelief').minimize``,
+``model.model``, ``model.getDeconvolved``) served by liblcb's ``lcb_deconv_*`` handle API.
+
+``joint_deconvolution`` is the single entry point a patched ``do_modelling_of_roi`` calls for its
+stage 2 (and ``do_one_star_forward_modelling`` for the shared-background variants).  Epochs can be
+sharded over ranks: every rank passes ITS epochs plus a ``torch.distributed`` process group, and one
+all-reduce of nu^2 + 2M + 2 floats per iteration keeps the shared parameters (h, c_x, c_y)
+bit-identical on all ranks.
+"""
+import ctypes as C
+
+import numpy as np
+
+from .. import _lib
+from .._lib import as_f32, ptr
+from ..conventions import Conventions, DEFAULT
+
+
+class JointDeconvolution:
+    """Thin owner of an ``lcb_deconv`` handle (host-pointer mode for inputs/outputs)."""
+
+    def __init__(self, data, weight, psf, subsampling_factor, n_sources, conventions: Conventions = DEFAULT):
+        _lib.require_device()
+        from ..conventions import apply_to_library
+        apply_to_library(conventions)
+        self.data, self.weight, self.psf = as_f32(data), as_f32(weight), as_f32(psf)
+        self.E, self.n = int(self.data.shape[0]), int(self.data.shape[-1])
+        self.k, self.M, self.P = int(subsampling_factor), int(n_sources), int(self.psf.shape[-1])
+        self.nu = self.n * self.k
+        if tuple(self.psf.shape) != (self.E, self.P, self.P) or tuple(self.weight.shape) != tuple(self.data.shape):
+            raise ValueError("data/weight must be (E,n,n) and psf (E,P,P)")
+        prob = _lib.DeconvProblem(self.E, self.n, self.k, self.P, self.M, ptr(self.data), ptr(self.weight), ptr(self.psf))
+        self.handle = C.c_void_p()
+        _lib.check(_lib.lib.lcb_deconv_create(C.byref(prob), _lib.MEM_HOST, None, C.byref(self.handle)), 'lcb_deconv_create')
+        self.J = int(_lib.lib.lcb_starlet_scales(self.nu))
+
+    def close(self):
+        if getattr(self, 'handle', None):
+            _lib.lib.lcb_deconv_destroy(self.handle)
+            self.handle = None
+
+    __del__ = close
+
+    # ---- parameters -------------------------------------------------------------------------
+    def set_params(self, h=None, mean=None, a=None, c_x=None, c_y=None, dx=None, dy=None, alpha=None,
+                   free_h=True, free_mean=True, free_a=True, free_c=True, free_d=True):
+        E, M = self.E, self.M
+        arrs = dict(h=(h, self.nu * self.nu), mean=(mean, E), a=(a, E * M), c_x=(c_x, M), c_y=(c_y, M),
+                    dx=(dx, E), dy=(dy, E), alpha=(alpha, E))
+        keep = {}
+        for nm, (v, cnt) in arrs.items():
+            if v is None:
+                keep[nm] = None
+                continue
+            v = np.ascontiguousarray(np.asarray(v, dtype=np.float32).reshape(-1))
+            if v.size != cnt:
+                raise ValueError(f"{nm} must have {cnt} elements (got {v.size})")
+            keep[nm] = v
+        q = _lib.DeconvParams(*[ptr(keep[nm]) for nm in ('h', 'mean', 'a', 'c_x', 'c_y', 'dx', 'dy', 'alpha')],
+                              int(free_h), int(free_mean), int(free_a), int(free_c), int(free_d))
+        _lib.check(_lib.lib.lcb_deconv_set_params(self.handle, C.byref(q), _lib.MEM_HOST), 'lcb_deconv_set_params')
+
+    def set_reg(self, lam_scales=0.0, lam_hf=0.0, lam_pos=0.0, W=None, prior=None):
+        W = None if W is None else np.ascontiguousarray(W, dtype=np.float32)
+        if W is not None and W.size != self.J * self.nu * self.nu:
+            raise ValueError(f"W must be ({self.J},{self.nu},{self.nu})")
+        pr = [None] * 4
+        if prior is not None:
+            pr = [np.ascontiguousarray(np.broadcast_to(np.asarray(p, dtype=np.float32), (self.M,))) for p in prior]
+        r = _lib.DeconvReg(float(lam_scales), float(lam_hf), float(lam_pos), ptr(W), *[ptr(p) for p in pr])
+        _lib.check(_lib.lib.lcb_deconv_set_reg(self.handle, C.byref(r), _lib.MEM_HOST), 'lcb_deconv_set_reg')
+
+    # ---- evaluation -------------------------------------------------------------------------
+    def get(self, want_model=True):
+        E, M, nu, n = self.E, self.M, self.nu, self.n
+        out = dict(h=np.empty(nu * nu, np.float32), mean=np.empty(E, np.float32), a=np.empty(E * M, np.float32),
+                   c_x=np.empty(M, np.float32), c_y=np.empty(M, np.float32), dx=np.empty(E, np.float32),
+                   dy=np.empty(E, np.float32), alpha=np.empty(E, np.float32))
+        q = _lib.DeconvParams(*[ptr(out[nm]) for nm in ('h', 'mean', 'a', 'c_x', 'c_y', 'dx', 'dy', 'alpha')], 0, 0, 0, 0, 0)
+        model = np.empty((E, n, n), np.float32) if want_model else None
+        loss = np.empty(1, np.float32) if want_model else None
+        _lib.check(_lib.lib.lcb_deconv_get(self.handle, C.byref(q), ptr(model), ptr(loss), _lib.MEM_HOST), 'lcb_deconv_get')
+        if want_model:
+            out['model'] = model
+            out['loss_local'] = float(loss[0])
+        return out
+
+    def loss_grad(self):
+        """Loss and gradient at the current parameters (single rank)."""
+        E, M, nu = self.E, self.M, self.nu
+        g = dict(loss=np.empty(1, np.float32), h=np.empty(nu * nu, np.float32), mean=np.empty(E, np.float32),
+                 a=np.empty(E * M, np.float32), c_x=np.empty(M, np.float32), c_y=np.empty(M, np.float32),
+                 dx=np.empty(E, np.float32), dy=np.empty(E, np.float32))
+        s = _lib.DeconvGrad(*[ptr(g[nm]) for nm in ('loss', 'h', 'mean', 'a', 'c_x', 'c_y', 'dx', 'dy')])
+        _lib.check(_lib.lib.lcb_deconv_loss_grad(self.handle, C.byref(s), _lib.MEM_HOST), 'lcb_deconv_loss_grad')
+        g['loss'] = float(g['loss'][0])
+        return g
+
+    # ---- optimisation -----------------------------------------------------------------------
+    def reduce_tensor(self):
+        """torch view (no copy) of the device buffer that must be sum-all-reduced between the halves."""
+        import torch
+        p, cnt = C.c_void_p(), C.c_int()
+        _lib.check(_lib.lib.lcb_deconv_reduce_buffer(self.handle, C.byref(p), C.byref(cnt)), 'lcb_deconv_reduce_buffer')
+
+        class _Ext:      # __cuda_array_interface__ holder
+            pass
+        ext = _Ext()
+        ext.__cuda_array_interface__ = dict(shape=(cnt.value,), typestr='<f4', data=(p.value, False), version=2)
+        return torch.as_tensor(ext, device='cuda')
+
+    def noise_weights(self, group=None):
+        _lib.check(_lib.lib.lcb_deconv_noise_weights(self.handle, 0, None, _lib.MEM_HOST), 'lcb_deconv_noise_weights')
+        if group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(self.reduce_tensor(), group=group)
+        W = np.empty((self.J, self.nu, self.nu), np.float32)
+        _lib.check(_lib.lib.lcb_deconv_noise_weights(self.handle, 1, ptr(W), _lib.MEM_HOST), 'lcb_deconv_noise_weights')
+        return W
+
+    def run(self, n_iter, lr=1e-4, schedule=False, group=None):
+        """n_iter AdaBelief iterations; returns the loss history (global loss when sharded)."""
+        if group is None:
+            hist = np.empty(n_iter, np.float32)
+            opts = _lib.FitOpts(int(n_iter), float(lr), int(bool(schedule)))
+            _lib.check(_lib.lib.lcb_deconv_run(self.handle, C.byref(opts), ptr(hist), _lib.MEM_HOST), 'lcb_deconv_run')
+            return hist
+        import torch
+        import torch.distributed as dist
+        red = self.reduce_tensor()
+        lossidx = self.nu * self.nu + 2 * self.M
+        hist = torch.empty(n_iter, device='cuda')
+        for it in range(n_iter):
+            _lib.check(_lib.lib.lcb_deconv_step_local(self.handle, 0), 'lcb_deconv_step_local')
+            dist.all_reduce(red, group=group)                     # ONE collective per iteration
+            _lib.check(_lib.lib.lcb_deconv_step_update(self.handle, it, n_iter, float(lr), int(bool(schedule))), 'lcb_deconv_step_update')
+            hist[it] = red[lossidx]
+        if n_iter:
+            _lib.check(_lib.lib.lcb_deconv_step_local(self.handle, 0), 'lcb_deconv_step_local')   # pending per-epoch update
+        torch.cuda.synchronize()
+        return hist.cpu().numpy()
+
+
+def epoch_shard(E, rank, world):
+    """Contiguous block partition of E epochs: returns slice(lo, hi)."""
+    base, rem = divmod(E, world)
+    lo = rank * base + min(rank, rem)
+    return slice(lo, lo + base + (1 if rank < rem else 0))
+
+
+def flux_sigma_multi(kwargs, data, noisemap, psf, subsampling_factor, conventions: Conventions = DEFAULT):
+    """starred_utilities.py:10-39 for M point sources: sigma_a[e,m] = (sum_p w (dm/da_em)^2)^-1/2, from M
+    model evaluations with unit amplitudes.  Returns (E*M,) epoch-major."""
+    ka = kwargs['kwargs_analytic']
+    E = data.shape[0]
+    M = len(np.atleast_1d(ka['c_x']))
+    with np.errstate(divide='ignore', invalid='ignore'):
+        w = np.where(np.isfinite(noisemap) & (noisemap > 0), 1.0 / np.asarray(noisemap, np.float64) ** 2, 0.0)
+    jd = JointDeconvolution(np.nan_to_num(np.asarray(data, np.float32)), w.astype(np.float32), psf, subsampling_factor, M, conventions)
+    H = np.empty((E, M))
+    for m in range(M):
+        a = np.zeros((E, M), np.float32)
+        a[:, m] = 1.0
+        jd.set_params(h=np.zeros(jd.nu ** 2), mean=np.zeros(E), a=a, c_x=ka['c_x'], c_y=ka['c_y'], dx=ka['dx'], dy=ka['dy'],
+                      alpha=ka.get('alpha', np.zeros(E)))
+        mod = jd.get()['model'].astype(np.float64)
+        H[:, m] = (w * mod * mod).sum((-1, -2)) * (1.0 if conventions.chi2_half else 2.0)
+    jd.close()
+    with np.errstate(divide='ignore'):
+        return (1.0 / np.sqrt(H)).reshape(-1)
+
+
+def joint_deconvolution(data, weight, psf, subsampling_factor, xs, ys, initial_a, n_iter=2000, lr=1e-4,
+                        schedule=False, alpha=None, h0=None, dx0=None, dy0=None, mean0=None,
+                        free_h=True, free_mean=True, free_a=True, free_c=True, free_d=True,
+                        regularization_strength_scales=1.0, regularization_strength_hf=1.0,
+                        regularization_strength_positivity=100.0, W='propagate', prior=None,
+                        conventions: Conventions = DEFAULT, group=None):
+    """Stage 2 of roi_modelling.py:285-335 (defaults: lr 1e-4, no schedule/clip, strengths 1/1/100).
+
+    data, weight (E,n,n) LOCAL epochs; psf (E,P,P); xs, ys (M,) point-source positions in data pixels
+    from the stamp centre (roi_modelling.py:207-210); initial_a (E*M,) epoch-major or (E,M).
+    ``prior`` = (mu_x, sigma_x, mu_y, sigma_y) Gaussian astrometric prior (roi_modelling.py:240-244).
+    ``W`` = 'propagate' (SLIT weights from the model), an array (J,nu,nu), or None (== 1).
+    Returns dict(kwargs_final, model, loss_history, W, flux_sigma, deconvolved_epoch0).
+    """
+    cv = conventions
+    E, n = data.shape[0], data.shape[-1]
+    M = len(np.atleast_1d(xs))
+    jd = JointDeconvolution(data, weight, psf, subsampling_factor, M, cv)
+    nu = jd.nu
+    a0 = np.asarray(initial_a, dtype=np.float32).reshape(E, M)
+    jd.set_params(h=np.zeros(nu * nu) if h0 is None else h0, mean=np.zeros(E) if mean0 is None else mean0, a=a0,
+                  c_x=np.atleast_1d(xs), c_y=np.atleast_1d(ys), dx=np.zeros(E) if dx0 is None else dx0,
+                  dy=np.zeros(E) if dy0 is None else dy0, alpha=np.zeros(E) if alpha is None else alpha,
+                  free_h=free_h, free_mean=free_mean, free_a=free_a, free_c=free_c, free_d=free_d)
+    propagate = isinstance(W, str)
+    if propagate and W != 'propagate':
+        raise ValueError("W must be 'propagate', an array (J,nu,nu) or None")
+    Wused = None if propagate else W
+    jd.set_reg(regularization_strength_scales, regularization_strength_hf, regularization_strength_positivity,
+               W=Wused, prior=prior)
+    if propagate and free_h and (regularization_strength_scales or regularization_strength_hf):
+        Wused = jd.noise_weights(group)               # installs the weights in the handle
+    hist = jd.run(n_iter, lr=lr, schedule=schedule, group=group)
+    fin = jd.get()
+    kw = {
+        'kwargs_analytic': {'c_x': fin['c_x'].astype(np.float64), 'c_y': fin['c_y'].astype(np.float64),
+                            'dx': fin['dx'].astype(np.float64), 'dy': fin['dy'].astype(np.float64),
+                            'a': fin['a'].astype(np.float64), 'alpha': fin['alpha'].astype(np.float64)},
+        'kwargs_background': {'h': fin['h'].astype(np.float64), 'mean': fin['mean'].astype(np.float64)},
+        'kwargs_sersic': {},
+    }
+    jd.close()
+    with np.errstate(divide='ignore', invalid='ignore'):
+        noisemap = np.where(weight > 0, 1.0 / np.sqrt(weight), np.inf)
+    sig = flux_sigma_multi(kw, data, noisemap, psf, subsampling_factor, cv)
+    # model.getDeconvolved(kwargs, 0): high-resolution scene of epoch 0 and its background only
+    from .star_photometry import point_source_image
+    h2 = fin['h'].reshape(nu, nu).astype(np.float64)
+    deconv = h2.copy()
+    for m in range(M):
+        deconv += point_source_image(fin['a'][m], fin['c_x'][m] + fin['dx'][0], fin['c_y'][m] + fin['dy'][0], n, jd.k, cv)
+    return dict(kwargs_final=kw, model=fin['model'], loss_history=hist, W=Wused, flux_sigma=sig,
+                deconvolved_epoch0=(deconv, h2))

@@ -339,6 +339,24 @@ def deconv_loss(h, mean, a, c_x, c_y, dx, dy, alpha, psf, data, weight, W, n, k,
     return L
 
 
+def deconv_noise_weights(psf, weight, dx, dy, alpha, n, k, cv: Conventions = DEFAULT, dtype=torch.float64):
+    """W (J,nu,nu) for the shared background h: var(p) = sum_e sum_q (d m_e[q] / d h[p])^2 w_e[q] with the
+    Jacobian taken explicitly by autograd (small sizes only), then starlet_noise_levels.  Same
+    definition as psf_noise_weights (SLIT diagonal propagation of the chi2-gradient noise)."""
+    psf, weight = _const(psf, dtype), _const(weight, dtype)
+    dx, dy, alpha = _const(dx, dtype), _const(dy, dtype), _const(alpha, dtype)
+    E, nu = psf.shape[0], n * k
+    zM = torch.zeros(1, dtype=dtype)
+
+    def model_of_h(hflat):
+        return deconv_model(hflat.reshape(nu, nu), torch.zeros(E, dtype=dtype), torch.zeros(E, 1, dtype=dtype), zM, zM,
+                            dx, dy, alpha, psf, n, k, cv, direct=True)
+
+    Jac = torch.autograd.functional.jacobian(model_of_h, torch.zeros(nu * nu, dtype=dtype))   # (E,n,n,nu^2)
+    var = (Jac ** 2 * weight[..., None]).sum((0, 1, 2)).reshape(nu, nu)
+    return starlet_noise_levels(var)
+
+
 def phot_models(psf, a, dx, dy, n, k, cv: Conventions = DEFAULT):
     """Fixed-PSF single point source at c=0, h=0, mean=0 (star_photometry.py:52-87), P == nu.
 

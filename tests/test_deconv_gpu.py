@@ -1,0 +1,131 @@
+"""K3 parity: CUDA joint deconvolution (through the C ABI) vs the CPU oracle.
+
+Loss and gradient at identical parameters within 1e-5 relative (BASELINE.json); fixed-iteration fits:
+fluxes 1e-4 relative, background within 1e-3 of its peak for a short run."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(E, n, k, M, P_data, seed, alpha_on=True):
+    from oracle import starred_model as sm
+    rng = np.random.default_rng(seed)
+    nu = n * k
+    npsf = P_data
+    fw = rng.uniform(2.5, 3.5, E)
+    psf = sm.moffat_image(torch.tensor(fw), torch.tensor(fw * 1.1), torch.tensor(rng.uniform(0, 3, E)),
+                          torch.tensor(rng.uniform(2.5, 3.5, E)), npsf, k).numpy()
+    P = npsf * k
+    c_x = rng.uniform(-n / 5, n / 5, M); c_y = rng.uniform(-n / 5, n / 5, M)
+    a = rng.uniform(50, 200, (E, M))
+    dx = rng.uniform(-1, 1, E); dy = rng.uniform(-1, 1, E)
+    alpha = rng.uniform(-0.2, 0.2, E) if alpha_on else np.zeros(E)
+    mean = rng.uniform(-0.01, 0.01, E)
+    ax = np.arange(nu) - (nu - 1) / 2
+    yy, xx = np.meshgrid(ax, ax, indexing='ij')
+    h = 0.5 * np.exp(-(xx ** 2 + 1.5 * yy ** 2) / (2 * (2.5 * k) ** 2)) + 0.02 * rng.standard_normal((nu, nu))
+    t = lambda v: torch.tensor(v, dtype=torch.float64)
+    model = sm.deconv_model(t(h), t(mean), t(a), t(c_x), t(c_y), t(dx), t(dy), t(alpha), t(psf), n, k).numpy()
+    sig = np.sqrt(0.05 ** 2 + np.abs(model) * 0.01)
+    data = model + sig * rng.standard_normal(model.shape)
+    weight = 1.0 / sig ** 2
+    return dict(psf=psf.astype(np.float32), data=data.astype(np.float32), weight=weight.astype(np.float32),
+                h=h.astype(np.float32), mean=mean.astype(np.float32), a=a.astype(np.float32), c_x=c_x.astype(np.float32),
+                c_y=c_y.astype(np.float32), dx=dx.astype(np.float32), dy=dy.astype(np.float32), alpha=alpha.astype(np.float32), P=P)
+
+
+@pytest.mark.parametrize("E,n,k,M,npsf", [(3, 16, 2, 2, 12), (2, 12, 3, 1, 12), (2, 16, 1, 3, 15), (3, 16, 2, 2, 16)])
+def test_deconv_loss_grad_parity(cuda_device, E, n, k, M, npsf):
+    from lightcurver_b200.processes.roi_modelling import JointDeconvolution
+    from lightcurver_b200 import engine
+    from oracle import starred_model as sm
+    p = _problem(E, n, k, M, npsf, seed=E * 100 + n)
+    nu = n * k
+    rng = np.random.default_rng(4)
+    J = engine.starlet_scales(nu)
+    W = rng.uniform(0.5, 2.0, (J, nu, nu)).astype(np.float32)
+    # evaluate away from the truth
+    q = {kk: p[kk] * (1 + 0.05 * rng.standard_normal(p[kk].shape)).astype(np.float32) for kk in ('a', 'c_x', 'c_y', 'dx', 'dy', 'mean', 'h')}
+    prior = (p['c_x'] + 0.1, np.full(M, 0.5, np.float32), p['c_y'] - 0.1, np.full(M, 0.7, np.float32))
+    jd = JointDeconvolution(p['data'], p['weight'], p['psf'], k, M)
+    jd.set_params(alpha=p['alpha'], **q)
+    jd.set_reg(0.8, 1.2, 50.0, W=W, prior=prior)
+    g = jd.loss_grad()
+    params = {kk: q[kk] for kk in ('h', 'mean', 'a', 'c_x', 'c_y', 'dx', 'dy')}
+    L, go = sm.deconv_loss_grad(params, dict(alpha=p['alpha']), p['psf'], p['data'], p['weight'], W, n, k,
+                                dict(lam_scales=0.8, lam_hf=1.2, lam_pos=50.0, prior=prior))
+    assert abs(g['loss'] - L) <= 1e-5 * abs(L), (g['loss'], L)
+    for nm in ('h', 'mean', 'a', 'c_x', 'c_y', 'dx', 'dy'):
+        ref = go[nm].reshape(-1)
+        np.testing.assert_allclose(g[nm].reshape(-1), ref, rtol=2e-5, atol=2e-5 * np.abs(ref).max(), err_msg=nm)
+    # model image
+    fin = jd.get()
+    t = lambda v: torch.tensor(v, dtype=torch.float64)
+    m = sm.deconv_model(t(q['h']).reshape(nu, nu), t(q['mean']), t(q['a']), t(q['c_x']), t(q['c_y']), t(q['dx']), t(q['dy']),
+                        t(p['alpha']), t(p['psf']), n, k).numpy()
+    np.testing.assert_allclose(fin['model'], m, rtol=1e-5, atol=1e-5 * np.abs(m).max())
+    jd.close()
+
+
+def test_deconv_fit_parity_and_photometry_consistency(cuda_device):
+    """15 AdaBelief iterations (roi_modelling.py:326-335 options) against the float64 oracle; and with
+    M = 1, h fixed at 0, c fixed, the engine reproduces the K2 photometry model exactly."""
+    from lightcurver_b200.processes.roi_modelling import JointDeconvolution
+    from lightcurver_b200 import engine
+    from oracle import starred_model as sm
+    E, n, k, M = 3, 16, 2, 2
+    p = _problem(E, n, k, M, 12, seed=2, alpha_on=False)
+    nu = n * k
+    T = 15
+    a0 = (p['a'] * 0.9).astype(np.float32)
+    h0 = (1e-3 * np.random.default_rng(0).standard_normal(nu * nu)).astype(np.float32)
+    jd = JointDeconvolution(p['data'], p['weight'], p['psf'], k, M)
+    jd.set_params(h=h0, mean=np.zeros(E), a=a0, c_x=p['c_x'], c_y=p['c_y'], dx=np.zeros(E), dy=np.zeros(E), alpha=p['alpha'])
+    W = jd.noise_weights()
+    Wo = sm.deconv_noise_weights(p['psf'], p['weight'], np.zeros(E), np.zeros(E), p['alpha'], n, k).numpy()
+    np.testing.assert_allclose(W, Wo, rtol=1e-4, atol=1e-6 * Wo.max())
+    jd.set_reg(1.0, 1.0, 100.0, W=W)
+    hist = jd.run(T, lr=1e-4, schedule=False)
+    fin = jd.get()
+    params = dict(h=h0, mean=np.zeros(E), a=a0, c_x=p['c_x'], c_y=p['c_y'], dx=np.zeros(E), dy=np.zeros(E))
+    ref = sm.fit_deconv(params, dict(alpha=p['alpha']), p['psf'], p['data'], p['weight'], W, n, k,
+                        dict(lam_scales=1.0, lam_hf=1.0, lam_pos=100.0), T, lr=1e-4, schedule=False, dtype=torch.float64)
+    np.testing.assert_allclose(hist, ref['loss_hist'], rtol=1e-5)
+    np.testing.assert_allclose(fin['a'].reshape(E, M), ref['a'], rtol=1e-4)
+    assert np.abs(fin['h'] - ref['h'].reshape(-1)).max() <= 1e-3 * np.abs(p['h']).max()
+    np.testing.assert_allclose(fin['dx'], ref['dx'], atol=1e-4)
+    np.testing.assert_allclose(fin['c_x'], ref['c_x'], atol=1e-4)
+    jd.close()
+    # M = 1 special case == K2 model (P == nu)
+    E2 = 2
+    p2 = _problem(E2, n, k, 1, n, seed=9, alpha_on=False)
+    jd2 = JointDeconvolution(p2['data'], p2['weight'], p2['psf'], k, 1)
+    jd2.set_params(h=np.zeros(nu * nu), mean=np.zeros(E2), a=p2['a'], c_x=np.zeros(1), c_y=np.zeros(1), dx=p2['dx'], dy=p2['dy'],
+                   alpha=np.zeros(E2), free_h=False, free_c=False, free_mean=False)
+    m3 = jd2.get()['model']
+    ph = engine.phot_fit_batch(p2['data'], p2['weight'], p2['psf'], np.arange(E2, dtype=np.int32), p2['a'].reshape(-1), k, 0,
+                               dx0=p2['dx'], dy0=p2['dy'])
+    np.testing.assert_allclose(m3, p2['data'] - ph['residuals'], rtol=1e-5, atol=1e-5 * np.abs(m3).max())
+    jd2.close()
+
+
+def test_do_one_star_reference_defaults(cuda_device):
+    """The reference's own API-contract test (tests/test_starred_calls/test_starred_calls.py:20-64) calls
+    do_one_star_forward_modelling with its DEFAULT flags (starlet_global_background=True)."""
+    from lightcurver_b200.processes.star_photometry import do_one_star_forward_modelling
+    x, y = np.meshgrid(np.arange(-8, 8), np.arange(-8, 8))
+    gauss = np.exp(-0.1 * (x ** 2 + y ** 2))
+    rng = np.random.default_rng(0)
+    data = 0.1 * rng.random((5, 16, 16)) + np.repeat(gauss[None, :, :], repeats=5, axis=0)
+    noisemap = 0.1 * np.ones((5, 16, 16))
+    psf = np.repeat(gauss[None, :, :], repeats=5, axis=0)
+    result = do_one_star_forward_modelling(data, noisemap, psf, 1, 50)
+    assert isinstance(result['scale'], float) and result['scale'] > 0
+    assert result['fluxes'].shape == (5,) and result['fluxes_uncertainties'].shape == (5,)
+    assert isinstance(result['chi2'], float) and result['chi2'] >= 0
+    assert len(result['loss_curve']) == 50 and result['residuals'].shape == data.shape
+    assert result['chi2_per_frame'].shape == (5,)
+    assert result['starlet_background'].shape == (16, 16) and result['deconvolved_image'].shape == (16, 16)
+    assert np.isfinite(result['fluxes']).all() and np.isfinite(result['fluxes_uncertainties']).all()

@@ -63,7 +63,11 @@ def _stage2_setup(F, N, n, k, seed):
     z = np.zeros((F, N))
     W = np.stack([sm.psf_noise_weights(weight[f], a0[f], z[f], z[f], n, k).numpy() for f in range(F)]).astype(np.float32)
     s_fixed = sm.moffat_image(moffat[:, 0], moffat[:, 1], moffat[:, 2], moffat[:, 3], n, k).numpy()
-    return data, weight, a0, off, moffat, z, W, s_fixed
+    # Start from a small random grid, not from b = 0: after one sign-like AdaBelief step from 0 the grid is
+    # +-c on plateaus whose starlet coefficients are EXACTLY zero in exact arithmetic, so sign(alpha) there
+    # is decided by the rounding of the 5-tap sum (summation order), in any implementation.
+    b0 = (1e-4 * np.random.default_rng(seed).standard_normal((F, n * k, n * k))).astype(np.float32)
+    return data, weight, a0, off, moffat, z, W, s_fixed, b0
 
 
 def test_psf_stage2_fit_parity_short(cuda_device):
@@ -73,11 +77,11 @@ def test_psf_stage2_fit_parity_short(cuda_device):
     from lightcurver_b200 import engine
     from oracle import starred_model as sm
     n, k, N, F, T = 32, 2, 6, 2, 12
-    data, weight, a0, off, moffat, z, W, s_fixed = _stage2_setup(F, N, n, k, 7)
+    data, weight, a0, off, moffat, z, W, s_fixed, b0 = _stage2_setup(F, N, n, k, 7)
     nu = n * k
-    out = engine.psf_fit_batch(_flat(data), _flat(weight), off, k, moffat, a0.ravel(), W=W,
+    out = engine.psf_fit_batch(_flat(data), _flat(weight), off, k, moffat, a0.ravel(), W=W, background0=b0,
                                n_iter_analytic=0, n_iter_adabelief=T, lr=2e-5, lam_scales=1.0, lam_hf=1.0)
-    ref = sm.fit_psf_stage2(s_fixed, np.zeros((F, nu, nu)), a0, z, z, data, weight, W, n, k, T, lr=2e-5,
+    ref = sm.fit_psf_stage2(s_fixed, b0, a0, z, z, data, weight, W, n, k, T, lr=2e-5,
                             lam_scales=1.0, lam_hf=1.0, dtype=torch.float64)
     np.testing.assert_allclose(out['a'].reshape(F, N), ref['a'], rtol=1e-4)
     np.testing.assert_allclose(out['loss_hist'], ref['loss_hist'], rtol=1e-5)
@@ -98,13 +102,13 @@ def test_psf_stage2_fit_parity_long(cuda_device):
     from lightcurver_b200 import engine
     from oracle import starred_model as sm
     n, k, N, F, T = 32, 2, 6, 2, 200
-    data, weight, a0, off, moffat, z, W, s_fixed = _stage2_setup(F, N, n, k, 7)
+    data, weight, a0, off, moffat, z, W, s_fixed, b0 = _stage2_setup(F, N, n, k, 7)
     nu = n * k
-    out = engine.psf_fit_batch(_flat(data), _flat(weight), off, k, moffat, a0.ravel(), W=W,
+    out = engine.psf_fit_batch(_flat(data), _flat(weight), off, k, moffat, a0.ravel(), W=W, background0=b0,
                                n_iter_analytic=0, n_iter_adabelief=T, lr=2e-5, lam_scales=1.0, lam_hf=1.0)
     kw = dict(lr=2e-5, lam_scales=1.0, lam_hf=1.0)
-    r64 = sm.fit_psf_stage2(s_fixed, np.zeros((F, nu, nu)), a0, z, z, data, weight, W, n, k, T, dtype=torch.float64, **kw)
-    r32 = sm.fit_psf_stage2(s_fixed, np.zeros((F, nu, nu)), a0, z, z, data, weight, W, n, k, T, dtype=torch.float32, **kw)
+    r64 = sm.fit_psf_stage2(s_fixed, b0, a0, z, z, data, weight, W, n, k, T, dtype=torch.float64, **kw)
+    r32 = sm.fit_psf_stage2(s_fixed, b0, a0, z, z, data, weight, W, n, k, T, dtype=torch.float32, **kw)
     np.testing.assert_allclose(out['a'].reshape(F, N), r64['a'], rtol=1e-4)
     np.testing.assert_allclose(out['loss_hist'], r64['loss_hist'], rtol=1e-3)
     peak = s_fixed.max()
