@@ -191,6 +191,8 @@ int lcb_deconv_destroy(void* handle);
 /* FP32 FMA micro-benchmark: runs `iters` dependent-chain FFMA loops on every SM and returns the
  * achieved TFLOP/s in *tflops (used as the measured roofline denominator by bench.py). */
 int lcb_fp32_peak(int iters, float* tflops, float* ms);
+/* same with three-register FFMAs in an 8x8 outer-product pattern (what a stencil inner loop issues) */
+int lcb_fp32_peak_rrr(int iters, float* tflops, float* ms);
 
 /* Per-kernel device timing: after lcb_profile_enable(1) every kernel launched by the library is
  * bracketed by CUDA events on its launch stream; lcb_profile_summary() synchronises on them and

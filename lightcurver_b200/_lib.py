@@ -155,6 +155,16 @@ def set_conventions(**kw):
     check(lib.lcb_conventions_set(C.byref(c)), 'lcb_conventions_set')
 
 
+lib.lcb_fp32_peak_rrr.argtypes = [C.c_int, c_fp, c_fp]
+
+
+def fp32_peak_rrr(iters=4096):
+    require_device()
+    t, ms = C.c_float(0), C.c_float(0)
+    check(lib.lcb_fp32_peak_rrr(iters, C.byref(t), C.byref(ms)), 'lcb_fp32_peak_rrr')
+    return float(t.value), float(ms.value)
+
+
 def fp32_peak(iters=4096):
     require_device()
     t, ms = C.c_float(0), C.c_float(0)

@@ -149,6 +149,59 @@ __global__ void __launch_bounds__(1024) k_fp32_peak(int iters, float* sink) {
     if (s == 123.456f) sink[0] = s;
 }
 
+// Same measurement with register-operand FFMAs in an 8x8 outer-product pattern (the shape of a stencil /
+// SGEMM inner loop: acc[i][j] += a[i] * b[j], three register sources per FFMA, no immediates).
+__global__ void __launch_bounds__(256) k_fp32_peak_rrr(int iters, const float* in, float* sink) {
+    float a[8], b[8], acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i] = in[i + (threadIdx.x & 7)]; b[i] = in[8 + i + (threadIdx.x & 3)]; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += acc[i][j];
+    if (s == 123.456f) sink[0] = s;
+}
+
+extern "C" int lcb_fp32_peak_rrr(int iters, float* tflops, float* ms_out) {
+    LCB_REQUIRE(iters > 0 && tflops != nullptr, "lcb_fp32_peak_rrr: bad arguments");
+    int dev = 0, sms = 0;
+    LCB_CUDA(cudaGetDevice(&dev));
+    LCB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    float *sink = nullptr, *in = nullptr;
+    LCB_CUDA(cudaMalloc(&sink, 4));
+    LCB_CUDA(cudaMalloc(&in, 64 * 4));
+    float h[64];
+    for (int i = 0; i < 64; ++i) h[i] = 1e-3f * (float)(i + 1);
+    LCB_CUDA(cudaMemcpy(in, h, sizeof(h), cudaMemcpyHostToDevice));
+    cudaEvent_t e0, e1;
+    LCB_CUDA(cudaEventCreate(&e0));
+    LCB_CUDA(cudaEventCreate(&e1));
+    const int grid = sms * 8;
+    k_fp32_peak_rrr<<<grid, 256>>>(iters / 8 + 1, in, sink);
+    LCB_CUDA(cudaEventRecord(e0));
+    k_fp32_peak_rrr<<<grid, 256>>>(iters, in, sink);
+    LCB_CUDA(cudaEventRecord(e1));
+    LCB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    LCB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 64.0 * (double)iters * 256.0 * (double)grid;
+    *tflops = (float)(flops / (ms * 1e-3) / 1e12);
+    if (ms_out) *ms_out = ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink); cudaFree(in);
+    return LCB_OK;
+}
+
 extern "C" int lcb_fp32_peak(int iters, float* tflops, float* ms_out) {
     LCB_REQUIRE(iters > 0 && tflops != nullptr, "lcb_fp32_peak: bad arguments");
     int dev = 0, sms = 0;

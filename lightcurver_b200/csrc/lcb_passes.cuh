@@ -10,15 +10,17 @@
 #pragma once
 #include "lcb_common.cuh"
 
-template <int K, int G>
+template <int K, int G, int OBV = 4>
 struct LcbPass {
     static constexpr int GE = G + K - 1;   // effective taps after folding the k-box
-    static constexpr int OB = 4;           // outputs per thread-task along the contracted axis
+    static constexpr int OB = OBV;         // outputs per thread-task along the contracted axis
     static constexpr int NR = GE + K * (OB - 1);
 };
 
 // pass 1: s (nu x nu, leading dim lds, row-major, shared or global) -> Vg, Vd stored [u][Y] (ld ldv)
-template <int K, int G>
+// HALO = true: the caller guarantees that every input index touched lies inside zero-filled halos
+// (no bounds predicates, loads use immediate offsets from one base address).
+template <int K, int G, bool HALO = false>
 __device__ __forceinline__ void lcb_pass1(const float* __restrict__ s, int lds, int nu, int n, int icy,
                                           const float* __restrict__ ey_s, const float* __restrict__ dey_s,
                                           float* __restrict__ Vg, float* __restrict__ Vd, int ldv,
@@ -38,7 +40,7 @@ __device__ __forceinline__ void lcb_pass1(const float* __restrict__ s, int lds, 
 #pragma unroll
         for (int r = 0; r < P::NR; ++r) {
             const int v = vbase + r;
-            const float sv = (v >= 0 && v < nu) ? s[v * lds + u] : 0.f;
+            const float sv = (HALO || (v >= 0 && v < nu)) ? s[v * lds + u] : 0.f;
 #pragma unroll
             for (int y = 0; y < P::OB; ++y) {
                 const int p = r - K * y;
@@ -53,12 +55,12 @@ __device__ __forceinline__ void lcb_pass1(const float* __restrict__ s, int lds, 
 
 // pass 2: V{g,d} [u][Y] -> (M0, Mx, My)[Y][X] handed to consume(Y, X, m0, mx, my).
 //   m0 = sum ex*Vg, mx = sum dex*Vg (d/dcx), my = sum ex*Vd (d/dcy); c in upsampled px.
-template <int K, int G, typename F>
+template <int K, int G, int OBV = 4, bool HALO = false, typename F>
 __device__ __forceinline__ void lcb_pass2(const float* __restrict__ Vg, const float* __restrict__ Vd, int ldv,
                                           int nu, int n, int icx,
                                           const float* __restrict__ ex_s, const float* __restrict__ dex_s,
                                           int tid, int nthreads, F&& consume) {
-    using P = LcbPass<K, G>;
+    using P = LcbPass<K, G, OBV>;
     float ex[P::GE], dex[P::GE];
 #pragma unroll
     for (int p = 0; p < P::GE; ++p) { ex[p] = ex_s[p]; dex[p] = dex_s[p]; }
@@ -73,7 +75,7 @@ __device__ __forceinline__ void lcb_pass2(const float* __restrict__ Vg, const fl
 #pragma unroll
         for (int r = 0; r < P::NR; ++r) {
             const int u = ubase + r;
-            const bool ok = (u >= 0 && u < nu);
+            const bool ok = HALO || (u >= 0 && u < nu);
             const float vg = ok ? Vg[u * ldv + Y] : 0.f;
             const float vd = ok ? Vd[u * ldv + Y] : 0.f;
 #pragma unroll
@@ -100,30 +102,30 @@ __device__ __forceinline__ int lcb_floordiv(int a, int b) { return (a >= 0) ? a 
 //
 // pass 2^T: r stored [X][Y] (ld ldr) -> Vbar[Y][u] (ld ldb):  Vbar[Y][u] = sum_X ex[u'-K X] r[Y][X]
 // lanes <-> Y.
-template <int K, int G>
+template <int K, int G, int OBV = 4, bool HALO = false>
 __device__ __forceinline__ void lcb_pass2T(const float* __restrict__ rT, int ldr, int nu, int n, int icx,
                                            const float* __restrict__ ex_s, float* __restrict__ Vbar, int ldb,
                                            int tid, int nthreads) {
-    using P = LcbPass<K, G>;
+    using P = LcbPass<K, G, OBV>;
     constexpr int UB = K * P::OB;
     constexpr int ILO = -((P::GE - 1 + K - 1) / K);
     float ex[P::GE];
 #pragma unroll
     for (int p = 0; p < P::GE; ++p) ex[p] = ex_s[p];
     const int off = icx + G / 2;
-    const int bmin = lcb_floordiv(off, UB);
-    const int nb = lcb_floordiv(nu - 1 + off, UB) - bmin + 1;
+    const int S0 = K * lcb_floordiv(off, K);            // block grid origin: <= off, multiple of K
+    const int nb = (nu + UB - 1) / UB;
     for (int task = tid; task < n * nb; task += nthreads) {
         const int Y = task % n;
-        const int U0 = UB * (bmin + task / n);
-        const int XB0 = U0 / K;                      // exact: U0 is a multiple of K (may be negative)
+        const int U0 = S0 + UB * (task / n);
+        const int XB0 = lcb_floordiv(U0, K);
         float acc[UB];
 #pragma unroll
         for (int j = 0; j < UB; ++j) acc[j] = 0.f;
 #pragma unroll
         for (int i = ILO; i < P::OB; ++i) {
             const int X = XB0 + i;
-            const float rv = (X >= 0 && X < n) ? rT[X * ldr + Y] : 0.f;
+            const float rv = (HALO || (X >= 0 && X < n)) ? rT[X * ldr + Y] : 0.f;
 #pragma unroll
             for (int j = 0; j < UB; ++j) {
                 const int p = j - K * i;
@@ -136,10 +138,32 @@ __device__ __forceinline__ void lcb_pass2T(const float* __restrict__ rT, int ldr
             if (u >= 0 && u < nu) Vbar[Y * ldb + u] = acc[j];
         }
     }
+    if (nu % UB == 0 && K > 1) {                        // trailing columns (see lcb_pass1T)
+        const int nt = off - S0;
+        const int Xb = (S0 + nb * UB) / K;
+        for (int task = tid; task < n * nt; task += nthreads) {
+            const int Y = task % n, t = task / n;
+            float acc = 0.f;
+#pragma unroll
+            for (int tt = 0; tt < K - 1; ++tt) {
+                if (tt == t) {
+#pragma unroll
+                    for (int q = 0; q < (P::GE + K - 1) / K; ++q) {
+                        const int p = tt + K * q, X = Xb - q;
+                        if (p < P::GE && (HALO || (X >= 0 && X < n))) acc = fmaf(ex[p], rT[X * ldr + Y], acc);
+                    }
+                }
+            }
+            Vbar[Y * ldb + nu - nt + t] = acc;
+        }
+    }
 }
 
 // pass 1^T: Vbar[Y][u] (ld ldb) -> emit(v, u, sum_Y ey[v'-K Y] Vbar[Y][u]);  lanes <-> u.
-template <int K, int G, typename F>
+// The block grid starts at V0 = K*floor(off/K) (any multiple of K keeps p = j - K*i static), so
+// nu/UB blocks cover all but at most K-1 trailing rows; those are finished by a short second loop
+// instead of a whole extra block per column (keeps the task count a multiple of the CTA size).
+template <int K, int G, bool HALO = false, typename F>
 __device__ __forceinline__ void lcb_pass1T(const float* __restrict__ Vbar, int ldb, int nu, int n, int icy,
                                            const float* __restrict__ ey_s, int tid, int nthreads, F&& emit) {
     using P = LcbPass<K, G>;
@@ -149,19 +173,19 @@ __device__ __forceinline__ void lcb_pass1T(const float* __restrict__ Vbar, int l
 #pragma unroll
     for (int p = 0; p < P::GE; ++p) ey[p] = ey_s[p];
     const int off = icy + G / 2;
-    const int bmin = lcb_floordiv(off, UB);
-    const int nb = lcb_floordiv(nu - 1 + off, UB) - bmin + 1;
+    const int S0 = K * lcb_floordiv(off, K);            // <= off, multiple of K
+    const int nb = (nu + UB - 1) / UB;                  // blocks covering v' in [S0, S0 + nb*UB)
     for (int task = tid; task < nu * nb; task += nthreads) {
         const int u = task % nu;
-        const int V0 = UB * (bmin + task / nu);
-        const int YB0 = V0 / K;
+        const int V0 = S0 + UB * (task / nu);
+        const int YB0 = lcb_floordiv(V0, K);
         float acc[UB];
 #pragma unroll
         for (int j = 0; j < UB; ++j) acc[j] = 0.f;
 #pragma unroll
         for (int i = ILO; i < P::OB; ++i) {
             const int Y = YB0 + i;
-            const float bv = (Y >= 0 && Y < n) ? Vbar[Y * ldb + u] : 0.f;
+            const float bv = (HALO || (Y >= 0 && Y < n)) ? Vbar[Y * ldb + u] : 0.f;
 #pragma unroll
             for (int j = 0; j < UB; ++j) {
                 const int p = j - K * i;
@@ -172,6 +196,27 @@ __device__ __forceinline__ void lcb_pass1T(const float* __restrict__ Vbar, int l
         for (int j = 0; j < UB; ++j) {
             const int v = V0 + j - off;
             if (v >= 0 && v < nu) emit(v, u, acc[j]);
+        }
+    }
+    // trailing rows v' = S0 + nb*UB + t, t < K-1 (only when nu % UB == 0): v' - t is a multiple of K, so
+    // the tap index p = t + K*q stays a compile-time constant.
+    if (nu % UB == 0 && K > 1) {
+        const int nt = off - S0;                        // 0 .. K-1 uncovered rows
+        const int Yb = (S0 + nb * UB) / K;              // exact
+        for (int task = tid; task < nu * nt; task += nthreads) {
+            const int u = task % nu, t = task / nu;
+            float acc = 0.f;
+#pragma unroll
+            for (int tt = 0; tt < K - 1; ++tt) {
+                if (tt == t) {
+#pragma unroll
+                    for (int q = 0; q < (P::GE + K - 1) / K; ++q) {
+                        const int p = tt + K * q, Y = Yb - q;
+                        if (p < P::GE && (HALO || (Y >= 0 && Y < n))) acc = fmaf(ey[p], Vbar[Y * ldb + u], acc);
+                    }
+                }
+            }
+            emit(nu - nt + t, u, acc);
         }
     }
 }

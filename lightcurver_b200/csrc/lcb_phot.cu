@@ -23,11 +23,12 @@ struct PhotArgs {
 
 #define PHOT_THREADS 256
 
-template <int K, int G>
-__global__ void __launch_bounds__(PHOT_THREADS) k_phot_fit(PhotArgs A) {
+// NS > 0: compile-time stamp side (no integer divisions in the passes); NS == 0: runtime sizes.
+template <int K, int G, int NS>
+__global__ void __launch_bounds__(PHOT_THREADS, (NS > 0 ? 3 : 1)) k_phot_fit(PhotArgs A) {
     using P = LcbPass<K, G>;
     extern __shared__ __align__(16) float sm[];
-    const int n = A.n, nu = A.nu, tid = threadIdx.x;
+    const int n = (NS > 0) ? NS : A.n, nu = (NS > 0) ? NS * K : A.nu, tid = threadIdx.x;
     const int ldv = n + 1, ldt = n + 1;
     const int item = blockIdx.x;
     // shared layout
@@ -155,20 +156,22 @@ __global__ void __launch_bounds__(PHOT_THREADS) k_phot_fit(PhotArgs A) {
     }
 }
 
-template <int K, int G>
+template <int K, int G, int NS>
 static int launch_phot(const PhotArgs& A, size_t smem, cudaStream_t st) {
-    LCB_CUDA(cudaFuncSetAttribute(k_phot_fit<K, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    { LcbProfScope ps("k_phot_fit", st); k_phot_fit<K, G><<<A.B, PHOT_THREADS, smem, st>>>(A); }
+    LCB_CUDA(cudaFuncSetAttribute(k_phot_fit<K, G, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { LcbProfScope ps("k_phot_fit", st); k_phot_fit<K, G, NS><<<A.B, PHOT_THREADS, smem, st>>>(A); }
     LCB_CUDA(cudaGetLastError());
     return LCB_OK;
 }
 
 static int dispatch_phot(const PhotArgs& A, size_t smem, cudaStream_t st) {
     const int G = A.cv.G;
-#define CASE(KK, GG) if (A.k == KK && G == GG) return launch_phot<KK, GG>(A, smem, st);
+    if (G == 12 && A.k == 2 && A.n == 32) return launch_phot<2, 12, 32>(A, smem, st);
+    if (G == 12 && A.k == 2 && A.n == 16) return launch_phot<2, 12, 16>(A, smem, st);
+    if (G == 12 && A.k == 1 && A.n == 32) return launch_phot<1, 12, 32>(A, smem, st);
+#define CASE(KK, GG) if (A.k == KK && G == GG) return launch_phot<KK, GG, 0>(A, smem, st);
     CASE(1, 12) CASE(2, 12) CASE(3, 12) CASE(4, 12)
-    CASE(1, 8) CASE(2, 8) CASE(3, 8)
-    CASE(1, 16) CASE(2, 16) CASE(3, 16)
+    CASE(2, 8) CASE(2, 16)
 #undef CASE
     lcb_set_error("photometry: unsupported (subsampling_factor=%d, gauss_taps=%d)", A.k, G);
     return LCB_ERR_ARG;

@@ -6,7 +6,9 @@
 
 size_t lcb_psf_fit_smem_small(int n, int nu, int Nmax);
 size_t lcb_psf_lm_smem_small(int n, int nu, int Nmax);
-int lcb_psf_fit_dispatch(const PsfArgs& A, size_t smem, cudaStream_t st);
+int lcb_psf_fit_dispatch(const PsfArgs& A, size_t smem, bool fast, cudaStream_t st);
+size_t lcb_psf_fit_smem_fast_extra(int n, int nu, int J);
+bool lcb_psf_fit_has_fast(int n, int k, int G);
 int lcb_psf_lm_dispatch(const PsfArgs& A, size_t smem, cudaStream_t st);
 int lcb_moffat_image_launch(const PsfArgs& A, cudaStream_t st);
 int lcb_noise_var_dispatch(const PsfArgs& A, cudaStream_t st);
@@ -74,7 +76,9 @@ static int psf_run_device(const lcb_psf_batch* in, const lcb_psf_opts* opt, lcb_
                 fit_small > lm_small ? fit_small : lm_small, maxsm);
     const bool fit_planes_sm = fit_small + (size_t)7 * pp * 4 <= (size_t)maxsm;
     const bool lm_planes_sm = lm_small + (size_t)5 * pp * 4 <= (size_t)maxsm;
-    const size_t wpf = (size_t)(J + 7) * pp;                 // floats per frame of workspace
+    const size_t wpf = (size_t)(J + 7) * pp + (size_t)2 * Nmax * n * n;   // floats per frame of workspace
+    const bool fit_fast = lcb_psf_fit_has_fast(n, k, lcb_conv().gauss_taps) &&
+                          fit_small + lcb_psf_fit_smem_fast_extra(n, nu, J) <= (size_t)maxsm;
     const int chunk = F < 1184 ? F : 1184;                   // 8 waves of 148 CTAs
 
     DevTemp work(st), sfix(st), Wtmp(st), tabd(st);
@@ -136,7 +140,9 @@ static int psf_run_device(const lcb_psf_batch* in, const lcb_psf_opts* opt, lcb_
                                                (float*)work.p, wpf, st))) return rc;
         }
         A.planes_in_smem = fit_planes_sm;
-        if ((rc = lcb_psf_fit_dispatch(A, fit_small + (fit_planes_sm ? (size_t)7 * pp * 4 : 0), st))) return rc;
+        const size_t fit_smem = fit_fast ? fit_small + lcb_psf_fit_smem_fast_extra(n, nu, J)
+                                         : fit_small + (fit_planes_sm ? (size_t)7 * pp * 4 : 0);
+        if ((rc = lcb_psf_fit_dispatch(A, fit_smem, fit_fast, st))) return rc;
     }
     (void)sumN;
     return LCB_OK;

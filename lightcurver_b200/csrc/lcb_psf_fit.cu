@@ -74,12 +74,182 @@ __device__ __forceinline__ float atrous_adj_line(const float* __restrict__ base,
     return acc;
 }
 
+
+// ---------------------------------------------------------------- fast starlet regulariser
+// Compile-time grid side NU (32 or 64, PSF_THREADS % NU == 0): thread <-> (column u, ROWS consecutive rows),
+// no integer division, clamped indices hoisted, sign(alpha_j) kept as int8 planes in shared memory
+// (t_j = lambda_j W_j sign(alpha_j) is rebuilt from W, fetched one phase ahead), and a branch-free adjoint:
+// H^T y = zero-extended symmetric stencil + the out-of-range taps folded onto the two border pixels
+// (prefix / suffix sums of D and 2D elements).  The folded sums come from 8-element chunk
+// sums that the PRODUCING phase leaves in shared memory (registers for the column direction, three
+// shuffles per row for the row direction), so no thread ever walks a line serially.
+// Returns the per-thread partial of the regulariser; leaves g_0 = d reg / d b in C0 (after a barrier).
+// aux: [2*GROUPS*NU + NU*NU/8 + 2*NU] floats of shared scratch.
+template <int NU>
+__device__ __forceinline__ float starlet_reg_fast(const float* __restrict__ Bp, float* __restrict__ C0,
+                                                  float* __restrict__ C1, signed char* __restrict__ sg,
+                                                  float* __restrict__ aux,
+                                                  const float* __restrict__ Wf, float lam_hf, float lam_scales,
+                                                  int J, int tid) {
+    constexpr int GROUPS = PSF_THREADS / NU;
+    constexpr int ROWS = NU / GROUPS;
+    static_assert(ROWS == 8 || ROWS == 2, "chunk logic written for 8-row (NU=64) and 2-row (NU=32) groups");
+    constexpr int CH = 8;                                // chunk length of the row-direction sums
+    constexpr int PP = NU * NU;
+    const float h0 = 1.f / 16.f, h1 = 4.f / 16.f, h2 = 6.f / 16.f;
+    const int u = tid % NU, rg = tid / NU, v0 = rg * ROWS;
+    float* chkC = aux;                                   // [GROUPS][NU] sums of the ROWS rows of a group
+    float* chkR = chkC + GROUPS * NU;                    // [NU][NU/CH]  sums of CH consecutive columns
+    float* ext = chkR + NU * (NU / CH);                  // [NU][2]      folded-tap extras of the row pass
+    float reg = 0.f;
+    float wreg[ROWS];
+    for (int j = 0; j < J; ++j) {
+        const int D = 1 << j;
+        const float* cur = (j == 0) ? Bp : C0;
+        const float lam = (j == 0) ? lam_hf : lam_scales;
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) wreg[r] = lam * (Wf ? __ldg(Wf + (size_t)j * PP + (v0 + r) * NU + u) : 1.f);
+        const int um2 = max(u - 2 * D, 0), um1 = max(u - D, 0), up1 = min(u + D, NU - 1), up2 = min(u + 2 * D, NU - 1);
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            const float* row = cur + (v0 + r) * NU;
+            C1[(v0 + r) * NU + u] = h0 * (row[um2] + row[up2]) + h1 * (row[um1] + row[up1]) + h2 * row[u];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            const int v = v0 + r, idx = v * NU + u;
+            const int vm2 = max(v - 2 * D, 0), vm1 = max(v - D, 0), vp1 = min(v + D, NU - 1), vp2 = min(v + 2 * D, NU - 1);
+            const float nxt = h0 * (C1[vm2 * NU + u] + C1[vp2 * NU + u]) + h1 * (C1[vm1 * NU + u] + C1[vp1 * NU + u]) + h2 * C1[idx];
+            const float al = cur[idx] - nxt;
+            reg = fmaf(wreg[r], fabsf(al), reg);
+            sg[j * PP + idx] = (al > 0.f) ? 1 : (al < 0.f) ? -1 : 0;
+            C0[idx] = nxt;
+        }
+        __syncthreads();
+    }
+    // ---- backward sweep.  wreg holds lambda W of scale J-1.
+    // prefix(m) / suffix(m) of a line from chunk sums (m is a power of two; chunks of c elements)
+    for (int j = J - 1; j >= 0; --j) {
+        const int D = 1 << j;
+        const int m1 = min(D, NU), m2 = min(2 * D, NU);
+        float tj[ROWS];
+        // (1) q = g_{j+1} - t_j  (+ the row-pass border extras of the previous scale), column chunk sums
+        float csum = 0.f;
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            const int v = v0 + r, idx = v * NU + u;
+            tj[r] = wreg[r] * (float)sg[j * PP + idx];
+            float g = 0.f;
+            if (j != J - 1) {
+                g = C0[idx];
+                if (u == 0) g += ext[v * 2];
+                if (u == NU - 1) g += ext[v * 2 + 1];
+            }
+            const float q = g - tj[r];
+            C0[idx] = q;
+            csum += q;
+        }
+        chkC[rg * NU + u] = csum;
+        if (j > 0) {
+            const float lamn = (j - 1 == 0) ? lam_hf : lam_scales;
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) wreg[r] = lamn * (Wf ? __ldg(Wf + (size_t)(j - 1) * PP + (v0 + r) * NU + u) : 1.f);
+        }
+        __syncthreads();
+        // (2) Hcol^T along v (fixed u) -> C1, with the folded taps on rows 0 and NU-1, + row chunk sums
+        float c1v[ROWS];
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            const int v = v0 + r;
+            float acc = h2 * C0[v * NU + u];
+            if (v - D >= 0) acc = fmaf(h1, C0[(v - D) * NU + u], acc);
+            if (v + D < NU) acc = fmaf(h1, C0[(v + D) * NU + u], acc);
+            if (v - 2 * D >= 0) acc = fmaf(h0, C0[(v - 2 * D) * NU + u], acc);
+            if (v + 2 * D < NU) acc = fmaf(h0, C0[(v + 2 * D) * NU + u], acc);
+            c1v[r] = acc;
+        }
+        if (rg == 0 || rg == GROUPS - 1) {
+            // sums of the first / last m rows of column u
+            float s1 = 0.f, s2 = 0.f;
+            const bool top = (rg == 0);
+            if (m2 >= ROWS) {
+                for (int g = 0; g < m2 / ROWS; ++g) {
+                    const float c = chkC[(top ? g : GROUPS - 1 - g) * NU + u];
+                    s2 += c;
+                    if (g < m1 / ROWS) s1 += c;
+                }
+                if (m1 < ROWS) for (int i = 0; i < m1; ++i) s1 += C0[(top ? i : NU - 1 - i) * NU + u];
+            } else {
+                for (int i = 0; i < m2; ++i) { const float y = C0[(top ? i : NU - 1 - i) * NU + u]; s2 += y; if (i < m1) s1 += y; }
+            }
+            const float e = h0 * s2 + h1 * s1;
+            if (top) c1v[0] += e;
+            if (rg == GROUPS - 1) {
+                if (GROUPS == 1 && top) {                 // (never: GROUPS >= 8) keeps both borders correct
+                }
+                if (!top) c1v[ROWS - 1] += e;
+            }
+        }
+        if (GROUPS == 1) { /* unreachable for NU in {32, 64} */ }
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            C1[(v0 + r) * NU + u] = c1v[r];
+            float cs = c1v[r];
+            cs += __shfl_xor_sync(0xffffffffu, cs, 1);
+            cs += __shfl_xor_sync(0xffffffffu, cs, 2);
+            cs += __shfl_xor_sync(0xffffffffu, cs, 4);
+            if ((u & (CH - 1)) == 0) chkR[(v0 + r) * (NU / CH) + (u >> 3)] = cs;
+        }
+        __syncthreads();
+        // (3) Hrow^T along u (fixed v) + t_j -> C0 ; threads 0..2NU-1 also prepare the folded extras
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            const float* row = C1 + (v0 + r) * NU;
+            float acc = h2 * row[u];
+            if (u - D >= 0) acc = fmaf(h1, row[u - D], acc);
+            if (u + D < NU) acc = fmaf(h1, row[u + D], acc);
+            if (u - 2 * D >= 0) acc = fmaf(h0, row[u - 2 * D], acc);
+            if (u + 2 * D < NU) acc = fmaf(h0, row[u + 2 * D], acc);
+            C0[(v0 + r) * NU + u] = tj[r] + acc;
+        }
+        if (tid < 2 * NU) {
+            const int v = tid % NU;
+            const bool left = tid < NU;
+            const float* row = C1 + v * NU;
+            float s1 = 0.f, s2 = 0.f;
+            if (m2 >= CH) {
+                for (int q = 0; q < m2 / CH; ++q) {
+                    const float c = chkR[v * (NU / CH) + (left ? q : NU / CH - 1 - q)];
+                    s2 += c;
+                    if (q < m1 / CH) s1 += c;
+                }
+                if (m1 < CH) for (int i = 0; i < m1; ++i) s1 += row[left ? i : NU - 1 - i];
+            } else {
+                for (int i = 0; i < m2; ++i) { const float y = row[left ? i : NU - 1 - i]; s2 += y; if (i < m1) s1 += y; }
+            }
+            ext[v * 2 + (left ? 0 : 1)] = h0 * s2 + h1 * s1;
+        }
+        __syncthreads();
+    }
+    // apply the extras of the last scale
+    if (u == 0 || u == NU - 1) {
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) C0[(v0 + r) * NU + u] += ext[(v0 + r) * 2 + (u == 0 ? 0 : 1)];
+    }
+    __syncthreads();
+    return reg;
+}
+
 // ---------------------------------------------------------------- the kernel
-template <int K, int G>
+// NS > 0: compile-time stamp side (fast path, requires NS*K in {32, 64}); NS == 0: runtime sizes.
+template <int K, int G, int NS>
 __global__ void __launch_bounds__(PSF_THREADS) k_psf_fit(PsfArgs A) {
     using P = LcbPass<K, G>;
+    constexpr bool FAST = (NS > 0);
+    static_assert(!FAST || (NS * K == 32 || NS * K == 64), "fast path needs a 32 or 64 wide grid");
     extern __shared__ __align__(16) float sm[];
-    const int n = A.n, nu = A.nu, nn = n * n, pp = nu * nu, tid = threadIdx.x;
+    const int n = FAST ? NS : A.n, nu = FAST ? NS * K : A.nu, nn = n * n, pp = nu * nu, tid = threadIdx.x;
     const int ldv = n + 1, ldt = n + 1, ldb = nu + 1;
     const int f = blockIdx.x;
     const int i0 = A.star_off[f], N = A.star_off[f + 1] - i0;
@@ -92,26 +262,59 @@ __global__ void __launch_bounds__(PSF_THREADS) k_psf_fit(PsfArgs A) {
     float* sp = taps + A.Nmax * 4 * LCB_GE_MAX;         // [Nmax][12] a,x0,y0, mu3, nu3, g3
     float* redS = sp + A.Nmax * 12;                     // [Nmax][PSF_WARPS][4]
     float* red = redS + A.Nmax * PSF_WARPS * 4;         // [2][PSF_WARPS][4]
-    float* Vg = red + 2 * PSF_WARPS * 4;                // [nu][ldv]
-    float* Vd = Vg + nu * ldv;                          // [nu][ldv]
-    float* rT = Vd + nu * ldv;                          // [n][ldt]
-    float* Vbar = rT + n * ldt;                         // [n][ldb]
-    float* planes = Vbar + n * ldb;
-    if (!A.planes_in_smem) planes = A.work + (size_t)f * A.work_per_frame + (size_t)J * pp;
-    float* S = planes;            // s = s_fixed + b
-    float* Bp = S + pp;           // b
+    // FAST: every plane read by the passes carries HB zero rows before and after (no bounds predicates)
+    constexpr int HB = FAST ? 8 : 0;
+    float* Vg = red + 2 * PSF_WARPS * 4 + HB * ldv;     // [HB + nu + HB][ldv]
+    float* Vd = Vg + (nu + 2 * HB) * ldv;               // [HB + nu + HB][ldv]
+    float* rT = Vd + (nu + HB) * ldv + HB * ldt;        // [HB + n + HB][ldt]
+    float* Vbar = rT + (n + HB) * ldt + HB * ldb;       // [HB + n + HB][ldb]
+    float* aux = Vbar + (n + HB) * ldb;                 // FAST: starlet chunk sums (see starlet_reg_fast)
+    float* planes = aux + (FAST ? (2 * (PSF_THREADS / (FAST ? NS * K : 1)) * nu + nu * nu / 8 + 2 * nu) : 0);
+    if constexpr (!FAST) {
+        if (!A.planes_in_smem) planes = A.work + (size_t)f * A.work_per_frame + (size_t)J * pp;
+    }
+    float* S = planes + HB * nu;  // s = s_fixed + b, [HB + nu + HB][nu]
+    float* Bp = S + pp + HB * nu; // b
     float* GR = Bp + pp;          // d chi2 / d s
     float* MU = GR + pp;
     float* NU = MU + pp;
     float* C0 = NU + pp;
     float* C1 = C0 + pp;
-    float* Tj = A.work + (size_t)f * A.work_per_frame;  // [J][pp] lambda_j W_j sign(alpha_j)
+    signed char* sg = reinterpret_cast<signed char*>(C1 + pp);   // FAST: [J][pp] sign(alpha_j) (always shared)
+    float* Tj = A.work + (size_t)f * A.work_per_frame;  // generic path: [J][pp] lambda_j W_j sign(alpha_j)
+    // stamps transposed ([X][Y], lanes <-> Y read coalesced) in the global workspace
+    float* dT = A.work + (size_t)f * A.work_per_frame + (size_t)(J + 7) * pp;
+    float* wT = dT + (size_t)A.Nmax * nn;
+
+    constexpr int NGRP = 1;          // (two concurrent star groups were measured: no gain, more registers)
+    constexpr int GT = PSF_THREADS / NGRP;
+    const int grp = tid / GT, ltid = tid % GT;
+    if (NGRP > 1 && grp == 1) {                         // second set of scratch planes, gradient plane = C0
+        const int sz = 2 * nu * ldv + n * ldt + n * ldb;
+        Vg += sz; Vd += sz; rT += sz; Vbar += sz;
+    }
+    float* GRg = (NGRP > 1 && grp == 1) ? C0 : GR;
+    auto group_sync = [&]() {
+        if (NGRP == 1) __syncthreads();
+        else asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(GT) : "memory");
+    };
 
     const float* sfix = A.s_fixed + (size_t)f * pp;
     const float* Wf = A.W ? A.W + (size_t)f * J * pp : nullptr;
     const float* dat = A.data + (size_t)i0 * nn;
     const float* wgt = A.weight + (size_t)i0 * nn;
 
+    if constexpr (FAST) {                               // halos must read as zero
+        float* z0 = red + 2 * PSF_WARPS * 4;
+        const int zc = (int)(Bp - z0);
+        for (int i = tid; i < zc; i += PSF_THREADS) z0[i] = 0.f;
+        __syncthreads();
+    }
+    for (int i = tid; i < N * nn; i += PSF_THREADS) {
+        const int st = i / nn, r = i % nn, Y = r / n, X = r % n;
+        dT[(size_t)st * nn + X * n + Y] = dat[i];
+        wT[(size_t)st * nn + X * n + Y] = wgt[i];
+    }
     for (int i = tid; i < pp; i += PSF_THREADS) {
         const float b = A.b[(size_t)f * pp + i];
         Bp[i] = b; MU[i] = 0.f; NU[i] = 0.f; S[i] = sfix[i] + b;
@@ -138,53 +341,67 @@ __global__ void __launch_bounds__(PSF_THREADS) k_psf_fit(PsfArgs A) {
             taps[(st * 4 + (which ? 2 : 0)) * LCB_GE_MAX + p] = e;
             taps[(st * 4 + (which ? 3 : 1)) * LCB_GE_MAX + p] = de;
         }
-        for (int i = tid; i < pp; i += PSF_THREADS) GR[i] = 0.f;
+        for (int i = tid; i < pp; i += PSF_THREADS) { GR[i] = 0.f; if (NGRP > 1) C0[i] = 0.f; }
         __syncthreads();
 
         float chi = 0.f, cnt = 0.f;
-        for (int st = 0; st < N; ++st) {
+        // FAST: the CTA works on NGRP stars at a time, one per group of GT threads, each group with its own
+        // scratch planes, its own gradient plane (group 1 accumulates into C0, free until the starlet phase)
+        // and its own named barrier: task counts per pass are exact multiples of GT, and while one group
+        // waits at a barrier the other one issues.
+        for (int st = grp; st < N; st += NGRP) {
             const float a = sp[st * 12], cx = fk * sp[st * 12 + 1], cy = fk * sp[st * 12 + 2];
             const int icx = (int)floorf(cx + 0.5f), icy = (int)floorf(cy + 0.5f);
             const float* tp = taps + st * 4 * LCB_GE_MAX;
-            lcb_pass1<K, G>(S, nu, nu, n, icy, tp, tp + LCB_GE_MAX, Vg, Vd, ldv, tid, PSF_THREADS);
-            __syncthreads();
+            // halo variant (no bounds checks) whenever the tap windows stay within HB rows of the planes
+            const bool hal = FAST && abs(icx) <= HB - G / 2 && abs(icy) <= HB - G / 2;
+            if (hal) lcb_pass1<K, G, FAST>(S, nu, nu, n, icy, tp, tp + LCB_GE_MAX, Vg, Vd, ldv, ltid, GT);
+            else lcb_pass1<K, G, false>(S, nu, nu, n, icy, tp, tp + LCB_GE_MAX, Vg, Vd, ldv, ltid, GT);
+            group_sync();
             float ga = 0.f, gx = 0.f, gy = 0.f;
-            const float* ds = dat + (size_t)st * nn;
-            const float* ws = wgt + (size_t)st * nn;
+            const float* ds = dT + (size_t)st * nn;
+            const float* ws = wT + (size_t)st * nn;
             float* resid = (last && A.residuals) ? A.residuals + (size_t)(i0 + st) * nn : nullptr;
-            lcb_pass2<K, G>(Vg, Vd, ldv, nu, n, icx, tp + 2 * LCB_GE_MAX, tp + 3 * LCB_GE_MAX, tid, PSF_THREADS,
-                            [&](int Y, int X, float m0, float mx, float my) {
-                                const float d = __ldg(ds + Y * n + X), w = __ldg(ws + Y * n + X);
-                                const float diff = fmaf(a, m0, -d);
-                                const float r = w * diff;
-                                rT[X * ldt + Y] = r;
-                                chi = fmaf(r, diff, chi);
-                                ga = fmaf(r, m0, ga);
-                                gx = fmaf(r, mx, gx);
-                                gy = fmaf(r, my, gy);
-                                if (last) {
-                                    cnt += (w > 0.f) ? 1.f : 0.f;
-                                    if (resid) resid[Y * n + X] = -diff;
-                                }
-                            });
+            auto consume = [&](int Y, int X, float m0, float mx, float my) {
+                const float d = ds[X * n + Y], w = ws[X * n + Y];
+                const float diff = fmaf(a, m0, -d);
+                const float r = w * diff;
+                rT[X * ldt + Y] = r;
+                chi = fmaf(r, diff, chi);
+                ga = fmaf(r, m0, ga);
+                gx = fmaf(r, mx, gx);
+                gy = fmaf(r, my, gy);
+                if (last) {
+                    cnt += (w > 0.f) ? 1.f : 0.f;
+                    if (resid) resid[Y * n + X] = -diff;
+                }
+            };
+            if (hal) lcb_pass2<K, G, (FAST ? 2 : 4), FAST>(Vg, Vd, ldv, nu, n, icx, tp + 2 * LCB_GE_MAX, tp + 3 * LCB_GE_MAX, ltid, GT, consume);
+            else lcb_pass2<K, G, (FAST ? 2 : 4), false>(Vg, Vd, ldv, nu, n, icx, tp + 2 * LCB_GE_MAX, tp + 3 * LCB_GE_MAX, ltid, GT, consume);
             ga = warp_sum(ga); gx = warp_sum(gx); gy = warp_sum(gy);
             if ((tid & 31) == 0) {
                 float* q = redS + (st * PSF_WARPS + (tid >> 5)) * 4;
                 q[0] = ga; q[1] = gx; q[2] = gy;
             }
-            __syncthreads();
+            group_sync();
             if (last) continue;
-            lcb_pass2T<K, G>(rT, ldt, nu, n, icx, tp + 2 * LCB_GE_MAX, Vbar, ldb, tid, PSF_THREADS);
-            __syncthreads();
-            lcb_pass1T<K, G>(Vbar, ldb, nu, n, icy, tp, tid, PSF_THREADS,
-                             [&](int v, int u, float val) { GR[v * nu + u] = fmaf(a, val, GR[v * nu + u]); });
+            if (hal) lcb_pass2T<K, G, (FAST ? 2 : 4), FAST>(rT, ldt, nu, n, icx, tp + 2 * LCB_GE_MAX, Vbar, ldb, ltid, GT);
+            else lcb_pass2T<K, G, (FAST ? 2 : 4), false>(rT, ldt, nu, n, icx, tp + 2 * LCB_GE_MAX, Vbar, ldb, ltid, GT);
+            group_sync();
+            auto emit = [&](int v, int u, float val) { GRg[v * nu + u] = fmaf(a, val, GRg[v * nu + u]); };
+            if (hal) lcb_pass1T<K, G, FAST>(Vbar, ldb, nu, n, icy, tp, ltid, GT, emit);
+            else lcb_pass1T<K, G, false>(Vbar, ldb, nu, n, icy, tp, ltid, GT, emit);
         }
         __syncthreads();
+        if (NGRP > 1 && !last) {
+            for (int i = tid; i < pp; i += PSF_THREADS) GR[i] += C0[i];
+        }
         // ---- per-star gradients (threads st < N)
         float gn2 = 0.f;
         if (tid < N) {
             float ga = 0.f, gx = 0.f, gy = 0.f;
-            for (int w = 0; w < PSF_WARPS; ++w) {
+            const int w0 = (tid % NGRP) * (PSF_WARPS / NGRP);      // star `tid` was handled by group tid % NGRP
+            for (int w = w0; w < w0 + PSF_WARPS / NGRP; ++w) {
                 const float* q = redS + (tid * PSF_WARPS + w) * 4;
                 ga += q[0]; gx += q[1]; gy += q[2];
             }
@@ -203,7 +420,9 @@ __global__ void __launch_bounds__(PSF_THREADS) k_psf_fit(PsfArgs A) {
         // ---- starlet regulariser: forward transform, loss, t_j = lambda_j W_j sign(alpha_j)
         float reg = 0.f;
         const bool do_reg = (A.lam_scales != 0.f || A.lam_hf != 0.f);
-        if (do_reg) {
+        if (do_reg && FAST) {
+            if constexpr (FAST) reg = starlet_reg_fast<NS * K>(Bp, C0, C1, sg, aux, Wf, A.lam_hf, A.lam_scales, J, tid);
+        } else if (do_reg) {
             for (int j = 0; j < J; ++j) {
                 const int D = 1 << j;
                 const float* cur = (j == 0) ? Bp : C0;
@@ -335,20 +554,38 @@ size_t lcb_psf_fit_smem_small(int n, int nu, int Nmax) {
                     2 * nu * (n + 1) + n * (n + 1) + n * (nu + 1)) * 4;
 }
 
-template <int K, int G>
+// shared bytes of the fast path on top of smem_small: 7 planes + J int8 sign planes
+// fast path: 7 planes + J int8 sign planes + starlet chunk sums + the zero halos (8 rows each side of
+// s, Vg, Vd, r^T, Vbar)
+size_t lcb_psf_fit_smem_fast_extra(int n, int nu, int J) {
+    const size_t halos = (size_t)16 * (nu + 2 * (n + 1) + (n + 1) + (nu + 1)) * 4;
+    return (size_t)7 * nu * nu * 4 + (size_t)J * nu * nu + (size_t)(2 * (PSF_THREADS / nu) * nu + nu * nu / 8 + 2 * nu) * 4 + halos;
+}
+
+bool lcb_psf_fit_has_fast(int n, int k, int G) {
+    return G == 12 && ((k == 2 && (n == 32 || n == 16)) || (k == 1 && (n == 32 || n == 64)));
+}
+
+template <int K, int G, int NS>
 static int launch_psf_fit(const PsfArgs& A, size_t smem, cudaStream_t st) {
-    LCB_CUDA(cudaFuncSetAttribute(k_psf_fit<K, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    { LcbProfScope ps("k_psf_fit", st); k_psf_fit<K, G><<<A.F, PSF_THREADS, smem, st>>>(A); }
+    LCB_CUDA(cudaFuncSetAttribute(k_psf_fit<K, G, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { LcbProfScope ps("k_psf_fit", st); k_psf_fit<K, G, NS><<<A.F, PSF_THREADS, smem, st>>>(A); }
     LCB_CUDA(cudaGetLastError());
     return LCB_OK;
 }
 
-int lcb_psf_fit_dispatch(const PsfArgs& A, size_t smem, cudaStream_t st) {
+// `fast`: the caller verified lcb_psf_fit_has_fast() and that planes + sign planes fit in shared memory
+int lcb_psf_fit_dispatch(const PsfArgs& A, size_t smem, bool fast, cudaStream_t st) {
     const int G = A.cv.G;
-#define CASE(KK, GG) if (A.k == KK && G == GG) return launch_psf_fit<KK, GG>(A, smem, st);
+    if (fast) {
+        if (A.k == 2 && A.n == 32) return launch_psf_fit<2, 12, 32>(A, smem, st);
+        if (A.k == 2 && A.n == 16) return launch_psf_fit<2, 12, 16>(A, smem, st);
+        if (A.k == 1 && A.n == 32) return launch_psf_fit<1, 12, 32>(A, smem, st);
+        if (A.k == 1 && A.n == 64) return launch_psf_fit<1, 12, 64>(A, smem, st);
+    }
+#define CASE(KK, GG) if (A.k == KK && G == GG) return launch_psf_fit<KK, GG, 0>(A, smem, st);
     CASE(1, 12) CASE(2, 12) CASE(3, 12) CASE(4, 12)
-    CASE(1, 8) CASE(2, 8) CASE(3, 8)
-    CASE(1, 16) CASE(2, 16) CASE(3, 16)
+    CASE(2, 8) CASE(2, 16)
 #undef CASE
     lcb_set_error("psf fit: unsupported (subsampling_factor=%d, gauss_taps=%d)", A.k, G);
     return LCB_ERR_ARG;

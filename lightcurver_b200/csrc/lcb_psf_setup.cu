@@ -361,8 +361,7 @@ int lcb_psf_lm_dispatch(const PsfArgs& A, size_t smem, cudaStream_t st) {
     const int G = A.cv.G;
 #define CASE(KK, GG) if (A.k == KK && G == GG) return launch_lm<KK, GG>(A, smem, st);
     CASE(1, 12) CASE(2, 12) CASE(3, 12) CASE(4, 12)
-    CASE(1, 8) CASE(2, 8) CASE(3, 8)
-    CASE(1, 16) CASE(2, 16) CASE(3, 16)
+    CASE(2, 8) CASE(2, 16)
 #undef CASE
     lcb_set_error("psf moffat stage: unsupported (subsampling_factor=%d, gauss_taps=%d)", A.k, G);
     return LCB_ERR_ARG;
@@ -429,8 +428,7 @@ int lcb_noise_var_dispatch(const PsfArgs& A, cudaStream_t st) {
     const int G = A.cv.G;
 #define CASE(KK, GG) if (A.k == KK && G == GG) return launch_nvar<KK, GG>(A, st);
     CASE(1, 12) CASE(2, 12) CASE(3, 12) CASE(4, 12)
-    CASE(1, 8) CASE(2, 8) CASE(3, 8)
-    CASE(1, 16) CASE(2, 16) CASE(3, 16)
+    CASE(2, 8) CASE(2, 16)
 #undef CASE
     lcb_set_error("noise weights: unsupported (subsampling_factor=%d, gauss_taps=%d)", A.k, G);
     return LCB_ERR_ARG;
