@@ -26,7 +26,11 @@ def _needs(target: Path, deps):
     return any(Path(d).stat().st_mtime > t for d in deps)
 
 
-def build(verbose=False, force=False, ptxas_info=False):
+def build(verbose=False, force=False, ptxas_info=False, extra_flags=(), out=None):
+    """extra_flags/out: build a variant (e.g. ['-DLCB_PHASE_TIMERS'] -> liblcb_timers.so for tools/phase_time.py)."""
+    global OUT
+    if out is not None or extra_flags:
+        force = True
     OBJ.mkdir(exist_ok=True)
     sources = sorted(CSRC.glob('*.cu'))
     headers = sorted(CSRC.glob('*.cuh')) + [HERE.parent / 'include' / 'lcb.h']
@@ -34,7 +38,7 @@ def build(verbose=False, force=False, ptxas_info=False):
     for src in sources:
         obj = OBJ / (src.stem + '.o')
         if force or _needs(obj, [src] + headers):
-            cmd = [NVCC] + FLAGS + (['-Xptxas', '-v'] if ptxas_info else []) + ['-c', str(src), '-o', str(obj)]
+            cmd = [NVCC] + FLAGS + list(extra_flags) + (['-Xptxas', '-v'] if ptxas_info else []) + ['-c', str(src), '-o', str(obj)]
             jobs.append((src, cmd))
     if jobs:
         with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
@@ -46,15 +50,23 @@ def build(verbose=False, force=False, ptxas_info=False):
                 if r.returncode != 0:
                     raise RuntimeError(f'nvcc failed on {futs[fut]}')
     objs = [str(OBJ / (s.stem + '.o')) for s in sources]
-    if jobs or not OUT.exists():
-        cmd = [NVCC, '-shared', '-o', str(OUT)] + objs + ['-lcudart']
+    target = Path(out) if out is not None else OUT
+    if jobs or not target.exists():
+        cmd = [NVCC, '-shared', '-o', str(target)] + objs + ['-lcudart']
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError('link failed')
-    return OUT
+    if out is not None:          # variant objects must not be mistaken for the default build
+        for o in objs:
+            Path(o).unlink(missing_ok=True)
+    return target
 
 
 if __name__ == '__main__':
-    p = build(verbose='-v' in sys.argv, force='-f' in sys.argv, ptxas_info='--ptxas' in sys.argv)
+    if '--timers' in sys.argv:
+        p = build(extra_flags=['-DLCB_PHASE_TIMERS'], out=HERE / 'liblcb_timers.so')
+        build(force=True)
+    else:
+        p = build(verbose='-v' in sys.argv, force='-f' in sys.argv, ptxas_info='--ptxas' in sys.argv)
     print(p)

@@ -55,10 +55,14 @@ __device__ __forceinline__ void lcb_pass1(const float* __restrict__ s, int lds, 
 
 // pass 2: V{g,d} [u][Y] -> (M0, Mx, My)[Y][X] handed to consume(Y, X, m0, mx, my).
 //   m0 = sum ex*Vg, mx = sum dex*Vg (d/dcx), my = sum ex*Vd (d/dcy); c in upsampled px.
+// `aux0`, `aux1` (may be NULL): two per-pixel arrays stored [X][Y] with leading dimension ldaux (stamp and
+// weight); their values for the task's outputs are fetched BEFORE the FMA loop so that the global/L2 latency
+// hides behind it, and handed to consume(Y, X, m0, mx, my, aux0[X][Y], aux1[X][Y]).
 template <int K, int G, int OBV = 4, bool HALO = false, typename F>
 __device__ __forceinline__ void lcb_pass2(const float* __restrict__ Vg, const float* __restrict__ Vd, int ldv,
                                           int nu, int n, int icx,
                                           const float* __restrict__ ex_s, const float* __restrict__ dex_s,
+                                          const float* __restrict__ aux0, const float* __restrict__ aux1, int ldaux,
                                           int tid, int nthreads, F&& consume) {
     using P = LcbPass<K, G, OBV>;
     float ex[P::GE], dex[P::GE];
@@ -69,6 +73,13 @@ __device__ __forceinline__ void lcb_pass2(const float* __restrict__ Vg, const fl
         const int Y = task % n;
         const int X0 = (task / n) * P::OB;
         const int ubase = K * X0 - icx - G / 2;
+        float pa[P::OB], pb[P::OB];
+#pragma unroll
+        for (int x = 0; x < P::OB; ++x) {
+            const bool ok = (X0 + x < n);
+            pa[x] = (ok && aux0) ? aux0[(X0 + x) * ldaux + Y] : 0.f;
+            pb[x] = (ok && aux1) ? aux1[(X0 + x) * ldaux + Y] : 0.f;
+        }
         float m0[P::OB], mx[P::OB], my[P::OB];
 #pragma unroll
         for (int x = 0; x < P::OB; ++x) { m0[x] = 0.f; mx[x] = 0.f; my[x] = 0.f; }
@@ -90,7 +101,7 @@ __device__ __forceinline__ void lcb_pass2(const float* __restrict__ Vg, const fl
         }
 #pragma unroll
         for (int x = 0; x < P::OB; ++x)
-            if (X0 + x < n) consume(Y, X0 + x, m0[x], mx[x], my[x]);
+            if (X0 + x < n) consume(Y, X0 + x, m0[x], mx[x], my[x], pa[x], pb[x]);
     }
 }
 

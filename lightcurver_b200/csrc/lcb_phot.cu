@@ -31,17 +31,24 @@ __global__ void __launch_bounds__(PHOT_THREADS, (NS > 0 ? 3 : 1)) k_phot_fit(Pho
     const int n = (NS > 0) ? NS : A.n, nu = (NS > 0) ? NS * K : A.nu, tid = threadIdx.x;
     const int ldv = n + 1, ldt = n + 1;
     const int item = blockIdx.x;
-    // shared layout
+    // shared layout.  NS > 0: HB zero rows before and after s and Vg/Vd (no bounds predicates in the passes)
+    constexpr int HB = (NS > 0) ? 8 : 0;
     float* taps = sm;                              // ey, dey, ex, dex  [4][LCB_GE_MAX]
     float* red = taps + 4 * LCB_GE_MAX;            // [2][8 warps][4] double-buffered partials
     float* dT = red + 2 * 8 * 4;                   // [n][ldt]  data, stored [X][Y]
     float* wT = dT + n * ldt;                      // [n][ldt]
-    float* Vg = wT + n * ldt;                      // [nu][ldv]
-    float* Vd = Vg + nu * ldv;                     // [nu][ldv]
-    float* s_sm = Vd + nu * ldv;                   // [nu][nu] when it fits
+    float* Vg = wT + n * ldt + HB * ldv;           // [HB + nu + HB][ldv]
+    float* Vd = Vg + (nu + 2 * HB) * ldv;          // [HB + nu + HB][ldv]
+    float* s_sm = Vd + (nu + HB) * ldv + HB * nu;  // [HB + nu + HB][nu] when it fits
     const float* psf_g = A.psf + (size_t)A.psf_index[item] * nu * nu;
     const float* s = A.s_in_smem ? s_sm : psf_g;
 
+    if (HB > 0) {
+        float* z0 = wT + n * ldt;
+        const int zc = 2 * (nu + 2 * HB) * ldv + (nu + 2 * HB) * nu;
+        for (int i = tid; i < zc; i += PHOT_THREADS) z0[i] = 0.f;
+        __syncthreads();
+    }
     // ---- load: stamp + weight transposed, PSF tile (coalesced float loads; 16 KB at n=32,k=2)
     const float* dg = A.data + (size_t)item * n * n;
     const float* wg = A.weight + (size_t)item * n * n;
@@ -79,26 +86,28 @@ __global__ void __launch_bounds__(PHOT_THREADS, (NS > 0 ? 3 : 1)) k_phot_fit(Pho
             taps[(which ? 3 : 1) * LCB_GE_MAX + p] = de;
         }
         __syncthreads();
-        lcb_pass1<K, G>(s, nu, nu, n, icy, taps, taps + LCB_GE_MAX, Vg, Vd, ldv, tid, PHOT_THREADS);
+        const bool hal = (HB > 0) && A.s_in_smem && abs(icx) <= HB - G / 2 && abs(icy) <= HB - G / 2;
+        if (hal) lcb_pass1<K, G, (NS > 0)>(s, nu, nu, n, icy, taps, taps + LCB_GE_MAX, Vg, Vd, ldv, tid, PHOT_THREADS);
+        else lcb_pass1<K, G, false>(s, nu, nu, n, icy, taps, taps + LCB_GE_MAX, Vg, Vd, ldv, tid, PHOT_THREADS);
         __syncthreads();
         float loss = 0.f, ga = 0.f, gx = 0.f, gy = 0.f;   // on the last pass: chi2, H, -, -
         float* resid = (last && A.residuals) ? A.residuals + (size_t)item * n * n : nullptr;
-        lcb_pass2<K, G>(Vg, Vd, ldv, nu, n, icx, taps + 2 * LCB_GE_MAX, taps + 3 * LCB_GE_MAX, tid,
-                        PHOT_THREADS, [&](int Y, int X, float m0, float mx, float my) {
-                            const float d = dT[X * ldt + Y], w = wT[X * ldt + Y];
-                            const float diff = fmaf(a, m0, -d);
-                            const float r = w * diff;
-                            if (!last) {
-                                loss = fmaf(r, diff, loss);
-                                ga = fmaf(r, m0, ga);
-                                gx = fmaf(r, mx, gx);
-                                gy = fmaf(r, my, gy);
-                            } else {
-                                loss = fmaf(r, diff, loss);
-                                ga = fmaf(w * m0, m0, ga);
-                                if (resid) resid[Y * n + X] = -diff;
-                            }
-                        });
+        auto consume = [&](int Y, int X, float m0, float mx, float my, float d, float w) {
+            const float diff = fmaf(a, m0, -d);
+            const float r = w * diff;
+            if (!last) {
+                loss = fmaf(r, diff, loss);
+                ga = fmaf(r, m0, ga);
+                gx = fmaf(r, mx, gx);
+                gy = fmaf(r, my, gy);
+            } else {
+                loss = fmaf(r, diff, loss);
+                ga = fmaf(w * m0, m0, ga);
+                if (resid) resid[Y * n + X] = -diff;
+            }
+        };
+        if (hal) lcb_pass2<K, G, 4, (NS > 0)>(Vg, Vd, ldv, nu, n, icx, taps + 2 * LCB_GE_MAX, taps + 3 * LCB_GE_MAX, dT, wT, ldt, tid, PHOT_THREADS, consume);
+        else lcb_pass2<K, G, 4, false>(Vg, Vd, ldv, nu, n, icx, taps + 2 * LCB_GE_MAX, taps + 3 * LCB_GE_MAX, dT, wT, ldt, tid, PHOT_THREADS, consume);
         loss = warp_sum(loss); ga = warp_sum(ga); gx = warp_sum(gx); gy = warp_sum(gy);
         float* rbuf = red + (it & 1) * 32;
         if ((tid & 31) == 0) {
@@ -194,8 +203,8 @@ extern "C" int lcb_phot_fit_batch(const lcb_phot_batch* in, const lcb_fit_opts* 
     memset(&A, 0, sizeof(A));
     A.B = B; A.n = n; A.k = k; A.nu = nu; A.n_iter = T; A.schedule = opt->schedule; A.lr = opt->lr;
     A.cv = lcb_devconv();
-    const size_t fixed = (size_t)(4 * LCB_GE_MAX + 64 + 2 * n * (n + 1) + 2 * nu * (n + 1)) * 4;
-    const size_t with_s = fixed + (size_t)nu * nu * 4;
+    const size_t fixed = (size_t)(4 * LCB_GE_MAX + 64 + 2 * n * (n + 1) + 2 * (nu + 16) * (n + 1)) * 4;
+    const size_t with_s = fixed + (size_t)(nu + 16) * nu * 4;
     int dev = 0, maxsm = 0;
     LCB_CUDA(cudaGetDevice(&dev));
     LCB_CUDA(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));

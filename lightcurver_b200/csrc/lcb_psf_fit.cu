@@ -7,8 +7,8 @@
 #include "lcb_psf.cuh"
 
 // ---------------------------------------------------------------- block reduction of NV scalars
-template <int NV>
-__device__ __forceinline__ void block_reduce(float (&v)[NV], float* red /* [PSF_WARPS][NV] */, int tid) {
+template <int NV, int NW = PSF_WARPS>
+__device__ __forceinline__ void block_reduce(float (&v)[NV], float* red /* [NW][NV] */, int tid) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
     if ((tid & 31) == 0) {
@@ -20,7 +20,7 @@ __device__ __forceinline__ void block_reduce(float (&v)[NV], float* red /* [PSF_
     for (int i = 0; i < NV; ++i) {
         float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < PSF_WARPS; ++w) s += red[w * NV + i];
+        for (int w = 0; w < NW; ++w) s += red[w * NV + i];
         v[i] = s;
     }
 }
@@ -241,12 +241,360 @@ __device__ __forceinline__ float starlet_reg_fast(const float* __restrict__ Bp, 
     return reg;
 }
 
+// ---------------------------------------------------------------- float4-vectorised starlet (NU = 64)
+// Same mathematics as starlet_reg_fast, with each thread owning a 4-pixel quad of 2 rows: every stencil tap
+// is one LDS.128 (quads at +-D, +-2D are 16-byte aligned for D >= 4; D = 1, 2 use three neighbouring quads
+// and register swizzles), edge replication / zero extension become whole-quad selects, signs are packed
+// four to a word.  About half the instructions per pixel of the scalar version.
+__device__ __forceinline__ float4 f4_splat(float v) { return make_float4(v, v, v, v); }
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 f4_b3(float4 c, float4 l1, float4 r1, float4 l2, float4 r2) {
+    const float h0 = 1.f / 16.f, h1 = 4.f / 16.f, h2 = 6.f / 16.f;
+    return make_float4(h0 * (l2.x + r2.x) + h1 * (l1.x + r1.x) + h2 * c.x, h0 * (l2.y + r2.y) + h1 * (l1.y + r1.y) + h2 * c.y,
+                       h0 * (l2.z + r2.z) + h1 * (l1.z + r1.z) + h2 * c.z, h0 * (l2.w + r2.w) + h1 * (l1.w + r1.w) + h2 * c.w);
+}
+// the four dilated neighbours of quad B along a row, from the quads A (4 left), C (4 right) for D = 1, 2
+__device__ __forceinline__ void f4_near(int D, float4 A, float4 B, float4 C, float4& l1, float4& r1, float4& l2, float4& r2) {
+    if (D == 1) {
+        l1 = make_float4(A.w, B.x, B.y, B.z); r1 = make_float4(B.y, B.z, B.w, C.x);
+        l2 = make_float4(A.z, A.w, B.x, B.y); r2 = make_float4(B.z, B.w, C.x, C.y);
+    } else {
+        l1 = make_float4(A.z, A.w, B.x, B.y); r1 = make_float4(B.z, B.w, C.x, C.y);
+        l2 = A; r2 = C;
+    }
+}
+
+__device__ __forceinline__ float starlet_reg_fast4(const float* __restrict__ Bp, float* __restrict__ C0,
+                                                   float* __restrict__ C1, signed char* __restrict__ sg,
+                                                   float* __restrict__ aux,
+                                                   const float* __restrict__ Wf, float lam_hf, float lam_scales,
+                                                   int J, int tid) {
+    constexpr int NU = 64, PP = NU * NU, QR = NU / 4, LDC = QR + 1;
+    const float h0 = 1.f / 16.f, h1 = 4.f / 16.f;
+    const int q = tid & (QR - 1), rg = tid >> 4, v0 = 2 * rg, u0 = 4 * q;
+    float* chkR = aux;                                   // [NU][LDC] quad sums of the rows of C1
+    float* ext = chkR + NU * LDC;                        // [NU][2]
+    auto L4 = [](const float* p) { return *reinterpret_cast<const float4*>(p); };
+    auto S4 = [](float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; };
+    float reg = 0.f;
+    float4 wreg[2];
+    for (int j = 0; j < J; ++j) {
+        const int D = 1 << j;
+        const float* cur = (j == 0) ? Bp : C0;
+        const float lam = (j == 0) ? lam_hf : lam_scales;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            float4 w = Wf ? __ldg(reinterpret_cast<const float4*>(Wf + (size_t)j * PP + (v0 + r) * NU + u0)) : f4_splat(1.f);
+            wreg[r] = make_float4(lam * w.x, lam * w.y, lam * w.z, lam * w.w);
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const float* row = cur + (v0 + r) * NU;
+            const float4 B = L4(row + u0);
+            float4 l1, r1, l2, r2;
+            if (D < 4) {
+                const float4 A = (q == 0) ? f4_splat(row[0]) : L4(row + u0 - 4);
+                const float4 C = (q == QR - 1) ? f4_splat(row[NU - 1]) : L4(row + u0 + 4);
+                f4_near(D, A, B, C, l1, r1, l2, r2);
+            } else {
+                l1 = (u0 - D < 0) ? f4_splat(row[0]) : L4(row + u0 - D);
+                r1 = (u0 + D >= NU) ? f4_splat(row[NU - 1]) : L4(row + u0 + D);
+                l2 = (u0 - 2 * D < 0) ? f4_splat(row[0]) : L4(row + u0 - 2 * D);
+                r2 = (u0 + 2 * D >= NU) ? f4_splat(row[NU - 1]) : L4(row + u0 + 2 * D);
+            }
+            S4(C1 + (v0 + r) * NU + u0, f4_b3(B, l1, r1, l2, r2));
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int v = v0 + r, idx = v * NU + u0;
+            const int vm2 = max(v - 2 * D, 0), vm1 = max(v - D, 0), vp1 = min(v + D, NU - 1), vp2 = min(v + 2 * D, NU - 1);
+            const float4 nxt = f4_b3(L4(C1 + idx), L4(C1 + vm1 * NU + u0), L4(C1 + vp1 * NU + u0), L4(C1 + vm2 * NU + u0), L4(C1 + vp2 * NU + u0));
+            const float4 c = L4(cur + idx);
+            const float4 al = make_float4(c.x - nxt.x, c.y - nxt.y, c.z - nxt.z, c.w - nxt.w);
+            reg = fmaf(wreg[r].x, fabsf(al.x), reg); reg = fmaf(wreg[r].y, fabsf(al.y), reg);
+            reg = fmaf(wreg[r].z, fabsf(al.z), reg); reg = fmaf(wreg[r].w, fabsf(al.w), reg);
+            char4 sgn;
+            sgn.x = (al.x > 0.f) ? 1 : (al.x < 0.f) ? -1 : 0; sgn.y = (al.y > 0.f) ? 1 : (al.y < 0.f) ? -1 : 0;
+            sgn.z = (al.z > 0.f) ? 1 : (al.z < 0.f) ? -1 : 0; sgn.w = (al.w > 0.f) ? 1 : (al.w < 0.f) ? -1 : 0;
+            *reinterpret_cast<char4*>(sg + j * PP + idx) = sgn;
+            S4(C0 + idx, nxt);
+        }
+        __syncthreads();
+    }
+    for (int j = J - 1; j >= 0; --j) {
+        const int D = 1 << j;
+        const int m1 = min(D, NU), m2 = min(2 * D, NU);
+        float4 tj[2];
+        // (1) q = g_{j+1} (+ row-pass border extras of the previous scale) - t_j
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int v = v0 + r, idx = v * NU + u0;
+            const char4 sgn = *reinterpret_cast<const char4*>(sg + j * PP + idx);
+            tj[r] = make_float4(wreg[r].x * (float)sgn.x, wreg[r].y * (float)sgn.y, wreg[r].z * (float)sgn.z, wreg[r].w * (float)sgn.w);
+            float4 g = f4_splat(0.f);
+            if (j != J - 1) {
+                g = L4(C0 + idx);
+                if (q == 0) g.x += ext[v * 2];
+                if (q == QR - 1) g.w += ext[v * 2 + 1];
+            }
+            S4(C0 + idx, make_float4(g.x - tj[r].x, g.y - tj[r].y, g.z - tj[r].z, g.w - tj[r].w));
+        }
+        if (j > 0) {
+            const float lamn = (j - 1 == 0) ? lam_hf : lam_scales;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                float4 w = Wf ? __ldg(reinterpret_cast<const float4*>(Wf + (size_t)(j - 1) * PP + (v0 + r) * NU + u0)) : f4_splat(1.f);
+                wreg[r] = make_float4(lamn * w.x, lamn * w.y, lamn * w.z, lamn * w.w);
+            }
+        }
+        __syncthreads();
+        // (2) Hcol^T (zero extension) + folded taps on rows 0 / NU-1, quad sums of the result
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int v = v0 + r, idx = v * NU + u0;
+            const float4 z = f4_splat(0.f);
+            float4 acc = f4_b3(L4(C0 + idx), (v - D >= 0) ? L4(C0 + idx - D * NU) : z, (v + D < NU) ? L4(C0 + idx + D * NU) : z,
+                               (v - 2 * D >= 0) ? L4(C0 + idx - 2 * D * NU) : z, (v + 2 * D < NU) ? L4(C0 + idx + 2 * D * NU) : z);
+            if (v == 0 || v == NU - 1) {
+                float4 s1 = z, s2 = z;
+                for (int i = 0; i < m2; ++i) {
+                    const float4 y = L4(C0 + ((v == 0) ? i : NU - 1 - i) * NU + u0);
+                    s2 = f4_add(s2, y);
+                    if (i < m1) s1 = f4_add(s1, y);
+                }
+                acc.x += h0 * s2.x + h1 * s1.x; acc.y += h0 * s2.y + h1 * s1.y;
+                acc.z += h0 * s2.z + h1 * s1.z; acc.w += h0 * s2.w + h1 * s1.w;
+            }
+            S4(C1 + idx, acc);
+            chkR[v * LDC + q] = (acc.x + acc.y) + (acc.z + acc.w);
+        }
+        __syncthreads();
+        // (3) Hrow^T (zero extension) + t_j ; threads 0..127 prepare the folded extras of the rows
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const float* row = C1 + (v0 + r) * NU;
+            const float4 z = f4_splat(0.f);
+            const float4 B = L4(row + u0);
+            float4 l1, r1, l2, r2;
+            if (D < 4) {
+                const float4 A = (q == 0) ? z : L4(row + u0 - 4);
+                const float4 C = (q == QR - 1) ? z : L4(row + u0 + 4);
+                f4_near(D, A, B, C, l1, r1, l2, r2);
+            } else {
+                l1 = (u0 - D < 0) ? z : L4(row + u0 - D);
+                r1 = (u0 + D >= NU) ? z : L4(row + u0 + D);
+                l2 = (u0 - 2 * D < 0) ? z : L4(row + u0 - 2 * D);
+                r2 = (u0 + 2 * D >= NU) ? z : L4(row + u0 + 2 * D);
+            }
+            const float4 a4 = f4_b3(B, l1, r1, l2, r2);
+            S4(C0 + (v0 + r) * NU + u0, make_float4(tj[r].x + a4.x, tj[r].y + a4.y, tj[r].z + a4.z, tj[r].w + a4.w));
+        }
+        if (tid < 2 * NU) {
+            const int v = tid & (NU - 1);
+            const bool left = tid < NU;
+            const float* row = C1 + v * NU;
+            float s1 = 0.f, s2 = 0.f;
+            if (m2 >= 4) {
+                for (int c = 0; c < m2 / 4; ++c) {
+                    const float y = chkR[v * LDC + (left ? c : QR - 1 - c)];
+                    s2 += y;
+                    if (c < m1 / 4) s1 += y;
+                }
+                if (m1 < 4) for (int i = 0; i < m1; ++i) s1 += row[left ? i : NU - 1 - i];
+            } else {
+                for (int i = 0; i < m2; ++i) { const float y = row[left ? i : NU - 1 - i]; s2 += y; if (i < m1) s1 += y; }
+            }
+            ext[v * 2 + (left ? 0 : 1)] = h0 * s2 + h1 * s1;
+        }
+        __syncthreads();
+    }
+    if (q == 0 || q == QR - 1) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            if (q == 0) C0[(v0 + r) * NU] += ext[(v0 + r) * 2];
+            else C0[(v0 + r) * NU + NU - 1] += ext[(v0 + r) * 2 + 1];
+        }
+    }
+    __syncthreads();
+    return reg;
+}
+
+// ---------------------------------------------------------------- warp-specialised starlet (NU = 64)
+// The regulariser gradient depends on b only, exactly like the star passes, so in the 64x64 fast path it runs
+// CONCURRENTLY with them on 4 dedicated warps (threads 512..639) that synchronise among themselves with the
+// named barrier SPEC_BAR; the 16 star warps use barrier 1.  Same arithmetic as starlet_reg_fast4 with 8 rows
+// per thread; W and the sign planes are re-read where needed instead of being cached in registers (the star
+// warps hide that latency).
+#define SPEC_THREADS 256
+#define SPEC_BAR 2
+__device__ __forceinline__ void spec_sync() { asm volatile("bar.sync %0, %1;" ::"n"(SPEC_BAR), "n"(SPEC_THREADS) : "memory"); }
+
+__device__ __noinline__ float starlet_reg_spec(const float* __restrict__ Bp, float* __restrict__ C0,
+                                               float* __restrict__ C1, signed char* __restrict__ sg,
+                                               float* __restrict__ aux,
+                                               const float* __restrict__ Wf, float lam_hf, float lam_scales,
+                                               int J, int lt) {
+    constexpr int NU = 64, PP = NU * NU, QR = NU / 4, LDC = QR + 1, ROWS = NU * QR / SPEC_THREADS;
+    const float h0 = 1.f / 16.f, h1 = 4.f / 16.f;
+    const int q = lt & (QR - 1), rg = lt >> 4, v0 = ROWS * rg, u0 = 4 * q;
+    float* chkR = aux;
+    float* ext = chkR + NU * LDC;
+    float4 wreg[ROWS];                                   // lambda_j W_j of the owned quads, fetched one phase ahead
+    auto L4 = [](const float* p) { return *reinterpret_cast<const float4*>(p); };
+    auto S4 = [](float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; };
+    auto W4 = [&](int j, int idx, float lam) {
+        const float4 w = Wf ? __ldg(reinterpret_cast<const float4*>(Wf + (size_t)j * PP + idx)) : f4_splat(1.f);
+        return make_float4(lam * w.x, lam * w.y, lam * w.z, lam * w.w);
+    };
+    float reg = 0.f;
+    for (int j = 0; j < J; ++j) {
+        const int D = 1 << j;
+        const float* cur = (j == 0) ? Bp : C0;
+        const float lam = (j == 0) ? lam_hf : lam_scales;
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) wreg[r] = W4(j, (v0 + r) * NU + u0, lam);
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            const float* row = cur + (v0 + r) * NU;
+            const float4 B = L4(row + u0);
+            float4 l1, r1, l2, r2;
+            if (D < 4) {
+                const float4 A = (q == 0) ? f4_splat(row[0]) : L4(row + u0 - 4);
+                const float4 C = (q == QR - 1) ? f4_splat(row[NU - 1]) : L4(row + u0 + 4);
+                f4_near(D, A, B, C, l1, r1, l2, r2);
+            } else {
+                l1 = (u0 - D < 0) ? f4_splat(row[0]) : L4(row + u0 - D);
+                r1 = (u0 + D >= NU) ? f4_splat(row[NU - 1]) : L4(row + u0 + D);
+                l2 = (u0 - 2 * D < 0) ? f4_splat(row[0]) : L4(row + u0 - 2 * D);
+                r2 = (u0 + 2 * D >= NU) ? f4_splat(row[NU - 1]) : L4(row + u0 + 2 * D);
+            }
+            S4(C1 + (v0 + r) * NU + u0, f4_b3(B, l1, r1, l2, r2));
+        }
+        spec_sync();
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            const int v = v0 + r, idx = v * NU + u0;
+            const int vm2 = max(v - 2 * D, 0), vm1 = max(v - D, 0), vp1 = min(v + D, NU - 1), vp2 = min(v + 2 * D, NU - 1);
+            const float4 wv = wreg[r];
+            const float4 nxt = f4_b3(L4(C1 + idx), L4(C1 + vm1 * NU + u0), L4(C1 + vp1 * NU + u0), L4(C1 + vm2 * NU + u0), L4(C1 + vp2 * NU + u0));
+            const float4 c = L4(cur + idx);
+            const float4 al = make_float4(c.x - nxt.x, c.y - nxt.y, c.z - nxt.z, c.w - nxt.w);
+            reg = fmaf(wv.x, fabsf(al.x), reg); reg = fmaf(wv.y, fabsf(al.y), reg);
+            reg = fmaf(wv.z, fabsf(al.z), reg); reg = fmaf(wv.w, fabsf(al.w), reg);
+            char4 sgn;
+            sgn.x = (al.x > 0.f) ? 1 : (al.x < 0.f) ? -1 : 0; sgn.y = (al.y > 0.f) ? 1 : (al.y < 0.f) ? -1 : 0;
+            sgn.z = (al.z > 0.f) ? 1 : (al.z < 0.f) ? -1 : 0; sgn.w = (al.w > 0.f) ? 1 : (al.w < 0.f) ? -1 : 0;
+            *reinterpret_cast<char4*>(sg + j * PP + idx) = sgn;
+            S4(C0 + idx, nxt);
+        }
+        spec_sync();
+    }
+    auto TJ = [&](int j, int idx, float4 wv) {
+        const char4 sgn = *reinterpret_cast<const char4*>(sg + j * PP + idx);
+        return make_float4(wv.x * (float)sgn.x, wv.y * (float)sgn.y, wv.z * (float)sgn.z, wv.w * (float)sgn.w);
+    };
+    for (int j = J - 1; j >= 0; --j) {
+        const int D = 1 << j;
+        const int m1 = min(D, NU), m2 = min(2 * D, NU);
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            const int v = v0 + r, idx = v * NU + u0;
+            const float4 t = TJ(j, idx, wreg[r]);
+            float4 g = f4_splat(0.f);
+            if (j != J - 1) {
+                g = L4(C0 + idx);
+                if (q == 0) g.x += ext[v * 2];
+                if (q == QR - 1) g.w += ext[v * 2 + 1];
+            }
+            S4(C0 + idx, make_float4(g.x - t.x, g.y - t.y, g.z - t.z, g.w - t.w));
+        }
+        spec_sync();
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            const int v = v0 + r, idx = v * NU + u0;
+            const float4 z = f4_splat(0.f);
+            float4 acc = f4_b3(L4(C0 + idx), (v - D >= 0) ? L4(C0 + idx - D * NU) : z, (v + D < NU) ? L4(C0 + idx + D * NU) : z,
+                               (v - 2 * D >= 0) ? L4(C0 + idx - 2 * D * NU) : z, (v + 2 * D < NU) ? L4(C0 + idx + 2 * D * NU) : z);
+            if (v == 0 || v == NU - 1) {
+                float4 s1 = z, s2 = z;
+                for (int i = 0; i < m2; ++i) {
+                    const float4 y = L4(C0 + ((v == 0) ? i : NU - 1 - i) * NU + u0);
+                    s2 = f4_add(s2, y);
+                    if (i < m1) s1 = f4_add(s1, y);
+                }
+                acc.x += h0 * s2.x + h1 * s1.x; acc.y += h0 * s2.y + h1 * s1.y;
+                acc.z += h0 * s2.z + h1 * s1.z; acc.w += h0 * s2.w + h1 * s1.w;
+            }
+            S4(C1 + idx, acc);
+            chkR[v * LDC + q] = (acc.x + acc.y) + (acc.z + acc.w);
+        }
+        spec_sync();
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            const int idx = (v0 + r) * NU + u0;
+            const float* row = C1 + (v0 + r) * NU;
+            const float4 z = f4_splat(0.f);
+            const float4 B = L4(row + u0);
+            float4 l1, r1, l2, r2;
+            if (D < 4) {
+                const float4 A = (q == 0) ? z : L4(row + u0 - 4);
+                const float4 C = (q == QR - 1) ? z : L4(row + u0 + 4);
+                f4_near(D, A, B, C, l1, r1, l2, r2);
+            } else {
+                l1 = (u0 - D < 0) ? z : L4(row + u0 - D);
+                r1 = (u0 + D >= NU) ? z : L4(row + u0 + D);
+                l2 = (u0 - 2 * D < 0) ? z : L4(row + u0 - 2 * D);
+                r2 = (u0 + 2 * D >= NU) ? z : L4(row + u0 + 2 * D);
+            }
+            const float4 a4 = f4_b3(B, l1, r1, l2, r2);
+            const float4 t = TJ(j, idx, wreg[r]);
+            S4(C0 + idx, make_float4(t.x + a4.x, t.y + a4.y, t.z + a4.z, t.w + a4.w));
+            if (j > 0) wreg[r] = W4(j - 1, idx, (j - 1 == 0) ? lam_hf : lam_scales);   // next scale's weights
+        }
+        if (lt < 2 * NU) {
+            const int v = lt & (NU - 1);
+            const bool left = lt < NU;
+            const float* row = C1 + v * NU;
+            float s1 = 0.f, s2 = 0.f;
+            if (m2 >= 4) {
+                for (int c = 0; c < m2 / 4; ++c) {
+                    const float y = chkR[v * LDC + (left ? c : QR - 1 - c)];
+                    s2 += y;
+                    if (c < m1 / 4) s1 += y;
+                }
+                if (m1 < 4) for (int i = 0; i < m1; ++i) s1 += row[left ? i : NU - 1 - i];
+            } else {
+                for (int i = 0; i < m2; ++i) { const float y = row[left ? i : NU - 1 - i]; s2 += y; if (i < m1) s1 += y; }
+            }
+            ext[v * 2 + (left ? 0 : 1)] = h0 * s2 + h1 * s1;
+        }
+        spec_sync();
+    }
+    if (q == 0 || q == QR - 1) {
+        for (int r = 0; r < ROWS; ++r) {
+            if (q == 0) C0[(v0 + r) * NU] += ext[(v0 + r) * 2];
+            else C0[(v0 + r) * NU + NU - 1] += ext[(v0 + r) * 2 + 1];
+        }
+    }
+    return reg;
+}
+
 // ---------------------------------------------------------------- the kernel
 // NS > 0: compile-time stamp side (fast path, requires NS*K in {32, 64}); NS == 0: runtime sizes.
+// Warp specialisation (star passes and starlet concurrently on disjoint warps) is implemented and parity-
+// tested but DISABLED: measured with the in-kernel phase timers at cfg2, 16 star + 4 starlet warps = 118k
+// cycles/iteration, 16 + 8 warps = 92k, against 85k for the sequential schedule on 16 warps -- the starlet
+// is 30 barrier-separated dependent phases and starves on few warps.  Set to the commented expression to re-enable.
+#define FIT_SPEC(K, NS) 0   /* ((NS) > 0 && (NS) * (K) == 64) */
+#define FIT_THREADS(K, NS) (FIT_SPEC(K, NS) ? PSF_THREADS + SPEC_THREADS : PSF_THREADS)
 template <int K, int G, int NS>
-__global__ void __launch_bounds__(PSF_THREADS) k_psf_fit(PsfArgs A) {
+__global__ void __launch_bounds__(FIT_THREADS(K, NS)) k_psf_fit(PsfArgs A) {
     using P = LcbPass<K, G>;
     constexpr bool FAST = (NS > 0);
+    constexpr bool SPEC = FIT_SPEC(K, NS);          // 64x64 grid: 16 star warps + 4 starlet warps run concurrently
+    constexpr int NT = FIT_THREADS(K, NS);          // threads of the CTA
+    constexpr int NW = NT / 32;
     static_assert(!FAST || (NS * K == 32 || NS * K == 64), "fast path needs a 32 or 64 wide grid");
     extern __shared__ __align__(16) float sm[];
     const int n = FAST ? NS : A.n, nu = FAST ? NS * K : A.nu, nn = n * n, pp = nu * nu, tid = threadIdx.x;
@@ -261,10 +609,10 @@ __global__ void __launch_bounds__(PSF_THREADS) k_psf_fit(PsfArgs A) {
     float* taps = sm;                                   // [Nmax][4][LCB_GE_MAX]
     float* sp = taps + A.Nmax * 4 * LCB_GE_MAX;         // [Nmax][12] a,x0,y0, mu3, nu3, g3
     float* redS = sp + A.Nmax * 12;                     // [Nmax][PSF_WARPS][4]
-    float* red = redS + A.Nmax * PSF_WARPS * 4;         // [2][PSF_WARPS][4]
+    float* red = redS + A.Nmax * PSF_WARPS * 4;         // [2][32 warps][4]
     // FAST: every plane read by the passes carries HB zero rows before and after (no bounds predicates)
     constexpr int HB = FAST ? 8 : 0;
-    float* Vg = red + 2 * PSF_WARPS * 4 + HB * ldv;     // [HB + nu + HB][ldv]
+    float* Vg = red + 2 * 32 * 4 + HB * ldv;     // [HB + nu + HB][ldv]
     float* Vd = Vg + (nu + 2 * HB) * ldv;               // [HB + nu + HB][ldv]
     float* rT = Vd + (nu + HB) * ldv + HB * ldt;        // [HB + n + HB][ldt]
     float* Vbar = rT + (n + HB) * ldt + HB * ldb;       // [HB + n + HB][ldb]
@@ -288,15 +636,15 @@ __global__ void __launch_bounds__(PSF_THREADS) k_psf_fit(PsfArgs A) {
 
     constexpr int NGRP = 1;          // (two concurrent star groups were measured: no gain, more registers)
     constexpr int GT = PSF_THREADS / NGRP;
-    const int grp = tid / GT, ltid = tid % GT;
+    const int grp = 0, ltid = tid;
     if (NGRP > 1 && grp == 1) {                         // second set of scratch planes, gradient plane = C0
         const int sz = 2 * nu * ldv + n * ldt + n * ldb;
         Vg += sz; Vd += sz; rT += sz; Vbar += sz;
     }
     float* GRg = (NGRP > 1 && grp == 1) ? C0 : GR;
     auto group_sync = [&]() {
-        if (NGRP == 1) __syncthreads();
-        else asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(GT) : "memory");
+        if (SPEC) asm volatile("bar.sync 1, %0;" ::"n"(PSF_THREADS) : "memory");
+        else __syncthreads();
     };
 
     const float* sfix = A.s_fixed + (size_t)f * pp;
@@ -305,21 +653,21 @@ __global__ void __launch_bounds__(PSF_THREADS) k_psf_fit(PsfArgs A) {
     const float* wgt = A.weight + (size_t)i0 * nn;
 
     if constexpr (FAST) {                               // halos must read as zero
-        float* z0 = red + 2 * PSF_WARPS * 4;
+        float* z0 = red + 2 * 32 * 4;
         const int zc = (int)(Bp - z0);
-        for (int i = tid; i < zc; i += PSF_THREADS) z0[i] = 0.f;
+        for (int i = tid; i < zc; i += NT) z0[i] = 0.f;
         __syncthreads();
     }
-    for (int i = tid; i < N * nn; i += PSF_THREADS) {
+    for (int i = tid; i < N * nn; i += NT) {
         const int st = i / nn, r = i % nn, Y = r / n, X = r % n;
         dT[(size_t)st * nn + X * n + Y] = dat[i];
         wT[(size_t)st * nn + X * n + Y] = wgt[i];
     }
-    for (int i = tid; i < pp; i += PSF_THREADS) {
+    for (int i = tid; i < pp; i += NT) {
         const float b = A.b[(size_t)f * pp + i];
         Bp[i] = b; MU[i] = 0.f; NU[i] = 0.f; S[i] = sfix[i] + b;
     }
-    for (int i = tid; i < N * 12; i += PSF_THREADS) {
+    for (int i = tid; i < N * 12; i += NT) {
         const int st = i / 12, c = i % 12;
         sp[i] = (c == 0) ? A.a[i0 + st] : (c == 1) ? A.x0[i0 + st] : (c == 2) ? A.y0[i0 + st] : 0.f;
     }
@@ -328,11 +676,18 @@ __global__ void __launch_bounds__(PSF_THREADS) k_psf_fit(PsfArgs A) {
     float b1t = 1.f, b2t = 1.f;
     int bad = 0;
     const float sc = (cv.half == 0.5f) ? 1.f : 2.f;
+#ifdef LCB_PHASE_TIMERS
+    long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tlast = clock64();
+#define PHASE(k) { const long long tnow = clock64(); ph[k] += tnow - tlast; tlast = tnow; }
+#else
+#define PHASE(k)
+#endif
 
     for (int it = 0; it <= A.n_iter; ++it) {
         const bool last = (it == A.n_iter);
         // ---- taps of every star, zero the gradient plane
-        for (int idx = tid; idx < N * 2 * P::GE; idx += PSF_THREADS) {
+        for (int idx = tid; idx < N * 2 * P::GE; idx += NT) {
             const int st = idx / (2 * P::GE), rem = idx % (2 * P::GE), which = rem / P::GE, p = rem % P::GE;
             const float c = fk * sp[st * 12 + (which ? 1 : 2)];      // which=0: y axis, 1: x axis
             const float ic = floorf(c + 0.5f);
@@ -341,14 +696,22 @@ __global__ void __launch_bounds__(PSF_THREADS) k_psf_fit(PsfArgs A) {
             taps[(st * 4 + (which ? 2 : 0)) * LCB_GE_MAX + p] = e;
             taps[(st * 4 + (which ? 3 : 1)) * LCB_GE_MAX + p] = de;
         }
-        for (int i = tid; i < pp; i += PSF_THREADS) { GR[i] = 0.f; if (NGRP > 1) C0[i] = 0.f; }
+        for (int i = tid; i < pp; i += NT) { GR[i] = 0.f; if (NGRP > 1) C0[i] = 0.f; }
         __syncthreads();
+        PHASE(0)
 
         float chi = 0.f, cnt = 0.f;
         // FAST: the CTA works on NGRP stars at a time, one per group of GT threads, each group with its own
         // scratch planes, its own gradient plane (group 1 accumulates into C0, free until the starlet phase)
         // and its own named barrier: task counts per pass are exact multiples of GT, and while one group
         // waits at a barrier the other one issues.
+        float reg = 0.f;
+        const bool do_reg = (A.lam_scales != 0.f || A.lam_hf != 0.f);
+        if (SPEC && tid >= PSF_THREADS) {
+            if constexpr (SPEC) {
+                if (do_reg && !last) reg = starlet_reg_spec(Bp, C0, C1, sg, aux, Wf, A.lam_hf, A.lam_scales, J, tid - PSF_THREADS);
+            }
+        } else
         for (int st = grp; st < N; st += NGRP) {
             const float a = sp[st * 12], cx = fk * sp[st * 12 + 1], cy = fk * sp[st * 12 + 2];
             const int icx = (int)floorf(cx + 0.5f), icy = (int)floorf(cy + 0.5f);
@@ -358,12 +721,12 @@ __global__ void __launch_bounds__(PSF_THREADS) k_psf_fit(PsfArgs A) {
             if (hal) lcb_pass1<K, G, FAST>(S, nu, nu, n, icy, tp, tp + LCB_GE_MAX, Vg, Vd, ldv, ltid, GT);
             else lcb_pass1<K, G, false>(S, nu, nu, n, icy, tp, tp + LCB_GE_MAX, Vg, Vd, ldv, ltid, GT);
             group_sync();
+            PHASE(1)
             float ga = 0.f, gx = 0.f, gy = 0.f;
             const float* ds = dT + (size_t)st * nn;
             const float* ws = wT + (size_t)st * nn;
             float* resid = (last && A.residuals) ? A.residuals + (size_t)(i0 + st) * nn : nullptr;
-            auto consume = [&](int Y, int X, float m0, float mx, float my) {
-                const float d = ds[X * n + Y], w = ws[X * n + Y];
+            auto consume = [&](int Y, int X, float m0, float mx, float my, float d, float w) {
                 const float diff = fmaf(a, m0, -d);
                 const float r = w * diff;
                 rT[X * ldt + Y] = r;
@@ -376,25 +739,28 @@ __global__ void __launch_bounds__(PSF_THREADS) k_psf_fit(PsfArgs A) {
                     if (resid) resid[Y * n + X] = -diff;
                 }
             };
-            if (hal) lcb_pass2<K, G, (FAST ? 2 : 4), FAST>(Vg, Vd, ldv, nu, n, icx, tp + 2 * LCB_GE_MAX, tp + 3 * LCB_GE_MAX, ltid, GT, consume);
-            else lcb_pass2<K, G, (FAST ? 2 : 4), false>(Vg, Vd, ldv, nu, n, icx, tp + 2 * LCB_GE_MAX, tp + 3 * LCB_GE_MAX, ltid, GT, consume);
+            if (hal) lcb_pass2<K, G, (FAST ? 2 : 4), FAST>(Vg, Vd, ldv, nu, n, icx, tp + 2 * LCB_GE_MAX, tp + 3 * LCB_GE_MAX, ds, ws, n, ltid, GT, consume);
+            else lcb_pass2<K, G, (FAST ? 2 : 4), false>(Vg, Vd, ldv, nu, n, icx, tp + 2 * LCB_GE_MAX, tp + 3 * LCB_GE_MAX, ds, ws, n, ltid, GT, consume);
             ga = warp_sum(ga); gx = warp_sum(gx); gy = warp_sum(gy);
             if ((tid & 31) == 0) {
                 float* q = redS + (st * PSF_WARPS + (tid >> 5)) * 4;
                 q[0] = ga; q[1] = gx; q[2] = gy;
             }
             group_sync();
+            PHASE(2)
             if (last) continue;
             if (hal) lcb_pass2T<K, G, (FAST ? 2 : 4), FAST>(rT, ldt, nu, n, icx, tp + 2 * LCB_GE_MAX, Vbar, ldb, ltid, GT);
             else lcb_pass2T<K, G, (FAST ? 2 : 4), false>(rT, ldt, nu, n, icx, tp + 2 * LCB_GE_MAX, Vbar, ldb, ltid, GT);
             group_sync();
+            PHASE(3)
             auto emit = [&](int v, int u, float val) { GRg[v * nu + u] = fmaf(a, val, GRg[v * nu + u]); };
             if (hal) lcb_pass1T<K, G, FAST>(Vbar, ldb, nu, n, icy, tp, ltid, GT, emit);
             else lcb_pass1T<K, G, false>(Vbar, ldb, nu, n, icy, tp, ltid, GT, emit);
         }
         __syncthreads();
+        PHASE(4)
         if (NGRP > 1 && !last) {
-            for (int i = tid; i < pp; i += PSF_THREADS) GR[i] += C0[i];
+            for (int i = tid; i < pp; i += NT) GR[i] += C0[i];
         }
         // ---- per-star gradients (threads st < N)
         float gn2 = 0.f;
@@ -412,24 +778,27 @@ __global__ void __launch_bounds__(PSF_THREADS) k_psf_fit(PsfArgs A) {
         }
         if (last) {
             float v2[2] = {chi, cnt};
-            block_reduce<2>(v2, red, tid);
+            block_reduce<2, NW>(v2, red, tid);
             if (tid == 0 && A.chi2) A.chi2[f] = v2[0] / fmaxf(v2[1], 1.f);
             break;
         }
 
         // ---- starlet regulariser: forward transform, loss, t_j = lambda_j W_j sign(alpha_j)
-        float reg = 0.f;
-        const bool do_reg = (A.lam_scales != 0.f || A.lam_hf != 0.f);
-        if (do_reg && FAST) {
-            if constexpr (FAST) reg = starlet_reg_fast<NS * K>(Bp, C0, C1, sg, aux, Wf, A.lam_hf, A.lam_scales, J, tid);
+        if (SPEC) {
+            // already computed by the starlet warps, concurrently with the star passes
+        } else if (do_reg && FAST) {
+            if constexpr (FAST) {
+                if constexpr (NS * K == 64) reg = starlet_reg_fast4(Bp, C0, C1, sg, aux, Wf, A.lam_hf, A.lam_scales, J, tid);
+                else reg = starlet_reg_fast<NS * K>(Bp, C0, C1, sg, aux, Wf, A.lam_hf, A.lam_scales, J, tid);
+            }
         } else if (do_reg) {
             for (int j = 0; j < J; ++j) {
                 const int D = 1 << j;
                 const float* cur = (j == 0) ? Bp : C0;
-                for (int i = tid; i < pp; i += PSF_THREADS) C1[i] = atrous_fwd(cur, nu, i / nu, i % nu, D, 0);
+                for (int i = tid; i < pp; i += NT) C1[i] = atrous_fwd(cur, nu, i / nu, i % nu, D, 0);
                 __syncthreads();
                 const float lam = (j == 0) ? A.lam_hf : A.lam_scales;
-                for (int i = tid; i < pp; i += PSF_THREADS) {
+                for (int i = tid; i < pp; i += NT) {
                     const float nxt = atrous_fwd(C1, nu, i / nu, i % nu, D, 1);
                     const float al = cur[i] - nxt;
                     const float lw = lam * (Wf ? __ldg(Wf + (size_t)j * pp + i) : 1.f);
@@ -442,32 +811,33 @@ __global__ void __launch_bounds__(PSF_THREADS) k_psf_fit(PsfArgs A) {
             // adjoint recursion: g_J = 0; g_j = t_j + H_j^T (g_{j+1} - t_j), H_j = Hcol Hrow
             for (int j = J - 1; j >= 0; --j) {
                 const int D = 1 << j;
-                for (int i = tid; i < pp; i += PSF_THREADS) {
+                for (int i = tid; i < pp; i += NT) {
                     const float t = Tj[(size_t)j * pp + i];
                     C0[i] = ((j == J - 1) ? 0.f : C0[i]) - t;
                 }
                 __syncthreads();
-                for (int i = tid; i < pp; i += PSF_THREADS)      // Hcol^T : along v for fixed u
+                for (int i = tid; i < pp; i += NT)      // Hcol^T : along v for fixed u
                     C1[i] = atrous_adj_line(C0 + (i % nu), nu, nu, i / nu, D);
                 __syncthreads();
-                for (int i = tid; i < pp; i += PSF_THREADS)      // Hrow^T : along u for fixed v
+                for (int i = tid; i < pp; i += NT)      // Hrow^T : along u for fixed v
                     C0[i] = Tj[(size_t)j * pp + i] + atrous_adj_line(C1 + (i / nu) * nu, 1, nu, i % nu, D);
                 __syncthreads();
             }
         }
+        PHASE(5)
         // ---- total gradient, norm, loss
-        for (int i = tid; i < pp; i += PSF_THREADS) {
+        for (int i = tid; i < pp; i += NT) {
             const float g = sc * GR[i] + (do_reg ? C0[i] : 0.f);
             GR[i] = g;
             gn2 = fmaf(g, g, gn2);
         }
         float v3[3] = {chi, reg, gn2};
-        block_reduce<3>(v3, red + (it & 1) * PSF_WARPS * 4, tid);
+        block_reduce<3, NW>(v3, red + (it & 1) * 32 * 4, tid);
         const float L = cv.half * v3[0] + v3[1];
         if (tid == 0 && A.loss_hist) A.loss_hist[(size_t)f * A.n_iter + it] = L;
         if (it == 0) {
             if (tid == 0 && A.loss0) A.loss0[f] = L;
-            if (A.grad_b0) for (int i = tid; i < pp; i += PSF_THREADS) A.grad_b0[(size_t)f * pp + i] = GR[i];
+            if (A.grad_b0) for (int i = tid; i < pp; i += NT) A.grad_b0[(size_t)f * pp + i] = GR[i];
             if (A.grad_s0 && tid < N) {
                 A.grad_s0[(i0 + tid) * 3] = sp[tid * 12 + 9];
                 A.grad_s0[(i0 + tid) * 3 + 1] = sp[tid * 12 + 10];
@@ -482,7 +852,7 @@ __global__ void __launch_bounds__(PSF_THREADS) k_psf_fit(PsfArgs A) {
         b1t *= cv.b1; b2t *= cv.b2;
         const BeliefCoef bc = {lr, cv.b1, cv.b2, 1.f - cv.b1, 1.f - cv.b2, 1.f / (1.f - b1t), 1.f / (1.f - b2t),
                                cv.eps, cv.eps_root};
-        for (int i = tid; i < pp; i += PSF_THREADS) {
+        for (int i = tid; i < pp; i += NT) {
             float b = Bp[i], mu = MU[i], nv = NU[i];
             belief_update(bc, cs * GR[i], b, mu, nv);
             Bp[i] = b; MU[i] = mu; NU[i] = nv;
@@ -498,19 +868,23 @@ __global__ void __launch_bounds__(PSF_THREADS) k_psf_fit(PsfArgs A) {
             q[2] = fminf(fmaxf(q[2], -lim), lim);
         }
         __syncthreads();
+        PHASE(6)
     }
+#ifdef LCB_PHASE_TIMERS
+    if (tid == 0 && A.loss_hist && A.n_iter >= 8) for (int k = 0; k < 8; ++k) A.loss_hist[(size_t)f * A.n_iter + k] = (float)ph[k];
+#endif
 
     // ---- products: fitted parameters, narrow_psf = s / sum s, full_psf = (s (*) g0) / sum
     __syncthreads();
-    for (int i = tid; i < pp; i += PSF_THREADS) A.b[(size_t)f * pp + i] = Bp[i];
+    for (int i = tid; i < pp; i += NT) A.b[(size_t)f * pp + i] = Bp[i];
     if (tid < N) { A.a[i0 + tid] = sp[tid * 12]; A.x0[i0 + tid] = sp[tid * 12 + 1]; A.y0[i0 + tid] = sp[tid * 12 + 2]; }
     if (tid == 0 && A.status) A.status[f] = bad ? LCB_ITEM_NONFINITE : LCB_ITEM_OK;
     if (A.narrow_psf || A.full_psf) {
         float tot[1] = {0.f};
-        for (int i = tid; i < pp; i += PSF_THREADS) tot[0] += S[i];
-        block_reduce<1>(tot, red, tid);
+        for (int i = tid; i < pp; i += NT) tot[0] += S[i];
+        block_reduce<1, NW>(tot, red, tid);
         const float inv = 1.f / tot[0];
-        if (A.narrow_psf) for (int i = tid; i < pp; i += PSF_THREADS) A.narrow_psf[(size_t)f * pp + i] = S[i] * inv;
+        if (A.narrow_psf) for (int i = tid; i < pp; i += NT) A.narrow_psf[(size_t)f * pp + i] = S[i] * inv;
         if (A.full_psf) {
             float g0[G];
 #pragma unroll
@@ -519,7 +893,7 @@ __global__ void __launch_bounds__(PSF_THREADS) k_psf_fit(PsfArgs A) {
                 g0[t] = cv.gnorm * expf(-x * x * cv.inv2s2);
             }
             __syncthreads();
-            for (int i = tid; i < pp; i += PSF_THREADS) {
+            for (int i = tid; i < pp; i += NT) {
                 const int v = i / nu, u = i % nu;
                 float acc = 0.f;
 #pragma unroll
@@ -531,7 +905,7 @@ __global__ void __launch_bounds__(PSF_THREADS) k_psf_fit(PsfArgs A) {
             }
             __syncthreads();
             float tf[1] = {0.f};
-            for (int i = tid; i < pp; i += PSF_THREADS) {
+            for (int i = tid; i < pp; i += NT) {
                 const int v = i / nu, u = i % nu;
                 float acc = 0.f;
 #pragma unroll
@@ -542,15 +916,15 @@ __global__ void __launch_bounds__(PSF_THREADS) k_psf_fit(PsfArgs A) {
                 C0[i] = acc;
                 tf[0] += acc;
             }
-            block_reduce<1>(tf, red + PSF_WARPS * 4, tid);
+            block_reduce<1, NW>(tf, red + 32 * 4, tid);
             const float invf = 1.f / tf[0];
-            for (int i = tid; i < pp; i += PSF_THREADS) A.full_psf[(size_t)f * pp + i] = C0[i] * invf;
+            for (int i = tid; i < pp; i += NT) A.full_psf[(size_t)f * pp + i] = C0[i] * invf;
         }
     }
 }
 
 size_t lcb_psf_fit_smem_small(int n, int nu, int Nmax) {
-    return (size_t)(Nmax * 4 * LCB_GE_MAX + Nmax * 12 + Nmax * PSF_WARPS * 4 + 2 * PSF_WARPS * 4 +
+    return (size_t)(Nmax * 4 * LCB_GE_MAX + Nmax * 12 + Nmax * PSF_WARPS * 4 + 2 * 32 * 4 +
                     2 * nu * (n + 1) + n * (n + 1) + n * (nu + 1)) * 4;
 }
 
@@ -569,7 +943,7 @@ bool lcb_psf_fit_has_fast(int n, int k, int G) {
 template <int K, int G, int NS>
 static int launch_psf_fit(const PsfArgs& A, size_t smem, cudaStream_t st) {
     LCB_CUDA(cudaFuncSetAttribute(k_psf_fit<K, G, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    { LcbProfScope ps("k_psf_fit", st); k_psf_fit<K, G, NS><<<A.F, PSF_THREADS, smem, st>>>(A); }
+    { LcbProfScope ps("k_psf_fit", st); k_psf_fit<K, G, NS><<<A.F, FIT_THREADS(K, NS), smem, st>>>(A); }
     LCB_CUDA(cudaGetLastError());
     return LCB_OK;
 }

@@ -233,8 +233,8 @@ __global__ void __launch_bounds__(PSF_THREADS) k_psf_moffat_lm(PsfArgs A) {
             for (int c = 0; c < 5; ++c) {
                 lcb_pass1<K, G>(planes + (size_t)c * pp, nu, nu, n, icy, tp, tp + LCB_GE_MAX, Vg, Vd, ldv, tid, PSF_THREADS);
                 __syncthreads();
-                lcb_pass2<K, G>(Vg, Vd, ldv, nu, n, icx, tp + 2 * LCB_GE_MAX, tp + 3 * LCB_GE_MAX, tid, PSF_THREADS,
-                                [&](int Y, int X, float m0, float mx, float my) {
+                lcb_pass2<K, G>(Vg, Vd, ldv, nu, n, icx, tp + 2 * LCB_GE_MAX, tp + 3 * LCB_GE_MAX, nullptr, nullptr, 0, tid, PSF_THREADS,
+                                [&](int Y, int X, float m0, float mx, float my, float, float) {
                                     const int o = X * ldt + Y;
                                     if (c == 0) {
                                         Jim[4 * n * ldt + o] = m0;
