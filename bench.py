@@ -99,7 +99,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ CPU baseline (oracle port)
-def cpu_baseline_run(sample_frames=4, t1=10, t2=20, tphot=20):
+def cpu_baseline_run(sample_frames=8, t1=10, t2=60, tphot=60):
     """Times the oracle (restated STARRED model, PyTorch CPU float32, all host threads) on a bounded
     sample of cfg2 and scales linearly in the iteration counts to (T1, T2, Tphot)."""
     import torch
@@ -164,6 +164,98 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------ cfg4: joint deconvolution
+def run_deconv(args):
+    """BASELINE cfg4: 200 epochs x 64x64, subsampling 2 (128x128 background), 4 point sources, P = 64; stage 2
+    of roi_modelling.py:326-335 (AdaBelief lr 1e-4, no schedule), epochs block-sharded over the ranks (strong
+    scaling), one all-reduce of nu^2 + 2M + 2 floats per iteration.  One step = --iters-per-step iterations."""
+    import torch
+    import torch.distributed as dist
+    from lightcurver_b200 import _lib, synthetic
+    from lightcurver_b200.processes.roi_modelling import JointDeconvolution, epoch_shard
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    group = None
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        group = dist.group.WORLD
+    E, n, k, M, npsf = 200, 64, 2, 4, 32
+    nu, P = n * k, npsf * k
+    sl = epoch_shard(E, rank, world)
+    Eloc = sl.stop - sl.start
+    t = synthetic.make_deconv_epochs(E, n, k, M=M, n_psf=npsf)
+    rng = np.random.default_rng(synthetic.SEEDS['cfg4'] + 1)
+    # render the truth with the library itself (data generator), add noise with the cutout_making.py:45 law
+    gen = JointDeconvolution(np.zeros((Eloc, n, n), np.float32), np.ones((Eloc, n, n), np.float32), t['psf'][sl], k, M)
+    gen.set_params(h=t['h'].reshape(-1), mean=np.zeros(Eloc), a=t['a'][sl], c_x=t['c_x'], c_y=t['c_y'], dx=t['dx'][sl],
+                   dy=t['dy'][sl], alpha=np.zeros(Eloc))
+    clean = gen.get()['model'].astype(np.float64)
+    gen.close()
+    sky = t['sky'][sl][:, None, None]
+    noise = np.random.default_rng(1000 + rank).standard_normal(clean.shape)
+    data = clean + np.sqrt(sky ** 2 + np.abs(clean)) * noise
+    sig = np.sqrt(sky ** 2 + np.abs(data))
+    scale = 1.0 / 3000.0
+    jd = JointDeconvolution((data * scale).astype(np.float32), (1.0 / (sig * scale) ** 2).astype(np.float32), t['psf'][sl], k, M)
+    jd.set_params(h=np.zeros(nu * nu), mean=np.zeros(Eloc), a=t['a'][sl] * scale * rng.uniform(0.9, 1.1, (E, M))[sl],
+                  c_x=t['c_x'], c_y=t['c_y'], dx=np.zeros(Eloc), dy=np.zeros(Eloc), alpha=np.zeros(Eloc))
+    jd.set_reg(1.0, 1.0, 100.0)
+    W = jd.noise_weights(group)
+    T = args.iters_per_step
+    fp32_peak, _ = _lib.fp32_peak(8192)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        jd.run(T, lr=1e-4, schedule=False, group=group)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.profile_enable(True)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    hist = None
+    for i in range(args.steps):
+        ev[i][0].record()
+        hist = jd.run(T, lr=1e-4, schedule=False, group=group)
+        ev[i][1].record()
+    barrier()
+    prof = _lib.profile_summary()
+    _lib.profile_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+    ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    tt = torch.tensor([ms], device='cuda')
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = float(tt.item())
+    if rank == 0:
+        C = sum(min(nu, v + (P - 1) // 2 + 1) - max(0, v - P // 2) for v in range(nu)) ** 2     # in-bounds MACs of 'same' PxP on nu x nu
+        flop_it = E * (4 * C + M * 14 * CFG['G'] * nu * nu + 16 * nu * nu)
+        kep = prof.get('k_deconv_epoch', {'ms': 0.0, 'launches': 1})
+        ach = (flop_it / world) / (kep['ms'] / max(kep['launches'], 1) * 1e-3) / 1e12 if kep['ms'] else 0.0
+        line = {"metric": "joint deconvolution iterations/s (cfg4: 200 epochs x 64x64, ss2, 4 point sources, starlet reg)",
+                "value": T / (ms * 1e-3), "unit": "it/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": {"workload": f"cfg4 joint deconvolution, {T} AdaBelief iterations per step, "
+                                                            f"{E} epochs sharded {world}-way, P={P}, M={M}", "E": E, "n": n, "k": k, "M": M, "P": P,
+                                                "collective": "1 NCCL all-reduce of nu^2+2M+2 floats per iteration" if world > 1 else "none",
+                                                "loss_first_last": [float(hist[0]), float(hist[-1])]},
+                "clocks": clocks, "gpu_launches": sum(v['launches'] for v in prof.values()), "kernels": prof,
+                "roofline": {"bound": "fp32", "kernel": "k_deconv_epoch", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
+                             "frac": ach / fp32_peak if fp32_peak else None, "traffic": None,
+                             "algorithmic_flop_per_iteration": flop_it}}
+        print(json.dumps(line))
+    jd.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------ our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -173,9 +265,14 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--frames', type=int, default=CFG['F'], help=argparse.SUPPRESS)
     ap.add_argument('--no-cpu-baseline', action='store_true', help=argparse.SUPPRESS)
+    ap.add_argument('--workload', default='psfphot', choices=['psfphot', 'deconv'],
+                    help='psfphot (default, BASELINE cfg2) or deconv (cfg4: joint deconvolution iterations/s, epochs sharded over ranks)')
+    ap.add_argument('--iters-per-step', type=int, default=50, help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
+    if args.workload == 'deconv':
+        return run_deconv(args)
 
     import torch
     import torch.distributed as dist

@@ -21,6 +21,7 @@
 // plain 2-D correlation of an n x n plane with an NA x NA kernel (NA ~ P/k + 1): 4x fewer MACs than
 // convolving at full resolution, and lanes <-> rows with an odd leading dimension is conflict free.
 #include "lcb_common.cuh"
+#include <cooperative_groups.h>
 #include <vector>
 
 void lcb_build_noise_table(int nu, int J, std::vector<float>& tab);
@@ -50,6 +51,7 @@ struct DeconvDev {
     float *eloss;                        // [E]
     float *red;                          // [nu^2 + 2M + 2] reduced: dL/dh, dL/dc, loss, |g_epoch|^2
     float *ctl;                          // [8] clip scale, lr, 1/bc1, 1/bc2, pending flag, loss
+    float *gpart;                        // [8][DU_CTAS] cross-CTA partial sums of k_deconv_update
     float *planes;                       // [3][nu^2] starlet scratch + Tj [J][nu^2]
     float *model;                        // [E][n][n] (written when requested)
     float *loss_hist;                    // [cap]
@@ -459,57 +461,75 @@ __device__ __forceinline__ float atrous_adj(const float* __restrict__ base, int 
 }
 
 #define DU_THREADS 1024
-__device__ __forceinline__ float block_sum_u(float v, float* red, int tid) {
+#define DU_CTAS 8
+// The replicated half of an iteration runs on ONE thread-block cluster of 8 CTAs (8192 threads): the nu x nu
+// planes live in global memory (L2), every stencil / point-wise pass is spread over the whole cluster and
+// passes are separated by cluster.sync() (barrier.cluster arrive.release / wait.acquire, ~0.3 us) instead of
+// kernel boundaries.  Cross-CTA sums go through a small global array in a fixed order (deterministic).
+namespace cg = cooperative_groups;
+
+__device__ __forceinline__ float cluster_sum(float v, float* red, float* gpart, int slot, int tid, int rank) {
     v = warp_sum(v);
     __syncthreads();
     if ((tid & 31) == 0) red[tid >> 5] = v;
     __syncthreads();
+    if (tid == 0) {
+        float s = 0.f;
+        for (int w = 0; w < DU_THREADS / 32; ++w) s += red[w];
+        gpart[slot * DU_CTAS + rank] = s;
+    }
+    cg::this_cluster().sync();
     float s = 0.f;
-    for (int w = 0; w < DU_THREADS / 32; ++w) s += red[w];
+    for (int c = 0; c < DU_CTAS; ++c) s += gpart[slot * DU_CTAS + c];
     return s;
 }
 
-// it < 0: evaluation only (loss + full gradient into red / planes, no update)
-__global__ void __launch_bounds__(DU_THREADS) k_deconv_update(DeconvDev D, int it, int n_iter, float lr0, int schedule,
-                                                              float* grad_h_out, float* grad_c_out, float* loss_out) {
+// it < 0: evaluation only (loss + full gradient into the output arrays, no update)
+__global__ void __cluster_dims__(DU_CTAS, 1, 1) __launch_bounds__(DU_THREADS)
+k_deconv_update(DeconvDev D, int it, int n_iter, float lr0, int schedule, float* grad_h_out, float* grad_c_out, float* loss_out) {
     __shared__ float red[DU_THREADS / 32];
-    const int tid = threadIdx.x, nu = D.nu, pp = nu * nu, M = D.M, J = D.J;
+    cg::cluster_group cl = cg::this_cluster();
+    const int rank = (int)cl.block_rank();
+    const int tid = threadIdx.x, gtid = rank * DU_THREADS + tid;
+    constexpr int GT_ALL = DU_CTAS * DU_THREADS;
+    const int nu = D.nu, pp = nu * nu, M = D.M, J = D.J;
     float* C0 = D.planes;
     float* C1 = C0 + pp;
     float* GT = C1 + pp;                 // total gradient wrt h
     float* Tj = GT + pp;                 // [J][pp]
+    float* gpart = D.gpart;              // [8 slots][DU_CTAS]
     float reg = 0.f;
     const bool do_reg = D.free_h && (D.lam_scales != 0.f || D.lam_hf != 0.f);
     if (do_reg) {
         for (int j = 0; j < J; ++j) {
             const int Dd = 1 << j;
             const float* cur = (j == 0) ? D.h : C0;
-            for (int i = tid; i < pp; i += DU_THREADS) C1[i] = atrous_g(cur, nu, i / nu, i % nu, Dd, 0);
-            __syncthreads();
+            for (int i = gtid; i < pp; i += GT_ALL) C1[i] = atrous_g(cur, nu, i / nu, i % nu, Dd, 0);
+            cl.sync();
             const float lam = (j == 0) ? D.lam_hf : D.lam_scales;
-            for (int i = tid; i < pp; i += DU_THREADS) {
+            for (int i = gtid; i < pp; i += GT_ALL) {
                 const float nxt = atrous_g(C1, nu, i / nu, i % nu, Dd, 1);
                 const float al = cur[i] - nxt;
                 const float lw = lam * (D.W ? D.W[(size_t)j * pp + i] : 1.f);
                 reg = fmaf(lw, fabsf(al), reg);
                 Tj[(size_t)j * pp + i] = (al > 0.f) ? lw : (al < 0.f) ? -lw : 0.f;
-                C0[i] = nxt;
+                C0[i] = nxt;             // in place: cur[i] is only read by the owner of pixel i in this pass
             }
-            __syncthreads();
+            cl.sync();
         }
         for (int j = J - 1; j >= 0; --j) {
             const int Dd = 1 << j;
-            for (int i = tid; i < pp; i += DU_THREADS) C0[i] = ((j == J - 1) ? 0.f : C0[i]) - Tj[(size_t)j * pp + i];
-            __syncthreads();
-            for (int i = tid; i < pp; i += DU_THREADS) C1[i] = atrous_adj(C0 + (i % nu), nu, nu, i / nu, Dd);
-            __syncthreads();
-            for (int i = tid; i < pp; i += DU_THREADS) C0[i] = Tj[(size_t)j * pp + i] + atrous_adj(C1 + (i / nu) * nu, 1, nu, i % nu, Dd);
-            __syncthreads();
+            for (int i = gtid; i < pp; i += GT_ALL) C0[i] = ((j == J - 1) ? 0.f : C0[i]) - Tj[(size_t)j * pp + i];
+            cl.sync();
+            for (int i = gtid; i < pp; i += GT_ALL) C1[i] = atrous_adj(C0 + (i % nu), nu, nu, i / nu, Dd);
+            cl.sync();
+            for (int i = gtid; i < pp; i += GT_ALL) C0[i] = Tj[(size_t)j * pp + i] + atrous_adj(C1 + (i / nu) * nu, 1, nu, i % nu, Dd);
+            cl.sync();
         }
     }
     float gn2 = 0.f, pos = 0.f;
     if (D.free_h) {
-        for (int i = tid; i < pp; i += DU_THREADS) {
+        for (int i = gtid; i < pp; i += GT_ALL) {
             const float hv = D.h[i];
             float g = D.red[i] + (do_reg ? C0[i] : 0.f);
             if (D.lam_pos != 0.f && hv < 0.f) { g -= D.lam_pos; pos -= D.lam_pos * hv; }
@@ -518,7 +538,7 @@ __global__ void __launch_bounds__(DU_THREADS) k_deconv_update(DeconvDev D, int i
             if (grad_h_out) grad_h_out[i] = g;
         }
     }
-    // c_x, c_y gradients (+ prior)
+    // c_x, c_y gradients (+ prior): every CTA computes them redundantly (identical), only rank 0 counts them
     float prior_loss = 0.f;
     __shared__ float gcs[2 * DC_MMAX];
     if (tid < 2 * M) {
@@ -528,24 +548,23 @@ __global__ void __launch_bounds__(DU_THREADS) k_deconv_update(DeconvDev D, int i
             const float mu = D.prior[(2 * ax) * M + m], sg = D.prior[(2 * ax + 1) * M + m];
             const float z = (D.c[tid] - mu) / sg;
             g += z / sg;
-            prior_loss = 0.5f * z * z;
+            if (rank == 0) prior_loss = 0.5f * z * z;
         }
         gcs[tid] = g;
-        if (grad_c_out) grad_c_out[tid] = g;
-        if (D.free_c) gn2 = fmaf(g, g, gn2);
+        if (grad_c_out && rank == 0) grad_c_out[tid] = g;
+        if (D.free_c && rank == 0) gn2 = fmaf(g, g, gn2);
     }
-    reg = block_sum_u(reg, red, tid);
-    pos = block_sum_u(pos, red, tid);
-    prior_loss = block_sum_u(prior_loss, red, tid);
-    gn2 = block_sum_u(gn2, red, tid) + D.red[pp + 2 * M + 1];
+    reg = cluster_sum(reg, red, gpart, 0, tid, rank);
+    pos = cluster_sum(pos, red, gpart, 1, tid, rank);
+    prior_loss = cluster_sum(prior_loss, red, gpart, 2, tid, rank);
+    gn2 = cluster_sum(gn2, red, gpart, 3, tid, rank) + D.red[pp + 2 * M + 1];
     const float L = D.red[pp + 2 * M] + reg + pos + prior_loss;
-    if (tid == 0) {
+    if (gtid == 0) {
         if (loss_out) loss_out[0] = L;
         if (it >= 0 && D.loss_hist) D.loss_hist[it] = L;
         D.ctl[5] = L;
     }
     if (it < 0) return;
-    // ---- optimiser coefficients; per-epoch parameters are updated by the next k_deconv_epoch launch
     float cs = 1.f, lr = lr0;
     if (schedule) {
         const float gn = sqrtf(gn2);
@@ -556,18 +575,18 @@ __global__ void __launch_bounds__(DU_THREADS) k_deconv_update(DeconvDev D, int i
     const BeliefCoef bc = {lr, D.cv.b1, D.cv.b2, 1.f - D.cv.b1, 1.f - D.cv.b2, 1.f / (1.f - b1t), 1.f / (1.f - b2t),
                            D.cv.eps, D.cv.eps_root};
     if (D.free_h) {
-        for (int i = tid; i < pp; i += DU_THREADS) {
+        for (int i = gtid; i < pp; i += GT_ALL) {
             float hv = D.h[i], mu = D.h_mu[i], nv = D.h_nu[i];
             belief_update(bc, cs * GT[i], hv, mu, nv);
             D.h[i] = hv; D.h_mu[i] = mu; D.h_nu[i] = nv;
         }
     }
-    if (D.free_c && tid < 2 * M) {
+    if (D.free_c && rank == 0 && tid < 2 * M) {
         float cvv = D.c[tid], mu = D.c_mu[tid], nv = D.c_nu[tid];
         belief_update(bc, cs * gcs[tid], cvv, mu, nv);
         D.c[tid] = cvv; D.c_mu[tid] = mu; D.c_nu[tid] = nv;
     }
-    if (tid == 0) { D.ctl[0] = cs; D.ctl[1] = lr; D.ctl[2] = bc.inv_bc1; D.ctl[3] = bc.inv_bc2; D.ctl[4] = 1.f; }
+    if (gtid == 0) { D.ctl[0] = cs; D.ctl[1] = lr; D.ctl[2] = bc.inv_bc1; D.ctl[3] = bc.inv_bc2; D.ctl[4] = 1.f; }
 }
 
 // ================================================================= host side: handle-based ABI
@@ -640,7 +659,7 @@ int lcb_deconv_create(const lcb_deconv_problem* p, int mem, void* stream, void**
     AL(c, 2 * (size_t)DC_MMAX, true) AL(c_mu, 2 * (size_t)DC_MMAX, true) AL(c_nu, 2 * (size_t)DC_MMAX, true)
     AL(ep, E * np, true) AL(ep_mu, E * np, true) AL(ep_nu, E * np, true) AL(ep_g, E * np, true)
     AL(alpha, E, true) AL(Gh, E * pp, true) AL(gc, E * 2 * (size_t)DC_MMAX, true) AL(eloss, E, true)
-    AL(red, pp + 2 * DC_MMAX + 2, true) AL(ctl, 8, true) AL(planes, (3 + (size_t)J) * pp, true)
+    AL(red, pp + 2 * DC_MMAX + 2, true) AL(ctl, 8, true) AL(gpart, 64, true) AL(planes, (3 + (size_t)J) * pp, true)
     AL(model, E * nn, true) AL(prior, 4 * (size_t)DC_MMAX, true)
 #undef AL
     D.W = nullptr;                                    // allocated by lcb_deconv_set_reg when weights are given
@@ -736,7 +755,7 @@ int lcb_deconv_step_update(void* handle, int it, int n_iter, float lr, int sched
     DeconvHandle* H = (DeconvHandle*)handle;
     LCB_REQUIRE(H, "lcb_deconv_step_update: NULL handle");
     { LcbProfScope ps("k_deconv_update", H->st);
-      k_deconv_update<<<1, DU_THREADS, 0, H->st>>>(H->D, it, n_iter, lr, schedule, nullptr, nullptr, nullptr); }
+      k_deconv_update<<<DU_CTAS, DU_THREADS, 0, H->st>>>(H->D, it, n_iter, lr, schedule, nullptr, nullptr, nullptr); }
     LCB_CUDA(cudaGetLastError());
     return LCB_OK;
 }
@@ -772,7 +791,7 @@ int lcb_deconv_loss_grad(void* handle, lcb_deconv_grad* g, int mem) {
     float *gh = nullptr, *gcx = nullptr, *ls = nullptr;
     if ((rc = dalloc(H, (void**)&gh, pp * 4, true)) || (rc = dalloc(H, (void**)&gcx, 2 * DC_MMAX * 4, true)) ||
         (rc = dalloc(H, (void**)&ls, 4, true))) return rc;
-    k_deconv_update<<<1, DU_THREADS, 0, H->st>>>(D, -1, 1, 0.f, 0, gh, gcx, ls);
+    k_deconv_update<<<DU_CTAS, DU_THREADS, 0, H->st>>>(D, -1, 1, 0.f, 0, gh, gcx, ls);
     LCB_CUDA(cudaGetLastError());
     if ((rc = get(H, g->loss, ls, 1, mem)) || (rc = get(H, g->h, gh, pp, mem)) || (rc = get(H, g->c_x, gcx, D.M, mem)) ||
         (rc = get(H, g->c_y, gcx + D.M, D.M, mem))) return rc;
@@ -797,7 +816,7 @@ int lcb_deconv_get(void* handle, lcb_deconv_params* q, float* model, float* loss
         if (loss) {
             float* ls = nullptr;
             if ((rc = dalloc(H, (void**)&ls, 4, true))) return rc;
-            k_deconv_update<<<1, DU_THREADS, 0, H->st>>>(D, -1, 1, 0.f, 0, nullptr, nullptr, ls);
+            k_deconv_update<<<DU_CTAS, DU_THREADS, 0, H->st>>>(D, -1, 1, 0.f, 0, nullptr, nullptr, ls);
             LCB_CUDA(cudaGetLastError());
             if ((rc = get(H, loss, ls, 1, mem))) return rc;
         }
