@@ -8,7 +8,7 @@
 #define LCB_JMAX 8
 
 struct PsfArgs {
-    int F, n, k, nu, J, n_iter, n_iter_lm, Nmax, planes_in_smem;
+    int F, n, k, nu, J, n_iter, n_iter_lm, Nmax, planes_in_smem, jim_in_smem;
     float lr, lam_scales, lam_hf;
     const int* star_off;            // [F+1] CSR offsets into the star arrays
     const float *data, *weight;     // [sumN][n][n]

@@ -75,7 +75,9 @@ static int psf_run_device(const lcb_psf_batch* in, const lcb_psf_opts* opt, lcb_
                 "psf fit: n=%d k=%d Nmax=%d needs %zu B of shared memory (> %d)", n, k, Nmax,
                 fit_small > lm_small ? fit_small : lm_small, maxsm);
     const bool fit_planes_sm = fit_small + (size_t)7 * pp * 4 <= (size_t)maxsm;
-    const bool lm_planes_sm = lm_small + (size_t)5 * pp * 4 <= (size_t)maxsm;
+    const size_t lm_jim = (size_t)8 * n * (n + 1) * 4;
+    const bool lm_jim_sm = lm_small + lm_jim <= (size_t)maxsm;
+    const bool lm_planes_sm = lm_jim_sm && lm_small + lm_jim + (size_t)5 * pp * 4 <= (size_t)maxsm;
     const size_t wpf = (size_t)(J + 7) * pp + (size_t)2 * Nmax * n * n;   // floats per frame of workspace
     const bool fit_fast = lcb_psf_fit_has_fast(n, k, lcb_conv().gauss_taps) &&
                           fit_small + lcb_psf_fit_smem_fast_extra(n, nu, J) <= (size_t)maxsm;
@@ -130,7 +132,8 @@ static int psf_run_device(const lcb_psf_batch* in, const lcb_psf_opts* opt, lcb_
         A.cv = lcb_devconv();
         if (opt->n_iter_analytic > 0) {
             A.planes_in_smem = lm_planes_sm;
-            if ((rc = lcb_psf_lm_dispatch(A, lm_small + (lm_planes_sm ? (size_t)5 * pp * 4 : 0), st))) return rc;
+            A.jim_in_smem = lm_jim_sm;
+            if ((rc = lcb_psf_lm_dispatch(A, lm_small + (lm_jim_sm ? lm_jim : 0) + (lm_planes_sm ? (size_t)5 * pp * 4 : 0), st))) return rc;
         } else {
             if ((rc = lcb_moffat_image_launch(A, st))) return rc;
         }

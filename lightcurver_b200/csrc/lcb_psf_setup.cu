@@ -182,9 +182,10 @@ __global__ void __launch_bounds__(PSF_THREADS) k_psf_moffat_lm(PsfArgs A) {
     float* Vg = ctl + 8;                                // [nu][ldv]
     float* Vd = Vg + nu * ldv;
     float* Jim = Vd + nu * ldv;                         // [7][n][ldt] Jacobian images, [X][Y]
-    float* dfT = Jim + 7 * n * ldt;                     // [n][ldt] a*m0 - d
-    float* planes = dfT + n * ldt;                      // [5][pp]: s, ds/dtheta_c
+    float* planes = Jim + (A.jim_in_smem ? 8 * n * ldt : 0);   // [5][pp]: s, ds/dtheta_c
     if (!A.planes_in_smem) planes = A.work + (size_t)f * A.work_per_frame;
+    if (!A.jim_in_smem) Jim = A.work + (size_t)f * A.work_per_frame + (size_t)5 * pp;   // large stamps: L2
+    float* dfT = Jim + 7 * n * ldt;                     // [n][ldt] a*m0 - d
 
     const float* dat = A.data + (size_t)i0 * nn;
     const float* wgt = A.weight + (size_t)i0 * nn;
@@ -344,9 +345,10 @@ __global__ void __launch_bounds__(PSF_THREADS) k_psf_moffat_lm(PsfArgs A) {
     }
 }
 
+// without the Jacobian images (8 n (n+1) floats) and the 5 planes, which move to L2 when they do not fit
 size_t lcb_psf_lm_smem_small(int n, int nu, int Nmax) {
     return (size_t)(Nmax * 4 * LCB_GE_MAX + 2 * (4 + 3 * Nmax) + 2 * Nmax * LM_GRAM + PSF_WARPS * LM_GRAM + 8 +
-                    2 * nu * (n + 1) + 8 * n * (n + 1)) * 4;
+                    2 * nu * (n + 1)) * 4;
 }
 
 template <int K, int G>

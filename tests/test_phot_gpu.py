@@ -21,7 +21,7 @@ def _items(F, S, n, k, seed):
     return d, data, weight, idx, a0
 
 
-@pytest.mark.parametrize("n,k", [(32, 2), (16, 1), (24, 2), (18, 3)])
+@pytest.mark.parametrize("n,k", [(32, 2), (16, 1), (24, 2), (18, 3), (16, 2), (32, 1), (64, 3)])
 def test_phot_loss_grad_parity(cuda_device, n, k):
     from lightcurver_b200 import engine
     from oracle import starred_model as sm

@@ -29,7 +29,7 @@ def _flat(x):
     return x.reshape(-1, *x.shape[2:])
 
 
-@pytest.mark.parametrize("n,k,N", [(32, 2, 5), (16, 1, 3), (24, 2, 2), (18, 3, 4)])
+@pytest.mark.parametrize("n,k,N", [(32, 2, 5), (16, 1, 3), (24, 2, 2), (18, 3, 4), (16, 2, 3), (32, 1, 2), (64, 1, 2), (64, 3, 2)])
 def test_psf_loss_grad_parity(cuda_device, n, k, N):
     """Loss and full gradient (grid, a, x0, y0) at an arbitrary point, with W != 1."""
     from lightcurver_b200 import engine
@@ -185,3 +185,26 @@ def test_psf_ragged_batch_matches_single_frames(cuda_device):
         assert np.array_equal(one['narrow_psf'][0], out['narrow_psf'][f])
         assert np.array_equal(one['a'], out['a'][s])
         assert np.array_equal(one['loss_hist'][0], out['loss_hist'][f])
+
+
+def test_psf_large_offsets_use_predicated_passes(cuda_device):
+    """Stars more than 1 px off-centre leave the zero-halo fast path (per star) and must still match."""
+    from lightcurver_b200 import engine
+    from oracle import starred_model as sm
+    n, k, N, F = 32, 2, 4, 1
+    d, data, nm, weight, a0, off = _frames(F, N, n, k, seed=55)
+    nu = n * k
+    moffat = np.array([[3.2, 3.4, 0.2, 2.8, 1.0]])
+    x00 = np.array([[2.7, -3.1, 0.2, 1.6]], np.float32)
+    y00 = np.array([[-2.2, 0.4, 3.3, -1.4]], np.float32)
+    rng = np.random.default_rng(3)
+    b0 = (1e-4 * rng.standard_normal((F, nu, nu))).astype(np.float32)
+    out = engine.psf_fit_batch(_flat(data), _flat(weight), off, k, moffat, a0.ravel(), x00.ravel(), y00.ravel(),
+                               background0=b0, n_iter_analytic=0, n_iter_adabelief=1, lam_scales=0.0, lam_hf=0.0,
+                               want=('loss0', 'grad_b0', 'grad_s0'))
+    s_fixed = sm.moffat_image(moffat[:, 0], moffat[:, 1], moffat[:, 2], moffat[:, 3], n, k).numpy()
+    L, (gb, ga, gx, gy) = sm.psf_loss_grad(s_fixed, b0, a0, x00, y00, data, weight, None, n, k, 0.0, 0.0)
+    np.testing.assert_allclose(out['loss0'], L, rtol=1e-5)
+    np.testing.assert_allclose(out['grad_b0'], gb, rtol=1e-5, atol=1e-5 * np.abs(gb).max())
+    gs = np.stack([ga, gx, gy], -1).reshape(-1, 3)
+    np.testing.assert_allclose(out['grad_s0'], gs, rtol=2e-5, atol=1e-5 * np.abs(gs).max(0).max())
