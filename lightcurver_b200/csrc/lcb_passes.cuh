@@ -10,6 +10,23 @@
 #pragma once
 #include "lcb_common.cuh"
 
+// Taps are broadcast reads (every lane the same address): fetch them as 16-byte vectors, one shared-memory
+// wavefront per four taps instead of one per tap.  Tap arrays are 16-byte aligned and LCB_GE_MAX long.
+template <int GE>
+__device__ __forceinline__ void lcb_load_taps(const float* __restrict__ src, float (&dst)[GE]) {
+    constexpr int NV = (GE + 3) / 4;
+    static_assert(NV * 4 <= LCB_GE_MAX, "tap arrays are LCB_GE_MAX floats");
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const float4 t = s4[i];
+        if (4 * i + 0 < GE) dst[4 * i + 0] = t.x;
+        if (4 * i + 1 < GE) dst[4 * i + 1] = t.y;
+        if (4 * i + 2 < GE) dst[4 * i + 2] = t.z;
+        if (4 * i + 3 < GE) dst[4 * i + 3] = t.w;
+    }
+}
+
 template <int K, int G, int OBV = 4>
 struct LcbPass {
     static constexpr int GE = G + K - 1;   // effective taps after folding the k-box
@@ -27,8 +44,8 @@ __device__ __forceinline__ void lcb_pass1(const float* __restrict__ s, int lds, 
                                           int tid, int nthreads) {
     using P = LcbPass<K, G>;
     float ey[P::GE], dey[P::GE];
-#pragma unroll
-    for (int p = 0; p < P::GE; ++p) { ey[p] = ey_s[p]; dey[p] = dey_s[p]; }
+    lcb_load_taps<P::GE>(ey_s, ey);
+    lcb_load_taps<P::GE>(dey_s, dey);
     const int nyb = (n + P::OB - 1) / P::OB;
     for (int task = tid; task < nu * nyb; task += nthreads) {
         const int u = task % nu;
@@ -66,8 +83,8 @@ __device__ __forceinline__ void lcb_pass2(const float* __restrict__ Vg, const fl
                                           int tid, int nthreads, F&& consume) {
     using P = LcbPass<K, G, OBV>;
     float ex[P::GE], dex[P::GE];
-#pragma unroll
-    for (int p = 0; p < P::GE; ++p) { ex[p] = ex_s[p]; dex[p] = dex_s[p]; }
+    lcb_load_taps<P::GE>(ex_s, ex);
+    lcb_load_taps<P::GE>(dex_s, dex);
     const int nxb = (n + P::OB - 1) / P::OB;
     for (int task = tid; task < n * nxb; task += nthreads) {
         const int Y = task % n;
@@ -121,8 +138,7 @@ __device__ __forceinline__ void lcb_pass2T(const float* __restrict__ rT, int ldr
     constexpr int UB = K * P::OB;
     constexpr int ILO = -((P::GE - 1 + K - 1) / K);
     float ex[P::GE];
-#pragma unroll
-    for (int p = 0; p < P::GE; ++p) ex[p] = ex_s[p];
+    lcb_load_taps<P::GE>(ex_s, ex);
     const int off = icx + G / 2;
     const int S0 = K * lcb_floordiv(off, K);            // block grid origin: <= off, multiple of K
     const int nb = (nu + UB - 1) / UB;
@@ -181,8 +197,7 @@ __device__ __forceinline__ void lcb_pass1T(const float* __restrict__ Vbar, int l
     constexpr int UB = K * P::OB;
     constexpr int ILO = -((P::GE - 1 + K - 1) / K);
     float ey[P::GE];
-#pragma unroll
-    for (int p = 0; p < P::GE; ++p) ey[p] = ey_s[p];
+    lcb_load_taps<P::GE>(ey_s, ey);
     const int off = icy + G / 2;
     const int S0 = K * lcb_floordiv(off, K);            // <= off, multiple of K
     const int nb = (nu + UB - 1) / UB;                  // blocks covering v' in [S0, S0 + nb*UB)

@@ -58,22 +58,32 @@ def build_psf_batch(images, noisemaps, subsampling_factor, masks=None, n_iter_an
     sumN = int(off[-1])
     cat = lambda seq: (np.asarray(seq).reshape(sumN, n, n) if isinstance(seq, np.ndarray)
                        else np.concatenate([np.asarray(x) for x in seq]))
-    img = cat(images).astype(np.float32)
-    nm = cat(noisemaps).astype(np.float32)
-    mk = np.ones((sumN, n, n), bool) if masks is None else (cat(masks) > 0)
+    data = np.array(cat(images), dtype=np.float32)            # private copies (normalised in place below)
+    nm = np.array(cat(noisemaps), dtype=np.float32)
     counts_a = np.asarray(counts)
     # global normalisation per frame (A.4): stamps / (max(image) / psf_norm_scale)
-    star_max = np.nanmax(np.where(np.isfinite(img), img, -np.inf).reshape(sumN, -1), axis=1)
-    norms = np.maximum.reduceat(star_max, off[:-1]).astype(np.float64) / cv.psf_norm_scale
+    star_max = np.fmax.reduce(data.reshape(sumN, -1), axis=1)
+    norms = np.fmax.reduceat(star_max, off[:-1]).astype(np.float64) / cv.psf_norm_scale
     norms[~np.isfinite(norms) | (norms <= 0)] = 1.0
     inv = np.repeat(1.0 / norms, counts_a).astype(np.float32)[:, None, None]
-    data = img * inv
-    nm = nm * inv
-    good = mk & (nm > 0) & np.isfinite(nm) & np.isfinite(data)
-    weight = np.zeros_like(data)
-    np.divide(1.0, nm * nm, out=weight, where=good)
-    data[~np.isfinite(data)] = 0.0
-    flux = np.where(good, data, 0.0).sum((-1, -2), dtype=np.float64)
+    data *= inv
+    nm *= inv
+    good = np.isfinite(data)
+    good &= np.isfinite(nm)
+    good &= nm > 0
+    if masks is not None:
+        good &= (cat(masks) > 0)
+    all_good = bool(good.all())
+    if not all_good:
+        data[~np.isfinite(data)] = 0.0
+        nm[~good] = 1.0
+    np.multiply(nm, nm, out=nm)
+    weight = np.reciprocal(nm, out=nm)                        # 1 / sigma^2 in place
+    if not all_good:
+        weight[~good] = 0.0
+        flux = np.where(good, data, 0.0).sum((-1, -2), dtype=np.float64)
+    else:
+        flux = data.sum((-1, -2), dtype=np.float64)
     a0 = (np.maximum(flux, 1e-6) * (k * k if cv.downsample_mean else 1.0)).astype(np.float32)
     x00, y00 = _guess_positions(data, good, guess_method_star_position)
     fwhm = np.broadcast_to(np.asarray(3.0 if guess_fwhm_pixels is None else guess_fwhm_pixels, dtype=np.float64), (F,))

@@ -120,23 +120,33 @@ def star_photometry_batch(data, noisemap, psfs, subsampling_factor, n_iter=2000,
     cv = conventions
     k = int(subsampling_factor)
     F, S, n, _ = data.shape
-    d = np.array(data, dtype=np.float32)
+    d = np.array(data, dtype=np.float32)                      # private copies: the caller's arrays stay untouched
     nm = np.array(noisemap, dtype=np.float32)
-    isnan = np.isnan(d) | np.isnan(nm)
-    d[isnan] = 0.0
-    nm[isnan] = 1e7
+    isnan = np.isnan(d)
+    isnan |= np.isnan(nm)
+    if isnan.any():
+        d[isnan] = 0.0
+        nm[isnan] = 1e7
     if masks is not None:
-        bad_epoch = (~np.asarray(masks, bool)).any((-1, -2))
-        nm[bad_epoch] *= 1000.0
-    scale = np.nanmax(d, axis=(0, 2, 3))                      # (S,)
-    d /= scale[None, :, None, None]
-    nm /= scale[None, :, None, None]
-    a_est = np.stack([_initial_flux_guess(d[:, s]) for s in range(S)], 1)   # (F,S)
+        bad_epoch = ~np.asarray(masks, bool).all((-1, -2))
+        if bad_epoch.any():
+            nm[bad_epoch] *= 1000.0
+    scale = d.max(axis=(0, 2, 3))                             # (S,)  == nanmax: NaNs are gone
+    inv = (1.0 / scale).astype(np.float32)[None, :, None, None]
+    d *= inv
+    nm *= inv
+    # star_photometry.py:55-64 for all stars at once: one background scalar per star = mean over the four
+    # edges and all epochs of the edge medians
+    edges = np.stack([np.median(d[:, :, 0, :], -1), np.median(d[:, :, :, 0], -1),
+                      np.median(d[:, :, -1, :], -1), np.median(d[:, :, :, -1], -1)])       # (4,F,S)
+    background = np.nan_to_num(edges.mean((0, 1)), nan=0.0)                                  # (S,)
+    a_est = d.sum((-1, -2), dtype=np.float64) - (n * n) * background[None]                   # (F,S)
     if cv.downsample_mean:
         a_est = a_est * (k * k)
-    weight = 1.0 / (nm.astype(np.float64) ** 2)
+    np.multiply(nm, nm, out=nm)
+    weight = np.reciprocal(nm, out=nm)                        # 1 / sigma^2, float32, in place
     idx = np.repeat(np.arange(F, dtype=np.int32), S)
-    out = engine.phot_fit_batch(d.reshape(F * S, n, n), weight.astype(np.float32).reshape(F * S, n, n),
+    out = engine.phot_fit_batch(d.reshape(F * S, n, n), weight.reshape(F * S, n, n),
                                 np.ascontiguousarray(psfs, np.float32), idx, a_est.reshape(-1).astype(np.float32),
                                 k, n_iter, lr=1e-3, schedule=True, want_residuals=want_residuals,
                                 want_loss_hist=want_loss_hist)
