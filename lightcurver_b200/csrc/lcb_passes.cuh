@@ -37,12 +37,12 @@ struct LcbPass {
 // pass 1: s (nu x nu, leading dim lds, row-major, shared or global) -> Vg, Vd stored [u][Y] (ld ldv)
 // HALO = true: the caller guarantees that every input index touched lies inside zero-filled halos
 // (no bounds predicates, loads use immediate offsets from one base address).
-template <int K, int G, bool HALO = false>
+template <int K, int G, bool HALO = false, int OBV = 4>
 __device__ __forceinline__ void lcb_pass1(const float* __restrict__ s, int lds, int nu, int n, int icy,
                                           const float* __restrict__ ey_s, const float* __restrict__ dey_s,
                                           float* __restrict__ Vg, float* __restrict__ Vd, int ldv,
                                           int tid, int nthreads) {
-    using P = LcbPass<K, G>;
+    using P = LcbPass<K, G, OBV>;
     float ey[P::GE], dey[P::GE];
     lcb_load_taps<P::GE>(ey_s, ey);
     lcb_load_taps<P::GE>(dey_s, dey);
@@ -190,10 +190,10 @@ __device__ __forceinline__ void lcb_pass2T(const float* __restrict__ rT, int ldr
 // The block grid starts at V0 = K*floor(off/K) (any multiple of K keeps p = j - K*i static), so
 // nu/UB blocks cover all but at most K-1 trailing rows; those are finished by a short second loop
 // instead of a whole extra block per column (keeps the task count a multiple of the CTA size).
-template <int K, int G, bool HALO = false, typename F>
+template <int K, int G, bool HALO = false, int OBV = 4, typename F>
 __device__ __forceinline__ void lcb_pass1T(const float* __restrict__ Vbar, int ldb, int nu, int n, int icy,
                                            const float* __restrict__ ey_s, int tid, int nthreads, F&& emit) {
-    using P = LcbPass<K, G>;
+    using P = LcbPass<K, G, OBV>;
     constexpr int UB = K * P::OB;
     constexpr int ILO = -((P::GE - 1 + K - 1) / K);
     float ey[P::GE];

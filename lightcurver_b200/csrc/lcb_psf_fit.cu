@@ -85,15 +85,15 @@ __device__ __forceinline__ float atrous_adj_line(const float* __restrict__ base,
 // shuffles per row for the row direction), so no thread ever walks a line serially.
 // Returns the per-thread partial of the regulariser; leaves g_0 = d reg / d b in C0 (after a barrier).
 // aux: [2*GROUPS*NU + NU*NU/8 + 2*NU] floats of shared scratch.
-template <int NU>
+template <int NU, int NTH>
 __device__ __forceinline__ float starlet_reg_fast(const float* __restrict__ Bp, float* __restrict__ C0,
                                                   float* __restrict__ C1, signed char* __restrict__ sg,
                                                   float* __restrict__ aux,
                                                   const float* __restrict__ Wf, float lam_hf, float lam_scales,
                                                   int J, int tid) {
-    constexpr int GROUPS = PSF_THREADS / NU;
+    constexpr int GROUPS = NTH / NU;
     constexpr int ROWS = NU / GROUPS;
-    static_assert(ROWS == 8 || ROWS == 2, "chunk logic written for 8-row (NU=64) and 2-row (NU=32) groups");
+    static_assert(ROWS >= 2 && (ROWS & (ROWS - 1)) == 0, "rows per group must be a power of two");
     constexpr int CH = 8;                                // chunk length of the row-direction sums
     constexpr int PP = NU * NU;
     const float h0 = 1.f / 16.f, h1 = 4.f / 16.f, h2 = 6.f / 16.f;
@@ -264,31 +264,32 @@ __device__ __forceinline__ void f4_near(int D, float4 A, float4 B, float4 C, flo
     }
 }
 
+template <int NTH>
 __device__ __forceinline__ float starlet_reg_fast4(const float* __restrict__ Bp, float* __restrict__ C0,
                                                    float* __restrict__ C1, signed char* __restrict__ sg,
                                                    float* __restrict__ aux,
                                                    const float* __restrict__ Wf, float lam_hf, float lam_scales,
                                                    int J, int tid) {
-    constexpr int NU = 64, PP = NU * NU, QR = NU / 4, LDC = QR + 1;
+    constexpr int NU = 64, PP = NU * NU, QR = NU / 4, LDC = QR + 1, ROWS = NU * QR / NTH, PQ = PP / 4;
     const float h0 = 1.f / 16.f, h1 = 4.f / 16.f;
-    const int q = tid & (QR - 1), rg = tid >> 4, v0 = 2 * rg, u0 = 4 * q;
+    const int q = tid & (QR - 1), rg = tid >> 4, v0 = ROWS * rg, u0 = 4 * q;
     float* chkR = aux;                                   // [NU][LDC] quad sums of the rows of C1
     float* ext = chkR + NU * LDC;                        // [NU][2]
     auto L4 = [](const float* p) { return *reinterpret_cast<const float4*>(p); };
     auto S4 = [](float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; };
     float reg = 0.f;
-    float4 wreg[2];
+    float4 wreg[ROWS];
     for (int j = 0; j < J; ++j) {
         const int D = 1 << j;
         const float* cur = (j == 0) ? Bp : C0;
         const float lam = (j == 0) ? lam_hf : lam_scales;
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < ROWS; ++r) {
             float4 w = Wf ? __ldg(reinterpret_cast<const float4*>(Wf + (size_t)j * PP + (v0 + r) * NU + u0)) : f4_splat(1.f);
             wreg[r] = make_float4(lam * w.x, lam * w.y, lam * w.z, lam * w.w);
         }
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < ROWS; ++r) {
             const float* row = cur + (v0 + r) * NU;
             const float4 B = L4(row + u0);
             float4 l1, r1, l2, r2;
@@ -306,7 +307,7 @@ __device__ __forceinline__ float starlet_reg_fast4(const float* __restrict__ Bp,
         }
         __syncthreads();
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < ROWS; ++r) {
             const int v = v0 + r, idx = v * NU + u0;
             const int vm2 = max(v - 2 * D, 0), vm1 = max(v - D, 0), vp1 = min(v + D, NU - 1), vp2 = min(v + 2 * D, NU - 1);
             const float4 nxt = f4_b3(L4(C1 + idx), L4(C1 + vm1 * NU + u0), L4(C1 + vp1 * NU + u0), L4(C1 + vm2 * NU + u0), L4(C1 + vp2 * NU + u0));
@@ -314,10 +315,10 @@ __device__ __forceinline__ float starlet_reg_fast4(const float* __restrict__ Bp,
             const float4 al = make_float4(c.x - nxt.x, c.y - nxt.y, c.z - nxt.z, c.w - nxt.w);
             reg = fmaf(wreg[r].x, fabsf(al.x), reg); reg = fmaf(wreg[r].y, fabsf(al.y), reg);
             reg = fmaf(wreg[r].z, fabsf(al.z), reg); reg = fmaf(wreg[r].w, fabsf(al.w), reg);
-            char4 sgn;
-            sgn.x = (al.x > 0.f) ? 1 : (al.x < 0.f) ? -1 : 0; sgn.y = (al.y > 0.f) ? 1 : (al.y < 0.f) ? -1 : 0;
-            sgn.z = (al.z > 0.f) ? 1 : (al.z < 0.f) ? -1 : 0; sgn.w = (al.w > 0.f) ? 1 : (al.w < 0.f) ? -1 : 0;
-            *reinterpret_cast<char4*>(sg + j * PP + idx) = sgn;
+            // four signs packed in one byte, two bits each: 0 -> -1, 1 -> 0, 2 -> +1
+            const int sx = (al.x > 0.f) ? 2 : (al.x < 0.f) ? 0 : 1, sy = (al.y > 0.f) ? 2 : (al.y < 0.f) ? 0 : 1;
+            const int sz = (al.z > 0.f) ? 2 : (al.z < 0.f) ? 0 : 1, sw = (al.w > 0.f) ? 2 : (al.w < 0.f) ? 0 : 1;
+            sg[j * PQ + (idx >> 2)] = (signed char)(sx | (sy << 2) | (sz << 4) | (sw << 6));
             S4(C0 + idx, nxt);
         }
         __syncthreads();
@@ -325,13 +326,14 @@ __device__ __forceinline__ float starlet_reg_fast4(const float* __restrict__ Bp,
     for (int j = J - 1; j >= 0; --j) {
         const int D = 1 << j;
         const int m1 = min(D, NU), m2 = min(2 * D, NU);
-        float4 tj[2];
+        float4 tj[ROWS];
         // (1) q = g_{j+1} (+ row-pass border extras of the previous scale) - t_j
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < ROWS; ++r) {
             const int v = v0 + r, idx = v * NU + u0;
-            const char4 sgn = *reinterpret_cast<const char4*>(sg + j * PP + idx);
-            tj[r] = make_float4(wreg[r].x * (float)sgn.x, wreg[r].y * (float)sgn.y, wreg[r].z * (float)sgn.z, wreg[r].w * (float)sgn.w);
+            const int pk = (int)(unsigned char)sg[j * PQ + (idx >> 2)];
+            tj[r] = make_float4(wreg[r].x * (float)((pk & 3) - 1), wreg[r].y * (float)(((pk >> 2) & 3) - 1),
+                                wreg[r].z * (float)(((pk >> 4) & 3) - 1), wreg[r].w * (float)(((pk >> 6) & 3) - 1));
             float4 g = f4_splat(0.f);
             if (j != J - 1) {
                 g = L4(C0 + idx);
@@ -343,7 +345,7 @@ __device__ __forceinline__ float starlet_reg_fast4(const float* __restrict__ Bp,
         if (j > 0) {
             const float lamn = (j - 1 == 0) ? lam_hf : lam_scales;
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
+            for (int r = 0; r < ROWS; ++r) {
                 float4 w = Wf ? __ldg(reinterpret_cast<const float4*>(Wf + (size_t)(j - 1) * PP + (v0 + r) * NU + u0)) : f4_splat(1.f);
                 wreg[r] = make_float4(lamn * w.x, lamn * w.y, lamn * w.z, lamn * w.w);
             }
@@ -351,7 +353,7 @@ __device__ __forceinline__ float starlet_reg_fast4(const float* __restrict__ Bp,
         __syncthreads();
         // (2) Hcol^T (zero extension) + folded taps on rows 0 / NU-1, quad sums of the result
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < ROWS; ++r) {
             const int v = v0 + r, idx = v * NU + u0;
             const float4 z = f4_splat(0.f);
             float4 acc = f4_b3(L4(C0 + idx), (v - D >= 0) ? L4(C0 + idx - D * NU) : z, (v + D < NU) ? L4(C0 + idx + D * NU) : z,
@@ -372,7 +374,7 @@ __device__ __forceinline__ float starlet_reg_fast4(const float* __restrict__ Bp,
         __syncthreads();
         // (3) Hrow^T (zero extension) + t_j ; threads 0..127 prepare the folded extras of the rows
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < ROWS; ++r) {
             const float* row = C1 + (v0 + r) * NU;
             const float4 z = f4_splat(0.f);
             const float4 B = L4(row + u0);
@@ -411,7 +413,7 @@ __device__ __forceinline__ float starlet_reg_fast4(const float* __restrict__ Bp,
     }
     if (q == 0 || q == QR - 1) {
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < ROWS; ++r) {
             if (q == 0) C0[(v0 + r) * NU] += ext[(v0 + r) * 2];
             else C0[(v0 + r) * NU + NU - 1] += ext[(v0 + r) * 2 + 1];
         }
@@ -587,9 +589,11 @@ __device__ __noinline__ float starlet_reg_spec(const float* __restrict__ Bp, flo
 // cycles/iteration, 16 + 8 warps = 92k, against 85k for the sequential schedule on 16 warps -- the starlet
 // is 30 barrier-separated dependent phases and starves on few warps.  Set to the commented expression to re-enable.
 #define FIT_SPEC(K, NS) 0   /* ((NS) > 0 && (NS) * (K) == 64) */
-#define FIT_THREADS(K, NS) (FIT_SPEC(K, NS) ? PSF_THREADS + SPEC_THREADS : PSF_THREADS)
+// Fast path: 256-thread CTAs sized (registers <= 128, shared memory <= 113 KB) so that TWO frames are resident
+// per SM: the barrier-separated phases of one frame overlap with the other's instead of idling the SM.
+#define FIT_THREADS(K, NS) (FIT_SPEC(K, NS) ? PSF_THREADS + SPEC_THREADS : ((NS) > 0 ? 256 : PSF_THREADS))
 template <int K, int G, int NS>
-__global__ void __launch_bounds__(FIT_THREADS(K, NS)) k_psf_fit(PsfArgs A) {
+__global__ void __launch_bounds__(FIT_THREADS(K, NS), ((NS) > 0 ? 2 : 1)) k_psf_fit(PsfArgs A) {
     using P = LcbPass<K, G>;
     constexpr bool FAST = (NS > 0);
     constexpr bool SPEC = FIT_SPEC(K, NS);          // 64x64 grid: 16 star warps + 4 starlet warps run concurrently
@@ -605,19 +609,24 @@ __global__ void __launch_bounds__(FIT_THREADS(K, NS)) k_psf_fit(PsfArgs A) {
     const float fk = (float)K;
     const int J = A.J;
 
-    // ---- shared layout (small arrays first; the 7 planes last so that they can move to global)
+    // ---- shared layout.  FAST (<= 113 KB so that two CTAs share an SM): s (with halo), b, grad in shared memory;
+    // the starlet scratch planes C0, C1 alias the star-pass scratch (Vg, Vd, r^T, Vbar: disjoint phases, the region
+    // is re-zeroed every iteration for the halos); AdaBelief moments live in the L2-resident workspace (touched once
+    // per iteration, coalesced); signs are packed 4 per byte (64-wide grid).  Generic: 7 planes, shared if they fit.
     float* taps = sm;                                   // [Nmax][4][LCB_GE_MAX]
     float* sp = taps + A.Nmax * 4 * LCB_GE_MAX;         // [Nmax][12] a,x0,y0, mu3, nu3, g3
     float* redS = sp + A.Nmax * 12;                     // [Nmax][PSF_WARPS][4]
     float* red = redS + A.Nmax * PSF_WARPS * 4;         // [2][32 warps][4]
     // FAST: every plane read by the passes carries HB zero rows before and after (no bounds predicates)
     constexpr int HB = FAST ? 8 : 0;
-    float* Vg = red + 2 * 32 * 4 + HB * ldv;     // [HB + nu + HB][ldv]
+    float* scr = red + 2 * 32 * 4;                      // start of the star-pass scratch
+    float* Vg = scr + HB * ldv;                         // [HB + nu + HB][ldv]
     float* Vd = Vg + (nu + 2 * HB) * ldv;               // [HB + nu + HB][ldv]
     float* rT = Vd + (nu + HB) * ldv + HB * ldt;        // [HB + n + HB][ldt]
     float* Vbar = rT + (n + HB) * ldt + HB * ldb;       // [HB + n + HB][ldb]
     float* aux = Vbar + (n + HB) * ldb;                 // FAST: starlet chunk sums (see starlet_reg_fast)
-    float* planes = aux + (FAST ? (2 * (PSF_THREADS / (FAST ? NS * K : 1)) * nu + nu * nu / 8 + 2 * nu) : 0);
+    const int scr_count = (int)(aux - scr);
+    float* planes = aux + (FAST ? (2 * (NT / (FAST ? NS * K : 1)) * nu + nu * nu / 8 + 2 * nu) : 0);
     if constexpr (!FAST) {
         if (!A.planes_in_smem) planes = A.work + (size_t)f * A.work_per_frame + (size_t)J * pp;
     }
@@ -628,14 +637,20 @@ __global__ void __launch_bounds__(FIT_THREADS(K, NS)) k_psf_fit(PsfArgs A) {
     float* NU = MU + pp;
     float* C0 = NU + pp;
     float* C1 = C0 + pp;
-    signed char* sg = reinterpret_cast<signed char*>(C1 + pp);   // FAST: [J][pp] sign(alpha_j) (always shared)
+    signed char* sg = reinterpret_cast<signed char*>(C1 + pp);   // [J][pp] sign(alpha_j)
     float* Tj = A.work + (size_t)f * A.work_per_frame;  // generic path: [J][pp] lambda_j W_j sign(alpha_j)
     // stamps transposed ([X][Y], lanes <-> Y read coalesced) in the global workspace
     float* dT = A.work + (size_t)f * A.work_per_frame + (size_t)(J + 7) * pp;
     float* wT = dT + (size_t)A.Nmax * nn;
+    if constexpr (FAST) {
+        sg = reinterpret_cast<signed char*>(GR + pp);
+        C0 = scr; C1 = scr + pp;                        // alias (scr_count >= 2 pp is checked by the host)
+        MU = A.work + (size_t)f * A.work_per_frame;     // the t_j area of the generic path is free here
+        NU = MU + pp;
+    }
 
     constexpr int NGRP = 1;          // (two concurrent star groups were measured: no gain, more registers)
-    constexpr int GT = PSF_THREADS / NGRP;
+    constexpr int GT = SPEC ? PSF_THREADS : NT;
     const int grp = 0, ltid = tid;
     if (NGRP > 1 && grp == 1) {                         // second set of scratch planes, gradient plane = C0
         const int sz = 2 * nu * ldv + n * ldt + n * ldb;
@@ -653,9 +668,8 @@ __global__ void __launch_bounds__(FIT_THREADS(K, NS)) k_psf_fit(PsfArgs A) {
     const float* wgt = A.weight + (size_t)i0 * nn;
 
     if constexpr (FAST) {                               // halos must read as zero
-        float* z0 = red + 2 * 32 * 4;
-        const int zc = (int)(Bp - z0);
-        for (int i = tid; i < zc; i += NT) z0[i] = 0.f;
+        const int zc = (int)(Bp - scr);
+        for (int i = tid; i < zc; i += NT) scr[i] = 0.f;
         __syncthreads();
     }
     for (int i = tid; i < N * nn; i += NT) {
@@ -696,7 +710,8 @@ __global__ void __launch_bounds__(FIT_THREADS(K, NS)) k_psf_fit(PsfArgs A) {
             taps[(st * 4 + (which ? 2 : 0)) * LCB_GE_MAX + p] = e;
             taps[(st * 4 + (which ? 3 : 1)) * LCB_GE_MAX + p] = de;
         }
-        for (int i = tid; i < pp; i += NT) { GR[i] = 0.f; if (NGRP > 1) C0[i] = 0.f; }
+        for (int i = tid; i < pp; i += NT) GR[i] = 0.f;
+        if constexpr (FAST) { for (int i = tid; i < scr_count; i += NT) scr[i] = 0.f; }
         __syncthreads();
         PHASE(0)
 
@@ -718,7 +733,9 @@ __global__ void __launch_bounds__(FIT_THREADS(K, NS)) k_psf_fit(PsfArgs A) {
             const float* tp = taps + st * 4 * LCB_GE_MAX;
             // halo variant (no bounds checks) whenever the tap windows stay within HB rows of the planes
             const bool hal = FAST && abs(icx) <= HB - G / 2 && abs(icy) <= HB - G / 2;
-            if (hal) lcb_pass1<K, G, FAST>(S, nu, nu, n, icy, tp, tp + LCB_GE_MAX, Vg, Vd, ldv, ltid, GT);
+            // FAST (256 threads): task shapes chosen so that every pass is exactly one task per thread at n = 32, k = 2
+            // (pass 1: 64 columns x 4 blocks of 8 rows; pass 2 / 2^T: 32 rows x 8 blocks of 4; pass 1^T: 64 x 4 blocks of 16)
+            if (hal) lcb_pass1<K, G, FAST, (FAST ? 8 : 4)>(S, nu, nu, n, icy, tp, tp + LCB_GE_MAX, Vg, Vd, ldv, ltid, GT);
             else lcb_pass1<K, G, false>(S, nu, nu, n, icy, tp, tp + LCB_GE_MAX, Vg, Vd, ldv, ltid, GT);
             group_sync();
             PHASE(1)
@@ -739,8 +756,8 @@ __global__ void __launch_bounds__(FIT_THREADS(K, NS)) k_psf_fit(PsfArgs A) {
                     if (resid) resid[Y * n + X] = -diff;
                 }
             };
-            if (hal) lcb_pass2<K, G, (FAST ? 2 : 4), FAST>(Vg, Vd, ldv, nu, n, icx, tp + 2 * LCB_GE_MAX, tp + 3 * LCB_GE_MAX, ds, ws, n, ltid, GT, consume);
-            else lcb_pass2<K, G, (FAST ? 2 : 4), false>(Vg, Vd, ldv, nu, n, icx, tp + 2 * LCB_GE_MAX, tp + 3 * LCB_GE_MAX, ds, ws, n, ltid, GT, consume);
+            if (hal) lcb_pass2<K, G, 4, FAST>(Vg, Vd, ldv, nu, n, icx, tp + 2 * LCB_GE_MAX, tp + 3 * LCB_GE_MAX, ds, ws, n, ltid, GT, consume);
+            else lcb_pass2<K, G, 4, false>(Vg, Vd, ldv, nu, n, icx, tp + 2 * LCB_GE_MAX, tp + 3 * LCB_GE_MAX, ds, ws, n, ltid, GT, consume);
             ga = warp_sum(ga); gx = warp_sum(gx); gy = warp_sum(gy);
             if ((tid & 31) == 0) {
                 float* q = redS + (st * PSF_WARPS + (tid >> 5)) * 4;
@@ -749,25 +766,21 @@ __global__ void __launch_bounds__(FIT_THREADS(K, NS)) k_psf_fit(PsfArgs A) {
             group_sync();
             PHASE(2)
             if (last) continue;
-            if (hal) lcb_pass2T<K, G, (FAST ? 2 : 4), FAST>(rT, ldt, nu, n, icx, tp + 2 * LCB_GE_MAX, Vbar, ldb, ltid, GT);
-            else lcb_pass2T<K, G, (FAST ? 2 : 4), false>(rT, ldt, nu, n, icx, tp + 2 * LCB_GE_MAX, Vbar, ldb, ltid, GT);
+            if (hal) lcb_pass2T<K, G, 4, FAST>(rT, ldt, nu, n, icx, tp + 2 * LCB_GE_MAX, Vbar, ldb, ltid, GT);
+            else lcb_pass2T<K, G, 4, false>(rT, ldt, nu, n, icx, tp + 2 * LCB_GE_MAX, Vbar, ldb, ltid, GT);
             group_sync();
             PHASE(3)
             auto emit = [&](int v, int u, float val) { GRg[v * nu + u] = fmaf(a, val, GRg[v * nu + u]); };
-            if (hal) lcb_pass1T<K, G, FAST>(Vbar, ldb, nu, n, icy, tp, ltid, GT, emit);
+            if (hal) lcb_pass1T<K, G, FAST, (FAST ? 8 : 4)>(Vbar, ldb, nu, n, icy, tp, ltid, GT, emit);
             else lcb_pass1T<K, G, false>(Vbar, ldb, nu, n, icy, tp, ltid, GT, emit);
         }
         __syncthreads();
         PHASE(4)
-        if (NGRP > 1 && !last) {
-            for (int i = tid; i < pp; i += NT) GR[i] += C0[i];
-        }
         // ---- per-star gradients (threads st < N)
         float gn2 = 0.f;
         if (tid < N) {
             float ga = 0.f, gx = 0.f, gy = 0.f;
-            const int w0 = (tid % NGRP) * (PSF_WARPS / NGRP);      // star `tid` was handled by group tid % NGRP
-            for (int w = w0; w < w0 + PSF_WARPS / NGRP; ++w) {
+            for (int w = 0; w < (SPEC ? PSF_WARPS : NW); ++w) {
                 const float* q = redS + (tid * PSF_WARPS + w) * 4;
                 ga += q[0]; gx += q[1]; gy += q[2];
             }
@@ -788,8 +801,8 @@ __global__ void __launch_bounds__(FIT_THREADS(K, NS)) k_psf_fit(PsfArgs A) {
             // already computed by the starlet warps, concurrently with the star passes
         } else if (do_reg && FAST) {
             if constexpr (FAST) {
-                if constexpr (NS * K == 64) reg = starlet_reg_fast4(Bp, C0, C1, sg, aux, Wf, A.lam_hf, A.lam_scales, J, tid);
-                else reg = starlet_reg_fast<NS * K>(Bp, C0, C1, sg, aux, Wf, A.lam_hf, A.lam_scales, J, tid);
+                if constexpr (NS * K == 64) reg = starlet_reg_fast4<NT>(Bp, C0, C1, sg, aux, Wf, A.lam_hf, A.lam_scales, J, tid);
+                else reg = starlet_reg_fast<NS * K, NT>(Bp, C0, C1, sg, aux, Wf, A.lam_hf, A.lam_scales, J, tid);
             }
         } else if (do_reg) {
             for (int j = 0; j < J; ++j) {
@@ -929,11 +942,12 @@ size_t lcb_psf_fit_smem_small(int n, int nu, int Nmax) {
 }
 
 // shared bytes of the fast path on top of smem_small: 7 planes + J int8 sign planes
-// fast path: 7 planes + J int8 sign planes + starlet chunk sums + the zero halos (8 rows each side of
-// s, Vg, Vd, r^T, Vbar)
+// fast path (on top of smem_small): s, b, grad planes + sign planes (packed 4/byte on the 64-wide grid) + starlet
+// chunk sums + the zero halos (8 rows each side of s, Vg, Vd, r^T, Vbar); C0/C1 alias the scratch, moments in L2
 size_t lcb_psf_fit_smem_fast_extra(int n, int nu, int J) {
     const size_t halos = (size_t)16 * (nu + 2 * (n + 1) + (n + 1) + (nu + 1)) * 4;
-    return (size_t)7 * nu * nu * 4 + (size_t)J * nu * nu + (size_t)(2 * (PSF_THREADS / nu) * nu + nu * nu / 8 + 2 * nu) * 4 + halos;
+    const size_t signs = (nu == 64) ? (size_t)J * nu * nu / 4 : (size_t)J * nu * nu;
+    return (size_t)3 * nu * nu * 4 + signs + (size_t)(2 * (256 / nu) * nu + nu * nu / 8 + 2 * nu) * 4 + halos;
 }
 
 bool lcb_psf_fit_has_fast(int n, int k, int G) {
@@ -943,6 +957,7 @@ bool lcb_psf_fit_has_fast(int n, int k, int G) {
 template <int K, int G, int NS>
 static int launch_psf_fit(const PsfArgs& A, size_t smem, cudaStream_t st) {
     LCB_CUDA(cudaFuncSetAttribute(k_psf_fit<K, G, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LCB_CUDA(cudaFuncSetAttribute(k_psf_fit<K, G, NS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     { LcbProfScope ps("k_psf_fit", st); k_psf_fit<K, G, NS><<<A.F, FIT_THREADS(K, NS), smem, st>>>(A); }
     LCB_CUDA(cudaGetLastError());
     return LCB_OK;
