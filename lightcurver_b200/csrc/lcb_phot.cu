@@ -64,6 +64,11 @@ __global__ void __launch_bounds__(PHOT_THREADS, (NS > 0 ? 3 : 1)) k_phot_fit(Pho
     }
 
     __syncthreads();
+    // Only warp 0 runs the scalar part of an iteration (sum of the per-warp partials, loss, clip, schedule,
+    // AdaBelief on the 3 parameters, the 2*GE taps) and publishes (a, icx, icy) + taps through shared memory:
+    // with three CTAs per SM the issue slots the other seven warps would spend on the same redundant arithmetic
+    // go to the other CTAs' passes.
+    float* par = red + 2 * 8 * 4 - 4;               // [a, icx, icy, -] (tail of the partials area: 8 warps use 2*32 floats)
     float a = A.a0[item];
     float dx = A.dx0 ? A.dx0[item] : 0.f;
     float dy = A.dy0 ? A.dy0[item] : 0.f;
@@ -72,28 +77,35 @@ __global__ void __launch_bounds__(PHOT_THREADS, (NS > 0 ? 3 : 1)) k_phot_fit(Pho
     int bad = 0;
     const DevConv cv = A.cv;
     const float fk = (float)K;
+    const float sched_c = log2f(cv.decay) / (float)max(A.n_iter, 1);   // lr_t = lr0 * 2^(t * log2(decay)/T)
+    const bool w0 = (tid < 32);
 
     // iteration n_iter is the final evaluation (outputs only, no update)
     for (int it = 0; it <= A.n_iter; ++it) {
         const bool last = (it == A.n_iter);
-        const float cx = fk * dx, cy = fk * dy;
-        const int icx = (int)floorf(cx + 0.5f), icy = (int)floorf(cy + 0.5f);
-        if (tid < 2 * P::GE) {                      // (readers of the previous taps passed the reduce barrier)
-            const int which = tid / P::GE, p = tid % P::GE;
-            float e, de;
-            lcb_tap(cv, K, which ? (cx - (float)icx) : (cy - (float)icy), p, e, de);
-            taps[(which ? 2 : 0) * LCB_GE_MAX + p] = e;
-            taps[(which ? 3 : 1) * LCB_GE_MAX + p] = de;
+        if (w0) {
+            const float cx = fk * dx, cy = fk * dy;
+            const float fx = floorf(cx + 0.5f), fy = floorf(cy + 0.5f);
+            if (tid < 2 * P::GE) {                  // (readers of the previous taps passed the reduce barrier)
+                const int which = tid / P::GE, p = tid % P::GE;
+                float e, de;
+                lcb_tap(cv, K, which ? (cx - fx) : (cy - fy), p, e, de);
+                taps[(which ? 2 : 0) * LCB_GE_MAX + p] = e;
+                taps[(which ? 3 : 1) * LCB_GE_MAX + p] = de;
+            }
+            if (tid == 0) { par[0] = a; par[1] = fx; par[2] = fy; }
         }
         __syncthreads();
+        const float ac = par[0];
+        const int icx = (int)par[1], icy = (int)par[2];
         const bool hal = (HB > 0) && A.s_in_smem && abs(icx) <= HB - G / 2 && abs(icy) <= HB - G / 2;
-        if (hal) lcb_pass1<K, G, (NS > 0)>(s, nu, nu, n, icy, taps, taps + LCB_GE_MAX, Vg, Vd, ldv, tid, PHOT_THREADS);
+        if (hal) lcb_pass1<K, G, (NS > 0), (NS > 0 ? 8 : 4)>(s, nu, nu, n, icy, taps, taps + LCB_GE_MAX, Vg, Vd, ldv, tid, PHOT_THREADS);
         else lcb_pass1<K, G, false>(s, nu, nu, n, icy, taps, taps + LCB_GE_MAX, Vg, Vd, ldv, tid, PHOT_THREADS);
         __syncthreads();
         float loss = 0.f, ga = 0.f, gx = 0.f, gy = 0.f;   // on the last pass: chi2, H, -, -
         float* resid = (last && A.residuals) ? A.residuals + (size_t)item * n * n : nullptr;
         auto consume = [&](int Y, int X, float m0, float mx, float my, float d, float w) {
-            const float diff = fmaf(a, m0, -d);
+            const float diff = fmaf(ac, m0, -d);
             const float r = w * diff;
             if (!last) {
                 loss = fmaf(r, diff, loss);
@@ -109,16 +121,13 @@ __global__ void __launch_bounds__(PHOT_THREADS, (NS > 0 ? 3 : 1)) k_phot_fit(Pho
         if (hal) lcb_pass2<K, G, 4, (NS > 0)>(Vg, Vd, ldv, nu, n, icx, taps + 2 * LCB_GE_MAX, taps + 3 * LCB_GE_MAX, dT, wT, ldt, tid, PHOT_THREADS, consume);
         else lcb_pass2<K, G, 4, false>(Vg, Vd, ldv, nu, n, icx, taps + 2 * LCB_GE_MAX, taps + 3 * LCB_GE_MAX, dT, wT, ldt, tid, PHOT_THREADS, consume);
         loss = warp_sum(loss); ga = warp_sum(ga); gx = warp_sum(gx); gy = warp_sum(gy);
-        float* rbuf = red + (it & 1) * 32;
-        if ((tid & 31) == 0) {
-            float4 v = make_float4(loss, ga, gx, gy);
-            reinterpret_cast<float4*>(rbuf)[tid >> 5] = v;
-        }
+        if ((tid & 31) == 0) reinterpret_cast<float4*>(red)[tid >> 5] = make_float4(loss, ga, gx, gy);
         __syncthreads();
+        if (!w0) continue;                          // (uniform per warp; warp 0 finishes the iteration)
         float L = 0.f, Ga = 0.f, Gx = 0.f, Gy = 0.f;
 #pragma unroll
         for (int w = 0; w < PHOT_THREADS / 32; ++w) {
-            const float4 v = reinterpret_cast<const float4*>(rbuf)[w];
+            const float4 v = reinterpret_cast<const float4*>(red)[w];
             L += v.x; Ga += v.y; Gx += v.z; Gy += v.w;
         }
         if (last) {
@@ -140,13 +149,13 @@ __global__ void __launch_bounds__(PHOT_THREADS, (NS > 0 ? 3 : 1)) k_phot_fit(Pho
             }
         }
         if (!isfinite(L)) bad = 1;
-        // ---- optimiser (every thread redundantly; 3 parameters)
+        // ---- optimiser (warp 0, every lane redundantly; 3 parameters)
         float lr = A.lr;
         if (A.schedule) {
             const float gn = sqrtf(Ga * Ga + Gdx * Gdx + Gdy * Gdy);
             const float cs = (gn < cv.clip) ? 1.f : cv.clip / gn;
             Ga *= cs; Gdx *= cs; Gdy *= cs;
-            lr = A.lr * powf(cv.decay, (float)it / (float)A.n_iter);
+            lr = A.lr * exp2f((float)it * sched_c);
         }
         b1t *= cv.b1; b2t *= cv.b2;
         BeliefCoef bc = {lr, cv.b1, cv.b2, 1.f - cv.b1, 1.f - cv.b2, 1.f / (1.f - b1t), 1.f / (1.f - b2t),

@@ -861,7 +861,7 @@ __global__ void __launch_bounds__(FIT_THREADS(K, NS), ((NS) > 0 ? 2 : 1)) k_psf_
         // ---- clip + schedule + AdaBelief (optax chain)
         const float gn = sqrtf(v3[2]);
         const float cs = (gn < cv.clip) ? 1.f : cv.clip / gn;
-        const float lr = A.lr * powf(cv.decay, (float)it / (float)A.n_iter);
+        const float lr = A.lr * exp2f((float)it * (log2f(cv.decay) / (float)A.n_iter));   // lr0 * decay^(it/T)
         b1t *= cv.b1; b2t *= cv.b2;
         const BeliefCoef bc = {lr, cv.b1, cv.b2, 1.f - cv.b1, 1.f - cv.b2, 1.f / (1.f - b1t), 1.f / (1.f - b2t),
                                cv.eps, cv.eps_root};
