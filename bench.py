@@ -400,7 +400,8 @@ def main():
         pass
     traffic = None
     try:
-        traffic = json.load(open(ROOT / 'profiles' / 'k_psf_fit_traffic.json'))['dram_bytes_per_launch']
+        tj = json.load(open(ROOT / 'profiles' / 'k_psf_fit_traffic.json'))      # from the committed ncu --set full capture
+        traffic = tj['dram_bytes_per_launch'] * F / tj['frames']              # per launch of F frames
     except Exception:
         pass
     hbm_ach = algorithmic_bytes_per_frame() * F / (fit_ms_per_launch * 1e-3) / 1e9 if fit_ms_per_launch > 0 else 0.0
