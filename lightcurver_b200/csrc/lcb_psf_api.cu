@@ -48,9 +48,24 @@ void lcb_build_noise_table(int nu, int J, std::vector<float>& tab) {
     }
 }
 
+// Keep freed stream-ordered allocations cached in the device's default pool: with the default release
+// threshold (0) every call would hand ~400 MB of workspace back to the driver at the next synchronisation
+// and pay for a fresh allocation on the following call.
+static void keep_pool_cached() {
+    static int done_for = -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    done_for = dev;
+}
+
 struct DevTemp {       // stream-ordered temporary
     void* p = nullptr; cudaStream_t st;
-    explicit DevTemp(cudaStream_t s) : st(s) {}
+    explicit DevTemp(cudaStream_t s) : st(s) { keep_pool_cached(); }
     int alloc(size_t bytes) {
         cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 4, st);
         if (e != cudaSuccess) { lcb_set_error("cudaMallocAsync(%zu): %s", bytes, cudaGetErrorString(e)); p = nullptr; return LCB_ERR_NOMEM; }

@@ -644,7 +644,9 @@ __global__ void __launch_bounds__(FIT_THREADS(K, NS), ((NS) > 0 ? 2 : 1)) k_psf_
     float* wT = dT + (size_t)A.Nmax * nn;
     if constexpr (FAST) {
         sg = reinterpret_cast<signed char*>(GR + pp);
-        C0 = scr; C1 = scr + pp;                        // alias (scr_count >= 2 pp is checked by the host)
+        static_assert(!FAST || (2 * (NS * K + 16) * (NS + 1) + (NS + 16) * (NS + 1) + (NS + 16) * (NS * K + 1) >= 2 * NS * K * NS * K),
+                      "the star-pass scratch must be able to hold the two starlet planes");
+        C0 = scr; C1 = scr + pp;                        // alias: disjoint phases
         MU = A.work + (size_t)f * A.work_per_frame;     // the t_j area of the generic path is free here
         NU = MU + pp;
     }
