@@ -422,181 +422,17 @@ __device__ __forceinline__ float starlet_reg_fast4(const float* __restrict__ Bp,
     return reg;
 }
 
-// ---------------------------------------------------------------- warp-specialised starlet (NU = 64)
-// The regulariser gradient depends on b only, exactly like the star passes, so in the 64x64 fast path it runs
-// CONCURRENTLY with them on 4 dedicated warps (threads 512..639) that synchronise among themselves with the
-// named barrier SPEC_BAR; the 16 star warps use barrier 1.  Same arithmetic as starlet_reg_fast4 with 8 rows
-// per thread; W and the sign planes are re-read where needed instead of being cached in registers (the star
-// warps hide that latency).
-#define SPEC_THREADS 256
-#define SPEC_BAR 2
-__device__ __forceinline__ void spec_sync() { asm volatile("bar.sync %0, %1;" ::"n"(SPEC_BAR), "n"(SPEC_THREADS) : "memory"); }
-
-__device__ __noinline__ float starlet_reg_spec(const float* __restrict__ Bp, float* __restrict__ C0,
-                                               float* __restrict__ C1, signed char* __restrict__ sg,
-                                               float* __restrict__ aux,
-                                               const float* __restrict__ Wf, float lam_hf, float lam_scales,
-                                               int J, int lt) {
-    constexpr int NU = 64, PP = NU * NU, QR = NU / 4, LDC = QR + 1, ROWS = NU * QR / SPEC_THREADS;
-    const float h0 = 1.f / 16.f, h1 = 4.f / 16.f;
-    const int q = lt & (QR - 1), rg = lt >> 4, v0 = ROWS * rg, u0 = 4 * q;
-    float* chkR = aux;
-    float* ext = chkR + NU * LDC;
-    float4 wreg[ROWS];                                   // lambda_j W_j of the owned quads, fetched one phase ahead
-    auto L4 = [](const float* p) { return *reinterpret_cast<const float4*>(p); };
-    auto S4 = [](float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; };
-    auto W4 = [&](int j, int idx, float lam) {
-        const float4 w = Wf ? __ldg(reinterpret_cast<const float4*>(Wf + (size_t)j * PP + idx)) : f4_splat(1.f);
-        return make_float4(lam * w.x, lam * w.y, lam * w.z, lam * w.w);
-    };
-    float reg = 0.f;
-    for (int j = 0; j < J; ++j) {
-        const int D = 1 << j;
-        const float* cur = (j == 0) ? Bp : C0;
-        const float lam = (j == 0) ? lam_hf : lam_scales;
-#pragma unroll
-        for (int r = 0; r < ROWS; ++r) wreg[r] = W4(j, (v0 + r) * NU + u0, lam);
-#pragma unroll
-        for (int r = 0; r < ROWS; ++r) {
-            const float* row = cur + (v0 + r) * NU;
-            const float4 B = L4(row + u0);
-            float4 l1, r1, l2, r2;
-            if (D < 4) {
-                const float4 A = (q == 0) ? f4_splat(row[0]) : L4(row + u0 - 4);
-                const float4 C = (q == QR - 1) ? f4_splat(row[NU - 1]) : L4(row + u0 + 4);
-                f4_near(D, A, B, C, l1, r1, l2, r2);
-            } else {
-                l1 = (u0 - D < 0) ? f4_splat(row[0]) : L4(row + u0 - D);
-                r1 = (u0 + D >= NU) ? f4_splat(row[NU - 1]) : L4(row + u0 + D);
-                l2 = (u0 - 2 * D < 0) ? f4_splat(row[0]) : L4(row + u0 - 2 * D);
-                r2 = (u0 + 2 * D >= NU) ? f4_splat(row[NU - 1]) : L4(row + u0 + 2 * D);
-            }
-            S4(C1 + (v0 + r) * NU + u0, f4_b3(B, l1, r1, l2, r2));
-        }
-        spec_sync();
-#pragma unroll
-        for (int r = 0; r < ROWS; ++r) {
-            const int v = v0 + r, idx = v * NU + u0;
-            const int vm2 = max(v - 2 * D, 0), vm1 = max(v - D, 0), vp1 = min(v + D, NU - 1), vp2 = min(v + 2 * D, NU - 1);
-            const float4 wv = wreg[r];
-            const float4 nxt = f4_b3(L4(C1 + idx), L4(C1 + vm1 * NU + u0), L4(C1 + vp1 * NU + u0), L4(C1 + vm2 * NU + u0), L4(C1 + vp2 * NU + u0));
-            const float4 c = L4(cur + idx);
-            const float4 al = make_float4(c.x - nxt.x, c.y - nxt.y, c.z - nxt.z, c.w - nxt.w);
-            reg = fmaf(wv.x, fabsf(al.x), reg); reg = fmaf(wv.y, fabsf(al.y), reg);
-            reg = fmaf(wv.z, fabsf(al.z), reg); reg = fmaf(wv.w, fabsf(al.w), reg);
-            char4 sgn;
-            sgn.x = (al.x > 0.f) ? 1 : (al.x < 0.f) ? -1 : 0; sgn.y = (al.y > 0.f) ? 1 : (al.y < 0.f) ? -1 : 0;
-            sgn.z = (al.z > 0.f) ? 1 : (al.z < 0.f) ? -1 : 0; sgn.w = (al.w > 0.f) ? 1 : (al.w < 0.f) ? -1 : 0;
-            *reinterpret_cast<char4*>(sg + j * PP + idx) = sgn;
-            S4(C0 + idx, nxt);
-        }
-        spec_sync();
-    }
-    auto TJ = [&](int j, int idx, float4 wv) {
-        const char4 sgn = *reinterpret_cast<const char4*>(sg + j * PP + idx);
-        return make_float4(wv.x * (float)sgn.x, wv.y * (float)sgn.y, wv.z * (float)sgn.z, wv.w * (float)sgn.w);
-    };
-    for (int j = J - 1; j >= 0; --j) {
-        const int D = 1 << j;
-        const int m1 = min(D, NU), m2 = min(2 * D, NU);
-#pragma unroll
-        for (int r = 0; r < ROWS; ++r) {
-            const int v = v0 + r, idx = v * NU + u0;
-            const float4 t = TJ(j, idx, wreg[r]);
-            float4 g = f4_splat(0.f);
-            if (j != J - 1) {
-                g = L4(C0 + idx);
-                if (q == 0) g.x += ext[v * 2];
-                if (q == QR - 1) g.w += ext[v * 2 + 1];
-            }
-            S4(C0 + idx, make_float4(g.x - t.x, g.y - t.y, g.z - t.z, g.w - t.w));
-        }
-        spec_sync();
-#pragma unroll
-        for (int r = 0; r < ROWS; ++r) {
-            const int v = v0 + r, idx = v * NU + u0;
-            const float4 z = f4_splat(0.f);
-            float4 acc = f4_b3(L4(C0 + idx), (v - D >= 0) ? L4(C0 + idx - D * NU) : z, (v + D < NU) ? L4(C0 + idx + D * NU) : z,
-                               (v - 2 * D >= 0) ? L4(C0 + idx - 2 * D * NU) : z, (v + 2 * D < NU) ? L4(C0 + idx + 2 * D * NU) : z);
-            if (v == 0 || v == NU - 1) {
-                float4 s1 = z, s2 = z;
-                for (int i = 0; i < m2; ++i) {
-                    const float4 y = L4(C0 + ((v == 0) ? i : NU - 1 - i) * NU + u0);
-                    s2 = f4_add(s2, y);
-                    if (i < m1) s1 = f4_add(s1, y);
-                }
-                acc.x += h0 * s2.x + h1 * s1.x; acc.y += h0 * s2.y + h1 * s1.y;
-                acc.z += h0 * s2.z + h1 * s1.z; acc.w += h0 * s2.w + h1 * s1.w;
-            }
-            S4(C1 + idx, acc);
-            chkR[v * LDC + q] = (acc.x + acc.y) + (acc.z + acc.w);
-        }
-        spec_sync();
-#pragma unroll
-        for (int r = 0; r < ROWS; ++r) {
-            const int idx = (v0 + r) * NU + u0;
-            const float* row = C1 + (v0 + r) * NU;
-            const float4 z = f4_splat(0.f);
-            const float4 B = L4(row + u0);
-            float4 l1, r1, l2, r2;
-            if (D < 4) {
-                const float4 A = (q == 0) ? z : L4(row + u0 - 4);
-                const float4 C = (q == QR - 1) ? z : L4(row + u0 + 4);
-                f4_near(D, A, B, C, l1, r1, l2, r2);
-            } else {
-                l1 = (u0 - D < 0) ? z : L4(row + u0 - D);
-                r1 = (u0 + D >= NU) ? z : L4(row + u0 + D);
-                l2 = (u0 - 2 * D < 0) ? z : L4(row + u0 - 2 * D);
-                r2 = (u0 + 2 * D >= NU) ? z : L4(row + u0 + 2 * D);
-            }
-            const float4 a4 = f4_b3(B, l1, r1, l2, r2);
-            const float4 t = TJ(j, idx, wreg[r]);
-            S4(C0 + idx, make_float4(t.x + a4.x, t.y + a4.y, t.z + a4.z, t.w + a4.w));
-            if (j > 0) wreg[r] = W4(j - 1, idx, (j - 1 == 0) ? lam_hf : lam_scales);   // next scale's weights
-        }
-        if (lt < 2 * NU) {
-            const int v = lt & (NU - 1);
-            const bool left = lt < NU;
-            const float* row = C1 + v * NU;
-            float s1 = 0.f, s2 = 0.f;
-            if (m2 >= 4) {
-                for (int c = 0; c < m2 / 4; ++c) {
-                    const float y = chkR[v * LDC + (left ? c : QR - 1 - c)];
-                    s2 += y;
-                    if (c < m1 / 4) s1 += y;
-                }
-                if (m1 < 4) for (int i = 0; i < m1; ++i) s1 += row[left ? i : NU - 1 - i];
-            } else {
-                for (int i = 0; i < m2; ++i) { const float y = row[left ? i : NU - 1 - i]; s2 += y; if (i < m1) s1 += y; }
-            }
-            ext[v * 2 + (left ? 0 : 1)] = h0 * s2 + h1 * s1;
-        }
-        spec_sync();
-    }
-    if (q == 0 || q == QR - 1) {
-        for (int r = 0; r < ROWS; ++r) {
-            if (q == 0) C0[(v0 + r) * NU] += ext[(v0 + r) * 2];
-            else C0[(v0 + r) * NU + NU - 1] += ext[(v0 + r) * 2 + 1];
-        }
-    }
-    return reg;
-}
-
 // ---------------------------------------------------------------- the kernel
 // NS > 0: compile-time stamp side (fast path, requires NS*K in {32, 64}); NS == 0: runtime sizes.
-// Warp specialisation (star passes and starlet concurrently on disjoint warps) is implemented and parity-
-// tested but DISABLED: measured with the in-kernel phase timers at cfg2, 16 star + 4 starlet warps = 118k
-// cycles/iteration, 16 + 8 warps = 92k, against 85k for the sequential schedule on 16 warps -- the starlet
-// is 30 barrier-separated dependent phases and starves on few warps.  Set to the commented expression to re-enable.
-#define FIT_SPEC(K, NS) 0   /* ((NS) > 0 && (NS) * (K) == 64) */
-// Fast path: 256-thread CTAs sized (registers <= 128, shared memory <= 113 KB) so that TWO frames are resident
+// Fast path: 256-thread CTAs sized (128 registers, <= 113 KB of shared memory) so that TWO frames are resident
 // per SM: the barrier-separated phases of one frame overlap with the other's instead of idling the SM.
-#define FIT_THREADS(K, NS) (FIT_SPEC(K, NS) ? PSF_THREADS + SPEC_THREADS : ((NS) > 0 ? 256 : PSF_THREADS))
+// (Measured alternatives, see profiles/README.md: 512-thread CTAs one per SM; two star groups with named
+// barriers; warp specialisation with the starlet on 4 / 8 dedicated warps -- all slower.)
+#define FIT_THREADS(K, NS) ((NS) > 0 ? 256 : PSF_THREADS)
 template <int K, int G, int NS>
 __global__ void __launch_bounds__(FIT_THREADS(K, NS), ((NS) > 0 ? 2 : 1)) k_psf_fit(PsfArgs A) {
     using P = LcbPass<K, G>;
     constexpr bool FAST = (NS > 0);
-    constexpr bool SPEC = FIT_SPEC(K, NS);          // 64x64 grid: 16 star warps + 4 starlet warps run concurrently
     constexpr int NT = FIT_THREADS(K, NS);          // threads of the CTA
     constexpr int NW = NT / 32;
     static_assert(!FAST || (NS * K == 32 || NS * K == 64), "fast path needs a 32 or 64 wide grid");
@@ -651,18 +487,6 @@ __global__ void __launch_bounds__(FIT_THREADS(K, NS), ((NS) > 0 ? 2 : 1)) k_psf_
         NU = MU + pp;
     }
 
-    constexpr int NGRP = 1;          // (two concurrent star groups were measured: no gain, more registers)
-    constexpr int GT = SPEC ? PSF_THREADS : NT;
-    const int grp = 0, ltid = tid;
-    if (NGRP > 1 && grp == 1) {                         // second set of scratch planes, gradient plane = C0
-        const int sz = 2 * nu * ldv + n * ldt + n * ldb;
-        Vg += sz; Vd += sz; rT += sz; Vbar += sz;
-    }
-    float* GRg = (NGRP > 1 && grp == 1) ? C0 : GR;
-    auto group_sync = [&]() {
-        if (SPEC) asm volatile("bar.sync 1, %0;" ::"n"(PSF_THREADS) : "memory");
-        else __syncthreads();
-    };
 
     const float* sfix = A.s_fixed + (size_t)f * pp;
     const float* Wf = A.W ? A.W + (size_t)f * J * pp : nullptr;
@@ -718,18 +542,9 @@ __global__ void __launch_bounds__(FIT_THREADS(K, NS), ((NS) > 0 ? 2 : 1)) k_psf_
         PHASE(0)
 
         float chi = 0.f, cnt = 0.f;
-        // FAST: the CTA works on NGRP stars at a time, one per group of GT threads, each group with its own
-        // scratch planes, its own gradient plane (group 1 accumulates into C0, free until the starlet phase)
-        // and its own named barrier: task counts per pass are exact multiples of GT, and while one group
-        // waits at a barrier the other one issues.
         float reg = 0.f;
         const bool do_reg = (A.lam_scales != 0.f || A.lam_hf != 0.f);
-        if (SPEC && tid >= PSF_THREADS) {
-            if constexpr (SPEC) {
-                if (do_reg && !last) reg = starlet_reg_spec(Bp, C0, C1, sg, aux, Wf, A.lam_hf, A.lam_scales, J, tid - PSF_THREADS);
-            }
-        } else
-        for (int st = grp; st < N; st += NGRP) {
+        for (int st = 0; st < N; ++st) {
             const float a = sp[st * 12], cx = fk * sp[st * 12 + 1], cy = fk * sp[st * 12 + 2];
             const int icx = (int)floorf(cx + 0.5f), icy = (int)floorf(cy + 0.5f);
             const float* tp = taps + st * 4 * LCB_GE_MAX;
@@ -737,9 +552,9 @@ __global__ void __launch_bounds__(FIT_THREADS(K, NS), ((NS) > 0 ? 2 : 1)) k_psf_
             const bool hal = FAST && abs(icx) <= HB - G / 2 && abs(icy) <= HB - G / 2;
             // FAST (256 threads): task shapes chosen so that every pass is exactly one task per thread at n = 32, k = 2
             // (pass 1: 64 columns x 4 blocks of 8 rows; pass 2 / 2^T: 32 rows x 8 blocks of 4; pass 1^T: 64 x 4 blocks of 16)
-            if (hal) lcb_pass1<K, G, FAST, (FAST ? 8 : 4)>(S, nu, nu, n, icy, tp, tp + LCB_GE_MAX, Vg, Vd, ldv, ltid, GT);
-            else lcb_pass1<K, G, false>(S, nu, nu, n, icy, tp, tp + LCB_GE_MAX, Vg, Vd, ldv, ltid, GT);
-            group_sync();
+            if (hal) lcb_pass1<K, G, FAST, (FAST ? 8 : 4)>(S, nu, nu, n, icy, tp, tp + LCB_GE_MAX, Vg, Vd, ldv, tid, NT);
+            else lcb_pass1<K, G, false>(S, nu, nu, n, icy, tp, tp + LCB_GE_MAX, Vg, Vd, ldv, tid, NT);
+            __syncthreads();
             PHASE(1)
             float ga = 0.f, gx = 0.f, gy = 0.f;
             const float* ds = dT + (size_t)st * nn;
@@ -758,23 +573,23 @@ __global__ void __launch_bounds__(FIT_THREADS(K, NS), ((NS) > 0 ? 2 : 1)) k_psf_
                     if (resid) resid[Y * n + X] = -diff;
                 }
             };
-            if (hal) lcb_pass2<K, G, 4, FAST>(Vg, Vd, ldv, nu, n, icx, tp + 2 * LCB_GE_MAX, tp + 3 * LCB_GE_MAX, ds, ws, n, ltid, GT, consume);
-            else lcb_pass2<K, G, 4, false>(Vg, Vd, ldv, nu, n, icx, tp + 2 * LCB_GE_MAX, tp + 3 * LCB_GE_MAX, ds, ws, n, ltid, GT, consume);
+            if (hal) lcb_pass2<K, G, 4, FAST>(Vg, Vd, ldv, nu, n, icx, tp + 2 * LCB_GE_MAX, tp + 3 * LCB_GE_MAX, ds, ws, n, tid, NT, consume);
+            else lcb_pass2<K, G, 4, false>(Vg, Vd, ldv, nu, n, icx, tp + 2 * LCB_GE_MAX, tp + 3 * LCB_GE_MAX, ds, ws, n, tid, NT, consume);
             ga = warp_sum(ga); gx = warp_sum(gx); gy = warp_sum(gy);
             if ((tid & 31) == 0) {
                 float* q = redS + (st * PSF_WARPS + (tid >> 5)) * 4;
                 q[0] = ga; q[1] = gx; q[2] = gy;
             }
-            group_sync();
+            __syncthreads();
             PHASE(2)
             if (last) continue;
-            if (hal) lcb_pass2T<K, G, 4, FAST>(rT, ldt, nu, n, icx, tp + 2 * LCB_GE_MAX, Vbar, ldb, ltid, GT);
-            else lcb_pass2T<K, G, 4, false>(rT, ldt, nu, n, icx, tp + 2 * LCB_GE_MAX, Vbar, ldb, ltid, GT);
-            group_sync();
+            if (hal) lcb_pass2T<K, G, 4, FAST>(rT, ldt, nu, n, icx, tp + 2 * LCB_GE_MAX, Vbar, ldb, tid, NT);
+            else lcb_pass2T<K, G, 4, false>(rT, ldt, nu, n, icx, tp + 2 * LCB_GE_MAX, Vbar, ldb, tid, NT);
+            __syncthreads();
             PHASE(3)
-            auto emit = [&](int v, int u, float val) { GRg[v * nu + u] = fmaf(a, val, GRg[v * nu + u]); };
-            if (hal) lcb_pass1T<K, G, FAST, (FAST ? 8 : 4)>(Vbar, ldb, nu, n, icy, tp, ltid, GT, emit);
-            else lcb_pass1T<K, G, false>(Vbar, ldb, nu, n, icy, tp, ltid, GT, emit);
+            auto emit = [&](int v, int u, float val) { GR[v * nu + u] = fmaf(a, val, GR[v * nu + u]); };
+            if (hal) lcb_pass1T<K, G, FAST, (FAST ? 8 : 4)>(Vbar, ldb, nu, n, icy, tp, tid, NT, emit);
+            else lcb_pass1T<K, G, false>(Vbar, ldb, nu, n, icy, tp, tid, NT, emit);
         }
         __syncthreads();
         PHASE(4)
@@ -782,7 +597,7 @@ __global__ void __launch_bounds__(FIT_THREADS(K, NS), ((NS) > 0 ? 2 : 1)) k_psf_
         float gn2 = 0.f;
         if (tid < N) {
             float ga = 0.f, gx = 0.f, gy = 0.f;
-            for (int w = 0; w < (SPEC ? PSF_WARPS : NW); ++w) {
+            for (int w = 0; w < NW; ++w) {
                 const float* q = redS + (tid * PSF_WARPS + w) * 4;
                 ga += q[0]; gx += q[1]; gy += q[2];
             }
@@ -799,9 +614,7 @@ __global__ void __launch_bounds__(FIT_THREADS(K, NS), ((NS) > 0 ? 2 : 1)) k_psf_
         }
 
         // ---- starlet regulariser: forward transform, loss, t_j = lambda_j W_j sign(alpha_j)
-        if (SPEC) {
-            // already computed by the starlet warps, concurrently with the star passes
-        } else if (do_reg && FAST) {
+        if (do_reg && FAST) {
             if constexpr (FAST) {
                 if constexpr (NS * K == 64) reg = starlet_reg_fast4<NT>(Bp, C0, C1, sg, aux, Wf, A.lam_hf, A.lam_scales, J, tid);
                 else reg = starlet_reg_fast<NS * K, NT>(Bp, C0, C1, sg, aux, Wf, A.lam_hf, A.lam_scales, J, tid);
