@@ -99,7 +99,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ CPU baseline (oracle port)
-def cpu_baseline_run(sample_frames=8, t1=10, t2=60, tphot=60):
+def cpu_baseline_run(sample_frames=8, t1=20, t2=200, tphot=200):
     """Times the oracle (restated STARRED model, PyTorch CPU float32, all host threads) on a bounded
     sample of cfg2 and scales linearly in the iteration counts to (T1, T2, Tphot)."""
     import torch

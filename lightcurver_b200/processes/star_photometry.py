@@ -7,6 +7,7 @@ and types (tests/test_starred_calls/test_starred_calls.py:20-64).  In the north-
 epochs of one star are independent fits (c fixed at the stamp centre, per-epoch gradient clip; see
 DESIGN.md "reference-coupled mode"), which is what makes frames shard across GPUs with no collective.
 """
+import logging
 import math
 
 import numpy as np
@@ -163,3 +164,123 @@ def star_photometry_batch(data, noisemap, psfs, subsampling_factor, n_iter=2000,
     if want_residuals:
         res['residuals'] = out['residuals'].reshape(F, S, n, n) * scale[None, :, None, None]
     return res
+
+
+STAR_FLUX_DDL = """CREATE TABLE IF NOT EXISTS star_flux_in_frame (
+    frame_id INTEGER, star_gaia_id TEXT, combined_footprint_hash INTEGER, flux REAL, flux_uncertainty REAL, chi2 REAL,
+    relative_loss_differential REAL,
+    PRIMARY KEY (combined_footprint_hash, frame_id, star_gaia_id))"""   # columns of structure/database.py:396-408
+
+
+def update_star_fluxes(db, flux_data):
+    """star_photometry.py:201-229: upsert; on conflict ONLY flux and flux_uncertainty are refreshed."""
+    db.execute(STAR_FLUX_DDL)
+    db.executemany(
+        "INSERT INTO star_flux_in_frame (combined_footprint_hash, frame_id, star_gaia_id, flux, flux_uncertainty, chi2, "
+        "relative_loss_differential) VALUES (?, ?, ?, ?, ?, ?, ?) "
+        "ON CONFLICT(combined_footprint_hash, frame_id, star_gaia_id) DO UPDATE SET "
+        "flux=excluded.flux, flux_uncertainty=excluded.flux_uncertainty", flux_data)
+    db.commit()
+
+
+def gather_star_stack(store, frames, gaia_id, psf_ref_for_frame):
+    """star_photometry.py:272-316 for one star: stamps, noise maps, PSFs of its frames from the stamp store, with the
+    reference's NaN policy (both NaN -> data 0, noise 1e7) and its mask policy (the noise map of every epoch that has
+    ANY masked pixel is multiplied by 1000 -- `noisemap[np.where(~mask)[0]] *= 1000.`, once per epoch)."""
+    data, noisemap, mask, psf = [], [], [], []
+    for frame in frames:
+        rel = frame['image_relpath']
+        data.append(store[f"{rel}/data/{gaia_id}"][...])
+        noisemap.append(store[f"{rel}/noisemap/{gaia_id}"][...])
+        mask.append(store[f"{rel}/cosmicsmask/{gaia_id}"][...])
+        psf.append(store[f"{rel}/{psf_ref_for_frame(frame['id'])}/narrow_psf"][...])
+    data, noisemap, psf = np.array(data, dtype=np.float64), np.array(noisemap, dtype=np.float64), np.array(psf)
+    isnan = np.isnan(data) & np.isnan(noisemap)
+    data[isnan] = 0.
+    noisemap[isnan] = 1e7
+    mask = ~(np.array(mask).astype(bool))
+    noisemap[np.unique(np.where(~mask)[0])] *= 1000.
+    return data, noisemap, psf
+
+
+def do_star_photometry_batched(store, db, stars, frames_for_star, psf_ref_for_frame, user_config,
+                               combined_footprint_hash, on_result=None):
+    """Batched form of do_star_photometry (star_photometry.py:232-373).
+
+    stars: iterable of mappings with 'name', 'gaia_id'; frames_for_star(gaia_id) -> list of frame mappings (id,
+    image_relpath) that need a measurement (get_frames_for_star's rows); psf_ref_for_frame(frame_id) -> psf_ref.
+    With the default pipeline flags (no shared background, no per-epoch constant) every (star, frame) item of every
+    star goes into ONE library call; with the background flags each star is a joint fit
+    (do_one_star_forward_modelling).  Rows are upserted with the reference's conflict rule.
+    Returns {gaia_id: result dict}.
+    """
+    logger = logging.getLogger('lightcurver.star_photometry')
+    cv = DEFAULT
+    k = int(user_config['subsampling_factor'])
+    n_iter = int(user_config['star_deconv_n_iter'])
+    coupled = bool(user_config.get('star_photometry_uniform_background_per_epoch', False)
+                   or user_config.get('star_photometry_starlet_global_background', False))
+    work = []
+    for star in stars:
+        frames = list(frames_for_star(star['gaia_id']))
+        if len(frames) == 0:
+            logger.info(f"Star {star['name']}: no new frames to process for this one. Skipping")
+            continue
+        data, noisemap, psf = gather_star_stack(store, frames, star['gaia_id'], psf_ref_for_frame)
+        work.append(dict(star=star, frames=frames, data=data, noisemap=noisemap, psf=psf))
+    results = {}
+    if not work:
+        return results
+    if coupled:
+        for wk in work:
+            wk['result'] = do_one_star_forward_modelling(
+                wk['data'], wk['noisemap'], wk['psf'], k, n_iter=n_iter,
+                uniform_background_per_epoch=user_config.get('star_photometry_uniform_background_per_epoch', False),
+                starlet_global_background=user_config.get('star_photometry_starlet_global_background', False))
+    else:
+        # per star: scale (:47-49), initial flux guess (:55-64); then one K2 launch over all stars' epochs
+        n = work[0]['data'].shape[-1]
+        ds, ws, ps, a0s, offs = [], [], [], [], [0]
+        for wk in work:
+            d, nm = wk['data'], wk['noisemap']
+            wk['scale'] = float(np.nanmax(d))
+            d /= wk['scale']
+            nm /= wk['scale']
+            a_est = _initial_flux_guess(d) * (k * k if cv.downsample_mean else 1.0)
+            ds.append(np.nan_to_num(d).astype(np.float32))
+            ws.append((1.0 / nm ** 2).astype(np.float32))
+            ps.append(np.asarray(wk['psf'], np.float32))
+            a0s.append(a_est.astype(np.float32))
+            offs.append(offs[-1] + d.shape[0])
+        B = offs[-1]
+        out = engine.phot_fit_batch(np.concatenate(ds), np.concatenate(ws), np.concatenate(ps),
+                                    np.arange(B, dtype=np.int32), np.concatenate(a0s), k, n_iter, lr=1e-3, schedule=True)
+        for i, wk in enumerate(work):
+            sl = slice(offs[i], offs[i + 1])
+            residuals = out['residuals'][sl].astype(np.float64)             # data - model, scaled units
+            with np.errstate(divide='ignore', invalid='ignore'):
+                chi2_per_frame = np.nansum(residuals ** 2 / wk['noisemap'] ** 2, axis=(1, 2)) / n ** 2
+            wk['result'] = {
+                'scale': wk['scale'], 'fluxes': wk['scale'] * out['a'][sl].astype(np.float64),
+                'fluxes_uncertainties': wk['scale'] * out['sigma_a'][sl].astype(np.float64),
+                'chi2': float(np.nanmean(chi2_per_frame)), 'chi2_per_frame': chi2_per_frame,
+                'loss_curve': list(out['loss_hist'][sl].astype(np.float64).sum(0)), 'residuals': wk['scale'] * residuals,
+                'kwargs_final': {'kwargs_analytic': {'c_x': np.zeros(1), 'c_y': np.zeros(1), 'dx': out['dx'][sl], 'dy': out['dy'][sl],
+                                                     'a': out['a'][sl], 'alpha': np.zeros(sl.stop - sl.start)},
+                                 'kwargs_background': {'h': np.zeros((n * k) ** 2), 'mean': np.zeros(sl.stop - sl.start)},
+                                 'kwargs_sersic': {}},
+            }
+    for wk in work:
+        result, star = wk['result'], wk['star']
+        if on_result is not None:
+            on_result(star, wk['data'], wk['noisemap'], result)
+        from .psf_modelling import relative_loss_differential
+        rld = relative_loss_differential(result['loss_curve'])
+        flux_data = [(combined_footprint_hash, frame['id'], star['gaia_id'], float(result['fluxes'][j]),
+                      float(result['fluxes_uncertainties'][j]), float(result['chi2_per_frame'][j]), rld)
+                     for j, frame in enumerate(wk['frames'])]
+        update_star_fluxes(db, flux_data)
+        results[star['gaia_id']] = result
+        logger.info(f"Measured star {star['name']} in {len(wk['frames'])} frames. "
+                    f"The global reduced chi2 is {result['chi2']:.02f}.")
+    return results
