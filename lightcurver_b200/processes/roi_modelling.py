@@ -224,3 +224,84 @@ def joint_deconvolution(data, weight, psf, subsampling_factor, xs, ys, initial_a
         deconv += point_source_image(fin['a'][m], fin['c_x'][m] + fin['dx'][0], fin['c_y'][m] + fin['dy'][0], n, jd.k, cv)
     return dict(kwargs_final=kw, model=fin['model'], loss_history=hist, W=Wused, flux_sigma=sig,
                 deconvolved_epoch0=(deconv, h2))
+
+
+def model_roi_arrays(data, noisemap, psf, subsampling_factor, xs, ys, initial_a, angles_to_north=None,
+                     fix_point_source_astrometry=False, starting_background=None, further_optimize_background=True,
+                     roi_model_regularization=None, roi_deconv_translations_iters=300, roi_deconv_all_iters=2000,
+                     conventions: Conventions = DEFAULT, group=None):
+    """The two optimisation stages of do_modelling_of_roi (roi_modelling.py:213-335) on arrays that are already
+    loaded and scaled (:154-170): data, noisemap (E,n,n); psf (E,P,P); xs, ys the point-source guesses in data
+    pixels from the stamp centre (:207-210); initial_a (E*M,) (:211-212).
+
+    Stage 1 (:260-281) frees {dx, dy, a}.  The reference runs scipy L-BFGS-B there (with a flux-uniformity penalty,
+    a 'next' row); this engine runs the same free set with scheduled AdaBelief (lr 1e-2 of the data scale) for
+    ``roi_deconv_translations_iters`` iterations -- same role (register the epochs, get the fluxes in range), not
+    the same trajectory.  Stage 2 (:285-335) is the reference's: SLIT noise weights, free {h (if
+    further_optimize_background), mean, a, c_x, c_y, dx, dy}, AdaBelief lr 1e-4, no schedule, strengths from
+    ``roi_model_regularization``; ``fix_point_source_astrometry``: True fixes c, a float is the sigma (data pixels) of
+    a Gaussian prior around the initial positions (:225-244).
+    """
+    reg = roi_model_regularization or {}
+    E, n = data.shape[0], data.shape[-1]
+    k = int(subsampling_factor)
+    xs, ys = np.atleast_1d(np.asarray(xs, float)), np.atleast_1d(np.asarray(ys, float))
+    with np.errstate(divide='ignore', invalid='ignore'):
+        weight = np.where(np.isfinite(noisemap) & (noisemap > 0), 1.0 / np.asarray(noisemap, np.float64) ** 2, 0.0).astype(np.float32)
+    d32 = np.nan_to_num(np.asarray(data, np.float32))
+    alpha = np.zeros(E) if angles_to_north is None else np.asarray(angles_to_north, float) - float(angles_to_north[0])
+    h0 = None if starting_background is None else np.asarray(starting_background, np.float32).reshape(-1)
+    fix_c = isinstance(fix_point_source_astrometry, bool) and fix_point_source_astrometry
+    prior = None
+    if isinstance(fix_point_source_astrometry, float):
+        sg = np.full(len(xs), fix_point_source_astrometry)
+        prior = (xs, sg, ys, sg)
+    # stage 1: translations and fluxes
+    s1 = joint_deconvolution(d32, weight, psf, k, xs, ys, initial_a, n_iter=int(roi_deconv_translations_iters), lr=1e-2,
+                             schedule=True, alpha=alpha, h0=h0, free_h=False, free_mean=False, free_a=True, free_c=False,
+                             free_d=True, regularization_strength_scales=0.0, regularization_strength_hf=0.0,
+                             regularization_strength_positivity=0.0, W=None, prior=None, conventions=conventions, group=group)
+    k1 = s1['kwargs_final']
+    # stage 2: everything
+    s2 = joint_deconvolution(d32, weight, psf, k, k1['kwargs_analytic']['c_x'], k1['kwargs_analytic']['c_y'],
+                             k1['kwargs_analytic']['a'], n_iter=int(roi_deconv_all_iters), lr=1e-4, schedule=False,
+                             alpha=alpha, h0=k1['kwargs_background']['h'], dx0=k1['kwargs_analytic']['dx'],
+                             dy0=k1['kwargs_analytic']['dy'], free_h=bool(further_optimize_background), free_mean=True,
+                             free_a=True, free_c=not fix_c, free_d=True,
+                             regularization_strength_scales=reg.get('regularization_strength_scales', 1.0),
+                             regularization_strength_hf=reg.get('regularization_strength_hf', 1.0),
+                             regularization_strength_positivity=reg.get('regularization_strength_positivity', 100.0),
+                             W='propagate', prior=prior, conventions=conventions, group=group)
+    s2['stage1'] = s1
+    return s2
+
+
+def get_fluxes_dataframe_from_model(result, data, noisemap, point_sources_names, model_scale, normalization_errors,
+                                    frame_ids, mjds, seeings, zeropoint, sky_level_electron_per_second):
+    """roi_modelling.py:420-497 up to the per-epoch table: fluxes per source ``a[i::M] * scale`` (:462), uncertainties
+    sqrt(sigma_Fisher^2 + (normalisation error * flux)^2) (:465-467), reduced chi2 per frame = sum r^2/sigma^2 / n^2
+    (:470-472).  Returns (per-epoch DataFrame indexed by frame_id, residuals); the grouping per night and the
+    magnitude conversion stay lightcurver's (utilities/lightcurves_postprocessing.py)."""
+    import pandas as pd
+    kw = result['kwargs_final']
+    M = len(point_sources_names)
+    fluxes = np.asarray(kw['kwargs_analytic']['a'])
+    sig = np.asarray(result['flux_sigma'])
+    curves, d_curves = {}, {}
+    for i, ps in enumerate(point_sources_names):
+        curve = fluxes[i::M] * model_scale
+        photon = sig[i::M] * model_scale
+        curves[ps] = curve
+        d_curves[ps] = (photon ** 2 + (np.asarray(normalization_errors) * curve) ** 2) ** 0.5
+    residuals = np.asarray(data) - np.asarray(result['model'])
+    with np.errstate(divide='ignore', invalid='ignore'):
+        chi2_per_frame = np.nansum(residuals ** 2 / np.asarray(noisemap) ** 2, axis=(1, 2)) / data.shape[-1] ** 2
+    rows = []
+    for e in range(len(frame_ids)):
+        row = {'frame_id': frame_ids[e], 'mjd': mjds[e], 'zeropoint': zeropoint, 'reduced_chi2': chi2_per_frame[e],
+               'seeing': seeings[e], 'sky_level_electron_per_second': sky_level_electron_per_second[e]}
+        for ps in point_sources_names:
+            row[f'{ps}_flux'] = curves[ps][e]
+            row[f'{ps}_d_flux'] = d_curves[ps][e]
+        rows.append(row)
+    return pd.DataFrame(rows).set_index('frame_id'), residuals

@@ -574,7 +574,7 @@ def deconv_loss_grad(params, fixed, psf, data, weight, W, n, k, reg, cv: Convent
                     prior, cv)
     names = list(leaves)
     g = torch.autograd.grad(L, [leaves[kk] for kk in names])
-    return float(L), {kk: t.numpy() for kk, t in zip(names, g)}
+    return float(L.detach()), {kk: t.numpy() for kk, t in zip(names, g)}
 
 
 def fit_deconv(params, fixed, psf, data, weight, W, n, k, reg, n_iter, lr=1e-4, schedule=False,
@@ -596,7 +596,7 @@ def fit_deconv(params, fixed, psf, data, weight, W, n, k, reg, n_iter, lr=1e-4, 
                         p['dy'], p['alpha'], psf, data, weight, W, n, k, reg.get('lam_scales', 0.0),
                         reg.get('lam_hf', 0.0), reg.get('lam_pos', 0.0), prior, cv)
         g = torch.autograd.grad(L, [leaves[kk] for kk in names])
-        hist[it] = float(L)
+        hist[it] = float(L.detach())
         opt.step(list(g))
     out = {kk: v.detach().numpy() for kk, v in leaves.items()}
     out['loss_hist'] = hist

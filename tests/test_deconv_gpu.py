@@ -129,3 +129,26 @@ def test_do_one_star_reference_defaults(cuda_device):
     assert result['chi2_per_frame'].shape == (5,)
     assert result['starlet_background'].shape == (16, 16) and result['deconvolved_image'].shape == (16, 16)
     assert np.isfinite(result['fluxes']).all() and np.isfinite(result['fluxes_uncertainties']).all()
+
+
+def test_model_roi_arrays_and_flux_table(cuda_device):
+    """Two-stage ROI modelling on a small synthetic blend (rows a6, a7): fluxes come back within a few sigma,
+    the per-epoch table has the reference's columns, chi2 per frame < 2."""
+    from lightcurver_b200.processes.roi_modelling import model_roi_arrays, get_fluxes_dataframe_from_model
+    E, n, k, M = 6, 16, 2, 2
+    p = _problem(E, n, k, M, 12, seed=77, alpha_on=False)
+    sig = 1.0 / np.sqrt(p['weight'].astype(np.float64))
+    res = model_roi_arrays(p['data'].astype(np.float64), sig, p['psf'], k, p['c_x'] + 0.2, p['c_y'] - 0.2,
+                           (p['a'] * 0.8).reshape(-1), fix_point_source_astrometry=1.0,
+                           roi_deconv_translations_iters=150, roi_deconv_all_iters=400,
+                           roi_model_regularization=dict(regularization_strength_positivity=0.0))
+    a = np.asarray(res['kwargs_final']['kwargs_analytic']['a']).reshape(E, M)
+    err = np.abs(a - p['a']) / (res['flux_sigma'].reshape(E, M))
+    assert np.median(err) < 6 and np.isfinite(res['flux_sigma']).all()
+    df, resid = get_fluxes_dataframe_from_model(res, p['data'], sig, ['A', 'B'], 3.0, np.full(E, 0.01), np.arange(E) + 10,
+                                                np.linspace(59000, 59005, E), np.full(E, 1.1), 25.0, np.full(E, 3.0))
+    assert list(df.columns) == ['mjd', 'zeropoint', 'reduced_chi2', 'seeing', 'sky_level_electron_per_second',
+                                'A_flux', 'A_d_flux', 'B_flux', 'B_d_flux']
+    assert (df['reduced_chi2'] < 2).all() and resid.shape == p['data'].shape
+    np.testing.assert_allclose(df['A_flux'].values, a[:, 0] * 3.0, rtol=1e-6)
+    assert (df['A_d_flux'].values >= 0.01 * df['A_flux'].values - 1e-9).all()
