@@ -160,6 +160,11 @@ typedef struct {
     const float* W;                       /* [J][nu*nu] or NULL (== 1) */
     const float* prior_mu_x; const float* prior_sig_x;   /* [M] Gaussian prior on c_x (Prior(prior_analytic=...)), or NULL */
     const float* prior_mu_y; const float* prior_sig_y;
+    float lam_pts;          /* regularization_strength_pts_source (roi_modelling.py:311): L1 of the first starlet scale of the
+                               point-source channel, weighted by W[0] */
+    float lam_fu;           /* regularization_strength_flux_uniformity (roi_modelling.py:275-276, 312): scatter of a over the epochs */
+    int pts_all_epochs;     /* 1: the pts-source term is summed over all epochs, 0: first epoch only */
+    int fu_relative;        /* 1: sum_m std_e(a_em)/|mean_e(a_em)|, 0: sum_m std_e(a_em) */
 } lcb_deconv_reg;
 
 typedef struct {           /* gradient of the loss at the current parameters */
@@ -171,9 +176,23 @@ typedef struct {           /* gradient of the loss at the current parameters */
 int lcb_deconv_create(const lcb_deconv_problem* p, int mem, void* stream, void** handle);
 int lcb_deconv_set_params(void* handle, const lcb_deconv_params* q, int mem);   /* also restarts the optimiser state */
 int lcb_deconv_set_reg(void* handle, const lcb_deconv_reg* r, int mem);
-/* single-rank driver: n_iter AdaBelief iterations; loss_hist [n_iter] may be NULL */
+/* CTAs per epoch of the per-epoch kernel (thread-block cluster size): 0 = automatic, or 1/2/4/8 */
+int lcb_deconv_set_cluster(void* handle, int ctas_per_epoch);
+int lcb_deconv_get_cluster(void* handle);
+/* Epoch sharding: total number of epochs over all ranks, global index of this rank's first epoch, and
+ * (may be NULL) one value per source near its mean flux, identical on all ranks (shift of the flux sums). */
+int lcb_deconv_set_global(void* handle, int E_total, int e0, const float* flux_shift, int mem);
+/* In-kernel all-reduce over NVLink peer memory (no NCCL launch per iteration): comm_init allocates this
+ * rank's receive buffer and writes its 64-byte CUDA IPC handle to ipc_handle_out; the caller exchanges the
+ * handles (any transport) and passes all of them, in rank order, to comm_connect.  world <= 8, one node.
+ * Afterwards lcb_deconv_run and lcb_deconv_loss_grad are COLLECTIVE calls (same arguments on every rank). */
+int lcb_deconv_comm_init(void* handle, int rank, int world, void* ipc_handle_out);
+int lcb_deconv_comm_connect(void* handle, const void* all_handles);
+/* n_iter AdaBelief iterations, enqueued without host synchronisation; loss_hist [n_iter] may be NULL.
+ * Single rank, or every rank of a connected communicator. */
 int lcb_deconv_run(void* handle, const lcb_fit_opts* opt, float* loss_hist, int mem);
-/* multi-rank driver, one iteration = step_local ; all-reduce(sum) of reduce_buffer ; step_update.
+/* Alternative multi-rank driver with an external collective (e.g. NCCL): one iteration = step_local ;
+ * all-reduce(sum) of reduce_buffer ; step_update.
  * After the last iteration call step_local once more to apply the pending per-epoch update. */
 int lcb_deconv_step_local(void* handle, int want_model);
 int lcb_deconv_reduce_buffer(void* handle, float** device_ptr, int* count);

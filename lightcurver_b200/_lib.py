@@ -224,7 +224,8 @@ class DeconvParams(C.Structure):
 
 class DeconvReg(C.Structure):
     _fields_ = [('lam_scales', C.c_float), ('lam_hf', C.c_float), ('lam_pos', C.c_float), ('W', C.c_void_p),
-                ('prior_mu_x', C.c_void_p), ('prior_sig_x', C.c_void_p), ('prior_mu_y', C.c_void_p), ('prior_sig_y', C.c_void_p)]
+                ('prior_mu_x', C.c_void_p), ('prior_sig_x', C.c_void_p), ('prior_mu_y', C.c_void_p), ('prior_sig_y', C.c_void_p),
+                ('lam_pts', C.c_float), ('lam_fu', C.c_float), ('pts_all_epochs', C.c_int), ('fu_relative', C.c_int)]
 
 
 class DeconvGrad(C.Structure):
@@ -242,3 +243,8 @@ lib.lcb_deconv_loss_grad.argtypes = [C.c_void_p, C.POINTER(DeconvGrad), C.c_int]
 lib.lcb_deconv_get.argtypes = [C.c_void_p, C.POINTER(DeconvParams), C.c_void_p, C.c_void_p, C.c_int]
 lib.lcb_deconv_destroy.argtypes = [C.c_void_p]
 lib.lcb_deconv_noise_weights.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+lib.lcb_deconv_set_cluster.argtypes = [C.c_void_p, C.c_int]
+lib.lcb_deconv_get_cluster.argtypes = [C.c_void_p]
+lib.lcb_deconv_set_global.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+lib.lcb_deconv_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+lib.lcb_deconv_comm_connect.argtypes = [C.c_void_p, C.c_void_p]

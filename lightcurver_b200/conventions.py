@@ -37,6 +37,11 @@ class Conventions:
     # regularisation strengths of build_psf stage 2
     psf_lambda_scales: float = 1.0
     psf_lambda_hf: float = 1.0
+    # deconvolution Loss: regularization_strength_pts_source = L1 of the first starlet scale of the point-source
+    # channel, weighted by W[0]; summed over all epochs (True) or evaluated on the first epoch only (False)
+    pts_source_all_epochs: bool = True
+    # regularization_strength_flux_uniformity: sum_m std_e(a_em) / |mean_e(a_em)| (True) or sum_m std_e(a_em) (False)
+    flux_uniformity_relative: bool = True
 
     def as_dict(self):
         return asdict(self)

@@ -5,16 +5,25 @@
 // reference-coupled form of star_photometry.py:66-137.  Model:
 //     f_e = Warp_{dx_e,dy_e,alpha_e}[h] + sum_m a_em G(. ; k (R_alpha c_m + d_e))        (nu x nu)
 //     m_e = D_k[ s_e (*) f_e ] + mean_e                                                  (n x n)
-// Loss (A.7): 1/2 sum w (m-d)^2 + starlet-L1(h; W) + positivity(h) + Gaussian prior on (c_x, c_y).
+// Loss (A.7): 1/2 sum w (m-d)^2 + starlet-L1(h; W) + positivity(h) + Gaussian prior on (c_x, c_y)
+//             + pts-source L1 (first starlet scale of the point-source channel) + flux uniformity.
 //
 // One iteration =
-//   k_deconv_epoch   one CTA per epoch: apply the pending AdaBelief update of the per-epoch parameters,
-//                    build f_e in shared memory (polyphase layout), direct FP32 convolution with the
-//                    k-box-folded PSF fused with the decimation, weighted residual, adjoint convolution,
-//                    point-source / shift / mean gradients, transposed warp -> partial dL/dh of the epoch
-//   k_deconv_reduce  deterministic sum over the local epochs -> red[nu^2 + 2M + 2]
-//   (multi-GPU: ONE all-reduce of red over NVLink, issued by the caller between the two entries)
-//   k_deconv_update  starlet / positivity / prior gradients, global norm, AdaBelief on h, c_x, c_y.
+//   k_deconv_epoch   one thread-block CLUSTER of CS CTAs per epoch (CS = 1, 2, 4, 8 chosen so that the local
+//                    epochs fill the 148 SMs): every CTA owns a band of data rows; it applies the pending
+//                    AdaBelief update of the per-epoch parameters, builds the rows of f_e it needs in shared
+//                    memory (polyphase layout), runs the direct FP32 convolution with the k-box-folded PSF
+//                    fused with the decimation for its band, broadcasts its rows of the weighted residual to
+//                    the other CTAs through distributed shared memory, runs the adjoint convolution for its
+//                    band, and the transposed warp reads dL/df of neighbouring bands through DSMEM
+//   k_deconv_reduce  deterministic sum over the local epochs -> red[] ; multi-GPU: every rank PUSHES its
+//                    partial sums into a slot of every peer's receive buffer over NVLink (peer memory mapped
+//                    with CUDA IPC), then raises a flag there
+//   k_deconv_update  multi-GPU: waits for the flags and sums the slots in rank order (bit-identical on all
+//                    ranks); starlet / positivity / prior / flux-uniformity terms, global norm, AdaBelief on
+//                    h, c_x, c_y.  No host round trip and no separate collective launch per iteration.
+//   (lcb_deconv_step_local / _step_update keep the two halves separately callable so that the caller can
+//    put ONE NCCL all-reduce of red[] between them instead.)
 //
 // Decimation is folded into the PSF: m[Y][X] = mean + 1/k^2 sum_phase sum_{av,au} S_ph[av][au] f_ph[Y+av][X+au]
 // with f_ph[Y'][X'] = f[kY'+pv][kX'+pu] and S_ph the polyphase components of s (*) box_k; each phase is a
@@ -24,6 +33,8 @@
 #include <cooperative_groups.h>
 #include <vector>
 
+namespace cg = cooperative_groups;
+
 void lcb_build_noise_table(int nu, int J, std::vector<float>& tab);
 int lcb_noise_weights_launch(int F, int nu, int J, const float* tab, float* W, float* work,
                              size_t work_per_frame, cudaStream_t st);
@@ -31,14 +42,27 @@ int lcb_noise_weights_launch(int F, int nu, int J, const float* tab, float* W, f
 #define DC_THREADS 256
 #define DC_XB 8
 #define DC_MMAX 8
+#define DC_MAXW 8            // ranks of one NVSwitch domain
+#define DC_CSMAX 8           // portable cluster size
+#define DC_EXT 20            // G + 4 <= 20
+
+struct DeconvComm {          // peer memory of the in-kernel all-reduce
+    int world, rank;
+    float* slots[DC_MAXW];   // receive buffer of rank r: [2 parities][world][tot]
+    int* flags[DC_MAXW];     // flags of rank r: [2][world], value = sequence number of the data in the slot
+    unsigned* ctr;           // [2] local last-block counters of k_deconv_reduce
+};
 
 struct DeconvDev {
     int E, n, k, nu, P, M, NA, A0, J, G;
+    int E_total, e0;                     // epochs over all ranks, global index of the first local epoch
+    int tot;                             // length of red[]
     int free_h, free_mean, free_a, free_c, free_d;
     // inputs
     float *data, *weight, *S;            // [E][n][n], [E][n][n], [E][k*k][NA][NA]
     float *W;                            // [J][nu^2] or NULL
-    float lam_scales, lam_hf, lam_pos;
+    float lam_scales, lam_hf, lam_pos, lam_pts, lam_fu;
+    int pts_all_epochs, fu_relative;
     int has_prior; float *prior;         // [4][M] mu_x, sig_x, mu_y, sig_y
     // parameters + AdaBelief state
     float *h, *h_mu, *h_nu;              // [nu^2]
@@ -49,16 +73,40 @@ struct DeconvDev {
     float *Gh;                           // [E][nu^2] per-epoch partial dL/dh
     float *gc;                           // [E][2M]
     float *eloss;                        // [E]
-    float *red;                          // [nu^2 + 2M + 2] reduced: dL/dh, dL/dc, loss, |g_epoch|^2
-    float *ctl;                          // [8] clip scale, lr, 1/bc1, 1/bc2, pending flag, loss
+    float *red;                          // [tot] reduced: dL/dh | dL/dc (2M) | loss | |g_epoch|^2 | flux sums (4M)
+    float *ctl;                          // [8] clip scale, lr, 1/bc1, 1/bc2, pending flag, loss, -, peer timeout
+    float *fu;                           // [3][DC_MMAX] flux uniformity: mean (= shift of the sums), A, B
     float *gpart;                        // [8][DU_CTAS] cross-CTA partial sums of k_deconv_update
     float *planes;                       // [3][nu^2] starlet scratch + Tj [J][nu^2]
     float *model;                        // [E][n][n] (written when requested)
     float *loss_hist;                    // [cap]
     DevConv cv;
+    DeconvComm cm;
 };
 
-__device__ __forceinline__ int fdiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+// red[] layout
+__host__ __device__ inline int red_loss(const DeconvDev& D) { return D.nu * D.nu + 2 * D.M; }
+__host__ __device__ inline int red_flux(const DeconvDev& D) { return D.nu * D.nu + 2 * D.M + 2; }
+
+// shared-memory layout of k_deconv_epoch (floats)
+struct DcLayout { int oS, oF, pst, oR, oG, oPar, oRed, oCp, oPts, oEx, total; };
+__host__ __device__ inline DcLayout dc_layout(int n, int k, int NA) {
+    const int kk = k * k;
+    DcLayout L;
+    int o = 0;
+    L.oS = o; o += (kk * NA * NA + 3) & ~3;
+    L.pst = n * (n + 1) + 8;                     // plane stride: +8 banks between polyphase planes
+    L.oF = o; o += kk * L.pst;
+    L.oR = o; o += n * (n + 1);
+    L.oG = o; o += 4 * DC_MMAX * 16;             // gx | d gx | gy | d gy, [M][16] each
+    L.oPar = o; o += 16;
+    L.oRed = o; o += 16;
+    L.oCp = o; o += DC_CSMAX * 32;               // per-CTA partial sums, gathered in rank 0
+    L.oPts = o; o += DC_MMAX * 32;               // pts-source partial sums per warp
+    L.oEx = o; o += 2 * DC_MMAX * 4 * DC_EXT;    // [axis][m][g, Bg, g', Bg'][G+4]
+    L.total = o;
+    return L;
+}
 
 // ---------------------------------------------------------------- setup: polyphase box-folded PSF
 // S[e][pv*k+pu][av-A0][au-A0] = stilde(tv = j0 - k av - pv, tu = j0 - k au - pu),
@@ -95,11 +143,11 @@ __device__ __forceinline__ float h_at(const float* __restrict__ h, int nu, int v
     return (v >= 0 && v < nu && u >= 0 && u < nu) ? __ldg(h + v * nu + u) : 0.f;
 }
 
-// correlation of one phase plane with its NA x NA kernel for XB consecutive outputs of row Y:
+// correlation of one phase plane with rows [ia0, ia1) of its NA x NA kernel for XB consecutive outputs of row Y:
 //   acc[x] += sum_{av,au} Sph[av-A0][au-A0] * src[Y+av][X0+x+au]      (zero outside [0,n))
 __device__ __forceinline__ void corr_row(const float* __restrict__ src, int ld, int n, const float* __restrict__ Sph,
-                                         int NA, int A0, int Y, int X0, float (&acc)[DC_XB]) {
-    for (int ia = 0; ia < NA; ++ia) {
+                                         int NA, int A0, int ia0, int ia1, int Y, int X0, float (&acc)[DC_XB]) {
+    for (int ia = ia0; ia < ia1; ++ia) {
         const int row = Y + A0 + ia;
         if (row < 0 || row >= n) continue;
         const float* fr = src + row * ld;
@@ -173,26 +221,43 @@ __device__ __forceinline__ float block_sum(float v, float* red, int tid) {
     return s;
 }
 
-// ---------------------------------------------------------------- per-epoch kernel
-__global__ void __launch_bounds__(DC_THREADS) k_deconv_epoch(DeconvDev D, int flags) {
+// ---------------------------------------------------------------- per-epoch kernel (cluster of CS CTAs)
+// flags: 1 = write the model image; 2 = propagate the weights instead of the residuals (noise weights).
+__global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int flags, int CS) {
+    cg::cluster_group cl = cg::this_cluster();
     const int want_model = flags & 1;
-    const bool noise = (flags & 2) != 0;   // propagate the weights instead of the residuals (lcb_deconv_noise_weights)
+    const bool noise = (flags & 2) != 0;
     extern __shared__ __align__(16) float sm[];
-    const int e = blockIdx.x, tid = threadIdx.x;
+    const int tid = threadIdx.x;
+    const int crank = (int)(blockIdx.x % CS);     // == cl.block_rank() for cluster dims (CS,1,1)
+    const int e = blockIdx.x / CS;
     const int n = D.n, k = D.k, nu = D.nu, M = D.M, NA = D.NA, A0 = D.A0, G = D.G;
     const int ldf = n + 1, ldr = n + 1, kk = k * k;
     const int np = M + 3;
-    float* Ssm = sm;                                  // [kk][NA][NA]
-    float* fpl = Ssm + kk * NA * NA;                  // [kk][n][ldf]   f, later dL/df
-    float* rsm = fpl + kk * n * ldf;                  // [n][ldr]
-    float* gx = rsm + n * ldr;                        // [M][G] and derivative [M][G]
+    const DcLayout L = dc_layout(n, k, NA);
+    const int pst = L.pst;
+    float* Ssm = sm + L.oS;                       // [kk][NA][NA]
+    float* fpl = sm + L.oF;                       // [kk][pst]   f, later dL/df (own band)
+    float* rsm = sm + L.oR;                       // [n][ldr]
+    float* gx = sm + L.oG;                        // [M][16] and derivative [M][16]
     float* gy = gx + 2 * DC_MMAX * 16;
-    float* par = gy + 2 * DC_MMAX * 16;               // [np]
-    float* red = par + 16;                            // [8 + 4*DC_MMAX]
+    float* par = sm + L.oPar;                     // [np]
+    float* red = sm + L.oRed;                     // [8] block_sum scratch
+    float* cpart = sm + L.oCp;                    // [CS][32] (rank 0's copy is the one that is read)
+    float* ptsacc = sm + L.oPts;                  // [M][32]
+    float* ext = sm + L.oEx;                      // [axis][m][4][DC_EXT]
     __shared__ int iwin[2 * DC_MMAX];
+    __shared__ const float* remf[DC_CSMAX];       // fpl of every CTA of the cluster (DSMEM)
 
-    // ---- pending AdaBelief update of the per-epoch parameters (gradients of the previous iteration)
+    // band of data rows (and of rows of every polyphase plane) owned by this CTA
+    const int rpc = (n + CS - 1) / CS;
+    const int Y0 = min(n, crank * rpc), Y1 = min(n, Y0 + rpc), own = Y1 - Y0;
+
+    // ---- pending AdaBelief update of the per-epoch parameters (gradients of the previous iteration):
+    //      every CTA of the cluster computes it (identical arithmetic), rank 0 stores it after the first cluster barrier
     float* ep = D.ep + (size_t)e * np;
+    float upd_p = 0.f, upd_mu = 0.f, upd_nv = 0.f;
+    bool upd = false;
     if (tid < np) {
         float p = ep[tid];
         if (D.ctl[4] != 0.f && !noise) {
@@ -201,13 +266,16 @@ __global__ void __launch_bounds__(DC_THREADS) k_deconv_epoch(DeconvDev D, int fl
                 const BeliefCoef bc = {D.ctl[1], D.cv.b1, D.cv.b2, 1.f - D.cv.b1, 1.f - D.cv.b2, D.ctl[2], D.ctl[3],
                                        D.cv.eps, D.cv.eps_root};
                 float mu = D.ep_mu[(size_t)e * np + tid], nv = D.ep_nu[(size_t)e * np + tid];
-                belief_update(bc, D.ctl[0] * D.ep_g[(size_t)e * np + tid], p, mu, nv);
-                D.ep_mu[(size_t)e * np + tid] = mu; D.ep_nu[(size_t)e * np + tid] = nv;
-                ep[tid] = p;
+                float g = D.ep_g[(size_t)e * np + tid];
+                if (tid < M && D.lam_fu != 0.f)      // flux-uniformity gradient from the global statistics of the last evaluation
+                    g += D.fu[DC_MMAX + tid] * (p - D.fu[tid]) - D.fu[2 * DC_MMAX + tid];
+                belief_update(bc, D.ctl[0] * g, p, mu, nv);
+                upd = true; upd_p = p; upd_mu = mu; upd_nv = nv;
             }
         }
         par[tid] = p;
     }
+    if (tid < CS) remf[tid] = (CS > 1) ? (const float*)cl.map_shared_rank(fpl, tid) : fpl;
     for (int i = tid; i < kk * NA * NA; i += DC_THREADS) Ssm[i] = __ldg(D.S + (size_t)e * kk * NA * NA + i);
     __syncthreads();
 
@@ -234,103 +302,135 @@ __global__ void __launch_bounds__(DC_THREADS) k_deconv_epoch(DeconvDev D, int fl
         dst[DC_MMAX * 16 + m * 16 + t] = x * D.cv.invs2 * g;     // d g / d pc
         if (t == 0) iwin[axis * DC_MMAX + m] = ic - G / 2 + 1;
     }
-    // ---- f = warp(h) in polyphase layout
-    for (int i = tid; i < nu * nu; i += DC_THREADS) {
-        const int v = i / nu, u = i % nu;
-        float val = 0.f;
-        if (D.free_h || D.h != nullptr) {
-            float qu, qv;
-            geo_src(geo, (float)u, (float)v, qu, qv);
-            const float fu0 = floorf(qu), fv0 = floorf(qv);
-            const float fu = qu - fu0, fv = qv - fv0;
-            const int u0 = (int)fu0, v0 = (int)fv0;
-            val = (1.f - fv) * ((1.f - fu) * h_at(D.h, nu, v0, u0) + fu * h_at(D.h, nu, v0, u0 + 1)) +
-                  fv * ((1.f - fu) * h_at(D.h, nu, v0 + 1, u0) + fu * h_at(D.h, nu, v0 + 1, u0 + 1));
+    // ---- f = warp(h) in polyphase layout, only the plane rows the forward band reads
+    const int flo = max(0, Y0 + A0), fhi = min(n, Y1 + A0 + NA - 1);
+    if (!noise && own > 0) {
+        for (int i = tid; i < (fhi - flo) * k * nu; i += DC_THREADS) {
+            const int v = flo * k + i / nu, u = i % nu;
+            float val = 0.f;
+            if (D.h != nullptr) {
+                float qu, qv;
+                geo_src(geo, (float)u, (float)v, qu, qv);
+                const float fu0 = floorf(qu), fv0 = floorf(qv);
+                const float fu = qu - fu0, fv = qv - fv0;
+                const int u0 = (int)fu0, v0 = (int)fv0;
+                val = (1.f - fv) * ((1.f - fu) * h_at(D.h, nu, v0, u0) + fu * h_at(D.h, nu, v0, u0 + 1)) +
+                      fv * ((1.f - fu) * h_at(D.h, nu, v0 + 1, u0) + fu * h_at(D.h, nu, v0 + 1, u0 + 1));
+            }
+            fpl[((v % k) * k + (u % k)) * pst + (v / k) * ldf + u / k] = val;
         }
-        fpl[(((v % k) * k + (u % k)) * n + v / k) * ldf + u / k] = val;
     }
     __syncthreads();
-    for (int m = 0; m < M; ++m) {          // serially per source: windows of different sources may overlap
-        for (int i = tid; i < G * G; i += DC_THREADS) {
-            const int tv = i / G, tu = i % G;
-            const int v = iwin[DC_MMAX + m] + tv, u = iwin[m] + tu;
-            if (v >= 0 && v < nu && u >= 0 && u < nu)
-                fpl[(((v % k) * k + (u % k)) * n + v / k) * ldf + u / k] += par[m] * gy[m * 16 + tv] * gx[m * 16 + tu];
+    if (!noise && own > 0) {
+        for (int m = 0; m < M; ++m) {          // serially per source: windows of different sources may overlap
+            for (int i = tid; i < G * G; i += DC_THREADS) {
+                const int tv = i / G, tu = i % G;
+                const int v = iwin[DC_MMAX + m] + tv, u = iwin[m] + tu;
+                if (v >= flo * k && v < fhi * k && u >= 0 && u < nu)
+                    fpl[((v % k) * k + (u % k)) * pst + (v / k) * ldf + u / k] += par[m] * gy[m * 16 + tv] * gx[m * 16 + tu];
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
 
-    // ---- forward: m = mean + 1/k^2 sum_ph corr(f_ph, S_ph);  r = w (m - d)
+    // ---- forward: m = mean + 1/k^2 sum_ph corr(f_ph, S_ph);  r = w (m - d).  A task = XB outputs of one row for
+    //      one slice of the NA kernel rows (SPLIT slices on adjacent lanes, summed with shuffles) so that a narrow
+    //      band still gives every thread a task.
     const float dscale = D.cv.mean ? 1.f / (float)kk : 1.f;
     const float* dat = D.data + (size_t)e * n * n;
     const float* wgt = D.weight + (size_t)e * n * n;
     float loss = 0.f, gmean = 0.f;
     const int nxb = (n + DC_XB - 1) / DC_XB;
-    if (noise) for (int i = tid; i < n * n; i += DC_THREADS) rsm[(i / n) * ldr + i % n] = __ldg(wgt + i);
-    for (int task = tid; task < (noise ? 0 : n * nxb); task += DC_THREADS) {
-        const int Y = task % n, X0 = (task / n) * DC_XB;
-        float acc[DC_XB];
+    float* rdst[DC_CSMAX];
 #pragma unroll
-        for (int x = 0; x < DC_XB; ++x) acc[x] = 0.f;
-        for (int ph = 0; ph < kk; ++ph) corr_row(fpl + ph * n * ldf, ldf, n, Ssm + ph * NA * NA, NA, A0, Y, X0, acc);
+    for (int c = 0; c < DC_CSMAX; ++c) rdst[c] = (c < CS && CS > 1) ? (float*)cl.map_shared_rank(rsm, c) : rsm;
+    if (noise) {
+        for (int i = tid; i < n * n; i += DC_THREADS) rsm[(i / n) * ldr + i % n] = __ldg(wgt + i);
+    } else {
+        int SPLIT = 1;
+        while (SPLIT < 4 && own * nxb * SPLIT < DC_THREADS) SPLIT *= 2;
+        const int ias = (NA + SPLIT - 1) / SPLIT;
+        const int ntask = own * nxb * SPLIT, ntask_pad = (ntask + 31) & ~31;
+        for (int task = tid; task < ntask_pad; task += DC_THREADS) {
+            const bool valid = task < ntask;
+            const int s = task & (SPLIT - 1), t2 = task / SPLIT;
+            const int Y = Y0 + (valid ? t2 % own : 0), X0 = (valid ? t2 / own : 0) * DC_XB;
+            float acc[DC_XB];
 #pragma unroll
-        for (int x = 0; x < DC_XB; ++x) {
-            const int X = X0 + x;
-            if (X < n) {
-                const float mval = fmaf(dscale, acc[x], mean);
-                const float d = __ldg(dat + Y * n + X), w = __ldg(wgt + Y * n + X);
-                const float diff = mval - d, r = w * diff;
-                rsm[Y * ldr + X] = r;
-                loss = fmaf(r, diff, loss);
-                gmean += r;
-                if (want_model) D.model[(size_t)e * n * n + Y * n + X] = mval;
+            for (int x = 0; x < DC_XB; ++x) acc[x] = 0.f;
+            if (valid) {
+                const int ia0 = s * ias, ia1 = min(NA, ia0 + ias);
+                for (int ph = 0; ph < kk; ++ph) corr_row(fpl + ph * pst, ldf, n, Ssm + ph * NA * NA, NA, A0, ia0, ia1, Y, X0, acc);
+            }
+            for (int o = 1; o < SPLIT; o <<= 1) {
+#pragma unroll
+                for (int x = 0; x < DC_XB; ++x) acc[x] += __shfl_xor_sync(0xffffffffu, acc[x], o);
+            }
+            if (valid && s == 0) {
+#pragma unroll
+                for (int x = 0; x < DC_XB; ++x) {
+                    const int X = X0 + x;
+                    if (X < n) {
+                        const float mval = fmaf(dscale, acc[x], mean);
+                        const float d = __ldg(dat + Y * n + X), w = __ldg(wgt + Y * n + X);
+                        const float diff = mval - d, r = w * diff;
+#pragma unroll
+                        for (int c = 0; c < DC_CSMAX; ++c) if (c < CS) rdst[c][Y * ldr + X] = r;
+                        loss = fmaf(r, diff, loss);
+                        gmean += r;
+                        if (want_model) D.model[(size_t)e * n * n + Y * n + X] = mval;
+                    }
+                }
             }
         }
     }
-    __syncthreads();
-    // ---- adjoint: dL/df_ph[Y'][X'] = 1/k^2 sum S_ph[av][au] r[Y'-av][X'-au]   (overwrites f)
-    for (int task = tid; task < kk * n * nxb; task += DC_THREADS) {
-        const int ph = task / (n * nxb), rem = task % (n * nxb), Y = rem % n, X0 = (rem / n) * DC_XB;
+    cl.sync();                                    // #1: r complete in every CTA; all CTAs have read the old parameters
+    if (upd && crank == 0) {
+        ep[tid] = upd_p; D.ep_mu[(size_t)e * np + tid] = upd_mu; D.ep_nu[(size_t)e * np + tid] = upd_nv;
+    }
+    // ---- adjoint for the own band: dL/df_ph[Y'][X'] = 1/k^2 sum S_ph[av][au] r[Y'-av][X'-au]   (overwrites f)
+    for (int task = tid; task < kk * own * nxb; task += DC_THREADS) {
+        const int ph = task / (own * nxb), rem = task % (own * nxb), Y = Y0 + rem % own, X0 = (rem / own) * DC_XB;
         float acc[DC_XB];
 #pragma unroll
         for (int x = 0; x < DC_XB; ++x) acc[x] = 0.f;
         conv_row_T(rsm, ldr, n, Ssm + ph * NA * NA, NA, A0, Y, X0, acc, noise);
 #pragma unroll
         for (int x = 0; x < DC_XB; ++x)
-            if (X0 + x < n) fpl[(ph * n + Y) * ldf + X0 + x] = (noise ? dscale * dscale : dscale) * acc[x];
+            if (X0 + x < n) fpl[ph * pst + Y * ldf + X0 + x] = (noise ? dscale * dscale : dscale) * acc[x];
     }
     __syncthreads();
-    auto dfat = [&](int v, int u) -> float {
-        return (v >= 0 && v < nu && u >= 0 && u < nu) ? fpl[(((v % k) * k + (u % k)) * n + v / k) * ldf + u / k] : 0.f;
-    };
-    // ---- point-source gradients: one warp per source (M <= 8 warps)
+    const int vlo = Y0 * k, vhi = Y1 * k;         // rows of f whose dL/df lives in this CTA
     const float sc = (D.cv.half == 0.5f) ? 1.f : 2.f;
     const int warp = tid >> 5, lane = tid & 31;
-    float* epg = D.ep_g + (size_t)e * np;
+    float* cp0 = (CS > 1) ? (float*)cl.map_shared_rank(cpart, 0) : cpart;
+    // ---- point-source gradients: one warp per source (M <= 8 warps), own rows only
     if (warp < M && !noise) {
         const int m = warp;
         float ga = 0.f, gu = 0.f, gv = 0.f;
         for (int i = lane; i < G * G; i += 32) {
             const int tv = i / G, tu = i % G;
-            const float df = dfat(iwin[DC_MMAX + m] + tv, iwin[m] + tu);
-            const float gyv = gy[m * 16 + tv], gxv = gx[m * 16 + tu];
-            ga = fmaf(df, gyv * gxv, ga);
-            gu = fmaf(df, gyv * gx[DC_MMAX * 16 + m * 16 + tu], gu);
-            gv = fmaf(df, gy[DC_MMAX * 16 + m * 16 + tv] * gxv, gv);
+            const int v = iwin[DC_MMAX + m] + tv, u = iwin[m] + tu;
+            if (v >= vlo && v < vhi && u >= 0 && u < nu) {
+                const float df = fpl[((v % k) * k + (u % k)) * pst + (v / k) * ldf + u / k];
+                const float gyv = gy[m * 16 + tv], gxv = gx[m * 16 + tu];
+                ga = fmaf(df, gyv * gxv, ga);
+                gu = fmaf(df, gyv * gx[DC_MMAX * 16 + m * 16 + tu], gu);
+                gv = fmaf(df, gy[DC_MMAX * 16 + m * 16 + tv] * gxv, gv);
+            }
         }
         ga = warp_sum(ga); gu = warp_sum(gu); gv = warp_sum(gv);
         if (lane == 0) {
-            const float a = par[m];
-            epg[m] = sc * ga;
-            red[8 + m * 4] = a * gu;            // dL/d uc_m
-            red[8 + m * 4 + 1] = a * gv;        // dL/d vc_m
+            cp0[crank * 32 + 4 + 3 * m] = ga;
+            cp0[crank * 32 + 4 + 3 * m + 1] = gu;     // dL/d uc_m / a_m
+            cp0[crank * 32 + 4 + 3 * m + 2] = gv;     // dL/d vc_m / a_m
         }
     }
-    // ---- shift gradient through the warp: dL/dd = sum_p dL/df[p] * grad h(q(p)) . dq/dd
+    // ---- shift gradient through the warp: dL/dd = sum_p dL/df[p] * grad h(q(p)) . dq/dd   (own rows)
     float gwx = 0.f, gwy = 0.f;
-    if (D.free_d && !noise) {
-        for (int i = tid; i < nu * nu; i += DC_THREADS) {
-            const int v = i / nu, u = i % nu;
+    if (D.free_d && !noise && D.h != nullptr) {
+        for (int i = tid; i < (vhi - vlo) * nu; i += DC_THREADS) {
+            const int v = vlo + i / nu, u = i % nu;
             float qu, qv;
             geo_src(geo, (float)u, (float)v, qu, qv);
             const float fu0 = floorf(qu), fv0 = floorf(qv);
@@ -340,7 +440,7 @@ __global__ void __launch_bounds__(DC_THREADS) k_deconv_epoch(DeconvDev D, int fl
             const float h10 = h_at(D.h, nu, v0 + 1, u0), h11 = h_at(D.h, nu, v0 + 1, u0 + 1);
             const float dhu = (1.f - fv) * (h01 - h00) + fv * (h11 - h10);
             const float dhv = (1.f - fu) * (h10 - h00) + fu * (h11 - h01);
-            const float df = fpl[(((v % k) * k + (u % k)) * n + v / k) * ldf + u / k];
+            const float df = fpl[((v % k) * k + (u % k)) * pst + (v / k) * ldf + u / k];
             // dq/ddx = -k (ca, -sa),  dq/ddy = -k (sa, ca)
             gwx = fmaf(df, -(float)k * (ca * dhu - sa * dhv), gwx);
             gwy = fmaf(df, -(float)k * (sa * dhu + ca * dhv), gwy);
@@ -350,31 +450,124 @@ __global__ void __launch_bounds__(DC_THREADS) k_deconv_epoch(DeconvDev D, int fl
     gmean = block_sum(gmean, red, tid);
     gwx = block_sum(gwx, red, tid);
     gwy = block_sum(gwy, red, tid);
-    if (tid == 0 && !noise) {
-        float gdx = sc * gwx, gdy = sc * gwy;
-        for (int m = 0; m < M; ++m) {
-            const float gu = sc * red[8 + m * 4], gv = sc * red[8 + m * 4 + 1];
-            gdx += (float)k * gu; gdy += (float)k * gv;
-            D.gc[(size_t)e * 2 * M + m] = (float)k * (ca * gu + sa * gv);
-            D.gc[(size_t)e * 2 * M + M + m] = (float)k * (-sa * gu + ca * gv);
+    if (tid == 0) { cp0[crank * 32] = loss; cp0[crank * 32 + 1] = gmean; cp0[crank * 32 + 2] = gwx; cp0[crank * 32 + 3] = gwy; }
+
+    // ---- pts-source regulariser (rank 0): lam * sum_x W_0[x] |alpha_0(p_e)[x]|, p_e = point-source channel of the
+    //      epoch, alpha_0 = first starlet scale.  The Gaussians are separable, so alpha_0(g_m)(v,u) =
+    //      g_y(v) g_x(u) - (B g_y)(v) (B g_x)(u) with B the edge-replicated 5-tap B3 filter; by linearity
+    //      dR/dtheta = sum_x T[x] alpha_0(dp/dtheta)[x], T = lam W_0 sign(alpha_0(p)).
+    const float lam_pts = (noise || (!D.pts_all_epochs && e + D.e0 != 0)) ? 0.f : D.lam_pts;
+    const int GEX = G + 4;
+    if (crank == 0 && lam_pts != 0.f) {
+        if (tid < 2 * M * GEX) {
+            const int axis = tid / (M * GEX), m = (tid / GEX) % M, t = tid % GEX;
+            const int w0 = iwin[axis * DC_MMAX + m];
+            const float* g0 = (axis == 0 ? gx : gy) + m * 16;
+            const float* g1 = g0 + DC_MMAX * 16;
+            const int u = w0 - 2 + t;
+            const float B[5] = {1.f / 16.f, 4.f / 16.f, 6.f / 16.f, 4.f / 16.f, 1.f / 16.f};
+            float bg = 0.f, bd = 0.f;
+#pragma unroll
+            for (int tt = -2; tt <= 2; ++tt) {
+                const int uu = min(max(u + tt, 0), nu - 1) - w0;
+                if (uu >= 0 && uu < G) { bg = fmaf(B[tt + 2], g0[uu], bg); bd = fmaf(B[tt + 2], g1[uu], bd); }
+            }
+            const bool in = (t >= 2 && t < G + 2);
+            float* ex = ext + (axis * DC_MMAX + m) * 4 * DC_EXT;
+            ex[t] = in ? g0[t - 2] : 0.f;
+            ex[DC_EXT + t] = bg;
+            ex[2 * DC_EXT + t] = in ? g1[t - 2] : 0.f;
+            ex[3 * DC_EXT + t] = bd;
         }
-        epg[M] = gdx; epg[M + 1] = gdy; epg[M + 2] = sc * gmean;
-        D.eloss[e] = D.cv.half * loss;
+        __syncthreads();
+        if (warp < M) {
+            const int m = warp;
+            float pl = 0.f, pa[DC_MMAX], pu[DC_MMAX], pv[DC_MMAX];
+#pragma unroll
+            for (int q = 0; q < DC_MMAX; ++q) pa[q] = pu[q] = pv[q] = 0.f;
+            for (int i = lane; i < GEX * GEX; i += 32) {
+                const int v = iwin[DC_MMAX + m] - 2 + i / GEX, u = iwin[m] - 2 + i % GEX;
+                if (v < 0 || v >= nu || u < 0 || u >= nu) continue;
+                bool dup = false;                  // pixel already counted by a source of lower index
+                for (int q = 0; q < m; ++q) {
+                    const int tv = v - (iwin[DC_MMAX + q] - 2), tu = u - (iwin[q] - 2);
+                    dup = dup || (tv >= 0 && tv < GEX && tu >= 0 && tu < GEX);
+                }
+                if (dup) continue;
+                float al0 = 0.f, ca_[DC_MMAX], cu_[DC_MMAX], cv_[DC_MMAX];
+#pragma unroll
+                for (int q = 0; q < DC_MMAX; ++q) {
+                    ca_[q] = cu_[q] = cv_[q] = 0.f;
+                    if (q < M) {
+                        const int tv = v - (iwin[DC_MMAX + q] - 2), tu = u - (iwin[q] - 2);
+                        if (tv >= 0 && tv < GEX && tu >= 0 && tu < GEX) {
+                            const float* ex = ext + q * 4 * DC_EXT;
+                            const float* ey = ext + (DC_MMAX + q) * 4 * DC_EXT;
+                            const float gxu = ex[tu], bxu = ex[DC_EXT + tu], dxu = ex[2 * DC_EXT + tu], bdxu = ex[3 * DC_EXT + tu];
+                            const float gyv = ey[tv], byv = ey[DC_EXT + tv], dyv = ey[2 * DC_EXT + tv], bdyv = ey[3 * DC_EXT + tv];
+                            ca_[q] = gyv * gxu - byv * bxu;
+                            cu_[q] = gyv * dxu - byv * bdxu;
+                            cv_[q] = dyv * gxu - bdyv * bxu;
+                            al0 = fmaf(par[q], ca_[q], al0);
+                        }
+                    }
+                }
+                const float lw = lam_pts * (D.W ? __ldg(D.W + (size_t)v * nu + u) : 1.f);
+                pl = fmaf(lw, fabsf(al0), pl);
+                const float T = (al0 > 0.f) ? lw : (al0 < 0.f) ? -lw : 0.f;
+#pragma unroll
+                for (int q = 0; q < DC_MMAX; ++q) { pa[q] = fmaf(T, ca_[q], pa[q]); pu[q] = fmaf(T, cu_[q], pu[q]); pv[q] = fmaf(T, cv_[q], pv[q]); }
+            }
+            pl = warp_sum(pl);
+            if (lane == 0) ptsacc[m * 32] = pl;
+#pragma unroll
+            for (int q = 0; q < DC_MMAX; ++q) {
+                const float s0 = warp_sum(pa[q]), s1 = warp_sum(pu[q]), s2 = warp_sum(pv[q]);
+                if (lane == 0 && q < M) { ptsacc[m * 32 + 1 + 3 * q] = s0; ptsacc[m * 32 + 2 + 3 * q] = s1; ptsacc[m * 32 + 3 + 3 * q] = s2; }
+            }
+        }
     }
-    // ---- transposed warp as an exact gather: dL/dh[q] = sum_p dL/df[p] * hat(q - q(p))
+    cl.sync();                                    // #2: dL/df bands and partial sums complete
+    float* epg = D.ep_g + (size_t)e * np;
+    if (crank == 0 && tid == 0 && !noise) {
+        float ls = 0.f, gm = 0.f, wx = 0.f, wy = 0.f, ga[DC_MMAX], gu[DC_MMAX], gv[DC_MMAX];
+        for (int m = 0; m < M; ++m) ga[m] = gu[m] = gv[m] = 0.f;
+        for (int c = 0; c < CS; ++c) {            // fixed order: the result does not depend on scheduling
+            const float* q = cpart + c * 32;
+            ls += q[0]; gm += q[1]; wx += q[2]; wy += q[3];
+            for (int m = 0; m < M; ++m) { ga[m] += q[4 + 3 * m]; gu[m] += q[5 + 3 * m]; gv[m] += q[6 + 3 * m]; }
+        }
+        float ploss = 0.f;
+        float gdx = sc * wx, gdy = sc * wy;
+        for (int m = 0; m < M; ++m) {
+            float pa = 0.f, pu = 0.f, pv = 0.f;
+            if (lam_pts != 0.f)
+                for (int w = 0; w < M; ++w) { pa += ptsacc[w * 32 + 1 + 3 * m]; pu += ptsacc[w * 32 + 2 + 3 * m]; pv += ptsacc[w * 32 + 3 + 3 * m]; }
+            const float a = par[m];
+            const float GU = a * (sc * gu[m] + pu), GV = a * (sc * gv[m] + pv);
+            gdx += (float)k * GU; gdy += (float)k * GV;
+            D.gc[(size_t)e * 2 * M + m] = (float)k * (ca * GU + sa * GV);
+            D.gc[(size_t)e * 2 * M + M + m] = (float)k * (-sa * GU + ca * GV);
+            epg[m] = sc * ga[m] + pa;
+        }
+        if (lam_pts != 0.f) for (int w = 0; w < M; ++w) ploss += ptsacc[w * 32];
+        epg[M] = gdx; epg[M + 1] = gdy; epg[M + 2] = sc * gm;
+        D.eloss[e] = D.cv.half * ls + ploss;
+    }
+    // ---- transposed warp as an exact gather for the own rows of h: dL/dh[q] = sum_p dL/df[p] * hat(q - q(p));
+    //      dL/df of the other bands is read through distributed shared memory
     if (D.free_h || noise) {
         float* Gh = D.Gh + (size_t)e * nu * nu;
-        for (int i = tid; i < nu * nu; i += DC_THREADS) {
-            const int qv_i = i / nu, qu_i = i % nu;
+        const int b_lo = (al == 0.f) ? 1 : 0, b_hi = (al == 0.f) ? 3 : 4;   // pure translation: 2 x 2 candidates
+        for (int i = tid; i < (vhi - vlo) * nu; i += DC_THREADS) {
+            const int qv_i = vlo + i / nu, qu_i = i % nu;
             // forward image of q: p_c = R (q - ctr) + ctr + k d
             const float ru = (float)qu_i - ctr, rv = (float)qv_i - ctr;
             const float pcu = ca * ru - sa * rv + ctr + geo.tx, pcv = sa * ru + ca * rv + ctr + geo.ty;
             const int pu0 = (int)floorf(pcu) - 1, pv0 = (int)floorf(pcv) - 1;
             float acc = 0.f;
-#pragma unroll
-            for (int b = 0; b < 4; ++b)
-#pragma unroll
-                for (int a2 = 0; a2 < 4; ++a2) {
+            for (int b = b_lo; b < b_hi; ++b)
+                for (int a2 = b_lo; a2 < b_hi; ++a2) {
                     const int pv = pv0 + b, pu = pu0 + a2;
                     if (pv < 0 || pv >= nu || pu < 0 || pu >= nu) continue;
                     float qu, qv;
@@ -385,42 +578,69 @@ __global__ void __launch_bounds__(DC_THREADS) k_deconv_epoch(DeconvDev D, int fl
                     if ((int)fu0 == qu_i) wu = 1.f - (qu - fu0); else if ((int)fu0 + 1 == qu_i) wu = qu - fu0;
                     if ((int)fv0 == qv_i) wv = 1.f - (qv - fv0); else if ((int)fv0 + 1 == qv_i) wv = qv - fv0;
                     if (noise) { wu *= wu; wv *= wv; }
-                    if (wu != 0.f && wv != 0.f) acc = fmaf(wu * wv, fpl[(((pv % k) * k + (pu % k)) * n + pv / k) * ldf + pu / k], acc);
+                    if (wu != 0.f && wv != 0.f) {
+                        const int Yp = pv / k;
+                        const float* src = remf[min(Yp / rpc, CS - 1)];
+                        acc = fmaf(wu * wv, src[((pv % k) * k + (pu % k)) * pst + Yp * ldf + pu / k], acc);
+                    }
                 }
-            Gh[i] = noise ? acc : sc * acc;
+            Gh[i + vlo * nu] = noise ? acc : sc * acc;
         }
     }
+    cl.sync();                                    // #3: no CTA leaves while its shared memory may still be read
 }
 
-// ---------------------------------------------------------------- reduction over the local epochs
-__global__ void __launch_bounds__(256) k_deconv_reduce(DeconvDev D, int force_h) {
+// ---------------------------------------------------------------- reduction over the local epochs (+ push to the peers)
+// seq == 0: red[] <- local sums.  seq > 0 (multi-GPU): the local sums go to slot [seq&1][my rank] of EVERY rank's
+// receive buffer (plain stores into peer memory over NVLink); the last CTA to finish raises flag [seq&1][my rank] = seq
+// on every rank (fence - atomic - fence - flag, the threadFenceReduction pattern at system scope).
+__global__ void __launch_bounds__(256) k_deconv_reduce(DeconvDev D, int force_h, int seq) {
     const int nu2 = D.nu * D.nu, M = D.M, np = D.M + 3;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int iflux = red_flux(D);
+    float s = 0.f;
     if (i < nu2) {
-        float s = 0.f;
         if (D.free_h || force_h) for (int e = 0; e < D.E; ++e) s += D.Gh[(size_t)e * nu2 + i];
-        D.red[i] = s;
     } else if (i < nu2 + 2 * M) {
-        float s = 0.f;
         for (int e = 0; e < D.E; ++e) s += D.gc[(size_t)e * 2 * M + (i - nu2)];
-        D.red[i] = s;
     } else if (i == nu2 + 2 * M) {
-        float s = 0.f;
         for (int e = 0; e < D.E; ++e) s += D.eloss[e];
-        D.red[i] = s;
     } else if (i == nu2 + 2 * M + 1) {
-        float s = 0.f;
         for (int e = 0; e < D.E; ++e)
             for (int p = 0; p < np; ++p) {
                 const bool is_free = (p < M) ? D.free_a : (p < M + 2) ? D.free_d : D.free_mean;
                 const float g = D.ep_g[(size_t)e * np + p];
                 if (is_free) s = fmaf(g, g, s);
             }
-        D.red[i] = s;
+    } else if (i < iflux + 4 * M) {
+        // flux statistics per source, shifted by the last known mean K_m: sum (a-K), sum (a-K)^2, sum g, sum g (a-K)
+        const int q = (i - iflux) / M, m = (i - iflux) % M;
+        const float K = D.fu[m];
+        for (int e = 0; e < D.E; ++e) {
+            const float a = D.ep[(size_t)e * np + m] - K, g = D.ep_g[(size_t)e * np + m];
+            s += (q == 0) ? a : (q == 1) ? a * a : (q == 2) ? g : g * a;
+        }
+    }
+    if (seq == 0) {
+        if (i < D.tot) D.red[i] = s;
+        return;
+    }
+    const int W = D.cm.world, par = seq & 1;
+    if (i < D.tot)
+        for (int r = 0; r < W; ++r) D.cm.slots[r][((size_t)par * W + D.cm.rank) * D.tot + i] = s;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(D.cm.ctr + par, 1u);
+        if (prev == gridDim.x - 1) {
+            D.cm.ctr[par] = 0;                      // next use of this parity is two iterations (kernel launches) later
+            __threadfence_system();
+            for (int r = 0; r < W; ++r) *(volatile int*)(D.cm.flags[r] + par * W + D.cm.rank) = seq;
+        }
     }
 }
 
-// ---------------------------------------------------------------- shared-parameter update (one CTA)
+// ---------------------------------------------------------------- shared-parameter update (one cluster)
 __device__ __forceinline__ float atrous_g(const float* __restrict__ c, int nu, int v, int u, int Dd, int axis) {
     const float h0 = 1.f / 16.f, h1 = 4.f / 16.f, h2 = 6.f / 16.f;
     if (axis == 0) {
@@ -462,11 +682,11 @@ __device__ __forceinline__ float atrous_adj(const float* __restrict__ base, int 
 
 #define DU_THREADS 1024
 #define DU_CTAS 8
+#define DU_TIMEOUT (5LL << 31)      // ~5 s of SM clocks: a peer that never arrives must not hang the GPU
 // The replicated half of an iteration runs on ONE thread-block cluster of 8 CTAs (8192 threads): the nu x nu
 // planes live in global memory (L2), every stencil / point-wise pass is spread over the whole cluster and
 // passes are separated by cluster.sync() (barrier.cluster arrive.release / wait.acquire, ~0.3 us) instead of
 // kernel boundaries.  Cross-CTA sums go through a small global array in a fixed order (deterministic).
-namespace cg = cooperative_groups;
 
 __device__ __forceinline__ float cluster_sum(float v, float* red, float* gpart, int slot, int tid, int rank) {
     v = warp_sum(v);
@@ -484,15 +704,39 @@ __device__ __forceinline__ float cluster_sum(float v, float* red, float* gpart, 
     return s;
 }
 
-// it < 0: evaluation only (loss + full gradient into the output arrays, no update)
+// it < 0: evaluation only (loss + full gradient into the output arrays, no update).  seq > 0: red[] is first
+// assembled from the receive slots of all ranks (summed in rank order: bit-identical everywhere).
 __global__ void __cluster_dims__(DU_CTAS, 1, 1) __launch_bounds__(DU_THREADS)
-k_deconv_update(DeconvDev D, int it, int n_iter, float lr0, int schedule, float* grad_h_out, float* grad_c_out, float* loss_out) {
+k_deconv_update(DeconvDev D, int it, int n_iter, float lr0, int schedule, int seq, float* grad_h_out, float* grad_c_out, float* loss_out) {
     __shared__ float red[DU_THREADS / 32];
+    __shared__ float fus[4 * DC_MMAX];
     cg::cluster_group cl = cg::this_cluster();
     const int rank = (int)cl.block_rank();
     const int tid = threadIdx.x, gtid = rank * DU_THREADS + tid;
     constexpr int GT_ALL = DU_CTAS * DU_THREADS;
     const int nu = D.nu, pp = nu * nu, M = D.M, J = D.J;
+    if (seq > 0) {
+        const int W = D.cm.world, par = seq & 1;
+        if (tid < W) {
+            volatile int* f = D.cm.flags[D.cm.rank] + par * W + tid;
+            if (*(volatile float*)(D.ctl + 7) == 0.f) {
+                const long long t0 = clock64();
+                while (*f < seq) {
+                    if (clock64() - t0 > DU_TIMEOUT) { D.ctl[7] = 1.f; break; }
+                }
+            }
+        }
+        __threadfence_system();
+        __syncthreads();
+        const float* sl = D.cm.slots[D.cm.rank] + (size_t)par * W * D.tot;
+        for (int i = gtid; i < D.tot; i += GT_ALL) {
+            float s = 0.f;
+            for (int r = 0; r < W; ++r) s += __ldcg(sl + (size_t)r * D.tot + i);
+            D.red[i] = s;
+        }
+        __threadfence();
+        cl.sync();
+    }
     float* C0 = D.planes;
     float* C1 = C0 + pp;
     float* GT = C1 + pp;                 // total gradient wrt h
@@ -554,11 +798,43 @@ k_deconv_update(DeconvDev D, int it, int n_iter, float lr0, int schedule, float*
         if (grad_c_out && rank == 0) grad_c_out[tid] = g;
         if (D.free_c && rank == 0) gn2 = fmaf(g, g, gn2);
     }
+    // flux uniformity: lam * sum_m std_e(a_em) [/ |mean_e(a_em)|] from the all-reduced shifted sums; the gradient
+    // wrt a_em is A_m (a_em - mean_m) - B_m, applied by the epoch kernel with the pending update
+    float fu_loss = 0.f;
+    if (D.lam_fu != 0.f && tid < M) {
+        const int o = red_flux(D);
+        const float Et = (float)D.E_total, K = D.fu[tid];
+        const float S1 = D.red[o + tid], S2 = D.red[o + M + tid], Sg = D.red[o + 2 * M + tid], Sga = D.red[o + 3 * M + tid];
+        const float dm = S1 / Et, mean = K + dm;
+        const float var = fmaxf(S2 / Et - dm * dm, 0.f), sd = sqrtf(var);
+        float A = 0.f, B = 0.f, val = 0.f;
+        if (sd > 0.f) {
+            if (D.fu_relative) {
+                const float am = fabsf(mean);
+                val = D.lam_fu * sd / am;
+                A = D.lam_fu / (Et * sd * am);
+                B = D.lam_fu * sd * ((mean > 0.f) ? 1.f : -1.f) / (Et * mean * mean);
+            } else {
+                val = D.lam_fu * sd;
+                A = D.lam_fu / (Et * sd);
+            }
+        }
+        fus[tid] = mean; fus[DC_MMAX + tid] = A; fus[2 * DC_MMAX + tid] = B;
+        if (rank == 0) {
+            fu_loss = val;
+            // |g_a|^2 with the flux-uniformity term: sum_e (g + A (a - mean) - B)^2
+            if (D.free_a) gn2 += A * A * var * Et + Et * B * B + 2.f * A * (Sga - dm * Sg) - 2.f * B * Sg;
+        }
+    }
     reg = cluster_sum(reg, red, gpart, 0, tid, rank);
     pos = cluster_sum(pos, red, gpart, 1, tid, rank);
     prior_loss = cluster_sum(prior_loss, red, gpart, 2, tid, rank);
+    fu_loss = cluster_sum(fu_loss, red, gpart, 4, tid, rank);
     gn2 = cluster_sum(gn2, red, gpart, 3, tid, rank) + D.red[pp + 2 * M + 1];
-    const float L = D.red[pp + 2 * M] + reg + pos + prior_loss;
+    const float L = D.red[pp + 2 * M] + reg + pos + prior_loss + fu_loss;
+    if (rank == 0 && D.lam_fu != 0.f && tid < M) {      // every read of D.fu above is behind a cluster barrier
+        D.fu[tid] = fus[tid]; D.fu[DC_MMAX + tid] = fus[DC_MMAX + tid]; D.fu[2 * DC_MMAX + tid] = fus[2 * DC_MMAX + tid];
+    }
     if (gtid == 0) {
         if (loss_out) loss_out[0] = L;
         if (it >= 0 && D.loss_hist) D.loss_hist[it] = L;
@@ -589,13 +865,29 @@ k_deconv_update(DeconvDev D, int it, int n_iter, float lr0, int schedule, float*
     if (gtid == 0) { D.ctl[0] = cs; D.ctl[1] = lr; D.ctl[2] = bc.inv_bc1; D.ctl[3] = bc.inv_bc2; D.ctl[4] = 1.f; }
 }
 
+// adds the flux-uniformity gradient to the stored per-epoch gradients (evaluation path only: lcb_deconv_loss_grad)
+__global__ void k_deconv_fu_apply(DeconvDev D) {
+    const int np = D.M + 3;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= D.E * D.M) return;
+    const int e = i / D.M, m = i % D.M;
+    D.ep_g[(size_t)e * np + m] += D.fu[DC_MMAX + m] * (D.ep[(size_t)e * np + m] - D.fu[m]) - D.fu[2 * DC_MMAX + m];
+}
+
 // ================================================================= host side: handle-based ABI
 struct DeconvHandle {
     DeconvDev D;
     std::vector<void*> owned;
+    std::vector<void*> ipc_open;         // peer mappings to close
+    void* comm_buf;                      // own receive buffer (IPC exported)
     cudaStream_t st;
     int loss_cap;
     size_t smem_epoch;
+    int CS;                              // CTAs per epoch (cluster size); 0 = not yet chosen
+    int CS_user;
+    int n_sm;
+    int seq;                             // sequence number of the in-kernel all-reduce
+    float *gh, *gcx, *ls;                // evaluation outputs (lcb_deconv_loss_grad / _get)
 };
 
 static int dalloc(DeconvHandle* H, void** p, size_t bytes, bool zero) {
@@ -620,12 +912,68 @@ static int get(DeconvHandle* H, float* dst, const float* src, size_t count, int 
     return LCB_OK;
 }
 
+// CTAs per epoch: the smallest power of two (<= 8, bands of >= 4 rows) that gives the GPU >= 4 CTAs per SM to
+// balance (two are resident at a time), e.g. 200 local epochs -> 4, 100 -> 8, 25 -> 8, >= 592 -> 1.
+static int choose_cluster(const DeconvHandle* H) {
+    const DeconvDev& D = H->D;
+    int cs = 1;
+    if (H->CS_user > 0) cs = H->CS_user;
+    else while (cs < DC_CSMAX && D.E * cs < 4 * H->n_sm) cs *= 2;
+    while (cs > 1 && (D.n + cs - 1) / cs < 4) cs /= 2;
+    return cs;
+}
+
+static int launch_epoch(DeconvHandle* H, int flags) {
+    DeconvDev& D = H->D;
+    if (H->CS == 0) H->CS = choose_cluster(H);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(D.E * H->CS), 1, 1);
+    cfg.blockDim = dim3(DC_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = H->smem_epoch;
+    cfg.stream = H->st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)H->CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    LcbProfScope ps("k_deconv_epoch", H->st);
+    LCB_CUDA(cudaLaunchKernelEx(&cfg, k_deconv_epoch, D, flags, H->CS));
+    return LCB_OK;
+}
+
+static int launch_reduce(DeconvHandle* H, int force_h, int seq) {
+    DeconvDev& D = H->D;
+    LcbProfScope ps("k_deconv_reduce", H->st);
+    k_deconv_reduce<<<(D.tot + 255) / 256, 256, 0, H->st>>>(D, force_h, seq);
+    LCB_CUDA(cudaGetLastError());
+    return LCB_OK;
+}
+
+static int launch_update(DeconvHandle* H, int it, int n_iter, float lr, int schedule, int seq, float* gh, float* gc, float* ls) {
+    LcbProfScope ps("k_deconv_update", H->st);
+    k_deconv_update<<<DU_CTAS, DU_THREADS, 0, H->st>>>(H->D, it, n_iter, lr, schedule, seq, gh, gc, ls);
+    LCB_CUDA(cudaGetLastError());
+    return LCB_OK;
+}
+
+static int next_seq(DeconvHandle* H) { return (H->D.cm.world > 1) ? ++H->seq : 0; }
+
+static int check_peers(DeconvHandle* H) {
+    if (H->D.cm.world <= 1) return LCB_OK;
+    float flag = 0.f;
+    LCB_CUDA(cudaMemcpyAsync(&flag, H->D.ctl + 7, 4, cudaMemcpyDeviceToHost, H->st));
+    LCB_CUDA(cudaStreamSynchronize(H->st));
+    if (flag != 0.f) { lcb_set_error("joint deconvolution: a peer rank did not deliver its gradient within the time limit"); return LCB_ERR_CUDA; }
+    return LCB_OK;
+}
+
 extern "C" {
 
 int lcb_deconv_destroy(void* handle) {
     DeconvHandle* H = (DeconvHandle*)handle;
     if (!H) return LCB_OK;
     cudaStreamSynchronize(H->st);
+    for (void* p : H->ipc_open) cudaIpcCloseMemHandle(p);
+    if (H->comm_buf) cudaFree(H->comm_buf);
     for (void* p : H->owned) cudaFree(p);
     delete H;
     return LCB_OK;
@@ -639,9 +987,15 @@ int lcb_deconv_create(const lcb_deconv_problem* p, int mem, void* stream, void**
     if (lcb_device_count() == 0) { lcb_set_error("no CUDA device: liblcb has no CPU fallback"); return LCB_ERR_CUDA; }
     DeconvHandle* H = new DeconvHandle();
     H->st = (cudaStream_t)stream;
+    H->comm_buf = nullptr; H->CS = 0; H->CS_user = 0; H->seq = 0;
+    if (const char* ev = getenv("LCB_DECONV_CS")) H->CS_user = atoi(ev);
     DeconvDev& D = H->D;
     memset(&D, 0, sizeof(D));
     D.E = p->E; D.n = p->n; D.k = p->k; D.nu = p->n * p->k; D.P = p->P; D.M = p->M;
+    D.E_total = p->E; D.e0 = 0;
+    D.cm.world = 1; D.cm.rank = 0;
+    D.pts_all_epochs = 1; D.fu_relative = 1;
+    D.tot = D.nu * D.nu + 6 * D.M + 2;
     D.cv = lcb_devconv();
     D.G = D.cv.G;
     LCB_REQUIRE(D.G <= 16, "gauss_taps must be <= 16");
@@ -659,9 +1013,11 @@ int lcb_deconv_create(const lcb_deconv_problem* p, int mem, void* stream, void**
     AL(c, 2 * (size_t)DC_MMAX, true) AL(c_mu, 2 * (size_t)DC_MMAX, true) AL(c_nu, 2 * (size_t)DC_MMAX, true)
     AL(ep, E * np, true) AL(ep_mu, E * np, true) AL(ep_nu, E * np, true) AL(ep_g, E * np, true)
     AL(alpha, E, true) AL(Gh, E * pp, true) AL(gc, E * 2 * (size_t)DC_MMAX, true) AL(eloss, E, true)
-    AL(red, pp + 2 * DC_MMAX + 2, true) AL(ctl, 8, true) AL(gpart, 64, true) AL(planes, (3 + (size_t)J) * pp, true)
-    AL(model, E * nn, true) AL(prior, 4 * (size_t)DC_MMAX, true)
+    AL(red, pp + 6 * DC_MMAX + 2, true) AL(ctl, 8, true) AL(fu, 3 * (size_t)DC_MMAX, true) AL(gpart, 64, true)
+    AL(planes, (3 + (size_t)J) * pp, true) AL(model, E * nn, true) AL(prior, 4 * (size_t)DC_MMAX, true)
 #undef AL
+    if ((rc = dalloc(H, (void**)&H->gh, pp * 4, true)) || (rc = dalloc(H, (void**)&H->gcx, 2 * DC_MMAX * 4, true)) ||
+        (rc = dalloc(H, (void**)&H->ls, 4, true))) { lcb_deconv_destroy(H); return rc; }
     D.W = nullptr;                                    // allocated by lcb_deconv_set_reg when weights are given
     H->loss_cap = 0; D.loss_hist = nullptr;
     // inputs
@@ -672,10 +1028,11 @@ int lcb_deconv_create(const lcb_deconv_problem* p, int mem, void* stream, void**
     k_deconv_fold_psf<<<D.E, 256, 0, H->st>>>(psf_d, D.S, D.E, D.P, D.k, D.NA, D.A0);
     if (cudaGetLastError() != cudaSuccess) { lcb_set_error("k_deconv_fold_psf launch failed"); lcb_deconv_destroy(H); return LCB_ERR_CUDA; }
     D.free_h = D.free_mean = D.free_a = D.free_c = D.free_d = 1;
-    H->smem_epoch = (kk * D.NA * D.NA + kk * D.n * (D.n + 1) + (size_t)D.n * (D.n + 1) + 4 * DC_MMAX * 16 + 16 + 8 + 4 * DC_MMAX) * 4;
+    H->smem_epoch = (size_t)dc_layout(D.n, D.k, D.NA).total * 4;
     int dev = 0, maxsm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaDeviceGetAttribute(&H->n_sm, cudaDevAttrMultiProcessorCount, dev);
     if (H->smem_epoch > (size_t)maxsm) {
         lcb_set_error("deconvolution: n=%d k=%d P=%d needs %zu B of shared memory per epoch (> %d)", D.n, D.k, D.P, H->smem_epoch, maxsm);
         lcb_deconv_destroy(H);
@@ -683,6 +1040,80 @@ int lcb_deconv_create(const lcb_deconv_problem* p, int mem, void* stream, void**
     }
     cudaFuncSetAttribute(k_deconv_epoch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H->smem_epoch);
     *handle = H;
+    return LCB_OK;
+}
+
+int lcb_deconv_set_cluster(void* handle, int ctas_per_epoch) {
+    DeconvHandle* H = (DeconvHandle*)handle;
+    LCB_REQUIRE(H, "lcb_deconv_set_cluster: NULL handle");
+    LCB_REQUIRE(ctas_per_epoch == 0 || ctas_per_epoch == 1 || ctas_per_epoch == 2 || ctas_per_epoch == 4 || ctas_per_epoch == 8,
+                "lcb_deconv_set_cluster: CTAs per epoch must be 0 (automatic), 1, 2, 4 or 8");
+    H->CS_user = ctas_per_epoch; H->CS = 0;
+    return LCB_OK;
+}
+
+int lcb_deconv_get_cluster(void* handle) {
+    DeconvHandle* H = (DeconvHandle*)handle;
+    if (!H) return 0;
+    return H->CS ? H->CS : choose_cluster(H);
+}
+
+// epochs over all ranks, global index of the first local epoch, and (may be NULL) the per-source shift used for
+// the flux statistics (any value near the mean flux of each source; identical on every rank)
+int lcb_deconv_set_global(void* handle, int E_total, int e0, const float* flux_shift, int mem) {
+    DeconvHandle* H = (DeconvHandle*)handle;
+    LCB_REQUIRE(H && E_total >= H->D.E && e0 >= 0, "lcb_deconv_set_global: bad arguments");
+    H->D.E_total = E_total; H->D.e0 = e0;
+    return put(H, H->D.fu, flux_shift, H->D.M, mem);
+}
+
+// ---- in-kernel all-reduce over peer memory: every rank allocates a receive buffer, exports it with CUDA IPC
+//      (comm_init), the caller exchanges the 64-byte handles (any transport) and every rank maps its peers (comm_connect)
+int lcb_deconv_comm_init(void* handle, int rank, int world, void* ipc_handle_out) {
+    DeconvHandle* H = (DeconvHandle*)handle;
+    LCB_REQUIRE(H && ipc_handle_out && world >= 1 && world <= DC_MAXW && rank >= 0 && rank < world,
+                "lcb_deconv_comm_init: bad arguments (world <= %d)", DC_MAXW);
+    LCB_REQUIRE(!H->comm_buf, "lcb_deconv_comm_init: already initialised");
+    DeconvDev& D = H->D;
+    const size_t slots_bytes = ((size_t)2 * world * D.tot * 4 + 255) & ~(size_t)255;
+    const size_t bytes = slots_bytes + (size_t)2 * world * 4 + 256;
+    LCB_CUDA(cudaMalloc(&H->comm_buf, bytes));
+    LCB_CUDA(cudaMemset(H->comm_buf, 0, bytes));
+    LCB_CUDA(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t hd;
+    LCB_CUDA(cudaIpcGetMemHandle(&hd, H->comm_buf));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    memcpy(ipc_handle_out, &hd, 64);
+    D.cm.world = world; D.cm.rank = rank;
+    D.cm.slots[rank] = (float*)H->comm_buf;
+    D.cm.flags[rank] = (int*)((char*)H->comm_buf + slots_bytes);
+    int rc;
+    if ((rc = dalloc(H, (void**)&D.cm.ctr, 2 * sizeof(unsigned), true))) return rc;
+    LCB_CUDA(cudaStreamSynchronize(H->st));
+    if (world == 1) { D.cm.world = 1; }
+    return LCB_OK;
+}
+
+int lcb_deconv_comm_connect(void* handle, const void* all_handles) {
+    DeconvHandle* H = (DeconvHandle*)handle;
+    LCB_REQUIRE(H && all_handles && H->comm_buf, "lcb_deconv_comm_connect: call lcb_deconv_comm_init first");
+    DeconvDev& D = H->D;
+    const size_t slots_bytes = ((size_t)2 * D.cm.world * D.tot * 4 + 255) & ~(size_t)255;
+    for (int r = 0; r < D.cm.world; ++r) {
+        if (r == D.cm.rank) continue;
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, (const char*)all_handles + (size_t)r * 64, 64);
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            lcb_set_error("cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+            cudaGetLastError();
+            return LCB_ERR_CUDA;
+        }
+        H->ipc_open.push_back(p);
+        D.cm.slots[r] = (float*)p;
+        D.cm.flags[r] = (int*)((char*)p + slots_bytes);
+    }
     return LCB_OK;
 }
 
@@ -696,7 +1127,7 @@ int lcb_deconv_set_params(void* handle, const lcb_deconv_params* q, int mem) {
     if ((rc = put(H, D.c, q->c_x, D.M, mem)) || (rc = put(H, D.c + D.M, q->c_y, D.M, mem))) return rc;
     if ((rc = put(H, D.alpha, q->alpha, E, mem))) return rc;
     // per-epoch block [E][M+3] is assembled on the host side of the copy: strided device copies
-    if (q->a) LCB_CUDA(cudaMemcpy2DAsync(D.ep, np * 4, q->a, D.M * 4, D.M * 4, E, mem == LCB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, H->st));
+    if (q->a && D.M > 0) LCB_CUDA(cudaMemcpy2DAsync(D.ep, np * 4, q->a, D.M * 4, D.M * 4, E, mem == LCB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, H->st));
     const float* cols[3] = {q->dx, q->dy, q->mean};
     for (int c = 0; c < 3; ++c)
         if (cols[c]) LCB_CUDA(cudaMemcpy2DAsync(D.ep + D.M + c, np * 4, cols[c], 4, 4, E, mem == LCB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, H->st));
@@ -704,7 +1135,7 @@ int lcb_deconv_set_params(void* handle, const lcb_deconv_params* q, int mem) {
     LCB_CUDA(cudaMemsetAsync(D.h_mu, 0, pp * 4, H->st)); LCB_CUDA(cudaMemsetAsync(D.h_nu, 0, pp * 4, H->st));
     LCB_CUDA(cudaMemsetAsync(D.c_mu, 0, 2 * DC_MMAX * 4, H->st)); LCB_CUDA(cudaMemsetAsync(D.c_nu, 0, 2 * DC_MMAX * 4, H->st));
     LCB_CUDA(cudaMemsetAsync(D.ep_mu, 0, E * np * 4, H->st)); LCB_CUDA(cudaMemsetAsync(D.ep_nu, 0, E * np * 4, H->st));
-    LCB_CUDA(cudaMemsetAsync(D.ctl, 0, 8 * 4, H->st));
+    LCB_CUDA(cudaMemsetAsync(D.ctl, 0, 7 * 4, H->st));
     D.free_h = q->free_h; D.free_mean = q->free_mean; D.free_a = q->free_a; D.free_c = q->free_c; D.free_d = q->free_d;
     LCB_CUDA(cudaStreamSynchronize(H->st));
     return LCB_OK;
@@ -716,6 +1147,7 @@ int lcb_deconv_set_reg(void* handle, const lcb_deconv_reg* r, int mem) {
     DeconvDev& D = H->D;
     const size_t pp = (size_t)D.nu * D.nu;
     D.lam_scales = r->lam_scales; D.lam_hf = r->lam_hf; D.lam_pos = r->lam_pos;
+    D.lam_pts = r->lam_pts; D.lam_fu = r->lam_fu; D.pts_all_epochs = r->pts_all_epochs; D.fu_relative = r->fu_relative;
     int rc;
     if (r->W) {
         if (!D.W) { if ((rc = dalloc(H, (void**)&D.W, (size_t)D.J * pp * 4, false))) return rc; }
@@ -733,20 +1165,16 @@ int lcb_deconv_set_reg(void* handle, const lcb_deconv_reg* r, int mem) {
 int lcb_deconv_step_local(void* handle, int want_model) {
     DeconvHandle* H = (DeconvHandle*)handle;
     LCB_REQUIRE(H, "lcb_deconv_step_local: NULL handle");
-    DeconvDev& D = H->D;
-    { LcbProfScope ps("k_deconv_epoch", H->st); k_deconv_epoch<<<D.E, DC_THREADS, H->smem_epoch, H->st>>>(D, want_model); }
-    LCB_CUDA(cudaGetLastError());
-    const int tot = D.nu * D.nu + 2 * D.M + 2;
-    { LcbProfScope ps("k_deconv_reduce", H->st); k_deconv_reduce<<<(tot + 255) / 256, 256, 0, H->st>>>(D, 0); }
-    LCB_CUDA(cudaGetLastError());
-    return LCB_OK;
+    int rc;
+    if ((rc = launch_epoch(H, want_model ? 1 : 0))) return rc;
+    return launch_reduce(H, 0, 0);
 }
 
 // device pointer and length of the buffer to all-reduce (sum) across ranks between the two halves
 int lcb_deconv_reduce_buffer(void* handle, float** ptr, int* count) {
     DeconvHandle* H = (DeconvHandle*)handle;
     LCB_REQUIRE(H && ptr && count, "lcb_deconv_reduce_buffer: NULL argument");
-    *ptr = H->D.red; *count = H->D.nu * H->D.nu + 2 * H->D.M + 2;
+    *ptr = H->D.red; *count = H->D.tot;
     return LCB_OK;
 }
 
@@ -754,12 +1182,12 @@ int lcb_deconv_reduce_buffer(void* handle, float** ptr, int* count) {
 int lcb_deconv_step_update(void* handle, int it, int n_iter, float lr, int schedule) {
     DeconvHandle* H = (DeconvHandle*)handle;
     LCB_REQUIRE(H, "lcb_deconv_step_update: NULL handle");
-    { LcbProfScope ps("k_deconv_update", H->st);
-      k_deconv_update<<<DU_CTAS, DU_THREADS, 0, H->st>>>(H->D, it, n_iter, lr, schedule, nullptr, nullptr, nullptr); }
-    LCB_CUDA(cudaGetLastError());
-    return LCB_OK;
+    return launch_update(H, it, n_iter, lr, schedule, 0, nullptr, nullptr, nullptr);
 }
 
+// n_iter AdaBelief iterations enqueued back to back, no host synchronisation inside the loop.  With a connected
+// communicator (lcb_deconv_comm_*) every rank calls this with the same options: the gradient of the shared
+// parameters is exchanged inside k_deconv_reduce / k_deconv_update over peer memory.
 int lcb_deconv_run(void* handle, const lcb_fit_opts* opt, float* loss_hist, int mem) {
     DeconvHandle* H = (DeconvHandle*)handle;
     LCB_REQUIRE(H && opt && opt->n_iter >= 0, "lcb_deconv_run: bad arguments");
@@ -770,16 +1198,18 @@ int lcb_deconv_run(void* handle, const lcb_fit_opts* opt, float* loss_hist, int 
         H->loss_cap = opt->n_iter;
     }
     for (int it = 0; it < opt->n_iter; ++it) {
-        if ((rc = lcb_deconv_step_local(H, 0))) return rc;
-        if ((rc = lcb_deconv_step_update(H, it, opt->n_iter, opt->lr, opt->schedule))) return rc;
+        const int seq = next_seq(H);
+        if ((rc = launch_epoch(H, 0)) || (rc = launch_reduce(H, 0, seq)) ||
+            (rc = launch_update(H, it, opt->n_iter, opt->lr, opt->schedule, seq, nullptr, nullptr, nullptr))) return rc;
     }
     // flush the pending per-epoch update so that get() sees the final parameters
-    if (opt->n_iter > 0) { if ((rc = lcb_deconv_step_local(H, 0))) return rc; LCB_CUDA(cudaMemsetAsync(D.ctl + 4, 0, 4, H->st)); }
+    if (opt->n_iter > 0) { if ((rc = launch_epoch(H, 0))) return rc; LCB_CUDA(cudaMemsetAsync(D.ctl + 4, 0, 4, H->st)); }
+    if ((rc = check_peers(H))) return rc;
     if (loss_hist) { if ((rc = get(H, loss_hist, D.loss_hist, opt->n_iter, mem))) return rc; }
     return LCB_OK;
 }
 
-// loss and gradient at the current parameters (no update)
+// loss and gradient at the current parameters (no update); collective when a communicator is connected
 int lcb_deconv_loss_grad(void* handle, lcb_deconv_grad* g, int mem) {
     DeconvHandle* H = (DeconvHandle*)handle;
     LCB_REQUIRE(H && g, "lcb_deconv_loss_grad: NULL argument");
@@ -787,16 +1217,18 @@ int lcb_deconv_loss_grad(void* handle, lcb_deconv_grad* g, int mem) {
     const size_t E = D.E, pp = (size_t)D.nu * D.nu, np = D.M + 3;
     int rc;
     LCB_CUDA(cudaMemsetAsync(D.ctl + 4, 0, 4, H->st));
-    if ((rc = lcb_deconv_step_local(H, 0))) return rc;
-    float *gh = nullptr, *gcx = nullptr, *ls = nullptr;
-    if ((rc = dalloc(H, (void**)&gh, pp * 4, true)) || (rc = dalloc(H, (void**)&gcx, 2 * DC_MMAX * 4, true)) ||
-        (rc = dalloc(H, (void**)&ls, 4, true))) return rc;
-    k_deconv_update<<<DU_CTAS, DU_THREADS, 0, H->st>>>(D, -1, 1, 0.f, 0, gh, gcx, ls);
-    LCB_CUDA(cudaGetLastError());
-    if ((rc = get(H, g->loss, ls, 1, mem)) || (rc = get(H, g->h, gh, pp, mem)) || (rc = get(H, g->c_x, gcx, D.M, mem)) ||
-        (rc = get(H, g->c_y, gcx + D.M, D.M, mem))) return rc;
+    const int seq = next_seq(H);
+    if ((rc = launch_epoch(H, 0)) || (rc = launch_reduce(H, 0, seq)) ||
+        (rc = launch_update(H, -1, 1, 0.f, 0, seq, H->gh, H->gcx, H->ls))) return rc;
+    if (D.lam_fu != 0.f && D.M > 0) {
+        k_deconv_fu_apply<<<(D.E * D.M + 255) / 256, 256, 0, H->st>>>(D);
+        LCB_CUDA(cudaGetLastError());
+    }
+    if ((rc = check_peers(H))) return rc;
+    if ((rc = get(H, g->loss, H->ls, 1, mem)) || (rc = get(H, g->h, H->gh, pp, mem)) || (rc = get(H, g->c_x, H->gcx, D.M, mem)) ||
+        (rc = get(H, g->c_y, H->gcx + D.M, D.M, mem))) return rc;
     const cudaMemcpyKind kd = mem == LCB_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
-    if (g->a) LCB_CUDA(cudaMemcpy2DAsync(g->a, D.M * 4, D.ep_g, np * 4, D.M * 4, E, kd, H->st));
+    if (g->a && D.M > 0) LCB_CUDA(cudaMemcpy2DAsync(g->a, D.M * 4, D.ep_g, np * 4, D.M * 4, E, kd, H->st));
     float* cols[3] = {g->dx, g->dy, g->mean};
     for (int c = 0; c < 3; ++c)
         if (cols[c]) LCB_CUDA(cudaMemcpy2DAsync(cols[c], 4, D.ep_g + D.M + c, np * 4, 4, E, kd, H->st));
@@ -812,20 +1244,17 @@ int lcb_deconv_get(void* handle, lcb_deconv_params* q, float* model, float* loss
     int rc;
     if (model || loss) {
         LCB_CUDA(cudaMemsetAsync(D.ctl + 4, 0, 4, H->st));
-        if ((rc = lcb_deconv_step_local(H, 1))) return rc;
-        if (loss) {
-            float* ls = nullptr;
-            if ((rc = dalloc(H, (void**)&ls, 4, true))) return rc;
-            k_deconv_update<<<DU_CTAS, DU_THREADS, 0, H->st>>>(D, -1, 1, 0.f, 0, nullptr, nullptr, ls);
-            LCB_CUDA(cudaGetLastError());
-            if ((rc = get(H, loss, ls, 1, mem))) return rc;
+        if ((rc = launch_epoch(H, 1))) return rc;
+        if (loss) {               // LOCAL loss (chi2 of the local epochs + replicated terms): no exchange here
+            if ((rc = launch_reduce(H, 0, 0)) || (rc = launch_update(H, -1, 1, 0.f, 0, 0, nullptr, nullptr, H->ls))) return rc;
+            if ((rc = get(H, loss, H->ls, 1, mem))) return rc;
         }
         if ((rc = get(H, model, D.model, E * nn, mem))) return rc;
     }
     if ((rc = get(H, (float*)q->h, D.h, pp, mem)) || (rc = get(H, (float*)q->c_x, D.c, D.M, mem)) ||
         (rc = get(H, (float*)q->c_y, D.c + D.M, D.M, mem)) || (rc = get(H, (float*)q->alpha, D.alpha, E, mem))) return rc;
     const cudaMemcpyKind kd = mem == LCB_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
-    if (q->a) LCB_CUDA(cudaMemcpy2DAsync((float*)q->a, D.M * 4, D.ep, np * 4, D.M * 4, E, kd, H->st));
+    if (q->a && D.M > 0) LCB_CUDA(cudaMemcpy2DAsync((float*)q->a, D.M * 4, D.ep, np * 4, D.M * 4, E, kd, H->st));
     float* cols[3] = {(float*)q->dx, (float*)q->dy, (float*)q->mean};
     for (int c = 0; c < 3; ++c)
         if (cols[c]) LCB_CUDA(cudaMemcpy2DAsync(cols[c], 4, D.ep + D.M + c, np * 4, 4, E, kd, H->st));
@@ -844,12 +1273,8 @@ int lcb_deconv_noise_weights(void* handle, int stage, float* W_out, int mem) {
     const size_t pp = (size_t)D.nu * D.nu;
     int rc;
     if (stage == 0) {
-        k_deconv_epoch<<<D.E, DC_THREADS, H->smem_epoch, H->st>>>(D, 2);
-        LCB_CUDA(cudaGetLastError());
-        const int tot = D.nu * D.nu + 2 * D.M + 2;
-        k_deconv_reduce<<<(tot + 255) / 256, 256, 0, H->st>>>(D, 1);
-        LCB_CUDA(cudaGetLastError());
-        return LCB_OK;
+        if ((rc = launch_epoch(H, 2))) return rc;
+        return launch_reduce(H, 1, 0);
     }
     std::vector<float> tab;
     lcb_build_noise_table(D.nu, D.J, tab);

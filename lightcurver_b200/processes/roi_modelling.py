@@ -5,8 +5,11 @@
 ``joint_deconvolution`` is the single entry point a patched ``do_modelling_of_roi`` calls for its
 stage 2 (and ``do_one_star_forward_modelling`` for the shared-background variants).  Epochs can be
 sharded over ranks: every rank passes ITS epochs plus a ``torch.distributed`` process group, and one
-all-reduce of nu^2 + 2M + 2 floats per iteration keeps the shared parameters (h, c_x, c_y)
-bit-identical on all ranks.
+all-reduce of nu^2 + 6M + 2 floats per iteration keeps the shared parameters (h, c_x, c_y)
+bit-identical on all ranks.  The exchange runs inside the kernels over NVLink peer
+memory (``comm='p2p'``: CUDA IPC mapped receive buffers, push + flag, summed in rank order; the process
+group is only used once to exchange the 64-byte IPC handles) or as one NCCL all-reduce between the two
+halves of an iteration (``comm='nccl'``).
 """
 import ctypes as C
 
@@ -34,11 +37,57 @@ class JointDeconvolution:
         self.handle = C.c_void_p()
         _lib.check(_lib.lib.lcb_deconv_create(C.byref(prob), _lib.MEM_HOST, None, C.byref(self.handle)), 'lcb_deconv_create')
         self.J = int(_lib.lib.lcb_starlet_scales(self.nu))
+        self.group, self.world, self.rank, self.comm = None, 1, 0, None
+        self.E_total, self.e0 = self.E, 0
 
     def close(self):
         if getattr(self, 'handle', None):
+            if self.comm == 'p2p':              # nobody may unmap a receive buffer a peer can still write to
+                import torch
+                import torch.distributed as dist
+                torch.cuda.synchronize()
+                dist.barrier(group=self.group)
             _lib.lib.lcb_deconv_destroy(self.handle)
             self.handle = None
+
+    # ---- multi-GPU ---------------------------------------------------------------------------
+    def connect(self, group, comm='p2p'):
+        """Epochs are sharded over the ranks of ``group`` (contiguous blocks in rank order, this rank holds its own).
+        comm='p2p': in-kernel all-reduce over NVLink peer memory; 'nccl': one NCCL all-reduce per iteration."""
+        import torch
+        import torch.distributed as dist
+        if comm not in ('p2p', 'nccl'):
+            raise ValueError("comm must be 'p2p' or 'nccl'")
+        self.group, self.world, self.rank = group, dist.get_world_size(group), dist.get_rank(group)
+        counts = [None] * self.world
+        dist.all_gather_object(counts, self.E, group=group)
+        self.E_total, self.e0 = int(sum(counts)), int(sum(counts[:self.rank]))
+        _lib.check(_lib.lib.lcb_deconv_set_global(self.handle, self.E_total, self.e0, None, _lib.MEM_HOST), 'lcb_deconv_set_global')
+        self.comm = comm if self.world > 1 else None
+        if self.comm == 'p2p':
+            mine = C.create_string_buffer(64)
+            _lib.check(_lib.lib.lcb_deconv_comm_init(self.handle, self.rank, self.world, mine), 'lcb_deconv_comm_init')
+            hs = [None] * self.world
+            dist.all_gather_object(hs, mine.raw, group=group)
+            allh = C.create_string_buffer(b''.join(hs), 64 * self.world)
+            _lib.check(_lib.lib.lcb_deconv_comm_connect(self.handle, allh), 'lcb_deconv_comm_connect')
+            torch.cuda.synchronize()
+            dist.barrier(group=group)
+        return self
+
+    def set_cluster(self, ctas_per_epoch=0):
+        """CTAs per epoch of the per-epoch kernel (0 = automatic)."""
+        _lib.check(_lib.lib.lcb_deconv_set_cluster(self.handle, int(ctas_per_epoch)), 'lcb_deconv_set_cluster')
+
+    def _global_mean_flux(self, a):
+        """Per-source mean flux over ALL epochs (the shift of the flux-uniformity sums; identical on all ranks)."""
+        sm_ = np.asarray(a, np.float64).reshape(self.E, self.M).sum(0) if self.M else np.zeros(0)
+        if self.world > 1:
+            import torch.distributed as dist
+            parts = [None] * self.world
+            dist.all_gather_object(parts, sm_, group=self.group)
+            sm_ = np.sum(parts, axis=0)
+        return (sm_ / max(self.E_total, 1)).astype(np.float32)
 
     __del__ = close
 
@@ -60,15 +109,21 @@ class JointDeconvolution:
         q = _lib.DeconvParams(*[ptr(keep[nm]) for nm in ('h', 'mean', 'a', 'c_x', 'c_y', 'dx', 'dy', 'alpha')],
                               int(free_h), int(free_mean), int(free_a), int(free_c), int(free_d))
         _lib.check(_lib.lib.lcb_deconv_set_params(self.handle, C.byref(q), _lib.MEM_HOST), 'lcb_deconv_set_params')
+        if keep['a'] is not None and self.M:
+            sh = np.ascontiguousarray(self._global_mean_flux(keep['a']))
+            _lib.check(_lib.lib.lcb_deconv_set_global(self.handle, self.E_total, self.e0, ptr(sh), _lib.MEM_HOST), 'lcb_deconv_set_global')
 
-    def set_reg(self, lam_scales=0.0, lam_hf=0.0, lam_pos=0.0, W=None, prior=None):
+    def set_reg(self, lam_scales=0.0, lam_hf=0.0, lam_pos=0.0, W=None, prior=None, lam_pts=0.0, lam_fu=0.0,
+                conventions: Conventions = DEFAULT):
         W = None if W is None else np.ascontiguousarray(W, dtype=np.float32)
         if W is not None and W.size != self.J * self.nu * self.nu:
             raise ValueError(f"W must be ({self.J},{self.nu},{self.nu})")
         pr = [None] * 4
         if prior is not None:
             pr = [np.ascontiguousarray(np.broadcast_to(np.asarray(p, dtype=np.float32), (self.M,))) for p in prior]
-        r = _lib.DeconvReg(float(lam_scales), float(lam_hf), float(lam_pos), ptr(W), *[ptr(p) for p in pr])
+        r = _lib.DeconvReg(float(lam_scales), float(lam_hf), float(lam_pos), ptr(W), *[ptr(p) for p in pr],
+                           float(lam_pts), float(lam_fu), int(conventions.pts_source_all_epochs),
+                           int(conventions.flux_uniformity_relative))
         _lib.check(_lib.lib.lcb_deconv_set_reg(self.handle, C.byref(r), _lib.MEM_HOST), 'lcb_deconv_set_reg')
 
     # ---- evaluation -------------------------------------------------------------------------
@@ -87,7 +142,10 @@ class JointDeconvolution:
         return out
 
     def loss_grad(self):
-        """Loss and gradient at the current parameters (single rank)."""
+        """Loss and gradient at the current parameters.  With comm='p2p' this is a collective call: the loss is the
+        global one, h / c gradients are all-reduced, per-epoch gradients are those of the local epochs."""
+        if self.comm == 'nccl':
+            raise NotImplementedError("loss_grad over sharded epochs needs comm='p2p'")
         E, M, nu = self.E, self.M, self.nu
         g = dict(loss=np.empty(1, np.float32), h=np.empty(nu * nu, np.float32), mean=np.empty(E, np.float32),
                  a=np.empty(E * M, np.float32), c_x=np.empty(M, np.float32), c_y=np.empty(M, np.float32),
@@ -111,6 +169,7 @@ class JointDeconvolution:
         return torch.as_tensor(ext, device='cuda')
 
     def noise_weights(self, group=None):
+        group = self.group if group is None else group
         _lib.check(_lib.lib.lcb_deconv_noise_weights(self.handle, 0, None, _lib.MEM_HOST), 'lcb_deconv_noise_weights')
         if group is not None:
             import torch.distributed as dist
@@ -121,6 +180,12 @@ class JointDeconvolution:
 
     def run(self, n_iter, lr=1e-4, schedule=False, group=None):
         """n_iter AdaBelief iterations; returns the loss history (global loss when sharded)."""
+        if group is not None and self.group is None:
+            self.connect(group, 'nccl')          # historical signature: a bare group means the NCCL route
+        if self.comm != 'nccl':                   # single rank, or in-kernel exchange over peer memory
+            group = None
+        else:
+            group = self.group
         if group is None:
             hist = np.empty(n_iter, np.float32)
             opts = _lib.FitOpts(int(n_iter), float(lr), int(bool(schedule)))
@@ -171,24 +236,56 @@ def flux_sigma_multi(kwargs, data, noisemap, psf, subsampling_factor, convention
         return (1.0 / np.sqrt(H)).reshape(-1)
 
 
+def _kwargs_of(fin):
+    return {
+        'kwargs_analytic': {'c_x': fin['c_x'].astype(np.float64), 'c_y': fin['c_y'].astype(np.float64),
+                            'dx': fin['dx'].astype(np.float64), 'dy': fin['dy'].astype(np.float64),
+                            'a': fin['a'].astype(np.float64), 'alpha': fin['alpha'].astype(np.float64)},
+        'kwargs_background': {'h': fin['h'].astype(np.float64), 'mean': fin['mean'].astype(np.float64)},
+        'kwargs_sersic': {},
+    }
+
+
+def _finish(jd, hist, Wused, data, weight, psf, cv):
+    """Products of a finished fit (roi_modelling.py:335-401): kwargs_final, model, sigma of the fluxes, deconvolved epoch 0."""
+    fin = jd.get()
+    kw = _kwargs_of(fin)
+    n, k, nu, M = jd.n, jd.k, jd.nu, jd.M
+    with np.errstate(divide='ignore', invalid='ignore'):
+        noisemap = np.where(weight > 0, 1.0 / np.sqrt(weight), np.inf)
+    sig = flux_sigma_multi(kw, data, noisemap, psf, k, cv)
+    # model.getDeconvolved(kwargs, 0): high-resolution scene of epoch 0 and its background only
+    from .star_photometry import point_source_image
+    h2 = fin['h'].reshape(nu, nu).astype(np.float64)
+    deconv = h2.copy()
+    for m in range(M):
+        deconv += point_source_image(fin['a'][m], fin['c_x'][m] + fin['dx'][0], fin['c_y'][m] + fin['dy'][0], n, k, cv)
+    return dict(kwargs_final=kw, model=fin['model'], loss_history=hist, W=Wused, flux_sigma=sig,
+                deconvolved_epoch0=(deconv, h2))
+
+
 def joint_deconvolution(data, weight, psf, subsampling_factor, xs, ys, initial_a, n_iter=2000, lr=1e-4,
                         schedule=False, alpha=None, h0=None, dx0=None, dy0=None, mean0=None,
                         free_h=True, free_mean=True, free_a=True, free_c=True, free_d=True,
                         regularization_strength_scales=1.0, regularization_strength_hf=1.0,
                         regularization_strength_positivity=100.0, W='propagate', prior=None,
-                        conventions: Conventions = DEFAULT, group=None):
+                        regularization_strength_pts_source=0.0, regularization_strength_flux_uniformity=0.0,
+                        conventions: Conventions = DEFAULT, group=None, comm='p2p'):
     """Stage 2 of roi_modelling.py:285-335 (defaults: lr 1e-4, no schedule/clip, strengths 1/1/100).
 
     data, weight (E,n,n) LOCAL epochs; psf (E,P,P); xs, ys (M,) point-source positions in data pixels
     from the stamp centre (roi_modelling.py:207-210); initial_a (E*M,) epoch-major or (E,M).
     ``prior`` = (mu_x, sigma_x, mu_y, sigma_y) Gaussian astrometric prior (roi_modelling.py:240-244).
     ``W`` = 'propagate' (SLIT weights from the model), an array (J,nu,nu), or None (== 1).
+    ``group``: torch.distributed process group over which the epochs are sharded (``comm`` = 'p2p' | 'nccl').
     Returns dict(kwargs_final, model, loss_history, W, flux_sigma, deconvolved_epoch0).
     """
     cv = conventions
-    E, n = data.shape[0], data.shape[-1]
+    E = data.shape[0]
     M = len(np.atleast_1d(xs))
     jd = JointDeconvolution(data, weight, psf, subsampling_factor, M, cv)
+    if group is not None:
+        jd.connect(group, comm)
     nu = jd.nu
     a0 = np.asarray(initial_a, dtype=np.float32).reshape(E, M)
     jd.set_params(h=np.zeros(nu * nu) if h0 is None else h0, mean=np.zeros(E) if mean0 is None else mean0, a=a0,
@@ -199,81 +296,126 @@ def joint_deconvolution(data, weight, psf, subsampling_factor, xs, ys, initial_a
     if propagate and W != 'propagate':
         raise ValueError("W must be 'propagate', an array (J,nu,nu) or None")
     Wused = None if propagate else W
-    jd.set_reg(regularization_strength_scales, regularization_strength_hf, regularization_strength_positivity,
-               W=Wused, prior=prior)
-    if propagate and free_h and (regularization_strength_scales or regularization_strength_hf):
-        Wused = jd.noise_weights(group)               # installs the weights in the handle
-    hist = jd.run(n_iter, lr=lr, schedule=schedule, group=group)
-    fin = jd.get()
-    kw = {
-        'kwargs_analytic': {'c_x': fin['c_x'].astype(np.float64), 'c_y': fin['c_y'].astype(np.float64),
-                            'dx': fin['dx'].astype(np.float64), 'dy': fin['dy'].astype(np.float64),
-                            'a': fin['a'].astype(np.float64), 'alpha': fin['alpha'].astype(np.float64)},
-        'kwargs_background': {'h': fin['h'].astype(np.float64), 'mean': fin['mean'].astype(np.float64)},
-        'kwargs_sersic': {},
-    }
+    reg = dict(lam_scales=regularization_strength_scales, lam_hf=regularization_strength_hf,
+               lam_pos=regularization_strength_positivity, prior=prior, lam_pts=regularization_strength_pts_source,
+               lam_fu=regularization_strength_flux_uniformity, conventions=cv)
+    jd.set_reg(W=Wused, **reg)
+    need_W = (free_h and (regularization_strength_scales or regularization_strength_hf)) or regularization_strength_pts_source
+    if propagate and need_W:
+        Wused = jd.noise_weights()                    # installs the weights in the handle
+    hist = jd.run(n_iter, lr=lr, schedule=schedule)
+    out = _finish(jd, hist, Wused, data, weight, psf, cv)
     jd.close()
-    with np.errstate(divide='ignore', invalid='ignore'):
-        noisemap = np.where(weight > 0, 1.0 / np.sqrt(weight), np.inf)
-    sig = flux_sigma_multi(kw, data, noisemap, psf, subsampling_factor, cv)
-    # model.getDeconvolved(kwargs, 0): high-resolution scene of epoch 0 and its background only
-    from .star_photometry import point_source_image
-    h2 = fin['h'].reshape(nu, nu).astype(np.float64)
-    deconv = h2.copy()
-    for m in range(M):
-        deconv += point_source_image(fin['a'][m], fin['c_x'][m] + fin['dx'][0], fin['c_y'][m] + fin['dy'][0], n, jd.k, cv)
-    return dict(kwargs_final=kw, model=fin['model'], loss_history=hist, W=Wused, flux_sigma=sig,
-                deconvolved_epoch0=(deconv, h2))
+    return out
+
+
+def lbfgsb_translations_and_fluxes(jd, maxiter, a_lower=0.0):
+    """Stage 1 of do_modelling_of_roi (roi_modelling.py:260-281): scipy L-BFGS-B over {dx, dy, a} with everything else
+    fixed, exactly the reference's structure (host optimiser, device loss and gradient: ``lcb_deconv_loss_grad``).
+    With sharded epochs every rank runs the same optimiser on the concatenated vector (local blocks are
+    all-gathered), so the trajectories are identical on all ranks.  Returns (loss history, scipy result)."""
+    from scipy.optimize import minimize
+    E, M = jd.E, jd.M
+    cur = jd.get(want_model=False)
+    x_loc = np.concatenate([cur['dx'], cur['dy'], cur['a']]).astype(np.float64)
+    nloc = x_loc.size
+    if jd.world > 1:
+        import torch.distributed as dist
+        sizes = [None] * jd.world
+        dist.all_gather_object(sizes, nloc, group=jd.group)
+        offs = np.concatenate([[0], np.cumsum(sizes)])
+
+        def gather(v):
+            parts = [None] * jd.world
+            dist.all_gather_object(parts, np.asarray(v, np.float64), group=jd.group)
+            return np.concatenate(parts)
+        x0 = gather(x_loc)
+        lo = int(offs[jd.rank])
+    else:
+        gather = lambda v: np.asarray(v, np.float64)
+        x0, lo = x_loc, 0
+    hist, last = [], {}
+
+    def fun(x):
+        xl = x[lo:lo + nloc]
+        jd.set_params(dx=xl[:E], dy=xl[E:2 * E], a=xl[2 * E:], free_h=False, free_mean=False, free_a=True, free_c=False, free_d=True)
+        g = jd.loss_grad()
+        last['L'] = g['loss']
+        return g['loss'], gather(np.concatenate([g['dx'], g['dy'], g['a']]))
+
+    # bounds (kwargs_down / kwargs_up of setup_model [R]): fluxes are non-negative, shifts stay inside the stamp
+    bl = [(-jd.n / 2.0, jd.n / 2.0)] * (2 * E) + [(a_lower, None)] * (E * M)
+    if jd.world > 1:
+        bparts = [None] * jd.world
+        import torch.distributed as dist
+        dist.all_gather_object(bparts, bl, group=jd.group)
+        bl = [b for part in bparts for b in part]
+    res = minimize(fun, x0, jac=True, method='L-BFGS-B', bounds=bl,
+                   options={'maxiter': int(maxiter), 'maxfun': 20 * int(maxiter) + 20},
+                   callback=lambda xk: hist.append(last['L']))
+    xl = res.x[lo:lo + nloc]
+    jd.set_params(dx=xl[:E], dy=xl[E:2 * E], a=xl[2 * E:], free_h=False, free_mean=False, free_a=True, free_c=False, free_d=True)
+    return np.asarray(hist), res
 
 
 def model_roi_arrays(data, noisemap, psf, subsampling_factor, xs, ys, initial_a, angles_to_north=None,
                      fix_point_source_astrometry=False, starting_background=None, further_optimize_background=True,
                      roi_model_regularization=None, roi_deconv_translations_iters=300, roi_deconv_all_iters=2000,
-                     conventions: Conventions = DEFAULT, group=None):
+                     conventions: Conventions = DEFAULT, group=None, comm='p2p'):
     """The two optimisation stages of do_modelling_of_roi (roi_modelling.py:213-335) on arrays that are already
     loaded and scaled (:154-170): data, noisemap (E,n,n); psf (E,P,P); xs, ys the point-source guesses in data
     pixels from the stamp centre (:207-210); initial_a (E*M,) (:211-212).
 
-    Stage 1 (:260-281) frees {dx, dy, a}.  The reference runs scipy L-BFGS-B there (with a flux-uniformity penalty,
-    a 'next' row); this engine runs the same free set with scheduled AdaBelief (lr 1e-2 of the data scale) for
-    ``roi_deconv_translations_iters`` iterations -- same role (register the epochs, get the fluxes in range), not
-    the same trajectory.  Stage 2 (:285-335) is the reference's: SLIT noise weights, free {h (if
-    further_optimize_background), mean, a, c_x, c_y, dx, dy}, AdaBelief lr 1e-4, no schedule, strengths from
-    ``roi_model_regularization``; ``fix_point_source_astrometry``: True fixes c, a float is the sigma (data pixels) of
-    a Gaussian prior around the initial positions (:225-244).
+    Stage 1 (:260-281): scipy L-BFGS-B, ``roi_deconv_translations_iters`` iterations over {dx, dy, a}, chi2 +
+    flux-uniformity penalty ``regularization_scatter_fluxes_pre_optim`` (default 10.0, :273) + the astrometric prior
+    (constant in this stage).  Stage 2 (:285-335): SLIT noise weights, free {h (if further_optimize_background),
+    mean, a, c_x, c_y, dx, dy}, AdaBelief lr 1e-4, no schedule; strengths from ``roi_model_regularization`` with the
+    reference's defaults (scales 1, hf 1, positivity 100, pts_source 0.01, flux scatter 10.0; :305-312).
+    ``fix_point_source_astrometry``: True fixes c, a float is the sigma (data pixels) of a Gaussian prior around the
+    initial positions (:225-244).  One device handle serves both stages (the stamps are uploaded once).
     """
     reg = roi_model_regularization or {}
-    E, n = data.shape[0], data.shape[-1]
+    cv = conventions
+    E = data.shape[0]
     k = int(subsampling_factor)
     xs, ys = np.atleast_1d(np.asarray(xs, float)), np.atleast_1d(np.asarray(ys, float))
+    M = len(xs)
     with np.errstate(divide='ignore', invalid='ignore'):
         weight = np.where(np.isfinite(noisemap) & (noisemap > 0), 1.0 / np.asarray(noisemap, np.float64) ** 2, 0.0).astype(np.float32)
     d32 = np.nan_to_num(np.asarray(data, np.float32))
-    alpha = np.zeros(E) if angles_to_north is None else np.asarray(angles_to_north, float) - float(angles_to_north[0])
+    alpha = np.zeros(E) if angles_to_north is None else np.asarray(angles_to_north, float)
     h0 = None if starting_background is None else np.asarray(starting_background, np.float32).reshape(-1)
     fix_c = isinstance(fix_point_source_astrometry, bool) and fix_point_source_astrometry
     prior = None
     if isinstance(fix_point_source_astrometry, float):
-        sg = np.full(len(xs), fix_point_source_astrometry)
+        sg = np.full(M, fix_point_source_astrometry)
         prior = (xs, sg, ys, sg)
+    jd = JointDeconvolution(d32, weight, psf, k, M, cv)
+    if group is not None:
+        jd.connect(group, comm)
+    nu = jd.nu
+    jd.set_params(h=np.zeros(nu * nu) if h0 is None else h0, mean=np.zeros(E), a=np.asarray(initial_a, np.float32).reshape(E, M),
+                  c_x=xs, c_y=ys, dx=np.zeros(E), dy=np.zeros(E), alpha=alpha,
+                  free_h=False, free_mean=False, free_a=True, free_c=False, free_d=True)
     # stage 1: translations and fluxes
-    s1 = joint_deconvolution(d32, weight, psf, k, xs, ys, initial_a, n_iter=int(roi_deconv_translations_iters), lr=1e-2,
-                             schedule=True, alpha=alpha, h0=h0, free_h=False, free_mean=False, free_a=True, free_c=False,
-                             free_d=True, regularization_strength_scales=0.0, regularization_strength_hf=0.0,
-                             regularization_strength_positivity=0.0, W=None, prior=None, conventions=conventions, group=group)
-    k1 = s1['kwargs_final']
+    jd.set_reg(0.0, 0.0, 0.0, W=None, prior=prior, lam_fu=reg.get('regularization_scatter_fluxes_pre_optim', 10.0), conventions=cv)
+    hist1, res1 = lbfgsb_translations_and_fluxes(jd, roi_deconv_translations_iters)
+    kwargs_partial1 = _kwargs_of(jd.get(want_model=False))
     # stage 2: everything
-    s2 = joint_deconvolution(d32, weight, psf, k, k1['kwargs_analytic']['c_x'], k1['kwargs_analytic']['c_y'],
-                             k1['kwargs_analytic']['a'], n_iter=int(roi_deconv_all_iters), lr=1e-4, schedule=False,
-                             alpha=alpha, h0=k1['kwargs_background']['h'], dx0=k1['kwargs_analytic']['dx'],
-                             dy0=k1['kwargs_analytic']['dy'], free_h=bool(further_optimize_background), free_mean=True,
-                             free_a=True, free_c=not fix_c, free_d=True,
-                             regularization_strength_scales=reg.get('regularization_strength_scales', 1.0),
-                             regularization_strength_hf=reg.get('regularization_strength_hf', 1.0),
-                             regularization_strength_positivity=reg.get('regularization_strength_positivity', 100.0),
-                             W='propagate', prior=prior, conventions=conventions, group=group)
-    s2['stage1'] = s1
-    return s2
+    free_h = bool(further_optimize_background)
+    lam_s, lam_hf = reg.get('regularization_strength_scales', 1.0), reg.get('regularization_strength_hf', 1.0)
+    lam_pts = reg.get('regularization_strength_pts_source', 0.01)
+    jd.set_params(free_h=free_h, free_mean=True, free_a=True, free_c=not fix_c, free_d=True)
+    jd.set_reg(lam_s, lam_hf, reg.get('regularization_strength_positivity', 100.0), W=None, prior=prior, lam_pts=lam_pts,
+               lam_fu=reg.get('regularization_scatter_fluxes_main_optim', 10.0), conventions=cv)
+    Wused = None
+    if (free_h and (lam_s or lam_hf)) or lam_pts:
+        Wused = jd.noise_weights()
+    hist = jd.run(int(roi_deconv_all_iters), lr=1e-4, schedule=False)
+    out = _finish(jd, hist, Wused, d32, weight, psf, cv)
+    jd.close()
+    out['stage1'] = dict(kwargs_final=kwargs_partial1, loss_history=hist1, nit=int(res1.nit), message=str(res1.message))
+    return out
 
 
 def get_fluxes_dataframe_from_model(result, data, noisemap, point_sources_names, model_scale, normalization_errors,

@@ -315,10 +315,37 @@ def deconv_model(h, mean, a, c_x, c_y, dx, dy, alpha, psf, n, k, cv: Conventions
     return downsample(conv, k, cv) + mean[:, None, None]
 
 
+def pts_source_l1(a, c_x, c_y, dx, dy, alpha, n, k, P, W, lam_pts, cv: Conventions = DEFAULT, first_epoch_is_local=True):
+    """regularization_strength_pts_source (roi_modelling.py:311; Millon et al. 2024) [R, low confidence]: weighted L1 of
+    the FIRST starlet scale of the point-source channel p_e = sum_m a_em g(. ; centres), weights W[0] (1 if W is None),
+    summed over the epochs (cv.pts_source_all_epochs) or taken on the first epoch only."""
+    p = deconv_highres(None, a, c_x, c_y, dx, dy, alpha, n, k, P, cv, with_h=False)
+    c1 = _atrous_axis(_atrous_axis(p, 0, -1), 0, -2)
+    al0 = (p - c1).abs()
+    if W is not None:
+        al0 = al0 * W[0]
+    per = al0.sum((-1, -2))
+    if cv.pts_source_all_epochs:
+        return lam_pts * per.sum()
+    return lam_pts * per[0] if first_epoch_is_local else 0.0 * per[0]
+
+
+def flux_uniformity(a, lam_fu, cv: Conventions = DEFAULT):
+    """regularization_strength_flux_uniformity (roi_modelling.py:275-276, 312) [R, low confidence]: scatter of the fluxes
+    of every source over the epochs, a (E,M): lam * sum_m std_e(a_em) (population std) [/ |mean_e(a_em)|]."""
+    mean = a.mean(0)
+    var = ((a - mean) ** 2).mean(0)
+    sd = torch.sqrt(torch.where(var > 0, var, torch.ones_like(var))) * (var > 0).to(a.dtype)
+    if cv.flux_uniformity_relative:
+        sd = sd / mean.abs()
+    return lam_fu * sd.sum()
+
+
 def deconv_loss(h, mean, a, c_x, c_y, dx, dy, alpha, psf, data, weight, W, n, k,
                 lam_scales=0.0, lam_hf=0.0, lam_pos=0.0, prior=None,
-                cv: Conventions = DEFAULT, with_h=True, direct=False, per_epoch=False):
-    """A.7: chi2 + starlet-L1(h) + positivity(h) + Gaussian prior on (c_x, c_y).
+                cv: Conventions = DEFAULT, with_h=True, direct=False, per_epoch=False,
+                lam_pts=0.0, lam_fu=0.0):
+    """A.7: chi2 + starlet-L1(h) + positivity(h) + Gaussian prior on (c_x, c_y) + pts-source L1 + flux uniformity.
 
     prior = (mu_x, sig_x, mu_y, sig_y) or None.  per_epoch=True returns the (E,) chi2 terms only.
     """
@@ -336,6 +363,10 @@ def deconv_loss(h, mean, a, c_x, c_y, dx, dy, alpha, psf, data, weight, W, n, k,
     if prior is not None:
         mux, sgx, muy, sgy = prior
         L = L + 0.5 * (((c_x - mux) / sgx) ** 2).sum() + 0.5 * (((c_y - muy) / sgy) ** 2).sum()
+    if lam_pts != 0.0:
+        L = L + pts_source_l1(a, c_x, c_y, dx, dy, alpha, n, k, psf.shape[-1], W, lam_pts, cv)
+    if lam_fu != 0.0:
+        L = L + flux_uniformity(a, lam_fu, cv)
     return L
 
 
@@ -571,7 +602,7 @@ def deconv_loss_grad(params, fixed, psf, data, weight, W, n, k, reg, cv: Convent
                     allp['dx'], allp['dy'], allp['alpha'], _const(psf, dtype), _const(data, dtype),
                     _const(weight, dtype), None if W is None else _const(W, dtype), n, k,
                     reg.get('lam_scales', 0.0), reg.get('lam_hf', 0.0), reg.get('lam_pos', 0.0),
-                    prior, cv)
+                    prior, cv, lam_pts=reg.get('lam_pts', 0.0), lam_fu=reg.get('lam_fu', 0.0))
     names = list(leaves)
     g = torch.autograd.grad(L, [leaves[kk] for kk in names])
     return float(L.detach()), {kk: t.numpy() for kk, t in zip(names, g)}
@@ -594,7 +625,8 @@ def fit_deconv(params, fixed, psf, data, weight, W, n, k, reg, n_iter, lr=1e-4, 
         p = {**consts, **leaves}
         L = deconv_loss(p['h'].reshape(n * k, n * k), p['mean'], p['a'], p['c_x'], p['c_y'], p['dx'],
                         p['dy'], p['alpha'], psf, data, weight, W, n, k, reg.get('lam_scales', 0.0),
-                        reg.get('lam_hf', 0.0), reg.get('lam_pos', 0.0), prior, cv)
+                        reg.get('lam_hf', 0.0), reg.get('lam_pos', 0.0), prior, cv,
+                        lam_pts=reg.get('lam_pts', 0.0), lam_fu=reg.get('lam_fu', 0.0))
         g = torch.autograd.grad(L, [leaves[kk] for kk in names])
         hist[it] = float(L.detach())
         opt.step(list(g))

@@ -1,0 +1,57 @@
+"""Timing sweep of the joint-deconvolution iteration (cfg4 shapes): local epochs x CTAs per epoch.
+
+    python tools/deconv_sweep.py [--iters 100]
+
+Prints, per (E_local, cluster size), ms per iteration and the per-kernel split from lcb_profile_*.
+E_local = 200/100/50/25 are the shards of cfg4 on 1/2/4/8 GPUs."""
+import argparse
+import sys
+from pathlib import Path
+
+import numpy as np
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--iters', type=int, default=100)
+    ap.add_argument('--epochs', default='200,100,50,25')
+    ap.add_argument('--cs', default='0,1,2,4,8')
+    ap.add_argument('--alpha', type=float, default=0.0)
+    args = ap.parse_args()
+    import torch
+    from lightcurver_b200 import _lib, synthetic
+    from lightcurver_b200.processes.roi_modelling import JointDeconvolution
+    n, k, M, npsf = 64, 2, 4, 32
+    nu = n * k
+    t = synthetic.make_deconv_epochs(200, n, k, M=M, n_psf=npsf)
+    rng = np.random.default_rng(0)
+    for E in [int(x) for x in args.epochs.split(',')]:
+        data = rng.standard_normal((E, n, n)).astype(np.float32)
+        weight = np.ones((E, n, n), np.float32)
+        for cs in [int(x) for x in args.cs.split(',')]:
+            jd = JointDeconvolution(data, weight, t['psf'][:E], k, M)
+            jd.set_cluster(cs)
+            jd.set_params(h=np.zeros(nu * nu), mean=np.zeros(E), a=t['a'][:E] / 3000.0, c_x=t['c_x'], c_y=t['c_y'],
+                          dx=t['dx'][:E], dy=t['dy'][:E], alpha=np.full(E, args.alpha))
+            jd.set_reg(1.0, 1.0, 100.0, lam_pts=0.01, lam_fu=10.0)
+            jd.run(10, lr=1e-4)
+            torch.cuda.synchronize()
+            _lib.profile_enable(True)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            jd.run(args.iters, lr=1e-4)
+            e1.record()
+            torch.cuda.synchronize()
+            prof = _lib.profile_summary()
+            _lib.profile_enable(False)
+            ms = e0.elapsed_time(e1) / args.iters
+            used = int(_lib.lib.lcb_deconv_get_cluster(jd.handle))
+            parts = ' '.join(f"{kn.replace('k_deconv_', '')}={v['ms'] / max(v['launches'], 1):.3f}" for kn, v in sorted(prof.items()))
+            print(f"E={E:4d} cs={cs} (used {used}) {ms:.3f} ms/it  {1e3 / ms:7.1f} it/s   [{parts}]", flush=True)
+            jd.close()
+
+
+if __name__ == '__main__':
+    main()
