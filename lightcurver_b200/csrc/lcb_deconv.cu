@@ -88,24 +88,141 @@ struct DeconvDev {
 __host__ __device__ inline int red_loss(const DeconvDev& D) { return D.nu * D.nu + 2 * D.M; }
 __host__ __device__ inline int red_flux(const DeconvDev& D) { return D.nu * D.nu + 2 * D.M + 2; }
 
-// shared-memory layout of k_deconv_epoch (floats)
-struct DcLayout { int oS, oF, pst, oR, oG, oPar, oRed, oCp, oPts, oEx, total; };
-__host__ __device__ inline DcLayout dc_layout(int n, int k, int NA) {
+// ---------------------------------------------------------------- shared-memory layout of k_deconv_epoch (floats)
+// Planes read by the convolutions are stored with ZEROS between consecutive rows: row r keeps its n values at
+// HL + r*ld + sh .. + n, the ld - n floats up to the next row are zero and serve as the right halo of row r and the
+// left halo of row r+1 (ld - n >= the reach of the kernel on either side).  No bounds predicate is needed along a
+// row, every window / tap load is an aligned LDS.128 (sh makes the first tap column a multiple of 4; ld = 4 mod 8
+// spreads the rows of a warp over all banks), and out-of-range ROWS are simply skipped.
+struct DcLayout {
+    int NAp, NA8, ld, HL, shF, shR, FR, RR, pst;
+    int oS, oF, oR, oG, oPar, oRed, oCp, oPts, oEx, zero_end, total;
+};
+__host__ __device__ inline DcLayout dc_layout(int n, int k, int NA, int A0, int CS) {
     const int kk = k * k;
     DcLayout L;
+    L.NA8 = NA & ~7;
+    L.NAp = (NA + 7) & ~7;
+    const int A1 = A0 + NA - 1;
+    int reach = (-A0 > A1 ? -A0 : A1);
+    if (reach < 0) reach = 0;
+    int ld = n + reach;
+    while ((ld & 7) != 4) ++ld;
+    L.ld = ld;
+    L.HL = (reach + 3) & ~3;
+    L.shF = ((-A0) % 4 + 4) % 4;                       // forward: first tap column X0 + A0 (+ sh) is a multiple of 4
+    L.shR = ((A0 + 7) % 4 + 4) % 4;                    // adjoint: first window column X0 - A0 - 7 (+ sh)
+    const int rpc = (n + CS - 1) / CS;
+    int rows = rpc + NA - 1;
+    if (rows > n) rows = n;
+    L.FR = rows; L.RR = rows;
+    L.pst = L.FR * ld;
     int o = 0;
-    L.oS = o; o += (kk * NA * NA + 3) & ~3;
-    L.pst = n * (n + 1) + 8;                     // plane stride: +8 banks between polyphase planes
-    L.oF = o; o += kk * L.pst;
-    L.oR = o; o += n * (n + 1);
-    L.oG = o; o += 4 * DC_MMAX * 16;             // gx | d gx | gy | d gy, [M][16] each
+    L.oS = o; o += kk * NA * L.NAp;
+    L.oF = o; o += L.HL + kk * L.pst + 32;
+    L.oR = o; o += L.HL + L.RR * ld + 32;
+    L.zero_end = o;                                    // [oF, zero_end) is cleared at kernel start
+    L.oG = o; o += 4 * DC_MMAX * 16;                   // gx | d gx | gy | d gy, [M][16] each
     L.oPar = o; o += 16;
     L.oRed = o; o += 16;
-    L.oCp = o; o += DC_CSMAX * 32;               // per-CTA partial sums, gathered in rank 0
-    L.oPts = o; o += DC_MMAX * 32;               // pts-source partial sums per warp
-    L.oEx = o; o += 2 * DC_MMAX * 4 * DC_EXT;    // [axis][m][g, Bg, g', Bg'][G+4]
+    L.oCp = o; o += DC_CSMAX * 32;                     // per-CTA partial sums, gathered in rank 0
+    L.oPts = o; o += DC_MMAX * 32;                     // pts-source partial sums per warp
+    L.oEx = o; o += 2 * DC_MMAX * 4 * DC_EXT;          // [axis][m][g, Bg, g', Bg'][G+4]
     L.total = o;
     return L;
+}
+
+// bands of CTA c of a cluster: own data rows [Y0,Y1), rows of f it stores [flo,fhi), rows of r it stores [rlo,rhi)
+struct DcBand { int Y0, Y1, flo, fhi, rlo, rhi; };
+__device__ __forceinline__ DcBand dc_band(int c, int n, int rpc, int A0, int NA) {
+    DcBand b;
+    b.Y0 = min(n, c * rpc); b.Y1 = min(n, b.Y0 + rpc);
+    b.flo = min(b.Y0, max(0, b.Y0 + A0)); b.fhi = max(b.Y1, min(n, b.Y1 + A0 + NA - 1));
+    b.rlo = min(b.Y0, max(0, b.Y0 - A0 - NA + 1)); b.rhi = max(b.Y1, min(n, b.Y1 - A0));
+    return b;
+}
+
+__device__ __forceinline__ void ld8(float (&d)[8], const float* __restrict__ p) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+}
+
+// acc[x] += sum_{j<8} tap[j] * w[j + x],  w = lo | hi (16 consecutive floats)
+template <bool REV>
+__device__ __forceinline__ void blk8(float (&acc)[DC_XB], const float (&tap)[8], const float (&lo)[8], const float (&hi)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float tv = REV ? tap[7 - j] : tap[j];
+#pragma unroll
+        for (int x = 0; x < DC_XB; ++x) {
+            const int i = j + x;
+            acc[x] = fmaf(tv, (i < 8) ? lo[i] : hi[i - 8], acc[x]);
+        }
+    }
+}
+
+// forward, one kernel row: acc[x] += sum_t sr[t] * fr[t + x]   (fr = window start: column X0 + A0 of the f row; 16 B aligned)
+__device__ __forceinline__ void corr_line(const float* __restrict__ fr, const float* __restrict__ sr, int NA, int NA8, float (&acc)[DC_XB]) {
+    float lo[8], hi[8], tap[8];
+    if (NA8 > 0) ld8(lo, fr);
+    for (int t0 = 0; t0 < NA8; t0 += 8) {
+        ld8(hi, fr + t0 + 8);
+        ld8(tap, sr + t0);
+        blk8<false>(acc, tap, lo, hi);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) lo[i] = hi[i];
+    }
+    const int R = NA - NA8;                            // tail taps: aligned loads, only the real taps are multiplied
+    if (R > 0) {
+        ld8(lo, fr + NA8); ld8(tap, sr + NA8);
+        if (R > 1) ld8(hi, fr + NA8 + 8);
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            if (j < R) {
+#pragma unroll
+                for (int x = 0; x < DC_XB; ++x) {
+                    const int i = j + x;
+                    acc[x] = fmaf(tap[j], (i < 8) ? lo[i] : hi[i - 8], acc[x]);
+                }
+            }
+        }
+    }
+}
+
+// adjoint, one kernel row: acc[x] += sum_t sr[t] * rr[(NA8 - 1 - t) + x]   (rr = column X0 - A0 - (NA8 - 1) of the r row).
+// Blocks run over t0 = NA8-8 ... 0 with the taps used in reverse, so the window slides forwards; rr + 8*b is 16 B aligned.
+template <bool SQ>
+__device__ __forceinline__ void conv_line_T(const float* __restrict__ rr, const float* __restrict__ sr, int NA, int NA8, float (&acc)[DC_XB]) {
+    float lo[8], hi[8], tap[8];
+    // tail taps t = NA8 + j first: column offset (NA8 - 1 - t) + x = x - 1 - j, i.e. w[7 - j + x] of the window rr[-8 .. 7]
+    const int R = NA - NA8;
+    if (R > 0) {
+        ld8(lo, rr - 8); ld8(hi, rr); ld8(tap, sr + NA8);
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            if (j < R) {
+                const float sv = SQ ? tap[j] * tap[j] : tap[j];
+#pragma unroll
+                for (int x = 0; x < DC_XB; ++x) {
+                    const int i = 7 - j + x;
+                    acc[x] = fmaf(sv, (i < 8) ? lo[i] : hi[i - 8], acc[x]);
+                }
+            }
+        }
+    }
+    // block b (t0 = NA8 - 8 - 8 b): j = t0 + 7 - t, column offset = (NA8 - 1 - t0 - 7) + j + x = 8 b + j + x
+    if (NA8 > 0) ld8(lo, rr);
+    for (int b = 0; b * 8 < NA8; ++b) {
+        ld8(hi, rr + 8 * b + 8);
+        ld8(tap, sr + NA8 - 8 - 8 * b);
+        if (SQ) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) tap[i] *= tap[i];
+        }
+        blk8<true>(acc, tap, lo, hi);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) lo[i] = hi[i];
+    }
 }
 
 // ---------------------------------------------------------------- setup: polyphase box-folded PSF
@@ -143,74 +260,6 @@ __device__ __forceinline__ float h_at(const float* __restrict__ h, int nu, int v
     return (v >= 0 && v < nu && u >= 0 && u < nu) ? __ldg(h + v * nu + u) : 0.f;
 }
 
-// correlation of one phase plane with rows [ia0, ia1) of its NA x NA kernel for XB consecutive outputs of row Y:
-//   acc[x] += sum_{av,au} Sph[av-A0][au-A0] * src[Y+av][X0+x+au]      (zero outside [0,n))
-__device__ __forceinline__ void corr_row(const float* __restrict__ src, int ld, int n, const float* __restrict__ Sph,
-                                         int NA, int A0, int ia0, int ia1, int Y, int X0, float (&acc)[DC_XB]) {
-    for (int ia = ia0; ia < ia1; ++ia) {
-        const int row = Y + A0 + ia;
-        if (row < 0 || row >= n) continue;
-        const float* fr = src + row * ld;
-        const float* sr = Sph + ia * NA;
-        float buf[2 * DC_XB];
-#pragma unroll
-        for (int i = 0; i < DC_XB; ++i) {
-            const int c = X0 + A0 + i;
-            buf[i] = (c >= 0 && c < n) ? fr[c] : 0.f;
-        }
-        for (int t0 = 0; t0 < NA; t0 += DC_XB) {
-#pragma unroll
-            for (int i = 0; i < DC_XB; ++i) {
-                const int c = X0 + A0 + t0 + DC_XB + i;
-                buf[DC_XB + i] = (c >= 0 && c < n) ? fr[c] : 0.f;
-            }
-#pragma unroll
-            for (int t = 0; t < DC_XB; ++t) {
-                const float sv = (t0 + t < NA) ? sr[t0 + t] : 0.f;
-#pragma unroll
-                for (int x = 0; x < DC_XB; ++x) acc[x] = fmaf(sv, buf[t + x], acc[x]);
-            }
-#pragma unroll
-            for (int i = 0; i < DC_XB; ++i) buf[i] = buf[DC_XB + i];
-        }
-    }
-}
-
-// transposed: acc[x] += sum_{av,au} Sph[av-A0][au-A0] * r[Y'-av][X0+x-au]
-__device__ __forceinline__ void conv_row_T(const float* __restrict__ src, int ld, int n, const float* __restrict__ Sph,
-                                           int NA, int A0, int Y, int X0, float (&acc)[DC_XB], bool squared) {
-    for (int ia = 0; ia < NA; ++ia) {
-        const int row = Y - A0 - ia;
-        if (row < 0 || row >= n) continue;
-        const float* fr = src + row * ld;
-        const float* sr = Sph + ia * NA;
-        // index c = X0 + x - A0 - t ; walk t upwards => c downwards.  window base b(t) = X0 - A0 - t
-        float buf[2 * DC_XB];              // buf[j] holds fr[base_hi - j] with base_hi = X0 - A0 + DC_XB - 1
-#pragma unroll
-        for (int i = 0; i < DC_XB; ++i) {
-            const int c = X0 - A0 + DC_XB - 1 - i;
-            buf[i] = (c >= 0 && c < n) ? fr[c] : 0.f;
-        }
-        for (int t0 = 0; t0 < NA; t0 += DC_XB) {
-#pragma unroll
-            for (int i = 0; i < DC_XB; ++i) {
-                const int c = X0 - A0 - 1 - t0 - i;
-                buf[DC_XB + i] = (c >= 0 && c < n) ? fr[c] : 0.f;
-            }
-#pragma unroll
-            for (int t = 0; t < DC_XB; ++t) {
-                float sv = (t0 + t < NA) ? sr[t0 + t] : 0.f;
-                if (squared) sv *= sv;
-                // output x needs fr[X0 + x - A0 - t0 - t] = buf[DC_XB - 1 - x + t]
-#pragma unroll
-                for (int x = 0; x < DC_XB; ++x) acc[x] = fmaf(sv, buf[DC_XB - 1 - x + t], acc[x]);
-            }
-#pragma unroll
-            for (int i = 0; i < DC_XB; ++i) buf[i] = buf[DC_XB + i];
-        }
-    }
-}
-
 __device__ __forceinline__ float block_sum(float v, float* red, int tid) {
     v = warp_sum(v);
     __syncthreads();
@@ -223,6 +272,7 @@ __device__ __forceinline__ float block_sum(float v, float* red, int tid) {
 
 // ---------------------------------------------------------------- per-epoch kernel (cluster of CS CTAs)
 // flags: 1 = write the model image; 2 = propagate the weights instead of the residuals (noise weights).
+template <int K>
 __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int flags, int CS) {
     cg::cluster_group cl = cg::this_cluster();
     const int want_model = flags & 1;
@@ -231,14 +281,14 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
     const int tid = threadIdx.x;
     const int crank = (int)(blockIdx.x % CS);     // == cl.block_rank() for cluster dims (CS,1,1)
     const int e = blockIdx.x / CS;
-    const int n = D.n, k = D.k, nu = D.nu, M = D.M, NA = D.NA, A0 = D.A0, G = D.G;
-    const int ldf = n + 1, ldr = n + 1, kk = k * k;
+    constexpr int k = K, kk = K * K;
+    const int n = D.n, nu = D.nu, M = D.M, NA = D.NA, A0 = D.A0, G = D.G;
     const int np = M + 3;
-    const DcLayout L = dc_layout(n, k, NA);
-    const int pst = L.pst;
-    float* Ssm = sm + L.oS;                       // [kk][NA][NA]
-    float* fpl = sm + L.oF;                       // [kk][pst]   f, later dL/df (own band)
-    float* rsm = sm + L.oR;                       // [n][ldr]
+    const DcLayout L = dc_layout(n, k, NA, A0, CS);
+    const int pst = L.pst, ld = L.ld, NAp = L.NAp, NA8 = L.NA8;
+    float* Ssm = sm + L.oS;                       // [kk][NA][NAp] zero padded
+    float* fpl = sm + L.oF + L.HL + L.shF;        // [kk][FR rows][ld]: f, later dL/df (own band); row r of the band at (r - flo) * ld
+    float* rsm = sm + L.oR + L.HL + L.shR;        // [RR rows][ld]: row Y at (Y - rlo) * ld
     float* gx = sm + L.oG;                        // [M][16] and derivative [M][16]
     float* gy = gx + 2 * DC_MMAX * 16;
     float* par = sm + L.oPar;                     // [np]
@@ -248,10 +298,13 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
     float* ext = sm + L.oEx;                      // [axis][m][4][DC_EXT]
     __shared__ int iwin[2 * DC_MMAX];
     __shared__ const float* remf[DC_CSMAX];       // fpl of every CTA of the cluster (DSMEM)
+    __shared__ float* remr[DC_CSMAX];             // rsm of every CTA of the cluster
+    __shared__ int remflo[DC_CSMAX], remrlo[DC_CSMAX], remrhi[DC_CSMAX];
 
     // band of data rows (and of rows of every polyphase plane) owned by this CTA
     const int rpc = (n + CS - 1) / CS;
-    const int Y0 = min(n, crank * rpc), Y1 = min(n, Y0 + rpc), own = Y1 - Y0;
+    const DcBand bd = dc_band(crank, n, rpc, A0, NA);
+    const int Y0 = bd.Y0, Y1 = bd.Y1, own = Y1 - Y0, flo = bd.flo, fhi = bd.fhi, rlo = bd.rlo;
 
     // ---- pending AdaBelief update of the per-epoch parameters (gradients of the previous iteration):
     //      every CTA of the cluster computes it (identical arithmetic), rank 0 stores it after the first cluster barrier
@@ -275,9 +328,21 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
         }
         par[tid] = p;
     }
-    if (tid < CS) remf[tid] = (CS > 1) ? (const float*)cl.map_shared_rank(fpl, tid) : fpl;
-    for (int i = tid; i < kk * NA * NA; i += DC_THREADS) Ssm[i] = __ldg(D.S + (size_t)e * kk * NA * NA + i);
-    __syncthreads();
+    if (tid < CS) {
+        const DcBand bc = dc_band(tid, n, rpc, A0, NA);
+        remf[tid] = (CS > 1) ? (const float*)cl.map_shared_rank(fpl, tid) : fpl;
+        remr[tid] = (CS > 1) ? (float*)cl.map_shared_rank(rsm, tid) : rsm;
+        remflo[tid] = bc.flo; remrlo[tid] = bc.rlo; remrhi[tid] = bc.rhi;
+    }
+    for (int i = tid; i < kk * NA * NAp; i += DC_THREADS) {
+        const int t = i % NAp, row = i / NAp;
+        Ssm[i] = (t < NA) ? __ldg(D.S + (size_t)e * kk * NA * NA + (size_t)row * NA + t) : 0.f;
+    }
+    {   // zero the planes (the gaps between rows are the halos)
+        float4* z = reinterpret_cast<float4*>(sm + L.oF);
+        for (int i = tid; i < (L.zero_end - L.oF) / 4; i += DC_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();                              // (remote writes of r only start after cluster barrier #0 below)
 
     const int j0 = (D.P - 1) / 2;
     const float delta = 0.5f * (float)(D.P - 1) - (float)j0;
@@ -302,11 +367,11 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
         dst[DC_MMAX * 16 + m * 16 + t] = x * D.cv.invs2 * g;     // d g / d pc
         if (t == 0) iwin[axis * DC_MMAX + m] = ic - G / 2 + 1;
     }
-    // ---- f = warp(h) in polyphase layout, only the plane rows the forward band reads
-    const int flo = max(0, Y0 + A0), fhi = min(n, Y1 + A0 + NA - 1);
+    // ---- f = warp(h) + point sources in polyphase layout: every CTA builds the rows of its OWN band, then copies the
+    //      other rows its forward pass reads from the CTAs that own them (distributed shared memory)
     if (!noise && own > 0) {
-        for (int i = tid; i < (fhi - flo) * k * nu; i += DC_THREADS) {
-            const int v = flo * k + i / nu, u = i % nu;
+        for (int i = tid; i < own * k * nu; i += DC_THREADS) {
+            const int v = Y0 * k + i / nu, u = i % nu;
             float val = 0.f;
             if (D.h != nullptr) {
                 float qu, qv;
@@ -317,7 +382,7 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
                 val = (1.f - fv) * ((1.f - fu) * h_at(D.h, nu, v0, u0) + fu * h_at(D.h, nu, v0, u0 + 1)) +
                       fv * ((1.f - fu) * h_at(D.h, nu, v0 + 1, u0) + fu * h_at(D.h, nu, v0 + 1, u0 + 1));
             }
-            fpl[((v % k) * k + (u % k)) * pst + (v / k) * ldf + u / k] = val;
+            fpl[((v % k) * k + (u % k)) * pst + (v / k - flo) * ld + u / k] = val;
         }
     }
     __syncthreads();
@@ -326,11 +391,28 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
             for (int i = tid; i < G * G; i += DC_THREADS) {
                 const int tv = i / G, tu = i % G;
                 const int v = iwin[DC_MMAX + m] + tv, u = iwin[m] + tu;
-                if (v >= flo * k && v < fhi * k && u >= 0 && u < nu)
-                    fpl[((v % k) * k + (u % k)) * pst + (v / k) * ldf + u / k] += par[m] * gy[m * 16 + tv] * gx[m * 16 + tu];
+                if (v >= Y0 * k && v < Y1 * k && u >= 0 && u < nu)
+                    fpl[((v % k) * k + (u % k)) * pst + (v / k - flo) * ld + u / k] += par[m] * gy[m * 16 + tv] * gx[m * 16 + tu];
             }
             __syncthreads();
         }
+    }
+    if (CS > 1) {
+        cl.sync();                                // #0: planes cleared and own bands of f complete in every CTA
+        if (!noise && own > 0) {
+            const int nq = n / 4 + 1;             // float4 per row (the tail reads into the zero gap / shift slack)
+            const int nrow = (fhi - flo) - own;
+            for (int i = tid; i < kk * nrow * nq; i += DC_THREADS) {
+                const int q = i % nq, rr = (i / nq) % nrow, ph = i / (nq * nrow);
+                const int Yp = (rr < Y0 - flo) ? flo + rr : Y1 + (rr - (Y0 - flo));
+                const int oc = min(Yp / rpc, CS - 1);
+                // both rows start at a 16-byte aligned address minus the same shift; copy whole aligned quads
+                const float* src = remf[oc] - L.shF + ph * pst + (Yp - remflo[oc]) * ld;
+                float* dst = fpl - L.shF + ph * pst + (Yp - flo) * ld;
+                reinterpret_cast<float4*>(dst)[q] = reinterpret_cast<const float4*>(src)[q];
+            }
+        }
+        __syncthreads();
     }
 
     // ---- forward: m = mean + 1/k^2 sum_ph corr(f_ph, S_ph);  r = w (m - d).  A task = XB outputs of one row for
@@ -341,28 +423,37 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
     const float* wgt = D.weight + (size_t)e * n * n;
     float loss = 0.f, gmean = 0.f;
     const int nxb = (n + DC_XB - 1) / DC_XB;
-    float* rdst[DC_CSMAX];
-#pragma unroll
-    for (int c = 0; c < DC_CSMAX; ++c) rdst[c] = (c < CS && CS > 1) ? (float*)cl.map_shared_rank(rsm, c) : rsm;
     if (noise) {
-        for (int i = tid; i < n * n; i += DC_THREADS) rsm[(i / n) * ldr + i % n] = __ldg(wgt + i);
+        for (int i = tid; i < n * n; i += DC_THREADS) {
+            const int Y = i / n;
+            if (Y >= rlo && Y < bd.rhi) rsm[(Y - rlo) * ld + i % n] = __ldg(wgt + i);
+        }
     } else {
         int SPLIT = 1;
         while (SPLIT < 4 && own * nxb * SPLIT < DC_THREADS) SPLIT *= 2;
         const int ias = (NA + SPLIT - 1) / SPLIT;
         const int ntask = own * nxb * SPLIT, ntask_pad = (ntask + 31) & ~31;
         for (int task = tid; task < ntask_pad; task += DC_THREADS) {
-            const bool valid = task < ntask;
-            const int s = task & (SPLIT - 1), t2 = task / SPLIT;
+            const int lpg = 32 / SPLIT;           // lanes per slice group
+            const int s = (task & 31) / lpg, t2 = (task & ~31) / SPLIT + (task & 31) % lpg;
+            const bool valid = t2 < own * nxb;
             const int Y = Y0 + (valid ? t2 % own : 0), X0 = (valid ? t2 / own : 0) * DC_XB;
             float acc[DC_XB];
 #pragma unroll
             for (int x = 0; x < DC_XB; ++x) acc[x] = 0.f;
             if (valid) {
                 const int ia0 = s * ias, ia1 = min(NA, ia0 + ias);
-                for (int ph = 0; ph < kk; ++ph) corr_row(fpl + ph * pst, ldf, n, Ssm + ph * NA * NA, NA, A0, ia0, ia1, Y, X0, acc);
+                for (int ph = 0; ph < kk; ++ph) {
+                    const float* pl = fpl + ph * pst + X0 + A0;
+                    const float* Sph = Ssm + ph * NA * NAp;
+                    for (int ia = ia0; ia < ia1; ++ia) {
+                        const int row = Y + A0 + ia;
+                        if (row < 0 || row >= n) continue;
+                        corr_line(pl + (row - flo) * ld, Sph + ia * NAp, NA, NA8, acc);
+                    }
+                }
             }
-            for (int o = 1; o < SPLIT; o <<= 1) {
+            for (int o = 32 / SPLIT; o < 32; o <<= 1) {
 #pragma unroll
                 for (int x = 0; x < DC_XB; ++x) acc[x] += __shfl_xor_sync(0xffffffffu, acc[x], o);
             }
@@ -374,8 +465,8 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
                         const float mval = fmaf(dscale, acc[x], mean);
                         const float d = __ldg(dat + Y * n + X), w = __ldg(wgt + Y * n + X);
                         const float diff = mval - d, r = w * diff;
-#pragma unroll
-                        for (int c = 0; c < DC_CSMAX; ++c) if (c < CS) rdst[c][Y * ldr + X] = r;
+                        for (int c = 0; c < CS; ++c)
+                            if (Y >= remrlo[c] && Y < remrhi[c]) remr[c][(Y - remrlo[c]) * ld + X] = r;
                         loss = fmaf(r, diff, loss);
                         gmean += r;
                         if (want_model) D.model[(size_t)e * n * n + Y * n + X] = mval;
@@ -394,10 +485,17 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
         float acc[DC_XB];
 #pragma unroll
         for (int x = 0; x < DC_XB; ++x) acc[x] = 0.f;
-        conv_row_T(rsm, ldr, n, Ssm + ph * NA * NA, NA, A0, Y, X0, acc, noise);
+        const float* Sph = Ssm + ph * NA * NAp;
+        const float* rbase = rsm + X0 - A0 - (NA8 - 1);
+        for (int ia = 0; ia < NA; ++ia) {
+            const int row = Y - A0 - ia;
+            if (row < 0 || row >= n) continue;
+            if (noise) conv_line_T<true>(rbase + (row - rlo) * ld, Sph + ia * NAp, NA, NA8, acc);
+            else conv_line_T<false>(rbase + (row - rlo) * ld, Sph + ia * NAp, NA, NA8, acc);
+        }
 #pragma unroll
         for (int x = 0; x < DC_XB; ++x)
-            if (X0 + x < n) fpl[ph * pst + Y * ldf + X0 + x] = (noise ? dscale * dscale : dscale) * acc[x];
+            if (X0 + x < n) fpl[ph * pst + (Y - flo) * ld + X0 + x] = (noise ? dscale * dscale : dscale) * acc[x];
     }
     __syncthreads();
     const int vlo = Y0 * k, vhi = Y1 * k;         // rows of f whose dL/df lives in this CTA
@@ -412,7 +510,7 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
             const int tv = i / G, tu = i % G;
             const int v = iwin[DC_MMAX + m] + tv, u = iwin[m] + tu;
             if (v >= vlo && v < vhi && u >= 0 && u < nu) {
-                const float df = fpl[((v % k) * k + (u % k)) * pst + (v / k) * ldf + u / k];
+                const float df = fpl[((v % k) * k + (u % k)) * pst + (v / k - flo) * ld + u / k];
                 const float gyv = gy[m * 16 + tv], gxv = gx[m * 16 + tu];
                 ga = fmaf(df, gyv * gxv, ga);
                 gu = fmaf(df, gyv * gx[DC_MMAX * 16 + m * 16 + tu], gu);
@@ -440,7 +538,7 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
             const float h10 = h_at(D.h, nu, v0 + 1, u0), h11 = h_at(D.h, nu, v0 + 1, u0 + 1);
             const float dhu = (1.f - fv) * (h01 - h00) + fv * (h11 - h10);
             const float dhv = (1.f - fu) * (h10 - h00) + fu * (h11 - h01);
-            const float df = fpl[((v % k) * k + (u % k)) * pst + (v / k) * ldf + u / k];
+            const float df = fpl[((v % k) * k + (u % k)) * pst + (v / k - flo) * ld + u / k];
             // dq/ddx = -k (ca, -sa),  dq/ddy = -k (sa, ca)
             gwx = fmaf(df, -(float)k * (ca * dhu - sa * dhv), gwx);
             gwy = fmaf(df, -(float)k * (sa * dhu + ca * dhv), gwy);
@@ -558,33 +656,48 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
     //      dL/df of the other bands is read through distributed shared memory
     if (D.free_h || noise) {
         float* Gh = D.Gh + (size_t)e * nu * nu;
-        const int b_lo = (al == 0.f) ? 1 : 0, b_hi = (al == 0.f) ? 3 : 4;   // pure translation: 2 x 2 candidates
-        for (int i = tid; i < (vhi - vlo) * nu; i += DC_THREADS) {
-            const int qv_i = vlo + i / nu, qu_i = i % nu;
-            // forward image of q: p_c = R (q - ctr) + ctr + k d
-            const float ru = (float)qu_i - ctr, rv = (float)qv_i - ctr;
-            const float pcu = ca * ru - sa * rv + ctr + geo.tx, pcv = sa * ru + ca * rv + ctr + geo.ty;
-            const int pu0 = (int)floorf(pcu) - 1, pv0 = (int)floorf(pcv) - 1;
-            float acc = 0.f;
-            for (int b = b_lo; b < b_hi; ++b)
-                for (int a2 = b_lo; a2 < b_hi; ++a2) {
-                    const int pv = pv0 + b, pu = pu0 + a2;
-                    if (pv < 0 || pv >= nu || pu < 0 || pu >= nu) continue;
-                    float qu, qv;
-                    geo_src(geo, (float)pu, (float)pv, qu, qv);
-                    // bilinear weight of tap q for source position (qu,qv): taps are floor(q), floor(q)+1
-                    const float fu0 = floorf(qu), fv0 = floorf(qv);
-                    float wu = 0.f, wv = 0.f;
-                    if ((int)fu0 == qu_i) wu = 1.f - (qu - fu0); else if ((int)fu0 + 1 == qu_i) wu = qu - fu0;
-                    if ((int)fv0 == qv_i) wv = 1.f - (qv - fv0); else if ((int)fv0 + 1 == qv_i) wv = qv - fv0;
-                    if (noise) { wu *= wu; wv *= wv; }
-                    if (wu != 0.f && wv != 0.f) {
-                        const int Yp = pv / k;
-                        const float* src = remf[min(Yp / rpc, CS - 1)];
-                        acc = fmaf(wu * wv, src[((pv % k) * k + (pu % k)) * pst + Yp * ldf + pu / k], acc);
+        auto dfr = [&](int pv, int pu) -> float {
+            if (pv < 0 || pv >= nu || pu < 0 || pu >= nu) return 0.f;
+            const int Yp = pv / k, oc = min(Yp / rpc, CS - 1);
+            return remf[oc][((pv % k) * k + (pu % k)) * pst + (Yp - remflo[oc]) * ld + pu / k];
+        };
+        if (al == 0.f) {
+            // pure translation t = it + ft: f(p) = ft h[p-it-1] + (1-ft) h[p-it] per axis, so
+            // dL/dh[q] = ft dL/df[q+it+1] + (1-ft) dL/df[q+it] (separable, constant weights)
+            const float itx = floorf(geo.tx), ity = floorf(geo.ty);
+            float wx1 = geo.tx - itx, wy1 = geo.ty - ity, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+            if (noise) { wx0 *= wx0; wx1 *= wx1; wy0 *= wy0; wy1 *= wy1; }
+            const int iu = (int)itx, iv = (int)ity;
+            for (int i = tid; i < (vhi - vlo) * nu; i += DC_THREADS) {
+                const int qv_i = vlo + i / nu, qu_i = i % nu;
+                const int pv = qv_i + iv, pu = qu_i + iu;
+                const float acc = wy0 * (wx0 * dfr(pv, pu) + wx1 * dfr(pv, pu + 1)) + wy1 * (wx0 * dfr(pv + 1, pu) + wx1 * dfr(pv + 1, pu + 1));
+                Gh[i + vlo * nu] = noise ? acc : sc * acc;
+            }
+        } else {
+            for (int i = tid; i < (vhi - vlo) * nu; i += DC_THREADS) {
+                const int qv_i = vlo + i / nu, qu_i = i % nu;
+                // forward image of q: p_c = R (q - ctr) + ctr + k d
+                const float ru = (float)qu_i - ctr, rv = (float)qv_i - ctr;
+                const float pcu = ca * ru - sa * rv + ctr + geo.tx, pcv = sa * ru + ca * rv + ctr + geo.ty;
+                const int pu0 = (int)floorf(pcu) - 1, pv0 = (int)floorf(pcv) - 1;
+                float acc = 0.f;
+                for (int b = 0; b < 4; ++b)
+                    for (int a2 = 0; a2 < 4; ++a2) {
+                        const int pv = pv0 + b, pu = pu0 + a2;
+                        if (pv < 0 || pv >= nu || pu < 0 || pu >= nu) continue;
+                        float qu, qv;
+                        geo_src(geo, (float)pu, (float)pv, qu, qv);
+                        // bilinear weight of tap q for source position (qu,qv): taps are floor(q), floor(q)+1
+                        const float fu0 = floorf(qu), fv0 = floorf(qv);
+                        float wu = 0.f, wv = 0.f;
+                        if ((int)fu0 == qu_i) wu = 1.f - (qu - fu0); else if ((int)fu0 + 1 == qu_i) wu = qu - fu0;
+                        if ((int)fv0 == qv_i) wv = 1.f - (qv - fv0); else if ((int)fv0 + 1 == qv_i) wv = qv - fv0;
+                        if (noise) { wu *= wu; wv *= wv; }
+                        if (wu != 0.f && wv != 0.f) acc = fmaf(wu * wv, dfr(pv, pu), acc);
                     }
-                }
-            Gh[i + vlo * nu] = noise ? acc : sc * acc;
+                Gh[i + vlo * nu] = noise ? acc : sc * acc;
+            }
         }
     }
     cl.sync();                                    // #3: no CTA leaves while its shared memory may still be read
@@ -885,7 +998,7 @@ struct DeconvHandle {
     size_t smem_epoch;
     int CS;                              // CTAs per epoch (cluster size); 0 = not yet chosen
     int CS_user;
-    int n_sm;
+    int n_sm, max_smem;
     int seq;                             // sequence number of the in-kernel all-reduce
     float *gh, *gcx, *ls;                // evaluation outputs (lcb_deconv_loss_grad / _get)
 };
@@ -920,12 +1033,24 @@ static int choose_cluster(const DeconvHandle* H) {
     if (H->CS_user > 0) cs = H->CS_user;
     else while (cs < DC_CSMAX && D.E * cs < 4 * H->n_sm) cs *= 2;
     while (cs > 1 && (D.n + cs - 1) / cs < 4) cs /= 2;
+    while (cs < DC_CSMAX && (size_t)dc_layout(D.n, D.k, D.NA, D.A0, cs).total * 4 > (size_t)H->max_smem) cs *= 2;
     return cs;
 }
 
 static int launch_epoch(DeconvHandle* H, int flags) {
     DeconvDev& D = H->D;
-    if (H->CS == 0) H->CS = choose_cluster(H);
+    if (H->CS == 0) {
+        H->CS = choose_cluster(H);
+        H->smem_epoch = (size_t)dc_layout(D.n, D.k, D.NA, D.A0, H->CS).total * 4;
+        if (H->smem_epoch > (size_t)H->max_smem) {
+            lcb_set_error("deconvolution: n=%d k=%d P=%d needs %zu B of shared memory per CTA (> %d)", D.n, D.k, D.P, H->smem_epoch, H->max_smem);
+            H->CS = 0;
+            return LCB_ERR_ARG;
+        }
+        const void* fn = D.k == 1 ? (const void*)k_deconv_epoch<1> : D.k == 2 ? (const void*)k_deconv_epoch<2>
+                         : D.k == 3 ? (const void*)k_deconv_epoch<3> : (const void*)k_deconv_epoch<4>;
+        LCB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H->smem_epoch));
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(D.E * H->CS), 1, 1);
     cfg.blockDim = dim3(DC_THREADS, 1, 1);
@@ -936,7 +1061,12 @@ static int launch_epoch(DeconvHandle* H, int flags) {
     at[0].val.clusterDim.x = (unsigned)H->CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     LcbProfScope ps("k_deconv_epoch", H->st);
-    LCB_CUDA(cudaLaunchKernelEx(&cfg, k_deconv_epoch, D, flags, H->CS));
+    switch (D.k) {
+        case 1: LCB_CUDA(cudaLaunchKernelEx(&cfg, k_deconv_epoch<1>, D, flags, H->CS)); break;
+        case 2: LCB_CUDA(cudaLaunchKernelEx(&cfg, k_deconv_epoch<2>, D, flags, H->CS)); break;
+        case 3: LCB_CUDA(cudaLaunchKernelEx(&cfg, k_deconv_epoch<3>, D, flags, H->CS)); break;
+        default: LCB_CUDA(cudaLaunchKernelEx(&cfg, k_deconv_epoch<4>, D, flags, H->CS)); break;
+    }
     return LCB_OK;
 }
 
@@ -1028,17 +1158,16 @@ int lcb_deconv_create(const lcb_deconv_problem* p, int mem, void* stream, void**
     k_deconv_fold_psf<<<D.E, 256, 0, H->st>>>(psf_d, D.S, D.E, D.P, D.k, D.NA, D.A0);
     if (cudaGetLastError() != cudaSuccess) { lcb_set_error("k_deconv_fold_psf launch failed"); lcb_deconv_destroy(H); return LCB_ERR_CUDA; }
     D.free_h = D.free_mean = D.free_a = D.free_c = D.free_d = 1;
-    H->smem_epoch = (size_t)dc_layout(D.n, D.k, D.NA).total * 4;
-    int dev = 0, maxsm = 0;
+    H->smem_epoch = 0;
+    int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaDeviceGetAttribute(&H->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     cudaDeviceGetAttribute(&H->n_sm, cudaDevAttrMultiProcessorCount, dev);
-    if (H->smem_epoch > (size_t)maxsm) {
-        lcb_set_error("deconvolution: n=%d k=%d P=%d needs %zu B of shared memory per epoch (> %d)", D.n, D.k, D.P, H->smem_epoch, maxsm);
+    if ((size_t)dc_layout(D.n, D.k, D.NA, D.A0, DC_CSMAX).total * 4 > (size_t)H->max_smem) {
+        lcb_set_error("deconvolution: n=%d k=%d P=%d does not fit the shared memory of one SM even with %d CTAs per epoch", D.n, D.k, D.P, DC_CSMAX);
         lcb_deconv_destroy(H);
         return LCB_ERR_ARG;
     }
-    cudaFuncSetAttribute(k_deconv_epoch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H->smem_epoch);
     *handle = H;
     return LCB_OK;
 }

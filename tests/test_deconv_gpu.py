@@ -147,8 +147,9 @@ def test_model_roi_arrays_and_flux_table(cuda_device):
                            (p['a'] * 0.8).reshape(-1), fix_point_source_astrometry=1.0,
                            roi_deconv_translations_iters=150, roi_deconv_all_iters=400,
                            roi_model_regularization=dict(regularization_strength_positivity=0.0,
+                                                         regularization_strength_pts_source=0.0,
                                                          regularization_scatter_fluxes_pre_optim=0.0,
-                                                         regularization_scatter_fluxes_main_optim=0.0))   # the truth has variable fluxes
+                                                         regularization_scatter_fluxes_main_optim=0.0))   # unbiased: the truth has variable fluxes
     assert res['stage1']['nit'] >= 1 and len(res['stage1']['loss_history']) >= 1
     a = np.asarray(res['kwargs_final']['kwargs_analytic']['a']).reshape(E, M)
     err = np.abs(a - p['a']) / (res['flux_sigma'].reshape(E, M))
@@ -160,6 +161,10 @@ def test_model_roi_arrays_and_flux_table(cuda_device):
     assert (df['reduced_chi2'] < 2).all() and resid.shape == p['data'].shape
     np.testing.assert_allclose(df['A_flux'].values, a[:, 0] * 3.0, rtol=1e-6)
     assert (df['A_d_flux'].values >= 0.01 * df['A_flux'].values - 1e-9).all()
+    # the reference's default regularisation (pts_source 0.01, flux scatter 10 in both stages) runs and stays finite
+    res2 = model_roi_arrays(p['data'].astype(np.float64), sig, p['psf'], k, p['c_x'] + 0.2, p['c_y'] - 0.2,
+                            (p['a'] * 0.8).reshape(-1), roi_deconv_translations_iters=20, roi_deconv_all_iters=50)
+    assert np.isfinite(res2['loss_history']).all() and res2['loss_history'][-1] < res2['loss_history'][0]
 
 
 def test_deconv_scheduled_fit_with_flux_uniformity(cuda_device):
