@@ -199,10 +199,12 @@ def run_deconv(args):
     sig = np.sqrt(sky ** 2 + np.abs(data))
     scale = 1.0 / 3000.0
     jd = JointDeconvolution((data * scale).astype(np.float32), (1.0 / (sig * scale) ** 2).astype(np.float32), t['psf'][sl], k, M)
+    if group is not None:
+        jd.connect(group, args.comm)
     jd.set_params(h=np.zeros(nu * nu), mean=np.zeros(Eloc), a=t['a'][sl] * scale * rng.uniform(0.9, 1.1, (E, M))[sl],
                   c_x=t['c_x'], c_y=t['c_y'], dx=np.zeros(Eloc), dy=np.zeros(Eloc), alpha=np.zeros(Eloc))
-    jd.set_reg(1.0, 1.0, 100.0)
-    W = jd.noise_weights(group)
+    jd.set_reg(1.0, 1.0, 100.0, lam_pts=0.01, lam_fu=10.0)        # roi_modelling.py:305-312 defaults
+    W = jd.noise_weights()
     T = args.iters_per_step
     fp32_peak, _ = _lib.fp32_peak(8192)
 
@@ -212,7 +214,7 @@ def run_deconv(args):
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        jd.run(T, lr=1e-4, schedule=False, group=group)
+        jd.run(T, lr=1e-4, schedule=False)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -223,7 +225,7 @@ def run_deconv(args):
     hist = None
     for i in range(args.steps):
         ev[i][0].record()
-        hist = jd.run(T, lr=1e-4, schedule=False, group=group)
+        hist = jd.run(T, lr=1e-4, schedule=False)
         ev[i][1].record()
     barrier()
     prof = _lib.profile_summary()
@@ -244,7 +246,10 @@ def run_deconv(args):
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": {"workload": f"cfg4 joint deconvolution, {T} AdaBelief iterations per step, "
                                                             f"{E} epochs sharded {world}-way, P={P}, M={M}", "E": E, "n": n, "k": k, "M": M, "P": P,
-                                                "collective": "1 NCCL all-reduce of nu^2+2M+2 floats per iteration" if world > 1 else "none",
+                                                "collective": ("none" if world == 1 else "in-kernel all-reduce of nu^2+6M+2 floats per iteration over NVLink peer memory "
+                                                               "(push + flag, summed in rank order)" if args.comm == 'p2p' else
+                                                               "1 NCCL all-reduce of nu^2+6M+2 floats per iteration"),
+                                                "ctas_per_epoch": int(_lib.lib.lcb_deconv_get_cluster(jd.handle)),
                                                 "loss_first_last": [float(hist[0]), float(hist[-1])]},
                 "clocks": clocks, "gpu_launches": sum(v['launches'] for v in prof.values()), "kernels": prof,
                 "roofline": {"bound": "fp32", "kernel": "k_deconv_epoch", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
@@ -268,6 +273,7 @@ def main():
     ap.add_argument('--workload', default='psfphot', choices=['psfphot', 'deconv'],
                     help='psfphot (default, BASELINE cfg2) or deconv (cfg4: joint deconvolution iterations/s, epochs sharded over ranks)')
     ap.add_argument('--iters-per-step', type=int, default=50, help=argparse.SUPPRESS)
+    ap.add_argument('--comm', default='p2p', choices=['p2p', 'nccl'], help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)

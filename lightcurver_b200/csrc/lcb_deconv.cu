@@ -708,18 +708,30 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
 // receive buffer (plain stores into peer memory over NVLink); the last CTA to finish raises flag [seq&1][my rank] = seq
 // on every rank (fence - atomic - fence - flag, the threadFenceReduction pattern at system scope).
 __global__ void __launch_bounds__(256) k_deconv_reduce(DeconvDev D, int force_h, int seq) {
+    // 64 entries of red[] per CTA, 4 threads per entry: thread g sums the epochs e = g, g+4, ... (independent loads in
+    // flight), the four partial sums are combined in a fixed order -> deterministic
+    __shared__ float part[4][64];
     const int nu2 = D.nu * D.nu, M = D.M, np = D.M + 3;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int col = threadIdx.x & 63, grp = threadIdx.x >> 6;
+    const int i = blockIdx.x * 64 + col;
     const int iflux = red_flux(D);
     float s = 0.f;
     if (i < nu2) {
-        if (D.free_h || force_h) for (int e = 0; e < D.E; ++e) s += D.Gh[(size_t)e * nu2 + i];
+        if (D.free_h || force_h) {
+            const float* src = D.Gh + i;
+            int e = grp;
+            for (; e + 12 < D.E; e += 16) {
+                const float a0 = src[(size_t)e * nu2], a1 = src[(size_t)(e + 4) * nu2], a2 = src[(size_t)(e + 8) * nu2], a3 = src[(size_t)(e + 12) * nu2];
+                s += a0; s += a1; s += a2; s += a3;
+            }
+            for (; e < D.E; e += 4) s += src[(size_t)e * nu2];
+        }
     } else if (i < nu2 + 2 * M) {
-        for (int e = 0; e < D.E; ++e) s += D.gc[(size_t)e * 2 * M + (i - nu2)];
+        for (int e = grp; e < D.E; e += 4) s += D.gc[(size_t)e * 2 * M + (i - nu2)];
     } else if (i == nu2 + 2 * M) {
-        for (int e = 0; e < D.E; ++e) s += D.eloss[e];
+        for (int e = grp; e < D.E; e += 4) s += D.eloss[e];
     } else if (i == nu2 + 2 * M + 1) {
-        for (int e = 0; e < D.E; ++e)
+        for (int e = grp; e < D.E; e += 4)
             for (int p = 0; p < np; ++p) {
                 const bool is_free = (p < M) ? D.free_a : (p < M + 2) ? D.free_d : D.free_mean;
                 const float g = D.ep_g[(size_t)e * np + p];
@@ -729,17 +741,21 @@ __global__ void __launch_bounds__(256) k_deconv_reduce(DeconvDev D, int force_h,
         // flux statistics per source, shifted by the last known mean K_m: sum (a-K), sum (a-K)^2, sum g, sum g (a-K)
         const int q = (i - iflux) / M, m = (i - iflux) % M;
         const float K = D.fu[m];
-        for (int e = 0; e < D.E; ++e) {
+        for (int e = grp; e < D.E; e += 4) {
             const float a = D.ep[(size_t)e * np + m] - K, g = D.ep_g[(size_t)e * np + m];
             s += (q == 0) ? a : (q == 1) ? a * a : (q == 2) ? g : g * a;
         }
     }
+    part[grp][col] = s;
+    __syncthreads();
+    s = (part[0][col] + part[1][col]) + (part[2][col] + part[3][col]);
+    const bool writer = (grp == 0) && (i < D.tot);
     if (seq == 0) {
-        if (i < D.tot) D.red[i] = s;
+        if (writer) D.red[i] = s;
         return;
     }
     const int W = D.cm.world, par = seq & 1;
-    if (i < D.tot)
+    if (writer)
         for (int r = 0; r < W; ++r) D.cm.slots[r][((size_t)par * W + D.cm.rank) * D.tot + i] = s;
     __threadfence_system();
     __syncthreads();
@@ -817,17 +833,116 @@ __device__ __forceinline__ float cluster_sum(float v, float* red, float* gpart, 
     return s;
 }
 
-// it < 0: evaluation only (loss + full gradient into the output arrays, no update).  seq > 0: red[] is first
-// assembled from the receive slots of all ranks (summed in rank order: bit-identical everywhere).
-__global__ void __cluster_dims__(DU_CTAS, 1, 1) __launch_bounds__(DU_THREADS)
-k_deconv_update(DeconvDev D, int it, int n_iter, float lr0, int schedule, int seq, float* grad_h_out, float* grad_c_out, float* loss_out) {
+// Starlet-L1 term of h: value -> ctl[6], gradient -> planes[0] (C0).  It depends on h only, so it runs on a second
+// stream CONCURRENTLY with k_deconv_epoch / k_deconv_reduce of the same iteration (8 SMs for ~0.1 ms).
+__global__ void __cluster_dims__(DU_CTAS, 1, 1) __launch_bounds__(DU_THREADS) k_deconv_starlet(DeconvDev D) {
     __shared__ float red[DU_THREADS / 32];
+    cg::cluster_group cl = cg::this_cluster();
+    const int rank = (int)cl.block_rank();
+    const int tid = threadIdx.x, gtid = rank * DU_THREADS + tid;
+    constexpr int GT_ALL = DU_CTAS * DU_THREADS;
+    const int nu = D.nu, pp = nu * nu, J = D.J;
+    float* C0 = D.planes;
+    float* C1 = C0 + pp;
+    float* Tj = C1 + 2 * pp;             // [J][pp]
+    float reg = 0.f;
+    for (int j = 0; j < J; ++j) {
+        const int Dd = 1 << j;
+        const float* cur = (j == 0) ? D.h : C0;
+        for (int i = gtid; i < pp; i += GT_ALL) C1[i] = atrous_g(cur, nu, i / nu, i % nu, Dd, 0);
+        cl.sync();
+        const float lam = (j == 0) ? D.lam_hf : D.lam_scales;
+        for (int i = gtid; i < pp; i += GT_ALL) {
+            const float nxt = atrous_g(C1, nu, i / nu, i % nu, Dd, 1);
+            const float al = cur[i] - nxt;
+            const float lw = lam * (D.W ? D.W[(size_t)j * pp + i] : 1.f);
+            reg = fmaf(lw, fabsf(al), reg);
+            Tj[(size_t)j * pp + i] = (al > 0.f) ? lw : (al < 0.f) ? -lw : 0.f;
+            C0[i] = nxt;             // in place: cur[i] is only read by the owner of pixel i in this pass
+        }
+        cl.sync();
+    }
+    // backward sweep g_j = t_j + H_j^T (g_{j+1} - t_j).  H^T folds the out-of-range taps of the edge-replicated filter
+    // onto the two border pixels of every line: those need sums over up to 2 Dd + 1 elements, done by one WARP per
+    // (line, side) instead of one thread, so that a pass stays one memory round trip long.
+    const int gw = gtid >> 5, lane = tid & 31;
+    constexpr int NW = GT_ALL / 32;
+    const float h0 = 1.f / 16.f, h1 = 4.f / 16.f, h2 = 6.f / 16.f;
+    for (int j = J - 1; j >= 0; --j) {
+        const int Dd = 1 << j;
+        for (int i = gtid; i < pp; i += GT_ALL) C0[i] = ((j == J - 1) ? 0.f : C0[i]) - Tj[(size_t)j * pp + i];
+        cl.sync();
+        for (int axis = 1; axis >= 0; --axis) {            // columns (C0 -> C1), then rows (C1 -> C0, + t_j)
+            const float* src = axis ? C0 : C1;
+            float* dst = axis ? C1 : C0;
+            const float* Tp = axis ? nullptr : Tj + (size_t)j * pp;
+            for (int i = gtid; i < pp; i += GT_ALL) {
+                const int v = i / nu, u = i % nu, pos = axis ? v : u;
+                if (pos > 0 && pos < nu - 1) {
+                    const float val = axis ? atrous_adj(src + u, nu, nu, v, Dd) : atrous_adj(src + v * nu, 1, nu, u, Dd);
+                    dst[i] = (Tp ? Tp[i] : 0.f) + val;
+                }
+            }
+            for (int b = gw; b < 2 * nu; b += NW) {
+                const int line = b >> 1, side = b & 1;
+                const float* base = axis ? src + line : src + line * nu;
+                const int stride = axis ? nu : 1;
+                float P1 = 0.f, P2 = 0.f;                   // sums over distances 1..Dd and Dd+1..2Dd from the border
+                for (int r = lane + 1; r <= 2 * Dd && r <= nu - 1; r += 32) {
+                    const float x = base[(side ? nu - 1 - r : r) * stride];
+                    if (r <= Dd) P1 += x; else P2 += x;
+                }
+                P1 = warp_sum(P1); P2 = warp_sum(P2);
+                if (lane == 0) {
+                    const float P0 = base[(side ? nu - 1 : 0) * stride];
+                    const int o = axis ? (side ? nu - 1 : 0) * nu + line : line * nu + (side ? nu - 1 : 0);
+                    dst[o] = (Tp ? Tp[o] : 0.f) + h0 * ((P0 + P1) + P2) + h1 * (P0 + P1) + h2 * P0;
+                }
+            }
+            cl.sync();
+        }
+    }
+    reg = cluster_sum(reg, red, D.gpart + 8 * DU_CTAS, 0, tid, rank);
+    if (gtid == 0) D.ctl[6] = reg;
+}
+
+// several cluster-wide sums with ONE cluster barrier
+template <int N>
+__device__ __forceinline__ void cluster_sums(float (&v)[N], float* red, float* gpart, int tid, int rank) {
+#pragma unroll
+    for (int q = 0; q < N; ++q) v[q] = warp_sum(v[q]);
+    __syncthreads();
+    if ((tid & 31) == 0) {
+#pragma unroll
+        for (int q = 0; q < N; ++q) red[q * (DU_THREADS / 32) + (tid >> 5)] = v[q];
+    }
+    __syncthreads();
+    if (tid < N) {
+        float s = 0.f;
+        for (int w = 0; w < DU_THREADS / 32; ++w) s += red[tid * (DU_THREADS / 32) + w];
+        gpart[tid * DU_CTAS + rank] = s;
+    }
+    cg::this_cluster().sync();
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+        float s = 0.f;
+        for (int c = 0; c < DU_CTAS; ++c) s += gpart[q * DU_CTAS + c];
+        v[q] = s;
+    }
+}
+
+// Replicated half of an iteration.  it < 0: evaluation only (loss + full gradient into the output arrays, no
+// update).  seq > 0: red[] is first assembled from the receive slots of all ranks (summed in rank order: bit-identical
+// everywhere).  with_reg: planes[0] / ctl[6] hold the starlet gradient / value from k_deconv_starlet.
+__global__ void __cluster_dims__(DU_CTAS, 1, 1) __launch_bounds__(DU_THREADS)
+k_deconv_update(DeconvDev D, int it, int n_iter, float lr0, int schedule, int seq, int with_reg, float* grad_h_out, float* grad_c_out, float* loss_out) {
+    __shared__ float red[4 * (DU_THREADS / 32)];
     __shared__ float fus[4 * DC_MMAX];
     cg::cluster_group cl = cg::this_cluster();
     const int rank = (int)cl.block_rank();
     const int tid = threadIdx.x, gtid = rank * DU_THREADS + tid;
     constexpr int GT_ALL = DU_CTAS * DU_THREADS;
-    const int nu = D.nu, pp = nu * nu, M = D.M, J = D.J;
+    const int nu = D.nu, pp = nu * nu, M = D.M;
     if (seq > 0) {
         const int W = D.cm.world, par = seq & 1;
         if (tid < W) {
@@ -850,53 +965,20 @@ k_deconv_update(DeconvDev D, int it, int n_iter, float lr0, int schedule, int se
         __threadfence();
         cl.sync();
     }
-    float* C0 = D.planes;
-    float* C1 = C0 + pp;
-    float* GT = C1 + pp;                 // total gradient wrt h
-    float* Tj = GT + pp;                 // [J][pp]
-    float* gpart = D.gpart;              // [8 slots][DU_CTAS]
-    float reg = 0.f;
-    const bool do_reg = D.free_h && (D.lam_scales != 0.f || D.lam_hf != 0.f);
-    if (do_reg) {
-        for (int j = 0; j < J; ++j) {
-            const int Dd = 1 << j;
-            const float* cur = (j == 0) ? D.h : C0;
-            for (int i = gtid; i < pp; i += GT_ALL) C1[i] = atrous_g(cur, nu, i / nu, i % nu, Dd, 0);
-            cl.sync();
-            const float lam = (j == 0) ? D.lam_hf : D.lam_scales;
-            for (int i = gtid; i < pp; i += GT_ALL) {
-                const float nxt = atrous_g(C1, nu, i / nu, i % nu, Dd, 1);
-                const float al = cur[i] - nxt;
-                const float lw = lam * (D.W ? D.W[(size_t)j * pp + i] : 1.f);
-                reg = fmaf(lw, fabsf(al), reg);
-                Tj[(size_t)j * pp + i] = (al > 0.f) ? lw : (al < 0.f) ? -lw : 0.f;
-                C0[i] = nxt;             // in place: cur[i] is only read by the owner of pixel i in this pass
-            }
-            cl.sync();
-        }
-        for (int j = J - 1; j >= 0; --j) {
-            const int Dd = 1 << j;
-            for (int i = gtid; i < pp; i += GT_ALL) C0[i] = ((j == J - 1) ? 0.f : C0[i]) - Tj[(size_t)j * pp + i];
-            cl.sync();
-            for (int i = gtid; i < pp; i += GT_ALL) C1[i] = atrous_adj(C0 + (i % nu), nu, nu, i / nu, Dd);
-            cl.sync();
-            for (int i = gtid; i < pp; i += GT_ALL) C0[i] = Tj[(size_t)j * pp + i] + atrous_adj(C1 + (i / nu) * nu, 1, nu, i % nu, Dd);
-            cl.sync();
-        }
-    }
-    float gn2 = 0.f, pos = 0.f;
+    const float* C0 = D.planes;
+    float* GT = D.planes + 2 * pp;       // total gradient wrt h
+    float v4[4] = {0.f, 0.f, 0.f, 0.f};  // |g|^2, positivity, prior, flux uniformity
     if (D.free_h) {
         for (int i = gtid; i < pp; i += GT_ALL) {
             const float hv = D.h[i];
-            float g = D.red[i] + (do_reg ? C0[i] : 0.f);
-            if (D.lam_pos != 0.f && hv < 0.f) { g -= D.lam_pos; pos -= D.lam_pos * hv; }
+            float g = D.red[i] + (with_reg ? C0[i] : 0.f);
+            if (D.lam_pos != 0.f && hv < 0.f) { g -= D.lam_pos; v4[1] -= D.lam_pos * hv; }
             GT[i] = g;
-            gn2 = fmaf(g, g, gn2);
+            v4[0] = fmaf(g, g, v4[0]);
             if (grad_h_out) grad_h_out[i] = g;
         }
     }
     // c_x, c_y gradients (+ prior): every CTA computes them redundantly (identical), only rank 0 counts them
-    float prior_loss = 0.f;
     __shared__ float gcs[2 * DC_MMAX];
     if (tid < 2 * M) {
         float g = D.red[pp + tid];
@@ -905,15 +987,14 @@ k_deconv_update(DeconvDev D, int it, int n_iter, float lr0, int schedule, int se
             const float mu = D.prior[(2 * ax) * M + m], sg = D.prior[(2 * ax + 1) * M + m];
             const float z = (D.c[tid] - mu) / sg;
             g += z / sg;
-            if (rank == 0) prior_loss = 0.5f * z * z;
+            if (rank == 0) v4[2] = 0.5f * z * z;
         }
         gcs[tid] = g;
         if (grad_c_out && rank == 0) grad_c_out[tid] = g;
-        if (D.free_c && rank == 0) gn2 = fmaf(g, g, gn2);
+        if (D.free_c && rank == 0) v4[0] = fmaf(g, g, v4[0]);
     }
     // flux uniformity: lam * sum_m std_e(a_em) [/ |mean_e(a_em)|] from the all-reduced shifted sums; the gradient
     // wrt a_em is A_m (a_em - mean_m) - B_m, applied by the epoch kernel with the pending update
-    float fu_loss = 0.f;
     if (D.lam_fu != 0.f && tid < M) {
         const int o = red_flux(D);
         const float Et = (float)D.E_total, K = D.fu[tid];
@@ -934,18 +1015,15 @@ k_deconv_update(DeconvDev D, int it, int n_iter, float lr0, int schedule, int se
         }
         fus[tid] = mean; fus[DC_MMAX + tid] = A; fus[2 * DC_MMAX + tid] = B;
         if (rank == 0) {
-            fu_loss = val;
+            v4[3] = val;
             // |g_a|^2 with the flux-uniformity term: sum_e (g + A (a - mean) - B)^2
-            if (D.free_a) gn2 += A * A * var * Et + Et * B * B + 2.f * A * (Sga - dm * Sg) - 2.f * B * Sg;
+            if (D.free_a) v4[0] += A * A * var * Et + Et * B * B + 2.f * A * (Sga - dm * Sg) - 2.f * B * Sg;
         }
     }
-    reg = cluster_sum(reg, red, gpart, 0, tid, rank);
-    pos = cluster_sum(pos, red, gpart, 1, tid, rank);
-    prior_loss = cluster_sum(prior_loss, red, gpart, 2, tid, rank);
-    fu_loss = cluster_sum(fu_loss, red, gpart, 4, tid, rank);
-    gn2 = cluster_sum(gn2, red, gpart, 3, tid, rank) + D.red[pp + 2 * M + 1];
-    const float L = D.red[pp + 2 * M] + reg + pos + prior_loss + fu_loss;
-    if (rank == 0 && D.lam_fu != 0.f && tid < M) {      // every read of D.fu above is behind a cluster barrier
+    cluster_sums<4>(v4, red, D.gpart, tid, rank);
+    const float gn2 = v4[0] + D.red[pp + 2 * M + 1];
+    const float L = D.red[pp + 2 * M] + (with_reg ? D.ctl[6] : 0.f) + v4[1] + v4[2] + v4[3];
+    if (rank == 0 && D.lam_fu != 0.f && tid < M) {      // every read of D.fu above is behind the cluster barrier
         D.fu[tid] = fus[tid]; D.fu[DC_MMAX + tid] = fus[DC_MMAX + tid]; D.fu[2 * DC_MMAX + tid] = fus[2 * DC_MMAX + tid];
     }
     if (gtid == 0) {
@@ -994,11 +1072,14 @@ struct DeconvHandle {
     std::vector<void*> ipc_open;         // peer mappings to close
     void* comm_buf;                      // own receive buffer (IPC exported)
     cudaStream_t st;
+    cudaStream_t st2;                    // the starlet term of h runs here, concurrently with the epoch kernel
+    cudaEvent_t ev_h, ev_go, ev_reg;     // h final (main stream) -> starlet may start ; starlet dispatched -> epoch may start ; starlet done -> update
+    bool reg_pending;
     int loss_cap;
     size_t smem_epoch;
     int CS;                              // CTAs per epoch (cluster size); 0 = not yet chosen
     int CS_user;
-    int n_sm, max_smem;
+    int n_sm, max_smem, smem_sm;
     int seq;                             // sequence number of the in-kernel all-reduce
     float *gh, *gcx, *ls;                // evaluation outputs (lcb_deconv_loss_grad / _get)
 };
@@ -1025,15 +1106,18 @@ static int get(DeconvHandle* H, float* dst, const float* src, size_t count, int 
     return LCB_OK;
 }
 
-// CTAs per epoch: the smallest power of two (<= 8, bands of >= 4 rows) that gives the GPU >= 4 CTAs per SM to
-// balance (two are resident at a time), e.g. 200 local epochs -> 4, 100 -> 8, 25 -> 8, >= 592 -> 1.
+// CTAs per epoch: the smallest power of two (<= 8, bands of >= 4 rows) for which two CTAs fit the shared memory of
+// an SM and the local epochs give every SM at least one CTA.  Measured on cfg4 shapes (n = 64, P = 64, 148 SMs):
+// 200 / 100 / 50 local epochs -> 4, 25 -> 8; small stamps whose planes fit twice per SM anyway -> 1.
 static int choose_cluster(const DeconvHandle* H) {
     const DeconvDev& D = H->D;
+    const size_t two_per_sm = (size_t)(H->smem_sm / 2 - 1024);
+    auto bytes = [&](int c) { return (size_t)dc_layout(D.n, D.k, D.NA, D.A0, c).total * 4; };
     int cs = 1;
     if (H->CS_user > 0) cs = H->CS_user;
-    else while (cs < DC_CSMAX && D.E * cs < 4 * H->n_sm) cs *= 2;
+    else while (cs < DC_CSMAX && (D.E * cs < H->n_sm || bytes(cs) > two_per_sm)) cs *= 2;
     while (cs > 1 && (D.n + cs - 1) / cs < 4) cs /= 2;
-    while (cs < DC_CSMAX && (size_t)dc_layout(D.n, D.k, D.NA, D.A0, cs).total * 4 > (size_t)H->max_smem) cs *= 2;
+    while (cs < DC_CSMAX && bytes(cs) > (size_t)H->max_smem) cs *= 2;
     return cs;
 }
 
@@ -1073,14 +1157,37 @@ static int launch_epoch(DeconvHandle* H, int flags) {
 static int launch_reduce(DeconvHandle* H, int force_h, int seq) {
     DeconvDev& D = H->D;
     LcbProfScope ps("k_deconv_reduce", H->st);
-    k_deconv_reduce<<<(D.tot + 255) / 256, 256, 0, H->st>>>(D, force_h, seq);
+    k_deconv_reduce<<<(D.tot + 63) / 64, 256, 0, H->st>>>(D, force_h, seq);
     LCB_CUDA(cudaGetLastError());
     return LCB_OK;
 }
 
+static bool with_reg(const DeconvHandle* H) {
+    const DeconvDev& D = H->D;
+    return D.free_h && (D.lam_scales != 0.f || D.lam_hf != 0.f);
+}
+
+// starlet term of the CURRENT h on the second stream; call before launch_epoch of the same evaluation
+static int launch_starlet(DeconvHandle* H) {
+    H->reg_pending = false;
+    if (!with_reg(H)) return LCB_OK;
+    LCB_CUDA(cudaEventRecord(H->ev_h, H->st));
+    LCB_CUDA(cudaStreamWaitEvent(H->st2, H->ev_h, 0));
+    LCB_CUDA(cudaEventRecord(H->ev_go, H->st2));          // the main stream resumes only once the second stream has seen ev_h:
+    LCB_CUDA(cudaStreamWaitEvent(H->st, H->ev_go, 0));    // both kernels become ready together, the priority decides
+    { LcbProfScope ps("k_deconv_starlet", H->st2); k_deconv_starlet<<<DU_CTAS, DU_THREADS, 0, H->st2>>>(H->D); }
+    LCB_CUDA(cudaGetLastError());
+    LCB_CUDA(cudaEventRecord(H->ev_reg, H->st2));
+    H->reg_pending = true;
+    return LCB_OK;
+}
+
 static int launch_update(DeconvHandle* H, int it, int n_iter, float lr, int schedule, int seq, float* gh, float* gc, float* ls) {
+    const int wr = H->reg_pending ? 1 : 0;
+    if (wr) LCB_CUDA(cudaStreamWaitEvent(H->st, H->ev_reg, 0));
+    H->reg_pending = false;
     LcbProfScope ps("k_deconv_update", H->st);
-    k_deconv_update<<<DU_CTAS, DU_THREADS, 0, H->st>>>(H->D, it, n_iter, lr, schedule, seq, gh, gc, ls);
+    k_deconv_update<<<DU_CTAS, DU_THREADS, 0, H->st>>>(H->D, it, n_iter, lr, schedule, seq, wr, gh, gc, ls);
     LCB_CUDA(cudaGetLastError());
     return LCB_OK;
 }
@@ -1102,6 +1209,10 @@ int lcb_deconv_destroy(void* handle) {
     DeconvHandle* H = (DeconvHandle*)handle;
     if (!H) return LCB_OK;
     cudaStreamSynchronize(H->st);
+    if (H->st2) { cudaStreamSynchronize(H->st2); cudaStreamDestroy(H->st2); }
+    if (H->ev_h) cudaEventDestroy(H->ev_h);
+    if (H->ev_go) cudaEventDestroy(H->ev_go);
+    if (H->ev_reg) cudaEventDestroy(H->ev_reg);
     for (void* p : H->ipc_open) cudaIpcCloseMemHandle(p);
     if (H->comm_buf) cudaFree(H->comm_buf);
     for (void* p : H->owned) cudaFree(p);
@@ -1118,6 +1229,15 @@ int lcb_deconv_create(const lcb_deconv_problem* p, int mem, void* stream, void**
     DeconvHandle* H = new DeconvHandle();
     H->st = (cudaStream_t)stream;
     H->comm_buf = nullptr; H->CS = 0; H->CS_user = 0; H->seq = 0;
+    H->st2 = nullptr; H->ev_h = nullptr; H->ev_go = nullptr; H->ev_reg = nullptr; H->reg_pending = false;
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);     // the 8 starlet CTAs must get their SMs before the epoch grid fills the GPU
+    if (cudaStreamCreateWithPriority(&H->st2, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaEventCreateWithFlags(&H->ev_go, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&H->ev_h, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&H->ev_reg, cudaEventDisableTiming) != cudaSuccess) {
+        lcb_set_error("lcb_deconv_create: cannot create the auxiliary stream"); delete H; return LCB_ERR_CUDA;
+    }
     if (const char* ev = getenv("LCB_DECONV_CS")) H->CS_user = atoi(ev);
     DeconvDev& D = H->D;
     memset(&D, 0, sizeof(D));
@@ -1143,7 +1263,7 @@ int lcb_deconv_create(const lcb_deconv_problem* p, int mem, void* stream, void**
     AL(c, 2 * (size_t)DC_MMAX, true) AL(c_mu, 2 * (size_t)DC_MMAX, true) AL(c_nu, 2 * (size_t)DC_MMAX, true)
     AL(ep, E * np, true) AL(ep_mu, E * np, true) AL(ep_nu, E * np, true) AL(ep_g, E * np, true)
     AL(alpha, E, true) AL(Gh, E * pp, true) AL(gc, E * 2 * (size_t)DC_MMAX, true) AL(eloss, E, true)
-    AL(red, pp + 6 * DC_MMAX + 2, true) AL(ctl, 8, true) AL(fu, 3 * (size_t)DC_MMAX, true) AL(gpart, 64, true)
+    AL(red, pp + 6 * DC_MMAX + 2, true) AL(ctl, 8, true) AL(fu, 3 * (size_t)DC_MMAX, true) AL(gpart, 16 * DU_CTAS, true)
     AL(planes, (3 + (size_t)J) * pp, true) AL(model, E * nn, true) AL(prior, 4 * (size_t)DC_MMAX, true)
 #undef AL
     if ((rc = dalloc(H, (void**)&H->gh, pp * 4, true)) || (rc = dalloc(H, (void**)&H->gcx, 2 * DC_MMAX * 4, true)) ||
@@ -1163,6 +1283,7 @@ int lcb_deconv_create(const lcb_deconv_problem* p, int mem, void* stream, void**
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&H->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     cudaDeviceGetAttribute(&H->n_sm, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&H->smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
     if ((size_t)dc_layout(D.n, D.k, D.NA, D.A0, DC_CSMAX).total * 4 > (size_t)H->max_smem) {
         lcb_set_error("deconvolution: n=%d k=%d P=%d does not fit the shared memory of one SM even with %d CTAs per epoch", D.n, D.k, D.P, DC_CSMAX);
         lcb_deconv_destroy(H);
@@ -1295,7 +1416,7 @@ int lcb_deconv_step_local(void* handle, int want_model) {
     DeconvHandle* H = (DeconvHandle*)handle;
     LCB_REQUIRE(H, "lcb_deconv_step_local: NULL handle");
     int rc;
-    if ((rc = launch_epoch(H, want_model ? 1 : 0))) return rc;
+    if ((rc = launch_starlet(H)) || (rc = launch_epoch(H, want_model ? 1 : 0))) return rc;
     return launch_reduce(H, 0, 0);
 }
 
@@ -1328,7 +1449,7 @@ int lcb_deconv_run(void* handle, const lcb_fit_opts* opt, float* loss_hist, int 
     }
     for (int it = 0; it < opt->n_iter; ++it) {
         const int seq = next_seq(H);
-        if ((rc = launch_epoch(H, 0)) || (rc = launch_reduce(H, 0, seq)) ||
+        if ((rc = launch_starlet(H)) || (rc = launch_epoch(H, 0)) || (rc = launch_reduce(H, 0, seq)) ||
             (rc = launch_update(H, it, opt->n_iter, opt->lr, opt->schedule, seq, nullptr, nullptr, nullptr))) return rc;
     }
     // flush the pending per-epoch update so that get() sees the final parameters
@@ -1347,7 +1468,7 @@ int lcb_deconv_loss_grad(void* handle, lcb_deconv_grad* g, int mem) {
     int rc;
     LCB_CUDA(cudaMemsetAsync(D.ctl + 4, 0, 4, H->st));
     const int seq = next_seq(H);
-    if ((rc = launch_epoch(H, 0)) || (rc = launch_reduce(H, 0, seq)) ||
+    if ((rc = launch_starlet(H)) || (rc = launch_epoch(H, 0)) || (rc = launch_reduce(H, 0, seq)) ||
         (rc = launch_update(H, -1, 1, 0.f, 0, seq, H->gh, H->gcx, H->ls))) return rc;
     if (D.lam_fu != 0.f && D.M > 0) {
         k_deconv_fu_apply<<<(D.E * D.M + 255) / 256, 256, 0, H->st>>>(D);
@@ -1375,7 +1496,7 @@ int lcb_deconv_get(void* handle, lcb_deconv_params* q, float* model, float* loss
         LCB_CUDA(cudaMemsetAsync(D.ctl + 4, 0, 4, H->st));
         if ((rc = launch_epoch(H, 1))) return rc;
         if (loss) {               // LOCAL loss (chi2 of the local epochs + replicated terms): no exchange here
-            if ((rc = launch_reduce(H, 0, 0)) || (rc = launch_update(H, -1, 1, 0.f, 0, 0, nullptr, nullptr, H->ls))) return rc;
+            if ((rc = launch_starlet(H)) || (rc = launch_reduce(H, 0, 0)) || (rc = launch_update(H, -1, 1, 0.f, 0, 0, nullptr, nullptr, H->ls))) return rc;
             if ((rc = get(H, loss, H->ls, 1, mem))) return rc;
         }
         if ((rc = get(H, model, D.model, E * nn, mem))) return rc;
