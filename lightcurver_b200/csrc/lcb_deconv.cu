@@ -165,12 +165,19 @@ __device__ __forceinline__ void blk8(float (&acc)[DC_XB], const float (&tap)[8],
 __device__ __forceinline__ void corr_line(const float* __restrict__ fr, const float* __restrict__ sr, int NA, int NA8, float (&acc)[DC_XB]) {
     float lo[8], hi[8], tap[8];
     if (NA8 > 0) ld8(lo, fr);
-    for (int t0 = 0; t0 < NA8; t0 += 8) {
+    int t0 = 0;
+    for (; t0 + 16 <= NA8; t0 += 16) {                 // two blocks per trip: the window registers ping-pong (no moves)
         ld8(hi, fr + t0 + 8);
         ld8(tap, sr + t0);
         blk8<false>(acc, tap, lo, hi);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) lo[i] = hi[i];
+        ld8(lo, fr + t0 + 16);
+        ld8(tap, sr + t0 + 8);
+        blk8<false>(acc, tap, hi, lo);
+    }
+    if (t0 < NA8) {
+        ld8(hi, fr + t0 + 8);
+        ld8(tap, sr + t0);
+        blk8<false>(acc, tap, lo, hi);
     }
     const int R = NA - NA8;                            // tail taps: aligned loads, only the real taps are multiplied
     if (R > 0) {
@@ -212,16 +219,28 @@ __device__ __forceinline__ void conv_line_T(const float* __restrict__ rr, const 
     }
     // block b (t0 = NA8 - 8 - 8 b): j = t0 + 7 - t, column offset = (NA8 - 1 - t0 - 7) + j + x = 8 b + j + x
     if (NA8 > 0) ld8(lo, rr);
-    for (int b = 0; b * 8 < NA8; ++b) {
-        ld8(hi, rr + 8 * b + 8);
-        ld8(tap, sr + NA8 - 8 - 8 * b);
+    auto sq = [](float (&t)[8]) {
         if (SQ) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) tap[i] *= tap[i];
+            for (int i = 0; i < 8; ++i) t[i] *= t[i];
         }
+    };
+    int b = 0;
+    for (; 8 * b + 16 <= NA8; b += 2) {                // two blocks per trip: the window registers ping-pong (no moves)
+        ld8(hi, rr + 8 * b + 8);
+        ld8(tap, sr + NA8 - 8 - 8 * b);
+        sq(tap);
         blk8<true>(acc, tap, lo, hi);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) lo[i] = hi[i];
+        ld8(lo, rr + 8 * b + 16);
+        ld8(tap, sr + NA8 - 16 - 8 * b);
+        sq(tap);
+        blk8<true>(acc, tap, hi, lo);
+    }
+    if (8 * b < NA8) {
+        ld8(hi, rr + 8 * b + 8);
+        ld8(tap, sr + NA8 - 8 - 8 * b);
+        sq(tap);
+        blk8<true>(acc, tap, lo, hi);
     }
 }
 
@@ -906,6 +925,133 @@ __global__ void __cluster_dims__(DU_CTAS, 1, 1) __launch_bounds__(DU_THREADS) k_
     if (gtid == 0) D.ctl[6] = reg;
 }
 
+// Same term with every plane DISTRIBUTED over the shared memories of the 8 CTAs (CTA c owns rows [c R, (c+1) R) of
+// h, the scratch planes and the J sign planes): row passes are local, column passes read the rows of other CTAs
+// through DSMEM, and only ONE cluster barrier per scale and direction is needed (scratch planes are double buffered),
+// with no global-memory fence inside the loop.  Used when (6 + J) R nu floats fit in shared memory.
+__global__ void __cluster_dims__(DU_CTAS, 1, 1) __launch_bounds__(DU_THREADS) k_deconv_starlet_dsm(DeconvDev D, int R) {
+    extern __shared__ __align__(16) float ssm[];
+    __shared__ float red[DU_THREADS / 32];
+    __shared__ float* peer[DU_CTAS];                  // ssm of every CTA
+    cg::cluster_group cl = cg::this_cluster();
+    const int rank = (int)cl.block_rank();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nu = D.nu, pp = nu * nu, J = D.J;
+    const int bs = R * nu;                            // floats per plane band
+    const int v0 = rank * R, nrow = max(0, min(R, nu - v0)), cnt = nrow * nu;
+    // band-local planes: C0 (current c_j / gradient g), X[2] (row-filtered, double buffered), Q[2] (g - t, double buffered), T[J]
+    float* C0 = ssm;
+    float* Xb = ssm + bs;
+    float* Qb = ssm + 3 * bs;
+    float* Tb = ssm + 5 * bs;
+    if (tid < DU_CTAS) peer[tid] = (float*)cl.map_shared_rank(ssm, tid);
+    for (int i = tid; i < cnt; i += DU_THREADS) C0[i] = D.h[v0 * nu + i];
+    cl.sync();
+    const float h0 = 1.f / 16.f, h1 = 4.f / 16.f, h2 = 6.f / 16.f;
+    auto rd = [&](int plane_off, int v, int u) -> float {      // element (v, u) of a distributed plane
+        const int c = v / R;
+        return peer[c][plane_off + (v - c * R) * nu + u];
+    };
+    float reg = 0.f;
+    for (int j = 0; j < J; ++j) {
+        const int Dd = 1 << j;
+        float* X = Xb + (j & 1) * bs;
+        const int xo = (int)(X - ssm);
+        for (int i = tid; i < cnt; i += DU_THREADS) {           // rows: local
+            const int u = i % nu;
+            const float* row = C0 + i - u;
+            X[i] = h0 * (row[max(u - 2 * Dd, 0)] + row[min(u + 2 * Dd, nu - 1)]) + h1 * (row[max(u - Dd, 0)] + row[min(u + Dd, nu - 1)]) + h2 * row[u];
+        }
+        cl.sync();
+        const float lam = (j == 0) ? D.lam_hf : D.lam_scales;
+        for (int i = tid; i < cnt; i += DU_THREADS) {           // columns: other bands through DSMEM
+            const int v = v0 + i / nu, u = i % nu;
+            const float nxt = h0 * (rd(xo, max(v - 2 * Dd, 0), u) + rd(xo, min(v + 2 * Dd, nu - 1), u)) +
+                              h1 * (rd(xo, max(v - Dd, 0), u) + rd(xo, min(v + Dd, nu - 1), u)) + h2 * X[i];
+            const float al = C0[i] - nxt;
+            const float lw = lam * (D.W ? D.W[(size_t)j * pp + v0 * nu + i] : 1.f);
+            reg = fmaf(lw, fabsf(al), reg);
+            Tb[j * bs + i] = (al > 0.f) ? lw : (al < 0.f) ? -lw : 0.f;
+            C0[i] = nxt;
+        }
+        __syncthreads();
+    }
+    // backward sweep g_j = t_j + H_j^T (g_{j+1} - t_j): Q = g - t (local) | barrier | columns (DSMEM) -> X | rows (local) -> C0
+    for (int j = J - 1; j >= 0; --j) {
+        const int Dd = 1 << j;
+        float* Q = Qb + (j & 1) * bs;
+        float* X = Xb;
+        const int qo = (int)(Q - ssm);
+        const float* T = Tb + j * bs;
+        for (int i = tid; i < cnt; i += DU_THREADS) Q[i] = ((j == J - 1) ? 0.f : C0[i]) - T[i];
+        cl.sync();
+        // columns: X[v][u] = sum_t h[t] Q[v - (t-2) Dd][u] for interior rows; rows 0 and nu-1 collect the folded taps
+        for (int i = tid; i < cnt; i += DU_THREADS) {
+            const int v = v0 + i / nu, u = i % nu;
+            if (v > 0 && v < nu - 1) {
+                float acc = h2 * Q[i];
+                if (v - Dd >= 0) acc = fmaf(h1, rd(qo, v - Dd, u), acc);
+                if (v + Dd < nu) acc = fmaf(h1, rd(qo, v + Dd, u), acc);
+                if (v - 2 * Dd >= 0) acc = fmaf(h0, rd(qo, v - 2 * Dd, u), acc);
+                if (v + 2 * Dd < nu) acc = fmaf(h0, rd(qo, v + 2 * Dd, u), acc);
+                X[i] = acc;
+            }
+        }
+        if (rank == 0 || v0 + nrow == nu) {           // bands holding row 0 / row nu-1: sums over <= 2 Dd rows
+            for (int side = 0; side < 2; ++side) {
+                if ((side == 0 && rank != 0) || (side == 1 && (v0 + nrow != nu || nrow == 0))) continue;
+                for (int u = warp; u < nu; u += DU_THREADS / 32) {     // one warp per column
+                    float P1 = 0.f, P2 = 0.f;
+                    for (int r = lane + 1; r <= 2 * Dd && r <= nu - 1; r += 32) {
+                        const float x = rd(qo, side ? nu - 1 - r : r, u);
+                        if (r <= Dd) P1 += x; else P2 += x;
+                    }
+                    P1 = warp_sum(P1); P2 = warp_sum(P2);
+                    if (lane == 0) {
+                        const int vb = side ? nu - 1 : 0;
+                        const float P0 = rd(qo, vb, u);
+                        X[(vb - v0) * nu + u] = h0 * ((P0 + P1) + P2) + h1 * (P0 + P1) + h2 * P0;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // rows (local): C0 = t_j + H^T X along u; columns 0 and nu-1 of every row collect the folded taps (one warp per row and side)
+        for (int i = tid; i < cnt; i += DU_THREADS) {
+            const int u = i % nu;
+            if (u > 0 && u < nu - 1) {
+                const float* row = X + i - u;
+                float acc = h2 * row[u];
+                if (u - Dd >= 0) acc = fmaf(h1, row[u - Dd], acc);
+                if (u + Dd < nu) acc = fmaf(h1, row[u + Dd], acc);
+                if (u - 2 * Dd >= 0) acc = fmaf(h0, row[u - 2 * Dd], acc);
+                if (u + 2 * Dd < nu) acc = fmaf(h0, row[u + 2 * Dd], acc);
+                C0[i] = T[i] + acc;
+            }
+        }
+        for (int b = warp; b < 2 * nrow; b += DU_THREADS / 32) {
+            const int rl = b >> 1, side = b & 1;
+            const float* row = X + rl * nu;
+            float P1 = 0.f, P2 = 0.f;
+            for (int r = lane + 1; r <= 2 * Dd && r <= nu - 1; r += 32) {
+                const float x = row[side ? nu - 1 - r : r];
+                if (r <= Dd) P1 += x; else P2 += x;
+            }
+            P1 = warp_sum(P1); P2 = warp_sum(P2);
+            if (lane == 0) {
+                const int ub = side ? nu - 1 : 0;
+                const float P0 = row[ub];
+                C0[rl * nu + ub] = T[rl * nu + ub] + h0 * ((P0 + P1) + P2) + h1 * (P0 + P1) + h2 * P0;
+            }
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < cnt; i += DU_THREADS) D.planes[v0 * nu + i] = C0[i];
+    reg = cluster_sum(reg, red, D.gpart + 8 * DU_CTAS, 0, tid, rank);
+    if (rank == 0 && tid == 0) D.ctl[6] = reg;
+    cl.sync();                                        // nobody leaves while its band may still be read
+}
+
 // several cluster-wide sums with ONE cluster barrier
 template <int N>
 __device__ __forceinline__ void cluster_sums(float (&v)[N], float* red, float* gpart, int tid, int rank) {
@@ -1074,7 +1220,7 @@ struct DeconvHandle {
     cudaStream_t st;
     cudaStream_t st2;                    // the starlet term of h runs here, concurrently with the epoch kernel
     cudaEvent_t ev_h, ev_go, ev_reg;     // h final (main stream) -> starlet may start ; starlet dispatched -> epoch may start ; starlet done -> update
-    bool reg_pending;
+    bool reg_pending, starlet_attr;
     int loss_cap;
     size_t smem_epoch;
     int CS;                              // CTAs per epoch (cluster size); 0 = not yet chosen
@@ -1175,7 +1321,21 @@ static int launch_starlet(DeconvHandle* H) {
     LCB_CUDA(cudaStreamWaitEvent(H->st2, H->ev_h, 0));
     LCB_CUDA(cudaEventRecord(H->ev_go, H->st2));          // the main stream resumes only once the second stream has seen ev_h:
     LCB_CUDA(cudaStreamWaitEvent(H->st, H->ev_go, 0));    // both kernels become ready together, the priority decides
-    { LcbProfScope ps("k_deconv_starlet", H->st2); k_deconv_starlet<<<DU_CTAS, DU_THREADS, 0, H->st2>>>(H->D); }
+    {
+        const DeconvDev& D = H->D;
+        const int R = (D.nu + DU_CTAS - 1) / DU_CTAS;
+        const size_t dsm = (size_t)(5 + D.J) * R * D.nu * 4;
+        LcbProfScope ps("k_deconv_starlet", H->st2);
+        if (dsm <= (size_t)H->max_smem && !getenv("LCB_DECONV_STARLET_L2")) {
+            if (!H->starlet_attr) {
+                LCB_CUDA(cudaFuncSetAttribute(k_deconv_starlet_dsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+                H->starlet_attr = true;
+            }
+            k_deconv_starlet_dsm<<<DU_CTAS, DU_THREADS, dsm, H->st2>>>(D, R);
+        } else {
+            k_deconv_starlet<<<DU_CTAS, DU_THREADS, 0, H->st2>>>(D);
+        }
+    }
     LCB_CUDA(cudaGetLastError());
     LCB_CUDA(cudaEventRecord(H->ev_reg, H->st2));
     H->reg_pending = true;
@@ -1229,7 +1389,7 @@ int lcb_deconv_create(const lcb_deconv_problem* p, int mem, void* stream, void**
     DeconvHandle* H = new DeconvHandle();
     H->st = (cudaStream_t)stream;
     H->comm_buf = nullptr; H->CS = 0; H->CS_user = 0; H->seq = 0;
-    H->st2 = nullptr; H->ev_h = nullptr; H->ev_go = nullptr; H->ev_reg = nullptr; H->reg_pending = false;
+    H->st2 = nullptr; H->ev_h = nullptr; H->ev_go = nullptr; H->ev_reg = nullptr; H->reg_pending = false; H->starlet_attr = false;
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);     // the 8 starlet CTAs must get their SMs before the epoch grid fills the GPU
     if (cudaStreamCreateWithPriority(&H->st2, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
