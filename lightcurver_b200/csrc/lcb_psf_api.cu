@@ -10,6 +10,8 @@ int lcb_psf_fit_dispatch(const PsfArgs& A, size_t smem, bool fast, cudaStream_t 
 size_t lcb_psf_fit_smem_fast_extra(int n, int nu, int J);
 bool lcb_psf_fit_has_fast(int n, int k, int G);
 int lcb_psf_lm_dispatch(const PsfArgs& A, size_t smem, cudaStream_t st);
+bool lcb_psf_fit_cluster_ok(int n, int k, int G, int Nmax, int J, int max_smem);
+int lcb_psf_fit_cluster_dispatch(const PsfArgs& A, cudaStream_t st);
 int lcb_moffat_image_launch(const PsfArgs& A, cudaStream_t st);
 int lcb_noise_var_dispatch(const PsfArgs& A, cudaStream_t st);
 int lcb_noise_weights_launch(int F, int nu, int J, const float* tab, float* W, float* work,
@@ -97,6 +99,11 @@ static int psf_run_device(const lcb_psf_batch* in, const lcb_psf_opts* opt, lcb_
     const bool fit_fast = lcb_psf_fit_has_fast(n, k, lcb_conv().gauss_taps) &&
                           fit_small + lcb_psf_fit_smem_fast_extra(n, nu, J) <= (size_t)maxsm;
     const int chunk = F < 1184 ? F : 1184;                   // 8 waves of 148 CTAs
+    // grids too large for one SM: one 8-CTA cluster per frame with the planes distributed over its shared memories
+    // (LCB_PSF_CLUSTER=0 / 1 forces the single-CTA / the cluster kernel: parity tests compare the two)
+    const char* cl_env = getenv("LCB_PSF_CLUSTER");
+    const bool cl_want = cl_env ? (cl_env[0] == '1') : (!fit_fast && !fit_planes_sm);
+    const bool fit_cluster = cl_want && lcb_psf_fit_cluster_ok(n, k, lcb_conv().gauss_taps, Nmax, J, maxsm);
 
     DevTemp work(st), sfix(st), Wtmp(st), tabd(st);
     int rc;
@@ -160,7 +167,12 @@ static int psf_run_device(const lcb_psf_batch* in, const lcb_psf_opts* opt, lcb_
         A.planes_in_smem = fit_planes_sm;
         const size_t fit_smem = fit_fast ? fit_small + lcb_psf_fit_smem_fast_extra(n, nu, J)
                                          : fit_small + (fit_planes_sm ? (size_t)7 * pp * 4 : 0);
-        if ((rc = lcb_psf_fit_dispatch(A, fit_smem, fit_fast, st))) return rc;
+        if (fit_cluster && A.n_iter > 0) {
+            if ((rc = lcb_psf_fit_cluster_dispatch(A, st))) return rc;
+            // products (residuals, chi2, narrow / full PSF) at the fitted parameters: the single-CTA kernel with 0 iterations
+            A.n_iter = 0; A.loss_hist = nullptr; A.loss0 = nullptr; A.grad_b0 = nullptr; A.grad_s0 = nullptr; A.status = nullptr;
+        }
+        if ((rc = lcb_psf_fit_dispatch(A, fit_smem, fit_fast && !(fit_cluster && opt->n_iter_adabelief > 0), st))) return rc;
     }
     (void)sumN;
     return LCB_OK;

@@ -208,3 +208,49 @@ def test_psf_large_offsets_use_predicated_passes(cuda_device):
     np.testing.assert_allclose(out['grad_b0'], gb, rtol=1e-5, atol=1e-5 * np.abs(gb).max())
     gs = np.stack([ga, gx, gy], -1).reshape(-1, 3)
     np.testing.assert_allclose(out['grad_s0'], gs, rtol=2e-5, atol=1e-5 * np.abs(gs).max(0).max())
+
+
+@pytest.mark.parametrize("n,k,N", [(64, 2, 3), (48, 3, 2), (32, 4, 2), (64, 3, 3)])
+def test_psf_cluster_kernel_parity(cuda_device, monkeypatch, n, k, N):
+    """The 8-CTA cluster kernel (planes distributed over the shared memories of a cluster, BASELINE cfg5 shapes)
+    against the oracle (loss and gradient at the initial point, 1e-5) and against the single-CTA kernel after a
+    short fit (same mathematics, different summation order)."""
+    from lightcurver_b200 import engine
+    from oracle import starred_model as sm
+    F = 2
+    d, data, nm, weight, a0, off = _frames(F, N, n, k, seed=300 + n + k)
+    nu = n * k
+    rng = np.random.default_rng(2)
+    moffat = np.stack([np.full(F, 3.2), np.full(F, 3.6), np.full(F, 0.4), np.full(F, 2.8), np.ones(F)], -1)
+    J = engine.starlet_scales(nu)
+    W = rng.uniform(0.5, 2.0, (F, J, nu, nu)).astype(np.float32)
+    b0 = (1e-4 * rng.standard_normal((F, nu, nu))).astype(np.float32)
+    x00 = rng.uniform(-1.2, 1.2, (F, N)).astype(np.float32)
+    y00 = rng.uniform(-1.2, 1.2, (F, N)).astype(np.float32)
+    a00 = (a0 * rng.uniform(0.9, 1.1, (F, N))).astype(np.float32)
+    T = 6
+
+    def run():
+        return engine.psf_fit_batch(_flat(data), _flat(weight), off, k, moffat, a00.ravel(), x00.ravel(), y00.ravel(),
+                                    background0=b0, W=W, n_iter_analytic=0, n_iter_adabelief=T, lr=1e-5,
+                                    lam_scales=0.7, lam_hf=1.3,
+                                    want=('loss0', 'grad_b0', 'grad_s0', 'loss_hist', 'narrow_psf', 'full_psf', 'residuals', 'chi2', 'status'))
+    monkeypatch.setenv('LCB_PSF_CLUSTER', '1')
+    oc = run()
+    monkeypatch.setenv('LCB_PSF_CLUSTER', '0')
+    og = run()
+    s_fixed = sm.moffat_image(moffat[:, 0], moffat[:, 1], moffat[:, 2], moffat[:, 3], n, k).numpy()
+    L, (gb, ga, gx, gy) = sm.psf_loss_grad(s_fixed, b0, a00, x00, y00, data, weight, W, n, k, 0.7, 1.3)
+    np.testing.assert_allclose(oc['loss0'], L, rtol=1e-5)
+    np.testing.assert_allclose(oc['grad_b0'], gb, rtol=1e-5, atol=1e-5 * np.abs(gb).max())
+    gs = np.stack([ga, gx, gy], -1).reshape(-1, 3)
+    np.testing.assert_allclose(oc['grad_s0'], gs, rtol=2e-5, atol=1e-5 * np.abs(gs).max(0).max())
+    assert (oc['status'] == 0).all()
+    np.testing.assert_allclose(oc['loss_hist'], og['loss_hist'], rtol=2e-5)
+    np.testing.assert_allclose(oc['a'], og['a'], rtol=1e-4)
+    np.testing.assert_allclose(oc['x0'], og['x0'], atol=1e-4)
+    # a pixel whose gradient is at the rounding level may step the other way (AdaBelief steps are ~lr whatever |g|)
+    assert np.abs(oc['background'] - og['background']).max() <= 2.5 * T * 1e-5
+    assert np.median(np.abs(oc['background'] - og['background'])) <= 1e-6
+    np.testing.assert_allclose(oc['narrow_psf'], og['narrow_psf'], atol=1e-3 * og['narrow_psf'].max())
+    np.testing.assert_allclose(oc['chi2'], og['chi2'], rtol=1e-3)

@@ -34,6 +34,10 @@ def main():
         res[T] = ev_time(lambda: engine.psf_fit_batch(data, w, off, k, mof, a0, n_iter_analytic=0, n_iter_adabelief=T,
                                                        noise_weights=False, lam_scales=1.0, lam_hf=1.0, want=('narrow_psf', 'chi2')))
     per_it = (res[2 * T2] - res[T2]) / T2 / F * 1e3
+    from lightcurver_b200 import _lib
+    _lib.profile_enable(True)
+    engine.psf_fit_batch(data, w, off, k, mof, a0, n_iter_analytic=0, n_iter_adabelief=T2, noise_weights=False, lam_scales=1.0, lam_hf=1.0, want=('narrow_psf', 'chi2'))
+    print('kernels:', _lib.profile_summary()); _lib.profile_enable(False)
     print(f"cfg5 psf: F={F} T2={T2}: {res[T2]:.1f} ms, {res[2*T2]:.1f} ms -> {per_it:.1f} us / iteration / frame (batch of {F}); "
           f"3000 its -> {1e6 / (per_it * 3000):.2f} frames/s", flush=True)
     ms = ev_time(lambda: engine.psf_fit_batch(data, w, off, k, mof, a0, n_iter_analytic=30, n_iter_adabelief=0, noise_weights=True,
