@@ -102,7 +102,10 @@ static int psf_run_device(const lcb_psf_batch* in, const lcb_psf_opts* opt, lcb_
     // grids too large for one SM: one 8-CTA cluster per frame with the planes distributed over its shared memories
     // (LCB_PSF_CLUSTER=0 / 1 forces the single-CTA / the cluster kernel: parity tests compare the two)
     const char* cl_env = getenv("LCB_PSF_CLUSTER");
-    const bool cl_want = cl_env ? (cl_env[0] == '1') : (!fit_fast && !fit_planes_sm);
+    // Measured on cfg5 shapes (profiles/README.md): the cluster kernel is bound by the 17-21 B/clk DSMEM port of an SM
+    // (column passes of the starlet) and by the latency of ~150 barrier-separated phases per iteration; at 20 us per
+    // iteration-frame it does not yet beat the single-CTA kernel with L2-resident planes (13.6 us), so it is opt-in.
+    const bool cl_want = cl_env ? (cl_env[0] == '1') : false;
     const bool fit_cluster = cl_want && lcb_psf_fit_cluster_ok(n, k, lcb_conv().gauss_taps, Nmax, J, maxsm);
 
     DevTemp work(st), sfix(st), Wtmp(st), tabd(st);

@@ -169,7 +169,7 @@ __device__ __forceinline__ void cl_block_reduce(float (&v)[NV], float* red /* [C
 }
 
 // shared-memory layout (floats), shared by host and device
-struct ClLayout { int NB, RB, ldv, oTaps, oSp, oRed, oXch, oS, oGR, oB, oC0, oSg, oScr, scr, total; };
+struct ClLayout { int NB, RB, ldv, oTaps, oSp, oRed, oXch, oBp4, oS, oGR, oB, oC0, oSg, oScr, scr, total; };
 __host__ __device__ inline ClLayout cl_layout(int n, int k, int Nmax, int J) {
     ClLayout L;
     L.NB = n / CL_CTAS; L.RB = L.NB * k;
@@ -180,6 +180,7 @@ __host__ __device__ inline ClLayout cl_layout(int n, int k, int Nmax, int J) {
     L.oSp = o; o += Nmax * 12;
     L.oRed = o; o += CL_WARPS * 4;
     L.oXch = o; o += CL_CTAS * (Nmax * 4 + 4);          // per-rank partial sums, pushed by every CTA
+    L.oBp4 = o; o += 4 * nu;                            // per-band partial column sums for the folded border taps
     o = (o + 3) & ~3;
     L.oS = o; o += (L.RB + 2 * CL_HB) * nu;             // s with halo rows
     L.oGR = o; o += (L.RB + 2 * CL_HB) * nu;            // d chi2 / d s with halo rows
@@ -218,6 +219,7 @@ __global__ void __cluster_dims__(CL_CTAS, 1, 1) __launch_bounds__(CL_THREADS, 1)
     float* sp = sm + L.oSp;                               // [Nmax][12] a,x0,y0, mu3, nu3, g3 (replicated in every CTA)
     float* red = sm + L.oRed;
     float* xch = sm + L.oXch;                             // [CL_CTAS][Nmax*4 + 4]
+    float* bp4 = sm + L.oBp4;                             // [top P1, top P2, bottom P1, bottom P2][nu]
     const int xsz = A.Nmax * 4 + 4;
     float* Sh = sm + L.oS;                                // [HB + RB + HB][nu]
     float* S = Sh + HB * nu;                              // own rows
@@ -277,6 +279,13 @@ __global__ void __cluster_dims__(CL_CTAS, 1, 1) __launch_bounds__(CL_THREADS, 1)
     };
     const int xo = L.oScr, qo = L.oScr + bsz;
 
+#ifdef LCB_PHASE_TIMERS
+    long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tlast = clock64();
+#define CPHASE(k) { const long long tnow = clock64(); ph[k] += tnow - tlast; tlast = tnow; }
+#else
+#define CPHASE(k)
+#endif
     for (int it = 0; it < A.n_iter; ++it) {
         // ---- halo rows of s from the neighbours (their own rows are final: cluster barrier at the end of the update)
         for (int i = tid; i < HB * nu; i += NT) {
@@ -295,6 +304,7 @@ __global__ void __cluster_dims__(CL_CTAS, 1, 1) __launch_bounds__(CL_THREADS, 1)
         for (int i = tid; i < (RB + 2 * HB) * nu; i += NT) GRh[i] = 0.f;
         for (int i = tid; i < L.scr; i += NT) scr[i] = 0.f;          // halo rows of Vg / Vd must read as zero
         __syncthreads();
+        CPHASE(0)
 
         float chi = 0.f, reg = 0.f;
         for (int st = 0; st < N; ++st) {
@@ -336,6 +346,7 @@ __global__ void __cluster_dims__(CL_CTAS, 1, 1) __launch_bounds__(CL_THREADS, 1)
             cl_block_reduce<1>(v1, red, tid);
             if (tid == 0) for (int c = 0; c < CL_CTAS; ++c) pl(c, L.oXch)[crank * xsz + A.Nmax * 4] = v1[0];
         }
+        CPHASE(1)
         cl.sync();                                        // A: gradient bands with halos and per-star sums complete everywhere
         // ---- fold the neighbours' halo rows into the own band (fixed order), per-star gradients (identical in every CTA)
         if (crank > 0) for (int i = tid; i < HB * nu; i += NT) GR[i] += pl(crank - 1, L.oGR)[(HB + RB) * nu + i];
@@ -357,6 +368,7 @@ __global__ void __cluster_dims__(CL_CTAS, 1, 1) __launch_bounds__(CL_THREADS, 1)
         for (int c = 0; c < CL_CTAS; ++c) chi_tot += xch[c * xsz + A.Nmax * 4];
         __syncthreads();
 
+        CPHASE(2)
         // ---- starlet regulariser on the distributed plane b: value + gradient (left in C0)
         if (do_reg) {
             for (int i = tid; i < bsz; i += NT) C0[i] = Bp[i];
@@ -382,12 +394,29 @@ __global__ void __cluster_dims__(CL_CTAS, 1, 1) __launch_bounds__(CL_THREADS, 1)
                 }
                 cl.sync();                                // X is rewritten by the next scale
             }
+            CPHASE(3)
             for (int j = J - 1; j >= 0; --j) {
                 const int Dd = 1 << j;
                 const float lam = (j == 0) ? A.lam_hf : A.lam_scales;
                 for (int i = tid; i < bsz; i += NT) {
                     const float t = lam * (Wf ? __ldg(Wf + (size_t)j * pp + i) : 1.f) * (float)sg[j * bsz + i];
                     Qp[i] = ((j == J - 1) ? 0.f : C0[i]) - t;
+                }
+                __syncthreads();
+                // The folded border taps of the column direction need, for every column, the sums of Q over the rows at
+                // distance 1..Dd and Dd+1..2Dd from the top / bottom edge: every band sums ITS rows (local), the two edge
+                // bands add the eight partial sums after the barrier.
+                for (int task = tid; task < 4 * nu; task += NT) {
+                    const int which = task / nu, u = task % nu;
+                    const int side = which >> 1, far = which & 1;
+                    const int rlo = far ? Dd + 1 : 1, rhi = min(far ? 2 * Dd : Dd, nu - 1);     // distances from the edge
+                    // rows of this band: v = v0 + l, distance r = side ? nu - 1 - v : v
+                    float sacc = 0.f;
+                    for (int l = 0; l < RB; ++l) {
+                        const int v = v0 + l, r = side ? nu - 1 - v : v;
+                        if (r >= rlo && r <= rhi) sacc += Qp[l * nu + u];
+                    }
+                    bp4[which * nu + u] = sacc;
                 }
                 cl.sync();
                 for (int i = tid; i < bsz; i += NT) {     // columns: H^T along v, other bands through DSMEM
@@ -401,20 +430,17 @@ __global__ void __cluster_dims__(CL_CTAS, 1, 1) __launch_bounds__(CL_THREADS, 1)
                         Xp[i] = acc;
                     }
                 }
-                if (crank == 0 || crank == CL_CTAS - 1) {  // rows 0 and nu-1 collect the folded taps: one warp per column
+                if (crank == 0 || crank == CL_CTAS - 1) {  // rows 0 and nu-1 collect the folded taps
                     const int side = (crank == 0) ? 0 : 1;
-                    for (int u = warp; u < nu; u += CL_WARPS) {
+                    for (int u = tid; u < nu; u += NT) {
                         float P1 = 0.f, P2 = 0.f;
-                        for (int r = lane + 1; r <= 2 * Dd && r <= nu - 1; r += 32) {
-                            const float x = rd(qo, side ? nu - 1 - r : r, u);
-                            if (r <= Dd) P1 += x; else P2 += x;
+                        for (int c = 0; c < CL_CTAS; ++c) {     // fixed order
+                            const float* q = pl(c, L.oBp4);
+                            P1 += q[(2 * side) * nu + u]; P2 += q[(2 * side + 1) * nu + u];
                         }
-                        P1 = warp_sum(P1); P2 = warp_sum(P2);
-                        if (lane == 0) {
-                            const int vb = side ? nu - 1 : 0;
-                            const float P0 = rd(qo, vb, u);
-                            Xp[(vb - v0) * nu + u] = h0 * ((P0 + P1) + P2) + h1 * (P0 + P1) + h2 * P0;
-                        }
+                        const int vb = side ? nu - 1 : 0;
+                        const float P0 = Qp[(vb - v0) * nu + u];
+                        Xp[(vb - v0) * nu + u] = h0 * ((P0 + P1) + P2) + h1 * (P0 + P1) + h2 * P0;
                     }
                 }
                 cl.sync();                                // Q is rewritten by the next scale; X complete (local use only)
@@ -450,6 +476,7 @@ __global__ void __cluster_dims__(CL_CTAS, 1, 1) __launch_bounds__(CL_THREADS, 1)
                 __syncthreads();
             }
         }
+        CPHASE(4)
         // ---- total gradient, norm, loss (cluster-wide sums: pushed to every CTA, summed in rank order)
         for (int i = tid; i < bsz; i += NT) {
             const float g = sc * GR[i] + (do_reg ? C0[i] : 0.f);
@@ -460,6 +487,7 @@ __global__ void __cluster_dims__(CL_CTAS, 1, 1) __launch_bounds__(CL_THREADS, 1)
         cl_block_reduce<2>(v2, red, tid);
         if (tid == 0) for (int c = 0; c < CL_CTAS; ++c) { float* q = pl(c, L.oXch) + crank * xsz + A.Nmax * 4 + 1; q[0] = v2[0]; q[1] = v2[1]; }
         cl.sync();                                        // B
+        CPHASE(5)
         float reg_tot = 0.f, gn2_tot = 0.f;
         for (int c = 0; c < CL_CTAS; ++c) { reg_tot += xch[c * xsz + A.Nmax * 4 + 1]; gn2_tot += xch[c * xsz + A.Nmax * 4 + 2]; }
         const float Lval = cv.half * chi_tot + reg_tot;
@@ -496,7 +524,11 @@ __global__ void __cluster_dims__(CL_CTAS, 1, 1) __launch_bounds__(CL_THREADS, 1)
             q[2] = fminf(fmaxf(q[2], -lim), lim);
         }
         cl.sync();                                        // C: own rows of s final; xch / GR halos free for the next iteration
+        CPHASE(6)
     }
+#ifdef LCB_PHASE_TIMERS
+    if (crank == 0 && tid == 0 && A.loss_hist && A.n_iter >= 8) for (int q = 0; q < 8; ++q) A.loss_hist[(size_t)f * A.n_iter + q] = (float)ph[q];
+#endif
     for (int i = tid; i < bsz; i += NT) A.b[(size_t)f * pp + v0 * nu + i] = Bp[i];
     if (crank == 0 && tid < N) { A.a[i0 + tid] = sp[tid * 12]; A.x0[i0 + tid] = sp[tid * 12 + 1]; A.y0[i0 + tid] = sp[tid * 12 + 2]; }
     if (crank == 0 && tid == 0 && A.status) A.status[f] = bad ? LCB_ITEM_NONFINITE : LCB_ITEM_OK;
