@@ -206,6 +206,44 @@ int lcb_deconv_get(void* handle, lcb_deconv_params* q, float* model, float* loss
 int lcb_deconv_noise_weights(void* handle, int stage, float* W_out, int mem);
 int lcb_deconv_destroy(void* handle);
 
+/* ---------------- host-side data policies of the batched drivers, on the device ------------------
+ * All pointers are DEVICE pointers; work is enqueued on `stream` (no synchronisation). */
+typedef struct {           /* psf_modelling.py:136-140 + build_psf's normalisation / smart guess */
+    int F; const int* star_off;      /* ragged batch, as lcb_psf_batch */
+    int n, k;
+    const float* image;              /* [sumN][n][n] raw stamps (NaN allowed) */
+    const float* noisemap;           /* [sumN][n][n] */
+    const unsigned char* mask;       /* [sumN][n][n] nonzero = good pixel, or NULL */
+    float norm_scale;                /* stamps are divided by max(frame) / norm_scale (100) */
+    int downsample_mean;             /* conventions: a0 = flux * k^2 when D_k is the block mean */
+    int guess_method;                /* guess_method_star_position: 0 'center', 1 'max', 2 'barycenter' */
+} lcb_psf_prepare_in;
+
+typedef struct {
+    float* data; float* weight;      /* [sumN][n][n] normalised stamps, mask / sigma^2 */
+    float* a0; float* x0; float* y0; /* [sumN] initial amplitudes and positions */
+    float* norm;                     /* [F] normalisation of each frame (may be NULL) */
+} lcb_psf_prepare_out;
+
+int lcb_psf_prepare_batch(const lcb_psf_prepare_in* in, lcb_psf_prepare_out* out, void* stream);
+
+typedef struct {           /* star_photometry.py:47-64, 309-316 for every star of a footprint at once */
+    int F, S, n, k;                  /* frames, stars, stamp side, subsampling factor */
+    const float* data;               /* [F][S][n][n] raw stamps */
+    const float* noisemap;           /* [F][S][n][n] */
+    const unsigned char* mask;       /* [F][S][n][n] nonzero = good pixel, or NULL */
+    int downsample_mean;
+} lcb_phot_prepare_in;
+
+typedef struct {
+    float* data; float* weight;      /* [F][S][n][n] stamps / scale[s], 1 / sigma^2 */
+    float* a0;                       /* [F][S] initial flux guess */
+    float* scale;                    /* [S] nanmax of each star over all its epochs */
+} lcb_phot_prepare_out;
+
+size_t lcb_phot_prepare_work_floats(int F, int S);
+int lcb_phot_prepare_batch(const lcb_phot_prepare_in* in, lcb_phot_prepare_out* out, float* work, void* stream);
+
 /* ---------------- measurement helper ---------------------------------------------------------- */
 /* FP32 FMA micro-benchmark: runs `iters` dependent-chain FFMA loops on every SM and returns the
  * achieved TFLOP/s in *tflops (used as the measured roofline denominator by bench.py). */

@@ -248,3 +248,28 @@ lib.lcb_deconv_get_cluster.argtypes = [C.c_void_p]
 lib.lcb_deconv_set_global.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
 lib.lcb_deconv_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
 lib.lcb_deconv_comm_connect.argtypes = [C.c_void_p, C.c_void_p]
+
+
+class PsfPrepareIn(C.Structure):
+    _fields_ = [('F', C.c_int), ('star_off', C.c_void_p), ('n', C.c_int), ('k', C.c_int), ('image', C.c_void_p),
+                ('noisemap', C.c_void_p), ('mask', C.c_void_p), ('norm_scale', C.c_float), ('downsample_mean', C.c_int),
+                ('guess_method', C.c_int)]
+
+
+class PsfPrepareOut(C.Structure):
+    _fields_ = [(nm, C.c_void_p) for nm in ('data', 'weight', 'a0', 'x0', 'y0', 'norm')]
+
+
+class PhotPrepareIn(C.Structure):
+    _fields_ = [('F', C.c_int), ('S', C.c_int), ('n', C.c_int), ('k', C.c_int), ('data', C.c_void_p),
+                ('noisemap', C.c_void_p), ('mask', C.c_void_p), ('downsample_mean', C.c_int)]
+
+
+class PhotPrepareOut(C.Structure):
+    _fields_ = [(nm, C.c_void_p) for nm in ('data', 'weight', 'a0', 'scale')]
+
+
+lib.lcb_psf_prepare_batch.argtypes = [C.POINTER(PsfPrepareIn), C.POINTER(PsfPrepareOut), C.c_void_p]
+lib.lcb_phot_prepare_work_floats.argtypes = [C.c_int, C.c_int]
+lib.lcb_phot_prepare_work_floats.restype = C.c_size_t
+lib.lcb_phot_prepare_batch.argtypes = [C.POINTER(PhotPrepareIn), C.POINTER(PhotPrepareOut), C.c_void_p, C.c_void_p]

@@ -103,3 +103,58 @@ def psf_fit_batch(data, weight, star_off, k, moffat0, a0, x00=None, y00=None, ba
     rc = _lib.lib.lcb_psf_fit_batch(C.byref(bi), C.byref(opts), C.byref(bo), mem, current_stream(data))
     _lib.check(rc, 'lcb_psf_fit_batch')
     return out
+
+
+def _to_device(x, dtype):
+    """numpy (pinned or pageable) / torch host or device array -> contiguous CUDA tensor of ``dtype`` on the current device."""
+    import torch
+    if _lib.is_torch(x):
+        return x.to(device='cuda', dtype=dtype, non_blocking=True).contiguous()
+    a = np.ascontiguousarray(x)
+    if dtype == torch.uint8:
+        a = a.view(np.uint8) if a.dtype == np.bool_ else (a > 0).view(np.uint8)
+    elif dtype == torch.int32:
+        a = a.astype(np.int32, copy=False)
+    elif a.dtype != np.float32:
+        a = a.astype(np.float32)
+    return torch.from_numpy(a).to('cuda', non_blocking=True)
+
+
+GUESS_METHODS = {'center': 0, 'max': 1, 'barycenter': 2}
+
+
+def psf_prepare_batch(images, noisemaps, masks, star_off, k, norm_scale=100.0, downsample_mean=True, guess_method='center'):
+    """lcb_psf_prepare_batch: raw stamps (sumN,n,n) -> device tensors (data, weight, a0, x0, y0, norm)."""
+    import torch
+    _lib.require_device()
+    if guess_method not in GUESS_METHODS:
+        raise ValueError(f"guess_method_star_position must be 'center', 'max' or 'barycenter' (got {guess_method!r})")
+    img, nm = _to_device(images, torch.float32), _to_device(noisemaps, torch.float32)
+    mk = None if masks is None else _to_device(masks, torch.uint8)
+    off = _to_device(np.asarray(star_off, np.int32), torch.int32) if not _lib.is_torch(star_off) else star_off.to('cuda', torch.int32)
+    sumN, n = int(img.shape[0]), int(img.shape[-1])
+    F = int(off.shape[0]) - 1
+    out = dict(data=torch.empty_like(img), weight=torch.empty_like(img), a0=torch.empty(sumN, device='cuda'),
+               x0=torch.empty(sumN, device='cuda'), y0=torch.empty(sumN, device='cuda'), norm=torch.empty(F, device='cuda'))
+    pi = _lib.PsfPrepareIn(F, ptr(off), n, int(k), ptr(img), ptr(nm), ptr(mk), float(norm_scale), int(bool(downsample_mean)),
+                           GUESS_METHODS[guess_method])
+    po = _lib.PsfPrepareOut(*[ptr(out[nm_]) for nm_ in ('data', 'weight', 'a0', 'x0', 'y0', 'norm')])
+    _lib.check(_lib.lib.lcb_psf_prepare_batch(C.byref(pi), C.byref(po), current_stream(img)), 'lcb_psf_prepare_batch')
+    out['star_off'] = off
+    return out
+
+
+def phot_prepare_batch(data, noisemap, masks, k, downsample_mean=True):
+    """lcb_phot_prepare_batch: raw stamps (F,S,n,n) -> device tensors (data, weight (F*S,n,n), a0 (F*S,), scale (S,))."""
+    import torch
+    _lib.require_device()
+    d, nm = _to_device(data, torch.float32), _to_device(noisemap, torch.float32)
+    mk = None if masks is None else _to_device(masks, torch.uint8)
+    F, S, n, _ = d.shape
+    out = dict(data=torch.empty((F * S, n, n), device='cuda'), weight=torch.empty((F * S, n, n), device='cuda'),
+               a0=torch.empty(F * S, device='cuda'), scale=torch.empty(S, device='cuda'))
+    work = torch.empty(int(_lib.lib.lcb_phot_prepare_work_floats(F, S)), device='cuda')
+    pi = _lib.PhotPrepareIn(int(F), int(S), int(n), int(k), ptr(d), ptr(nm), ptr(mk), int(bool(downsample_mean)))
+    po = _lib.PhotPrepareOut(*[ptr(out[nm_]) for nm_ in ('data', 'weight', 'a0', 'scale')])
+    _lib.check(_lib.lib.lcb_phot_prepare_batch(C.byref(pi), C.byref(po), ptr(work), current_stream(d)), 'lcb_phot_prepare_batch')
+    return out

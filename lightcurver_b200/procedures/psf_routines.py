@@ -58,44 +58,24 @@ def build_psf_batch(images, noisemaps, subsampling_factor, masks=None, n_iter_an
     sumN = int(off[-1])
     cat = lambda seq: (np.asarray(seq).reshape(sumN, n, n) if isinstance(seq, np.ndarray)
                        else np.concatenate([np.asarray(x) for x in seq]))
-    data = np.array(cat(images), dtype=np.float32)            # private copies (normalised in place below)
-    nm = np.array(cat(noisemaps), dtype=np.float32)
-    counts_a = np.asarray(counts)
-    # global normalisation per frame (A.4): stamps / (max(image) / psf_norm_scale)
-    star_max = np.fmax.reduce(data.reshape(sumN, -1), axis=1)
-    norms = np.fmax.reduceat(star_max, off[:-1]).astype(np.float64) / cv.psf_norm_scale
-    norms[~np.isfinite(norms) | (norms <= 0)] = 1.0
-    inv = np.repeat(1.0 / norms, counts_a).astype(np.float32)[:, None, None]
-    data *= inv
-    nm *= inv
-    good = np.isfinite(data)
-    good &= np.isfinite(nm)
-    good &= nm > 0
-    if masks is not None:
-        good &= (cat(masks) > 0)
-    all_good = bool(good.all())
-    if not all_good:
-        data[~np.isfinite(data)] = 0.0
-        nm[~good] = 1.0
-    np.multiply(nm, nm, out=nm)
-    weight = np.reciprocal(nm, out=nm)                        # 1 / sigma^2 in place
-    if not all_good:
-        weight[~good] = 0.0
-        flux = np.where(good, data, 0.0).sum((-1, -2), dtype=np.float64)
-    else:
-        flux = data.sum((-1, -2), dtype=np.float64)
-    a0 = (np.maximum(flux, 1e-6) * (k * k if cv.downsample_mean else 1.0)).astype(np.float32)
-    x00, y00 = _guess_positions(data, good, guess_method_star_position)
+    # normalisation (A.4), NaN / mask policy, weights and the smart guess run on the device (lcb_psf_prepare_batch):
+    # the raw arrays are uploaded once (asynchronously when they are pinned) and stay there for the fit
+    prep = engine.psf_prepare_batch(cat(images), cat(noisemaps), None if masks is None else cat(masks), off, k,
+                                    norm_scale=cv.psf_norm_scale, downsample_mean=cv.downsample_mean,
+                                    guess_method=guess_method_star_position)
+    data, weight, a0, x00, y00 = prep['data'], prep['weight'], prep['a0'], prep['x0'], prep['y0']
     fwhm = np.broadcast_to(np.asarray(3.0 if guess_fwhm_pixels is None else guess_fwhm_pixels, dtype=np.float64), (F,))
     moffat0 = np.stack([fwhm, fwhm, np.zeros(F), np.full(F, cv.moffat_beta_init), np.ones(F)], -1)
     lam_s = cv.psf_lambda_scales if regularization_strength_scales is None else regularization_strength_scales
     lam_h = cv.psf_lambda_hf if regularization_strength_hf is None else regularization_strength_hf
     out = engine.psf_fit_batch(
-        data, weight, off, k, moffat0, a0, x00, y00, n_iter_analytic=n_iter_analytic,
+        data, weight, prep['star_off'], k, moffat0, a0, x00, y00, n_iter_analytic=n_iter_analytic,
         n_iter_adabelief=n_iter_adabelief, lr=cv.psf_stage2_lr if adabelief_learning_rate is None else adabelief_learning_rate,
         lam_scales=lam_s, lam_hf=lam_h, noise_weights=True,
         bounds=dict(fwhm_min=cv.moffat_fwhm_min, fwhm_max=n / 2.0, beta_min=cv.moffat_beta_min, beta_max=cv.moffat_beta_max),
         want=('narrow_psf', 'full_psf', 'residuals', 'chi2', 'loss_hist', 'loss_hist_analytic', 'status'))
+    out = {kk: v.cpu().numpy() for kk, v in out.items()}            # one device -> host copy per product
+    norms = prep['norm'].cpu().numpy().astype(np.float64)
     out['norms'] = norms
     out['star_off'] = off
     if not return_dicts:

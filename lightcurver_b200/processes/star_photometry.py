@@ -121,36 +121,15 @@ def star_photometry_batch(data, noisemap, psfs, subsampling_factor, n_iter=2000,
     cv = conventions
     k = int(subsampling_factor)
     F, S, n, _ = data.shape
-    d = np.array(data, dtype=np.float32)                      # private copies: the caller's arrays stay untouched
-    nm = np.array(noisemap, dtype=np.float32)
-    isnan = np.isnan(d)
-    isnan |= np.isnan(nm)
-    if isnan.any():
-        d[isnan] = 0.0
-        nm[isnan] = 1e7
-    if masks is not None:
-        bad_epoch = ~np.asarray(masks, bool).all((-1, -2))
-        if bad_epoch.any():
-            nm[bad_epoch] *= 1000.0
-    scale = d.max(axis=(0, 2, 3))                             # (S,)  == nanmax: NaNs are gone
-    inv = (1.0 / scale).astype(np.float32)[None, :, None, None]
-    d *= inv
-    nm *= inv
-    # star_photometry.py:55-64 for all stars at once: one background scalar per star = mean over the four
-    # edges and all epochs of the edge medians
-    edges = np.stack([np.median(d[:, :, 0, :], -1), np.median(d[:, :, :, 0], -1),
-                      np.median(d[:, :, -1, :], -1), np.median(d[:, :, :, -1], -1)])       # (4,F,S)
-    background = np.nan_to_num(edges.mean((0, 1)), nan=0.0)                                  # (S,)
-    a_est = d.sum((-1, -2), dtype=np.float64) - (n * n) * background[None]                   # (F,S)
-    if cv.downsample_mean:
-        a_est = a_est * (k * k)
-    np.multiply(nm, nm, out=nm)
-    weight = np.reciprocal(nm, out=nm)                        # 1 / sigma^2, float32, in place
-    idx = np.repeat(np.arange(F, dtype=np.int32), S)
-    out = engine.phot_fit_batch(d.reshape(F * S, n, n), weight.reshape(F * S, n, n),
-                                np.ascontiguousarray(psfs, np.float32), idx, a_est.reshape(-1).astype(np.float32),
-                                k, n_iter, lr=1e-3, schedule=True, want_residuals=want_residuals,
-                                want_loss_hist=want_loss_hist)
+    # NaN / mask policies, per-star scale, initial flux guess and weights run on the device (lcb_phot_prepare_batch)
+    import torch
+    prep = engine.phot_prepare_batch(data, noisemap, masks, k, downsample_mean=cv.downsample_mean)
+    idx = torch.arange(F, dtype=torch.int32, device='cuda').repeat_interleave(S)
+    psf_d = engine._to_device(psfs, torch.float32)
+    out = engine.phot_fit_batch(prep['data'], prep['weight'], psf_d, idx, prep['a0'], k, n_iter, lr=1e-3, schedule=True,
+                                want_residuals=want_residuals, want_loss_hist=want_loss_hist)
+    out = {kk: v.cpu().numpy() for kk, v in out.items()}
+    scale = prep['scale'].cpu().numpy()
     res = {
         'scale': scale,
         'fluxes': out['a'].reshape(F, S) * scale[None],

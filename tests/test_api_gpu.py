@@ -84,3 +84,71 @@ def test_pipeline_shaped_run_chi2_below_2(cuda_device):
                            masks=[d['masks'][0], d['masks'][1][:1]], n_iter_analytic=50, n_iter_adabelief=50,
                            guess_method_star_position='center', guess_fwhm_pixels=d['fwhm'])
     assert res2[1]['residuals'].shape == (1, n, n) and res2[0]['residuals'].shape == (2, n, n)
+
+
+def test_device_prepare_matches_host_policies(cuda_device):
+    """lcb_psf_prepare_batch / lcb_phot_prepare_batch against a numpy statement of the same policies
+    (psf_modelling.py:136-140 + build_psf normalisation and smart guess; star_photometry.py:47-64, 309-316)."""
+    from lightcurver_b200 import engine
+    rng = np.random.default_rng(5)
+    # ---- PSF side: ragged frames, NaNs, masks, non-positive noise
+    counts = [3, 1, 4]
+    n, k = 16, 2
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    sumN = int(off[-1])
+    img = rng.normal(5.0, 2.0, (sumN, n, n)).astype(np.float32)
+    img[:, 6:10, 6:10] += 200.0
+    nm = rng.uniform(0.5, 2.0, (sumN, n, n)).astype(np.float32)
+    mk = rng.random((sumN, n, n)) > 0.05
+    img[0, 3, 4] = np.nan; nm[0, 3, 4] = np.nan; img[2, 1, 1] = np.inf; nm[5, 0, 0] = 0.0; nm[6, 2, 2] = np.nan
+    for method in ('center', 'max', 'barycenter'):
+        prep = engine.psf_prepare_batch(img, nm, mk, off, k, norm_scale=100.0, downsample_mean=True, guess_method=method)
+        star_max = np.fmax.reduce(img.reshape(sumN, -1), axis=1)
+        norms = np.fmax.reduceat(star_max, off[:-1]).astype(np.float64) / 100.0
+        norms[~np.isfinite(norms) | (norms <= 0)] = 1.0
+        inv = np.repeat(1.0 / norms, counts).astype(np.float32)[:, None, None]
+        d, s = img * inv, nm * inv
+        good = np.isfinite(d) & np.isfinite(s) & (s > 0) & mk
+        d = np.where(np.isfinite(d), d, 0.0).astype(np.float32)
+        w = np.where(good, 1.0 / np.where(good, s, 1.0) ** 2, 0.0)
+        flux = np.where(good, d, 0.0).sum((-1, -2), dtype=np.float64)
+        np.testing.assert_allclose(prep['norm'].cpu().numpy(), norms, rtol=1e-6)
+        np.testing.assert_allclose(prep['data'].cpu().numpy(), d, rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(prep['weight'].cpu().numpy(), w, rtol=2e-6)
+        np.testing.assert_allclose(prep['a0'].cpu().numpy(), np.maximum(flux, 1e-6) * k * k, rtol=1e-5)
+        ctr = (n - 1) / 2.0
+        if method == 'center':
+            x0 = y0 = np.zeros(sumN)
+        elif method == 'max':
+            flat = np.where(good, d, -np.inf).reshape(sumN, -1).argmax(-1)
+            x0, y0 = (flat % n) - ctr, (flat // n) - ctr
+        else:
+            ww = np.clip(np.where(good, d, 0.0), 0.0, None)
+            tot = np.maximum(ww.sum((-1, -2)), 1e-30)
+            ax = np.arange(n) - ctr
+            x0, y0 = (ww.sum(-2) * ax).sum(-1) / tot, (ww.sum(-1) * ax).sum(-1) / tot
+        np.testing.assert_allclose(prep['x0'].cpu().numpy(), x0, atol=1e-4)
+        np.testing.assert_allclose(prep['y0'].cpu().numpy(), y0, atol=1e-4)
+    # ---- photometry side
+    F, S, n = 5, 3, 17
+    data = rng.normal(1.0, 0.3, (F, S, n, n)).astype(np.float32)
+    data[:, :, 7:10, 7:10] += rng.uniform(50, 100, (F, S, 1, 1)).astype(np.float32)
+    noise = rng.uniform(0.5, 2.0, (F, S, n, n)).astype(np.float32)
+    masks = np.ones((F, S, n, n), bool)
+    masks[1, 2, 4, 4] = False; masks[3, 0, 0, 0] = False
+    data[0, 1, 2, 3] = np.nan; noise[2, 2, 5, 5] = np.nan
+    prep = engine.phot_prepare_batch(data, noise, masks, k)
+    d, s = data.copy(), noise.copy()
+    isn = np.isnan(d) | np.isnan(s)
+    d[isn] = 0.0; s[isn] = 1e7
+    s[~masks.all((-1, -2))] *= 1000.0
+    scale = d.max(axis=(0, 2, 3))
+    inv = (1.0 / scale).astype(np.float32)[None, :, None, None]
+    d *= inv; s *= inv
+    edges = np.stack([np.median(d[:, :, 0, :], -1), np.median(d[:, :, :, 0], -1), np.median(d[:, :, -1, :], -1), np.median(d[:, :, :, -1], -1)])
+    bg = np.nan_to_num(edges.mean((0, 1)), nan=0.0)
+    a_est = (d.sum((-1, -2), dtype=np.float64) - n * n * bg[None]) * k * k
+    np.testing.assert_allclose(prep['scale'].cpu().numpy(), scale, rtol=1e-6)
+    np.testing.assert_allclose(prep['data'].cpu().numpy().reshape(F, S, n, n), d, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(prep['weight'].cpu().numpy().reshape(F, S, n, n), 1.0 / s.astype(np.float64) ** 2, rtol=3e-6)
+    np.testing.assert_allclose(prep['a0'].cpu().numpy().reshape(F, S), a_est, rtol=2e-5, atol=1e-4)
