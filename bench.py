@@ -384,10 +384,12 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * F / float(te.item())
-    h2d = 2 * F * N * n * n * 4 + (F + 1) * 4 + F * 20 + 3 * F * N * 4 + F * nu * nu * 4 \
-        + 2 * F * N * n * n * 4 + F * nu * nu * 4 + 4 * F * N * 4
-    d2h = (2 * F * nu * nu + F * N * n * n + F * (CFG['T1'] + CFG['T2']) + 3 * F * N + 8 * F) * 4 + F * nu * nu * 4 \
-        + 6 * F * N * 4
+    # bytes moved by the public API per step (counted from the tensors it copies): raw stamps, noise maps (f32) and masks
+    # (u8) for the PSF step and again for the photometry step, the fitted PSFs back up for the photometry; down: every
+    # product of build_psf_batch (parameters, grids, PSFs, residuals, loss histories) and of star_photometry_batch
+    h2d = 2 * (2 * F * N * n * n * 4 + F * N * n * n) + (F + 1) * 4 + F * 5 * 4 + F * nu * nu * 4
+    d2h = (3 * F * nu * nu + F * N * n * n + F * (CFG['T1'] + CFG['T2']) + 3 * F * N + 5 * F + 3 * F) * 4 \
+        + 6 * F * N * 4 + N * 4
 
     if rank != 0:
         if world > 1:
@@ -422,7 +424,7 @@ def main():
                    "quality": {"psf_chi2_median": chi2_med, "phot_chi2_median": phot_chi2_med}},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "build_psf_batch + star_photometry_batch, pinned host numpy in, numpy out", "steps": e2e_steps},
+                "api": "build_psf_batch + star_photometry_batch: pinned host numpy in (raw stamps, noise maps, masks), numpy out; data policies, fits and products on the device", "steps": e2e_steps},
         "gpu_launches": launches,
         "kernels": prof,
         "roofline": {"bound": "fp32", "kernel": "k_psf_fit", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
