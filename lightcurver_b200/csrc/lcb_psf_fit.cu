@@ -680,11 +680,31 @@ __global__ void __launch_bounds__(FIT_THREADS(K, NS), ((NS) > 0 ? 2 : 1)) k_psf_
         b1t *= cv.b1; b2t *= cv.b2;
         const BeliefCoef bc = {lr, cv.b1, cv.b2, 1.f - cv.b1, 1.f - cv.b2, 1.f / (1.f - b1t), 1.f / (1.f - b2t),
                                cv.eps, cv.eps_root};
-        for (int i = tid; i < pp; i += NT) {
-            float b = Bp[i], mu = MU[i], nv = NU[i];
-            belief_update(bc, cs * GR[i], b, mu, nv);
-            Bp[i] = b; MU[i] = mu; NU[i] = nv;
-            S[i] = __ldg(sfix + i) + b;
+        if constexpr (FAST) {
+            // the moments and the fixed Moffat image come from L2: issue the loads of four pixels before the first
+            // dependent store, otherwise every pixel pays a full L2 round trip (16 per thread and iteration)
+            constexpr int UQ = 4;
+            static_assert(!FAST || ((NS * K) * (NS * K)) % (UQ * NT) == 0, "update loop: grid must be a multiple of 4 * NT");
+            for (int i0 = tid; i0 < pp; i0 += UQ * NT) {
+                float mu[UQ], nv[UQ], sf[UQ];
+#pragma unroll
+                for (int q = 0; q < UQ; ++q) { mu[q] = MU[i0 + q * NT]; nv[q] = NU[i0 + q * NT]; sf[q] = __ldg(sfix + i0 + q * NT); }
+#pragma unroll
+                for (int q = 0; q < UQ; ++q) {
+                    const int i = i0 + q * NT;
+                    float b = Bp[i];
+                    belief_update(bc, cs * GR[i], b, mu[q], nv[q]);
+                    Bp[i] = b; MU[i] = mu[q]; NU[i] = nv[q];
+                    S[i] = sf[q] + b;
+                }
+            }
+        } else {
+            for (int i = tid; i < pp; i += NT) {
+                float b = Bp[i], mu = MU[i], nv = NU[i];
+                belief_update(bc, cs * GR[i], b, mu, nv);
+                Bp[i] = b; MU[i] = mu; NU[i] = nv;
+                S[i] = __ldg(sfix + i) + b;
+            }
         }
         if (tid < N) {
             float* q = sp + tid * 12;
