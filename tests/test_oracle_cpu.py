@@ -125,3 +125,86 @@ def test_golden_vectors():
             np.testing.assert_allclose(L, g['loss'], rtol=1e-12)
             np.testing.assert_allclose(gr[0], g['grad_b'], rtol=1e-9, atol=1e-12)
             np.testing.assert_allclose(np.stack(gr[1:], -1), g['grad_s'], rtol=1e-9, atol=1e-12)
+
+
+def test_pts_source_and_flux_uniformity_closed_forms():
+    """Hand-derived forms used by k_deconv_epoch / k_deconv_update against autograd, float64:
+    the first starlet scale of a separable Gaussian is g_y g_x - (B g_y)(B g_x) with B the edge-replicated B3 filter, so
+    dR/dtheta = sum_x T[x] alpha_0(dp/dtheta)[x] with T = lam W_0 sign(alpha_0(p)) (overlapping windows counted once);
+    flux uniformity: d/da_e [lam std/|mean|] = A (a_e - mean) - B."""
+    import numpy as np
+    import torch
+    from oracle import starred_model as sm
+    from oracle.conventions import DEFAULT as cv
+    E,n,k,M,P=1,12,2,3,24
+    nu=n*k
+    rng=np.random.default_rng(0)
+    t=lambda v: torch.tensor(v,dtype=torch.float64,requires_grad=True)
+    a=t(rng.uniform(1,2,(E,M))); cx=t(np.array([-5.2,-4.0,4.9])); cy=t(np.array([-5.4,-3.1,0.3])); dx=t(rng.uniform(-1,1,E)); dy=t(rng.uniform(-1,1,E))
+    alpha=torch.tensor([0.1],dtype=torch.float64)
+    W=torch.tensor(rng.uniform(0.5,2,(4,nu,nu)))
+    lam=0.7
+    L=sm.pts_source_l1(a,cx,cy,dx,dy,alpha,n,k,P,W,lam,cv)
+    gr=torch.autograd.grad(L,[a,cx,cy,dx,dy])
+    # closed form as in the kernel
+    G=cv.gauss_taps; sig=sm.gauss_sigma(cv)
+    uc,vc,ctr=sm.deconv_positions(cx.detach(),cy.detach(),dx.detach(),dy.detach(),alpha,k,nu,P)
+    uc=uc[0].numpy(); vc=vc[0].numpy()
+    B=np.array([1,4,6,4,1])/16
+    def taps(pc):
+        ic=int(np.floor(pc+0.5)); w0=ic-G//2+1
+        u=np.arange(w0,w0+G); x=u-pc
+        g=np.exp(-x*x/(2*sig*sig))/(np.sqrt(2*np.pi)*sig)
+        return w0,g,x/sig**2*g
+    def ext(w0,g):
+        gE=np.zeros(G+4); BE=np.zeros(G+4)
+        for t_ in range(G+4):
+            u=w0-2+t_
+            if 2<=t_<G+2: gE[t_]=g[t_-2]
+            s=0
+            for tt in range(-2,3):
+                uu=min(max(u+tt,0),nu-1)-w0
+                if 0<=uu<G: s+=B[tt+2]*g[uu]
+            BE[t_]=s
+        return gE,BE
+    ex=[];ey=[];wx=[];wy=[]
+    for m in range(M):
+        w0,g,d=taps(uc[m]); wx.append(w0); ex.append(ext(w0,g)+ext(w0,d))
+        w0,g,d=taps(vc[m]); wy.append(w0); ey.append(ext(w0,g)+ext(w0,d))
+    av=a.detach().numpy()[0]
+    loss=0; pa=np.zeros(M); pu=np.zeros(M); pv=np.zeros(M)
+    GEX=G+4
+    for m in range(M):
+        for i in range(GEX*GEX):
+            v=wy[m]-2+i//GEX; u=wx[m]-2+i%GEX
+            if v<0 or v>=nu or u<0 or u>=nu: continue
+            dup=any(0<=v-(wy[q]-2)<GEX and 0<=u-(wx[q]-2)<GEX for q in range(m))
+            if dup: continue
+            al0=0; ca=np.zeros(M);cu=np.zeros(M);cvv=np.zeros(M)
+            for q in range(M):
+                tv=v-(wy[q]-2); tu=u-(wx[q]-2)
+                if 0<=tv<GEX and 0<=tu<GEX:
+                    gxu,bxu,dxu,bdxu=[ex[q][j][tu] for j in range(4)]
+                    gyv,byv,dyv,bdyv=[ey[q][j][tv] for j in range(4)]
+                    ca[q]=gyv*gxu-byv*bxu; cu[q]=gyv*dxu-byv*bdxu; cvv[q]=dyv*gxu-bdyv*bxu
+                    al0+=av[q]*ca[q]
+            lw=lam*W[0,v,u].item()
+            loss+=lw*abs(al0); T=lw*np.sign(al0)
+            pa+=T*ca; pu+=T*cu; pv+=T*cvv
+    assert abs(L.item() - loss) <= 1e-12 * abs(loss)
+    np.testing.assert_allclose(gr[0].numpy()[0], pa, rtol=1e-10, atol=1e-13)
+    ca_,sa_=np.cos(0.1),np.sin(0.1)
+    GU=av*pu; GV=av*pv
+    np.testing.assert_allclose(gr[1].numpy(), k * (ca_ * GU + sa_ * GV), rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(gr[2].numpy(), k * (-sa_ * GU + ca_ * GV), rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(gr[3].numpy(), [k * GU.sum()], rtol=1e-10); np.testing.assert_allclose(gr[4].numpy(), [k * GV.sum()], rtol=1e-10)
+    # flux uniformity check
+    a2=t(rng.uniform(1,2,(7,3)))
+    for rel in (True,False):
+        import dataclasses
+        c2=dataclasses.replace(cv,flux_uniformity_relative=rel)
+        L2=sm.flux_uniformity(a2,10.0,c2); g2=torch.autograd.grad(L2,[a2])[0].numpy()
+        A_=a2.detach().numpy(); Et=7; mean=A_.mean(0); sd=A_.std(0)
+        if rel: Ac=10/(Et*sd*abs(mean)); Bc=10*sd*np.sign(mean)/(Et*mean**2)
+        else: Ac=10/(Et*sd); Bc=0
+        assert np.abs(g2 - (Ac * (A_ - mean) - Bc)).max() < 1e-12
