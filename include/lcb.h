@@ -108,8 +108,11 @@ typedef struct {
     int   n_iter_adabelief;  /* stage 2 iterations */
     float lr;                /* stage 2 init_learning_rate (scheduled, clipped) */
     float lam_scales, lam_hf;/* regularization_strength_scales / _hf */
-    int   noise_weights;     /* 0: W from batch (NULL -> 1);  1: SLIT propagation of the weights through the stage-1 model */
+    int   noise_weights;     /* 0: W from batch (NULL -> 1);  1: SLIT (diagonal, deterministic) propagation of the weights through the
+                                stage-1 model;  2: Monte-Carlo propagation (propagate_noise(method='MC')): mc_samples noise draws */
     float fwhm_min, fwhm_max, beta_min, beta_max;   /* bounds of the analytic stage */
+    int   mc_samples;        /* noise_weights == 2: number of noise realisations (<= 0: 100) */
+    unsigned mc_seed;        /* noise_weights == 2: seed of the counter-based generator */
 } lcb_psf_opts;
 
 typedef struct {

@@ -180,7 +180,8 @@ class PsfBatch(C.Structure):
 class PsfOpts(C.Structure):
     _fields_ = [('n_iter_analytic', C.c_int), ('n_iter_adabelief', C.c_int), ('lr', C.c_float),
                 ('lam_scales', C.c_float), ('lam_hf', C.c_float), ('noise_weights', C.c_int),
-                ('fwhm_min', C.c_float), ('fwhm_max', C.c_float), ('beta_min', C.c_float), ('beta_max', C.c_float)]
+                ('fwhm_min', C.c_float), ('fwhm_max', C.c_float), ('beta_min', C.c_float), ('beta_max', C.c_float),
+                ('mc_samples', C.c_int), ('mc_seed', C.c_uint)]
 
 
 PSF_OUT_FIELDS = ('moffat', 'a', 'x0', 'y0', 'background', 'narrow_psf', 'full_psf', 'residuals', 'chi2',

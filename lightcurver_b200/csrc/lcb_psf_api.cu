@@ -14,6 +14,7 @@ bool lcb_psf_fit_cluster_ok(int n, int k, int G, int Nmax, int J, int max_smem);
 int lcb_psf_fit_cluster_dispatch(const PsfArgs& A, cudaStream_t st);
 int lcb_moffat_image_launch(const PsfArgs& A, cudaStream_t st);
 int lcb_noise_var_dispatch(const PsfArgs& A, cudaStream_t st);
+int lcb_noise_mc_dispatch(const PsfArgs& A, float* W, int n_samples, unsigned seed, cudaStream_t st);
 int lcb_noise_weights_launch(int F, int nu, int J, const float* tab, float* W, float* work,
                              size_t work_per_frame, cudaStream_t st);
 
@@ -162,7 +163,11 @@ static int psf_run_device(const lcb_psf_batch* in, const lcb_psf_opts* opt, lcb_
         } else {
             if ((rc = lcb_moffat_image_launch(A, st))) return rc;
         }
-        if (opt->noise_weights && do_reg) {
+        if (opt->noise_weights == 2 && do_reg) {
+            // the per-(star, pixel) counters are local to the chunk: mix the first frame into the seed
+            if ((rc = lcb_noise_mc_dispatch(A, Wuse + (size_t)f0 * J * pp, opt->mc_samples > 0 ? opt->mc_samples : 100,
+                                            opt->mc_seed + 0x9e3779b9u * (unsigned)f0, st))) return rc;
+        } else if (opt->noise_weights && do_reg) {
             if ((rc = lcb_noise_var_dispatch(A, st))) return rc;
             if ((rc = lcb_noise_weights_launch(Fc, nu, J, (const float*)tabd.p, Wuse + (size_t)f0 * J * pp,
                                                (float*)work.p, wpf, st))) return rc;

@@ -436,6 +436,114 @@ int lcb_noise_var_dispatch(const PsfArgs& A, cudaStream_t st) {
     return LCB_ERR_ARG;
 }
 
+// ---------------------------------------------------------------- K5b: Monte-Carlo noise propagation
+// propagate_noise(model, noisemap, kwargs, ['starlet'], method='MC', num_samples, seed, likelihood_type='chi2') [R]:
+// for every sample draw z ~ N(0,1) per stamp pixel, push the chi2-gradient noise g = sum_i a_i A_i^T (sqrt(w_i) z_i) to
+// the grid (the same transposed passes as the gradient of the fit), take its starlet transform and accumulate the
+// squares; W_j = sqrt(mean).  Unlike the SLIT form this keeps the correlations of g between grid pixels.
+// Counter-based generator: every (seed, star, pixel, sample) hashes to its own normal deviate (reproducible, order free).
+__device__ __forceinline__ unsigned mc_mix(unsigned x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ float mc_normal(unsigned seed, unsigned item, unsigned sample) {
+    const unsigned h1 = mc_mix(mc_mix(seed ^ 0x9e3779b9U) + item * 0x85ebca6bU + mc_mix(sample * 0xc2b2ae35U + 0x27d4eb2fU));
+    const unsigned h2 = mc_mix(h1 ^ 0x165667b1U);
+    const float u1 = ((float)(h1 >> 8) + 0.5f) * (1.f / 16777216.f);       // (0, 1)
+    const float u2 = ((float)(h2 >> 8) + 0.5f) * (1.f / 16777216.f);
+    return sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
+}
+
+__device__ __forceinline__ float mc_atrous(const float* __restrict__ c, int nu, int v, int u, int D, int axis) {
+    const float h0 = 1.f / 16.f, h1 = 4.f / 16.f, h2 = 6.f / 16.f;
+    if (axis == 0) {
+        const float* row = c + v * nu;
+        return h0 * (row[max(u - 2 * D, 0)] + row[min(u + 2 * D, nu - 1)]) + h1 * (row[max(u - D, 0)] + row[min(u + D, nu - 1)]) + h2 * row[u];
+    }
+    return h0 * (c[max(v - 2 * D, 0) * nu + u] + c[min(v + 2 * D, nu - 1) * nu + u]) +
+           h1 * (c[max(v - D, 0) * nu + u] + c[min(v + D, nu - 1) * nu + u]) + h2 * c[v * nu + u];
+}
+
+template <int K, int G>
+__global__ void __launch_bounds__(PSF_THREADS) k_noise_mc(PsfArgs A, float* W, int n_samples, unsigned seed, int frame0) {
+    using P = LcbPass<K, G>;
+    extern __shared__ __align__(16) float sm[];
+    const int n = A.n, nu = A.nu, nn = n * n, pp = nu * nu, tid = threadIdx.x, J = A.J;
+    const int ldt = n + 1, ldb = nu + 1;
+    const int f = blockIdx.x;
+    const int i0 = A.star_off[f], N = A.star_off[f + 1] - i0;
+    const float fk = (float)K;
+    float* taps = sm;                                // [Nmax][2][GE_MAX]  ey, ex
+    float* wT = taps + A.Nmax * 2 * LCB_GE_MAX;      // [n][ldt]
+    float* Vbar = wT + n * ldt;                      // [n][ldb]
+    float* Gp = A.work + (size_t)f * A.work_per_frame;   // gradient-noise plane, then c_j
+    float* C1 = Gp + pp;
+    float* Wf = W + (size_t)f * J * pp;              // accumulators, then the weights
+    (void)frame0;
+    for (int idx = tid; idx < N * 2 * P::GE; idx += PSF_THREADS) {
+        const int st = idx / (2 * P::GE), rem = idx % (2 * P::GE), which = rem / P::GE, p = rem % P::GE;
+        const float c = fk * (which ? A.x0[i0 + st] : A.y0[i0 + st]);
+        const float ic = floorf(c + 0.5f);
+        float e, de;
+        lcb_tap(A.cv, K, c - ic, p, e, de);
+        taps[(st * 2 + which) * LCB_GE_MAX + p] = e;
+    }
+    for (int i = tid; i < J * pp; i += PSF_THREADS) Wf[i] = 0.f;
+    __syncthreads();
+    for (int smp = 0; smp < n_samples; ++smp) {
+        for (int i = tid; i < pp; i += PSF_THREADS) Gp[i] = 0.f;
+        __syncthreads();
+        for (int st = 0; st < N; ++st) {
+            const float a = A.a[i0 + st];
+            const float cx = fk * A.x0[i0 + st], cy = fk * A.y0[i0 + st];
+            const int icx = (int)floorf(cx + 0.5f), icy = (int)floorf(cy + 0.5f);
+            const float* ws = A.weight + (size_t)(i0 + st) * nn;
+            for (int i = tid; i < nn; i += PSF_THREADS)
+                wT[(i % n) * ldt + i / n] = sqrtf(ws[i]) * mc_normal(seed, (unsigned)((i0 + st) * nn + i), (unsigned)smp);
+            __syncthreads();
+            lcb_pass2T<K, G>(wT, ldt, nu, n, icx, taps + (st * 2 + 1) * LCB_GE_MAX, Vbar, ldb, tid, PSF_THREADS);
+            __syncthreads();
+            lcb_pass1T<K, G>(Vbar, ldb, nu, n, icy, taps + (st * 2) * LCB_GE_MAX, tid, PSF_THREADS,
+                             [&](int v, int u, float val) { Gp[v * nu + u] = fmaf(a, val, Gp[v * nu + u]); });
+            __syncthreads();
+        }
+        for (int j = 0; j < J; ++j) {
+            const int D = 1 << j;
+            for (int i = tid; i < pp; i += PSF_THREADS) C1[i] = mc_atrous(Gp, nu, i / nu, i % nu, D, 0);
+            __syncthreads();
+            for (int i = tid; i < pp; i += PSF_THREADS) {
+                const float nxt = mc_atrous(C1, nu, i / nu, i % nu, D, 1);
+                const float al = Gp[i] - nxt;
+                Wf[(size_t)j * pp + i] = fmaf(al, al, Wf[(size_t)j * pp + i]);
+                Gp[i] = nxt;                         // in place: Gp[i] is only read by the owner of pixel i in this pass
+            }
+            __syncthreads();
+        }
+    }
+    const float inv = 1.f / (float)n_samples;
+    for (int i = tid; i < J * pp; i += PSF_THREADS) Wf[i] = sqrtf(Wf[i] * inv);
+}
+
+template <int K, int G>
+static int launch_nmc(const PsfArgs& A, float* W, int n_samples, unsigned seed, cudaStream_t st) {
+    const size_t smem = (size_t)(A.Nmax * 2 * LCB_GE_MAX + A.n * (A.n + 1) + A.n * (A.nu + 1)) * 4;
+    LCB_CUDA(cudaFuncSetAttribute(k_noise_mc<K, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { LcbProfScope ps("k_noise_mc", st); k_noise_mc<K, G><<<A.F, PSF_THREADS, smem, st>>>(A, W, n_samples, seed, 0); }
+    LCB_CUDA(cudaGetLastError());
+    return LCB_OK;
+}
+
+// W: [A.F][J][nu^2] of the frames of this chunk
+int lcb_noise_mc_dispatch(const PsfArgs& A, float* W, int n_samples, unsigned seed, cudaStream_t st) {
+    const int G = A.cv.G;
+#define CASE(KK, GG) if (A.k == KK && G == GG) return launch_nmc<KK, GG>(A, W, n_samples, seed, st);
+    CASE(1, 12) CASE(2, 12) CASE(3, 12) CASE(4, 12)
+    CASE(2, 8) CASE(2, 16)
+#undef CASE
+    lcb_set_error("noise weights (MC): unsupported (subsampling_factor=%d, gauss_taps=%d)", A.k, G);
+    return LCB_ERR_ARG;
+}
+
 // tab: [J][3][nu] 1-D kernels f_j^2, f_j f_{j+1}, f_{j+1}^2 (host-computed, clamped cascade of a
 // Dirac at nu/2).  W[f][j] = sqrt(max(0, sep(f_j^2) - 2 sep(f_j f_j+1) + sep(f_j+1^2))) of the
 // variance plane at work[f] (written by k_noise_var or by the caller).

@@ -64,12 +64,13 @@ def _clone_f32(x, ref):
 
 def psf_fit_batch(data, weight, star_off, k, moffat0, a0, x00=None, y00=None, background0=None,
                   W=None, n_iter_analytic=100, n_iter_adabelief=3000, lr=1e-3,
-                  lam_scales=1.0, lam_hf=1.0, noise_weights=False, bounds=None,
+                  lam_scales=1.0, lam_hf=1.0, noise_weights=False, bounds=None, mc_samples=100, mc_seed=1,
                   want=('narrow_psf', 'full_psf', 'residuals', 'chi2', 'loss_hist', 'status')):
     """K1: ragged batch of per-frame PSF fits (lcb_psf_fit_batch).
 
     data, weight (sumN,n,n); star_off (F+1,) CSR offsets; moffat0 (F,5) = fwhm_x, fwhm_y, phi, beta, C
     guesses; a0 (sumN,).  ``want`` lists optional outputs (see lcb_psf_out in include/lcb.h).
+    noise_weights: False (W from the caller, None == 1), True / 'SLIT' (diagonal propagation), 'MC' (mc_samples draws).
     Returns a dict with moffat, a, x0, y0, background and the requested outputs.
     """
     _lib.require_device()
@@ -96,8 +97,9 @@ def psf_fit_batch(data, weight, star_off, k, moffat0, a0, x00=None, y00=None, ba
         out[nm] = empty_like_kind(data, shapes[nm], 'i' if nm == 'status' else 'f')
     b = bounds or {}
     opts = _lib.PsfOpts(int(n_iter_analytic), int(n_iter_adabelief), float(lr), float(lam_scales), float(lam_hf),
-                        int(bool(noise_weights)), float(b.get('fwhm_min', 1.0)), float(b.get('fwhm_max', n / 2.0)),
-                        float(b.get('beta_min', 1.1)), float(b.get('beta_max', 12.0)))
+                        (2 if noise_weights == 'MC' else int(bool(noise_weights))), float(b.get('fwhm_min', 1.0)),
+                        float(b.get('fwhm_max', n / 2.0)), float(b.get('beta_min', 1.1)), float(b.get('beta_max', 12.0)),
+                        int(mc_samples), int(mc_seed) & 0xffffffff)
     bi = _lib.PsfBatch(F, ptr(star_off), n, k, ptr(data), ptr(weight), ptr(W))
     bo = _lib.PsfOut(*[ptr(out.get(nm)) for nm in _lib.PSF_OUT_FIELDS])
     rc = _lib.lib.lcb_psf_fit_batch(C.byref(bi), C.byref(opts), C.byref(bo), mem, current_stream(data))

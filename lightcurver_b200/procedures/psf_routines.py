@@ -33,11 +33,14 @@ def build_psf_batch(images, noisemaps, subsampling_factor, masks=None, n_iter_an
                     n_iter_adabelief=2000, guess_method_star_position='barycenter', guess_fwhm_pixels=3.,
                     field_distortion=False, stamp_coordinates=None, regularization_strength_scales=None,
                     regularization_strength_hf=None, adabelief_learning_rate=None,
-                    conventions: Conventions = DEFAULT, return_dicts=True):
+                    conventions: Conventions = DEFAULT, return_dicts=True, noise_propagation='SLIT', noise_samples=100,
+                    noise_seed=1):
     """Fits F frames in one library call.
 
     images / noisemaps / masks: sequences (length F) of arrays (N_f, n, n) -- N_f may differ per
     frame (psf_modelling.py:144-153 drops stars per frame).  guess_fwhm_pixels: scalar or (F,).
+    noise_propagation: 'SLIT' (deterministic diagonal propagation, default) or 'MC' (``noise_samples`` noise draws, the
+    method STARRED's build_psf passes to propagate_noise [R]); both give the starlet-space weights W of stage 2.
     Returns a list of per-frame result dicts shaped like STARRED's (``return_dicts``), or the raw
     batched arrays.
     """
@@ -71,7 +74,7 @@ def build_psf_batch(images, noisemaps, subsampling_factor, masks=None, n_iter_an
     out = engine.psf_fit_batch(
         data, weight, prep['star_off'], k, moffat0, a0, x00, y00, n_iter_analytic=n_iter_analytic,
         n_iter_adabelief=n_iter_adabelief, lr=cv.psf_stage2_lr if adabelief_learning_rate is None else adabelief_learning_rate,
-        lam_scales=lam_s, lam_hf=lam_h, noise_weights=True,
+        lam_scales=lam_s, lam_hf=lam_h, noise_weights=noise_propagation, mc_samples=noise_samples, mc_seed=noise_seed,
         bounds=dict(fwhm_min=cv.moffat_fwhm_min, fwhm_max=n / 2.0, beta_min=cv.moffat_beta_min, beta_max=cv.moffat_beta_max),
         want=('narrow_psf', 'full_psf', 'residuals', 'chi2', 'loss_hist', 'loss_hist_analytic', 'status'))
     out = {kk: v.cpu().numpy() for kk, v in out.items()}            # one device -> host copy per product

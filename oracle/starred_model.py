@@ -180,6 +180,30 @@ def psf_noise_weights(weight, a, x0, y0, n, k, cv: Conventions = DEFAULT, dtype=
     return starlet_noise_levels(var)
 
 
+def psf_noise_weights_mc_limit(weight, a, x0, y0, n, k, cv: Conventions = DEFAULT, dtype=torch.float64):
+    """The limit (num_samples -> infinity) of ``propagate_noise(..., method='MC')`` for the PSF grid [R]: draw noise
+    maps n_i ~ N(0, sigma_i^2), push them to the grid as the chi2-gradient noise g = sum_i a_i A_i^T (n_i / sigma_i^2),
+    take the starlet transform, W_j = std of the coefficients.  Exactly: W_j[p]^2 = sum_q,q' Phi_j[p,q] Cov_g[q,q']
+    Phi_j[p,q'] with Cov_g = sum_i a_i^2 A_i^T diag(w_i) A_i -- the SLIT form (psf_noise_weights) keeps only the
+    diagonal of Cov_g.  Dense linear algebra: small grids only."""
+    weight = _const(weight, dtype)
+    a, x0, y0 = _const(a, dtype), _const(x0, dtype), _const(y0, dtype)
+    N, nu = weight.shape[0], n * k
+    Ay = shift_matrix(k * y0, n, k, cv)               # (N, n, nu)
+    Ax = shift_matrix(k * x0, n, k, cv)
+    # B maps the N*n*n white unit-variance draws to the grid: g = sum_i a_i Ay_i^T (sqrt(w_i) z_i) Ax_i
+    cols = []
+    for i in range(N):
+        Bi = torch.einsum('yv,xu->vuyx', Ay[i], Ax[i]) * (a[i] * torch.sqrt(weight[i]))[None, None]
+        cols.append(Bi.reshape(nu * nu, n * n))
+    B = torch.cat(cols, dim=1)                         # (nu^2, N n^2)
+    J = starlet_n_scales(nu)
+    # starlet of every column of B (linear), then the row norms
+    planes = B.T.reshape(-1, nu, nu)
+    al, _ = starlet(planes, J)                         # (N n^2, J, nu, nu)
+    return torch.sqrt((al ** 2).sum(0))
+
+
 # ----------------------------------------------------------------------------------------------
 # PSF loss (A.2)
 # ----------------------------------------------------------------------------------------------

@@ -254,3 +254,36 @@ def test_psf_cluster_kernel_parity(cuda_device, monkeypatch, n, k, N):
     assert np.median(np.abs(oc['background'] - og['background'])) <= 1e-6
     np.testing.assert_allclose(oc['narrow_psf'], og['narrow_psf'], atol=1e-3 * og['narrow_psf'].max())
     np.testing.assert_allclose(oc['chi2'], og['chi2'], rtol=1e-3)
+
+
+def test_psf_noise_weights_monte_carlo(cuda_device):
+    """propagate_noise(method='MC') on the device (k_noise_mc, counter-based generator) converges to the exact
+    full-covariance limit computed by the oracle; it is reproducible for a given seed and differs from the SLIT
+    (diagonal) form, which over-weights the finest scale."""
+    from lightcurver_b200 import engine
+    from oracle import starred_model as sm
+    n, k, N, F = 8, 2, 3, 2
+    nu = n * k
+    rng = np.random.default_rng(11)
+    weight = rng.uniform(0.5, 2.0, (F, N, n, n)).astype(np.float32)
+    weight[0, 1, 2, 3] = 0.0
+    data = rng.normal(0, 1, (F, N, n, n)).astype(np.float32)
+    a = rng.uniform(50, 100, (F, N)).astype(np.float32)
+    x0 = rng.uniform(-0.5, 0.5, (F, N)).astype(np.float32)
+    y0 = rng.uniform(-0.5, 0.5, (F, N)).astype(np.float32)
+    off = np.arange(F + 1, dtype=np.int32) * N
+    moffat = np.stack([np.full(F, 3.0), np.full(F, 3.0), np.zeros(F), np.full(F, 2.5), np.ones(F)], -1)
+
+    def run(mode, samples=6000, seed=3):
+        return engine.psf_fit_batch(_flat(data), _flat(weight), off, k, moffat, a.ravel(), x0.ravel(), y0.ravel(),
+                                    n_iter_analytic=0, n_iter_adabelief=0, noise_weights=mode, mc_samples=samples, mc_seed=seed,
+                                    want=('W_out',))['W_out']
+    Wmc = run('MC')
+    for f in range(F):
+        Wl = sm.psf_noise_weights_mc_limit(weight[f], a[f], x0[f], y0[f], n, k).numpy()
+        big = Wl > 0.02 * Wl.max()
+        np.testing.assert_allclose(Wmc[f][big], Wl[big], rtol=0.08)
+    assert np.array_equal(Wmc, run('MC')) and not np.array_equal(Wmc, run('MC', seed=4))
+    Wslit = run('SLIT')
+    ratio = np.median((Wmc / Wslit).reshape(F, -1, nu * nu), axis=-1)
+    assert (ratio[:, 0] < 0.8).all() and (ratio[:, -1] > 1.5).all()       # correlated gradient noise: less power at the finest scale
