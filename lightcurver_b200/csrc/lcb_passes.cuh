@@ -246,3 +246,50 @@ __device__ __forceinline__ void lcb_pass1T(const float* __restrict__ Vbar, int l
         }
     }
 }
+
+
+// pass 1^T accumulating into a plane that lives in GLOBAL memory (grids too large for shared memory):
+// Gp[v][u] += a * sum_Y ey[v'-K Y] Vbar[Y][u].  Same blocking as lcb_pass1T, but the UB values of Gp a task updates
+// are loaded together BEFORE the first store -- one L2 round trip per task instead of UB dependent ones.
+template <int K, int G, int OBV = 4>
+__device__ __forceinline__ void lcb_pass1T_rmw(const float* __restrict__ Vbar, int ldb, int nu, int n, int icy,
+                                               const float* __restrict__ ey_s, float a, float* __restrict__ Gp,
+                                               int tid, int nthreads) {
+    using P = LcbPass<K, G, OBV>;
+    constexpr int UB = K * P::OB;
+    constexpr int ILO = -((P::GE - 1 + K - 1) / K);
+    float ey[P::GE];
+    lcb_load_taps<P::GE>(ey_s, ey);
+    const int off = icy + G / 2;
+    const int S0 = K * lcb_floordiv(off, K);
+    const int nb = (nu + K - 1 + UB - 1) / UB;          // covers every row (no trailing loop)
+    for (int task = tid; task < nu * nb; task += nthreads) {
+        const int u = task % nu;
+        const int V0 = S0 + UB * (task / nu);
+        const int YB0 = lcb_floordiv(V0, K);
+        float old[UB];
+#pragma unroll
+        for (int j = 0; j < UB; ++j) {
+            const int v = V0 + j - off;
+            old[j] = (v >= 0 && v < nu) ? Gp[v * nu + u] : 0.f;
+        }
+        float acc[UB];
+#pragma unroll
+        for (int j = 0; j < UB; ++j) acc[j] = 0.f;
+#pragma unroll
+        for (int i = ILO; i < P::OB; ++i) {
+            const int Y = YB0 + i;
+            const float bv = (Y >= 0 && Y < n) ? Vbar[Y * ldb + u] : 0.f;
+#pragma unroll
+            for (int j = 0; j < UB; ++j) {
+                const int p = j - K * i;
+                if (p >= 0 && p < P::GE) acc[j] = fmaf(ey[p], bv, acc[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < UB; ++j) {
+            const int v = V0 + j - off;
+            if (v >= 0 && v < nu) Gp[v * nu + u] = fmaf(a, acc[j], old[j]);
+        }
+    }
+}

@@ -75,6 +75,132 @@ __device__ __forceinline__ float atrous_adj_line(const float* __restrict__ base,
 }
 
 
+// ---------------------------------------------------------------- in-place starlet regulariser for large grids
+// Grids whose seven planes do not fit in shared memory (BASELINE cfg5: 192 x 192) keep them in the L2 / HBM workspace,
+// where every one of the 35 stencil passes per iteration is a latency-bound gather.  Here ONE plane lives in shared
+// memory (in the star-pass scratch, which is dead during this phase; leading dimension nu + 1: conflict free along rows
+// and columns) and every dilated 5-tap pass runs IN PLACE: a thread owns one residue class mod D of one line and sweeps
+// it with a rolling register window of original values (the classes of a line are independent except through the
+// edge-replicated / folded border pixels, whose original values or folded sums are saved before the sweep).  Global
+// traffic per scale drops to coalesced streams: c_j read once, t_j written once and read twice.
+// Returns the per-thread partial of the regulariser; leaves d reg / d b in the global plane C0g (after a barrier).
+template <bool ADJ>
+__device__ __forceinline__ void starlet_sweep(float* __restrict__ base, int stride, int nu, int D, int r, float edgeL, float edgeR) {
+    const float h0 = 1.f / 16.f, h1 = 4.f / 16.f, h2 = 6.f / 16.f;
+    const int m = (nu - r + D - 1) / D;
+    float p2 = ADJ ? 0.f : edgeL, p1 = p2;
+    auto ldo = [&](int i) -> float { const int u = r + i * D; return (u < nu) ? base[u * stride] : (ADJ ? 0.f : edgeR); };
+    float c = ldo(0), n1 = ldo(1);
+    for (int i = 0; i < m; ++i) {
+        const float n2 = ldo(i + 2);
+        float out = h2 * c + h1 * (p1 + n1) + h0 * (p2 + n2);
+        const int u = r + i * D;
+        if (ADJ) { if (u == 0) out = edgeL; else if (u == nu - 1) out = edgeR; }
+        base[u * stride] = out;
+        p2 = p1; p1 = c; c = n1; n1 = n2;
+    }
+}
+
+// folded border value of H^T for one end of a line: h0 (P0 + S1 + S2) + h1 (P0 + S1) + h2 P0, S1 / S2 = sums of the
+// elements at distance 1..D / D+1..2D from that end (one warp per line end)
+__device__ __forceinline__ float starlet_fold(const float* __restrict__ base, int stride, int nu, int D, int side, int lane) {
+    float S1 = 0.f, S2 = 0.f;
+    for (int r = lane + 1; r <= 2 * D && r <= nu - 1; r += 32) {
+        const float x = base[(side ? nu - 1 - r : r) * stride];
+        if (r <= D) S1 += x; else S2 += x;
+    }
+    S1 = warp_sum(S1); S2 = warp_sum(S2);
+    const float P0 = base[(side ? nu - 1 : 0) * stride];
+    return (1.f / 16.f) * ((P0 + S1) + S2) + (4.f / 16.f) * (P0 + S1) + (6.f / 16.f) * P0;
+}
+
+template <int NTH>
+__device__ __forceinline__ float starlet_reg_inplace(const float* __restrict__ Bp, float* __restrict__ C0g, float* __restrict__ Tj,
+                                                     const float* __restrict__ Wf, float* __restrict__ P, float* __restrict__ side,
+                                                     int nu, int J, float lam_hf, float lam_scales, int tid) {
+    const int pp = nu * nu, ld = nu + 1;
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr int NWP = NTH / 32;
+    constexpr int UQ = 8;        // pixels per lane and trip of the point-wise passes: their global loads are issued together
+    float* eA = side;            // [nu] left / top edge values (forward: originals, adjoint: folded sums)
+    float* eB = side + nu;       // [nu] right / bottom
+    float reg = 0.f;
+    // point-wise passes walk (row = warp, column = lane + 32 q): coalesced in global memory, conflict free in P, no division
+#define LCB_PW_LOOP(BODY_LOAD, BODY_USE)                                              \
+    for (int v = warp; v < nu; v += NWP)                                              \
+        for (int u0 = lane; u0 < nu; u0 += 32 * UQ) {                                 \
+            _Pragma("unroll") for (int q = 0; q < UQ; ++q) { const int u = u0 + 32 * q; const int i = v * nu + u; const bool ok = u < nu; BODY_LOAD }   \
+            _Pragma("unroll") for (int q = 0; q < UQ; ++q) { const int u = u0 + 32 * q; const int i = v * nu + u; const int o = v * ld + u; if (u < nu) { BODY_USE } }  \
+        }
+    {
+        float bv[UQ];
+        LCB_PW_LOOP(bv[q] = ok ? Bp[i] : 0.f;, P[o] = bv[q]; (void)i;)
+    }
+    __syncthreads();
+    for (int j = 0; j < J; ++j) {
+        const int D = 1 << j;
+        const float* cur = (j == 0) ? Bp : C0g;
+        for (int axis = 0; axis < 2; ++axis) {            // rows (axis 0), then columns
+            const int ls = axis ? 1 : ld, es = axis ? ld : 1;           // stride between lines / along a line
+            for (int l = tid; l < nu; l += NTH) { eA[l] = P[l * ls]; eB[l] = P[l * ls + (nu - 1) * es]; }
+            __syncthreads();
+            for (int t = tid; t < nu * D; t += NTH) {
+                const int l = t % nu, r = t / nu;
+                starlet_sweep<false>(P + l * ls, es, nu, D, r, eA[l], eB[l]);
+            }
+            __syncthreads();
+        }
+        const float lam = (j == 0) ? lam_hf : lam_scales;
+        const float* Wj = Wf ? Wf + (size_t)j * pp : nullptr;
+        float* Tw = Tj + (size_t)j * pp;
+        const bool keep = j < J - 1;
+        {
+            float cu[UQ], wv[UQ];
+            LCB_PW_LOOP(cu[q] = ok ? cur[i] : 0.f; wv[q] = (ok && Wj) ? __ldg(Wj + i) : 1.f;,
+                        const float nxt = P[o]; const float al = cu[q] - nxt; const float lw = lam * wv[q];
+                        reg = fmaf(lw, fabsf(al), reg);
+                        Tw[i] = (al > 0.f) ? lw : (al < 0.f) ? -lw : 0.f;
+                        if (keep) C0g[i] = nxt;)
+        }
+        __syncthreads();
+    }
+    // adjoint recursion: g_J = 0; g_j = t_j + H_j^T (g_{j+1} - t_j)
+    for (int j = J - 1; j >= 0; --j) {
+        const int D = 1 << j;
+        const float* T = Tj + (size_t)j * pp;
+        const bool first = (j == J - 1);
+        {
+            float tv[UQ];
+            LCB_PW_LOOP(tv[q] = ok ? T[i] : 0.f;, P[o] = (first ? 0.f : P[o]) - tv[q]; (void)i;)
+        }
+        __syncthreads();
+        for (int axis = 1; axis >= 0; --axis) {           // columns, then rows
+            const int ls = axis ? 1 : ld, es = axis ? ld : 1;
+            for (int b = warp; b < 2 * nu; b += NWP) {
+                const int l = b >> 1, sd = b & 1;
+                const float fv = starlet_fold(P + l * ls, es, nu, D, sd, lane);
+                if (lane == 0) (sd ? eB : eA)[l] = fv;
+            }
+            __syncthreads();
+            for (int t = tid; t < nu * D; t += NTH) {
+                const int l = t % nu, r = t / nu;
+                starlet_sweep<true>(P + l * ls, es, nu, D, r, eA[l], eB[l]);
+            }
+            __syncthreads();
+        }
+        {
+            float tv[UQ];
+            LCB_PW_LOOP(tv[q] = ok ? T[i] : 0.f;, P[o] += tv[q]; (void)i;)
+        }
+        __syncthreads();
+    }
+    for (int v = warp; v < nu; v += NWP)
+        for (int u = lane; u < nu; u += 32) C0g[v * nu + u] = P[v * ld + u];
+#undef LCB_PW_LOOP
+    __syncthreads();
+    return reg;
+}
+
 // ---------------------------------------------------------------- fast starlet regulariser
 // Compile-time grid side NU (32 or 64, PSF_THREADS % NU == 0): thread <-> (column u, ROWS consecutive rows),
 // no integer division, clamped indices hoisted, sign(alpha_j) kept as int8 planes in shared memory
@@ -589,6 +715,7 @@ __global__ void __launch_bounds__(FIT_THREADS(K, NS), ((NS) > 0 ? 2 : 1)) k_psf_
             PHASE(3)
             auto emit = [&](int v, int u, float val) { GR[v * nu + u] = fmaf(a, val, GR[v * nu + u]); };
             if (hal) lcb_pass1T<K, G, FAST, (FAST ? 8 : 4)>(Vbar, ldb, nu, n, icy, tp, tid, NT, emit);
+            else if (!FAST && !A.planes_in_smem) lcb_pass1T_rmw<K, G>(Vbar, ldb, nu, n, icy, tp, a, GR, tid, NT);   // gradient plane in L2
             else lcb_pass1T<K, G, false>(Vbar, ldb, nu, n, icy, tp, tid, NT, emit);
         }
         __syncthreads();
@@ -619,6 +746,8 @@ __global__ void __launch_bounds__(FIT_THREADS(K, NS), ((NS) > 0 ? 2 : 1)) k_psf_
                 if constexpr (NS * K == 64) reg = starlet_reg_fast4<NT>(Bp, C0, C1, sg, aux, Wf, A.lam_hf, A.lam_scales, J, tid);
                 else reg = starlet_reg_fast<NS * K, NT>(Bp, C0, C1, sg, aux, Wf, A.lam_hf, A.lam_scales, J, tid);
             }
+        } else if (do_reg && !A.planes_in_smem && scr_count >= nu * (nu + 1) + 2 * nu) {
+            reg = starlet_reg_inplace<NT>(Bp, C0, Tj, Wf, scr, scr + nu * (nu + 1), nu, J, A.lam_hf, A.lam_scales, tid);
         } else if (do_reg) {
             for (int j = 0; j < J; ++j) {
                 const int D = 1 << j;
@@ -654,6 +783,19 @@ __global__ void __launch_bounds__(FIT_THREADS(K, NS), ((NS) > 0 ? 2 : 1)) k_psf_
         }
         PHASE(5)
         // ---- total gradient, norm, loss
+        if (!FAST && !A.planes_in_smem) {                // planes in L2: loads of 8 pixels in flight
+            constexpr int UG = 8;
+            for (int i0 = tid; i0 < pp; i0 += UG * NT) {
+                float gv[UG], cv0[UG];
+#pragma unroll
+                for (int q = 0; q < UG; ++q) { const int i = i0 + q * NT; gv[q] = (i < pp) ? GR[i] : 0.f; cv0[q] = (i < pp && do_reg) ? C0[i] : 0.f; }
+#pragma unroll
+                for (int q = 0; q < UG; ++q) {
+                    const int i = i0 + q * NT;
+                    if (i < pp) { const float g = sc * gv[q] + cv0[q]; GR[i] = g; gn2 = fmaf(g, g, gn2); }
+                }
+            }
+        } else
         for (int i = tid; i < pp; i += NT) {
             const float g = sc * GR[i] + (do_reg ? C0[i] : 0.f);
             GR[i] = g;
@@ -696,6 +838,25 @@ __global__ void __launch_bounds__(FIT_THREADS(K, NS), ((NS) > 0 ? 2 : 1)) k_psf_
                     belief_update(bc, cs * GR[i], b, mu[q], nv[q]);
                     Bp[i] = b; MU[i] = mu[q]; NU[i] = nv[q];
                     S[i] = sf[q] + b;
+                }
+            }
+        } else if (!A.planes_in_smem) {                   // planes in L2: loads of 4 pixels in flight
+            constexpr int UQ = 4;
+            for (int i0 = tid; i0 < pp; i0 += UQ * NT) {
+                float bq[UQ], mu[UQ], nv[UQ], gq[UQ], sf[UQ];
+#pragma unroll
+                for (int q = 0; q < UQ; ++q) {
+                    const int i = min(i0 + q * NT, pp - 1);
+                    bq[q] = Bp[i]; mu[q] = MU[i]; nv[q] = NU[i]; gq[q] = GR[i]; sf[q] = __ldg(sfix + i);
+                }
+#pragma unroll
+                for (int q = 0; q < UQ; ++q) {
+                    const int i = i0 + q * NT;
+                    if (i < pp) {
+                        belief_update(bc, cs * gq[q], bq[q], mu[q], nv[q]);
+                        Bp[i] = bq[q]; MU[i] = mu[q]; NU[i] = nv[q];
+                        S[i] = sf[q] + bq[q];
+                    }
                 }
             }
         } else {
