@@ -121,16 +121,17 @@ __device__ __forceinline__ float starlet_reg_inplace(const float* __restrict__ B
     const int pp = nu * nu, ld = nu + 1;
     const int lane = tid & 31, warp = tid >> 5;
     constexpr int NWP = NTH / 32;
-    constexpr int UQ = 8;        // pixels per lane and trip of the point-wise passes: their global loads are issued together
+    constexpr int UQ = 16;       // pixels per lane and trip of the point-wise passes: their global loads are issued together
     float* eA = side;            // [nu] left / top edge values (forward: originals, adjoint: folded sums)
     float* eB = side + nu;       // [nu] right / bottom
     float reg = 0.f;
     // point-wise passes walk (row = warp, column = lane + 32 q): coalesced in global memory, conflict free in P, no division
+    // (two rows per trip: q = 0..UQ/2-1 walks the columns of row v, q = UQ/2.. those of row v + NWP)
 #define LCB_PW_LOOP(BODY_LOAD, BODY_USE)                                              \
-    for (int v = warp; v < nu; v += NWP)                                              \
-        for (int u0 = lane; u0 < nu; u0 += 32 * UQ) {                                 \
-            _Pragma("unroll") for (int q = 0; q < UQ; ++q) { const int u = u0 + 32 * q; const int i = v * nu + u; const bool ok = u < nu; BODY_LOAD }   \
-            _Pragma("unroll") for (int q = 0; q < UQ; ++q) { const int u = u0 + 32 * q; const int i = v * nu + u; const int o = v * ld + u; if (u < nu) { BODY_USE } }  \
+    for (int v0 = warp; v0 < nu; v0 += 2 * NWP)                                       \
+        for (int u0 = lane; u0 < nu; u0 += 32 * (UQ / 2)) {                           \
+            _Pragma("unroll") for (int q = 0; q < UQ; ++q) { const int v = v0 + (q / (UQ / 2)) * NWP; const int u = u0 + 32 * (q % (UQ / 2)); const int i = v * nu + u; const bool ok = (u < nu) && (v < nu); BODY_LOAD }   \
+            _Pragma("unroll") for (int q = 0; q < UQ; ++q) { const int v = v0 + (q / (UQ / 2)) * NWP; const int u = u0 + 32 * (q % (UQ / 2)); const int i = v * nu + u; const int o = v * ld + u; if ((u < nu) && (v < nu)) { BODY_USE } }  \
         }
     {
         float bv[UQ];
