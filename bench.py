@@ -137,7 +137,7 @@ def cpu_baseline_run(sample_frames=8, t1=20, t2=200, tphot=200):
     n_lbfgs = max(1, int(np.mean([len(r['loss_hist']) for r in st1])))
     per_frame = (t_stage1 * CFG['T1'] / n_lbfgs + t_w + t_stage2 * CFG['T2'] / t2 + t_phot * CFG['Tphot'] / tphot) / sample_frames
     return dict(value=1.0 / per_frame, unit="frames/s", cores=cores, kind="port",
-                sample=f"{sample_frames} frames x {N} stars of cfg2; oracle (restated STARRED model, PyTorch CPU f32 + autograd, "
+                sample=f"{sample_frames} frames x {N} stars x {n}x{n} (subsampling {k}) of the workload; oracle (restated STARRED model, PyTorch CPU f32 + autograd, "
                        f"scipy L-BFGS-B f64): stage1 {n_lbfgs} its {t_stage1:.2f}s, W {t_w:.2f}s, stage2 {t2} its {t_stage2:.2f}s, "
                        f"phot {tphot} its {t_phot:.2f}s; scaled linearly to {CFG['T1']}/{CFG['T2']}/{CFG['Tphot']} iterations",
                 seconds=t_stage1 + t_w + t_stage2 + t_phot)
@@ -281,8 +281,9 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--frames', type=int, default=CFG['F'], help=argparse.SUPPRESS)
     ap.add_argument('--no-cpu-baseline', action='store_true', help=argparse.SUPPRESS)
-    ap.add_argument('--workload', default='psfphot', choices=['psfphot', 'deconv'],
-                    help='psfphot (default, BASELINE cfg2) or deconv (cfg4: joint deconvolution iterations/s, epochs sharded over ranks)')
+    ap.add_argument('--workload', default='psfphot', choices=['psfphot', 'deconv', 'cfg5'],
+                    help='psfphot (default, BASELINE cfg2), deconv (cfg4: joint deconvolution iterations/s, epochs sharded over ranks) '
+                         'or cfg5 (PSF + photometry at the large-survey shapes: 64x64 stamps, subsampling 3, 30 stars; one 148-frame wave per GPU)')
     ap.add_argument('--iters-per-step', type=int, default=50, help=argparse.SUPPRESS)
     ap.add_argument('--comm', default='p2p', choices=['p2p', 'nccl'], help=argparse.SUPPRESS)
     args = ap.parse_args()
@@ -290,6 +291,13 @@ def main():
         return run_reference(args)
     if args.workload == 'deconv':
         return run_deconv(args)
+    global METRIC
+    if args.workload == 'cfg5':
+        # BASELINE cfg5 is 20,000 frames; throughput is linear in the number of 148-frame waves, so one wave per GPU is timed
+        CFG.update(F=148, N=30, n=64, k=3)
+        METRIC = "frames/sec PSF+photometry fit (cfg5 shapes: 30 stars x 64x64, ss3, Moffat+grid; one 148-frame wave per GPU)"
+        if args.frames == 1000:
+            args.frames = 148
 
     import torch
     import torch.distributed as dist
@@ -310,7 +318,8 @@ def main():
     nu = n * k
 
     # ---- synthetic workload (seed differs per rank: every rank owns its own frames)
-    d = synthetic.make_psf_frames(F, N, n, k, seed=synthetic.SEEDS['cfg2'] + rank)
+    cfg_name = 'cfg5' if args.workload == 'cfg5' else 'cfg2'
+    d = synthetic.make_psf_frames(F, N, n, k, seed=synthetic.SEEDS[cfg_name] + rank)
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     h_data, h_nm, h_mask = pin(d['data']), pin(d['noisemap']), pin(d['masks'])
     fwhm_guess = d['fwhm'] * np.random.default_rng(1).uniform(0.9, 1.1, F)
@@ -419,8 +428,9 @@ def main():
         pass
     traffic = None
     try:
-        tj = json.load(open(ROOT / 'profiles' / 'k_psf_fit_traffic.json'))      # from the committed ncu --set full capture
-        traffic = tj['dram_bytes_per_launch'] * F / tj['frames']              # per launch of F frames
+        if args.workload == 'psfphot':
+            tj = json.load(open(ROOT / 'profiles' / 'k_psf_fit_traffic.json'))      # from the committed ncu --set full capture
+            traffic = tj['dram_bytes_per_launch'] * F / tj['frames']              # per launch of F frames
     except Exception:
         pass
     hbm_ach = algorithmic_bytes_per_frame() * F / (fit_ms_per_launch * 1e-3) / 1e9 if fit_ms_per_launch > 0 else 0.0
@@ -428,10 +438,10 @@ def main():
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step_max, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"cfg2: {F} frames x {N} stars x {n}x{n} per GPU, subsampling {k}: PSF fit (Moffat LM<= {CFG['T1']} its, "
+        "config": {"workload": f"{cfg_name}: {F} frames x {N} stars x {n}x{n} per GPU, subsampling {k}: PSF fit (Moffat LM<= {CFG['T1']} its, "
                                f"SLIT noise weights, {CFG['T2']} AdaBelief its on the {nu}x{nu} grid) + photometry of the same stars "
                                f"({CFG['Tphot']} AdaBelief its)", **{kk: (F if kk == 'F' else v) for kk, v in CFG.items()},
-                   "l2": "256 MiB buffer written between timed steps (L2 flush)", "seed": synthetic.SEEDS['cfg2'],
+                   "l2": "256 MiB buffer written between timed steps (L2 flush)", "seed": synthetic.SEEDS[cfg_name],
                    "quality": {"psf_chi2_median": chi2_med, "phot_chi2_median": phot_chi2_med}},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -447,7 +457,7 @@ def main():
         "wall_s_timed_region": t_wall,
     }
     if not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"] = cpu_baseline_run()
+        line["cpu_baseline"] = cpu_baseline_run(**(dict(sample_frames=1, t1=4, t2=20, tphot=20) if args.workload == 'cfg5' else {}))
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
