@@ -48,6 +48,8 @@ def build_psf_batch(images, noisemaps, subsampling_factor, masks=None, n_iter_an
         raise NotImplementedError("field_distortion=True is a 'next' row (SURVEY.md section 8f rank 3); "
                                   "run with field_distortion: false")
     cv = conventions
+    from ..conventions import apply_to_library
+    apply_to_library(cv)                       # the kernels read the library-wide conventions at call time
     F = len(images)
     k = int(subsampling_factor)
     counts = [int(np.shape(im)[0]) for im in images]

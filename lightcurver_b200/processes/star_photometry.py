@@ -45,6 +45,8 @@ def do_one_star_forward_modelling(data, noisemap, psf, subsampling_factor, n_ite
                                   conventions: Conventions = DEFAULT):
     """See lightcurver/processes/star_photometry.py:23-151.  data, noisemap (E,n,n); psf (E,n*k,n*k)."""
     cv = conventions
+    from ..conventions import apply_to_library
+    apply_to_library(cv)
     k = int(subsampling_factor)
     E, n = data.shape[0], data.shape[-1]
     # star_photometry.py:47-49 -- IN PLACE on the caller's arrays, like the reference
@@ -119,6 +121,8 @@ def star_photometry_batch(data, noisemap, psfs, subsampling_factor, n_iter=2000,
     Returns dict(fluxes, fluxes_uncertainties, chi2_per_frame (F,S), dx, dy, scale (S,), loss_curve (S,T)).
     """
     cv = conventions
+    from ..conventions import apply_to_library
+    apply_to_library(cv)
     k = int(subsampling_factor)
     F, S, n, _ = data.shape
     # NaN / mask policies, per-star scale, initial flux guess and weights run on the device (lcb_phot_prepare_batch)
@@ -195,6 +199,8 @@ def do_star_photometry_batched(store, db, stars, frames_for_star, psf_ref_for_fr
     """
     logger = logging.getLogger('lightcurver.star_photometry')
     cv = DEFAULT
+    from ..conventions import apply_to_library
+    apply_to_library(cv)
     k = int(user_config['subsampling_factor'])
     n_iter = int(user_config['star_deconv_n_iter'])
     coupled = bool(user_config.get('star_photometry_uniform_background_per_epoch', False)

@@ -152,3 +152,79 @@ def test_device_prepare_matches_host_policies(cuda_device):
     np.testing.assert_allclose(prep['data'].cpu().numpy().reshape(F, S, n, n), d, rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(prep['weight'].cpu().numpy().reshape(F, S, n, n), 1.0 / s.astype(np.float64) ** 2, rtol=3e-6)
     np.testing.assert_allclose(prep['a0'].cpu().numpy().reshape(F, S), a_est, rtol=2e-5, atol=1e-4)
+
+
+def test_alternate_conventions_parity(cuda_device):
+    """Every recalled STARRED convention is a switch: with D_k = block SUM (what lightcurver's use of pixel sums as
+    initial_a and of `a` as the flux suggests) and chi2 without the 1/2, K2, K1 (fast and generic
+    path) and K3 still match the oracle to 1e-5."""
+    import dataclasses
+    from lightcurver_b200 import engine, _lib, synthetic
+    from lightcurver_b200.conventions import DEFAULT, apply_to_library
+    from lightcurver_b200.processes.roi_modelling import JointDeconvolution
+    from oracle import starred_model as sm
+    from oracle.conventions import DEFAULT as ODEF
+    cvp = dataclasses.replace(DEFAULT, downsample_mean=False, chi2_half=False)
+    cvo = dataclasses.replace(ODEF, downsample_mean=False, chi2_half=False)
+    rng = np.random.default_rng(8)
+    try:
+        apply_to_library(cvp)
+        # K2
+        n, k, F, S = 16, 2, 2, 3
+        d = synthetic.make_phot_frames(F, S, n, k, seed=4)
+        data = d['data'].reshape(F * S, n, n); w = (1.0 / d['noisemap'].reshape(F * S, n, n).astype(np.float64) ** 2).astype(np.float32)
+        idx = np.repeat(np.arange(F), S).astype(np.int32)
+        a0 = (data.sum((-1, -2)) * rng.uniform(0.8, 1.2, F * S)).astype(np.float32)
+        dx0 = rng.uniform(-0.5, 0.5, F * S).astype(np.float32); dy0 = rng.uniform(-0.5, 0.5, F * S).astype(np.float32)
+        out = engine.phot_fit_batch(data, w, d['psf'], idx, a0, k, n_iter=1, dx0=dx0, dy0=dy0, want_grad0=True)
+        L, (ga, gx, gy) = sm.phot_loss_grad(d['psf'][idx], data, w, a0, dx0, dy0, n, k, cv=cvo)
+        np.testing.assert_allclose(out['loss0'], L, rtol=1e-5)
+        g = np.stack([ga, gx, gy], -1)
+        np.testing.assert_allclose(out['grad0'], g, rtol=2e-5, atol=1e-5 * np.abs(g).max())
+        # K1, fast (32 x 2) and generic (18 x 3) paths
+        for (n, k, N) in [(32, 2, 3), (18, 3, 2)]:
+            Fp = 2
+            dd = synthetic.make_psf_frames(Fp, N, n, k, seed=20 + n)
+            sc = dd['data'].max() / 100.0
+            dat = (dd['data'] / sc).astype(np.float32); nm = (dd['noisemap'] / sc).astype(np.float32)
+            wt = (dd['masks'] / nm.astype(np.float64) ** 2).astype(np.float32)
+            nu = n * k
+            J = engine.starlet_scales(nu)
+            W = rng.uniform(0.5, 2.0, (Fp, J, nu, nu)).astype(np.float32)
+            b0 = (1e-4 * rng.standard_normal((Fp, nu, nu))).astype(np.float32)
+            a00 = (dat.sum((-1, -2)) * rng.uniform(0.9, 1.1, (Fp, N))).astype(np.float32)
+            x00 = rng.uniform(-0.6, 0.6, (Fp, N)).astype(np.float32); y00 = rng.uniform(-0.6, 0.6, (Fp, N)).astype(np.float32)
+            mof = np.stack([np.full(Fp, 3.2), np.full(Fp, 3.5), np.full(Fp, 0.3), np.full(Fp, 2.8), np.ones(Fp)], -1)
+            off = np.arange(Fp + 1, dtype=np.int32) * N
+            o = engine.psf_fit_batch(dat.reshape(-1, n, n), wt.reshape(-1, n, n), off, k, mof, a00.ravel(), x00.ravel(), y00.ravel(),
+                                     background0=b0, W=W, n_iter_analytic=0, n_iter_adabelief=1, lr=1e-5, lam_scales=0.7, lam_hf=1.3,
+                                     want=('loss0', 'grad_b0', 'grad_s0'))
+            s_fixed = sm.moffat_image(mof[:, 0], mof[:, 1], mof[:, 2], mof[:, 3], n, k).numpy()
+            L, (gb, ga, gx, gy) = sm.psf_loss_grad(s_fixed, b0, a00, x00, y00, dat, wt, W, n, k, 0.7, 1.3, cv=cvo)
+            np.testing.assert_allclose(o['loss0'], L, rtol=1e-5)
+            np.testing.assert_allclose(o['grad_b0'], gb, rtol=1e-5, atol=1e-5 * np.abs(gb).max())
+            gs = np.stack([ga, gx, gy], -1).reshape(-1, 3)
+            np.testing.assert_allclose(o['grad_s0'], gs, rtol=2e-5, atol=1e-5 * np.abs(gs).max(0).max())
+        # K3
+        import torch
+        E, n, k, M = 2, 16, 2, 2
+        nu = n * k
+        psf = sm.moffat_image(torch.tensor([3.0, 3.3]), torch.tensor([3.2, 3.1]), torch.tensor([0.2, 1.0]), torch.tensor([3.0, 2.7]), 12, k).numpy().astype(np.float32)
+        prm = dict(h=(0.05 * rng.standard_normal(nu * nu)).astype(np.float32), mean=rng.uniform(-0.01, 0.01, E).astype(np.float32),
+                   a=rng.uniform(20, 60, (E, M)).astype(np.float32), c_x=rng.uniform(-3, 3, M).astype(np.float32),
+                   c_y=rng.uniform(-3, 3, M).astype(np.float32), dx=rng.uniform(-1, 1, E).astype(np.float32), dy=rng.uniform(-1, 1, E).astype(np.float32))
+        alpha = rng.uniform(-0.1, 0.1, E).astype(np.float32)
+        dat3 = rng.standard_normal((E, n, n)).astype(np.float32); w3 = rng.uniform(0.5, 2.0, (E, n, n)).astype(np.float32)
+        jd = JointDeconvolution(dat3, w3, psf, k, M, cvp)
+        jd.set_params(alpha=alpha, **prm)
+        jd.set_reg(0.8, 1.2, 50.0, lam_pts=0.2, lam_fu=3.0, conventions=cvp)
+        g3 = jd.loss_grad()
+        jd.close()
+        L3, go = sm.deconv_loss_grad(prm, dict(alpha=alpha), psf, dat3, w3, None, n, k,
+                                     dict(lam_scales=0.8, lam_hf=1.2, lam_pos=50.0, lam_pts=0.2, lam_fu=3.0), cv=cvo)
+        assert abs(g3['loss'] - L3) <= 1e-5 * abs(L3)
+        for nm_ in ('h', 'mean', 'a', 'c_x', 'c_y', 'dx', 'dy'):
+            ref = go[nm_].reshape(-1)
+            np.testing.assert_allclose(g3[nm_].reshape(-1), ref, rtol=2e-5, atol=2e-5 * np.abs(ref).max(), err_msg=nm_)
+    finally:
+        apply_to_library(DEFAULT)
