@@ -57,6 +57,7 @@ def test_no_cpu_fallback(lcb):
 def test_product_does_not_import_oracle():
     import subprocess, sys
     code = ("import sys; import lightcurver_b200, lightcurver_b200.engine, lightcurver_b200.procedures.psf_routines, "
-            "lightcurver_b200.processes.star_photometry, lightcurver_b200.utilities.starred_utilities; "
+            "lightcurver_b200.processes.star_photometry, lightcurver_b200.processes.roi_modelling, lightcurver_b200.starred_api, "
+            "lightcurver_b200.utilities.starred_utilities; "
             "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), 'product imported the oracle'")
     subprocess.run([sys.executable, '-c', code], check=True, cwd=str(ROOT))
