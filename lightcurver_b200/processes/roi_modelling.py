@@ -261,7 +261,8 @@ def _finish(jd, hist, Wused, data, weight, psf, cv):
     for m in range(M):
         deconv += point_source_image(fin['a'][m], fin['c_x'][m] + fin['dx'][0], fin['c_y'][m] + fin['dy'][0], n, k, cv)
     return dict(kwargs_final=kw, model=fin['model'], loss_history=hist, W=Wused, flux_sigma=sig,
-                deconvolved_epoch0=(deconv, h2))
+                deconvolved_epoch0=(deconv, h2),
+                amplitude_per_flux=float(k * k if cv.downsample_mean else 1))     # kernel amplitude a = amplitude_per_flux * pixel-sum flux
 
 
 def joint_deconvolution(data, weight, psf, subsampling_factor, xs, ys, initial_a, n_iter=2000, lr=1e-4,
@@ -431,8 +432,9 @@ def get_fluxes_dataframe_from_model(result, data, noisemap, point_sources_names,
     sig = np.asarray(result['flux_sigma'])
     curves, d_curves = {}, {}
     for i, ps in enumerate(point_sources_names):
-        curve = fluxes[i::M] * model_scale
-        photon = sig[i::M] * model_scale
+        # fluxes in pixel-sum units (what `a * scale` is in the reference, roi_modelling.py:462)
+        curve = fluxes[i::M] * model_scale / result.get('amplitude_per_flux', 1.0)
+        photon = sig[i::M] * model_scale / result.get('amplitude_per_flux', 1.0)
         curves[ps] = curve
         d_curves[ps] = (photon ** 2 + (np.asarray(normalization_errors) * curve) ** 2) ** 0.5
     residuals = np.asarray(data) - np.asarray(result['model'])

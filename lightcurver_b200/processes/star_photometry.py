@@ -97,8 +97,10 @@ def do_one_star_forward_modelling(data, noisemap, psf, subsampling_factor, n_ite
     return {
         'scale': scale,
         'kwargs_final': kw,
-        'fluxes': scale * a,
-        'fluxes_uncertainties': scale * np.asarray(sigma),
+        # fluxes are reported as pixel sums (the unit of lightcurver's star_flux_in_frame.flux, star_photometry.py:128) whatever the
+        # normalisation of D_k in the kernels: with the block mean the amplitude a is k^2 x the flux
+        'fluxes': scale * a / (k * k if cv.downsample_mean else 1.0),
+        'fluxes_uncertainties': scale * np.asarray(sigma) / (k * k if cv.downsample_mean else 1.0),
         'chi2': float(chi2),
         'chi2_per_frame': np.array(chi2_per_frame),
         'loss_curve': list(np.asarray(loss_curve)),
@@ -136,8 +138,8 @@ def star_photometry_batch(data, noisemap, psfs, subsampling_factor, n_iter=2000,
     scale = prep['scale'].cpu().numpy()
     res = {
         'scale': scale,
-        'fluxes': out['a'].reshape(F, S) * scale[None],
-        'fluxes_uncertainties': out['sigma_a'].reshape(F, S) * scale[None],
+        'fluxes': out['a'].reshape(F, S) * scale[None] / (k * k if cv.downsample_mean else 1.0),          # pixel-sum units
+        'fluxes_uncertainties': out['sigma_a'].reshape(F, S) * scale[None] / (k * k if cv.downsample_mean else 1.0),
         'chi2_per_frame': out['chi2'].reshape(F, S),
         'dx': out['dx'].reshape(F, S), 'dy': out['dy'].reshape(F, S),
         'status': out['status'].reshape(F, S),
@@ -246,8 +248,8 @@ def do_star_photometry_batched(store, db, stars, frames_for_star, psf_ref_for_fr
             with np.errstate(divide='ignore', invalid='ignore'):
                 chi2_per_frame = np.nansum(residuals ** 2 / wk['noisemap'] ** 2, axis=(1, 2)) / n ** 2
             wk['result'] = {
-                'scale': wk['scale'], 'fluxes': wk['scale'] * out['a'][sl].astype(np.float64),
-                'fluxes_uncertainties': wk['scale'] * out['sigma_a'][sl].astype(np.float64),
+                'scale': wk['scale'], 'fluxes': wk['scale'] * out['a'][sl].astype(np.float64) / (k * k if cv.downsample_mean else 1.0),
+                'fluxes_uncertainties': wk['scale'] * out['sigma_a'][sl].astype(np.float64) / (k * k if cv.downsample_mean else 1.0),
                 'chi2': float(np.nanmean(chi2_per_frame)), 'chi2_per_frame': chi2_per_frame,
                 'loss_curve': list(out['loss_hist'][sl].astype(np.float64).sum(0)), 'residuals': wk['scale'] * residuals,
                 'kwargs_final': {'kwargs_analytic': {'c_x': np.zeros(1), 'c_y': np.zeros(1), 'dx': out['dx'][sl], 'dy': out['dy'][sl],

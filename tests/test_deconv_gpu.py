@@ -167,7 +167,7 @@ def test_model_roi_arrays_and_flux_table(cuda_device):
     assert list(df.columns) == ['mjd', 'zeropoint', 'reduced_chi2', 'seeing', 'sky_level_electron_per_second',
                                 'A_flux', 'A_d_flux', 'B_flux', 'B_d_flux']
     assert (df['reduced_chi2'] < 2).all() and resid.shape == p['data'].shape
-    np.testing.assert_allclose(df['A_flux'].values, a[:, 0] * 3.0, rtol=1e-6)
+    np.testing.assert_allclose(df['A_flux'].values, a[:, 0] * 3.0 / res['amplitude_per_flux'], rtol=1e-6)
     assert (df['A_d_flux'].values >= 0.01 * df['A_flux'].values - 1e-9).all()
     # the reference's default regularisation (pts_source 0.01, flux scatter 10 in both stages) runs and stays finite
     res2 = model_roi_arrays(p['data'].astype(np.float64) / scale, sig / scale, p['psf'], k, p['c_x'] + 0.2, p['c_y'] - 0.2,

@@ -65,7 +65,7 @@ def test_psf_then_photometry_drivers(cuda_device):
     for fid, gid, flux, sig, chi2 in rows:
         if (fid, gid) == (2, '1002'):
             continue                                    # the half-masked epoch: noise x1000, flux unconstrained
-        assert abs(flux / 4 - truth[(fid, gid)]) < 8 * sig / 4 + 0.05 * truth[(fid, gid)], (fid, gid, flux / 4, truth[(fid, gid)])
+        assert abs(flux - truth[(fid, gid)]) < 8 * sig + 0.05 * truth[(fid, gid)], (fid, gid, flux, truth[(fid, gid)])   # pixel-sum units
         assert sig > 0
     # upsert semantics (star_photometry.py:220-225): a redo refreshes flux and flux_uncertainty only
     db.execute("UPDATE star_flux_in_frame SET chi2 = -1, flux = 0")
