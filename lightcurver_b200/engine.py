@@ -160,3 +160,44 @@ def phot_prepare_batch(data, noisemap, masks, k, downsample_mean=True):
     po = _lib.PhotPrepareOut(*[ptr(out[nm_]) for nm_ in ('data', 'weight', 'a0', 'scale')])
     _lib.check(_lib.lib.lcb_phot_prepare_batch(C.byref(pi), C.byref(po), ptr(work), current_stream(d)), 'lcb_phot_prepare_batch')
     return out
+
+
+def resolve_devices(devices):
+    """devices: None / 1 (current device), 'all', an int count or a list of CUDA device indices -> list of indices."""
+    import torch
+    if devices is None or devices == 1:
+        return [torch.cuda.current_device()]
+    if devices == 'all':
+        return list(range(torch.cuda.device_count()))
+    if isinstance(devices, int):
+        return list(range(min(devices, torch.cuda.device_count())))
+    return [int(d) for d in devices]
+
+
+def split_by_work(work, parts):
+    """Contiguous partition of len(work) items into ``parts`` blocks of roughly equal total work (SURVEY.md section 8e:
+    'contiguous blocks of frames per GPU, balanced by sum N'); returns [(lo, hi), ...], empty blocks dropped."""
+    work = np.asarray(work, np.float64)
+    csum = np.concatenate([[0.0], np.cumsum(work)])
+    bounds = [0]
+    for p in range(1, parts):
+        bounds.append(int(np.searchsorted(csum, csum[-1] * p / parts)))
+    bounds.append(len(work))
+    bounds = np.maximum.accumulate(bounds)
+    return [(int(a), int(b)) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
+
+
+def fan_out(blocks, devices, fn):
+    """Runs fn(lo, hi) for every block on its own device from its own host thread (the library calls release the GIL;
+    no data-path collective: the items are independent) and returns the results in block order."""
+    import concurrent.futures
+    import torch
+    if len(blocks) == 1:
+        with torch.cuda.device(devices[0]):
+            return [fn(*blocks[0])]
+
+    def run(i):
+        with torch.cuda.device(devices[i % len(devices)]):
+            return fn(*blocks[i])
+    with concurrent.futures.ThreadPoolExecutor(max_workers=len(blocks)) as ex:
+        return list(ex.map(run, range(len(blocks))))

@@ -34,16 +34,40 @@ def build_psf_batch(images, noisemaps, subsampling_factor, masks=None, n_iter_an
                     field_distortion=False, stamp_coordinates=None, regularization_strength_scales=None,
                     regularization_strength_hf=None, adabelief_learning_rate=None,
                     conventions: Conventions = DEFAULT, return_dicts=True, noise_propagation='SLIT', noise_samples=100,
-                    noise_seed=1):
+                    noise_seed=1, devices=None):
     """Fits F frames in one library call.
 
     images / noisemaps / masks: sequences (length F) of arrays (N_f, n, n) -- N_f may differ per
     frame (psf_modelling.py:144-153 drops stars per frame).  guess_fwhm_pixels: scalar or (F,).
     noise_propagation: 'SLIT' (deterministic diagonal propagation, default) or 'MC' (``noise_samples`` noise draws, the
     method STARRED's build_psf passes to propagate_noise [R]); both give the starlet-space weights W of stage 2.
+    devices: None (current CUDA device), 'all', a count or a list of device indices: the frames are split into contiguous
+    blocks balanced by their star counts, one host thread per GPU, no collective (frames are independent).
     Returns a list of per-frame result dicts shaped like STARRED's (``return_dicts``), or the raw
     batched arrays.
     """
+    devs = engine.resolve_devices(devices)
+    if len(devs) > 1 and len(images) > 1:
+        counts = [int(np.shape(im)[0]) for im in images]
+        blocks = engine.split_by_work(counts, len(devs))
+        fw = np.broadcast_to(np.asarray(3.0 if guess_fwhm_pixels is None else guess_fwhm_pixels, dtype=np.float64), (len(images),))
+        kw = dict(n_iter_analytic=n_iter_analytic, n_iter_adabelief=n_iter_adabelief,
+                  guess_method_star_position=guess_method_star_position, field_distortion=field_distortion,
+                  regularization_strength_scales=regularization_strength_scales, regularization_strength_hf=regularization_strength_hf,
+                  adabelief_learning_rate=adabelief_learning_rate, conventions=conventions, return_dicts=return_dicts,
+                  noise_propagation=noise_propagation, noise_samples=noise_samples, noise_seed=noise_seed, devices=None)
+
+        def one(lo, hi):
+            return build_psf_batch(images[lo:hi], noisemaps[lo:hi], subsampling_factor, None if masks is None else masks[lo:hi],
+                                   guess_fwhm_pixels=fw[lo:hi], **kw)
+        parts = engine.fan_out(blocks, devs, one)
+        if return_dicts:
+            return [r for part in parts for r in part]
+        out = {kk: np.concatenate([part[kk] for part in parts]) for kk in parts[0] if kk != 'star_off'}
+        off = np.zeros(len(images) + 1, np.int32)
+        off[1:] = np.cumsum(counts)
+        out['star_off'] = off
+        return out
     if field_distortion:
         raise NotImplementedError("field_distortion=True is a 'next' row (SURVEY.md section 8f rank 3); "
                                   "run with field_distortion: false")

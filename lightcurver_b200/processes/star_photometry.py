@@ -111,7 +111,7 @@ def do_one_star_forward_modelling(data, noisemap, psf, subsampling_factor, n_ite
 
 
 def star_photometry_batch(data, noisemap, psfs, subsampling_factor, n_iter=2000, masks=None,
-                          conventions: Conventions = DEFAULT, want_residuals=False, want_loss_hist=True):
+                          conventions: Conventions = DEFAULT, want_residuals=False, want_loss_hist=True, devices=None):
     """Batched driver replacing the serial loop of do_star_photometry (star_photometry.py:257-366):
     every (frame, star) item of a footprint in ONE library call.
 
@@ -120,8 +120,21 @@ def star_photometry_batch(data, noisemap, psfs, subsampling_factor, n_iter=2000,
     noise 1e7, and the noise of an epoch with ANY masked pixel is multiplied by 1000).
     Per star the stack is scaled by its nanmax over all frames (:47-49) and a single background
     scalar enters the initial flux guess (:55-64).  Arrays are NOT modified in place.
+    devices: None (current CUDA device), 'all', a count or a list of device indices: the STARS are split over the GPUs
+    (every per-star quantity -- scale, background scalar -- needs all the epochs of that star), one host thread per GPU.
     Returns dict(fluxes, fluxes_uncertainties, chi2_per_frame (F,S), dx, dy, scale (S,), loss_curve (S,T)).
     """
+    devs = engine.resolve_devices(devices)
+    if len(devs) > 1 and data.shape[1] > 1:
+        blocks = engine.split_by_work(np.ones(data.shape[1]), len(devs))
+
+        def one(lo, hi):
+            return star_photometry_batch(data[:, lo:hi], noisemap[:, lo:hi], psfs, subsampling_factor, n_iter=n_iter,
+                                         masks=None if masks is None else masks[:, lo:hi], conventions=conventions,
+                                         want_residuals=want_residuals, want_loss_hist=want_loss_hist, devices=None)
+        parts = engine.fan_out(blocks, devs, one)
+        star_axis = dict(scale=0, loss_curve=0)
+        return {kk: np.concatenate([part[kk] for part in parts], axis=star_axis.get(kk, 1)) for kk in parts[0]}
     cv = conventions
     from ..conventions import apply_to_library
     apply_to_library(cv)

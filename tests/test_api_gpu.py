@@ -228,3 +228,31 @@ def test_alternate_conventions_parity(cuda_device):
             np.testing.assert_allclose(g3[nm_].reshape(-1), ref, rtol=2e-5, atol=2e-5 * np.abs(ref).max(), err_msg=nm_)
     finally:
         apply_to_library(DEFAULT)
+
+
+def test_in_process_multi_gpu_fan_out(cuda_device):
+    """build_psf_batch / star_photometry_batch with devices=2: frames (resp. stars) split over two GPUs from two host
+    threads of ONE process, no collective; results identical to the single-GPU call (items are independent)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    from lightcurver_b200 import synthetic, engine
+    from lightcurver_b200.procedures.psf_routines import build_psf_batch
+    from lightcurver_b200.processes.star_photometry import star_photometry_batch
+    assert engine.split_by_work([3, 1, 1, 1, 3, 3], 2) == [(0, 4), (4, 6)] and engine.split_by_work([1, 1], 4) == [(0, 1), (1, 2)]
+    F, N, n, k = 7, 4, 16, 2
+    d = synthetic.make_psf_frames(F, N, n, k, seed=5)
+    images = [d['data'][f][:N - (f % 2)] for f in range(F)]            # ragged
+    noise = [d['noisemap'][f][:N - (f % 2)] for f in range(F)]
+    masks = [d['masks'][f][:N - (f % 2)] for f in range(F)]
+    kw = dict(n_iter_analytic=30, n_iter_adabelief=60, guess_method_star_position='center', guess_fwhm_pixels=d['fwhm'])
+    one = build_psf_batch(images, noise, k, masks=masks, return_dicts=False, **kw)
+    two = build_psf_batch(images, noise, k, masks=masks, return_dicts=False, devices=2, **kw)
+    for key in ('narrow_psf', 'a', 'x0', 'chi2', 'loss_hist', 'moffat', 'norms', 'star_off'):
+        assert np.array_equal(one[key], two[key]), key
+    dicts = build_psf_batch(images, noise, k, masks=masks, devices='all', **kw)
+    assert len(dicts) == F and np.array_equal(dicts[3]['narrow_psf'], one['narrow_psf'][3])
+    p1 = star_photometry_batch(d['data'], d['noisemap'], one['narrow_psf'], k, n_iter=80, masks=d['masks'], want_residuals=True)
+    p2 = star_photometry_batch(d['data'], d['noisemap'], one['narrow_psf'], k, n_iter=80, masks=d['masks'], want_residuals=True, devices=[0, 1])
+    for key in p1:
+        assert np.array_equal(p1[key], p2[key]), key
