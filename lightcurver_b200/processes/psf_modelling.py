@@ -136,7 +136,7 @@ def check_psf_exists(db, frame_id, psf_ref, combined_footprint_hash):
 
 
 def model_all_psfs_batched(store, db, frames, stars_for_frame, user_config, combined_footprint_hash,
-                           automatic_mask_fn=mask_surrounding_stars, on_result=None):
+                           automatic_mask_fn=mask_surrounding_stars, on_result=None, devices=None):
     """One pass over ``frames`` (iterable of mappings with id, image_relpath, seeing_pixels, pixel_scale):
     gather every frame that needs a PSF, fit them all in ONE ``build_psf_batch`` call, then write the per-frame
     products to the store and the PSFs table in the original order.
@@ -179,7 +179,8 @@ def model_all_psfs_batched(store, db, frames, stars_for_frame, user_config, comb
                               n_iter_adabelief=user_config['psf_n_iter_pixels'],
                               guess_method_star_position='center',
                               guess_fwhm_pixels=np.array([float(p['frame']['seeing_pixels']) for p in pending]),
-                              field_distortion=user_config.get('field_distortion', False))
+                              field_distortion=user_config.get('field_distortion', False),
+                              devices=devices)          # None: current GPU; 'all': every visible GPU, one host thread each
     written = []
     for p, result in zip(pending, results):
         frame, psf_ref = p['frame'], p['psf_ref']
