@@ -12,23 +12,6 @@ from .. import engine
 from ..conventions import Conventions, DEFAULT
 
 
-def _guess_positions(img, mask, method):
-    """x0, y0 (data px, origin at the stamp centre) per star.  'center' is what lightcurver uses."""
-    N, n, _ = img.shape
-    if method == 'center':
-        return np.zeros(N), np.zeros(N)
-    ctr = (n - 1) / 2.0
-    if method == 'max':
-        flat = np.where(mask > 0, img, -np.inf).reshape(N, -1).argmax(-1)
-        return (flat % n) - ctr, (flat // n) - ctr
-    if method == 'barycenter':
-        w = np.clip(np.where(mask > 0, img, 0.0), 0.0, None)
-        tot = np.maximum(w.sum((-1, -2)), 1e-30)
-        ax = np.arange(n) - ctr
-        return (w.sum(-2) * ax).sum(-1) / tot, (w.sum(-1) * ax).sum(-1) / tot
-    raise ValueError(f"guess_method_star_position must be 'center', 'max' or 'barycenter' (got {method!r})")
-
-
 def build_psf_batch(images, noisemaps, subsampling_factor, masks=None, n_iter_analytic=40,
                     n_iter_adabelief=2000, guess_method_star_position='barycenter', guess_fwhm_pixels=3.,
                     field_distortion=False, stamp_coordinates=None, regularization_strength_scales=None,
