@@ -462,14 +462,12 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
             for (int x = 0; x < DC_XB; ++x) acc[x] = 0.f;
             if (valid) {
                 const int ia0 = s * ias, ia1 = min(NA, ia0 + ias);
+                // kernel rows whose f row Y + A0 + ia lies inside the stamp: a plain loop without per-row branches
+                const int ja = max(ia0, -(Y + A0)), jb = min(ia1, n - (Y + A0));
                 for (int ph = 0; ph < kk; ++ph) {
-                    const float* pl = fpl + ph * pst + X0 + A0;
+                    const float* pl = fpl + ph * pst + X0 + A0 + (Y + A0 - flo) * ld;
                     const float* Sph = Ssm + ph * NA * NAp;
-                    for (int ia = ia0; ia < ia1; ++ia) {
-                        const int row = Y + A0 + ia;
-                        if (row < 0 || row >= n) continue;
-                        corr_line(pl + (row - flo) * ld, Sph + ia * NAp, NA, NA8, acc);
-                    }
+                    for (int ia = ja; ia < jb; ++ia) corr_line(pl + ia * ld, Sph + ia * NAp, NA, NA8, acc);
                 }
             }
             for (int o = 32 / SPLIT; o < 32; o <<= 1) {
@@ -506,12 +504,11 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
         for (int x = 0; x < DC_XB; ++x) acc[x] = 0.f;
         const float* Sph = Ssm + ph * NA * NAp;
         const float* rbase = rsm + X0 - A0 - (NA8 - 1);
-        for (int ia = 0; ia < NA; ++ia) {
-            const int row = Y - A0 - ia;
-            if (row < 0 || row >= n) continue;
-            if (noise) conv_line_T<true>(rbase + (row - rlo) * ld, Sph + ia * NAp, NA, NA8, acc);
-            else conv_line_T<false>(rbase + (row - rlo) * ld, Sph + ia * NAp, NA, NA8, acc);
-        }
+        // kernel rows whose r row Y - A0 - ia lies inside the stamp
+        const int ja = max(0, Y - A0 - (n - 1)), jb = min(NA, Y - A0 + 1);
+        const float* rrow = rbase + (Y - A0 - rlo) * ld;
+        if (noise) { for (int ia = ja; ia < jb; ++ia) conv_line_T<true>(rrow - ia * ld, Sph + ia * NAp, NA, NA8, acc); }
+        else { for (int ia = ja; ia < jb; ++ia) conv_line_T<false>(rrow - ia * ld, Sph + ia * NAp, NA, NA8, acc); }
 #pragma unroll
         for (int x = 0; x < DC_XB; ++x)
             if (X0 + x < n) fpl[ph * pst + (Y - flo) * ld + X0 + x] = (noise ? dscale * dscale : dscale) * acc[x];
