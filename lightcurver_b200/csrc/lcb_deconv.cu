@@ -1225,6 +1225,8 @@ struct DeconvHandle {
     int n_sm, max_smem, smem_sm;
     int seq;                             // sequence number of the in-kernel all-reduce
     float *gh, *gcx, *ls;                // evaluation outputs (lcb_deconv_loss_grad / _get)
+    float* W_spare;                      // weight cube detached by set_reg(W = NULL), reused by the next one
+    float* noise_tab;                    // 1-D kernels of the starlet-space noise propagation
 };
 
 static int dalloc(DeconvHandle* H, void** p, size_t bytes, bool zero) {
@@ -1386,7 +1388,7 @@ int lcb_deconv_create(const lcb_deconv_problem* p, int mem, void* stream, void**
     DeconvHandle* H = new DeconvHandle();
     H->st = (cudaStream_t)stream;
     H->comm_buf = nullptr; H->CS = 0; H->CS_user = 0; H->seq = 0;
-    H->st2 = nullptr; H->ev_h = nullptr; H->ev_go = nullptr; H->ev_reg = nullptr; H->reg_pending = false; H->starlet_attr = false;
+    H->st2 = nullptr; H->ev_h = nullptr; H->ev_go = nullptr; H->ev_reg = nullptr; H->reg_pending = false; H->starlet_attr = false; H->noise_tab = nullptr; H->W_spare = nullptr;
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);     // the 8 starlet CTAs must get their SMs before the epoch grid fills the GPU
     if (cudaStreamCreateWithPriority(&H->st2, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
@@ -1557,9 +1559,9 @@ int lcb_deconv_set_reg(void* handle, const lcb_deconv_reg* r, int mem) {
     D.lam_pts = r->lam_pts; D.lam_fu = r->lam_fu; D.pts_all_epochs = r->pts_all_epochs; D.fu_relative = r->fu_relative;
     int rc;
     if (r->W) {
-        if (!D.W) { if ((rc = dalloc(H, (void**)&D.W, (size_t)D.J * pp * 4, false))) return rc; }
+        if (!D.W) { if (H->W_spare) { D.W = H->W_spare; H->W_spare = nullptr; } else if ((rc = dalloc(H, (void**)&D.W, (size_t)D.J * pp * 4, false))) return rc; }
         if ((rc = put(H, D.W, r->W, (size_t)D.J * pp, mem))) return rc;
-    } else D.W = nullptr;
+    } else { if (D.W) H->W_spare = D.W; D.W = nullptr; }
     D.has_prior = (r->prior_mu_x && r->prior_sig_x && r->prior_mu_y && r->prior_sig_y) ? 1 : 0;
     if (D.has_prior) {
         if ((rc = put(H, D.prior, r->prior_mu_x, D.M, mem)) || (rc = put(H, D.prior + D.M, r->prior_sig_x, D.M, mem)) ||
@@ -1683,13 +1685,16 @@ int lcb_deconv_noise_weights(void* handle, int stage, float* W_out, int mem) {
         if ((rc = launch_epoch(H, 2))) return rc;
         return launch_reduce(H, 1, 0);
     }
-    std::vector<float> tab;
-    lcb_build_noise_table(D.nu, D.J, tab);
-    float* tabd = nullptr;
-    if ((rc = dalloc(H, (void**)&tabd, tab.size() * 4, false))) return rc;
-    LCB_CUDA(cudaMemcpyAsync(tabd, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, H->st));
-    LCB_CUDA(cudaStreamSynchronize(H->st));
-    if (!D.W) { if ((rc = dalloc(H, (void**)&D.W, (size_t)D.J * pp * 4, false))) return rc; }
+    float* tabd = H->noise_tab;
+    if (!tabd) {                                     // built once per handle
+        std::vector<float> tab;
+        lcb_build_noise_table(D.nu, D.J, tab);
+        if ((rc = dalloc(H, (void**)&tabd, tab.size() * 4, false))) return rc;
+        LCB_CUDA(cudaMemcpyAsync(tabd, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, H->st));
+        LCB_CUDA(cudaStreamSynchronize(H->st));      // tab is a host temporary
+        H->noise_tab = tabd;
+    }
+    if (!D.W) { if (H->W_spare) { D.W = H->W_spare; H->W_spare = nullptr; } else if ((rc = dalloc(H, (void**)&D.W, (size_t)D.J * pp * 4, false))) return rc; }
     LCB_CUDA(cudaMemcpyAsync(D.planes, D.red, pp * 4, cudaMemcpyDeviceToDevice, H->st));
     if ((rc = lcb_noise_weights_launch(1, D.nu, D.J, tabd, D.W, D.planes, 2 * pp, H->st))) return rc;
     return get(H, W_out, D.W, (size_t)D.J * pp, mem);
