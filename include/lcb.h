@@ -9,7 +9,11 @@
  *   lcb_psf_fit_batch      psf_modelling.py:164-171    starred.procedures.psf_routines.build_psf
  *   lcb_psf_loss_grad      (same Loss object, one evaluation; used by parity tests)
  *   lcb_noise_weights      star_photometry.py:108, roi_modelling.py:299  propagate_noise(method='SLIT')
- *   lcb_deconv_*           roi_modelling.py:213-335    setup_model / Loss / Optimizer('adabelief').minimize
+ *   lcb_deconv_*           roi_modelling.py:213-335    setup_model / Loss (chi2, starlet-L1, positivity, prior, pts-source,
+ *                                                      flux uniformity) / Optimizer('adabelief').minimize / the loss-gradient
+ *                                                      pair of Optimizer('l-bfgs-b'); epochs shard over GPUs (lcb_deconv_comm_*)
+ *   lcb_psf_prepare_batch  psf_modelling.py:136-140 + build_psf's normalisation and smart guess (device-side data policies)
+ *   lcb_phot_prepare_batch star_photometry.py:47-64, 309-316 (scale, flux guess, NaN and mask rules)
  *
  * Conventions: all arrays are C-contiguous float32, row-major [item][y][x]; positions are in data
  * pixels with the origin at the stamp centre (n-1)/2 (roi_modelling.py:207-210).  `mem` selects
