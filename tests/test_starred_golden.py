@@ -24,3 +24,50 @@ def test_oracle_matches_starred_photometry_model():
                        torch.zeros(E, dtype=torch.float64), torch.zeros(E, dtype=torch.float64), n, k).numpy()
     np.testing.assert_allclose(m, g['model'], rtol=1e-4, atol=1e-4 * np.abs(g['model']).max(),
                                err_msg="restated forward model differs from STARRED: check Conventions (downsample_mean, gauss_*)")
+
+
+@pytest.mark.skipif(not FILES, reason="no STARRED golden vectors (run tools/dump_starred_vectors.py where STARRED is installed)")
+def test_oracle_matches_starred_deconvolution_terms():
+    """Every term of the deconvolution Loss against real STARRED (values dumped term by term): reports which variant of
+    each uncertain convention matches, so that flipping a field of Conventions pins the restatement."""
+    import dataclasses
+    import itertools
+    import torch
+    from oracle import starred_model as sm
+    from oracle.conventions import DEFAULT
+    f = GOLD / 'starred_deconv_terms_n16_k2.npz'
+    if not f.exists():
+        pytest.skip("deconvolution term vector absent")
+    g = np.load(f)
+    n, k, E, M = int(g['n']), int(g['k']), int(g['E']), int(g['M'])
+    t = lambda v: torch.tensor(np.asarray(v), dtype=torch.float64)
+    ka = {kk: g[f'kw_kwargs_analytic_{kk}'] for kk in ('c_x', 'c_y', 'dx', 'dy', 'a', 'alpha')}
+    kb = {kk: g[f'kw_kwargs_background_{kk}'] for kk in ('h', 'mean')}
+    W = g['W'][:sm.starlet_n_scales(n * k)]
+    weight = 1.0 / g['noisemap'] ** 2
+    report, ok = [], True
+    for mean, half in itertools.product((True, False), (True, False)):
+        cv = dataclasses.replace(DEFAULT, downsample_mean=mean, chi2_half=half)
+        args = (t(kb['h']).reshape(n * k, n * k), t(kb['mean']), t(ka['a']).reshape(E, M), t(ka['c_x']), t(ka['c_y']), t(ka['dx']), t(ka['dy']),
+                t(ka['alpha']), t(g['psf']), t(g['data']), t(weight), t(W), n, k)
+        chi = float(sm.deconv_loss(*args, cv=cv))
+        report.append((f"downsample_mean={mean} chi2_half={half}", chi, float(g['loss_chi2'])))
+    # STARRED returns the negative log-likelihood up to its sign convention: compare magnitudes
+    matches = [r for r in report if abs(abs(r[1]) - abs(r[2])) <= 1e-4 * abs(r[2])]
+    assert matches, f"no (downsample_mean, chi2_half) variant reproduces STARRED's chi2 term: {report}"
+    mean = 'downsample_mean=True' in matches[0][0]
+    half = 'chi2_half=True' in matches[0][0]
+    for name, kwv, variants in (('starlet_scales', dict(lam_scales=1.0), [{}]), ('starlet_hf', dict(lam_hf=1.0), [{}]),
+                                ('positivity', dict(lam_pos=100.0), [{}]),
+                                ('pts_source', dict(lam_pts=0.5), [dict(pts_source_all_epochs=True), dict(pts_source_all_epochs=False)]),
+                                ('flux_uniformity', dict(lam_fu=5.0), [dict(flux_uniformity_relative=True), dict(flux_uniformity_relative=False)])):
+        want = abs(float(g['loss_' + name])) - abs(float(g['loss_chi2']))
+        got = []
+        for var in variants:
+            cv = dataclasses.replace(DEFAULT, downsample_mean=mean, chi2_half=half, **var)
+            val = float(sm.deconv_loss(*args, cv=cv, **kwv)) - float(sm.deconv_loss(*args, cv=cv))
+            got.append((var, val))
+        if not any(abs(v - want) <= 1e-3 * max(abs(want), 1e-12) for _, v in got):
+            ok = False
+            report.append((name, want, got))
+    assert ok, f"terms of the deconvolution Loss that no restated variant reproduces (STARRED value, restated variants): {report}"

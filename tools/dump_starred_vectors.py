@@ -72,6 +72,39 @@ def main():
     np.savez_compressed(out / 'starred_phot_n16_k2.npz', kind='starred_phot', n=n, k=k, data=data, noisemap=nm, psf=p['psf'],
                         args=np.asarray(x0), loss=float(val), grad=np.asarray(grad), model=np.asarray(model.model(kwargs_init)),
                         a=np.asarray(kwargs_init['kwargs_analytic']['a']))
+    # --- joint deconvolution: every term of the Loss separately at a non-trivial point (roi_modelling.py:275-321), and the
+    #     SLIT weights (roi_modelling.py:299).  tests/test_starred_golden.py tells which Conventions field matches.
+    from starred.utils.noise_utils import propagate_noise
+    rng = np.random.default_rng(7)
+    E, M = 3, 2
+    d3 = rng.normal(0.0, 0.02, (E, n, n)) + 0.05
+    nm3 = np.full((E, n, n), 0.02)
+    xs, ys = np.array([-2.0, 2.5]), np.array([1.0, -1.5])
+    a3 = rng.uniform(1.0, 2.0, E * M)
+    model, kwargs_init, kwargs_up, kwargs_down, kwargs_fixed = setup_model(d3, nm3 ** 2, p['psf'][:1].repeat(E, 0).astype(np.float64),
+                                                                           xs, ys, k, list(a3))
+    kw = {'kwargs_analytic': dict(kwargs_init['kwargs_analytic']), 'kwargs_background': dict(kwargs_init['kwargs_background']),
+          'kwargs_sersic': {}}
+    kw['kwargs_analytic']['dx'] = rng.uniform(-0.5, 0.5, E); kw['kwargs_analytic']['dy'] = rng.uniform(-0.5, 0.5, E)
+    kw['kwargs_background']['h'] = 0.01 * rng.standard_normal((n * k) ** 2)
+    kw['kwargs_background']['mean'] = rng.uniform(-0.01, 0.01, E)
+    fixed = {'kwargs_analytic': {'alpha': kwargs_init['kwargs_analytic']['alpha']}, 'kwargs_background': {}, 'kwargs_sersic': {}}
+    params = ParametersDeconv(kwargs_init=kw, kwargs_fixed=fixed, kwargs_up=kwargs_up, kwargs_down=kwargs_down)
+    W = np.asarray(propagate_noise(model, nm3, kwargs_init, wavelet_type_list=['starlet'], method='SLIT', num_samples=100, seed=1,
+                                   likelihood_type='chi2', verbose=False, upsampling_factor=k)[0])
+    x = jnp.asarray(params.kwargs2args(kw))
+    terms = {}
+    base = dict(regularization_terms='l1_starlet', regularization_strength_scales=0., regularization_strength_hf=0.,
+                regularization_strength_positivity=0., regularization_strength_pts_source=0., regularization_strength_flux_uniformity=0., W=W)
+    for name, over in (('chi2', {}), ('starlet_scales', dict(regularization_strength_scales=1.0)), ('starlet_hf', dict(regularization_strength_hf=1.0)),
+                       ('positivity', dict(regularization_strength_positivity=100.0)), ('pts_source', dict(regularization_strength_pts_source=0.5)),
+                       ('flux_uniformity', dict(regularization_strength_flux_uniformity=5.0))):
+        lo = DeconvLoss(d3, model, params, nm3 ** 2, **{**base, **over})
+        v, g = jax.value_and_grad(lo)(x)
+        terms['loss_' + name] = float(v); terms['grad_' + name] = np.asarray(g)
+    np.savez_compressed(out / 'starred_deconv_terms_n16_k2.npz', kind='starred_deconv_terms', n=n, k=k, E=E, M=M, data=d3, noisemap=nm3,
+                        psf=p['psf'][:1].repeat(E, 0), xs=xs, ys=ys, W=W, args=np.asarray(x), model=np.asarray(model.model(kw)),
+                        **{f'kw_{g_}_{kk}': np.asarray(v) for g_ in ('kwargs_analytic', 'kwargs_background') for kk, v in kw[g_].items()}, **terms)
     print('wrote', sorted(f.name for f in out.glob('starred_*.npz')))
 
 
