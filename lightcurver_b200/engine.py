@@ -164,6 +164,7 @@ def phot_prepare_batch(data, noisemap, masks, k, downsample_mean=True):
 
 def resolve_devices(devices):
     """devices: None / 1 (current device), 'all', an int count or a list of CUDA device indices -> list of indices."""
+    _lib.require_device()                        # no CPU fallback: fail loudly before touching torch.cuda
     import torch
     if devices is None or devices == 1:
         return [torch.cuda.current_device()]
