@@ -38,7 +38,7 @@ def _problem(E, n, k, M, P_data, seed, alpha_on=True, h_sigma=2.5, h_peak=0.5):
 
 @pytest.mark.parametrize("E,n,k,M,npsf,cs,alpha_on", [(3, 16, 2, 2, 12, 0, True), (2, 12, 3, 1, 12, 2, True), (2, 16, 1, 3, 15, 4, True),
                                                       (3, 16, 2, 2, 16, 1, True), (3, 16, 2, 2, 12, 4, False), (2, 32, 2, 3, 16, 8, True),
-                                                      (2, 32, 2, 3, 16, 8, False), (3, 20, 2, 2, 12, 4, True)])
+                                                      (2, 32, 2, 3, 16, 8, False), (3, 20, 2, 2, 12, 4, True), (2, 8, 4, 1, 8, 2, True)])
 def test_deconv_loss_grad_parity(cuda_device, E, n, k, M, npsf, cs, alpha_on):
     """Every cluster size (CTAs per epoch) of the per-epoch kernel, rotated and purely translated epochs, all loss terms."""
     from lightcurver_b200.processes.roi_modelling import JointDeconvolution
