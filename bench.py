@@ -42,7 +42,13 @@ def algorithmic_flops():
     psf = per_it * CFG['T2']
     phot_it = 10 * G * nu * nu + 3 * nu * nu + 18 * n * n
     phot = phot_it * CFG['Tphot'] * N
-    return dict(psf_per_frame=psf, phot_per_frame=phot, psf_per_it=per_it, phot_per_it_item=phot_it)
+    # flops the kernels EXECUTE per PSF iteration and frame: the k-box is folded into GE = G + k - 1 decimating
+    # taps, so one star costs 2 nu n GE (vertical, 2 kernels) + 3 n^2 GE (horizontal, 3 kernels) FMAs forward and n nu GE/k + nu^2 GE/k
+    # for the two transposed passes; the starlet is 2 x 2 five-tap passes per scale (+ the point-wise steps)
+    GE = G + k - 1
+    fma_star = 2 * nu * n * GE + 3 * n * n * GE + (n * nu * GE) // k + (nu * nu * GE) // k
+    fma_it = N * fma_star + J * (4 * 5 + 4) * nu * nu + 8 * (nu * nu + 3 * N)
+    return dict(psf_per_frame=psf, phot_per_frame=phot, psf_per_it=per_it, phot_per_it_item=phot_it, psf_executed_per_it=2 * fma_it)
 
 
 def algorithmic_bytes_per_frame():
@@ -548,6 +554,9 @@ def main():
                      "frac": achieved / fp32_peak if fp32_peak else None, "traffic": traffic,
                      "peak_source": "lcb_fp32_peak measured live (FFMA chains on all SMs); MEASURED_PEAKS.json has no FP32 SIMT figure",
                      "algorithmic_flop_per_launch": fl['psf_per_frame'] * F, "ms_per_launch": fit_ms_per_launch,
+                     "frac_executed": (achieved / fp32_peak if fp32_peak else 0.0) * fl['psf_executed_per_it'] / fl['psf_per_it'],
+                     "note": "frac uses SURVEY 8d's algorithmic count (full-resolution separable passes); frac_executed is the FP32 pipe "
+                             "utilisation on the flops the kernel executes after folding the k-box into the taps",
                      "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s",
                              "frac": (hbm_ach / hbm_peak) if hbm_peak else None, "peak_source": "MEASURED_PEAKS.json (of measured)"}},
         "wall_s_timed_region": t_wall,
