@@ -161,3 +161,21 @@ def test_sharded_lbfgsb_stage1_equals_unsharded():
         np.testing.assert_allclose(prm['dx'], ref[3]['dx'][lo:hi], atol=2e-3)
         M = 2
         np.testing.assert_allclose(prm['a'], ref[3]['a'][lo * M:hi * M], rtol=2e-3)
+
+
+def test_split_by_work_properties():
+    """In-process multi-GPU fan-out: contiguous blocks in order, every item exactly once, no empty
+    block, and no block heavier than the ideal share plus one item."""
+    sys.path.insert(0, str(ROOT))
+    from lightcurver_b200.engine import split_by_work
+    rng = np.random.default_rng(0)
+    for trial in range(200):
+        nitem = int(rng.integers(1, 40))
+        parts = int(rng.integers(1, 9))
+        work = rng.integers(1, 31, nitem)
+        blocks = split_by_work(work, parts)
+        assert 1 <= len(blocks) <= min(parts, nitem)
+        assert blocks[0][0] == 0 and blocks[-1][1] == nitem
+        assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:])) and all(hi > lo for lo, hi in blocks)
+        heaviest = max(work[lo:hi].sum() for lo, hi in blocks)
+        assert heaviest <= work.sum() / parts + work.max()
