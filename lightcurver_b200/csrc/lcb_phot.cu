@@ -25,7 +25,7 @@ struct PhotArgs {
 
 // NS > 0: compile-time stamp side (no integer divisions in the passes); NS == 0: runtime sizes.
 template <int K, int G, int NS>
-__global__ void __launch_bounds__(PHOT_THREADS, (NS > 0 ? 3 : 1)) k_phot_fit(PhotArgs A) {
+__global__ void __launch_bounds__(PHOT_THREADS, (NS > 0 ? 4 : 1)) k_phot_fit(PhotArgs A) {
     using P = LcbPass<K, G>;
     extern __shared__ __align__(16) float sm[];
     const int n = (NS > 0) ? NS : A.n, nu = (NS > 0) ? NS * K : A.nu, tid = threadIdx.x;
