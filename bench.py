@@ -119,7 +119,7 @@ def cpu_baseline_run(sample_frames=8, t1=20, t2=200, tphot=200):
     data = d['data'] / sc
     nm = d['noisemap'] / sc
     weight = d['masks'] / nm ** 2
-    a0 = (data * d['masks']).sum((-1, -2)) * k * k
+    a0 = (data * d['masks']).sum((-1, -2)) * sm.DEFAULT.amplitude_per_flux(k)
     nu = n * k
     sm.fit_psf_stage1(data[0], weight[0], n, k, float(d['fwhm'][0]), a0[0], 1)   # untimed: first-call overheads
     t0 = time.perf_counter()
@@ -433,7 +433,7 @@ def main():
     g_w = (torch.from_numpy(d['masks']).reshape(F * N, n, n).to(dev) / g_nm ** 2).contiguous()
     g_wphot = (1.0 / g_nm ** 2).contiguous()
     g_off = (torch.arange(F + 1, dtype=torch.int32) * N).to(dev)
-    g_a0 = ((g_data * (g_w > 0)).sum((-1, -2)) * (k * k)).contiguous()
+    g_a0 = ((g_data * (g_w > 0)).sum((-1, -2)) * APF).contiguous()
     g_mof = torch.tensor(np.stack([fwhm_guess, fwhm_guess, np.zeros(F), np.full(F, 2.5), np.ones(F)], -1), dtype=torch.float32).to(dev)
     g_idx = torch.arange(F, dtype=torch.int32).repeat_interleave(N).to(dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)

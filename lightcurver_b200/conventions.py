@@ -13,8 +13,10 @@ class Conventions:
     # point-source / PSF "target resolution" Gaussian: FWHM in upsampled pixels, number of taps (even)
     gauss_fwhm_up: float = 2.0
     gauss_taps: int = 12
-    # D_k: k x k block mean (True) or block sum (False)
-    downsample_mean: bool = True
+    # D_k: k x k block mean (True) or block sum (False).  Default SUM: lightcurver hands pixel sums to STARRED as initial
+    # amplitudes and reads the fitted amplitudes back as fluxes (star_photometry.py:55-69,128; roi_modelling.py:199-212,462;
+    # docs/example_starred_notebooks/example_roi_modelling.ipynb cells 13 -> 21 -> 36: a ~ sum of pixels / scale)
+    downsample_mean: bool = False
     # chi2 term carries a factor 1/2
     chi2_half: bool = True
     # optax chain used when schedule_learning_rate=True
@@ -45,6 +47,10 @@ class Conventions:
 
     def as_dict(self):
         return asdict(self)
+
+    def amplitude_per_flux(self, k):
+        """Amplitude of a point source per unit of pixel-sum flux: 1 with the block sum, k^2 with the block mean."""
+        return float(k * k) if self.downsample_mean else 1.0
 
 
 DEFAULT = Conventions()

@@ -1,8 +1,17 @@
 // lcb_api.cu -- library-wide state of liblcb: last error, conventions, staging arena, FP32 peak probe.
 #include "lcb_common.cuh"
 
+#include <mutex>
+#include <vector>
+#include <string>
+#include <map>
+
 static thread_local char g_err[512] = "";
-static lcb_conventions g_conv = {2.0f, 12, 1, 1, 1.0f, 0.99f, 0.9f, 0.999f, 1e-16f, 1e-16f};
+// Conventions are PER HOST THREAD (every thread starts from the defaults below and lcb_conventions_set only touches the
+// calling thread): engine.fan_out runs one host thread per GPU and each of them applies the conventions of its own call.
+// Defaults: D_k is the block SUM -- lightcurver passes pixel sums as initial amplitudes and reads the fitted amplitudes back
+// as fluxes (star_photometry.py:55-69,128; roi_modelling.py:199-212,462; notebook cells 13/21/36), see DESIGN.md section 2.
+static thread_local lcb_conventions g_conv = {2.0f, 12, 0, 1, 1.0f, 0.99f, 0.9f, 0.999f, 1e-16f, 1e-16f};
 
 void lcb_set_error(const char* fmt, ...) {
     va_list ap;
@@ -29,14 +38,35 @@ DevConv lcb_devconv() {
     return d;
 }
 
-static LcbArena g_arena;
-LcbArena& lcb_arena() { return g_arena; }
+// Staging arenas of the LCB_MEM_HOST calls: a pool of arenas per device behind one mutex.  A call leases an arena of the
+// current device for its duration (LcbArenaLease), so that concurrent host-pointer calls from several host threads -- on
+// the same or on different devices -- never share or free each other's staging memory.
+static std::mutex g_arena_mu;
+static std::vector<LcbArena*> g_arena_free;
+
+LcbArenaLease::LcbArenaLease() : a(nullptr) {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); d = 0; }
+    {
+        std::lock_guard<std::mutex> lk(g_arena_mu);
+        for (size_t i = 0; i < g_arena_free.size(); ++i)
+            if (g_arena_free[i]->dev == d) { a = g_arena_free[i]; g_arena_free.erase(g_arena_free.begin() + i); break; }
+    }
+    if (!a) { a = new LcbArena(); a->dev = d; }
+}
+LcbArenaLease::~LcbArenaLease() {
+    if (!a) return;
+    a->rewind();
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    g_arena_free.push_back(a);
+}
 
 int LcbArena::reserve(size_t bytes) {
     int d = 0;
     LCB_CUDA(cudaGetDevice(&d));
-    if (base && d == dev && cap >= bytes) return LCB_OK;
-    if (base) { cudaSetDevice(dev); cudaFree(base); cudaSetDevice(d); base = nullptr; cap = 0; }
+    LCB_REQUIRE(dev < 0 || d == dev, "staging arena of device %d used while device %d is current", dev, d);
+    if (base && cap >= bytes) return LCB_OK;
+    if (base) { cudaFree(base); base = nullptr; cap = 0; }
     size_t want = bytes + (bytes >> 2) + (1u << 20);
     cudaError_t e = cudaMalloc((void**)&base, want);
     if (e != cudaSuccess) {
@@ -56,24 +86,25 @@ void* LcbArena::take(size_t bytes) {
 }
 
 // ---------------------------------------------------------------- profiling
-#include <vector>
-#include <string>
-#include <map>
 struct ProfRec { const char* name; cudaEvent_t e0, e1; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
+static std::mutex g_prof_mu;          // launches may come from several host threads (one per GPU)
 
 LcbProfScope::LcbProfScope(const char* name, cudaStream_t s) : idx(-1), st(s) {
     if (!g_prof_on) return;
     ProfRec r; r.name = name;
     if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
     cudaEventRecord(r.e0, st);
+    e1 = r.e1;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     g_prof.push_back(r);
     idx = (int)g_prof.size() - 1;
 }
-LcbProfScope::~LcbProfScope() { if (idx >= 0) cudaEventRecord(g_prof[idx].e1, st); }
+LcbProfScope::~LcbProfScope() { if (idx >= 0) cudaEventRecord(e1, st); }
 
 extern "C" int lcb_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     for (ProfRec& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     g_prof.clear();
     g_prof_on = (on != 0);
@@ -83,6 +114,7 @@ extern "C" int lcb_profile_enable(int on) {
 extern "C" int lcb_profile_summary(char* buf, int buflen) {
     LCB_REQUIRE(buf && buflen > 2, "lcb_profile_summary: bad buffer");
     std::map<std::string, std::pair<double, int>> agg;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     for (ProfRec& r : g_prof) {
         float ms = 0.f;
         if (cudaEventSynchronize(r.e1) == cudaSuccess && cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {

@@ -26,20 +26,27 @@ const lcb_conventions& lcb_conv();
         if (!(cond)) { lcb_set_error(__VA_ARGS__); return LCB_ERR_ARG; }                 \
     } while (0)
 
-// Device staging arena for LCB_MEM_HOST calls: one growing allocation per process and device.
-// h2d()/alloc() hand out 256-byte aligned slices; release() rewinds (no free between calls).
+// Device staging arena for LCB_MEM_HOST calls: a growing allocation on ONE device; take() hands out 256-byte aligned
+// slices, rewind() releases them (no free between calls).  Calls lease an arena of the current device from a process-wide
+// pool for their duration (thread safe: two host threads never share an arena).
 struct LcbArena {
     char* base = nullptr; size_t cap = 0; size_t off = 0; int dev = -1;
     int reserve(size_t bytes);
     void* take(size_t bytes);
     void rewind() { off = 0; }
 };
-LcbArena& lcb_arena();
+struct LcbArenaLease {
+    LcbArena* a;
+    LcbArenaLease();
+    ~LcbArenaLease();
+    LcbArenaLease(const LcbArenaLease&) = delete;
+    LcbArenaLease& operator=(const LcbArenaLease&) = delete;
+};
 
 // Optional per-kernel timing (lcb_profile_enable): CUDA events recorded on the launch stream around
 // every kernel launch of the library; lcb_profile_summary() synchronises and aggregates by name.
 struct LcbProfScope {
-    int idx; cudaStream_t st;
+    int idx; cudaStream_t st; cudaEvent_t e1;
     LcbProfScope(const char* name, cudaStream_t s);
     ~LcbProfScope();
 };

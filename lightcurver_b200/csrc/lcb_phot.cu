@@ -231,7 +231,8 @@ extern "C" int lcb_phot_fit_batch(const lcb_phot_batch* in, const lcb_fit_opts* 
     }
     LCB_REQUIRE(mem == LCB_MEM_HOST, "mem must be LCB_MEM_DEVICE or LCB_MEM_HOST");
     // ---- host pointers: stage through the arena
-    LcbArena& ar = lcb_arena();
+    LcbArenaLease lease;
+    LcbArena& ar = *lease.a;
     const size_t nn = (size_t)n * n, pp = (size_t)nu * nu;
     size_t need = 2 * B * nn * 4 + (size_t)in->Fp * pp * 4 + (size_t)B * 4 * 16 + (size_t)B * nn * 4 +
                   (size_t)B * T * 4 + 64 * 256;

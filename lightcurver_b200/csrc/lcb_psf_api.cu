@@ -3,6 +3,7 @@
 #include "lcb_psf.cuh"
 #include <vector>
 #include <mutex>
+#include <atomic>
 
 size_t lcb_psf_fit_smem_small(int n, int nu, int Nmax);
 size_t lcb_psf_lm_smem_small(int n, int nu, int Nmax);
@@ -55,15 +56,17 @@ void lcb_build_noise_table(int nu, int J, std::vector<float>& tab) {
 // threshold (0) every call would hand ~400 MB of workspace back to the driver at the next synchronisation
 // and pay for a fresh allocation on the following call.
 static void keep_pool_cached() {
-    static int done_for = -1;
+    static std::atomic<unsigned long long> done_mask{0};     // one bit per device; host threads of several GPUs call this
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for) return;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+    const unsigned long long bit = 1ull << dev;
+    if (done_mask.load(std::memory_order_relaxed) & bit) return;
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
         unsigned long long thr = ~0ull;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
-    done_for = dev;
+    done_mask.fetch_or(bit, std::memory_order_relaxed);
 }
 
 struct DevTemp {       // stream-ordered temporary
@@ -226,7 +229,8 @@ extern "C" int lcb_psf_fit_batch(const lcb_psf_batch* in, const lcb_psf_opts* op
     size_t need = (size_t)(F + 1) * 4 + 2 * sumN * nn * 4 + (in->W || out->W_out ? (size_t)F * J * pp * 4 : 0) +
                   (size_t)F * 5 * 4 + 3 * (size_t)sumN * 4 + 4 * F * pp * 4 + sumN * nn * 4 + (size_t)F * 4 * 3 +
                   (size_t)F * (T1 + T2) * 4 + (size_t)sumN * 12 + 64 * 256;
-    LcbArena& ar = lcb_arena();
+    LcbArenaLease lease;
+    LcbArena& ar = *lease.a;
     int rc = ar.reserve(need);
     if (rc) return rc;
     ar.rewind();

@@ -125,7 +125,7 @@ def _to_device(x, dtype):
 GUESS_METHODS = {'center': 0, 'max': 1, 'barycenter': 2}
 
 
-def psf_prepare_batch(images, noisemaps, masks, star_off, k, norm_scale=100.0, downsample_mean=True, guess_method='center'):
+def psf_prepare_batch(images, noisemaps, masks, star_off, k, norm_scale=100.0, downsample_mean=False, guess_method='center'):
     """lcb_psf_prepare_batch: raw stamps (sumN,n,n) -> device tensors (data, weight, a0, x0, y0, norm)."""
     import torch
     _lib.require_device()
@@ -146,7 +146,7 @@ def psf_prepare_batch(images, noisemaps, masks, star_off, k, norm_scale=100.0, d
     return out
 
 
-def phot_prepare_batch(data, noisemap, masks, k, downsample_mean=True):
+def phot_prepare_batch(data, noisemap, masks, k, downsample_mean=False):
     """lcb_phot_prepare_batch: raw stamps (F,S,n,n) -> device tensors (data, weight (F*S,n,n), a0 (F*S,), scale (S,))."""
     import torch
     _lib.require_device()

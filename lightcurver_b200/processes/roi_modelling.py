@@ -41,14 +41,34 @@ class JointDeconvolution:
         self.E_total, self.e0 = self.E, 0
 
     def close(self):
+        """Frees the handle.  With comm='p2p' this is a COLLECTIVE call (device synchronise + barrier: nobody may unmap a
+        receive buffer a peer can still write to), so sharded users must call close() explicitly, or use the object as
+        a context manager, on every rank."""
         if getattr(self, 'handle', None):
-            if self.comm == 'p2p':              # nobody may unmap a receive buffer a peer can still write to
+            if self.comm == 'p2p':
                 import torch
                 import torch.distributed as dist
                 torch.cuda.synchronize()
                 dist.barrier(group=self.group)
             _lib.lib.lcb_deconv_destroy(self.handle)
             self.handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+    def __del__(self):
+        # finalisers run at garbage-collection / interpreter-shutdown time, which differs per rank: NO collective here.
+        # A connected p2p handle that was never closed is leaked on purpose (its receive buffer may still be mapped by peers).
+        try:
+            if getattr(self, 'handle', None) and self.comm != 'p2p':
+                _lib.lib.lcb_deconv_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
 
     # ---- multi-GPU ---------------------------------------------------------------------------
     def connect(self, group, comm='p2p'):
@@ -88,8 +108,6 @@ class JointDeconvolution:
             dist.all_gather_object(parts, sm_, group=self.group)
             sm_ = np.sum(parts, axis=0)
         return (sm_ / max(self.E_total, 1)).astype(np.float32)
-
-    __del__ = close
 
     # ---- parameters -------------------------------------------------------------------------
     def set_params(self, h=None, mean=None, a=None, c_x=None, c_y=None, dx=None, dy=None, alpha=None,
@@ -262,7 +280,7 @@ def _finish(jd, hist, Wused, data, weight, psf, cv):
         deconv += point_source_image(fin['a'][m], fin['c_x'][m] + fin['dx'][0], fin['c_y'][m] + fin['dy'][0], n, k, cv)
     return dict(kwargs_final=kw, model=fin['model'], loss_history=hist, W=Wused, flux_sigma=sig,
                 deconvolved_epoch0=(deconv, h2),
-                amplitude_per_flux=float(k * k if cv.downsample_mean else 1))     # kernel amplitude a = amplitude_per_flux * pixel-sum flux
+                amplitude_per_flux=cv.amplitude_per_flux(k))     # kernel amplitude a = amplitude_per_flux * pixel-sum flux (1 by default)
 
 
 def joint_deconvolution(data, weight, psf, subsampling_factor, xs, ys, initial_a, n_iter=2000, lr=1e-4,
@@ -381,9 +399,10 @@ def model_roi_arrays(data, noisemap, psf, subsampling_factor, xs, ys, initial_a,
     k = int(subsampling_factor)
     xs, ys = np.atleast_1d(np.asarray(xs, float)), np.atleast_1d(np.asarray(ys, float))
     M = len(xs)
-    with np.errstate(divide='ignore', invalid='ignore'):
-        weight = np.where(np.isfinite(noisemap) & (noisemap > 0), 1.0 / np.asarray(noisemap, np.float64) ** 2, 0.0).astype(np.float32)
-    d32 = np.nan_to_num(np.asarray(data, np.float32))
+    from .star_photometry import stamps_and_weights
+    d32, weight = stamps_and_weights(data, noisemap)
+    # initial_a are pixel-sum (aperture) fluxes (roi_modelling.py:199-212): amplitude = amplitude_per_flux x flux
+    initial_a = np.asarray(initial_a, np.float64) * cv.amplitude_per_flux(k)
     alpha = np.zeros(E) if angles_to_north is None else np.asarray(angles_to_north, float)
     h0 = None if starting_background is None else np.asarray(starting_background, np.float32).reshape(-1)
     fix_c = isinstance(fix_point_source_astrometry, bool) and fix_point_source_astrometry

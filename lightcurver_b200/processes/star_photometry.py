@@ -30,6 +30,21 @@ def _initial_flux_guess(data):
     return np.nansum(data, axis=(1, 2)) - data[0].size * background_values
 
 
+def stamps_and_weights(data, noisemap):
+    """The ONE weight rule of every host path of this package (the device rule of k_phot_prep_item is the same): a pixel
+    counts with weight 1/sigma^2 only where the data AND the noise are finite and the noise is positive; everywhere else
+    the stamp value is 0 and the weight 0 (the reference's `data 0, noise 1e7` for doubly-NaN pixels, star_photometry.py:
+    309-311, is the same thing to 1e-14 of a typical weight; a pixel where only the data is NaN would make STARRED's
+    loss NaN, here it is ignored).  Returns (float32 stamps, float32 weights); the inputs are not modified."""
+    d = np.asarray(data)
+    nm = np.asarray(noisemap, dtype=np.float64)
+    ok = np.isfinite(d) & np.isfinite(nm) & (nm > 0)
+    with np.errstate(divide='ignore', invalid='ignore', over='ignore'):
+        weight = np.where(ok, 1.0 / nm ** 2, 0.0)
+    weight = np.where(np.isfinite(weight), weight, 0.0)
+    return np.where(ok, d, 0.0).astype(np.float32), weight.astype(np.float32)
+
+
 def point_source_image(a, x, y, n, k, cv: Conventions = DEFAULT):
     """a * G(.; k x, k y) on the nu x nu grid (what model.getDeconvolved shows for a point source)."""
     nu = n * k
@@ -54,16 +69,13 @@ def do_one_star_forward_modelling(data, noisemap, psf, subsampling_factor, n_ite
     data /= scale
     noisemap /= scale
     a_est = _initial_flux_guess(data)
-    if cv.downsample_mean:
-        a_est = a_est * (k * k)
-    with np.errstate(divide='ignore', invalid='ignore'):
-        weight = np.where(np.isfinite(noisemap) & (noisemap > 0), 1.0 / noisemap.astype(np.float64) ** 2, 0.0)
-    d32 = np.nan_to_num(np.asarray(data, dtype=np.float32), nan=0.0)
+    a_est = a_est * cv.amplitude_per_flux(k)
+    d32, weight = stamps_and_weights(data, noisemap)
     psf = np.ascontiguousarray(psf, dtype=np.float32)
     if starlet_global_background or uniform_background_per_epoch:
         from .roi_modelling import joint_deconvolution
         res = joint_deconvolution(
-            d32, weight.astype(np.float32), psf, k, xs=np.zeros(1), ys=np.zeros(1), initial_a=a_est,
+            d32, weight, psf, k, xs=np.zeros(1), ys=np.zeros(1), initial_a=a_est,
             n_iter=n_iter, lr=1e-3, schedule=True, free_h=bool(starlet_global_background),
             free_mean=bool(uniform_background_per_epoch), free_c=True,
             regularization_strength_scales=3.0, regularization_strength_hf=3.0,
@@ -75,7 +87,7 @@ def do_one_star_forward_modelling(data, noisemap, psf, subsampling_factor, n_ite
         loss_curve = res['loss_history']
         deconv, bkg = res['deconvolved_epoch0']
     else:
-        out = engine.phot_fit_batch(d32, weight.astype(np.float32), psf, np.arange(E, dtype=np.int32),
+        out = engine.phot_fit_batch(d32, weight, psf, np.arange(E, dtype=np.int32),
                                     a_est.astype(np.float32), k, n_iter, lr=1e-3, schedule=True)
         a = out['a'].astype(np.float64)
         kw = {
@@ -99,8 +111,8 @@ def do_one_star_forward_modelling(data, noisemap, psf, subsampling_factor, n_ite
         'kwargs_final': kw,
         # fluxes are reported as pixel sums (the unit of lightcurver's star_flux_in_frame.flux, star_photometry.py:128) whatever the
         # normalisation of D_k in the kernels: with the block mean the amplitude a is k^2 x the flux
-        'fluxes': scale * a / (k * k if cv.downsample_mean else 1.0),
-        'fluxes_uncertainties': scale * np.asarray(sigma) / (k * k if cv.downsample_mean else 1.0),
+        'fluxes': scale * a / cv.amplitude_per_flux(k),
+        'fluxes_uncertainties': scale * np.asarray(sigma) / cv.amplitude_per_flux(k),
         'chi2': float(chi2),
         'chi2_per_frame': np.array(chi2_per_frame),
         'loss_curve': list(np.asarray(loss_curve)),
@@ -151,8 +163,8 @@ def star_photometry_batch(data, noisemap, psfs, subsampling_factor, n_iter=2000,
     scale = prep['scale'].cpu().numpy()
     res = {
         'scale': scale,
-        'fluxes': out['a'].reshape(F, S) * scale[None] / (k * k if cv.downsample_mean else 1.0),          # pixel-sum units
-        'fluxes_uncertainties': out['sigma_a'].reshape(F, S) * scale[None] / (k * k if cv.downsample_mean else 1.0),
+        'fluxes': out['a'].reshape(F, S) * scale[None] / cv.amplitude_per_flux(k),          # pixel-sum units
+        'fluxes_uncertainties': out['sigma_a'].reshape(F, S) * scale[None] / cv.amplitude_per_flux(k),
         'chi2_per_frame': out['chi2'].reshape(F, S),
         'dx': out['dx'].reshape(F, S), 'dy': out['dy'].reshape(F, S),
         'status': out['status'].reshape(F, S),
@@ -246,9 +258,10 @@ def do_star_photometry_batched(store, db, stars, frames_for_star, psf_ref_for_fr
             wk['scale'] = float(np.nanmax(d))
             d /= wk['scale']
             nm /= wk['scale']
-            a_est = _initial_flux_guess(d) * (k * k if cv.downsample_mean else 1.0)
-            ds.append(np.nan_to_num(d).astype(np.float32))
-            ws.append((1.0 / nm ** 2).astype(np.float32))
+            a_est = _initial_flux_guess(d) * cv.amplitude_per_flux(k)
+            d32, w32 = stamps_and_weights(d, nm)
+            ds.append(d32)
+            ws.append(w32)
             ps.append(np.asarray(wk['psf'], np.float32))
             a0s.append(a_est.astype(np.float32))
             offs.append(offs[-1] + d.shape[0])
@@ -261,8 +274,9 @@ def do_star_photometry_batched(store, db, stars, frames_for_star, psf_ref_for_fr
             with np.errstate(divide='ignore', invalid='ignore'):
                 chi2_per_frame = np.nansum(residuals ** 2 / wk['noisemap'] ** 2, axis=(1, 2)) / n ** 2
             wk['result'] = {
-                'scale': wk['scale'], 'fluxes': wk['scale'] * out['a'][sl].astype(np.float64) / (k * k if cv.downsample_mean else 1.0),
-                'fluxes_uncertainties': wk['scale'] * out['sigma_a'][sl].astype(np.float64) / (k * k if cv.downsample_mean else 1.0),
+                'scale': wk['scale'], 'fluxes': wk['scale'] * out['a'][sl].astype(np.float64) / cv.amplitude_per_flux(k),
+                'fluxes_uncertainties': wk['scale'] * out['sigma_a'][sl].astype(np.float64) / cv.amplitude_per_flux(k),
+                'status': out['status'][sl],
                 'chi2': float(np.nanmean(chi2_per_frame)), 'chi2_per_frame': chi2_per_frame,
                 'loss_curve': list(out['loss_hist'][sl].astype(np.float64).sum(0)), 'residuals': wk['scale'] * residuals,
                 'kwargs_final': {'kwargs_analytic': {'c_x': np.zeros(1), 'c_y': np.zeros(1), 'dx': out['dx'][sl], 'dy': out['dy'][sl],
@@ -276,9 +290,17 @@ def do_star_photometry_batched(store, db, stars, frames_for_star, psf_ref_for_fr
             on_result(star, wk['data'], wk['noisemap'], result)
         from .psf_modelling import relative_loss_differential
         rld = relative_loss_differential(result['loss_curve'])
-        flux_data = [(combined_footprint_hash, frame['id'], star['gaia_id'], float(result['fluxes'][j]),
+        # non-finite measurements (per-item status of the library, or a NaN that slipped through) never reach the database:
+        # the reference has no such guard because a NaN loss aborts its whole task (failure detection)
+        status = np.asarray(result.get('status', np.zeros(len(wk['frames']), np.int32)))
+        good = [j for j in range(len(wk['frames']))
+                if status[j] == 0 and np.isfinite(result['fluxes'][j]) and np.isfinite(result['fluxes_uncertainties'][j])]
+        if len(good) != len(wk['frames']):
+            logger.warning(f"Star {star['name']}: {len(wk['frames']) - len(good)} non-finite measurement(s) skipped "
+                           f"(frames {[wk['frames'][j]['id'] for j in range(len(wk['frames'])) if j not in good]})")
+        flux_data = [(combined_footprint_hash, wk['frames'][j]['id'], star['gaia_id'], float(result['fluxes'][j]),
                       float(result['fluxes_uncertainties'][j]), float(result['chi2_per_frame'][j]), rld)
-                     for j, frame in enumerate(wk['frames'])]
+                     for j in good]
         update_star_fluxes(db, flux_data)
         results[star['gaia_id']] = result
         logger.info(f"Measured star {star['name']} in {len(wk['frames'])} frames. "

@@ -28,9 +28,9 @@ import dataclasses
 _GROUPS = {'kwargs_analytic': ('c_x', 'c_y', 'dx', 'dy', 'a', 'alpha'), 'kwargs_background': ('h', 'mean')}
 
 # lightcurver hands pixel SUMS to setup_model as initial_a (star_photometry.py:55-69, roi_modelling.py:199-212) and reads
-# `a` back as the flux (:128, :462): that is the D_k = block-sum normalisation, so this front end runs the kernels with it
-# (the amplitude of the block-mean convention is k^2 times larger; both are tested against the oracle).
-STARRED_CONVENTIONS = dataclasses.replace(DEFAULT, downsample_mean=False)
+# `a` back as the flux (:128, :462): that is the D_k = block-sum normalisation, which is the library-wide default since
+# round 2 (the block-mean alternative, amplitude k^2 times larger, stays switchable and is tested against the oracle).
+STARRED_CONVENTIONS = DEFAULT
 
 
 class Deconv:

@@ -140,7 +140,8 @@ def make_deconv_epochs(E, n, k, M=4, n_psf=32, seed=SEEDS['cfg4']):
     s, _ = true_narrow_psf(rng, E, n_psf, k)
     quad = np.array([[-3.1, 2.4], [2.8, 3.0], [3.3, -2.2], [-2.6, -2.9]])[:M] * (n / 64.0) * 2.0
     c_x, c_y = quad[:, 0], quad[:, 1]
-    base_flux = np.array([8e4, 6e4, 4e4, 2.5e4])[:M]
+    # fluxes are pixel sums (block-sum convention, amplitude == flux): 2e4 ... 6e3 e-/s per source
+    base_flux = np.array([8e4, 6e4, 4e4, 2.5e4])[:M] / (k * k)
     a = base_flux[None] * rng.lognormal(0, 0.05, (E, M))
     dx = rng.uniform(-1, 1, E)
     dy = rng.uniform(-1, 1, E)
@@ -148,6 +149,6 @@ def make_deconv_epochs(E, n, k, M=4, n_psf=32, seed=SEEDS['cfg4']):
     y, x = np.meshgrid(ax, ax, indexing='ij')
     h = 30.0 * np.exp(-(x ** 2 + (y * 1.3) ** 2) / (2 * (3.0 * k) ** 2)) + 8.0 * np.exp(
         -((x - 4 * k) ** 2 + (y + 2 * k) ** 2) / (2 * (6.0 * k) ** 2))
-    h /= k * k
+    h /= (k * k) ** 2        # per upsampled pixel: a data pixel sums k^2 of them -> peak surface brightness 30 / k^2 per data pixel
     return dict(psf=s.astype(np.float32), c_x=c_x, c_y=c_y, a=a, dx=dx, dy=dy, h=h, P=P,
                 sky=rng.uniform(5.0, 15.0, E), rng=rng)

@@ -26,7 +26,7 @@ def test_header_symbols_exported(lcb):
 
 def test_conventions_roundtrip(lcb):
     c = lcb.get_conventions()
-    assert c.gauss_taps == 12 and abs(c.gauss_fwhm_up - 2.0) < 1e-7 and c.downsample_mean == 1
+    assert c.gauss_taps == 12 and abs(c.gauss_fwhm_up - 2.0) < 1e-7 and c.downsample_mean == 0
     lcb.set_conventions(gauss_taps=16)
     assert lcb.get_conventions().gauss_taps == 16
     with pytest.raises(lcb.LcbError):

@@ -5,6 +5,8 @@ keys / types / shapes, plus the reference's acceptance bound chi2 < 2
 import numpy as np
 import pytest
 
+from lightcurver_b200.conventions import DEFAULT
+
 pytestmark = pytest.mark.gpu
 
 
@@ -101,8 +103,9 @@ def test_device_prepare_matches_host_policies(cuda_device):
     nm = rng.uniform(0.5, 2.0, (sumN, n, n)).astype(np.float32)
     mk = rng.random((sumN, n, n)) > 0.05
     img[0, 3, 4] = np.nan; nm[0, 3, 4] = np.nan; img[2, 1, 1] = np.inf; nm[5, 0, 0] = 0.0; nm[6, 2, 2] = np.nan
-    for method in ('center', 'max', 'barycenter'):
-        prep = engine.psf_prepare_batch(img, nm, mk, off, k, norm_scale=100.0, downsample_mean=True, guess_method=method)
+    for method, dmean in (('center', True), ('max', False), ('barycenter', False)):
+        cv_apf = k * k if dmean else 1.0
+        prep = engine.psf_prepare_batch(img, nm, mk, off, k, norm_scale=100.0, downsample_mean=dmean, guess_method=method)
         star_max = np.fmax.reduce(img.reshape(sumN, -1), axis=1)
         norms = np.fmax.reduceat(star_max, off[:-1]).astype(np.float64) / 100.0
         norms[~np.isfinite(norms) | (norms <= 0)] = 1.0
@@ -115,7 +118,7 @@ def test_device_prepare_matches_host_policies(cuda_device):
         np.testing.assert_allclose(prep['norm'].cpu().numpy(), norms, rtol=1e-6)
         np.testing.assert_allclose(prep['data'].cpu().numpy(), d, rtol=1e-6, atol=1e-7)
         np.testing.assert_allclose(prep['weight'].cpu().numpy(), w, rtol=2e-6)
-        np.testing.assert_allclose(prep['a0'].cpu().numpy(), np.maximum(flux, 1e-6) * k * k, rtol=1e-5)
+        np.testing.assert_allclose(prep['a0'].cpu().numpy(), np.maximum(flux, 1e-6) * cv_apf, rtol=1e-5)
         ctr = (n - 1) / 2.0
         if method == 'center':
             x0 = y0 = np.zeros(sumN)
@@ -147,7 +150,7 @@ def test_device_prepare_matches_host_policies(cuda_device):
     d *= inv; s *= inv
     edges = np.stack([np.median(d[:, :, 0, :], -1), np.median(d[:, :, :, 0], -1), np.median(d[:, :, -1, :], -1), np.median(d[:, :, :, -1], -1)])
     bg = np.nan_to_num(edges.mean((0, 1)), nan=0.0)
-    a_est = (d.sum((-1, -2), dtype=np.float64) - n * n * bg[None]) * k * k
+    a_est = (d.sum((-1, -2), dtype=np.float64) - n * n * bg[None]) * DEFAULT.amplitude_per_flux(k)
     np.testing.assert_allclose(prep['scale'].cpu().numpy(), scale, rtol=1e-6)
     np.testing.assert_allclose(prep['data'].cpu().numpy().reshape(F, S, n, n), d, rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(prep['weight'].cpu().numpy().reshape(F, S, n, n), 1.0 / s.astype(np.float64) ** 2, rtol=3e-6)
@@ -155,17 +158,17 @@ def test_device_prepare_matches_host_policies(cuda_device):
 
 
 def test_alternate_conventions_parity(cuda_device):
-    """Every recalled STARRED convention is a switch: with D_k = block SUM (what lightcurver's use of pixel sums as
-    initial_a and of `a` as the flux suggests) and chi2 without the 1/2, K2, K1 (fast and generic
-    path) and K3 still match the oracle to 1e-5."""
+    """Every recalled STARRED convention is a switch: with D_k = block MEAN (the default is the block SUM, which is what
+    lightcurver's use of pixel sums as initial_a and of `a` as the flux implies) and chi2 without the
+    1/2, K2, K1 (fast and generic path) and K3 still match the oracle to 1e-5."""
     import dataclasses
     from lightcurver_b200 import engine, _lib, synthetic
     from lightcurver_b200.conventions import DEFAULT, apply_to_library
     from lightcurver_b200.processes.roi_modelling import JointDeconvolution
     from oracle import starred_model as sm
     from oracle.conventions import DEFAULT as ODEF
-    cvp = dataclasses.replace(DEFAULT, downsample_mean=False, chi2_half=False)
-    cvo = dataclasses.replace(ODEF, downsample_mean=False, chi2_half=False)
+    cvp = dataclasses.replace(DEFAULT, downsample_mean=True, chi2_half=False)
+    cvo = dataclasses.replace(ODEF, downsample_mean=True, chi2_half=False)
     rng = np.random.default_rng(8)
     try:
         apply_to_library(cvp)

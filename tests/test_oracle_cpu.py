@@ -34,8 +34,10 @@ def test_banded_equals_general_deconvolution_model():
     m2 = sm.deconv_model(torch.zeros(nu, nu, dtype=torch.float64), zE, a[:, None], z1, z1, dx, dy, zE, psf, n, k, with_h=False)
     m3 = sm.deconv_model(torch.zeros(nu, nu, dtype=torch.float64), zE, a[:, None], z1, z1, dx, dy, zE, psf, n, k, with_h=False, direct=True)
     assert (m1 - m2).abs().max() < 1e-14 and (m2 - m3).abs().max() < 1e-14
-    # mean-downsample convention: sum of the model = a / k^2 when nothing falls off the stamp
-    np.testing.assert_allclose(m1.sum((-1, -2)).numpy(), a.numpy() / k ** 2, rtol=2e-2)
+    # block-sum convention (default): the amplitude IS the pixel-sum flux when nothing falls off the stamp -- the scale
+    # relation of the reference's notebook (example_roi_modelling.ipynb cells 13 -> 21 -> 36: a ~ sum of pixels / scale)
+    np.testing.assert_allclose(m1.sum((-1, -2)).numpy(), a.numpy() / sm.DEFAULT.amplitude_per_flux(k), rtol=2e-2)
+    assert sm.DEFAULT.amplitude_per_flux(k) == 1.0
 
 
 def test_fft_equals_direct_with_background_and_rotation():
@@ -98,11 +100,11 @@ def test_phot_fit_recovers_flux_cpu():
     data = d['data'].reshape(-1, n, n)
     sc = data.max()
     w = sc ** 2 / d['noisemap'].reshape(-1, n, n).astype(np.float64) ** 2
-    a0 = data.sum((-1, -2)) * k * k / sc
+    a0 = data.sum((-1, -2)) * sm.DEFAULT.amplitude_per_flux(k) / sc
     r = sm.fit_phot(np.repeat(d['psf'], 2, 0), data / sc, w, a0, n, k, 300, dtype=torch.float64)
     truth = (d['transparency'][:, None] * d['star_flux'][None]).reshape(-1)
-    flux = r['a'] * sc / k ** 2
-    assert np.all(np.abs(flux - truth) < 6 * r['sigma_a'] * sc / k ** 2)
+    flux = r['a'] * sc / sm.DEFAULT.amplitude_per_flux(k)
+    assert np.all(np.abs(flux - truth) < 6 * r['sigma_a'] * sc / sm.DEFAULT.amplitude_per_flux(k))
     assert r['loss_hist'][:, -1].sum() < r['loss_hist'][:, 0].sum()
 
 

@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 from lightcurver_b200 import synthetic
+from lightcurver_b200.conventions import DEFAULT
 
 pytestmark = pytest.mark.gpu
 
@@ -17,7 +18,7 @@ def _items(F, S, n, k, seed):
     nm = d['noisemap'].reshape(F * S, n, n)
     weight = (1.0 / nm.astype(np.float64) ** 2).astype(np.float32)
     idx = np.repeat(np.arange(F), S).astype(np.int32)
-    a0 = (data.sum((-1, -2)) * k * k).astype(np.float32)
+    a0 = (data.sum((-1, -2)) * DEFAULT.amplitude_per_flux(k)).astype(np.float32)
     return d, data, weight, idx, a0
 
 
@@ -79,9 +80,9 @@ def test_phot_recovers_fluxes_and_device_tensors(cuda_device):
     torch.cuda.synchronize()
     assert np.array_equal(host['a'], dev['a'].cpu().numpy())
     assert np.array_equal(host['loss_hist'], dev['loss_hist'].cpu().numpy())
-    flux = host['a'] * scale / (k * k)
+    flux = host['a'] * scale / DEFAULT.amplitude_per_flux(k)
     truth = (d['transparency'][:, None] * d['star_flux'][None]).reshape(-1)
-    err = np.abs(flux - truth) / (host['sigma_a'] * scale / (k * k))
+    err = np.abs(flux - truth) / (host['sigma_a'] * scale / DEFAULT.amplitude_per_flux(k))
     assert np.median(err) < 1.5 and err.max() < 6.0
     assert np.median(host['chi2']) < 1.3
 

@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 from lightcurver_b200 import synthetic
+from lightcurver_b200.conventions import DEFAULT
 
 pytestmark = pytest.mark.gpu
 
@@ -20,7 +21,7 @@ def _frames(F, N, n, k, seed, norm=True):
         sc = data.max() / 100.0
         data, nm = data / sc, nm / sc
     weight = d['masks'] / nm ** 2
-    a0 = (data * d['masks']).sum((-1, -2)) * k * k
+    a0 = (data * d['masks']).sum((-1, -2)) * DEFAULT.amplitude_per_flux(k)
     off = np.arange(F + 1, dtype=np.int32) * N
     return d, data.astype(np.float32), nm.astype(np.float32), weight.astype(np.float32), a0.astype(np.float32), off
 

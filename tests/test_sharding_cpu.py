@@ -29,7 +29,9 @@ def _problem():
     nu = n * k
     fw = rng.uniform(2.5, 3.5, E)
     psf = sm.moffat_image(torch.tensor(fw), torch.tensor(fw), torch.zeros(E, dtype=torch.float64), torch.full((E,), 3.0, dtype=torch.float64), 8, k).numpy()
-    prm = dict(h=0.1 * rng.standard_normal(nu * nu), mean=0.01 * rng.standard_normal(E), a=rng.uniform(1, 2, (E, M)),
+    prm = dict(h=0.1 * rng.standard_normal(nu * nu), mean=0.01 * rng.standard_normal(E),
+               a=rng.uniform(1, 2, (E, M)) * sm.DEFAULT.amplitude_per_flux(k) / (k * k),      # pixel-sum fluxes of 0.25 .. 0.5
+              
                c_x=rng.uniform(-2, 2, M), c_y=rng.uniform(-2, 2, M), dx=rng.uniform(-1, 1, E), dy=rng.uniform(-1, 1, E))
     data = rng.standard_normal((E, n, n)); weight = rng.uniform(0.5, 2, (E, n, n))
     return E, n, k, M, psf, prm, data, weight

@@ -21,7 +21,7 @@ data = d['data'].reshape(-1, n, n).astype(np.float64)
 sc = data.max()
 w = sc ** 2 / d['noisemap'].reshape(-1, n, n).astype(np.float64) ** 2
 psf = np.repeat(d['psf'], S, 0).astype(np.float64)
-a = data.sum((-1, -2)) * k * k / sc * rng.uniform(0.9, 1.1, F * S)
+a = data.sum((-1, -2)) * sm.DEFAULT.amplitude_per_flux(k) / sc * rng.uniform(0.9, 1.1, F * S)
 dx, dy = rng.uniform(-0.8, 0.8, F * S), rng.uniform(-0.8, 0.8, F * S)
 L, g = sm.phot_loss_grad(psf, data / sc, w, a, dx, dy, n, k)
 np.savez_compressed(out / 'phot_n16_k2.npz', kind='phot', n=n, k=k, psf=psf.astype(np.float32), data=(data / sc).astype(np.float32),
@@ -41,7 +41,7 @@ nm = d['noisemap'][0] / sc
 weight = (d['masks'][0] / nm ** 2).astype(np.float32)
 s_fixed = sm.moffat_image(3.1, 3.4, 0.5, 2.7, n, k).numpy().astype(np.float32)
 b = (1e-4 * rng.standard_normal((nu, nu))).astype(np.float32)
-a = ((data * d['masks'][0]).sum((-1, -2)) * k * k).astype(np.float32)
+a = ((data * d['masks'][0]).sum((-1, -2)) * sm.DEFAULT.amplitude_per_flux(k)).astype(np.float32)
 x0, y0 = rng.uniform(-0.6, 0.6, N).astype(np.float32), rng.uniform(-0.6, 0.6, N).astype(np.float32)
 W = rng.uniform(0.5, 2.0, (4 + 1, nu, nu)).astype(np.float32)
 L, g = sm.psf_loss_grad(s_fixed, b, a, x0, y0, data, weight, W, n, k, 0.7, 1.3)

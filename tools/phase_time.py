@@ -11,7 +11,7 @@ data = torch.as_tensor(d['data'] / sc).reshape(F * N, n, n).cuda()
 nm = torch.as_tensor(d['noisemap'] / sc).reshape(F * N, n, n).cuda()
 w = (torch.as_tensor(d['masks']).reshape(F * N, n, n).cuda() / nm ** 2).contiguous()
 off = torch.arange(F + 1, dtype=torch.int32).cuda() * N
-a0 = (data.sum((-1, -2)) * k * k)
+a0 = data.sum((-1, -2))   # block-sum convention: amplitude = pixel-sum flux
 mof = torch.tensor([[3.0, 3.0, 0.0, 2.5, 1.0]]).repeat(F, 1).cuda()
 out = engine.psf_fit_batch(data, w, off, k, mof, a0, n_iter_analytic=0, n_iter_adabelief=T2, lr=1e-5,
                            noise_weights=True, lam_scales=1.0, lam_hf=1.0, want=('loss_hist',))

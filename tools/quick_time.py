@@ -25,7 +25,7 @@ def main():
     nm = torch.as_tensor(d['noisemap'] / sc).reshape(F * N, n, n).cuda()
     w = (torch.as_tensor(d['masks']).reshape(F * N, n, n).cuda() / nm ** 2).contiguous()
     off = torch.arange(F + 1, dtype=torch.int32).cuda() * N
-    a0 = (data.sum((-1, -2)) * k * k)
+    a0 = data.sum((-1, -2))   # block-sum convention: amplitude = pixel-sum flux
     mof = torch.tensor([[3.0, 3.0, 0.0, 2.5, 1.0]]).repeat(F, 1).cuda()
     for (t1, t2, nw, lam) in [(0, T2, False, 1.0), (0, T2, False, 0.0), (100, 0, False, 1.0), (0, 1, True, 1.0), (100, T2, True, 1.0)]:
         ms = ev_time(lambda: engine.psf_fit_batch(data, w, off, k, mof, a0, n_iter_analytic=t1,
@@ -44,7 +44,7 @@ def main():
     w3 = (sc3 ** 2 / torch.as_tensor(d3['noisemap']).reshape(B, n, n).cuda() ** 2).contiguous()
     dat3 = dat3 / sc3
     idx = torch.arange(F, dtype=torch.int32).repeat_interleave(20).cuda()
-    a3 = dat3.sum((-1, -2)) * k * k
+    a3 = dat3.sum((-1, -2))
     psf3 = torch.as_tensor(d3['psf']).cuda()
     T = 200
     ms = ev_time(lambda: engine.phot_fit_batch(dat3, w3, psf3, idx, a3, k, T, want_residuals=False, want_loss_hist=False))
