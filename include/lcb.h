@@ -6,9 +6,10 @@
  *   lcb_phot_fit_batch     star_photometry.py:66-128  setup_model / Loss / Optimizer('adabelief').minimize /
  *                                                      model.model  (fixed-PSF amplitude+shift fit)
  *                          + starred_utilities.py:10-39 get_flux_uncertainties (closed form, sigma_a)
- *   lcb_psf_fit_batch      psf_modelling.py:164-171    starred.procedures.psf_routines.build_psf
- *   lcb_psf_loss_grad      (same Loss object, one evaluation; used by parity tests)
- *   lcb_noise_weights      star_photometry.py:108, roi_modelling.py:299  propagate_noise(method='SLIT')
+ *   lcb_psf_fit_batch      psf_modelling.py:164-171    starred.procedures.psf_routines.build_psf  (loss0 / grad_b0 / grad_s0 of
+ *                                                      lcb_psf_out expose one evaluation of its Loss object to the parity tests;
+ *                                                      noise_weights = 1 / 2 is propagate_noise(method='SLIT' / 'MC') [R])
+ *   lcb_deconv_noise_weights  star_photometry.py:108, roi_modelling.py:299  propagate_noise(model, ..., method='SLIT')
  *   lcb_deconv_*           roi_modelling.py:213-335    setup_model / Loss (chi2, starlet-L1, positivity, prior, pts-source,
  *                                                      flux uniformity) / Optimizer('adabelief').minimize / the loss-gradient
  *                                                      pair of Optimizer('l-bfgs-b'); epochs shard over GPUs (lcb_deconv_comm_*)
@@ -18,8 +19,10 @@
  * Conventions: all arrays are C-contiguous float32, row-major [item][y][x]; positions are in data
  * pixels with the origin at the stamp centre (n-1)/2 (roi_modelling.py:207-210).  `mem` selects
  * where EVERY pointer of a call lives: LCB_MEM_DEVICE (device pointers, work is enqueued on
- * `stream`, the call does not synchronise) or LCB_MEM_HOST (host pointers; the library stages
- * through its own device arena, H2D and D2H copies included, and returns after synchronising).
+ * `stream`; the only host synchronisations are the ones documented per entry point: lcb_psf_fit_batch reads star_off back
+ * to size its launches) or LCB_MEM_HOST (host pointers; the library stages through a device arena leased for the call,
+ * H2D and D2H copies included, and returns after synchronising).  Calls may come from several host threads (one per
+ * GPU): conventions and the last-error string are per thread, staging arenas are leased per call and device.
  * The caller owns every buffer; nothing is retained after return except explicit handles.
  * Return value: 0 on success, negative lcb_status otherwise; lcb_last_error() gives the text.
  * There is no CPU fallback: without a CUDA device every compute entry returns LCB_ERR_CUDA.
@@ -43,11 +46,12 @@ enum lcb_mem { LCB_MEM_DEVICE = 0, LCB_MEM_HOST = 1 };
 /* per-item status flags written to status[] */
 enum lcb_item_status { LCB_ITEM_OK = 0, LCB_ITEM_NONFINITE = 1 };
 
-/* every recalled STARRED constant, switchable at run time. */
+/* every recalled STARRED constant, switchable at run time, PER HOST THREAD (lcb_conventions_set
+ * touches only the calling thread; a deconvolution handle keeps the conventions of the thread that created it). */
 typedef struct {
     float gauss_fwhm_up;     /* FWHM of the target-resolution Gaussian, upsampled px (2.0) */
     int   gauss_taps;        /* G, even, one of 8/12/16 (12) */
-    int   downsample_mean;   /* 1: D_k is the block mean, 0: block sum */
+    int   downsample_mean;   /* 0 (default): D_k is the block sum, amplitudes are pixel-sum fluxes; 1: block mean */
     int   chi2_half;         /* 1: chi2 term is 1/2 sum w r^2 */
     float clip_global_norm;  /* optax.clip_by_global_norm when scheduled (1.0) */
     float lr_decay_rate;     /* exponential_decay rate over max_iterations (0.99) */
@@ -200,10 +204,12 @@ int lcb_deconv_comm_connect(void* handle, const void* all_handles);
 int lcb_deconv_run(void* handle, const lcb_fit_opts* opt, float* loss_hist, int mem);
 /* Alternative multi-rank driver with an external collective (e.g. NCCL): one iteration = step_local ;
  * all-reduce(sum) of reduce_buffer ; step_update.
- * After the last iteration call step_local once more to apply the pending per-epoch update. */
+ * After the last iteration call lcb_deconv_flush to apply the pending per-epoch update. */
 int lcb_deconv_step_local(void* handle, int want_model);
 int lcb_deconv_reduce_buffer(void* handle, float** device_ptr, int* count);
 int lcb_deconv_step_update(void* handle, int it, int n_iter, float lr, int schedule);
+/* applies the pending per-epoch update of the last step_update and clears the pending flag (end of an external loop) */
+int lcb_deconv_flush(void* handle);
 int lcb_deconv_loss_grad(void* handle, lcb_deconv_grad* g, int mem);
 /* current parameters; model [E][n][n] and loss [1] are evaluated when non-NULL */
 int lcb_deconv_get(void* handle, lcb_deconv_params* q, float* model, float* loss, int mem);

@@ -240,6 +240,7 @@ lib.lcb_deconv_run.argtypes = [C.c_void_p, C.POINTER(FitOpts), C.c_void_p, C.c_i
 lib.lcb_deconv_step_local.argtypes = [C.c_void_p, C.c_int]
 lib.lcb_deconv_reduce_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
 lib.lcb_deconv_step_update.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int]
+lib.lcb_deconv_flush.argtypes = [C.c_void_p]
 lib.lcb_deconv_loss_grad.argtypes = [C.c_void_p, C.POINTER(DeconvGrad), C.c_int]
 lib.lcb_deconv_get.argtypes = [C.c_void_p, C.POINTER(DeconvParams), C.c_void_p, C.c_void_p, C.c_int]
 lib.lcb_deconv_destroy.argtypes = [C.c_void_p]

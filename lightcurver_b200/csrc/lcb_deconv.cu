@@ -1587,6 +1587,17 @@ int lcb_deconv_reduce_buffer(void* handle, float** ptr, int* count) {
     return LCB_OK;
 }
 
+// applies the pending per-epoch AdaBelief update left by the last lcb_deconv_step_update and clears the pending flag
+// (ctl[4]): the last call of an external-collective loop (lcb_deconv_run does the same internally)
+int lcb_deconv_flush(void* handle) {
+    DeconvHandle* H = (DeconvHandle*)handle;
+    LCB_REQUIRE(H, "lcb_deconv_flush: NULL handle");
+    int rc;
+    if ((rc = launch_epoch(H, 0))) return rc;
+    LCB_CUDA(cudaMemsetAsync(H->D.ctl + 4, 0, 4, H->st));
+    return LCB_OK;
+}
+
 // replicated half: regularisers, global norm, AdaBelief on the shared parameters; it < 0 = evaluate only
 int lcb_deconv_step_update(void* handle, int it, int n_iter, float lr, int schedule) {
     DeconvHandle* H = (DeconvHandle*)handle;

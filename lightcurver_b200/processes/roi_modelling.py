@@ -220,7 +220,7 @@ class JointDeconvolution:
             _lib.check(_lib.lib.lcb_deconv_step_update(self.handle, it, n_iter, float(lr), int(bool(schedule))), 'lcb_deconv_step_update')
             hist[it] = red[lossidx]
         if n_iter:
-            _lib.check(_lib.lib.lcb_deconv_step_local(self.handle, 0), 'lcb_deconv_step_local')   # pending per-epoch update
+            _lib.check(_lib.lib.lcb_deconv_flush(self.handle), 'lcb_deconv_flush')   # pending per-epoch update, flag cleared
         torch.cuda.synchronize()
         return hist.cpu().numpy()
 

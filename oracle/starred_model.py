@@ -576,7 +576,7 @@ def psf_products(s, a, x0, y0, data, weight, n, k, cv: Conventions = DEFAULT, dt
                 residuals=res.numpy(), chi2=float(chi2))
 
 
-def fit_psf_stage1(data, weight, n, k, fwhm_guess, a0, n_iter, cv: Conventions = DEFAULT):
+def fit_psf_stage1(data, weight, n, k, fwhm_guess, a0, n_iter, cv: Conventions = DEFAULT, strict_tol=True):
     """Analytic stage (A.4 stage 1): scipy L-BFGS-B over {fwhm_x, fwhm_y, phi, beta, a, x0, y0},
     background 0, lambda 0, C fixed at 1.  float64.  One frame."""
     from scipy.optimize import minimize
@@ -607,7 +607,8 @@ def fit_psf_stage1(data, weight, n, k, fwhm_guess, a0, n_iter, cv: Conventions =
 
     hist = []
     res = minimize(fun, x_init, jac=True, method='L-BFGS-B', bounds=list(zip(lo, hi)),
-                   options={'maxiter': n_iter, 'maxfun': 20 * n_iter, 'ftol': 1e-15, 'gtol': 1e-10},
+                   options=({'maxiter': n_iter, 'maxfun': 20 * n_iter, 'ftol': 1e-15, 'gtol': 1e-10} if strict_tol else
+                            {'maxiter': n_iter, 'maxfun': 20 * n_iter}),      # strict: convergence tests; else scipy's defaults
                    callback=lambda xk: hist.append(last['L']))
     fx, fy, ph, be, a, x0, y0 = unpack(res.x)
     return dict(fwhm_x=fx, fwhm_y=fy, phi=ph, beta=be, C=1.0, a=a, x0=x0, y0=y0,

@@ -38,7 +38,9 @@ def _problem(E, n, k, M, P_data, seed, alpha_on=True, h_sigma=2.5, h_peak=0.5):
 
 @pytest.mark.parametrize("E,n,k,M,npsf,cs,alpha_on", [(3, 16, 2, 2, 12, 0, True), (2, 12, 3, 1, 12, 2, True), (2, 16, 1, 3, 15, 4, True),
                                                       (3, 16, 2, 2, 16, 1, True), (3, 16, 2, 2, 12, 4, False), (2, 32, 2, 3, 16, 8, True),
-                                                      (2, 32, 2, 3, 16, 8, False), (3, 20, 2, 2, 12, 4, True), (2, 8, 4, 1, 8, 2, True)])
+                                                      (2, 32, 2, 3, 16, 8, False), (3, 20, 2, 2, 12, 4, True), (2, 8, 4, 1, 8, 2, True),
+                                                      # BASELINE cfg4 shape (n = 64, k = 2, P = 64, M = 4) at both cluster sizes the bench uses
+                                                      (4, 64, 2, 4, 32, 4, False), (4, 64, 2, 4, 32, 8, False), (2, 64, 2, 4, 32, 8, True)])
 def test_deconv_loss_grad_parity(cuda_device, E, n, k, M, npsf, cs, alpha_on):
     """Every cluster size (CTAs per epoch) of the per-epoch kernel, rotated and purely translated epochs, all loss terms."""
     from lightcurver_b200.processes.roi_modelling import JointDeconvolution
@@ -114,6 +116,39 @@ def test_deconv_fit_parity_and_photometry_consistency(cuda_device):
                                dx0=p2['dx'], dy0=p2['dy'])
     np.testing.assert_allclose(m3, p2['data'] - ph['residuals'], rtol=1e-5, atol=1e-5 * np.abs(m3).max())
     jd2.close()
+
+
+@pytest.mark.parametrize("cs", [4, 8])
+def test_deconv_fit_parity_cfg4_shape(cuda_device, cs):
+    """BASELINE cfg4 shape (E = 4 epochs of 64 x 64, k = 2, P = 64, M = 4), 20 AdaBelief iterations with the reference's stage-2
+    options (roi_modelling.py:326-335: lr 1e-4, no schedule) against the float64 oracle, for both cluster sizes the bench runs."""
+    from lightcurver_b200.processes.roi_modelling import JointDeconvolution
+    from oracle import starred_model as sm
+    E, n, k, M, T = 4, 64, 2, 4, 20
+    p = _problem(E, n, k, M, 32, seed=64, alpha_on=False)
+    nu = n * k
+    a0 = (p['a'] * 0.9).astype(np.float32)
+    h0 = (1e-3 * np.random.default_rng(0).standard_normal(nu * nu)).astype(np.float32)
+    jd = JointDeconvolution(p['data'], p['weight'], p['psf'], k, M)
+    jd.set_cluster(cs)
+    jd.set_params(h=h0, mean=np.zeros(E), a=a0, c_x=p['c_x'], c_y=p['c_y'], dx=np.zeros(E), dy=np.zeros(E), alpha=p['alpha'])
+    W = jd.noise_weights()
+    jd.set_reg(1.0, 1.0, 100.0, W=W, lam_pts=0.01, lam_fu=10.0)
+    hist = jd.run(T, lr=1e-4, schedule=False)
+    fin = jd.get()
+    jd.close()
+    params = dict(h=h0, mean=np.zeros(E), a=a0, c_x=p['c_x'], c_y=p['c_y'], dx=np.zeros(E), dy=np.zeros(E))
+    ref = sm.fit_deconv(params, dict(alpha=p['alpha']), p['psf'], p['data'], p['weight'], W, n, k,
+                        dict(lam_scales=1.0, lam_hf=1.0, lam_pos=100.0, lam_pts=0.01, lam_fu=10.0), T, lr=1e-4, schedule=False,
+                        dtype=torch.float64)
+    err_a = float(np.max(np.abs(fin['a'].reshape(E, M) - ref['a']) / np.abs(ref['a'])))
+    err_h = float(np.abs(fin['h'] - ref['h'].reshape(-1)).max() / np.abs(p['h']).max())
+    print(f"[parity] deconv cfg4 shape, CS={cs}, T={T}: max rel flux error {err_a:.2e}, max |dh| / peak(h) {err_h:.2e}, "
+          f"max rel loss error {float(np.max(np.abs(hist - ref['loss_hist']) / np.abs(ref['loss_hist']))):.2e}")
+    np.testing.assert_allclose(hist, ref['loss_hist'], rtol=1e-5)
+    assert err_a <= 1e-4 and err_h <= 1e-3
+    np.testing.assert_allclose(fin['dx'], ref['dx'], atol=1e-4)
+    np.testing.assert_allclose(fin['c_x'], ref['c_x'], atol=1e-4)
 
 
 def test_do_one_star_reference_defaults(cuda_device):

@@ -66,6 +66,28 @@ def test_phot_fit_parity_fixed_iterations(cuda_device):
     assert out['loss_hist'].shape == (F * S, T)
 
 
+def test_phot_fit_parity_configured_length(cuda_device, record_property):
+    """The CONFIGURED run: star_deconv_n_iter = 2000 (config.yaml:248), lr 1e-3 scheduled (star_photometry.py:113-122), 32 x 32
+    stamps, k = 2, against the float64 oracle; fluxes within 1e-4 relative (north star), achieved numbers printed."""
+    import torch
+    from lightcurver_b200 import engine
+    from oracle import starred_model as sm
+    n, k, F, S, T = 32, 2, 1, 4, 2000
+    d, data, weight, idx, a0 = _items(F, S, n, k, seed=13)
+    scale = data.max()
+    data, weight, a0 = data / scale, weight * scale ** 2, a0 / scale * 0.9
+    out = engine.phot_fit_batch(data, weight, d['psf'], idx, a0, k, n_iter=T, lr=1e-3, schedule=True)
+    ref = sm.fit_phot(d['psf'][idx], data, weight, a0, n, k, T, lr=1e-3, schedule=True, dtype=torch.float64)
+    nums = dict(flux_rel_err=float(np.max(np.abs(out['a'] - ref['a']) / np.abs(ref['a']))),
+                shift_abs_err_px=float(max(np.abs(out['dx'] - ref['dx']).max(), np.abs(out['dy'] - ref['dy']).max())),
+                final_loss_rel_err=float(np.max(np.abs(out['loss_hist'][:, -1] - ref['loss_hist'][:, -1]) / np.abs(ref['loss_hist'][:, -1]))),
+                iterations=T)
+    print("[parity] photometry at the configured length:", nums)
+    for kk, v in nums.items():
+        record_property(kk, v)
+    assert nums['flux_rel_err'] <= 1e-4 and nums['shift_abs_err_px'] <= 1e-3 and nums['final_loss_rel_err'] <= 1e-4
+
+
 def test_phot_recovers_fluxes_and_device_tensors(cuda_device):
     """Converged fit recovers the injected fluxes; torch CUDA tensors take the device-pointer path
     and give the same answer as the host-pointer path (bit-exact: same kernel, same inputs)."""

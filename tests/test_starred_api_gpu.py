@@ -157,3 +157,52 @@ def test_roi_call_sequence(cuda_device, starred_installed):
     assert x_pixels.shape == (M,)
     res = data - np.array(model.model(kwargs_final))
     assert (np.nansum(res ** 2 / noisemap ** 2, axis=(1, 2)) / model.image_size ** 2 < 3).all()
+
+
+def test_three_paths_agree_on_fluxes_at_2000_iterations(cuda_device, starred_installed):
+    """One convention everywhere (D_k = block sum, amplitude == pixel-sum flux): at n_iter = 2000 the batched driver
+    (star_photometry_batch, per-(frame, star) K2 fits), do_one_star_forward_modelling and the STARRED-shaped call sequence
+    (setup_model / Loss / Optimizer, which couples the epochs through c and the clip norm) return the same fluxes in the same
+    units -- a k^2 slip in any of them would show as a factor 4 -- and the fitted amplitude of a unit-max stamp is its pixel
+    sum, the scale relation of the reference's notebook (example_roi_modelling.ipynb cells 13 -> 21 -> 36)."""
+    from starred.deconvolution.deconvolution import setup_model
+    from starred.deconvolution.loss import Loss
+    from starred.deconvolution.parameters import ParametersDeconv
+    from starred.optim.optimization import Optimizer
+    from lightcurver_b200.processes.star_photometry import star_photometry_batch, do_one_star_forward_modelling
+    from lightcurver_b200.utilities.starred_utilities import get_flux_uncertainties
+    E, n, k, n_iter = 6, 16, 2, 2000
+    d, data, noisemap, psf = _star_stack(E, n, k, seed=21)
+    truth = d['transparency'] * d['star_flux'][0]
+    # (1) batched driver: (F, S = 1, n, n)
+    b = star_photometry_batch(data[:, None].astype(np.float32), noisemap[:, None].astype(np.float32), psf.astype(np.float32), k,
+                              n_iter=n_iter)
+    f_batch, s_batch = b['fluxes'][:, 0], b['fluxes_uncertainties'][:, 0]
+    # (2) the reference-shaped single-star function (in-place scaling of its arguments, like the reference)
+    d2, n2 = data.copy(), noisemap.copy()
+    r = do_one_star_forward_modelling(d2, n2, psf, k, n_iter=n_iter, uniform_background_per_epoch=False, starlet_global_background=False)
+    # (3) the STARRED call sequence with h and mean fixed
+    scale = np.nanmax(data)
+    ds, ns = data / scale, noisemap / scale
+    model, kwargs_init, kwargs_up, kwargs_down, _ = setup_model(ds, ns ** 2, psf, np.array([0.]), np.array([0.]), k, list(np.nansum(ds, axis=(1, 2))))
+    kwargs_fixed = {'kwargs_analytic': {'alpha': kwargs_init['kwargs_analytic']['alpha']},
+                    'kwargs_background': {'h': kwargs_init['kwargs_background']['h'], 'mean': np.zeros(E)}, 'kwargs_sersic': {}}
+    parameters = ParametersDeconv(kwargs_init=kwargs_init, kwargs_fixed=kwargs_fixed, kwargs_up=kwargs_up, kwargs_down=kwargs_down)
+    loss = Loss(ds, model, parameters, ns ** 2, regularization_terms='l1_starlet', regularization_strength_scales=3.0,
+                regularization_strength_hf=3.0, regularization_strength_flux_uniformity=0.)
+    Optimizer(loss, parameters, method='adabelief').minimize(max_iterations=n_iter, init_learning_rate=1e-3, schedule_learning_rate=True,
+                                                             restart_from_init=True)
+    kw = parameters.best_fit_values(as_kwargs=True)
+    f_api = scale * np.asarray(kw['kwargs_analytic']['a'])
+    s_api = scale * get_flux_uncertainties(kw, kwargs_up, kwargs_down, ds, ns, model=model)
+    print("[parity] fluxes at 2000 iterations: batched/one-star max rel diff", float(np.max(np.abs(f_batch / r['fluxes'] - 1))),
+          "batched/starred-api", float(np.max(np.abs(f_batch / f_api - 1))), "vs truth (sigma units)",
+          float(np.max(np.abs(f_batch - truth) / s_batch)))
+    np.testing.assert_allclose(r['fluxes'], f_batch, rtol=2e-4)           # same K2 kernel behind both, same scale rule
+    np.testing.assert_allclose(f_api, f_batch, rtol=2e-3)                 # coupled trajectory, same optimum
+    np.testing.assert_allclose(r['fluxes_uncertainties'], s_batch, rtol=1e-3)
+    np.testing.assert_allclose(s_api, s_batch, rtol=5e-3)
+    assert np.all(np.abs(f_batch - truth) < 6 * s_batch)
+    # the notebook's scale relation: amplitude of a stamp scaled to unit maximum ~ its pixel sum
+    a_unit = np.asarray(kw['kwargs_analytic']['a'])
+    np.testing.assert_allclose(a_unit, np.nansum(ds, axis=(1, 2)), rtol=0.1)
