@@ -187,7 +187,7 @@ typedef struct {           /* gradient of the loss at the current parameters */
 int lcb_deconv_create(const lcb_deconv_problem* p, int mem, void* stream, void** handle);
 int lcb_deconv_set_params(void* handle, const lcb_deconv_params* q, int mem);   /* also restarts the optimiser state */
 int lcb_deconv_set_reg(void* handle, const lcb_deconv_reg* r, int mem);
-/* CTAs per epoch of the per-epoch kernel (thread-block cluster size): 0 = automatic, or 1/2/4/8 */
+/* CTAs per epoch of the per-epoch kernel (thread-block cluster size): 0 = automatic, or 1 .. 8 (any size: bands of ceil(n / size) rows) */
 int lcb_deconv_set_cluster(void* handle, int ctas_per_epoch);
 int lcb_deconv_get_cluster(void* handle);
 /* Epoch sharding: total number of epochs over all ranks, global index of this rank's first epoch, and

@@ -1455,8 +1455,8 @@ int lcb_deconv_create(const lcb_deconv_problem* p, int mem, void* stream, void**
 int lcb_deconv_set_cluster(void* handle, int ctas_per_epoch) {
     DeconvHandle* H = (DeconvHandle*)handle;
     LCB_REQUIRE(H, "lcb_deconv_set_cluster: NULL handle");
-    LCB_REQUIRE(ctas_per_epoch == 0 || ctas_per_epoch == 1 || ctas_per_epoch == 2 || ctas_per_epoch == 4 || ctas_per_epoch == 8,
-                "lcb_deconv_set_cluster: CTAs per epoch must be 0 (automatic), 1, 2, 4 or 8");
+    LCB_REQUIRE(ctas_per_epoch >= 0 && ctas_per_epoch <= DC_CSMAX,
+                "lcb_deconv_set_cluster: CTAs per epoch must be 0 (automatic) or 1 .. %d", DC_CSMAX);
     H->CS_user = ctas_per_epoch; H->CS = 0;
     return LCB_OK;
 }
