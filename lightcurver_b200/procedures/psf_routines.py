@@ -17,7 +17,7 @@ def build_psf_batch(images, noisemaps, subsampling_factor, masks=None, n_iter_an
                     field_distortion=False, stamp_coordinates=None, regularization_strength_scales=None,
                     regularization_strength_hf=None, adabelief_learning_rate=None,
                     conventions: Conventions = DEFAULT, return_dicts=True, noise_propagation='SLIT', noise_samples=100,
-                    noise_seed=1, devices=None):
+                    noise_seed=1, devices=None, star_counts=None):
     """Fits F frames in one library call.
 
     images / noisemaps / masks: sequences (length F) of arrays (N_f, n, n) -- N_f may differ per
@@ -26,11 +26,18 @@ def build_psf_batch(images, noisemaps, subsampling_factor, masks=None, n_iter_an
     method STARRED's build_psf passes to propagate_noise [R]); both give the starlet-space weights W of stage 2.
     devices: None (current CUDA device), 'all', a count or a list of device indices: the frames are split into contiguous
     blocks balanced by their star counts, one host thread per GPU, no collective (frames are independent).
+    star_counts: when given, ``images`` / ``noisemaps`` / ``masks`` are already CONCATENATED arrays (sumN, n, n) -- e.g. views
+    of the page-locked staging buffer of ``stamp_store`` -- and star_counts[f] is the number of stars of frame f.
     Returns a list of per-frame result dicts shaped like STARRED's (``return_dicts``), or the raw
     batched arrays.
     """
     devs = engine.resolve_devices(devices)
-    if len(devs) > 1 and len(images) > 1:
+    n_frames = len(images) if star_counts is None else len(star_counts)
+    if star_counts is not None and len(devs) > 1 and n_frames > 1:      # per-device blocks need per-frame slices
+        offs = np.concatenate([[0], np.cumsum(np.asarray(star_counts, np.int64))])
+        split = lambda a: None if a is None else [a[offs[f]:offs[f + 1]] for f in range(n_frames)]
+        images, noisemaps, masks, star_counts = split(images), split(noisemaps), split(masks), None
+    if len(devs) > 1 and n_frames > 1:
         counts = [int(np.shape(im)[0]) for im in images]
         blocks = engine.split_by_work(counts, len(devs))
         fw = np.broadcast_to(np.asarray(3.0 if guess_fwhm_pixels is None else guess_fwhm_pixels, dtype=np.float64), (len(images),))
@@ -57,19 +64,21 @@ def build_psf_batch(images, noisemaps, subsampling_factor, masks=None, n_iter_an
     cv = conventions
     from ..conventions import apply_to_library
     apply_to_library(cv)                       # the kernels read the library-wide conventions at call time
-    F = len(images)
+    F = n_frames
     k = int(subsampling_factor)
-    counts = [int(np.shape(im)[0]) for im in images]
+    counts = [int(c) for c in star_counts] if star_counts is not None else [int(np.shape(im)[0]) for im in images]
     if F == 0:
         return []
     if min(counts) < 1:
         raise ValueError("every frame needs at least one star (psf_modelling.py:154-160 skips empty frames)")
-    n = int(np.shape(images[0])[-1])
+    n = int(np.shape(images)[-1]) if star_counts is not None else int(np.shape(images[0])[-1])
     off = np.zeros(F + 1, np.int32)
     off[1:] = np.cumsum(counts)
     sumN = int(off[-1])
-    cat = lambda seq: (np.asarray(seq).reshape(sumN, n, n) if isinstance(seq, np.ndarray)
-                       else np.concatenate([np.asarray(x) for x in seq]))
+    def cat(seq):
+        if isinstance(seq, np.ndarray):            # already concatenated (star_counts form): no copy
+            return np.asarray(seq).reshape(sumN, n, n)
+        return np.concatenate([np.asarray(x) for x in seq])
     # normalisation (A.4), NaN / mask policy, weights and the smart guess run on the device (lcb_psf_prepare_batch):
     # the raw arrays are uploaded once (asynchronously when they are pinned) and stay there for the fit
     prep = engine.psf_prepare_batch(cat(images), cat(noisemaps), None if masks is None else cat(masks), off, k,

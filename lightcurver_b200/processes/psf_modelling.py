@@ -136,19 +136,24 @@ def check_psf_exists(db, frame_id, psf_ref, combined_footprint_hash):
 
 
 def model_all_psfs_batched(store, db, frames, stars_for_frame, user_config, combined_footprint_hash,
-                           automatic_mask_fn=mask_surrounding_stars, on_result=None, devices=None):
+                           automatic_mask_fn=mask_surrounding_stars, on_result=None, devices=None, stager=None):
     """One pass over ``frames`` (iterable of mappings with id, image_relpath, seeing_pixels, pixel_scale):
     gather every frame that needs a PSF, fit them all in ONE ``build_psf_batch`` call, then write the per-frame
     products to the store and the PSFs table in the original order.
 
     stars_for_frame(frame_id) -> list of mappings with 'name' and 'gaia_id' (select_stars_for_a_frame's rows).
     on_result(frame, result, datas, noisemaps, masks, names) is called per frame (diagnostic plot hook, :182-187).
+    automatic_mask_fn: per-stamp masking of neighbouring objects (:129-135; ``sep`` based by default), None = no masking.
+    stager: a reusable ``stamp_store.StampStager`` (page-locked staging buffers; one is created per call otherwise).
+    The stamps are gathered in bulk (``stamp_store.gather_psf_batch``), the products are written back group by group and the
+    PSFs rows in ONE executemany.
     Returns the list of (frame_id, psf_ref, chi2) written.
     """
     logger = logging.getLogger('lightcurver.psf_modelling')
+    from .. import stamp_store
     db.execute(PSFS_DDL)
     k = int(user_config['subsampling_factor'])
-    pending = []
+    cand = []
     for frame in frames:
         stars = list(stars_for_frame(frame['id']))
         if len(stars) == 0:
@@ -158,54 +163,64 @@ def model_all_psfs_batched(store, db, frames, stars_for_frame, user_config, comb
         if check_psf_exists(db, frame['id'], psf_ref, combined_footprint_hash) and not user_config.get('redo_psf', False):
             logger.info(f"The frame with id {frame['id']} already has a PSF (ref {psf_ref}), redo flag not set. Skipping.")
             continue
-        rel = frame['image_relpath']
-        ids = [s['gaia_id'] for s in stars]
-        datas = np.array([store[f"{rel}/data/{g}"][...] for g in ids])
-        noisemaps = np.array([store[f"{rel}/noisemap/{g}"][...] for g in ids])
-        cosmics = np.array([store[f"{rel}/cosmicsmask/{g}"][...] for g in ids]).astype(bool)
-        auto = np.array([automatic_mask_fn(d, nm) for d, nm in zip(datas, noisemaps)])
-        datas, noisemaps, masks, keep = prepare_psf_inputs(datas, noisemaps, cosmics, auto)
-        if len(datas) == 0:
+        cand.append((frame, stars, psf_ref))
+    if not cand:
+        return []
+    # ---- gather: every stamp of every pending frame into ONE page-locked staging buffer (three group lookups per frame)
+    stager = stager if stager is not None else stamp_store.StampStager()
+    datas, noisemaps, cosmics, off = stamp_store.gather_psf_batch(store, [c[0] for c in cand], [[s['gaia_id'] for s in c[1]] for c in cand],
+                                                                  stager)
+    # ---- host policies of psf_modelling.py:128-153, vectorised over the whole batch (in place in the staging buffer)
+    if automatic_mask_fn is None:
+        masks = ~cosmics
+    else:
+        masks = ~cosmics & np.array([automatic_mask_fn(d, nm) for d, nm in zip(datas, noisemaps)], dtype=bool).reshape(cosmics.shape)
+    isnan = np.isnan(datas) & np.isnan(noisemaps)
+    datas[isnan] = 0.
+    noisemaps[isnan] = 1.0
+    masks[isnan] = False
+    keep = ~((~masks).sum(axis=(1, 2)) > MASK_THRESHOLD_FRACTION * datas.shape[1] * datas.shape[2])
+    pending, counts, sel = [], [], []
+    for f, (frame, stars, psf_ref) in enumerate(cand):
+        kf = np.nonzero(keep[off[f]:off[f + 1]])[0]
+        if len(kf) == 0:
             logger.warning(f"The frame with id {frame['id']} had {len(stars)} reference stars, but none could be used "
                            "due to too many masked pixels. Skipping.")
             continue
-        pending.append(dict(frame=frame, psf_ref=psf_ref, datas=datas, noisemaps=noisemaps, masks=masks,
-                            names=[stars[i]['name'] for i in keep], n_before=len(stars)))
+        pending.append(dict(frame=frame, psf_ref=psf_ref, names=[stars[i]['name'] for i in kf], n_before=len(stars),
+                            rows=off[f] + kf))
+        counts.append(len(kf))
+        sel.append(off[f] + kf)
     if not pending:
         return []
-    results = build_psf_batch([p['datas'] for p in pending], [p['noisemaps'] for p in pending], k,
-                              masks=[p['masks'] for p in pending],
+    sel = np.concatenate(sel)
+    if len(sel) != len(keep):                 # some stars dropped: compact (one copy); otherwise the staging views go straight up
+        datas, noisemaps, masks = datas[sel], noisemaps[sel], masks[sel]
+    results = build_psf_batch(datas, noisemaps, k, masks=masks, star_counts=counts,
                               n_iter_analytic=user_config['psf_n_iter_analytic'],
                               n_iter_adabelief=user_config['psf_n_iter_pixels'],
                               guess_method_star_position='center',
                               guess_fwhm_pixels=np.array([float(p['frame']['seeing_pixels']) for p in pending]),
                               field_distortion=user_config.get('field_distortion', False),
                               devices=devices)          # None: current GPU; 'all': every visible GPU, one host thread each
-    written = []
+    written, rows = [], []
+    pos = 0
     for p, result in zip(pending, results):
         frame, psf_ref = p['frame'], p['psf_ref']
         km = result['kwargs_psf']['kwargs_moffat']
         fwhm_moffat_arcseconds = float((0.5 * (km['fwhm_x'] + km['fwhm_y']) * frame['pixel_scale']).item())
         loss_history = result['adabelief_extra_fields']['loss_history']
         if on_result is not None:
-            on_result(frame, result, p['datas'], p['noisemaps'], p['masks'], p['names'])
-        frame_group = store[frame['image_relpath']]
-        if psf_ref in frame_group.keys():
-            del frame_group[psf_ref]
-        psf_group = frame_group.create_group(psf_ref)
-        psf_group['narrow_psf'] = np.array(result['narrow_psf'])
-        psf_group['full_psf'] = np.array(result['full_psf'])
-        psf_group['subsampling_factor'] = np.array([k])
-        distortion_group = psf_group.create_group('distortion')
-        for key, value in result['kwargs_psf']['kwargs_distortion'].items():
-            distortion_group[key] = value
+            sl = slice(pos, pos + len(p['names']))
+            on_result(frame, result, datas[sl], noisemaps[sl], masks[sl], p['names'])
+        pos += len(p['names'])
+        stamp_store.write_psf_products(store, frame, psf_ref, result['narrow_psf'], result['full_psf'], k,
+                                       result['kwargs_psf']['kwargs_distortion'])
         rld = relative_loss_differential(loss_history)
-        db.execute("REPLACE INTO PSFs (frame_id, chi2, relative_loss_differential, psf_ref, combined_footprint_hash, "
-                   "subsampling_factor, fwhm_moffat_arcseconds) VALUES (?,?,?,?,?,?,?)",
-                   (frame['id'], float(result['chi2']), rld, psf_ref, combined_footprint_hash, k, fwhm_moffat_arcseconds))
+        rows.append((frame['id'], float(result['chi2']), rld, psf_ref, combined_footprint_hash, k, fwhm_moffat_arcseconds))
         written.append((frame['id'], psf_ref, float(result['chi2'])))
         logger.info(f"PSF built for frame with id {frame['id']}. The reference is {psf_ref}, that is {p['n_before']} stars "
                     f"available, and {len(p['names'])} actually used after filtering of masked pixels. "
                     f"The reduced chi2 is {result['chi2']:.02f}.")
-    db.commit()
+    stamp_store.replace_psf_rows(db, rows)               # one executemany + one commit for the batch
     return written

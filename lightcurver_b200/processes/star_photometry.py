@@ -214,17 +214,20 @@ def gather_star_stack(store, frames, gaia_id, psf_ref_for_frame):
 
 
 def do_star_photometry_batched(store, db, stars, frames_for_star, psf_ref_for_frame, user_config,
-                               combined_footprint_hash, on_result=None):
+                               combined_footprint_hash, on_result=None, stager=None):
     """Batched form of do_star_photometry (star_photometry.py:232-373).
 
     stars: iterable of mappings with 'name', 'gaia_id'; frames_for_star(gaia_id) -> list of frame mappings (id,
     image_relpath) that need a measurement (get_frames_for_star's rows); psf_ref_for_frame(frame_id) -> psf_ref.
-    With the default pipeline flags (no shared background, no per-epoch constant) every (star, frame) item of every
-    star goes into ONE library call; with the background flags each star is a joint fit
-    (do_one_star_forward_modelling).  Rows are upserted with the reference's conflict rule.
+    The stamps of every (star, frame) item are gathered in bulk (``stamp_store.gather_photometry_batch``: groups resolved once
+    per frame, the narrow PSF of a frame read once for all its stars, one page-locked staging buffer).  With the default
+    pipeline flags (no shared background, no per-epoch constant) every item of every star goes into ONE K2 call; with the
+    background flags the stars are joint fits (shared h / c / clip norm per star).  Rows are upserted with the reference's
+    conflict rule, one executemany per star batch.
     Returns {gaia_id: result dict}.
     """
     logger = logging.getLogger('lightcurver.star_photometry')
+    from .. import stamp_store
     cv = DEFAULT
     from ..conventions import apply_to_library
     apply_to_library(cv)
@@ -238,38 +241,42 @@ def do_star_photometry_batched(store, db, stars, frames_for_star, psf_ref_for_fr
         if len(frames) == 0:
             logger.info(f"Star {star['name']}: no new frames to process for this one. Skipping")
             continue
-        data, noisemap, psf = gather_star_stack(store, frames, star['gaia_id'], psf_ref_for_frame)
-        work.append(dict(star=star, frames=frames, data=data, noisemap=noisemap, psf=psf))
+        work.append(dict(star=star, frames=frames))
     results = {}
     if not work:
         return results
+    d32, n32, cosmic, psfs, psf_index, off = stamp_store.gather_photometry_batch(
+        store, [(wk['star']['gaia_id'], wk['frames']) for wk in work], psf_ref_for_frame, stager)
+    # star_photometry.py:309-316 on the whole batch: doubly-NaN pixels -> (0, 1e7); the noise map of every epoch that has ANY
+    # masked pixel is multiplied by 1000 (`noisemap[np.where(~mask)[0]] *= 1000.`, once per epoch)
+    data, noisemap = d32.astype(np.float64), n32.astype(np.float64)
+    isnan = np.isnan(data) & np.isnan(noisemap)
+    data[isnan] = 0.
+    noisemap[isnan] = 1e7
+    noisemap[cosmic.any(axis=(1, 2))] *= 1000.
+    for i, wk in enumerate(work):
+        sl = slice(int(off[i]), int(off[i + 1]))
+        wk['sl'], wk['data'], wk['noisemap'] = sl, data[sl], noisemap[sl]
     if coupled:
         for wk in work:
             wk['result'] = do_one_star_forward_modelling(
-                wk['data'], wk['noisemap'], wk['psf'], k, n_iter=n_iter,
+                wk['data'], wk['noisemap'], psfs[psf_index[wk['sl']]], k, n_iter=n_iter,
                 uniform_background_per_epoch=user_config.get('star_photometry_uniform_background_per_epoch', False),
                 starlet_global_background=user_config.get('star_photometry_starlet_global_background', False))
     else:
         # per star: scale (:47-49), initial flux guess (:55-64); then one K2 launch over all stars' epochs
-        n = work[0]['data'].shape[-1]
-        ds, ws, ps, a0s, offs = [], [], [], [], [0]
+        n = data.shape[-1]
+        a0 = np.empty(data.shape[0], np.float32)
         for wk in work:
             d, nm = wk['data'], wk['noisemap']
             wk['scale'] = float(np.nanmax(d))
-            d /= wk['scale']
+            d /= wk['scale']                       # in place on the batch arrays, like the reference on its own (:48-49)
             nm /= wk['scale']
-            a_est = _initial_flux_guess(d) * cv.amplitude_per_flux(k)
-            d32, w32 = stamps_and_weights(d, nm)
-            ds.append(d32)
-            ws.append(w32)
-            ps.append(np.asarray(wk['psf'], np.float32))
-            a0s.append(a_est.astype(np.float32))
-            offs.append(offs[-1] + d.shape[0])
-        B = offs[-1]
-        out = engine.phot_fit_batch(np.concatenate(ds), np.concatenate(ws), np.concatenate(ps),
-                                    np.arange(B, dtype=np.int32), np.concatenate(a0s), k, n_iter, lr=1e-3, schedule=True)
-        for i, wk in enumerate(work):
-            sl = slice(offs[i], offs[i + 1])
+            a0[wk['sl']] = _initial_flux_guess(d) * cv.amplitude_per_flux(k)
+        ds, ws = stamps_and_weights(data, noisemap)
+        out = engine.phot_fit_batch(ds, ws, psfs, psf_index, a0, k, n_iter, lr=1e-3, schedule=True)
+        for wk in work:
+            sl = wk['sl']
             residuals = out['residuals'][sl].astype(np.float64)             # data - model, scaled units
             with np.errstate(divide='ignore', invalid='ignore'):
                 chi2_per_frame = np.nansum(residuals ** 2 / wk['noisemap'] ** 2, axis=(1, 2)) / n ** 2
@@ -284,11 +291,12 @@ def do_star_photometry_batched(store, db, stars, frames_for_star, psf_ref_for_fr
                                  'kwargs_background': {'h': np.zeros((n * k) ** 2), 'mean': np.zeros(sl.stop - sl.start)},
                                  'kwargs_sersic': {}},
             }
+    flux_rows = []
+    from .psf_modelling import relative_loss_differential
     for wk in work:
         result, star = wk['result'], wk['star']
         if on_result is not None:
             on_result(star, wk['data'], wk['noisemap'], result)
-        from .psf_modelling import relative_loss_differential
         rld = relative_loss_differential(result['loss_curve'])
         # non-finite measurements (per-item status of the library, or a NaN that slipped through) never reach the database:
         # the reference has no such guard because a NaN loss aborts its whole task (failure detection)
@@ -298,11 +306,10 @@ def do_star_photometry_batched(store, db, stars, frames_for_star, psf_ref_for_fr
         if len(good) != len(wk['frames']):
             logger.warning(f"Star {star['name']}: {len(wk['frames']) - len(good)} non-finite measurement(s) skipped "
                            f"(frames {[wk['frames'][j]['id'] for j in range(len(wk['frames'])) if j not in good]})")
-        flux_data = [(combined_footprint_hash, wk['frames'][j]['id'], star['gaia_id'], float(result['fluxes'][j]),
-                      float(result['fluxes_uncertainties'][j]), float(result['chi2_per_frame'][j]), rld)
-                     for j in good]
-        update_star_fluxes(db, flux_data)
+        flux_rows += [(combined_footprint_hash, wk['frames'][j]['id'], star['gaia_id'], float(result['fluxes'][j]),
+                       float(result['fluxes_uncertainties'][j]), float(result['chi2_per_frame'][j]), rld) for j in good]
         results[star['gaia_id']] = result
         logger.info(f"Measured star {star['name']} in {len(wk['frames'])} frames. "
                     f"The global reduced chi2 is {result['chi2']:.02f}.")
+    update_star_fluxes(db, flux_rows)              # one executemany + one commit for every star of the batch
     return results
