@@ -90,6 +90,7 @@ struct ProfRec { const char* name; cudaEvent_t e0, e1; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 static std::mutex g_prof_mu;          // launches may come from several host threads (one per GPU)
+bool lcb_profiling() { return g_prof_on; }
 
 LcbProfScope::LcbProfScope(const char* name, cudaStream_t s) : idx(-1), st(s) {
     if (!g_prof_on) return;

@@ -88,6 +88,35 @@ __device__ __forceinline__ void lcb_tap(const DevConv& cv, int k, float fr, int 
     de = d * sc;
 }
 
+// ---------------------------------------------------------------- bulk asynchronous copies (TMA, 1-D form) + mbarrier
+// cp.async.bulk moves a contiguous, 16-byte aligned block global -> shared through the TMA unit without occupying the
+// issuing warps; completion is signalled on an mbarrier in shared memory (transaction-byte count).  One thread arms the
+// barrier (expect_tx) and issues the copies; every consumer waits on the barrier's phase parity.
+__device__ __forceinline__ unsigned lcb_smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void lcb_mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(lcb_smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");      // visible to the async proxy
+}
+
+__device__ __forceinline__ void lcb_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(lcb_smem_addr(bar)), "r"(bytes) : "memory");
+}
+
+// dst (shared, 16 B aligned), src (global, 16 B aligned), bytes (multiple of 16)
+__device__ __forceinline__ void lcb_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(lcb_smem_addr(dst)), "l"(src), "r"(bytes), "r"(lcb_smem_addr(bar)) : "memory");
+}
+
+__device__ __forceinline__ void lcb_mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(lcb_smem_addr(bar)), "r"(parity) : "memory");
+    }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

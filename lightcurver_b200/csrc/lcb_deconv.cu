@@ -36,6 +36,7 @@
 namespace cg = cooperative_groups;
 
 void lcb_build_noise_table(int nu, int J, std::vector<float>& tab);
+bool lcb_profiling();
 int lcb_noise_weights_launch(int F, int nu, int J, const float* tab, float* W, float* work,
                              size_t work_per_frame, cudaStream_t st);
 
@@ -80,6 +81,8 @@ struct DeconvDev {
     float *planes;                       // [3][nu^2] starlet scratch + Tj [J][nu^2]
     float *model;                        // [E][n][n] (written when requested)
     float *loss_hist;                    // [cap]
+    unsigned *band_ctr;                  // [DC_CSMAX + 1] arrival counters of the fused reduction (self-resetting)
+    int *ictl;                           // [2] device-resident iteration index and exchange sequence number (graph replay)
     DevConv cv;
     DeconvComm cm;
 };
@@ -247,13 +250,17 @@ __device__ __forceinline__ void conv_line_T(const float* __restrict__ rr, const 
 // ---------------------------------------------------------------- setup: polyphase box-folded PSF
 // S[e][pv*k+pu][av-A0][au-A0] = stilde(tv = j0 - k av - pv, tu = j0 - k au - pu),
 // stilde(tv,tu) = sum_{kv,ku<k} s[tv+kv][tu+ku]   (zero outside the P x P array).
+// Rows are zero padded to NAp = roundup(NA, 8) taps, so that one epoch's kernel is ONE contiguous, 16-byte aligned block that the
+// per-epoch kernel fetches with a single bulk asynchronous copy (TMA) straight into its shared-memory layout.
 __global__ void k_deconv_fold_psf(const float* psf, float* S, int E, int P, int k, int NA, int A0) {
     const int e = blockIdx.x;
     const int j0 = (P - 1) / 2;
+    const int NAp = (NA + 7) & ~7;
     const float* s = psf + (size_t)e * P * P;
-    float* out = S + (size_t)e * k * k * NA * NA;
-    for (int i = threadIdx.x; i < k * k * NA * NA; i += blockDim.x) {
-        const int ph = i / (NA * NA), r = i % (NA * NA), av = r / NA + A0, au = r % NA + A0;
+    float* out = S + (size_t)e * k * k * NA * NAp;
+    for (int i = threadIdx.x; i < k * k * NA * NAp; i += blockDim.x) {
+        const int ph = i / (NA * NAp), r = i % (NA * NAp), av = r / NAp + A0, au = r % NAp + A0;
+        if (r % NAp >= NA) { out[i] = 0.f; continue; }
         const int pv = ph / k, pu = ph % k;
         const int tv = j0 - k * av - pv, tu = j0 - k * au - pu;
         float acc = 0.f;
@@ -290,9 +297,13 @@ __device__ __forceinline__ float block_sum(float v, float* red, int tid) {
 }
 
 // ---------------------------------------------------------------- per-epoch kernel (cluster of CS CTAs)
-// flags: 1 = write the model image; 2 = propagate the weights instead of the residuals (noise weights).
+// flags: 1 = write the model image; 2 = propagate the weights instead of the residuals (noise weights); 4 = fused reduction:
+// the LAST cluster to finish a band of rows sums that band of dL/dh over the local epochs (fixed order) into red[] -- or, with
+// epochs sharded over GPUs (seq > 0), pushes the sums straight into the receive slots of every peer over NVLink -- and the last
+// band raises the peers' flags: the exchange starts from the tail of the epoch kernel, there is no separate reduce launch.
+// seq_arg < 0: the sequence number is read from D.ictl[1] (CUDA-graph replay: identical arguments every iteration).
 template <int K>
-__global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int flags, int CS) {
+__global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int flags, int CS, int seq_arg) {
     cg::cluster_group cl = cg::this_cluster();
     const int want_model = flags & 1;
     const bool noise = (flags & 2) != 0;
@@ -353,9 +364,16 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
         remr[tid] = (CS > 1) ? (float*)cl.map_shared_rank(rsm, tid) : rsm;
         remflo[tid] = bc.flo; remrlo[tid] = bc.rlo; remrhi[tid] = bc.rhi;
     }
-    for (int i = tid; i < kk * NA * NAp; i += DC_THREADS) {
-        const int t = i % NAp, row = i / NAp;
-        Ssm[i] = (t < NA) ? __ldg(D.S + (size_t)e * kk * NA * NA + (size_t)row * NA + t) : 0.f;
+    // the folded PSF of the epoch (kk x NA x NAp floats, ~21 KB at cfg4) comes in through the TMA unit: one thread arms an
+    // mbarrier and issues ONE bulk copy; the other warps go on zeroing the planes and building f, and wait just before the
+    // forward pass
+    __shared__ __align__(8) unsigned long long s_bar;
+    if (tid == 0) lcb_mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned bytes = (unsigned)(kk * NA * NAp) * 4u;
+        lcb_mbar_expect_tx(&s_bar, bytes);
+        lcb_bulk_g2s(Ssm, D.S + (size_t)e * kk * NA * NAp, bytes, &s_bar);
     }
     {   // zero the planes (the gaps between rows are the halos)
         float4* z = reinterpret_cast<float4*>(sm + L.oF);
@@ -437,6 +455,7 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
     // ---- forward: m = mean + 1/k^2 sum_ph corr(f_ph, S_ph);  r = w (m - d).  A task = XB outputs of one row for
     //      one slice of the NA kernel rows (SPLIT slices on adjacent lanes, summed with shuffles) so that a narrow
     //      band still gives every thread a task.
+    lcb_mbar_wait(&s_bar, 0);                     // folded PSF landed in shared memory
     const float dscale = D.cv.mean ? 1.f / (float)kk : 1.f;
     const float* dat = D.data + (size_t)e * n * n;
     const float* wgt = D.weight + (size_t)e * n * n;
@@ -717,6 +736,81 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
         }
     }
     cl.sync();                                    // #3: no CTA leaves while its shared memory may still be read
+    if (!(flags & 4)) return;
+
+    // ---- fused reduction over the local epochs (replaces k_deconv_reduce inside lcb_deconv_run)
+    __shared__ int s_last;
+    __threadfence();                              // this CTA's rows of Gh (and, rank 0, the per-epoch scalars) are visible device wide
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(D.band_ctr + crank, 1u) == (unsigned)(D.E - 1)) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int seq = (D.cm.world > 1) ? ((seq_arg < 0) ? D.ictl[1] : seq_arg) : 0;
+    const int Wn = D.cm.world, parity = seq & 1, nu2 = nu * nu;
+    auto emit = [&](int i, float v) {
+        if (seq == 0) D.red[i] = v;
+        else for (int r = 0; r < Wn; ++r) D.cm.slots[r][((size_t)parity * Wn + D.cm.rank) * D.tot + i] = v;
+    };
+    {
+        const int cnt = (vhi - vlo) * nu;
+        const float* src = D.Gh + (size_t)vlo * nu;
+        for (int i0 = tid; i0 < cnt; i0 += 4 * DC_THREADS) {      // 4 pixels x 4 epochs in flight per thread, epochs summed in order
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            if (D.free_h) {
+                for (int e0 = 0; e0 < D.E; e0 += 4) {
+                    float v[4][4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+#pragma unroll
+                        for (int ee = 0; ee < 4; ++ee) {
+                            const int i = i0 + q * DC_THREADS;
+                            v[q][ee] = (i < cnt && e0 + ee < D.E) ? __ldcg(src + (size_t)(e0 + ee) * nu2 + i) : 0.f;
+                        }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+#pragma unroll
+                        for (int ee = 0; ee < 4; ++ee) acc[q] += v[q][ee];
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const int i = i0 + q * DC_THREADS; if (i < cnt) emit(vlo * nu + i, acc[q]); }
+        }
+    }
+    if (crank == 0 && tid < D.tot - nu2) {       // per-epoch scalars: every rank-0 CTA wrote its own before raising the band counter
+        const int i = nu2 + tid, iflux = red_flux(D);
+        float sacc = 0.f;
+        if (i < nu2 + 2 * M) {
+            for (int ee = 0; ee < D.E; ++ee) sacc += __ldcg(D.gc + (size_t)ee * 2 * M + (i - nu2));
+        } else if (i == nu2 + 2 * M) {
+            for (int ee = 0; ee < D.E; ++ee) sacc += __ldcg(D.eloss + ee);
+        } else if (i == nu2 + 2 * M + 1) {
+            for (int ee = 0; ee < D.E; ++ee)
+                for (int p = 0; p < np; ++p) {
+                    const bool is_free = (p < M) ? D.free_a : (p < M + 2) ? D.free_d : D.free_mean;
+                    const float g = __ldcg(D.ep_g + (size_t)ee * np + p);
+                    if (is_free) sacc = fmaf(g, g, sacc);
+                }
+        } else if (i < iflux + 4 * M) {
+            const int q = (i - iflux) / M, m = (i - iflux) % M;
+            const float Kf = D.fu[m];
+            for (int ee = 0; ee < D.E; ++ee) {
+                const float a = __ldcg(D.ep + (size_t)ee * np + m) - Kf, g = __ldcg(D.ep_g + (size_t)ee * np + m);
+                sacc += (q == 0) ? a : (q == 1) ? a * a : (q == 2) ? g : g * a;
+            }
+        }
+        emit(i, sacc);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+        D.band_ctr[crank] = 0;                      // next use: the next launch of this kernel
+        if (atomicAdd(D.band_ctr + DC_CSMAX, 1u) == (unsigned)(CS - 1)) {
+            D.band_ctr[DC_CSMAX] = 0;
+            __threadfence_system();
+            if (seq > 0) for (int r = 0; r < Wn; ++r) *(volatile int*)(D.cm.flags[r] + parity * Wn + D.cm.rank) = seq;
+        }
+    }
 }
 
 // ---------------------------------------------------------------- reduction over the local epochs (+ push to the peers)
@@ -1078,7 +1172,12 @@ __device__ __forceinline__ void cluster_sums(float (&v)[N], float* red, float* g
 // update).  seq > 0: red[] is first assembled from the receive slots of all ranks (summed in rank order: bit-identical
 // everywhere).  with_reg: planes[0] / ctl[6] hold the starlet gradient / value from k_deconv_starlet.
 __global__ void __cluster_dims__(DU_CTAS, 1, 1) __launch_bounds__(DU_THREADS)
-k_deconv_update(DeconvDev D, int it, int n_iter, float lr0, int schedule, int seq, int with_reg, float* grad_h_out, float* grad_c_out, float* loss_out) {
+k_deconv_update(DeconvDev D, int it_arg, int n_iter, float lr0, int schedule, int seq_arg, int with_reg, float* grad_h_out, float* grad_c_out, float* loss_out) {
+    // it_arg == -2: iteration index and sequence number come from D.ictl (identical launch arguments for every iteration, so that
+    // one captured CUDA graph of an iteration can be replayed); the kernel advances them at its end
+    const bool dev_it = (it_arg == -2);
+    const int it = dev_it ? D.ictl[0] : it_arg;
+    const int seq = dev_it ? ((D.cm.world > 1) ? D.ictl[1] : 0) : seq_arg;
     __shared__ float red[4 * (DU_THREADS / 32)];
     __shared__ float fus[4 * DC_MMAX];
     cg::cluster_group cl = cg::this_cluster();
@@ -1197,6 +1296,10 @@ k_deconv_update(DeconvDev D, int it, int n_iter, float lr0, int schedule, int se
         D.c[tid] = cvv; D.c_mu[tid] = mu; D.c_nu[tid] = nv;
     }
     if (gtid == 0) { D.ctl[0] = cs; D.ctl[1] = lr; D.ctl[2] = bc.inv_bc1; D.ctl[3] = bc.inv_bc2; D.ctl[4] = 1.f; }
+    if (dev_it) {
+        cl.sync();                                   // every CTA has read ictl
+        if (gtid == 0) { D.ictl[0] = it + 1; D.ictl[1] = D.ictl[1] + 1; }
+    }
 }
 
 // adds the flux-uniformity gradient to the stored per-epoch gradients (evaluation path only: lcb_deconv_loss_grad)
@@ -1215,6 +1318,7 @@ struct DeconvHandle {
     std::vector<void*> ipc_open;         // peer mappings to close
     void* comm_buf;                      // own receive buffer (IPC exported)
     cudaStream_t st;
+    cudaStream_t st_own;                 // created when the caller passes the NULL stream (the legacy stream cannot be captured into a graph)
     cudaStream_t st2;                    // the starlet term of h runs here, concurrently with the epoch kernel
     cudaEvent_t ev_h, ev_go, ev_reg;     // h final (main stream) -> starlet may start ; starlet dispatched -> epoch may start ; starlet done -> update
     bool reg_pending, starlet_attr;
@@ -1266,7 +1370,7 @@ static int choose_cluster(const DeconvHandle* H) {
     return cs;
 }
 
-static int launch_epoch(DeconvHandle* H, int flags) {
+static int launch_epoch(DeconvHandle* H, int flags, int seq = 0) {
     DeconvDev& D = H->D;
     if (H->CS == 0) {
         H->CS = choose_cluster(H);
@@ -1291,10 +1395,10 @@ static int launch_epoch(DeconvHandle* H, int flags) {
     cfg.attrs = at; cfg.numAttrs = 1;
     LcbProfScope ps("k_deconv_epoch", H->st);
     switch (D.k) {
-        case 1: LCB_CUDA(cudaLaunchKernelEx(&cfg, k_deconv_epoch<1>, D, flags, H->CS)); break;
-        case 2: LCB_CUDA(cudaLaunchKernelEx(&cfg, k_deconv_epoch<2>, D, flags, H->CS)); break;
-        case 3: LCB_CUDA(cudaLaunchKernelEx(&cfg, k_deconv_epoch<3>, D, flags, H->CS)); break;
-        default: LCB_CUDA(cudaLaunchKernelEx(&cfg, k_deconv_epoch<4>, D, flags, H->CS)); break;
+        case 1: LCB_CUDA(cudaLaunchKernelEx(&cfg, k_deconv_epoch<1>, D, flags, H->CS, seq)); break;
+        case 2: LCB_CUDA(cudaLaunchKernelEx(&cfg, k_deconv_epoch<2>, D, flags, H->CS, seq)); break;
+        case 3: LCB_CUDA(cudaLaunchKernelEx(&cfg, k_deconv_epoch<3>, D, flags, H->CS, seq)); break;
+        default: LCB_CUDA(cudaLaunchKernelEx(&cfg, k_deconv_epoch<4>, D, flags, H->CS, seq)); break;
     }
     return LCB_OK;
 }
@@ -1369,6 +1473,7 @@ int lcb_deconv_destroy(void* handle) {
     if (!H) return LCB_OK;
     cudaStreamSynchronize(H->st);
     if (H->st2) { cudaStreamSynchronize(H->st2); cudaStreamDestroy(H->st2); }
+    if (H->st_own) cudaStreamDestroy(H->st_own);
     if (H->ev_h) cudaEventDestroy(H->ev_h);
     if (H->ev_go) cudaEventDestroy(H->ev_go);
     if (H->ev_reg) cudaEventDestroy(H->ev_reg);
@@ -1387,6 +1492,13 @@ int lcb_deconv_create(const lcb_deconv_problem* p, int mem, void* stream, void**
     if (lcb_device_count() == 0) { lcb_set_error("no CUDA device: liblcb has no CPU fallback"); return LCB_ERR_CUDA; }
     DeconvHandle* H = new DeconvHandle();
     H->st = (cudaStream_t)stream;
+    H->st_own = nullptr;
+    if (!H->st) {
+        // a BLOCKING stream of our own: it keeps the implicit ordering with the legacy default stream (torch's current stream
+        // unless the caller changed it) and, unlike the legacy stream, can be captured into a CUDA graph
+        if (cudaStreamCreate(&H->st_own) != cudaSuccess) { lcb_set_error("lcb_deconv_create: cannot create a stream"); delete H; return LCB_ERR_CUDA; }
+        H->st = H->st_own;
+    }
     H->comm_buf = nullptr; H->CS = 0; H->CS_user = 0; H->seq = 0;
     H->st2 = nullptr; H->ev_h = nullptr; H->ev_go = nullptr; H->ev_reg = nullptr; H->reg_pending = false; H->starlet_attr = false; H->noise_tab = nullptr; H->W_spare = nullptr;
     int prio_lo = 0, prio_hi = 0;
@@ -1417,13 +1529,14 @@ int lcb_deconv_create(const lcb_deconv_problem* p, int mem, void* stream, void**
     const size_t E = D.E, nn = (size_t)D.n * D.n, pp = (size_t)D.nu * D.nu, np = D.M + 3, kk = (size_t)D.k * D.k;
     int rc = 0;
 #define AL(field, count, zero) if ((rc = dalloc(H, (void**)&D.field, (count) * 4, zero))) { lcb_deconv_destroy(H); return rc; }
-    AL(data, E * nn, false) AL(weight, E * nn, false) AL(S, E * kk * D.NA * D.NA, false)
+    AL(data, E * nn, false) AL(weight, E * nn, false) AL(S, E * kk * D.NA * (size_t)((D.NA + 7) & ~7), false)
     AL(h, pp, true) AL(h_mu, pp, true) AL(h_nu, pp, true)
     AL(c, 2 * (size_t)DC_MMAX, true) AL(c_mu, 2 * (size_t)DC_MMAX, true) AL(c_nu, 2 * (size_t)DC_MMAX, true)
     AL(ep, E * np, true) AL(ep_mu, E * np, true) AL(ep_nu, E * np, true) AL(ep_g, E * np, true)
     AL(alpha, E, true) AL(Gh, E * pp, true) AL(gc, E * 2 * (size_t)DC_MMAX, true) AL(eloss, E, true)
     AL(red, pp + 6 * DC_MMAX + 2, true) AL(ctl, 8, true) AL(fu, 3 * (size_t)DC_MMAX, true) AL(gpart, 16 * DU_CTAS, true)
     AL(planes, (3 + (size_t)J) * pp, true) AL(model, E * nn, true) AL(prior, 4 * (size_t)DC_MMAX, true)
+    AL(band_ctr, (size_t)DC_CSMAX + 1, true) AL(ictl, 2, true)
 #undef AL
     if ((rc = dalloc(H, (void**)&H->gh, pp * 4, true)) || (rc = dalloc(H, (void**)&H->gcx, 2 * DC_MMAX * 4, true)) ||
         (rc = dalloc(H, (void**)&H->ls, 4, true))) { lcb_deconv_destroy(H); return rc; }
@@ -1617,11 +1730,54 @@ int lcb_deconv_run(void* handle, const lcb_fit_opts* opt, float* loss_hist, int 
         if ((rc = dalloc(H, (void**)&D.loss_hist, (size_t)opt->n_iter * 4, true))) return rc;
         H->loss_cap = opt->n_iter;
     }
-    for (int it = 0; it < opt->n_iter; ++it) {
-        const int seq = next_seq(H);
-        if ((rc = launch_starlet(H)) || (rc = launch_epoch(H, 0)) || (rc = launch_reduce(H, 0, seq)) ||
-            (rc = launch_update(H, it, opt->n_iter, opt->lr, opt->schedule, seq, nullptr, nullptr, nullptr))) return rc;
+    // One iteration = starlet term (second stream) | epoch kernel with the fused reduction / NVLink push in its tail | update.
+    // The first iteration is launched eagerly (it also sets the function attributes); the remaining ones replay ONE captured
+    // CUDA graph of an iteration whose kernels read the iteration index and the exchange sequence number from device memory
+    // (identical launch arguments), which removes the per-launch gaps of a launch-bound loop.  With per-kernel profiling
+    // enabled (lcb_profile_enable) or LCB_DECONV_GRAPH=0 every iteration is launched eagerly.
+    const bool multi = D.cm.world > 1;
+    const int seq0 = H->seq + 1;
+    if (opt->n_iter > 0) {
+        const int init[2] = {0, seq0};
+        LCB_CUDA(cudaMemcpyAsync(D.ictl, init, sizeof(init), cudaMemcpyHostToDevice, H->st));
+        LCB_CUDA(cudaStreamSynchronize(H->st));            // init is a stack temporary
     }
+    auto one_iteration = [&](int it_arg, int seq_arg) -> int {
+        int r;
+        if ((r = launch_starlet(H)) || (r = launch_epoch(H, 4, seq_arg)) ||
+            (r = launch_update(H, it_arg, opt->n_iter, opt->lr, opt->schedule, seq_arg, nullptr, nullptr, nullptr))) return r;
+        return LCB_OK;
+    };
+    const char* genv = getenv("LCB_DECONV_GRAPH");
+    const bool use_graph = !(genv && genv[0] == '0') && !lcb_profiling() && opt->n_iter >= 8;
+    int done = 0;
+    if (use_graph) {
+        if ((rc = one_iteration(-2, -1))) return rc;       // eager: function attributes, cluster size
+        done = 1;
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t gexec = nullptr;
+        cudaError_t ce = cudaStreamBeginCapture(H->st, cudaStreamCaptureModeThreadLocal);
+        bool ok = (ce == cudaSuccess);
+        if (ok) {
+            rc = one_iteration(-2, -1);
+            ce = cudaStreamEndCapture(H->st, &graph);
+            ok = (rc == LCB_OK && ce == cudaSuccess && graph != nullptr);
+        }
+        if (ok) ok = (cudaGraphInstantiate(&gexec, graph, 0) == cudaSuccess);
+        if (ok) {
+            for (; done < opt->n_iter && ok; ++done) ok = (cudaGraphLaunch(gexec, H->st) == cudaSuccess);
+            if (!ok) { lcb_set_error("joint deconvolution: cudaGraphLaunch failed: %s", cudaGetErrorString(cudaGetLastError())); }
+        } else {
+            cudaGetLastError();                            // capture unavailable: fall back to eager launches below
+        }
+        if (gexec) cudaGraphExecDestroy(gexec);
+        if (graph) cudaGraphDestroy(graph);
+        if (gexec && !ok) return LCB_ERR_CUDA;
+        H->reg_pending = false;
+    }
+    for (int it = done; it < opt->n_iter; ++it)
+        if ((rc = one_iteration(use_graph ? -2 : it, use_graph ? -1 : (multi ? seq0 + it : 0)))) return rc;
+    if (multi) H->seq += opt->n_iter;
     // flush the pending per-epoch update so that get() sees the final parameters
     if (opt->n_iter > 0) { if ((rc = launch_epoch(H, 0))) return rc; LCB_CUDA(cudaMemsetAsync(D.ctl + 4, 0, 4, H->st)); }
     if ((rc = check_peers(H))) return rc;

@@ -43,13 +43,27 @@ __global__ void __launch_bounds__(PHOT_THREADS, (NS > 0 ? 4 : 1)) k_phot_fit(Pho
     const float* psf_g = A.psf + (size_t)A.psf_index[item] * nu * nu;
     const float* s = A.s_in_smem ? s_sm : psf_g;
 
-    if (HB > 0) {
-        float* z0 = wT + n * ldt;
-        const int zc = 2 * (nu + 2 * HB) * ldv + (nu + 2 * HB) * nu;
-        for (int i = tid; i < zc; i += PHOT_THREADS) z0[i] = 0.f;
-        __syncthreads();
+    // The narrow PSF of the item's frame (nu x nu floats, contiguous in HBM: 16 KB at n = 32, k = 2) is fetched by the TMA unit:
+    // one thread arms an mbarrier and issues ONE bulk asynchronous copy into the interior of the haloed tile while the other
+    // warps zero the halos and transpose the stamp and its weights; everybody waits on the barrier before the first pass.
+    __shared__ __align__(8) unsigned long long s_bar;
+    const bool tma_ok = A.s_in_smem && ((nu * nu) & 3) == 0 && (reinterpret_cast<size_t>(psf_g) & 15) == 0;
+    if (tid == 0) lcb_mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (tma_ok && tid == 0) {
+        lcb_mbar_expect_tx(&s_bar, (unsigned)(nu * nu) * 4u);
+        lcb_bulk_g2s(s_sm, psf_g, (unsigned)(nu * nu) * 4u, &s_bar);
     }
-    // ---- load: stamp + weight transposed, PSF tile (coalesced float loads; 16 KB at n=32,k=2)
+    if (HB > 0) {
+        // zero rows of the halos: everything from the end of wT up to the interior of the PSF tile, and the rows after it
+        // (the interior itself belongs to the bulk copy in flight)
+        float* z0 = wT + n * ldt;
+        const int zc = A.s_in_smem ? (int)(s_sm - z0) : 2 * (nu + 2 * HB) * ldv;
+        for (int i = tid; i < zc; i += PHOT_THREADS) z0[i] = 0.f;
+        float* z1 = s_sm + nu * nu;
+        if (A.s_in_smem) for (int i = tid; i < HB * nu; i += PHOT_THREADS) z1[i] = 0.f;
+    }
+    // ---- load: stamp + weight transposed (the transposition is why these two are not bulk copies)
     const float* dg = A.data + (size_t)item * n * n;
     const float* wg = A.weight + (size_t)item * n * n;
     for (int i = tid; i < n * n; i += PHOT_THREADS) {
@@ -57,11 +71,10 @@ __global__ void __launch_bounds__(PHOT_THREADS, (NS > 0 ? 4 : 1)) k_phot_fit(Pho
         dT[X * ldt + Y] = dg[i];
         wT[X * ldt + Y] = wg[i];
     }
-    if (A.s_in_smem) {
-        const float4* src = reinterpret_cast<const float4*>(psf_g);
-        float4* dst = reinterpret_cast<float4*>(s_sm);
-        for (int i = tid; i < nu * nu / 4; i += PHOT_THREADS) dst[i] = __ldg(src + i);
+    if (A.s_in_smem && !tma_ok) {
+        for (int i = tid; i < nu * nu; i += PHOT_THREADS) s_sm[i] = __ldg(psf_g + i);
     }
+    if (tma_ok) lcb_mbar_wait(&s_bar, 0);
 
     __syncthreads();
     // Only warp 0 runs the scalar part of an iteration (sum of the per-warp partials, loss, clip, schedule,

@@ -309,3 +309,32 @@ def test_deconv_two_ranks_match_single_rank(cuda_device, comm):
     assert np.abs(res[0][4] - fin['h']).max() <= 3e-4 and np.median(np.abs(res[0][4] - fin['h'])) <= 2e-5
     a_all = np.concatenate([res[0][6], res[1][6]])
     np.testing.assert_allclose(a_all, fin['a'], rtol=1e-4)
+
+
+def test_deconv_graph_replay_equals_eager(cuda_device, monkeypatch):
+    """lcb_deconv_run replays ONE captured CUDA graph of an iteration (device-resident iteration counter); with
+    LCB_DECONV_GRAPH=0 every iteration is launched eagerly.  Same kernels, same order: bit-identical loss histories and
+    parameters, for a cluster-split epoch kernel, scheduled learning rate and every regulariser."""
+    from lightcurver_b200.processes.roi_modelling import JointDeconvolution
+    E, n, k, M, T = 5, 20, 2, 2, 24
+    p = _problem(E, n, k, M, 12, seed=77, alpha_on=True)
+    nu = n * k
+    outs = []
+    for mode in ('1', '0'):
+        monkeypatch.setenv('LCB_DECONV_GRAPH', mode)
+        jd = JointDeconvolution(p['data'], p['weight'], p['psf'], k, M)
+        jd.set_cluster(2)
+        jd.set_params(h=np.zeros(nu * nu), mean=np.zeros(E), a=(p['a'] * 0.9).astype(np.float32), c_x=p['c_x'], c_y=p['c_y'],
+                      dx=np.zeros(E), dy=np.zeros(E), alpha=p['alpha'])
+        jd.set_reg(1.0, 1.0, 100.0, lam_pts=0.01, lam_fu=10.0)
+        jd.noise_weights()
+        h1 = jd.run(T, lr=1e-4, schedule=True)
+        h2 = jd.run(T, lr=1e-4, schedule=True)          # a second run on the same handle continues from the fitted parameters
+        fin = jd.get()
+        jd.close()
+        outs.append((h1, h2, fin))
+    for a, b in zip(outs[0][:2], outs[1][:2]):
+        assert np.array_equal(a, b)
+    for kk in ('h', 'a', 'dx', 'dy', 'mean', 'c_x', 'c_y', 'model'):
+        assert np.array_equal(outs[0][2][kk], outs[1][2][kk]), kk
+    assert outs[0][0][-1] < outs[0][0][0] and np.isfinite(outs[0][1]).all()

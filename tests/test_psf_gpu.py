@@ -156,6 +156,8 @@ def test_psf_stage2_fit_parity_configured_length(cuda_device, record_property):
                 flux_rel_err_f32_oracle=float(np.max(np.abs(r32['a'] - r64['a']) / np.abs(r64['a']))),
                 psf_pixel_err_over_peak_gpu=float(np.abs(pg - p64).max() / peak),
                 psf_pixel_err_over_peak_f32_oracle=float(np.abs(p32 - p64).max() / peak),
+                psf_pixel_err_over_peak_gpu_vs_f32_oracle=float(np.abs(pg - p32).max() / peak),
+                flux_rel_err_gpu_vs_f32_oracle=float(np.max(np.abs(out['a'].reshape(F, N) - r32['a']) / np.abs(r32['a']))),
                 psf_pixel_rms_over_peak_gpu=float(np.sqrt(((pg - p64) ** 2).mean()) / peak),
                 psf_pixel_rms_over_peak_f32_oracle=float(np.sqrt(((p32 - p64) ** 2).mean()) / peak),
                 final_loss_rel_err_gpu=float(abs(out['loss_hist'][0, -1] - r64['loss_hist'][0, -1]) / abs(r64['loss_hist'][0, -1])),
@@ -165,6 +167,10 @@ def test_psf_stage2_fit_parity_configured_length(cuda_device, record_property):
         record_property(kk, v)
     assert nums['flux_rel_err_gpu'] <= 1e-4
     assert nums['final_loss_rel_err_gpu'] <= 1e-3
+    # north star, literally: "checked against STARRED/JAX run in float32 ... PSF pixels within 1e-3 of the peak" -> the float32
+    # restatement is the comparison; the distance of BOTH float32 implementations to float64 is reported beside it
+    assert nums['psf_pixel_err_over_peak_gpu_vs_f32_oracle'] <= 1e-3, nums
+    assert nums['flux_rel_err_gpu_vs_f32_oracle'] <= 1e-4, nums
     assert (nums['psf_pixel_err_over_peak_gpu'] <= 1e-3 or
             nums['psf_pixel_err_over_peak_gpu'] <= 2.0 * nums['psf_pixel_err_over_peak_f32_oracle']), nums
     assert (out['status'] == 0).all()
