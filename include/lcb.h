@@ -202,6 +202,10 @@ int lcb_deconv_comm_connect(void* handle, const void* all_handles);
 /* n_iter AdaBelief iterations, enqueued without host synchronisation; loss_hist [n_iter] may be NULL.
  * Single rank, or every rank of a connected communicator. */
 int lcb_deconv_run(void* handle, const lcb_fit_opts* opt, float* loss_hist, int mem);
+/* The same run on `count` independent single-rank handles at once: the iterations of the handles are interleaved, each handle on
+ * its own stream, so that many small joint fits (the reference-coupled star photometry of star_photometry.py:74-87, one joint fit
+ * per star) fill the GPU together instead of one after the other.  loss_hist: `count` pointers ([n_iter] each) or NULL. */
+int lcb_deconv_run_many(void* const* handles, int count, const lcb_fit_opts* opt, float* const* loss_hist, int mem);
 /* Alternative multi-rank driver with an external collective (e.g. NCCL): one iteration = step_local ;
  * all-reduce(sum) of reduce_buffer ; step_update.
  * After the last iteration call lcb_deconv_flush to apply the pending per-epoch update. */

@@ -237,6 +237,7 @@ lib.lcb_deconv_create.argtypes = [C.POINTER(DeconvProblem), C.c_int, C.c_void_p,
 lib.lcb_deconv_set_params.argtypes = [C.c_void_p, C.POINTER(DeconvParams), C.c_int]
 lib.lcb_deconv_set_reg.argtypes = [C.c_void_p, C.POINTER(DeconvReg), C.c_int]
 lib.lcb_deconv_run.argtypes = [C.c_void_p, C.POINTER(FitOpts), C.c_void_p, C.c_int]
+lib.lcb_deconv_run_many.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(FitOpts), C.POINTER(C.c_void_p), C.c_int]
 lib.lcb_deconv_step_local.argtypes = [C.c_void_p, C.c_int]
 lib.lcb_deconv_reduce_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
 lib.lcb_deconv_step_update.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int]

@@ -82,6 +82,9 @@ struct DeconvDev {
     float *model;                        // [E][n][n] (written when requested)
     float *loss_hist;                    // [cap]
     unsigned *band_ctr;                  // [DC_CSMAX + 1] arrival counters of the fused reduction (self-resetting)
+    unsigned *grp_ctr;                   // [NG][DC_CSMAX] arrivals per group of GS consecutive epochs and band (self-resetting)
+    float *Gp;                           // [NG][nu^2] dL/dh summed over the epochs of a group (level 1 of the fused reduction)
+    int GS, NG;                          // epochs per group (~ sqrt(E)), number of groups
     int *ictl;                           // [2] device-resident iteration index and exchange sequence number (graph replay)
     DevConv cv;
     DeconvComm cm;
@@ -738,11 +741,15 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
     cl.sync();                                    // #3: no CTA leaves while its shared memory may still be read
     if (!(flags & 4)) return;
 
-    // ---- fused reduction over the local epochs (replaces k_deconv_reduce inside lcb_deconv_run)
+    // ---- fused reduction over the local epochs (replaces k_deconv_reduce inside lcb_deconv_run), two levels so that no CTA
+    //      walks more than ~2 sqrt(E) planes: the last cluster to finish a band of a GROUP of GS consecutive epochs sums the
+    //      group (epoch order) into Gp[group]; the last group to finish a band sums the NG partial planes (group order) and
+    //      emits them.  Fixed summation order: deterministic, identical on every rank.
     __shared__ int s_last;
+    const int grp = e / D.GS, g_lo = grp * D.GS, g_hi = min(g_lo + D.GS, D.E);
     __threadfence();                              // this CTA's rows of Gh (and, rank 0, the per-epoch scalars) are visible device wide
     __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(D.band_ctr + crank, 1u) == (unsigned)(D.E - 1)) ? 1 : 0;
+    if (tid == 0) s_last = (atomicAdd(D.grp_ctr + grp * DC_CSMAX + crank, 1u) == (unsigned)(g_hi - g_lo - 1)) ? 1 : 0;
     __syncthreads();
     if (!s_last) return;
     __threadfence();
@@ -752,54 +759,77 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
         if (seq == 0) D.red[i] = v;
         else for (int r = 0; r < Wn; ++r) D.cm.slots[r][((size_t)parity * Wn + D.cm.rank) * D.tot + i] = v;
     };
-    {
-        const int cnt = (vhi - vlo) * nu;
-        const float* src = D.Gh + (size_t)vlo * nu;
-        for (int i0 = tid; i0 < cnt; i0 += 4 * DC_THREADS) {      // 4 pixels x 4 epochs in flight per thread, epochs summed in order
+    const int cnt = (vhi - vlo) * nu;
+    // sums planes src[p * nu2 + i], p = 0 .. np_-1 (in order) over the pixels of the band; 4 pixels x 4 planes in flight per thread
+    auto band_sum = [&](const float* __restrict__ src, int np_, auto&& put) {
+        for (int i0 = tid; i0 < cnt; i0 += 4 * DC_THREADS) {
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            if (D.free_h) {
-                for (int e0 = 0; e0 < D.E; e0 += 4) {
-                    float v[4][4];
+            for (int p0 = 0; p0 < np_; p0 += 4) {
+                float v[4][4];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
+                for (int q = 0; q < 4; ++q)
 #pragma unroll
-                        for (int ee = 0; ee < 4; ++ee) {
-                            const int i = i0 + q * DC_THREADS;
-                            v[q][ee] = (i < cnt && e0 + ee < D.E) ? __ldcg(src + (size_t)(e0 + ee) * nu2 + i) : 0.f;
-                        }
+                    for (int pe = 0; pe < 4; ++pe) {
+                        const int i = i0 + q * DC_THREADS;
+                        v[q][pe] = (i < cnt && p0 + pe < np_) ? __ldcg(src + (size_t)(p0 + pe) * nu2 + i) : 0.f;
+                    }
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
+                for (int q = 0; q < 4; ++q)
 #pragma unroll
-                        for (int ee = 0; ee < 4; ++ee) acc[q] += v[q][ee];
-                }
+                    for (int pe = 0; pe < 4; ++pe) acc[q] += v[q][pe];
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { const int i = i0 + q * DC_THREADS; if (i < cnt) emit(vlo * nu + i, acc[q]); }
+            for (int q = 0; q < 4; ++q) { const int i = i0 + q * DC_THREADS; if (i < cnt) put(vlo * nu + i, acc[q]); }
         }
+    };
+    const bool one_level = (D.NG == 1);
+    if (D.free_h) {
+        const float* src = D.Gh + (size_t)g_lo * nu2 + (size_t)vlo * nu;
+        float* dst = D.Gp + (size_t)grp * nu2;
+        if (one_level) band_sum(src, g_hi - g_lo, emit);
+        else band_sum(src, g_hi - g_lo, [&](int i, float v) { dst[i] = v; });
+    } else if (one_level) {
+        for (int i = tid; i < cnt; i += DC_THREADS) emit(vlo * nu + i, 0.f);
     }
-    if (crank == 0 && tid < D.tot - nu2) {       // per-epoch scalars: every rank-0 CTA wrote its own before raising the band counter
-        const int i = nu2 + tid, iflux = red_flux(D);
-        float sacc = 0.f;
-        if (i < nu2 + 2 * M) {
-            for (int ee = 0; ee < D.E; ++ee) sacc += __ldcg(D.gc + (size_t)ee * 2 * M + (i - nu2));
-        } else if (i == nu2 + 2 * M) {
-            for (int ee = 0; ee < D.E; ++ee) sacc += __ldcg(D.eloss + ee);
-        } else if (i == nu2 + 2 * M + 1) {
-            for (int ee = 0; ee < D.E; ++ee)
-                for (int p = 0; p < np; ++p) {
-                    const bool is_free = (p < M) ? D.free_a : (p < M + 2) ? D.free_d : D.free_mean;
-                    const float g = __ldcg(D.ep_g + (size_t)ee * np + p);
-                    if (is_free) sacc = fmaf(g, g, sacc);
+    if (tid == 0) D.grp_ctr[grp * DC_CSMAX + crank] = 0;       // next use: the next launch of this kernel
+    if (!one_level) {
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = (atomicAdd(D.band_ctr + crank, 1u) == (unsigned)(D.NG - 1)) ? 1 : 0;
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        if (D.free_h) band_sum(D.Gp + (size_t)vlo * nu, D.NG, emit);
+        else for (int i = tid; i < cnt; i += DC_THREADS) emit(vlo * nu + i, 0.f);
+    }
+    if (crank == 0) {
+        // per-epoch scalars (every rank-0 CTA wrote its own before raising its counter): one warp per entry, lanes stride the
+        // epochs, fixed-order shuffle tree
+        const int lane = tid & 31, iflux = red_flux(D);
+        for (int i = nu2 + (tid >> 5); i < D.tot; i += DC_THREADS / 32) {
+            float sacc = 0.f;
+            if (i < nu2 + 2 * M) {
+                for (int ee = lane; ee < D.E; ee += 32) sacc += __ldcg(D.gc + (size_t)ee * 2 * M + (i - nu2));
+            } else if (i == nu2 + 2 * M) {
+                for (int ee = lane; ee < D.E; ee += 32) sacc += __ldcg(D.eloss + ee);
+            } else if (i == nu2 + 2 * M + 1) {
+                for (int ee = lane; ee < D.E; ee += 32)
+                    for (int p = 0; p < np; ++p) {
+                        const bool is_free = (p < M) ? D.free_a : (p < M + 2) ? D.free_d : D.free_mean;
+                        const float g = __ldcg(D.ep_g + (size_t)ee * np + p);
+                        if (is_free) sacc = fmaf(g, g, sacc);
+                    }
+            } else if (i < iflux + 4 * M) {
+                const int q = (i - iflux) / M, m = (i - iflux) % M;
+                const float Kf = D.fu[m];
+                for (int ee = lane; ee < D.E; ee += 32) {
+                    const float a = __ldcg(D.ep + (size_t)ee * np + m) - Kf, g = __ldcg(D.ep_g + (size_t)ee * np + m);
+                    sacc += (q == 0) ? a : (q == 1) ? a * a : (q == 2) ? g : g * a;
                 }
-        } else if (i < iflux + 4 * M) {
-            const int q = (i - iflux) / M, m = (i - iflux) % M;
-            const float Kf = D.fu[m];
-            for (int ee = 0; ee < D.E; ++ee) {
-                const float a = __ldcg(D.ep + (size_t)ee * np + m) - Kf, g = __ldcg(D.ep_g + (size_t)ee * np + m);
-                sacc += (q == 0) ? a : (q == 1) ? a * a : (q == 2) ? g : g * a;
             }
+            sacc = warp_sum(sacc);
+            if (lane == 0) emit(i, sacc);
         }
-        emit(i, sacc);
     }
     __threadfence_system();
     __syncthreads();
@@ -1537,6 +1567,9 @@ int lcb_deconv_create(const lcb_deconv_problem* p, int mem, void* stream, void**
     AL(red, pp + 6 * DC_MMAX + 2, true) AL(ctl, 8, true) AL(fu, 3 * (size_t)DC_MMAX, true) AL(gpart, 16 * DU_CTAS, true)
     AL(planes, (3 + (size_t)J) * pp, true) AL(model, E * nn, true) AL(prior, 4 * (size_t)DC_MMAX, true)
     AL(band_ctr, (size_t)DC_CSMAX + 1, true) AL(ictl, 2, true)
+    D.GS = 1; while (D.GS * D.GS < D.E) ++D.GS;          // ~ sqrt(E) epochs per group
+    D.NG = (D.E + D.GS - 1) / D.GS;
+    AL(grp_ctr, (size_t)D.NG * DC_CSMAX, true) AL(Gp, (size_t)D.NG * pp, true)
 #undef AL
     if ((rc = dalloc(H, (void**)&H->gh, pp * 4, true)) || (rc = dalloc(H, (void**)&H->gcx, 2 * DC_MMAX * 4, true)) ||
         (rc = dalloc(H, (void**)&H->ls, 4, true))) { lcb_deconv_destroy(H); return rc; }
@@ -1721,9 +1754,30 @@ int lcb_deconv_step_update(void* handle, int it, int n_iter, float lr, int sched
 // n_iter AdaBelief iterations enqueued back to back, no host synchronisation inside the loop.  With a connected
 // communicator (lcb_deconv_comm_*) every rank calls this with the same options: the gradient of the shared
 // parameters is exchanged inside k_deconv_reduce / k_deconv_update over peer memory.
-int lcb_deconv_run(void* handle, const lcb_fit_opts* opt, float* loss_hist, int mem) {
-    DeconvHandle* H = (DeconvHandle*)handle;
-    LCB_REQUIRE(H && opt && opt->n_iter >= 0, "lcb_deconv_run: bad arguments");
+// One run = begin (loss buffer, device-resident counters, first iteration eagerly, ONE captured CUDA graph of an iteration),
+// n_iter - 1 replays, end (pending per-epoch update, peers, loss history).  lcb_deconv_run drives one handle; lcb_deconv_run_many
+// interleaves the replays of several handles (each on its own stream), so that many small joint fits fill the GPU together.
+struct DeconvRun {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    bool use_graph = false, multi = false;
+    int done = 0, seq0 = 0;
+};
+
+static int run_iteration(DeconvHandle* H, const lcb_fit_opts* opt, int it_arg, int seq_arg) {
+    int r;
+    if ((r = launch_starlet(H)) || (r = launch_epoch(H, 4, seq_arg)) ||
+        (r = launch_update(H, it_arg, opt->n_iter, opt->lr, opt->schedule, seq_arg, nullptr, nullptr, nullptr))) return r;
+    return LCB_OK;
+}
+
+static void run_release(DeconvRun& R) {
+    if (R.gexec) cudaGraphExecDestroy(R.gexec);
+    if (R.graph) cudaGraphDestroy(R.graph);
+    R.gexec = nullptr; R.graph = nullptr;
+}
+
+static int run_begin(DeconvHandle* H, const lcb_fit_opts* opt, DeconvRun& R) {
     DeconvDev& D = H->D;
     int rc;
     if (opt->n_iter > H->loss_cap) {
@@ -1735,54 +1789,85 @@ int lcb_deconv_run(void* handle, const lcb_fit_opts* opt, float* loss_hist, int 
     // CUDA graph of an iteration whose kernels read the iteration index and the exchange sequence number from device memory
     // (identical launch arguments), which removes the per-launch gaps of a launch-bound loop.  With per-kernel profiling
     // enabled (lcb_profile_enable) or LCB_DECONV_GRAPH=0 every iteration is launched eagerly.
-    const bool multi = D.cm.world > 1;
-    const int seq0 = H->seq + 1;
+    R.multi = D.cm.world > 1;
+    R.seq0 = H->seq + 1;
     if (opt->n_iter > 0) {
-        const int init[2] = {0, seq0};
+        const int init[2] = {0, R.seq0};
         LCB_CUDA(cudaMemcpyAsync(D.ictl, init, sizeof(init), cudaMemcpyHostToDevice, H->st));
         LCB_CUDA(cudaStreamSynchronize(H->st));            // init is a stack temporary
     }
-    auto one_iteration = [&](int it_arg, int seq_arg) -> int {
-        int r;
-        if ((r = launch_starlet(H)) || (r = launch_epoch(H, 4, seq_arg)) ||
-            (r = launch_update(H, it_arg, opt->n_iter, opt->lr, opt->schedule, seq_arg, nullptr, nullptr, nullptr))) return r;
-        return LCB_OK;
-    };
     const char* genv = getenv("LCB_DECONV_GRAPH");
-    const bool use_graph = !(genv && genv[0] == '0') && !lcb_profiling() && opt->n_iter >= 8;
-    int done = 0;
-    if (use_graph) {
-        if ((rc = one_iteration(-2, -1))) return rc;       // eager: function attributes, cluster size
-        done = 1;
-        cudaGraph_t graph = nullptr;
-        cudaGraphExec_t gexec = nullptr;
+    R.use_graph = !(genv && genv[0] == '0') && !lcb_profiling() && opt->n_iter >= 8;
+    R.done = 0;
+    if (R.use_graph) {
+        if ((rc = run_iteration(H, opt, -2, -1))) return rc;   // eager: function attributes, cluster size
+        R.done = 1;
         cudaError_t ce = cudaStreamBeginCapture(H->st, cudaStreamCaptureModeThreadLocal);
         bool ok = (ce == cudaSuccess);
         if (ok) {
-            rc = one_iteration(-2, -1);
-            ce = cudaStreamEndCapture(H->st, &graph);
-            ok = (rc == LCB_OK && ce == cudaSuccess && graph != nullptr);
+            rc = run_iteration(H, opt, -2, -1);
+            ce = cudaStreamEndCapture(H->st, &R.graph);
+            ok = (rc == LCB_OK && ce == cudaSuccess && R.graph != nullptr);
         }
-        if (ok) ok = (cudaGraphInstantiate(&gexec, graph, 0) == cudaSuccess);
-        if (ok) {
-            for (; done < opt->n_iter && ok; ++done) ok = (cudaGraphLaunch(gexec, H->st) == cudaSuccess);
-            if (!ok) { lcb_set_error("joint deconvolution: cudaGraphLaunch failed: %s", cudaGetErrorString(cudaGetLastError())); }
-        } else {
-            cudaGetLastError();                            // capture unavailable: fall back to eager launches below
-        }
-        if (gexec) cudaGraphExecDestroy(gexec);
-        if (graph) cudaGraphDestroy(graph);
-        if (gexec && !ok) return LCB_ERR_CUDA;
+        if (ok) ok = (cudaGraphInstantiate(&R.gexec, R.graph, 0) == cudaSuccess);
+        if (!ok) { cudaGetLastError(); run_release(R); }       // capture unavailable: eager launches
         H->reg_pending = false;
     }
-    for (int it = done; it < opt->n_iter; ++it)
-        if ((rc = one_iteration(use_graph ? -2 : it, use_graph ? -1 : (multi ? seq0 + it : 0)))) return rc;
-    if (multi) H->seq += opt->n_iter;
+    return LCB_OK;
+}
+
+// launches up to `count` further iterations (graph replay when available)
+static int run_some(DeconvHandle* H, const lcb_fit_opts* opt, DeconvRun& R, int count) {
+    int rc;
+    for (int i = 0; i < count && R.done < opt->n_iter; ++i, ++R.done) {
+        if (R.gexec) {
+            if (cudaGraphLaunch(R.gexec, H->st) != cudaSuccess) {
+                lcb_set_error("joint deconvolution: cudaGraphLaunch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                return LCB_ERR_CUDA;
+            }
+        } else if ((rc = run_iteration(H, opt, R.use_graph ? -2 : R.done, R.use_graph ? -1 : (R.multi ? R.seq0 + R.done : 0)))) return rc;
+    }
+    return LCB_OK;
+}
+
+static int run_end(DeconvHandle* H, const lcb_fit_opts* opt, DeconvRun& R, float* loss_hist, int mem) {
+    DeconvDev& D = H->D;
+    int rc;
+    run_release(R);
+    if (R.multi) H->seq += opt->n_iter;
     // flush the pending per-epoch update so that get() sees the final parameters
     if (opt->n_iter > 0) { if ((rc = launch_epoch(H, 0))) return rc; LCB_CUDA(cudaMemsetAsync(D.ctl + 4, 0, 4, H->st)); }
     if ((rc = check_peers(H))) return rc;
     if (loss_hist) { if ((rc = get(H, loss_hist, D.loss_hist, opt->n_iter, mem))) return rc; }
     return LCB_OK;
+}
+
+int lcb_deconv_run(void* handle, const lcb_fit_opts* opt, float* loss_hist, int mem) {
+    DeconvHandle* H = (DeconvHandle*)handle;
+    LCB_REQUIRE(H && opt && opt->n_iter >= 0, "lcb_deconv_run: bad arguments");
+    DeconvRun R;
+    int rc;
+    if ((rc = run_begin(H, opt, R)) || (rc = run_some(H, opt, R, opt->n_iter))) { run_release(R); return rc; }
+    return run_end(H, opt, R, loss_hist, mem);
+}
+
+int lcb_deconv_run_many(void* const* handles, int count, const lcb_fit_opts* opt, float* const* loss_hist, int mem) {
+    LCB_REQUIRE(handles && count >= 0 && opt && opt->n_iter >= 0, "lcb_deconv_run_many: bad arguments");
+    std::vector<DeconvRun> R((size_t)count);
+    int rc = LCB_OK;
+    for (int i = 0; i < count && !rc; ++i) {
+        DeconvHandle* H = (DeconvHandle*)handles[i];
+        if (!H || H->D.cm.world > 1) { lcb_set_error("lcb_deconv_run_many: handle %d is NULL or sharded over ranks", i); rc = LCB_ERR_ARG; break; }
+        rc = run_begin(H, opt, R[i]);
+    }
+    // round-robin over the handles, a few iterations at a time: every stream always has work queued, no stream's queue overflows
+    for (int it = 0; it < opt->n_iter && !rc; it += 4)
+        for (int i = 0; i < count && !rc; ++i) rc = run_some((DeconvHandle*)handles[i], opt, R[i], 4);
+    for (int i = 0; i < count; ++i) {
+        if (rc) { run_release(R[i]); continue; }
+        rc = run_end((DeconvHandle*)handles[i], opt, R[i], loss_hist ? loss_hist[i] : nullptr, mem);
+    }
+    return rc;
 }
 
 // loss and gradient at the current parameters (no update); collective when a communicator is connected

@@ -264,14 +264,34 @@ def _kwargs_of(fin):
     }
 
 
+def _flux_sigma_from_handle(jd, fin, weight, cv):
+    """flux_sigma_multi on a handle that already holds the stamps and folded PSFs (no second upload): M model evaluations with
+    unit amplitudes, h = 0, mean = 0 at the fitted positions.  Overwrites the handle's parameters: call after get()."""
+    E, M = jd.E, jd.M
+    w = np.asarray(weight, np.float64)
+    H = np.empty((E, M))
+    for m in range(M):
+        a = np.zeros((E, M), np.float32)
+        a[:, m] = 1.0
+        jd.set_params(h=np.zeros(jd.nu ** 2), mean=np.zeros(E), a=a, c_x=fin['c_x'], c_y=fin['c_y'], dx=fin['dx'], dy=fin['dy'],
+                      alpha=fin['alpha'])
+        mod = jd.get()['model'].astype(np.float64)
+        H[:, m] = (w * mod * mod).sum((-1, -2)) * (1.0 if cv.chi2_half else 2.0)
+    with np.errstate(divide='ignore'):
+        return (1.0 / np.sqrt(H)).reshape(-1)
+
+
 def _finish(jd, hist, Wused, data, weight, psf, cv):
     """Products of a finished fit (roi_modelling.py:335-401): kwargs_final, model, sigma of the fluxes, deconvolved epoch 0."""
     fin = jd.get()
     kw = _kwargs_of(fin)
     n, k, nu, M = jd.n, jd.k, jd.nu, jd.M
-    with np.errstate(divide='ignore', invalid='ignore'):
-        noisemap = np.where(weight > 0, 1.0 / np.sqrt(weight), np.inf)
-    sig = flux_sigma_multi(kw, data, noisemap, psf, k, cv)
+    if jd.world > 1:          # the sharded handle keeps its exchange state: evaluate sigma on a local single-rank handle
+        with np.errstate(divide='ignore', invalid='ignore'):
+            noisemap = np.where(weight > 0, 1.0 / np.sqrt(weight), np.inf)
+        sig = flux_sigma_multi(kw, data, noisemap, psf, k, cv)
+    else:
+        sig = _flux_sigma_from_handle(jd, fin, weight, cv)
     # model.getDeconvolved(kwargs, 0): high-resolution scene of epoch 0 and its background only
     from .star_photometry import point_source_image
     h2 = fin['h'].reshape(nu, nu).astype(np.float64)
@@ -326,6 +346,47 @@ def joint_deconvolution(data, weight, psf, subsampling_factor, xs, ys, initial_a
     out = _finish(jd, hist, Wused, data, weight, psf, cv)
     jd.close()
     return out
+
+
+def joint_deconvolution_many(problems, subsampling_factor, n_iter=2000, lr=1e-4, schedule=False,
+                             free_h=True, free_mean=True, free_a=True, free_c=True, free_d=True,
+                             regularization_strength_scales=1.0, regularization_strength_hf=1.0,
+                             regularization_strength_positivity=100.0, prior=None,
+                             regularization_strength_pts_source=0.0, regularization_strength_flux_uniformity=0.0,
+                             conventions: Conventions = DEFAULT):
+    """Several INDEPENDENT joint fits in one library call (``lcb_deconv_run_many``): the reference-coupled star photometry
+    (star_photometry.py:74-87 with ``starlet_global_background`` / ``uniform_background_per_epoch``) is one joint fit per star --
+    shared h, c and clip norm over the star's epochs -- and the reference runs the stars one after the other (:257); here every
+    star gets a handle and the iterations of all handles are interleaved on their own streams.
+
+    problems: list of dict(data, weight, psf, xs, ys, initial_a) with the meaning of ``joint_deconvolution``; epoch counts may
+    differ.  The remaining arguments are shared.  Returns the list of ``joint_deconvolution`` result dicts, in order."""
+    cv = conventions
+    jds, Ws = [], []
+    need_W = (free_h and (regularization_strength_scales or regularization_strength_hf)) or regularization_strength_pts_source
+    try:
+        for pr in problems:
+            E = pr['data'].shape[0]
+            M = len(np.atleast_1d(pr['xs']))
+            jd = JointDeconvolution(pr['data'], pr['weight'], pr['psf'], subsampling_factor, M, cv)
+            jds.append(jd)
+            jd.set_params(h=np.zeros(jd.nu ** 2), mean=np.zeros(E), a=np.asarray(pr['initial_a'], np.float32).reshape(E, M),
+                          c_x=np.atleast_1d(pr['xs']), c_y=np.atleast_1d(pr['ys']), dx=np.zeros(E), dy=np.zeros(E), alpha=np.zeros(E),
+                          free_h=free_h, free_mean=free_mean, free_a=free_a, free_c=free_c, free_d=free_d)
+            jd.set_reg(lam_scales=regularization_strength_scales, lam_hf=regularization_strength_hf,
+                       lam_pos=regularization_strength_positivity, W=None, prior=prior, lam_pts=regularization_strength_pts_source,
+                       lam_fu=regularization_strength_flux_uniformity, conventions=cv)
+            Ws.append(jd.noise_weights() if need_W else None)
+        hists = [np.empty(n_iter, np.float32) for _ in jds]
+        if jds:
+            hs = (C.c_void_p * len(jds))(*[jd.handle for jd in jds])
+            lh = (C.c_void_p * len(jds))(*[ptr(h) for h in hists])
+            opts = _lib.FitOpts(int(n_iter), float(lr), int(bool(schedule)))
+            _lib.check(_lib.lib.lcb_deconv_run_many(hs, len(jds), C.byref(opts), lh, _lib.MEM_HOST), 'lcb_deconv_run_many')
+        return [_finish(jd, hist, W, pr['data'], pr['weight'], pr['psf'], cv) for jd, hist, W, pr in zip(jds, hists, Ws, problems)]
+    finally:
+        for jd in jds:
+            jd.close()
 
 
 def lbfgsb_translations_and_fluxes(jd, maxiter, a_lower=0.0):

@@ -55,53 +55,30 @@ def point_source_image(a, x, y, n, k, cv: Conventions = DEFAULT):
     return a * np.outer(gy, gx)
 
 
-def do_one_star_forward_modelling(data, noisemap, psf, subsampling_factor, n_iter=2000,
-                                  uniform_background_per_epoch=False, starlet_global_background=True,
-                                  conventions: Conventions = DEFAULT):
-    """See lightcurver/processes/star_photometry.py:23-151.  data, noisemap (E,n,n); psf (E,n*k,n*k)."""
-    cv = conventions
-    from ..conventions import apply_to_library
-    apply_to_library(cv)
-    k = int(subsampling_factor)
-    E, n = data.shape[0], data.shape[-1]
-    # star_photometry.py:47-49 -- IN PLACE on the caller's arrays, like the reference
+COUPLED_FIT = dict(lr=1e-3, schedule=True, free_c=True, regularization_strength_scales=3.0, regularization_strength_hf=3.0,
+                   regularization_strength_positivity=0.0)     # star_photometry.py:76-122 [R]
+
+
+def _scale_and_guess(data, noisemap, k, cv):
+    """star_photometry.py:47-64 -- IN PLACE on the caller's arrays, like the reference: divide the stack by its nanmax, then the
+    initial flux guess.  Returns (scale, initial amplitudes, float32 stamps, float32 weights)."""
     scale = float(np.nanmax(data))
     data /= scale
     noisemap /= scale
-    a_est = _initial_flux_guess(data)
-    a_est = a_est * cv.amplitude_per_flux(k)
+    a_est = _initial_flux_guess(data) * cv.amplitude_per_flux(k)
     d32, weight = stamps_and_weights(data, noisemap)
-    psf = np.ascontiguousarray(psf, dtype=np.float32)
-    if starlet_global_background or uniform_background_per_epoch:
-        from .roi_modelling import joint_deconvolution
-        res = joint_deconvolution(
-            d32, weight, psf, k, xs=np.zeros(1), ys=np.zeros(1), initial_a=a_est,
-            n_iter=n_iter, lr=1e-3, schedule=True, free_h=bool(starlet_global_background),
-            free_mean=bool(uniform_background_per_epoch), free_c=True,
-            regularization_strength_scales=3.0, regularization_strength_hf=3.0,
-            regularization_strength_positivity=0.0, conventions=cv)
-        kw = res['kwargs_final']
-        a = np.asarray(kw['kwargs_analytic']['a'])
-        model = res['model']
-        sigma = res['flux_sigma']
-        loss_curve = res['loss_history']
-        deconv, bkg = res['deconvolved_epoch0']
-    else:
-        out = engine.phot_fit_batch(d32, weight, psf, np.arange(E, dtype=np.int32),
-                                    a_est.astype(np.float32), k, n_iter, lr=1e-3, schedule=True)
-        a = out['a'].astype(np.float64)
-        kw = {
-            'kwargs_analytic': {'c_x': np.zeros(1), 'c_y': np.zeros(1), 'dx': out['dx'].astype(np.float64),
-                                'dy': out['dy'].astype(np.float64), 'a': a, 'alpha': np.zeros(E)},
-            'kwargs_background': {'h': np.zeros((n * k) ** 2), 'mean': np.zeros(E)},
-            'kwargs_sersic': {},
-        }
-        model = d32 - out['residuals']
-        sigma = out['sigma_a'].astype(np.float64)
-        loss_curve = out['loss_hist'].astype(np.float64).sum(0)   # the joint loss is the sum over epochs
-        deconv = point_source_image(a[0], out['dx'][0], out['dy'][0], n, k, cv)
-        bkg = np.zeros((n * k, n * k))
-    residuals = data - model
+    return scale, a_est, d32, weight
+
+
+def _coupled_result(res, scale, data, noisemap, n, k, cv):
+    """Result dict of do_one_star_forward_modelling (:124-150) from a finished joint fit with M = 1."""
+    kw = res['kwargs_final']
+    a = np.asarray(kw['kwargs_analytic']['a'])
+    deconv, bkg = res['deconvolved_epoch0']
+    return _result_dict(scale, kw, a, res['flux_sigma'], res['loss_history'], data - res['model'], noisemap, deconv, bkg, n, k, cv)
+
+
+def _result_dict(scale, kw, a, sigma, loss_curve, residuals, noisemap, deconv, bkg, n, k, cv):
     sigma_2 = noisemap ** 2
     with np.errstate(divide='ignore', invalid='ignore'):
         chi2_per_frame = np.nansum(residuals ** 2 / sigma_2, axis=(1, 2)) / n ** 2   # :127 (image_size^2, not dof)
@@ -120,6 +97,62 @@ def do_one_star_forward_modelling(data, noisemap, psf, subsampling_factor, n_ite
         'deconvolved_image': scale * np.asarray(deconv),
         'starlet_background': scale * np.asarray(bkg),
     }
+
+
+def do_one_star_forward_modelling(data, noisemap, psf, subsampling_factor, n_iter=2000,
+                                  uniform_background_per_epoch=False, starlet_global_background=True,
+                                  conventions: Conventions = DEFAULT):
+    """See lightcurver/processes/star_photometry.py:23-151.  data, noisemap (E,n,n); psf (E,n*k,n*k)."""
+    cv = conventions
+    from ..conventions import apply_to_library
+    apply_to_library(cv)
+    k = int(subsampling_factor)
+    E, n = data.shape[0], data.shape[-1]
+    scale, a_est, d32, weight = _scale_and_guess(data, noisemap, k, cv)
+    psf = np.ascontiguousarray(psf, dtype=np.float32)
+    if starlet_global_background or uniform_background_per_epoch:
+        from .roi_modelling import joint_deconvolution
+        res = joint_deconvolution(
+            d32, weight, psf, k, xs=np.zeros(1), ys=np.zeros(1), initial_a=a_est,
+            n_iter=n_iter, free_h=bool(starlet_global_background), free_mean=bool(uniform_background_per_epoch),
+            conventions=cv, **COUPLED_FIT)
+        return _coupled_result(res, scale, data, noisemap, n, k, cv)
+    out = engine.phot_fit_batch(d32, weight, psf, np.arange(E, dtype=np.int32),
+                                a_est.astype(np.float32), k, n_iter, lr=1e-3, schedule=True)
+    a = out['a'].astype(np.float64)
+    kw = {
+        'kwargs_analytic': {'c_x': np.zeros(1), 'c_y': np.zeros(1), 'dx': out['dx'].astype(np.float64),
+                            'dy': out['dy'].astype(np.float64), 'a': a, 'alpha': np.zeros(E)},
+        'kwargs_background': {'h': np.zeros((n * k) ** 2), 'mean': np.zeros(E)},
+        'kwargs_sersic': {},
+    }
+    model = d32 - out['residuals']
+    loss_curve = out['loss_hist'].astype(np.float64).sum(0)   # the joint loss is the sum over epochs
+    deconv = point_source_image(a[0], out['dx'][0], out['dy'][0], n, k, cv)
+    return _result_dict(scale, kw, a, out['sigma_a'].astype(np.float64), loss_curve, data - model, noisemap, deconv,
+                        np.zeros((n * k, n * k)), n, k, cv)
+
+
+def do_stars_forward_modelling_coupled(stacks, subsampling_factor, n_iter=2000, uniform_background_per_epoch=False,
+                                       starlet_global_background=True, conventions: Conventions = DEFAULT):
+    """``do_one_star_forward_modelling`` with the background flags for MANY stars in one library call (the reference loops over the
+    stars, star_photometry.py:257): stacks = list of (data, noisemap, psf) per star (scaled in place like the one-star function);
+    every star is one joint fit (shared h / c / clip norm over its epochs), all fits are iterated together by
+    ``lcb_deconv_run_many``.  Returns the list of result dicts."""
+    cv = conventions
+    from ..conventions import apply_to_library
+    apply_to_library(cv)
+    from .roi_modelling import joint_deconvolution_many
+    k = int(subsampling_factor)
+    problems, meta = [], []
+    for data, noisemap, psf in stacks:
+        scale, a_est, d32, weight = _scale_and_guess(data, noisemap, k, cv)
+        problems.append(dict(data=d32, weight=weight, psf=np.ascontiguousarray(psf, dtype=np.float32), xs=np.zeros(1), ys=np.zeros(1),
+                             initial_a=a_est))
+        meta.append((scale, data, noisemap))
+    res = joint_deconvolution_many(problems, k, n_iter=n_iter, free_h=bool(starlet_global_background),
+                                   free_mean=bool(uniform_background_per_epoch), conventions=cv, **COUPLED_FIT)
+    return [_coupled_result(r, scale, data, noisemap, data.shape[-1], k, cv) for r, (scale, data, noisemap) in zip(res, meta)]
 
 
 def star_photometry_batch(data, noisemap, psfs, subsampling_factor, n_iter=2000, masks=None,
@@ -258,11 +291,13 @@ def do_star_photometry_batched(store, db, stars, frames_for_star, psf_ref_for_fr
         sl = slice(int(off[i]), int(off[i + 1]))
         wk['sl'], wk['data'], wk['noisemap'] = sl, data[sl], noisemap[sl]
     if coupled:
-        for wk in work:
-            wk['result'] = do_one_star_forward_modelling(
-                wk['data'], wk['noisemap'], psfs[psf_index[wk['sl']]], k, n_iter=n_iter,
-                uniform_background_per_epoch=user_config.get('star_photometry_uniform_background_per_epoch', False),
-                starlet_global_background=user_config.get('star_photometry_starlet_global_background', False))
+        # every star is a joint fit over its epochs (shared background / centre / clip norm); all stars in ONE library call
+        res = do_stars_forward_modelling_coupled(
+            [(wk['data'], wk['noisemap'], psfs[psf_index[wk['sl']]]) for wk in work], k, n_iter=n_iter,
+            uniform_background_per_epoch=user_config.get('star_photometry_uniform_background_per_epoch', False),
+            starlet_global_background=user_config.get('star_photometry_starlet_global_background', False))
+        for wk, r in zip(work, res):
+            wk['result'] = r
     else:
         # per star: scale (:47-49), initial flux guess (:55-64); then one K2 launch over all stars' epochs
         n = data.shape[-1]

@@ -259,3 +259,29 @@ def test_in_process_multi_gpu_fan_out(cuda_device):
     p2 = star_photometry_batch(d['data'], d['noisemap'], one['narrow_psf'], k, n_iter=80, masks=d['masks'], want_residuals=True, devices=[0, 1])
     for key in p1:
         assert np.array_equal(p1[key], p2[key]), key
+
+
+@pytest.mark.parametrize("flags", [dict(starlet_global_background=True, uniform_background_per_epoch=False),
+                                   dict(starlet_global_background=False, uniform_background_per_epoch=True)])
+def test_coupled_photometry_of_many_stars_in_one_call(cuda_device, flags):
+    """star_photometry.py:257 loops over the stars; with the background flags every star is one joint fit (shared h / c / clip norm,
+    :74-87).  ``do_stars_forward_modelling_coupled`` runs all those fits in ONE library call (lcb_deconv_run_many: a handle per
+    star, iterations interleaved on separate streams): the results must be those of the one-star function, star by star, also
+    for stars with different numbers of epochs."""
+    from lightcurver_b200 import synthetic
+    from lightcurver_b200.processes.star_photometry import do_one_star_forward_modelling, do_stars_forward_modelling_coupled
+    n, k, n_iter = 16, 2, 40
+    stacks = []
+    for s, E in enumerate((5, 3, 6)):
+        d = synthetic.make_phot_frames(E, 1, n, k, seed=40 + s)
+        stacks.append((d['data'][:, 0].astype(np.float64), d['noisemap'][:, 0].astype(np.float64), d['psf']))
+    one = [do_one_star_forward_modelling(dd.copy(), nm.copy(), psf, k, n_iter, **flags) for dd, nm, psf in stacks]
+    many = do_stars_forward_modelling_coupled([(dd.copy(), nm.copy(), psf) for dd, nm, psf in stacks], k, n_iter, **flags)
+    assert len(many) == len(one)
+    for a, b in zip(one, many):
+        assert a['scale'] == b['scale']
+        np.testing.assert_allclose(b['fluxes'], a['fluxes'], rtol=1e-6)
+        np.testing.assert_allclose(b['fluxes_uncertainties'], a['fluxes_uncertainties'], rtol=1e-5)
+        np.testing.assert_allclose(b['loss_curve'], a['loss_curve'], rtol=1e-6)
+        np.testing.assert_allclose(b['residuals'], a['residuals'], atol=1e-5 * np.abs(a['residuals']).max() + 1e-9)
+        assert len(b['loss_curve']) == n_iter and np.isfinite(b['chi2'])
