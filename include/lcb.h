@@ -100,6 +100,33 @@ typedef struct {
 int lcb_phot_fit_batch(const lcb_phot_batch* in, const lcb_fit_opts* opt, lcb_phot_out* out,
                        int mem, void* stream);
 
+/* starred.psf.psf.apply_distortion (star_photometry.py:303, roi_file_preparation.py:179): the narrow PSF of frame psf_index[i]
+ * seen at the rescaled frame position xy[i] under that frame's distortion coefficients.  psf [Fp][nu][nu]; theta [Fp][6];
+ * psf_index [B]; xy [B][2]; out [B][nu][nu]; mode as lcb_psf_opts.field_distortion (1 or 2). */
+int lcb_apply_distortion_batch(const float* psf, const float* theta, const int* psf_index, const float* xy, int B, int Fp,
+                               int nu, int mode, float* out, int mem, void* stream);
+
+/* ---------------- reductions on the fitted fluxes (DEVICE pointers only, enqueued on `stream`) ---------------------------
+ * flux, dflux: [F][S] frame-major (item f*S + s, the order of lcb_phot_fit_batch's outputs for F frames x S stars); NaN = no
+ * measurement.  S <= 64 for the scatter matrix and the zero points.
+ *
+ * lightcurver/processes/normalization_calculation.py:157-206 (calculate_coefficient):
+ *   lcb_norm_medians         per-star median flux over the frames (:158)                                        -> median [S]
+ *   lcb_norm_scatter_matrix  Q [S][S] (double) with cost_function_scatter_in_frame(c) = c^T Q c (:75-98) for the fluxes divided
+ *                            by the star medians; work: lcb_norm_scatter_work_doubles(F, S) doubles
+ *   lcb_norm_coefficients    per-frame coefficient = weighted mean over the stars of star_scale * flux / median, weights
+ *                            1 / (scaled uncertainty)^2, and its weighted standard deviation (0 -> 10 % of the coefficient) (:185-204)
+ * lightcurver/processes/absolute_zeropoint_calculation.py:95-100:
+ *   lcb_zeropoints           per-frame median and standard deviation (ddof 1) of catalog_mag[s] + 2.5 log10(flux[f][s]) */
+int lcb_norm_medians(const float* flux, int F, int S, float* median, void* stream);
+int lcb_norm_scatter_work_doubles(int F, int S);
+int lcb_norm_scatter_matrix(const float* flux, const float* dflux, const float* median, int F, int S, double* Q, double* work,
+                            void* stream);
+int lcb_norm_coefficients(const float* flux, const float* dflux, const float* median, const float* star_scale, int F, int S,
+                          float* coefficient, float* coefficient_uncertainty, void* stream);
+int lcb_zeropoints(const float* flux, const float* catalog_mag, int F, int S, float* zeropoint, float* zeropoint_uncertainty,
+                   void* stream);
+
 /* ---------------- K1: per-frame PSF fit (starred build_psf) ------------------------------------ */
 /* Ragged batch: frame f owns stars star_off[f] .. star_off[f+1]-1 of every per-star array. */
 typedef struct {
@@ -109,6 +136,8 @@ typedef struct {
     const float* data;       /* [sumN][n][n] stamps, already normalised by the caller */
     const float* weight;     /* [sumN][n][n] mask / sigma^2 */
     const float* W;          /* [F][J][nu*nu] starlet-space weights supplied by the caller, or NULL */
+    const float* stamp_xy;   /* [sumN][2] rescaled frame coordinates (x, y) of the stamps (utilities/image_coordinates.py:4-25);
+                                needed when lcb_psf_opts.field_distortion != 0, else may be NULL */
 } lcb_psf_batch;
 
 typedef struct {
@@ -121,6 +150,9 @@ typedef struct {
     float fwhm_min, fwhm_max, beta_min, beta_max;   /* bounds of the analytic stage */
     int   mc_samples;        /* noise_weights == 2: number of noise realisations (<= 0: 100) */
     unsigned mc_seed;        /* noise_weights == 2: seed of the counter-based generator */
+    int   field_distortion;  /* build_psf(field_distortion=...), psf_modelling.py:169: 0 off; 1: every star sees the affine
+                                resampling of the frame's narrow PSF given by kwargs_distortion at its frame position (flux
+                                conserving); 2: the same without the determinant factor.  Stage 2 fits the 6 coefficients. */
 } lcb_psf_opts;
 
 typedef struct {
@@ -138,6 +170,9 @@ typedef struct {
     float* grad_b0;          /* [F][nu*nu] d loss / d background at the initial point (may be NULL) */
     float* grad_s0;          /* [sumN][3] d loss / d (a, x0, y0) at the initial point (may be NULL) */
     int*   status;           /* [F] (may be NULL) */
+    float* distortion;       /* [F][6] kwargs_distortion: dilation_x (2), dilation_y (2), shear (2), each linear in the rescaled
+                                frame position (X, Y); in: initial, out: fitted.  Mandatory when field_distortion != 0 */
+    float* grad_dist0;       /* [F][6] d loss / d distortion at the initial point (may be NULL) */
 } lcb_psf_out;
 
 /* number of starlet scales used for a grid of side nu: int(log2(nu)) */
@@ -215,6 +250,13 @@ int lcb_deconv_step_update(void* handle, int it, int n_iter, float lr, int sched
 /* applies the pending per-epoch update of the last step_update and clears the pending flag (end of an external loop) */
 int lcb_deconv_flush(void* handle);
 int lcb_deconv_loss_grad(void* handle, lcb_deconv_grad* g, int mem);
+/* Stage 1 of do_modelling_of_roi (roi_modelling.py:260-281: Optimizer('l-bfgs-b').minimize over {dx, dy, a}) with the optimiser
+ * state resident on the device: projected L-BFGS (10 pairs) + Armijo backtracking, bounds a >= a_lower and |dx|, |dy| <= n/2,
+ * scipy's stopping rules (relative decrease <= ftol, projected gradient <= pgtol, maxiter).  No host round trip per evaluation:
+ * the host enqueues 16 evaluate-and-step rounds at a time and reads one flag.  Single-rank handles.
+ * loss_hist [maxiter] (may be NULL): loss after every accepted iteration; info [5] (may be NULL): iterations, evaluations, stop
+ * reason (1 ftol, 2 pgtol, 3 maxiter, 4 line search stalled, 0 budget), final loss, |projected gradient|_inf. */
+int lcb_deconv_lbfgs(void* handle, int maxiter, float a_lower, float ftol, float pgtol, float* loss_hist, float* info, int mem);
 /* current parameters; model [E][n][n] and loss [1] are evaluated when non-NULL */
 int lcb_deconv_get(void* handle, lcb_deconv_params* q, float* model, float* loss, int mem);
 /* starlet-space noise weights of h: stage 0 fills the reduce buffer with the local variance plane
@@ -267,6 +309,9 @@ int lcb_phot_prepare_batch(const lcb_phot_prepare_in* in, lcb_phot_prepare_out* 
 int lcb_fp32_peak(int iters, float* tflops, float* ms);
 /* same with three-register FFMAs in an 8x8 outer-product pattern (what a stencil inner loop issues) */
 int lcb_fp32_peak_rrr(int iters, float* tflops, float* ms);
+/* packed FP32 (FFMA2, sm_100): which = 0 FFMA2 chains; 1 / 2 = scalar / packed FMAs interleaved with one shared-memory load per
+ * two FMAs (how many issue slots the packed form leaves for the loads of a stencil loop).  2 flops per scalar FMA. */
+int lcb_fp32x2_peak(int iters, int which, float* tflops, float* ms);
 
 /* Per-kernel device timing: after lcb_profile_enable(1) every kernel launched by the library is
  * bracketed by CUDA events on its launch stream; lcb_profile_summary() synchronises on them and

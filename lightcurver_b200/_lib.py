@@ -156,12 +156,20 @@ def set_conventions(**kw):
 
 
 lib.lcb_fp32_peak_rrr.argtypes = [C.c_int, c_fp, c_fp]
+lib.lcb_fp32x2_peak.argtypes = [C.c_int, C.c_int, c_fp, c_fp]
 
 
 def fp32_peak_rrr(iters=4096):
     require_device()
     t, ms = C.c_float(0), C.c_float(0)
     check(lib.lcb_fp32_peak_rrr(iters, C.byref(t), C.byref(ms)), 'lcb_fp32_peak_rrr')
+    return float(t.value), float(ms.value)
+
+
+def fp32x2_peak(which=0, iters=4096):
+    require_device()
+    t, ms = C.c_float(0), C.c_float(0)
+    check(lib.lcb_fp32x2_peak(iters, which, C.byref(t), C.byref(ms)), 'lcb_fp32x2_peak')
     return float(t.value), float(ms.value)
 
 
@@ -174,18 +182,18 @@ def fp32_peak(iters=4096):
 
 class PsfBatch(C.Structure):
     _fields_ = [('F', C.c_int), ('star_off', C.c_void_p), ('n', C.c_int), ('k', C.c_int),
-                ('data', C.c_void_p), ('weight', C.c_void_p), ('W', C.c_void_p)]
+                ('data', C.c_void_p), ('weight', C.c_void_p), ('W', C.c_void_p), ('stamp_xy', C.c_void_p)]
 
 
 class PsfOpts(C.Structure):
     _fields_ = [('n_iter_analytic', C.c_int), ('n_iter_adabelief', C.c_int), ('lr', C.c_float),
                 ('lam_scales', C.c_float), ('lam_hf', C.c_float), ('noise_weights', C.c_int),
                 ('fwhm_min', C.c_float), ('fwhm_max', C.c_float), ('beta_min', C.c_float), ('beta_max', C.c_float),
-                ('mc_samples', C.c_int), ('mc_seed', C.c_uint)]
+                ('mc_samples', C.c_int), ('mc_seed', C.c_uint), ('field_distortion', C.c_int)]
 
 
 PSF_OUT_FIELDS = ('moffat', 'a', 'x0', 'y0', 'background', 'narrow_psf', 'full_psf', 'residuals', 'chi2',
-                  'loss_hist', 'loss_hist_analytic', 'W_out', 'loss0', 'grad_b0', 'grad_s0', 'status')
+                  'loss_hist', 'loss_hist_analytic', 'W_out', 'loss0', 'grad_b0', 'grad_s0', 'status', 'distortion', 'grad_dist0')
 
 
 class PsfOut(C.Structure):
@@ -196,6 +204,14 @@ lib.lcb_starlet_scales.argtypes = [C.c_int]
 lib.lcb_starlet_scales.restype = C.c_int
 lib.lcb_psf_fit_batch.argtypes = [C.POINTER(PsfBatch), C.POINTER(PsfOpts), C.POINTER(PsfOut), C.c_int, C.c_void_p]
 lib.lcb_psf_fit_batch.restype = C.c_int
+lib.lcb_apply_distortion_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                           C.c_void_p, C.c_int, C.c_void_p]
+lib.lcb_apply_distortion_batch.restype = C.c_int
+lib.lcb_norm_medians.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+lib.lcb_norm_scatter_work_doubles.argtypes = [C.c_int, C.c_int]
+lib.lcb_norm_scatter_matrix.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+lib.lcb_norm_coefficients.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+lib.lcb_zeropoints.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
 
 
 lib.lcb_profile_enable.argtypes = [C.c_int]
@@ -243,6 +259,7 @@ lib.lcb_deconv_reduce_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.PO
 lib.lcb_deconv_step_update.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int]
 lib.lcb_deconv_flush.argtypes = [C.c_void_p]
 lib.lcb_deconv_loss_grad.argtypes = [C.c_void_p, C.POINTER(DeconvGrad), C.c_int]
+lib.lcb_deconv_lbfgs.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int]
 lib.lcb_deconv_get.argtypes = [C.c_void_p, C.POINTER(DeconvParams), C.c_void_p, C.c_void_p, C.c_int]
 lib.lcb_deconv_destroy.argtypes = [C.c_void_p]
 lib.lcb_deconv_noise_weights.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]

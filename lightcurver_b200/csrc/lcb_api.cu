@@ -206,6 +206,84 @@ __global__ void __launch_bounds__(256) k_fp32_peak_rrr(int iters, const float* i
     if (s == 123.456f) sink[0] = s;
 }
 
+// The same probe with the packed FP32 instructions of sm_100 (FFMA2: one instruction, two FMAs per lane on a 64-bit register
+// pair; __ffma2_rn).  8 independent FFMA2 chains per thread.  Tells whether a kernel that is bound by instruction ISSUE (the
+// stencil kernels: DESIGN.md section 4) can halve the issue slots its arithmetic takes.
+__global__ void __launch_bounds__(1024) k_fp32x2_peak(int iters, float* sink) {
+    float2 a0 = make_float2(threadIdx.x * 1e-3f, 0.5f), a1 = a0, a2 = a0, a3 = a0, a4 = a0, a5 = a0, a6 = a0, a7 = a0;
+    a1.x += 1.f; a2.x += 2.f; a3.x += 3.f; a4.x += 4.f; a5.x += 5.f; a6.x += 6.f; a7.x += 7.f;
+    const float2 m = make_float2(0.999f, 0.998f), c = make_float2(1e-3f, 2e-3f);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            a0 = __ffma2_rn(a0, m, c); a1 = __ffma2_rn(a1, m, c); a2 = __ffma2_rn(a2, m, c); a3 = __ffma2_rn(a3, m, c);
+            a4 = __ffma2_rn(a4, m, c); a5 = __ffma2_rn(a5, m, c); a6 = __ffma2_rn(a6, m, c); a7 = __ffma2_rn(a7, m, c);
+        }
+    }
+    const float s = (a0.x + a1.x + a2.x + a3.x + a4.x + a5.x + a6.x + a7.x) + (a0.y + a1.y + a2.y + a3.y + a4.y + a5.y + a6.y + a7.y);
+    if (s == 123.456f) sink[0] = s;
+}
+
+// mixed issue probe: per FFMA2 (or per pair of FFMAs when packed == 0) one conflict-free LDS.32 whose value feeds the chain --
+// measures how many issue slots the packed form leaves for the loads of a stencil loop
+template <int PACKED>
+__global__ void __launch_bounds__(1024) k_fp32_mix(int iters, float* sink) {
+    __shared__ float sm[2048];
+    for (int i = threadIdx.x; i < 2048; i += 1024) sm[i] = 1e-3f * (float)i;
+    __syncthreads();
+    float2 a0 = make_float2(threadIdx.x * 1e-3f, 0.5f), a1 = a0, a2 = a0, a3 = a0;
+    const float2 m = make_float2(0.999f, 0.998f);
+    int idx = threadIdx.x;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float v0 = sm[(idx + 32 * j) & 2047], v1 = sm[(idx + 32 * j + 512) & 2047];
+            const float v2 = sm[(idx + 32 * j + 1024) & 2047], v3 = sm[(idx + 32 * j + 1536) & 2047];
+            if (PACKED) {
+                a0 = __ffma2_rn(a0, m, make_float2(v0, v0)); a1 = __ffma2_rn(a1, m, make_float2(v1, v1));
+                a2 = __ffma2_rn(a2, m, make_float2(v2, v2)); a3 = __ffma2_rn(a3, m, make_float2(v3, v3));
+            } else {
+                a0.x = fmaf(a0.x, m.x, v0); a0.y = fmaf(a0.y, m.y, v0); a1.x = fmaf(a1.x, m.x, v1); a1.y = fmaf(a1.y, m.y, v1);
+                a2.x = fmaf(a2.x, m.x, v2); a2.y = fmaf(a2.y, m.y, v2); a3.x = fmaf(a3.x, m.x, v3); a3.y = fmaf(a3.y, m.y, v3);
+            }
+        }
+        idx += 7;
+    }
+    const float s = (a0.x + a1.x + a2.x + a3.x) + (a0.y + a1.y + a2.y + a3.y);
+    if (s == 123.456f) sink[0] = s;
+}
+
+// which: 0 = FFMA2 chains, 1 = FFMA + LDS mix, 2 = FFMA2 + LDS mix.  tflops counts 2 flops per scalar FMA.
+extern "C" int lcb_fp32x2_peak(int iters, int which, float* tflops, float* ms_out) {
+    LCB_REQUIRE(iters > 0 && tflops != nullptr && which >= 0 && which <= 2, "lcb_fp32x2_peak: bad arguments");
+    int dev = 0, sms = 0;
+    LCB_CUDA(cudaGetDevice(&dev));
+    LCB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    float* sink = nullptr;
+    LCB_CUDA(cudaMalloc(&sink, 4));
+    cudaEvent_t e0, e1;
+    LCB_CUDA(cudaEventCreate(&e0));
+    LCB_CUDA(cudaEventCreate(&e1));
+    const int grid = sms * 2;
+    auto launch = [&](int it) {
+        if (which == 0) k_fp32x2_peak<<<grid, 1024>>>(it, sink);
+        else if (which == 1) k_fp32_mix<0><<<grid, 1024>>>(it, sink);
+        else k_fp32_mix<1><<<grid, 1024>>>(it, sink);
+    };
+    launch(iters / 8 + 1);
+    LCB_CUDA(cudaEventRecord(e0));
+    launch(iters);
+    LCB_CUDA(cudaEventRecord(e1));
+    LCB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    LCB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double fma_per_thread = (which == 0 ? 2.0 * 8.0 : 2.0 * 4.0) * 16.0 * (double)iters;
+    *tflops = (float)(2.0 * fma_per_thread * 1024.0 * (double)grid / (ms * 1e-3) / 1e12);
+    if (ms_out) *ms_out = ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    return LCB_OK;
+}
+
 extern "C" int lcb_fp32_peak_rrr(int iters, float* tflops, float* ms_out) {
     LCB_REQUIRE(iters > 0 && tflops != nullptr, "lcb_fp32_peak_rrr: bad arguments");
     int dev = 0, sms = 0;

@@ -1341,6 +1341,186 @@ __global__ void k_deconv_fu_apply(DeconvDev D) {
     D.ep_g[(size_t)e * np + m] += D.fu[DC_MMAX + m] * (D.ep[(size_t)e * np + m] - D.fu[m]) - D.fu[2 * DC_MMAX + m];
 }
 
+// ---------------------------------------------------------------- device-side L-BFGS of stage 1 (roi_modelling.py:260-281)
+// The reference minimises {dx, dy, a} with scipy's L-BFGS-B (host optimiser, one host round trip per evaluation).  Here the
+// optimiser state lives in device memory and ONE CTA drives it between evaluations: projected L-BFGS (m = LB_M pairs, two-loop
+// recursion on the gradient with the coordinates that sit on an active bound removed, trial points projected onto the box,
+// Armijo backtracking, curvature pairs kept only when s.y > 0) with scipy's stopping rules (relative loss decrease <= ftol,
+// projected gradient <= pgtol, maxiter).  The host only enqueues "evaluate ; step" rounds and polls one flag per chunk.
+// Vector layout: i = e * (M + 2) + p, p < M: a_em (lower bound a_lo), p = M, M+1: dx_e, dy_e (|.| <= n/2).
+#define LB_M 10
+#define LB_THREADS 1024
+#define LB_FLAT 10
+struct LbState {
+    float *x, *g, *d, *S, *Y;      // [nv], [nv], [nv], [LB_M][nv], [LB_M][nv]
+    float *rho;                    // [LB_M]
+    float *sc;                     // [16] 0 f, 1 step t, 2 slope g.d, 3 iterations, 4 pairs stored, 5 converged (1 ftol, 2 pgtol, 3 maxiter,
+                                   //      4 line search stalled), 6 evaluations, 7 head of the circular history, 8 |proj grad|_inf, 9 rejected steps in a row,
+                                   //      10 accepted steps in a row whose relative decrease was <= ftol
+    float *hist;                   // [maxiter] loss after every accepted iteration
+    int nv, maxiter;
+    float a_lo, d_max, ftol, pgtol;
+};
+
+__device__ __forceinline__ float lb_block_sum(float v, float* red, int tid) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < LB_THREADS / 32; ++w) s += red[w];
+    return s;
+}
+__device__ __forceinline__ float lb_block_max(float v, float* red, int tid) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < LB_THREADS / 32; ++w) s = fmaxf(s, red[w]);
+    return s;
+}
+
+__global__ void __launch_bounds__(LB_THREADS) k_deconv_lbfgs_step(DeconvDev D, LbState L, const float* __restrict__ loss_in) {
+    __shared__ float red[LB_THREADS / 32];
+    __shared__ float alpha[LB_M];
+    const int tid = threadIdx.x, nv = L.nv, M = D.M, np = M + 3, npv = M + 2;
+    float* sc = L.sc;
+    if (sc[5] != 0.f) return;                                   // converged: the remaining rounds of the chunk are no-ops
+    auto lo = [&](int i) { return (i % npv < M) ? L.a_lo : -L.d_max; };
+    auto hi = [&](int i) { return (i % npv < M) ? INFINITY : L.d_max; };
+    auto ep_idx = [&](int i) { return (i / npv) * np + (i % npv); };
+    const float f_t = *loss_in;
+    const int evals = (int)sc[6];
+    bool accept = true;
+    const float f_old = sc[0];
+    if (evals > 0) {
+        // Armijo on the projected step: f_t <= f + c1 g.(x_t - x)
+        float part = 0.f;
+        for (int i = tid; i < nv; i += LB_THREADS) part = fmaf(L.g[i], D.ep[ep_idx(i)] - L.x[i], part);
+        const float gs = lb_block_sum(part, red, tid);
+        accept = isfinite(f_t) && (f_t <= f_old + 1e-4f * gs);
+    }
+    if (!accept) {
+        const float t = sc[1] * 0.5f;
+        const float rej = sc[9] + 1.f;
+        __syncthreads();
+        if (tid == 0) { sc[1] = t; sc[9] = rej; sc[6] = (float)(evals + 1); if (rej > 30.f) sc[5] = 4.f; }
+        for (int i = tid; i < nv; i += LB_THREADS) D.ep[ep_idx(i)] = fminf(fmaxf(fmaf(t, L.d[i], L.x[i]), lo(i)), hi(i));
+        return;
+    }
+    // ---- accepted (or first evaluation): curvature pair, new point
+    int pairs = (int)sc[4], head = (int)sc[7];
+    const int iters = (int)sc[3] + (evals > 0 ? 1 : 0);
+    if (evals > 0) {
+        float sy = 0.f, yy = 0.f;
+        float* Sn = L.S + (size_t)head * nv;
+        float* Yn = L.Y + (size_t)head * nv;
+        for (int i = tid; i < nv; i += LB_THREADS) {
+            const float s_ = D.ep[ep_idx(i)] - L.x[i], y_ = D.ep_g[ep_idx(i)] - L.g[i];
+            Sn[i] = s_; Yn[i] = y_;
+            sy = fmaf(s_, y_, sy); yy = fmaf(y_, y_, yy);
+        }
+        sy = lb_block_sum(sy, red, tid);
+        yy = lb_block_sum(yy, red, tid);
+        if (sy > 1e-10f * yy && sy > 0.f) {
+            if (tid == 0) L.rho[head] = 1.f / sy;
+            head = (head + 1) % LB_M;
+            pairs = min(pairs + 1, LB_M);
+        }
+    }
+    float pgmax = 0.f;
+    for (int i = tid; i < nv; i += LB_THREADS) {
+        const float xi = D.ep[ep_idx(i)], gi = D.ep_g[ep_idx(i)];
+        L.x[i] = xi; L.g[i] = gi;
+        // projected gradient: x - P(x - g)
+        const float pg = xi - fminf(fmaxf(xi - gi, lo(i)), hi(i));
+        pgmax = fmaxf(pgmax, fabsf(pg));
+    }
+    pgmax = lb_block_max(pgmax, red, tid);
+    int conv = 0;
+    float flat = 0.f;
+    if (evals > 0) {
+        if (tid == 0 && iters - 1 < L.maxiter) L.hist[iters - 1] = f_t;
+        // scipy stops at the first relative decrease <= ftol (2.2e-9 by default).  The loss here is a float32 number: decreases
+        // below ~1e-7 of it read as zero although the iteration is still making progress (measured: scipy in float64 gains
+        // another 0.3 % over 230 such iterations), so the rule only fires after LB_FLAT accepted steps in a row without a
+        // resolvable decrease
+        if (f_old - f_t <= L.ftol * fmaxf(fmaxf(fabsf(f_old), fabsf(f_t)), 1.f)) flat = sc[10] + 1.f;
+        if (flat >= (float)LB_FLAT) conv = 1;
+    }
+    if (pgmax <= L.pgtol) conv = 2;
+    if (!conv && iters >= L.maxiter) conv = 3;
+    __syncthreads();
+    // ---- direction: two-loop recursion on the free part of the gradient
+    auto is_free = [&](int i, float xi, float gi) { return !((xi <= lo(i) && gi > 0.f) || (xi >= hi(i) && gi < 0.f)); };
+    for (int i = tid; i < nv; i += LB_THREADS) { const float xi = L.x[i], gi = L.g[i]; L.d[i] = is_free(i, xi, gi) ? gi : 0.f; }
+    __syncthreads();
+    for (int q = 0; q < pairs; ++q) {
+        const int j = (head - 1 - q + 2 * LB_M) % LB_M;
+        float part = 0.f;
+        for (int i = tid; i < nv; i += LB_THREADS) part = fmaf(L.S[(size_t)j * nv + i], L.d[i], part);
+        const float a_ = L.rho[j] * lb_block_sum(part, red, tid);
+        if (tid == 0) alpha[j] = a_;
+        for (int i = tid; i < nv; i += LB_THREADS) L.d[i] = fmaf(-a_, L.Y[(size_t)j * nv + i], L.d[i]);
+        __syncthreads();
+    }
+    if (pairs > 0) {
+        const int j = (head - 1 + LB_M) % LB_M;
+        float yy = 0.f;
+        for (int i = tid; i < nv; i += LB_THREADS) { const float y_ = L.Y[(size_t)j * nv + i]; yy = fmaf(y_, y_, yy); }
+        yy = lb_block_sum(yy, red, tid);
+        const float gam = 1.f / (L.rho[j] * yy);
+        for (int i = tid; i < nv; i += LB_THREADS) L.d[i] *= gam;
+        __syncthreads();
+    }
+    for (int q = pairs - 1; q >= 0; --q) {
+        const int j = (head - 1 - q + 2 * LB_M) % LB_M;
+        float part = 0.f;
+        for (int i = tid; i < nv; i += LB_THREADS) part = fmaf(L.Y[(size_t)j * nv + i], L.d[i], part);
+        const float b_ = L.rho[j] * lb_block_sum(part, red, tid);
+        const float a_ = alpha[j];
+        for (int i = tid; i < nv; i += LB_THREADS) L.d[i] = fmaf(a_ - b_, L.S[(size_t)j * nv + i], L.d[i]);
+        __syncthreads();
+    }
+    // d = -H g on the free coordinates; fall back to steepest descent if it is not a descent direction
+    float slope = 0.f, gn2 = 0.f;
+    for (int i = tid; i < nv; i += LB_THREADS) {
+        const float xi = L.x[i], gi = L.g[i];
+        const float di = is_free(i, xi, gi) ? -L.d[i] : 0.f;
+        L.d[i] = di;
+        slope = fmaf(gi, di, slope);
+        gn2 += is_free(i, xi, gi) ? gi * gi : 0.f;
+    }
+    slope = lb_block_sum(slope, red, tid);
+    gn2 = lb_block_sum(gn2, red, tid);
+    float t = 1.f;
+    if (!(slope < 0.f) || pairs == 0) {
+        for (int i = tid; i < nv; i += LB_THREADS) { const float xi = L.x[i], gi = L.g[i]; L.d[i] = is_free(i, xi, gi) ? -gi : 0.f; }
+        slope = -gn2;
+        t = fminf(1.f, rsqrtf(fmaxf(gn2, 1e-30f)));             // scipy / Nocedal: first step of length min(1, 1/|g|)
+    }
+    __syncthreads();
+    if (tid == 0) {
+        sc[0] = f_t; sc[1] = t; sc[2] = slope; sc[3] = (float)iters; sc[4] = (float)pairs; sc[5] = (float)conv;
+        sc[6] = (float)(evals + 1); sc[7] = (float)head; sc[8] = pgmax; sc[9] = 0.f; sc[10] = flat;
+    }
+    // next trial point (or, when converged, the accepted point itself: it is already in D.ep)
+    if (!conv)
+        for (int i = tid; i < nv; i += LB_THREADS) D.ep[ep_idx(i)] = fminf(fmaxf(fmaf(t, L.d[i], L.x[i]), lo(i)), hi(i));
+}
+
+// restores the last ACCEPTED point (a rejected trial may be sitting in D.ep when the rounds run out)
+__global__ void k_deconv_lbfgs_finish(DeconvDev D, LbState L) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L.nv || L.sc[6] == 0.f) return;
+    const int npv = D.M + 2;
+    D.ep[(i / npv) * (D.M + 3) + (i % npv)] = L.x[i];
+}
+
 // ================================================================= host side: handle-based ABI
 struct DeconvHandle {
     DeconvDev D;
@@ -1361,6 +1541,7 @@ struct DeconvHandle {
     float *gh, *gcx, *ls;                // evaluation outputs (lcb_deconv_loss_grad / _get)
     float* W_spare;                      // weight cube detached by set_reg(W = NULL), reused by the next one
     float* noise_tab;                    // 1-D kernels of the starlet-space noise propagation
+    float* lbfgs; size_t lbfgs_floats;   // state of the device-side L-BFGS of stage 1 (lcb_deconv_lbfgs)
 };
 
 static int dalloc(DeconvHandle* H, void** p, size_t bytes, bool zero) {
@@ -1529,7 +1710,7 @@ int lcb_deconv_create(const lcb_deconv_problem* p, int mem, void* stream, void**
         if (cudaStreamCreate(&H->st_own) != cudaSuccess) { lcb_set_error("lcb_deconv_create: cannot create a stream"); delete H; return LCB_ERR_CUDA; }
         H->st = H->st_own;
     }
-    H->comm_buf = nullptr; H->CS = 0; H->CS_user = 0; H->seq = 0;
+    H->comm_buf = nullptr; H->CS = 0; H->CS_user = 0; H->seq = 0; H->lbfgs = nullptr; H->lbfgs_floats = 0;
     H->st2 = nullptr; H->ev_h = nullptr; H->ev_go = nullptr; H->ev_reg = nullptr; H->reg_pending = false; H->starlet_attr = false; H->noise_tab = nullptr; H->W_spare = nullptr;
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);     // the 8 starlet CTAs must get their SMs before the epoch grid fills the GPU
@@ -1754,6 +1935,59 @@ int lcb_deconv_step_update(void* handle, int it, int n_iter, float lr, int sched
 // n_iter AdaBelief iterations enqueued back to back, no host synchronisation inside the loop.  With a connected
 // communicator (lcb_deconv_comm_*) every rank calls this with the same options: the gradient of the shared
 // parameters is exchanged inside k_deconv_reduce / k_deconv_update over peer memory.
+// Stage 1 of do_modelling_of_roi on the device: minimises the current loss over {dx, dy, a} (whatever the free flags say about
+// the other parameters, they stay where they are), at most maxiter iterations.  Single rank only (the sharded stage 1 keeps
+// the host optimiser over lcb_deconv_loss_grad).  info: [0] iterations, [1] evaluations, [2] stop reason (1 ftol, 2 pgtol,
+// 3 maxiter, 4 line search stalled, 0 evaluation budget exhausted), [3] final loss, [4] |projected gradient|_inf.
+int lcb_deconv_lbfgs(void* handle, int maxiter, float a_lower, float ftol, float pgtol, float* loss_hist, float* info, int mem) {
+    DeconvHandle* H = (DeconvHandle*)handle;
+    LCB_REQUIRE(H && maxiter >= 1, "lcb_deconv_lbfgs: bad arguments");
+    DeconvDev& D = H->D;
+    LCB_REQUIRE(D.cm.world <= 1, "lcb_deconv_lbfgs: single-rank handles only (sharded stage 1: host L-BFGS-B over lcb_deconv_loss_grad)");
+    const int nv = D.E * (D.M + 2);
+    const size_t need = (size_t)nv * (3 + 2 * LB_M) + LB_M + 16 + (size_t)maxiter;
+    int rc;
+    if (need > H->lbfgs_floats) {
+        if ((rc = dalloc(H, (void**)&H->lbfgs, need * 4, false))) return rc;
+        H->lbfgs_floats = need;
+    }
+    LbState L;
+    L.x = H->lbfgs; L.g = L.x + nv; L.d = L.g + nv; L.S = L.d + nv; L.Y = L.S + (size_t)LB_M * nv;
+    L.rho = L.Y + (size_t)LB_M * nv; L.sc = L.rho + LB_M; L.hist = L.sc + 16;
+    L.nv = nv; L.maxiter = maxiter; L.a_lo = a_lower; L.d_max = 0.5f * (float)D.n; L.ftol = ftol; L.pgtol = pgtol;
+    LCB_CUDA(cudaMemsetAsync(L.rho, 0, (LB_M + 16 + (size_t)maxiter) * 4, H->st));
+    const int max_evals = 20 * maxiter + 20;              // scipy's maxfun as the reference-shaped host path passes it
+    int evals = 0;
+    float flag = 0.f;
+    while (evals < max_evals && flag == 0.f) {
+        const int chunk = (max_evals - evals < 16) ? max_evals - evals : 16;
+        for (int c = 0; c < chunk; ++c) {
+            LCB_CUDA(cudaMemsetAsync(D.ctl + 4, 0, 4, H->st));
+            if ((rc = launch_starlet(H)) || (rc = launch_epoch(H, 0)) || (rc = launch_reduce(H, 0, 0)) ||
+                (rc = launch_update(H, -1, 1, 0.f, 0, 0, H->gh, H->gcx, H->ls))) return rc;
+            if (D.lam_fu != 0.f && D.M > 0) k_deconv_fu_apply<<<(D.E * D.M + 255) / 256, 256, 0, H->st>>>(D);
+            { LcbProfScope ps("k_deconv_lbfgs_step", H->st); k_deconv_lbfgs_step<<<1, LB_THREADS, 0, H->st>>>(D, L, H->ls); }
+            LCB_CUDA(cudaGetLastError());
+        }
+        evals += chunk;
+        LCB_CUDA(cudaMemcpyAsync(&flag, L.sc + 5, 4, cudaMemcpyDeviceToHost, H->st));     // ONE 4-byte read per 16 evaluations
+        LCB_CUDA(cudaStreamSynchronize(H->st));
+    }
+    k_deconv_lbfgs_finish<<<(nv + 255) / 256, 256, 0, H->st>>>(D, L);
+    LCB_CUDA(cudaGetLastError());
+    float scl[16];
+    LCB_CUDA(cudaMemcpyAsync(scl, L.sc, sizeof(scl), cudaMemcpyDeviceToHost, H->st));
+    LCB_CUDA(cudaStreamSynchronize(H->st));
+    const int iters = (int)scl[3];
+    if (info) {
+        const float inf[5] = {scl[3], scl[6], scl[5], scl[0], scl[8]};
+        if (mem == LCB_MEM_HOST) memcpy(info, inf, sizeof(inf));
+        else LCB_CUDA(cudaMemcpy(info, inf, sizeof(inf), cudaMemcpyHostToDevice));
+    }
+    if (loss_hist && iters > 0) { if ((rc = get(H, loss_hist, L.hist, (size_t)(iters < maxiter ? iters : maxiter), mem))) return rc; }
+    return LCB_OK;
+}
+
 // One run = begin (loss buffer, device-resident counters, first iteration eagerly, ONE captured CUDA graph of an iteration),
 // n_iter - 1 replays, end (pending per-epoch update, peers, loss history).  lcb_deconv_run drives one handle; lcb_deconv_run_many
 // interleaves the replays of several handles (each on its own stream), so that many small joint fits fill the GPU together.

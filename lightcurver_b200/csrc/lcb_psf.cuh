@@ -27,5 +27,10 @@ struct PsfArgs {
     size_t work_per_frame;          // floats
     int* status;                    // [F]
     float fwhm_min, fwhm_max, beta_min, beta_max;
+    // field distortion (lcb_distort.cuh): 0 = off, 1 = flux-conserving affine resampling, 2 = plain resampling
+    int distort;
+    const float* stamp_xy;          // [sumN][2] rescaled frame coordinates of the stamps (image_coordinates.py:4-25)
+    float* distortion;              // [F][6] theta, in: initial, out: fitted
+    float* grad_dist0;              // [F][6] d loss / d theta at the initial point, or NULL
     DevConv cv;
 };

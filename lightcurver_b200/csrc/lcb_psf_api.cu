@@ -99,8 +99,12 @@ static int psf_run_device(const lcb_psf_batch* in, const lcb_psf_opts* opt, lcb_
     const size_t lm_jim = (size_t)8 * n * (n + 1) * 4;
     const bool lm_jim_sm = lm_small + lm_jim <= (size_t)maxsm;
     const bool lm_planes_sm = lm_jim_sm && lm_small + lm_jim + (size_t)5 * pp * 4 <= (size_t)maxsm;
-    const size_t wpf = (size_t)(J + 7) * pp + (size_t)2 * Nmax * n * n;   // floats per frame of workspace
-    const bool fit_fast = lcb_psf_fit_has_fast(n, k, lcb_conv().gauss_taps) &&
+    const bool distort = opt->field_distortion != 0;
+    LCB_REQUIRE(!distort || (in->stamp_xy && out->distortion), "field_distortion needs stamp_xy and the distortion in/out array");
+    LCB_REQUIRE(opt->field_distortion >= 0 && opt->field_distortion <= 2, "field_distortion must be 0, 1 or 2");
+    // floats per frame of workspace (+ the resampled PSF of the current star and its gradient plane with field distortion)
+    const size_t wpf = (size_t)(J + 7) * pp + (size_t)2 * Nmax * n * n + (distort ? (size_t)2 * pp : 0);
+    const bool fit_fast = !distort && lcb_psf_fit_has_fast(n, k, lcb_conv().gauss_taps) &&
                           fit_small + lcb_psf_fit_smem_fast_extra(n, nu, J) <= (size_t)maxsm;
     const int chunk = F < 1184 ? F : 1184;                   // 8 waves of 148 CTAs
     // grids too large for one SM: one 8-CTA cluster per frame with the planes distributed over its shared memories
@@ -110,7 +114,7 @@ static int psf_run_device(const lcb_psf_batch* in, const lcb_psf_opts* opt, lcb_
     // (column passes of the starlet) and by the latency of ~150 barrier-separated phases per iteration; at 20 us per
     // iteration-frame it does not yet beat the single-CTA kernel with L2-resident planes (13.6 us), so it is opt-in.
     const bool cl_want = cl_env ? (cl_env[0] == '1') : false;
-    const bool fit_cluster = cl_want && lcb_psf_fit_cluster_ok(n, k, lcb_conv().gauss_taps, Nmax, J, maxsm);
+    const bool fit_cluster = cl_want && !distort && lcb_psf_fit_cluster_ok(n, k, lcb_conv().gauss_taps, Nmax, J, maxsm);
 
     DevTemp work(st), sfix(st), Wtmp(st), tabd(st);
     int rc;
@@ -159,6 +163,10 @@ static int psf_run_device(const lcb_psf_batch* in, const lcb_psf_opts* opt, lcb_
         A.status = out->status ? out->status + f0 : nullptr;
         A.fwhm_min = opt->fwhm_min; A.fwhm_max = opt->fwhm_max; A.beta_min = opt->beta_min; A.beta_max = opt->beta_max;
         A.cv = lcb_devconv();
+        A.distort = opt->field_distortion;
+        A.stamp_xy = in->stamp_xy;
+        A.distortion = distort ? out->distortion + (size_t)f0 * 6 : nullptr;
+        A.grad_dist0 = (distort && out->grad_dist0) ? out->grad_dist0 + (size_t)f0 * 6 : nullptr;
         if (opt->n_iter_analytic > 0) {
             A.planes_in_smem = lm_planes_sm;
             A.jim_in_smem = lm_jim_sm;
@@ -228,7 +236,7 @@ extern "C" int lcb_psf_fit_batch(const lcb_psf_batch* in, const lcb_psf_opts* op
     const int T1 = opt->n_iter_analytic, T2 = opt->n_iter_adabelief;
     size_t need = (size_t)(F + 1) * 4 + 2 * sumN * nn * 4 + (in->W || out->W_out ? (size_t)F * J * pp * 4 : 0) +
                   (size_t)F * 5 * 4 + 3 * (size_t)sumN * 4 + 4 * F * pp * 4 + sumN * nn * 4 + (size_t)F * 4 * 3 +
-                  (size_t)F * (T1 + T2) * 4 + (size_t)sumN * 12 + 64 * 256;
+                  (size_t)F * (T1 + T2) * 4 + (size_t)sumN * 12 + (size_t)sumN * 8 + (size_t)F * 48 + 64 * 256;
     LcbArenaLease lease;
     LcbArena& ar = *lease.a;
     int rc = ar.reserve(need);
@@ -260,7 +268,7 @@ extern "C" int lcb_psf_fit_batch(const lcb_psf_batch* in, const lcb_psf_opts* op
     };
 #define UP(f, bytes) if ((rc = up(in->f, bytes, (const void**)&din.f))) return rc;
     UP(star_off, (size_t)(F + 1) * 4) UP(data, sumN * nn * 4) UP(weight, sumN * nn * 4)
-    UP(W, (size_t)F * J * pp * 4)
+    UP(W, (size_t)F * J * pp * 4) UP(stamp_xy, (size_t)sumN * 8)
 #undef UP
 #define IO(f, bytes, upl) if ((rc = io(out->f, bytes, (void**)&dout.f, upl))) return rc;
     IO(moffat, (size_t)F * 20, true) IO(a, (size_t)sumN * 4, true) IO(x0, (size_t)sumN * 4, true) IO(y0, (size_t)sumN * 4, true)
@@ -269,10 +277,57 @@ extern "C" int lcb_psf_fit_batch(const lcb_psf_batch* in, const lcb_psf_opts* op
     IO(chi2, (size_t)F * 4, false) IO(loss_hist, (size_t)F * T2 * 4, false) IO(loss_hist_analytic, (size_t)F * T1 * 4, false)
     IO(W_out, (size_t)F * J * pp * 4, false) IO(loss0, (size_t)F * 4, false) IO(grad_b0, F * pp * 4, false)
     IO(grad_s0, (size_t)sumN * 12, false) IO(status, (size_t)F * 4, false)
+    IO(distortion, (size_t)F * 24, true) IO(grad_dist0, (size_t)F * 24, false)
 #undef IO
     rc = psf_run_device(&din, opt, &dout, sumN, Nmax, st);
     if (rc) return rc;
     for (const Back& b : back) LCB_CUDA(cudaMemcpyAsync(b.h, b.d, b.bytes, cudaMemcpyDeviceToHost, st));
+    LCB_CUDA(cudaStreamSynchronize(st));
+    return LCB_OK;
+}
+
+// ---------------------------------------------------------------- apply_distortion (one CTA per item)
+#include "lcb_distort.cuh"
+__global__ void __launch_bounds__(256) k_apply_distortion(const float* __restrict__ psf, const float* __restrict__ theta,
+                                                          const int* __restrict__ psf_index, const float* __restrict__ xy,
+                                                          int nu, int mode, float* __restrict__ out) {
+    const int i = blockIdx.x, f = psf_index[i];
+    const float* s = psf + (size_t)f * nu * nu;
+    const LcbAffine A = lcb_affine(theta + (size_t)f * 6, xy[2 * i], xy[2 * i + 1], mode);
+    float* o = out + (size_t)i * nu * nu;
+    for (int p = threadIdx.x; p < nu * nu; p += blockDim.x)
+        o[p] = A.det * lcb_bilin_value(lcb_bilin(s, nu, nu, A, p % nu, p / nu));
+}
+
+extern "C" int lcb_apply_distortion_batch(const float* psf, const float* theta, const int* psf_index, const float* xy, int B, int Fp,
+                                          int nu, int mode, float* out, int mem, void* stream) {
+    LCB_REQUIRE(psf && theta && psf_index && xy && out, "lcb_apply_distortion_batch: NULL argument");
+    LCB_REQUIRE(B >= 0 && Fp >= 1 && nu >= 2 && (mode == 1 || mode == 2), "lcb_apply_distortion_batch: bad sizes / mode");
+    if (B == 0) return LCB_OK;
+    if (lcb_device_count() == 0) { lcb_set_error("no CUDA device: liblcb has no CPU fallback"); return LCB_ERR_CUDA; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t pp = (size_t)nu * nu;
+    if (mem == LCB_MEM_DEVICE) {
+        { LcbProfScope ps("k_apply_distortion", st); k_apply_distortion<<<B, 256, 0, st>>>(psf, theta, psf_index, xy, nu, mode, out); }
+        LCB_CUDA(cudaGetLastError());
+        return LCB_OK;
+    }
+    LCB_REQUIRE(mem == LCB_MEM_HOST, "mem must be LCB_MEM_DEVICE or LCB_MEM_HOST");
+    LcbArenaLease lease;
+    LcbArena& ar = *lease.a;
+    int rc = ar.reserve((size_t)Fp * pp * 4 + (size_t)Fp * 24 + (size_t)B * 12 + (size_t)B * pp * 4 + 8 * 256);
+    if (rc) return rc;
+    ar.rewind();
+    float* dpsf = (float*)ar.take((size_t)Fp * pp * 4); float* dth = (float*)ar.take((size_t)Fp * 24);
+    int* didx = (int*)ar.take((size_t)B * 4); float* dxy = (float*)ar.take((size_t)B * 8); float* dout = (float*)ar.take((size_t)B * pp * 4);
+    if (!dpsf || !dth || !didx || !dxy || !dout) { lcb_set_error("arena overflow"); return LCB_ERR_NOMEM; }
+    LCB_CUDA(cudaMemcpyAsync(dpsf, psf, (size_t)Fp * pp * 4, cudaMemcpyHostToDevice, st));
+    LCB_CUDA(cudaMemcpyAsync(dth, theta, (size_t)Fp * 24, cudaMemcpyHostToDevice, st));
+    LCB_CUDA(cudaMemcpyAsync(didx, psf_index, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+    LCB_CUDA(cudaMemcpyAsync(dxy, xy, (size_t)B * 8, cudaMemcpyHostToDevice, st));
+    { LcbProfScope ps("k_apply_distortion", st); k_apply_distortion<<<B, 256, 0, st>>>(dpsf, dth, didx, dxy, nu, mode, dout); }
+    LCB_CUDA(cudaGetLastError());
+    LCB_CUDA(cudaMemcpyAsync(out, dout, (size_t)B * pp * 4, cudaMemcpyDeviceToHost, st));
     LCB_CUDA(cudaStreamSynchronize(st));
     return LCB_OK;
 }

@@ -5,6 +5,7 @@
 // (SURVEY.md B.1-B.3), global-norm clip and the AdaBelief update are fused in one kernel, with the
 // grid planes (s, b, grad, mu, nu, 2 starlet scratch) resident in shared memory.
 #include "lcb_psf.cuh"
+#include "lcb_distort.cuh"
 
 // ---------------------------------------------------------------- block reduction of NV scalars
 template <int NV, int NW = PSF_WARPS>
@@ -582,7 +583,8 @@ __global__ void __launch_bounds__(FIT_THREADS(K, NS), ((NS) > 0 ? 2 : 1)) k_psf_
     float* red = redS + A.Nmax * PSF_WARPS * 4;         // [2][32 warps][4]
     // FAST: every plane read by the passes carries HB zero rows before and after (no bounds predicates)
     constexpr int HB = FAST ? 8 : 0;
-    float* scr = red + 2 * 32 * 4;                      // start of the star-pass scratch
+    float* dth = red + 2 * 32 * 4;                      // [4][6] field distortion: theta, mu, nu, gradient (+ 8 spare)
+    float* scr = dth + 32;                              // start of the star-pass scratch
     float* Vg = scr + HB * ldv;                         // [HB + nu + HB][ldv]
     float* Vd = Vg + (nu + 2 * HB) * ldv;               // [HB + nu + HB][ldv]
     float* rT = Vd + (nu + HB) * ldv + HB * ldt;        // [HB + n + HB][ldt]
@@ -605,6 +607,10 @@ __global__ void __launch_bounds__(FIT_THREADS(K, NS), ((NS) > 0 ? 2 : 1)) k_psf_
     // stamps transposed ([X][Y], lanes <-> Y read coalesced) in the global workspace
     float* dT = A.work + (size_t)f * A.work_per_frame + (size_t)(J + 7) * pp;
     float* wT = dT + (size_t)A.Nmax * nn;
+    // field distortion (generic path only): the resampled PSF of the current star and d loss / d (that plane), in the workspace
+    float* Sd = wT + (size_t)A.Nmax * nn;
+    float* Gd = Sd + pp;
+    const bool distort = !FAST && A.distort != 0;
     if constexpr (FAST) {
         sg = reinterpret_cast<signed char*>(GR + pp);
         static_assert(!FAST || (2 * (NS * K + 16) * (NS + 1) + (NS + 16) * (NS + 1) + (NS + 16) * (NS * K + 1) >= 2 * NS * K * NS * K),
@@ -638,6 +644,7 @@ __global__ void __launch_bounds__(FIT_THREADS(K, NS), ((NS) > 0 ? 2 : 1)) k_psf_
         const int st = i / 12, c = i % 12;
         sp[i] = (c == 0) ? A.a[i0 + st] : (c == 1) ? A.x0[i0 + st] : (c == 2) ? A.y0[i0 + st] : 0.f;
     }
+    if (tid < 24) dth[tid] = (distort && tid < 6) ? A.distortion[(size_t)f * 6 + tid] : 0.f;
     __syncthreads();
 
     float b1t = 1.f, b2t = 1.f;
@@ -671,16 +678,29 @@ __global__ void __launch_bounds__(FIT_THREADS(K, NS), ((NS) > 0 ? 2 : 1)) k_psf_
         float chi = 0.f, cnt = 0.f;
         float reg = 0.f;
         const bool do_reg = (A.lam_scales != 0.f || A.lam_hf != 0.f);
+        float gth[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // per-thread partial of d chi2 / d theta (field distortion)
         for (int st = 0; st < N; ++st) {
             const float a = sp[st * 12], cx = fk * sp[st * 12 + 1], cy = fk * sp[st * 12 + 2];
             const int icx = (int)floorf(cx + 0.5f), icy = (int)floorf(cy + 0.5f);
             const float* tp = taps + st * 4 * LCB_GE_MAX;
             // halo variant (no bounds checks) whenever the tap windows stay within HB rows of the planes
             const bool hal = FAST && abs(icx) <= HB - G / 2 && abs(icy) <= HB - G / 2;
+            LcbAffine aff = {0.f, 0.f, 0.f, 1.f};
+            float sX = 0.f, sY = 0.f;
+            const float* Ssrc = S;
+            if constexpr (!FAST) {
+                if (distort) {                          // s_i = det * bilinear(s; c0 + A_i (p - c0))
+                    sX = A.stamp_xy[(size_t)(i0 + st) * 2]; sY = A.stamp_xy[(size_t)(i0 + st) * 2 + 1];
+                    aff = lcb_affine(dth, sX, sY, A.distort);
+                    for (int i = tid; i < pp; i += NT) Sd[i] = aff.det * lcb_bilin_value(lcb_bilin(S, nu, nu, aff, i % nu, i / nu));
+                    __syncthreads();
+                    Ssrc = Sd;
+                }
+            }
             // FAST (256 threads): task shapes chosen so that every pass is exactly one task per thread at n = 32, k = 2
             // (pass 1: 64 columns x 4 blocks of 8 rows; pass 2 / 2^T: 32 rows x 8 blocks of 4; pass 1^T: 64 x 4 blocks of 16)
             if (hal) lcb_pass1<K, G, FAST, (FAST ? 8 : 4)>(S, nu, nu, n, icy, tp, tp + LCB_GE_MAX, Vg, Vd, ldv, tid, NT);
-            else lcb_pass1<K, G, false>(S, nu, nu, n, icy, tp, tp + LCB_GE_MAX, Vg, Vd, ldv, tid, NT);
+            else lcb_pass1<K, G, false>(Ssrc, nu, nu, n, icy, tp, tp + LCB_GE_MAX, Vg, Vd, ldv, tid, NT);
             __syncthreads();
             PHASE(1)
             float ga = 0.f, gx = 0.f, gy = 0.f;
@@ -715,6 +735,37 @@ __global__ void __launch_bounds__(FIT_THREADS(K, NS), ((NS) > 0 ? 2 : 1)) k_psf_
             __syncthreads();
             PHASE(3)
             auto emit = [&](int v, int u, float val) { GR[v * nu + u] = fmaf(a, val, GR[v * nu + u]); };
+            if constexpr (!FAST) {
+                if (distort) {
+                    // d loss / d s_i into its own plane, then the transposed resampling: scatter onto the four source pixels of
+                    // every output pixel (float atomics: the order of the additions is not fixed) and the chain rule to theta
+                    auto emit_d = [&](int v, int u, float val) { Gd[v * nu + u] = a * val; };
+                    lcb_pass1T<K, G, false>(Vbar, ldb, nu, n, icy, tp, tid, NT, emit_d);
+                    __syncthreads();
+                    float t_ex = 0.f, t_ey = 0.f, t_sh = 0.f;
+                    for (int i = tid; i < pp; i += NT) {
+                        const float g = Gd[i];
+                        const LcbBilin bl = lcb_bilin(S, nu, nu, aff, i % nu, i / nu);
+                        const float gd = g * aff.det;
+                        const bool x0 = bl.i0 >= 0 && bl.i0 < nu, x1 = bl.i0 + 1 >= 0 && bl.i0 + 1 < nu;
+                        const bool y0 = bl.j0 >= 0 && bl.j0 < nu, y1 = bl.j0 + 1 >= 0 && bl.j0 + 1 < nu;
+                        if (x0 && y0) atomicAdd(GR + bl.j0 * nu + bl.i0, gd * (1.f - bl.fy) * (1.f - bl.fx));
+                        if (x1 && y0) atomicAdd(GR + bl.j0 * nu + bl.i0 + 1, gd * (1.f - bl.fy) * bl.fx);
+                        if (x0 && y1) atomicAdd(GR + (bl.j0 + 1) * nu + bl.i0, gd * bl.fy * (1.f - bl.fx));
+                        if (x1 && y1) atomicAdd(GR + (bl.j0 + 1) * nu + bl.i0 + 1, gd * bl.fy * bl.fx);
+                        const float dIx = (1.f - bl.fy) * (bl.s01 - bl.s00) + bl.fy * (bl.s11 - bl.s10);
+                        const float dIy = (1.f - bl.fx) * (bl.s10 - bl.s00) + bl.fx * (bl.s11 - bl.s01);
+                        const float gI = (A.distort == 1) ? g * lcb_bilin_value(bl) : 0.f;      // through det
+                        t_ex += gd * dIx * bl.rx + gI * (1.f + aff.ey);
+                        t_ey += gd * dIy * bl.ry + gI * (1.f + aff.ex);
+                        t_sh += gd * (dIx * bl.ry + dIy * bl.rx) - 2.f * aff.sh * gI;
+                    }
+                    gth[0] = fmaf(sX, t_ex, gth[0]); gth[1] = fmaf(sY, t_ex, gth[1]);
+                    gth[2] = fmaf(sX, t_ey, gth[2]); gth[3] = fmaf(sY, t_ey, gth[3]);
+                    gth[4] = fmaf(sX, t_sh, gth[4]); gth[5] = fmaf(sY, t_sh, gth[5]);
+                    continue;                           // the next star's resampling pass ends with a barrier before Gd / Vbar are reused
+                }
+            }
             if (hal) lcb_pass1T<K, G, FAST, (FAST ? 8 : 4)>(Vbar, ldb, nu, n, icy, tp, tid, NT, emit);
             else if (!FAST && !A.planes_in_smem) lcb_pass1T_rmw<K, G>(Vbar, ldb, nu, n, icy, tp, a, GR, tid, NT);   // gradient plane in L2
             else lcb_pass1T<K, G, false>(Vbar, ldb, nu, n, icy, tp, tid, NT, emit);
@@ -733,6 +784,16 @@ __global__ void __launch_bounds__(FIT_THREADS(K, NS), ((NS) > 0 ? 2 : 1)) k_psf_
             ga *= sc; gx *= sc * a * fk; gy *= sc * a * fk;
             sp[tid * 12 + 9] = ga; sp[tid * 12 + 10] = gx; sp[tid * 12 + 11] = gy;
             gn2 = ga * ga + gx * gx + gy * gy;
+        }
+        if constexpr (!FAST) {
+            if (distort && !last) {                     // d loss / d theta: block sum (the half of `red` the loss reduction does not use now)
+                block_reduce<6, NW>(gth, red + ((it + 1) & 1) * 32 * 4, tid);
+                if (tid < 6) dth[18 + tid] = sc * gth[tid];
+                if (tid == 0) {
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) gn2 = fmaf(sc * gth[q], sc * gth[q], gn2);
+                }
+            }
         }
         if (last) {
             float v2[2] = {chi, cnt};
@@ -809,6 +870,7 @@ __global__ void __launch_bounds__(FIT_THREADS(K, NS), ((NS) > 0 ? 2 : 1)) k_psf_
         if (it == 0) {
             if (tid == 0 && A.loss0) A.loss0[f] = L;
             if (A.grad_b0) for (int i = tid; i < pp; i += NT) A.grad_b0[(size_t)f * pp + i] = GR[i];
+            if (distort && A.grad_dist0 && tid < 6) A.grad_dist0[(size_t)f * 6 + tid] = dth[18 + tid];
             if (A.grad_s0 && tid < N) {
                 A.grad_s0[(i0 + tid) * 3] = sp[tid * 12 + 9];
                 A.grad_s0[(i0 + tid) * 3 + 1] = sp[tid * 12 + 10];
@@ -868,6 +930,10 @@ __global__ void __launch_bounds__(FIT_THREADS(K, NS), ((NS) > 0 ? 2 : 1)) k_psf_
                 S[i] = __ldg(sfix + i) + b;
             }
         }
+        if (distort && tid >= 32 && tid < 38) {         // warp 1: the six distortion coefficients
+            const int q = tid - 32;
+            belief_update(bc, cs * dth[18 + q], dth[q], dth[6 + q], dth[12 + q]);
+        }
         if (tid < N) {
             float* q = sp + tid * 12;
             belief_update(bc, cs * q[9], q[0], q[3], q[6]);
@@ -889,6 +955,7 @@ __global__ void __launch_bounds__(FIT_THREADS(K, NS), ((NS) > 0 ? 2 : 1)) k_psf_
     for (int i = tid; i < pp; i += NT) A.b[(size_t)f * pp + i] = Bp[i];
     if (tid < N) { A.a[i0 + tid] = sp[tid * 12]; A.x0[i0 + tid] = sp[tid * 12 + 1]; A.y0[i0 + tid] = sp[tid * 12 + 2]; }
     if (tid == 0 && A.status) A.status[f] = bad ? LCB_ITEM_NONFINITE : LCB_ITEM_OK;
+    if (distort && tid < 6) A.distortion[(size_t)f * 6 + tid] = dth[tid];
     if (A.narrow_psf || A.full_psf) {
         float tot[1] = {0.f};
         for (int i = tid; i < pp; i += NT) tot[0] += S[i];
@@ -934,7 +1001,7 @@ __global__ void __launch_bounds__(FIT_THREADS(K, NS), ((NS) > 0 ? 2 : 1)) k_psf_
 }
 
 size_t lcb_psf_fit_smem_small(int n, int nu, int Nmax) {
-    return (size_t)(Nmax * 4 * LCB_GE_MAX + Nmax * 12 + Nmax * PSF_WARPS * 4 + 2 * 32 * 4 +
+    return (size_t)(Nmax * 4 * LCB_GE_MAX + Nmax * 12 + Nmax * PSF_WARPS * 4 + 2 * 32 * 4 + 32 +
                     2 * nu * (n + 1) + n * (n + 1) + n * (nu + 1)) * 4;
 }
 

@@ -65,13 +65,16 @@ def _clone_f32(x, ref):
 def psf_fit_batch(data, weight, star_off, k, moffat0, a0, x00=None, y00=None, background0=None,
                   W=None, n_iter_analytic=100, n_iter_adabelief=3000, lr=1e-3,
                   lam_scales=1.0, lam_hf=1.0, noise_weights=False, bounds=None, mc_samples=100, mc_seed=1,
-                  want=('narrow_psf', 'full_psf', 'residuals', 'chi2', 'loss_hist', 'status')):
+                  want=('narrow_psf', 'full_psf', 'residuals', 'chi2', 'loss_hist', 'status'),
+                  field_distortion=0, stamp_xy=None, distortion0=None):
     """K1: ragged batch of per-frame PSF fits (lcb_psf_fit_batch).
 
     data, weight (sumN,n,n); star_off (F+1,) CSR offsets; moffat0 (F,5) = fwhm_x, fwhm_y, phi, beta, C
     guesses; a0 (sumN,).  ``want`` lists optional outputs (see lcb_psf_out in include/lcb.h).
     noise_weights: False (W from the caller, None == 1), True / 'SLIT' (diagonal propagation), 'MC' (mc_samples draws).
-    Returns a dict with moffat, a, x0, y0, background and the requested outputs.
+    field_distortion: 0 off, 1 flux-conserving / 2 plain affine resampling of the narrow PSF per star (include/lcb.h);
+    stamp_xy (sumN,2) rescaled frame coordinates of the stamps, distortion0 (F,6) initial coefficients (default 0).
+    Returns a dict with moffat, a, x0, y0, background (+ distortion) and the requested outputs.
     """
     _lib.require_device()
     data, weight = as_f32(data), as_f32(weight)
@@ -90,20 +93,43 @@ def psf_fit_batch(data, weight, star_off, k, moffat0, a0, x00=None, y00=None, ba
                background=_clone_f32(np.zeros((F, nu, nu)) if background0 is None else background0, data))
     if tuple(out['moffat'].shape) != (F, 5) or tuple(out['a'].shape) != (sumN,):
         raise ValueError("moffat0 must be (F,5) and a0 (sumN,)")
+    xy = None
+    if field_distortion:
+        if stamp_xy is None:
+            raise ValueError("field_distortion needs stamp_xy (sumN,2)")
+        xy = _clone_f32(stamp_xy, data)
+        if tuple(xy.shape) != (sumN, 2):
+            raise ValueError(f"stamp_xy must be ({sumN},2); got {tuple(xy.shape)}")
+        out['distortion'] = _clone_f32(np.zeros((F, 6)) if distortion0 is None else distortion0, data)
     shapes = dict(narrow_psf=(F, nu, nu), full_psf=(F, nu, nu), residuals=(sumN, n, n), chi2=(F,),
                   loss_hist=(F, n_iter_adabelief), loss_hist_analytic=(F, n_iter_analytic),
-                  W_out=(F, J, nu, nu), loss0=(F,), grad_b0=(F, nu, nu), grad_s0=(sumN, 3), status=(F,))
+                  W_out=(F, J, nu, nu), loss0=(F,), grad_b0=(F, nu, nu), grad_s0=(sumN, 3), status=(F,), grad_dist0=(F, 6))
     for nm in want:
         out[nm] = empty_like_kind(data, shapes[nm], 'i' if nm == 'status' else 'f')
     b = bounds or {}
     opts = _lib.PsfOpts(int(n_iter_analytic), int(n_iter_adabelief), float(lr), float(lam_scales), float(lam_hf),
                         (2 if noise_weights == 'MC' else int(bool(noise_weights))), float(b.get('fwhm_min', 1.0)),
                         float(b.get('fwhm_max', n / 2.0)), float(b.get('beta_min', 1.1)), float(b.get('beta_max', 12.0)),
-                        int(mc_samples), int(mc_seed) & 0xffffffff)
-    bi = _lib.PsfBatch(F, ptr(star_off), n, k, ptr(data), ptr(weight), ptr(W))
+                        int(mc_samples), int(mc_seed) & 0xffffffff, int(field_distortion))
+    bi = _lib.PsfBatch(F, ptr(star_off), n, k, ptr(data), ptr(weight), ptr(W), ptr(xy))
     bo = _lib.PsfOut(*[ptr(out.get(nm)) for nm in _lib.PSF_OUT_FIELDS])
     rc = _lib.lib.lcb_psf_fit_batch(C.byref(bi), C.byref(opts), C.byref(bo), mem, current_stream(data))
     _lib.check(rc, 'lcb_psf_fit_batch')
+    return out
+
+
+def apply_distortion_batch(psfs, theta, psf_index, xy, mode=1):
+    """lcb_apply_distortion_batch: psfs (Fp,nu,nu), theta (Fp,6), psf_index (B,), xy (B,2) -> (B,nu,nu) distorted PSFs."""
+    _lib.require_device()
+    psfs, theta, xy = as_f32(psfs), as_f32(theta), as_f32(xy)
+    psf_index = as_i32(psf_index)
+    mem = mem_kind(psfs, theta, psf_index, xy)
+    B, Fp, nu = int(psf_index.shape[0]), int(psfs.shape[0]), int(psfs.shape[-1])
+    if tuple(theta.shape) != (Fp, 6) or tuple(xy.shape) != (B, 2):
+        raise ValueError("theta must be (Fp,6) and xy (B,2)")
+    out = empty_like_kind(psfs, (B, nu, nu), 'f')
+    _lib.check(_lib.lib.lcb_apply_distortion_batch(ptr(psfs), ptr(theta), ptr(psf_index), ptr(xy), B, Fp, nu, int(mode), ptr(out), mem,
+                                                   current_stream(psfs)), 'lcb_apply_distortion_batch')
     return out
 
 

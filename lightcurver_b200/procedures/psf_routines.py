@@ -28,6 +28,10 @@ def build_psf_batch(images, noisemaps, subsampling_factor, masks=None, n_iter_an
     blocks balanced by their star counts, one host thread per GPU, no collective (frames are independent).
     star_counts: when given, ``images`` / ``noisemaps`` / ``masks`` are already CONCATENATED arrays (sumN, n, n) -- e.g. views
     of the page-locked staging buffer of ``stamp_store`` -- and star_counts[f] is the number of stars of frame f.
+    field_distortion (psf_modelling.py:169-170): every star sees the affine resampling of the frame's narrow PSF given by
+    ``kwargs_distortion`` = {dilation_x, dilation_y, shear} (each a first-order polynomial, 2 coefficients, in the rescaled frame
+    position) at ``stamp_coordinates`` -- a sequence (length F) of (N_f, 2) arrays from ``rescale_image_coordinates``
+    (utilities/image_coordinates.py:4-25), or one (sumN, 2) array with ``star_counts``; stage 2 fits the six coefficients.
     Returns a list of per-frame result dicts shaped like STARRED's (``return_dicts``), or the raw
     batched arrays.
     """
@@ -37,6 +41,7 @@ def build_psf_batch(images, noisemaps, subsampling_factor, masks=None, n_iter_an
         offs = np.concatenate([[0], np.cumsum(np.asarray(star_counts, np.int64))])
         split = lambda a: None if a is None else [a[offs[f]:offs[f + 1]] for f in range(n_frames)]
         images, noisemaps, masks, star_counts = split(images), split(noisemaps), split(masks), None
+        stamp_coordinates = split(None if stamp_coordinates is None else np.asarray(stamp_coordinates))
     if len(devs) > 1 and n_frames > 1:
         counts = [int(np.shape(im)[0]) for im in images]
         blocks = engine.split_by_work(counts, len(devs))
@@ -49,7 +54,8 @@ def build_psf_batch(images, noisemaps, subsampling_factor, masks=None, n_iter_an
 
         def one(lo, hi):
             return build_psf_batch(images[lo:hi], noisemaps[lo:hi], subsampling_factor, None if masks is None else masks[lo:hi],
-                                   guess_fwhm_pixels=fw[lo:hi], **kw)
+                                   guess_fwhm_pixels=fw[lo:hi],
+                                   stamp_coordinates=None if stamp_coordinates is None else stamp_coordinates[lo:hi], **kw)
         parts = engine.fan_out(blocks, devs, one)
         if return_dicts:
             return [r for part in parts for r in part]
@@ -58,9 +64,8 @@ def build_psf_batch(images, noisemaps, subsampling_factor, masks=None, n_iter_an
         off[1:] = np.cumsum(counts)
         out['star_off'] = off
         return out
-    if field_distortion:
-        raise NotImplementedError("field_distortion=True is a 'next' row (SURVEY.md section 8f rank 3); "
-                                  "run with field_distortion: false")
+    if field_distortion and stamp_coordinates is None:
+        raise ValueError("field_distortion=True needs stamp_coordinates (psf_modelling.py:122-124, 170)")
     cv = conventions
     from ..conventions import apply_to_library
     apply_to_library(cv)                       # the kernels read the library-wide conventions at call time
@@ -89,12 +94,19 @@ def build_psf_batch(images, noisemaps, subsampling_factor, masks=None, n_iter_an
     moffat0 = np.stack([fwhm, fwhm, np.zeros(F), np.full(F, cv.moffat_beta_init), np.ones(F)], -1)
     lam_s = cv.psf_lambda_scales if regularization_strength_scales is None else regularization_strength_scales
     lam_h = cv.psf_lambda_hf if regularization_strength_hf is None else regularization_strength_hf
+    dist = {}
+    if field_distortion:
+        xy = np.asarray(stamp_coordinates, np.float32) if isinstance(stamp_coordinates, np.ndarray) else \
+            np.concatenate([np.asarray(c, np.float32).reshape(-1, 2) for c in stamp_coordinates])
+        if xy.shape != (sumN, 2):
+            raise ValueError(f"stamp_coordinates must hold one (x, y) pair per star: expected ({sumN}, 2), got {xy.shape}")
+        dist = dict(field_distortion=cv.distortion_mode(), stamp_xy=xy)
     out = engine.psf_fit_batch(
         data, weight, prep['star_off'], k, moffat0, a0, x00, y00, n_iter_analytic=n_iter_analytic,
         n_iter_adabelief=n_iter_adabelief, lr=cv.psf_stage2_lr if adabelief_learning_rate is None else adabelief_learning_rate,
         lam_scales=lam_s, lam_hf=lam_h, noise_weights=noise_propagation, mc_samples=noise_samples, mc_seed=noise_seed,
         bounds=dict(fwhm_min=cv.moffat_fwhm_min, fwhm_max=n / 2.0, beta_min=cv.moffat_beta_min, beta_max=cv.moffat_beta_max),
-        want=('narrow_psf', 'full_psf', 'residuals', 'chi2', 'loss_hist', 'loss_hist_analytic', 'status'))
+        want=('narrow_psf', 'full_psf', 'residuals', 'chi2', 'loss_hist', 'loss_hist_analytic', 'status'), **dist)
     out = {kk: v.cpu().numpy() for kk, v in out.items()}            # one device -> host copy per product
     norms = prep['norm'].cpu().numpy().astype(np.float64)
     out['norms'] = norms
@@ -116,7 +128,9 @@ def build_psf_batch(images, noisemaps, subsampling_factor, masks=None, n_iter_an
                                   'beta': np.array([mo[3]]), 'C': np.array([mo[4]])},
                 'kwargs_gaussian': {'a': out['a'][sl], 'x0': out['x0'][sl], 'y0': out['y0'][sl]},
                 'kwargs_background': {'background': out['background'][f].reshape(nu * nu)},
-                'kwargs_distortion': {},
+                # empty without field distortion (psf_modelling.py:200-202 iterates over the items)
+                'kwargs_distortion': ({'dilation_x': out['distortion'][f, 0:2].copy(), 'dilation_y': out['distortion'][f, 2:4].copy(),
+                                       'shear': out['distortion'][f, 4:6].copy()} if field_distortion else {}),
             },
             'adabelief_extra_fields': {'loss_history': out['loss_hist'][f]},
             'analytical_extra_fields': {'loss_history': out['loss_hist_analytic'][f]},

@@ -194,6 +194,10 @@ def model_all_psfs_batched(store, db, frames, stars_for_frame, user_config, comb
     if not pending:
         return []
     sel = np.concatenate(sel)
+    field_distortion = bool(user_config.get('field_distortion', False))
+    positions = None
+    if field_distortion:                      # psf_modelling.py:121-124: rescaled frame positions of the stamps
+        positions = stamp_store.gather_positions(store, [c[0] for c in cand], [[s['gaia_id'] for s in c[1]] for c in cand])[sel]
     if len(sel) != len(keep):                 # some stars dropped: compact (one copy); otherwise the staging views go straight up
         datas, noisemaps, masks = datas[sel], noisemaps[sel], masks[sel]
     results = build_psf_batch(datas, noisemaps, k, masks=masks, star_counts=counts,
@@ -201,7 +205,7 @@ def model_all_psfs_batched(store, db, frames, stars_for_frame, user_config, comb
                               n_iter_adabelief=user_config['psf_n_iter_pixels'],
                               guess_method_star_position='center',
                               guess_fwhm_pixels=np.array([float(p['frame']['seeing_pixels']) for p in pending]),
-                              field_distortion=user_config.get('field_distortion', False),
+                              field_distortion=field_distortion, stamp_coordinates=positions,
                               devices=devices)          # None: current GPU; 'all': every visible GPU, one host thread each
     written, rows = [], []
     pos = 0

@@ -438,10 +438,26 @@ def lbfgsb_translations_and_fluxes(jd, maxiter, a_lower=0.0):
     return np.asarray(hist), res
 
 
+def lbfgs_translations_and_fluxes_device(jd, maxiter, a_lower=0.0, ftol=2.220446049250313e-09, pgtol=1e-5):
+    """Stage 1 of do_modelling_of_roi (roi_modelling.py:260-281) with the optimiser on the device (``lcb_deconv_lbfgs``):
+    projected L-BFGS over {dx, dy, a}, scipy's default stopping rules (ftol = 1e7 eps, pgtol = 1e-5), no host round trip per
+    evaluation.  Single-rank handles.  Returns (loss history per iteration, info dict)."""
+    jd.set_params(free_h=False, free_mean=False, free_a=True, free_c=False, free_d=True)
+    hist = np.zeros(int(maxiter), np.float32)
+    info = np.zeros(5, np.float32)
+    _lib.check(_lib.lib.lcb_deconv_lbfgs(jd.handle, int(maxiter), float(a_lower), float(ftol), float(pgtol), ptr(hist), ptr(info),
+                                         _lib.MEM_HOST), 'lcb_deconv_lbfgs')
+    reasons = {0: 'evaluation budget exhausted', 1: 'relative reduction of the loss <= ftol', 2: 'projected gradient <= pgtol',
+               3: 'iteration limit reached', 4: 'line search could not improve the loss'}
+    nit = int(info[0])
+    return hist[:nit].astype(np.float64), dict(nit=nit, nfev=int(info[1]), message=reasons.get(int(info[2]), '?'), fun=float(info[3]),
+                                               projected_gradient=float(info[4]))
+
+
 def model_roi_arrays(data, noisemap, psf, subsampling_factor, xs, ys, initial_a, angles_to_north=None,
                      fix_point_source_astrometry=False, starting_background=None, further_optimize_background=True,
                      roi_model_regularization=None, roi_deconv_translations_iters=300, roi_deconv_all_iters=2000,
-                     conventions: Conventions = DEFAULT, group=None, comm='p2p'):
+                     conventions: Conventions = DEFAULT, group=None, comm='p2p', stage1='device'):
     """The two optimisation stages of do_modelling_of_roi (roi_modelling.py:213-335) on arrays that are already
     loaded and scaled (:154-170): data, noisemap (E,n,n); psf (E,P,P); xs, ys the point-source guesses in data
     pixels from the stamp centre (:207-210); initial_a (E*M,) (:211-212).
@@ -453,6 +469,8 @@ def model_roi_arrays(data, noisemap, psf, subsampling_factor, xs, ys, initial_a,
     reference's defaults (scales 1, hf 1, positivity 100, pts_source 0.01, flux scatter 10.0; :305-312).
     ``fix_point_source_astrometry``: True fixes c, a float is the sigma (data pixels) of a Gaussian prior around the
     initial positions (:225-244).  One device handle serves both stages (the stamps are uploaded once).
+    ``stage1``: 'device' (default: L-BFGS with its state on the GPU, ``lcb_deconv_lbfgs``) or 'scipy' (the reference's own
+    structure: host L-BFGS-B over device loss / gradient; always used when the epochs are sharded over ranks).
     """
     reg = roi_model_regularization or {}
     cv = conventions
@@ -480,7 +498,13 @@ def model_roi_arrays(data, noisemap, psf, subsampling_factor, xs, ys, initial_a,
                   free_h=False, free_mean=False, free_a=True, free_c=False, free_d=True)
     # stage 1: translations and fluxes
     jd.set_reg(0.0, 0.0, 0.0, W=None, prior=prior, lam_fu=reg.get('regularization_scatter_fluxes_pre_optim', 10.0), conventions=cv)
-    hist1, res1 = lbfgsb_translations_and_fluxes(jd, roi_deconv_translations_iters)
+    if stage1 not in ('device', 'scipy'):
+        raise ValueError("stage1 must be 'device' or 'scipy'")
+    if stage1 == 'device' and jd.world == 1:
+        hist1, info1 = lbfgs_translations_and_fluxes_device(jd, roi_deconv_translations_iters)
+    else:
+        hist1, res1 = lbfgsb_translations_and_fluxes(jd, roi_deconv_translations_iters)
+        info1 = dict(nit=int(res1.nit), nfev=int(res1.nfev), message=str(res1.message), fun=float(res1.fun))
     kwargs_partial1 = _kwargs_of(jd.get(want_model=False))
     # stage 2: everything
     free_h = bool(further_optimize_background)
@@ -495,7 +519,7 @@ def model_roi_arrays(data, noisemap, psf, subsampling_factor, xs, ys, initial_a,
     hist = jd.run(int(roi_deconv_all_iters), lr=1e-4, schedule=False)
     out = _finish(jd, hist, Wused, d32, weight, psf, cv)
     jd.close()
-    out['stage1'] = dict(kwargs_final=kwargs_partial1, loss_history=hist1, nit=int(res1.nit), message=str(res1.message))
+    out['stage1'] = dict(kwargs_final=kwargs_partial1, loss_history=hist1, **info1)
     return out
 
 

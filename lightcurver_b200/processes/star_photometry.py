@@ -278,8 +278,15 @@ def do_star_photometry_batched(store, db, stars, frames_for_star, psf_ref_for_fr
     results = {}
     if not work:
         return results
-    d32, n32, cosmic, psfs, psf_index, off = stamp_store.gather_photometry_batch(
-        store, [(wk['star']['gaia_id'], wk['frames']) for wk in work], psf_ref_for_frame, stager)
+    star_frames = [(wk['star']['gaia_id'], wk['frames']) for wk in work]
+    if user_config.get('field_distortion', False):
+        # star_photometry.py:291-304: every (star, frame) item sees the frame's narrow PSF resampled at the star's frame position
+        d32, n32, cosmic, psfs, psf_index, off, thetas, xy = stamp_store.gather_photometry_batch(
+            store, star_frames, psf_ref_for_frame, stager, with_distortion=True)
+        psfs = engine.apply_distortion_batch(psfs, thetas, psf_index, xy, mode=cv.distortion_mode())   # one launch for the batch
+        psf_index = np.arange(len(psf_index), dtype=np.int32)
+    else:
+        d32, n32, cosmic, psfs, psf_index, off = stamp_store.gather_photometry_batch(store, star_frames, psf_ref_for_frame, stager)
     # star_photometry.py:309-316 on the whole batch: doubly-NaN pixels -> (0, 1e7); the noise map of every epoch that has ANY
     # masked pixel is multiplied by 1000 (`noisemap[np.where(~mask)[0]] *= 1000.`, once per epoch)
     data, noisemap = d32.astype(np.float64), n32.astype(np.float64)

@@ -102,18 +102,52 @@ def gather_psf_batch(store, frames, ids_per_frame, stager=None):
     return st.data[:total], st.noise[:total], st.cosmic[:total], off
 
 
-def gather_photometry_batch(store, star_frames, psf_ref_for_frame, stager=None):
+def rescale_image_coordinates(xy_coordinates_array, image_shape):
+    """utilities/image_coordinates.py:4-25: pixel coordinates (x, y) with the origin at the bottom left of the frame -> origin at
+    the frame centre, divided by the frame dimensions (values in [-1/2, 1/2]); image_shape is (rows, columns)."""
+    dims = np.asarray(image_shape, dtype=np.float64).reshape(-1)[::-1]        # (x extent, y extent)
+    return (np.asarray(xy_coordinates_array, dtype=np.float64) - (dims - 1) / 2.) / dims
+
+
+def gather_positions(store, frames, ids_per_frame):
+    """Rescaled frame positions of the stamps (psf_modelling.py:121-124: ``image_pixel_coordinates/<id>`` and ``frame_shape`` of
+    every frame), one (x, y) pair per star in the order of ``gather_psf_batch``.  Returns (sumN, 2) float32."""
+    out = []
+    for frame, ids in zip(frames, ids_per_frame):
+        if not ids:
+            continue
+        frame_group = store[frame['image_relpath']]
+        pg = frame_group['image_pixel_coordinates']
+        shape = np.asarray(frame_group['frame_shape'][...])
+        pos = np.array([np.asarray(pg[gid][...], dtype=np.float64).reshape(2) for gid in ids])
+        out.append(rescale_image_coordinates(pos, shape))
+    return np.concatenate(out).astype(np.float32) if out else np.zeros((0, 2), np.float32)
+
+
+def read_distortion(psf_group):
+    """star_photometry.py:293-297: the ``distortion`` group of a stored PSF -> (6,) coefficients (dilation_x, dilation_y, shear),
+    zeros when the group is empty (the PSF was built without field distortion)."""
+    dg = psf_group['distortion']
+    keys = set(dg.keys())
+    if not {'dilation_x', 'dilation_y', 'shear'} <= keys:
+        return np.zeros(6, np.float32)
+    return np.concatenate([np.asarray(dg[key][...], dtype=np.float32).reshape(2) for key in ('dilation_x', 'dilation_y', 'shear')])
+
+
+def gather_photometry_batch(store, star_frames, psf_ref_for_frame, stager=None, with_distortion=False):
     """``star_frames``: list (one entry per star) of (gaia_id, [frame mappings]).  Frames are walked in the OUTER loop so that
     the groups of a frame are resolved once and its narrow PSF is read once, whatever the number of stars measured in it.
     Returns (data, noisemap, cosmics, psf_stack (n_psf, nu, nu), psf_index (B,), star_off (S + 1,)) with the items of a star
-    contiguous and in the order of its frame list (star_photometry.py:272-306)."""
+    contiguous and in the order of its frame list (star_photometry.py:272-306).  with_distortion (:293-304): two more values,
+    the distortion coefficients of every PSF (n_psf, 6) and the rescaled frame position of every item (B, 2)."""
     counts = [len(fr) for _, fr in star_frames]
     off = np.zeros(len(star_frames) + 1, np.int64)
     off[1:] = np.cumsum(counts)
     total = int(off[-1])
     if total == 0:
         z = np.zeros((0, 0, 0), np.float32)
-        return z, z, z.astype(bool), z, np.zeros(0, np.int32), off
+        empty = (z, z, z.astype(bool), z, np.zeros(0, np.int32), off)
+        return empty + (np.zeros((0, 6), np.float32), np.zeros((0, 2), np.float32)) if with_distortion else empty
     by_frame = {}                                  # image_relpath -> (frame, [(item index, gaia_id)])
     for s, (gid, frs) in enumerate(star_frames):
         for j, fr in enumerate(frs):
@@ -123,6 +157,7 @@ def gather_photometry_batch(store, star_frames, psf_ref_for_frame, stager=None):
     st = (stager or StampStager()).ensure(total, n)
     psf_index = np.empty(total, np.int32)
     psfs, psf_slot = [], {}
+    thetas, xy = [], np.zeros((total, 2), np.float32)
     for rel, (fr, items) in by_frame.items():
         frame_group = store[rel]
         dg, ng, mg = frame_group['data'], frame_group['noisemap'], frame_group['cosmicsmask']
@@ -131,12 +166,19 @@ def gather_photometry_batch(store, star_frames, psf_ref_for_frame, stager=None):
         if key not in psf_slot:
             psf_slot[key] = len(psfs)
             psfs.append(np.asarray(frame_group[ref]['narrow_psf'][...], dtype=np.float32))
+            if with_distortion:
+                thetas.append(read_distortion(frame_group[ref]))
+        if with_distortion:
+            pg, shape = frame_group['image_pixel_coordinates'], np.asarray(frame_group['frame_shape'][...])
+            for idx, gid in items:
+                xy[idx] = rescale_image_coordinates(np.asarray(pg[gid][...], dtype=np.float64).reshape(2), shape)
         for idx, gid in items:
             read_into(dg[gid], st.data[idx])
             read_into(ng[gid], st.noise[idx])
             st.cosmic[idx] = np.asarray(mg[gid][...], dtype=bool)
             psf_index[idx] = psf_slot[key]
-    return st.data[:total], st.noise[:total], st.cosmic[:total], np.stack(psfs), psf_index, off
+    res = (st.data[:total], st.noise[:total], st.cosmic[:total], np.stack(psfs), psf_index, off)
+    return res + (np.stack(thetas), xy) if with_distortion else res
 
 
 def write_psf_products(store, frame, psf_ref, narrow_psf, full_psf, subsampling_factor, kwargs_distortion):

@@ -330,12 +330,26 @@ class PSF:
         raise NotImplementedError("use lightcurver_b200.procedures.psf_routines.build_psf")
 
 
-def apply_distortion(narrow_psf, kwargs_distortion, star_xy_coordinates):
-    """starred.psf.psf.apply_distortion (star_photometry.py:303, roi_file_preparation.py:179): field distortion is a 'next'
-    row; with an empty kwargs_distortion (what build_psf returns here) the PSF is returned unchanged."""
-    if kwargs_distortion:
-        raise NotImplementedError("field_distortion")
-    return narrow_psf
+def distortion_theta(kwargs_distortion):
+    """kwargs_distortion {dilation_x, dilation_y, shear} (2 coefficients each) -> the (6,) vector of the C ABI; {} -> None."""
+    if not kwargs_distortion:
+        return None
+    return np.concatenate([np.asarray(kwargs_distortion[key], np.float32).reshape(2) for key in ('dilation_x', 'dilation_y', 'shear')])
+
+
+def apply_distortion(narrow_psf, kwargs_distortion, star_xy_coordinates, conventions: Conventions = STARRED_CONVENTIONS):
+    """starred.psf.psf.apply_distortion (star_photometry.py:303, roi_file_preparation.py:179): the narrow PSF seen at the rescaled
+    frame position ``star_xy_coordinates`` (utilities/image_coordinates.py:4-25) under ``kwargs_distortion`` (the dict build_psf
+    returned and psf_modelling.py:200-202 stored).  Runs on the device (lcb_apply_distortion_batch); an empty kwargs_distortion
+    (field_distortion was off) returns the PSF unchanged."""
+    theta = distortion_theta(kwargs_distortion)
+    if theta is None:
+        return narrow_psf
+    from . import engine
+    psf = np.ascontiguousarray(narrow_psf, np.float32)
+    out = engine.apply_distortion_batch(psf[None], theta[None], np.zeros(1, np.int32),
+                                        np.asarray(star_xy_coordinates, np.float32).reshape(1, 2), mode=conventions.distortion_mode())
+    return out[0]
 
 
 def install():

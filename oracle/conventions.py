@@ -44,9 +44,17 @@ class Conventions:
     pts_source_all_epochs: bool = True
     # regularization_strength_flux_uniformity: sum_m std_e(a_em) / |mean_e(a_em)| (True) or sum_m std_e(a_em) (False)
     flux_uniformity_relative: bool = True
+    # field distortion (PSF(field_distortion=True), apply_distortion): dilation_x, dilation_y, shear are first-order polynomials
+    # (no constant term) in the rescaled frame position; the resampled PSF is multiplied by |det A| (True) so that its integral is
+    # kept, or left as sampled (False)
+    distortion_conserve_flux: bool = True
 
     def as_dict(self):
         return asdict(self)
+
+    def distortion_mode(self):
+        """lcb_psf_opts.field_distortion / lcb_apply_distortion_batch mode."""
+        return 1 if self.distortion_conserve_flux else 2
 
     def amplitude_per_flux(self, k):
         """Amplitude of a point source per unit of pixel-sum flux: 1 with the block sum, k^2 with the block mean."""

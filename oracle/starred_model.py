@@ -81,14 +81,55 @@ def moffat_image(fwhm_x, fwhm_y, phi, beta, n, k, dtype=torch.float64):
     return m / m.sum((-1, -2), keepdim=True)
 
 
-def psf_star_models(s, a, x0, y0, n, k, cv: Conventions = DEFAULT):
-    """m_i = a_i D_k[ s (*) g(. ; k x0_i, k y0_i) ]   (A.1).
+def distortion_terms(theta, xy):
+    """kwargs_distortion at the stamps' frame positions [R]: theta (..., 6) = dilation_x (2), dilation_y (2), shear (2), each a
+    first-order polynomial without constant term in the rescaled position xy (..., N, 2) of utilities/image_coordinates.py:4-25
+    (psf_modelling.py:122-124).  Returns ex, ey, sh (..., N)."""
+    X, Y = xy[..., 0], xy[..., 1]
+    th = theta[..., None, :]
+    return th[..., 0] * X + th[..., 1] * Y, th[..., 2] * X + th[..., 3] * Y, th[..., 4] * X + th[..., 5] * Y
+
+
+def distort_psf(s, theta, xy, cv: Conventions = DEFAULT):
+    """apply_distortion (star_photometry.py:303, roi_file_preparation.py:179) [R]: the narrow PSF s (..., nu, nu) seen at the
+    positions xy (..., N, 2): s_i[v][u] = det_i * bilinear(s; c0 + A_i (u - c0, v - c0)), A_i = [[1+ex, sh], [sh, 1+ey]],
+    c0 = (nu-1)/2, zeros outside the grid, det_i = |A_i| (``distortion_conserve_flux``) or 1.  Returns (..., N, nu, nu)."""
+    nu = s.shape[-1]
+    dt = s.dtype
+    ex, ey, sh = distortion_terms(theta, xy)
+    c0 = 0.5 * (nu - 1)
+    r = torch.arange(nu, dtype=dt) - c0
+    ry, rx = r[:, None], r[None, :]
+    e = lambda t: t[..., None, None]
+    qx = c0 + (1.0 + e(ex)) * rx + e(sh) * ry
+    qy = c0 + e(sh) * rx + (1.0 + e(ey)) * ry
+    i0, j0 = torch.floor(qx.detach()), torch.floor(qy.detach())
+    fx, fy = qx - i0, qy - j0
+    sp = torch.nn.functional.pad(s, (1, 1, 1, 1))                        # one ring of zeros; far-away cells are clamped onto it
+    N = xy.shape[-2]
+    spf = sp.reshape(*sp.shape[:-2], 1, -1).expand(*sp.shape[:-2], N, -1)
+
+    def tap(jj, ii):
+        jc = (jj + 1).clamp(0, nu + 1).long()
+        ic = (ii + 1).clamp(0, nu + 1).long()
+        inside = ((jj >= -1) & (jj <= nu) & (ii >= -1) & (ii <= nu)).to(dt)
+        idx = (jc * (nu + 2) + ic).reshape(*jc.shape[:-2], -1)
+        return torch.gather(spf, -1, idx).reshape(jc.shape) * inside
+    val = (1 - fy) * ((1 - fx) * tap(j0, i0) + fx * tap(j0, i0 + 1)) + fy * ((1 - fx) * tap(j0 + 1, i0) + fx * tap(j0 + 1, i0 + 1))
+    if cv.distortion_conserve_flux:
+        val = val * e((1.0 + ex) * (1.0 + ey) - sh * sh)
+    return val
+
+
+def psf_star_models(s, a, x0, y0, n, k, cv: Conventions = DEFAULT, theta=None, xy=None):
+    """m_i = a_i D_k[ s_i (*) g(. ; k x0_i, k y0_i) ]   (A.1); s_i = s, or ``distort_psf(s, theta, xy)[i]`` with field distortion.
 
     s (..., nu, nu); a, x0, y0 (..., N)  ->  (..., N, n, n)
     """
     Ay = shift_matrix(k * y0, n, k, cv)               # (..., N, n, nu)
     Ax = shift_matrix(k * x0, n, k, cv)
-    core = Ay @ s[..., None, :, :] @ Ax.transpose(-1, -2)
+    si = s[..., None, :, :] if theta is None else distort_psf(s, theta, xy, cv)
+    core = Ay @ si @ Ax.transpose(-1, -2)
     return a[..., None, None] * core
 
 
@@ -209,12 +250,13 @@ def psf_noise_weights_mc_limit(weight, a, x0, y0, n, k, cv: Conventions = DEFAUL
 # ----------------------------------------------------------------------------------------------
 
 def psf_loss(s_fixed, b, a, x0, y0, data, weight, W, n, k, lam_scales, lam_hf,
-             cv: Conventions = DEFAULT):
-    """Per-frame loss.  s_fixed, b (..., nu, nu); a,x0,y0 (..., N); data, weight (..., N, n, n).
+             cv: Conventions = DEFAULT, theta=None, xy=None):
+    """Per-frame loss.  s_fixed, b (..., nu, nu); a,x0,y0 (..., N); data, weight (..., N, n, n); with field distortion
+    theta (..., 6) and the stamps' rescaled frame positions xy (..., N, 2).
 
     weight = mask / sigma^2.  Returns (...,).
     """
-    m = psf_star_models(s_fixed + b, a, x0, y0, n, k, cv)
+    m = psf_star_models(s_fixed + b, a, x0, y0, n, k, cv, theta, xy)
     chi = (weight * (m - data) ** 2).sum((-1, -2, -3))
     if cv.chi2_half:
         chi = 0.5 * chi
@@ -527,18 +569,22 @@ def phot_loss_grad(psf, data, weight, a, dx, dy, n, k, cv: Conventions = DEFAULT
 
 
 def psf_loss_grad(s_fixed, b, a, x0, y0, data, weight, W, n, k, lam_scales, lam_hf,
-                  cv: Conventions = DEFAULT, dtype=torch.float64):
-    """Loss and gradient wrt (b, a, x0, y0) for ONE frame or a batch with uniform N."""
+                  cv: Conventions = DEFAULT, dtype=torch.float64, theta=None, xy=None):
+    """Loss and gradient wrt (b, a, x0, y0 [, theta]) for ONE frame or a batch with uniform N."""
     s_fixed, data, weight = _const(s_fixed, dtype), _const(data, dtype), _const(weight, dtype)
     W = None if W is None else _const(W, dtype)
     b, a, x0, y0 = _leaf(b, dtype), _leaf(a, dtype), _leaf(x0, dtype), _leaf(y0, dtype)
-    L = psf_loss(s_fixed, b, a, x0, y0, data, weight, W, n, k, lam_scales, lam_hf, cv)
-    g = torch.autograd.grad(L.sum(), [b, a, x0, y0])
+    leaves = [b, a, x0, y0]
+    if theta is not None:
+        theta, xy = _leaf(theta, dtype), _const(xy, dtype)
+        leaves.append(theta)
+    L = psf_loss(s_fixed, b, a, x0, y0, data, weight, W, n, k, lam_scales, lam_hf, cv, theta, xy)
+    g = torch.autograd.grad(L.sum(), leaves)
     return L.detach().numpy(), [t.numpy() for t in g]
 
 
 def fit_psf_stage2(s_fixed, b0, a0, x00, y00, data, weight, W, n, k, n_iter, lr=None,
-                   lam_scales=None, lam_hf=None, cv: Conventions = DEFAULT, dtype=torch.float32):
+                   lam_scales=None, lam_hf=None, cv: Conventions = DEFAULT, dtype=torch.float32, theta0=None, xy=None):
     """AdaBelief on {background grid, a, x0, y0}, Moffat fixed (A.4 stage 2).  Leading batch dim
     (frames, uniform N) optional; clip is per frame."""
     lr = cv.psf_stage2_lr if lr is None else lr
@@ -548,15 +594,23 @@ def fit_psf_stage2(s_fixed, b0, a0, x00, y00, data, weight, W, n, k, n_iter, lr=
     W = None if W is None else _const(W, dtype)
     b, a, x0, y0 = _leaf(b0, dtype), _leaf(a0, dtype), _leaf(x00, dtype), _leaf(y00, dtype)
     pd = a.dim() - 1
-    opt = AdaBelief([b, a, x0, y0], lr, n_iter, True, cv, problem_dims=pd)
+    leaves = [b, a, x0, y0]
+    theta = None
+    if theta0 is not None:                                # field distortion: six more free parameters per frame
+        theta, xy = _leaf(theta0, dtype), _const(xy, dtype)
+        leaves.append(theta)
+    opt = AdaBelief(leaves, lr, n_iter, True, cv, problem_dims=pd)
     hist = []
     for it in range(n_iter):
-        L = psf_loss(s_fixed, b, a, x0, y0, data, weight, W, n, k, lam_scales, lam_hf, cv)
-        g = torch.autograd.grad(L.sum(), [b, a, x0, y0])
+        L = psf_loss(s_fixed, b, a, x0, y0, data, weight, W, n, k, lam_scales, lam_hf, cv, theta, xy)
+        g = torch.autograd.grad(L.sum(), leaves)
         hist.append(L.detach().double().numpy().copy())
         opt.step(list(g))
-    return dict(b=b.detach().numpy(), a=a.detach().numpy(), x0=x0.detach().numpy(),
-                y0=y0.detach().numpy(), loss_hist=np.stack(hist, -1))
+    out = dict(b=b.detach().numpy(), a=a.detach().numpy(), x0=x0.detach().numpy(),
+               y0=y0.detach().numpy(), loss_hist=np.stack(hist, -1))
+    if theta is not None:
+        out['theta'] = theta.detach().numpy()
+    return out
 
 
 def psf_products(s, a, x0, y0, data, weight, n, k, cv: Conventions = DEFAULT, dtype=torch.float64):

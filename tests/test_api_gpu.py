@@ -60,8 +60,16 @@ def test_build_psf_contract(cuda_device):
     assert float(0.5 * (km['fwhm_x'] + km['fwhm_y']).item()) > 0          # psf_modelling.py:177-179
     assert set(result['kwargs_psf']) >= {'kwargs_moffat', 'kwargs_gaussian', 'kwargs_background', 'kwargs_distortion'}
     assert abs(result['narrow_psf'].sum() - 1) < 1e-4 and abs(result['full_psf'].sum() - 1) < 1e-4
-    with pytest.raises(NotImplementedError):
+    assert result['kwargs_psf']['kwargs_distortion'] == {}
+    with pytest.raises(ValueError):                                       # the positions of the stamps in the frame are needed
         build_psf(data, noisemap, 1, field_distortion=True)
+    # the call of psf_modelling.py:164-171 with field_distortion on: same keys + the distortion coefficients (:199-202)
+    xy = np.array([[-0.3, 0.2], [0.1, -0.4], [0.4, 0.4], [-0.2, -0.1], [0.0, 0.3]])
+    r2 = build_psf(data, noisemap, subsampling_factor=1, n_iter_analytic=5, n_iter_adabelief=10, masks=np.ones_like(data),
+                   guess_method_star_position='center', guess_fwhm_pixels=3.0, field_distortion=True, stamp_coordinates=xy)
+    assert set(r2['kwargs_psf']['kwargs_distortion']) == {'dilation_x', 'dilation_y', 'shear'}
+    assert all(v.shape == (2,) and np.isfinite(v).all() for v in r2['kwargs_psf']['kwargs_distortion'].values())
+    assert r2['narrow_psf'].shape == (16, 16) and len(r2['adabelief_extra_fields']['loss_history']) == 10
 
 
 def test_pipeline_shaped_run_chi2_below_2(cuda_device):

@@ -111,7 +111,7 @@ def test_phot_fit_recovers_flux_cpu():
 def test_golden_vectors():
     """Committed golden vectors (tests/golden/*.npz, generated by tools/make_golden.py from the oracle
     in float64) pin the oracle against silent edits."""
-    files = sorted(GOLD.glob('*.npz'))
+    files = sorted(f for f in GOLD.glob('*.npz') if not f.name.startswith('reference_'))    # reference_*: tests/test_reductions_*
     assert files, "tests/golden is empty"
     for f in files:
         g = np.load(f)
@@ -210,3 +210,46 @@ def test_pts_source_and_flux_uniformity_closed_forms():
         if rel: Ac=10/(Et*sd*abs(mean)); Bc=10*sd*np.sign(mean)/(Et*mean**2)
         else: Ac=10/(Et*sd); Bc=0
         assert np.abs(g2 - (Ac * (A_ - mean) - Bc)).max() < 1e-12
+
+
+def test_distortion_oracle_identity_and_gradient():
+    """Field distortion of the oracle (distort_psf): theta = 0 is the identity, a smooth PSF keeps its integral with the
+    determinant factor, and autograd agrees with central differences in the six coefficients."""
+    import torch
+    rng = np.random.default_rng(0)
+    n, k, N = 12, 2, 3
+    nu = n * k
+    yy, xx = np.mgrid[:nu, :nu] - (nu - 1) / 2
+    s = torch.tensor(np.exp(-(xx ** 2 + yy ** 2) / 18.0))
+    xy = torch.tensor(rng.uniform(-0.5, 0.5, (N, 2)))
+    assert float((sm.distort_psf(s, torch.zeros(6, dtype=torch.float64), xy) - s[None]).abs().max()) == 0.0
+    th = rng.uniform(-0.1, 0.1, 6)
+    ratio = sm.distort_psf(s, torch.tensor(th), xy).sum((-1, -2)) / s.sum()
+    assert float((ratio - 1).abs().max()) < 1e-2
+    data, w = rng.random((N, n, n)), np.ones((N, n, n))
+    b = 0.01 * rng.standard_normal((nu, nu))
+    args = (s.numpy(), b, np.ones(N), np.zeros(N), np.zeros(N), data, w, None, n, k, 0.0, 0.0)
+    L, g = sm.psf_loss_grad(*args, theta=th, xy=xy.numpy())
+    eps = 1e-6
+    for q in range(6):
+        tp, tm = th.copy(), th.copy()
+        tp[q] += eps
+        tm[q] -= eps
+        fd = (sm.psf_loss_grad(*args, theta=tp, xy=xy.numpy())[0] - sm.psf_loss_grad(*args, theta=tm, xy=xy.numpy())[0]) / (2 * eps)
+        assert abs(fd - g[4][q]) < 1e-5 * max(1.0, abs(g[4][q])), (q, fd, g[4][q])
+
+
+def test_rescale_image_coordinates_and_position_gather():
+    """utilities/image_coordinates.py:4-25 restated in stamp_store (the product cannot import lightcurver): centre -> (0, 0),
+    corners -> about +-1/2; gather_positions follows the order of gather_psf_batch."""
+    from lightcurver_b200 import stamp_store
+    from lightcurver_b200.processes.psf_modelling import MemoryStore
+    shape = (100, 200)                                         # rows (y), columns (x)
+    out = stamp_store.rescale_image_coordinates(np.array([[99.5, 49.5], [0.0, 0.0], [199.0, 99.0]]), shape)
+    np.testing.assert_allclose(out, [[0, 0], [-99.5 / 200, -49.5 / 100], [99.5 / 200, 49.5 / 100]])
+    store = MemoryStore()
+    store['f0/frame_shape'] = np.array(shape)
+    store['f0/image_pixel_coordinates/s1'] = np.array([10.0, 20.0])
+    store['f0/image_pixel_coordinates/s2'] = np.array([150.0, 80.0])
+    xy = stamp_store.gather_positions(store, [dict(image_relpath='f0')], [['s2', 's1']])
+    np.testing.assert_allclose(xy, stamp_store.rescale_image_coordinates(np.array([[150.0, 80.0], [10.0, 20.0]]), shape), rtol=1e-6)

@@ -23,8 +23,12 @@ def test_install_registers_starred_modules_and_refuses_to_shadow():
             sa.install()                                                        # never shadows an importable `starred`
         psf = np.ones((4, 4))
         assert apply_distortion(psf, {}, np.zeros(2)) is psf
-        with pytest.raises(NotImplementedError):
-            apply_distortion(psf, {'dilation_x': np.zeros(3)}, np.zeros(2))
+        # with coefficients the resampling runs on the device: without one the library refuses (no CPU fallback)
+        kd = {'dilation_x': np.zeros(2), 'dilation_y': np.zeros(2), 'shear': np.zeros(2)}
+        from lightcurver_b200 import _lib
+        if _lib.device_count() == 0:
+            with pytest.raises(_lib.LcbError):
+                apply_distortion(psf, kd, np.zeros(2))
     finally:
         sa.uninstall()
     assert not any(m == 'starred' or m.startswith('starred.') for m in sys.modules)

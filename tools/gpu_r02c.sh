@@ -1,0 +1,3 @@
+set -x
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q -s -p no:cacheprovider > gpurun_out/tests_r02c.log 2>&1; echo "tests rc=$?"; grep -v "^\[parity\]" gpurun_out/tests_r02c.log | tail -30
