@@ -284,9 +284,16 @@ def deconv_parity_vs_single_rank(world, rank, group, comm):
         out = dict(shared_bit_identical=identical, max_abs_dh=float(dh.max()), median_abs_dh=float(np.median(dh)),
                    max_rel_da=float(np.max(np.abs(a_all - fin1['a']) / np.abs(fin1['a']))),
                    loss_rel=float(np.max(np.abs(hist - hist1) / np.abs(hist1))), epochs=E, iterations=20, ranks=world,
-                   ok=bool(identical and dh.max() <= 3e-4 and np.median(dh) <= 2e-5),
-                   note="h, c_x, c_y compared bit for bit across ranks; against the single-rank fit AdaBelief moves a pixel whose gradient is at the "
-                        "rounding level by ~lr per iteration, so h may differ by a couple of steps (lr = 1e-4) where the two summation orders differ")
+                   h_peak=float(np.abs(fin1['h']).max()), lr=1e-4,
+                   # shared parameters bit-identical on every rank; against the single-rank fit: fluxes 1e-5, loss 1e-4, and the background
+                   # within a few AdaBelief steps (a pixel whose gradient is at the rounding level moves by ~lr per iteration in a
+                   # direction that depends on the summation order of the reduction, which differs between 1 and N ranks)
+                   ok=bool(identical and dh.max() <= 10 * 1e-4 and np.median(dh) <= 0.5 * 1e-4 and
+                           np.max(np.abs(a_all - fin1['a']) / np.abs(fin1['a'])) <= 1e-5 and
+                           np.max(np.abs(hist - hist1) / np.abs(hist1)) <= 1e-4),
+                   note="h, c_x, c_y compared bit for bit across ranks; against the single-rank fit: max |dh| <= 10 lr, median |dh| <= lr / 2, "
+                        "fluxes 1e-5, loss history 1e-4 (the summation order of the gradient reduction differs between 1 and N ranks, and "
+                        "AdaBelief moves a pixel whose gradient is at the rounding level by ~lr per iteration)")
     dist.barrier(group=group)
     return out
 

@@ -760,8 +760,41 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
         else for (int r = 0; r < Wn; ++r) D.cm.slots[r][((size_t)parity * Wn + D.cm.rank) * D.tot + i] = v;
     };
     const int cnt = (vhi - vlo) * nu;
-    // sums planes src[p * nu2 + i], p = 0 .. np_-1 (in order) over the pixels of the band; 4 pixels x 4 planes in flight per thread
+    // sums planes src[p * nu2 + i], p = 0 .. np_-1 (in order) over the pixels of the band.  The walk is bound by L2 latency, so
+    // every thread keeps 4 quads x 4 planes (16 independent 16-byte loads) in flight; rows that are not a multiple of 4 pixels
+    // fall back to scalar loads
     auto band_sum = [&](const float* __restrict__ src, int np_, auto&& put) {
+        if ((nu & 3) == 0) {
+            const int cnt4 = cnt >> 2;
+            for (int i0 = tid; i0 < cnt4; i0 += 4 * DC_THREADS) {
+                float4 acc[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int p0 = 0; p0 < np_; p0 += 4) {
+                    float4 v[4][4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+#pragma unroll
+                        for (int pe = 0; pe < 4; ++pe) {
+                            const int i = i0 + q * DC_THREADS;
+                            v[q][pe] = (i < cnt4 && p0 + pe < np_) ? __ldcg(reinterpret_cast<const float4*>(src + (size_t)(p0 + pe) * nu2) + i)
+                                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+#pragma unroll
+                        for (int pe = 0; pe < 4; ++pe) {
+                            acc[q].x += v[q][pe].x; acc[q].y += v[q][pe].y; acc[q].z += v[q][pe].z; acc[q].w += v[q][pe].w;
+                        }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int i = i0 + q * DC_THREADS;
+                    if (i < cnt4) { const int o = vlo * nu + 4 * i; put(o, acc[q].x); put(o + 1, acc[q].y); put(o + 2, acc[q].z); put(o + 3, acc[q].w); }
+                }
+            }
+            return;
+        }
         for (int i0 = tid; i0 < cnt; i0 += 4 * DC_THREADS) {
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
             for (int p0 = 0; p0 < np_; p0 += 4) {
