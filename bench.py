@@ -635,7 +635,7 @@ def main():
     phot_chi2_med = float(ph['chi2'].median())
 
     # ---- e2e through the public API with pinned host buffers
-    e2e_steps = max(1, min(args.steps, 5))
+    e2e_steps = 5 if args.steps >= 3 else max(1, args.steps)      # at least five end-to-end steps in the default run
     step_e2e()
     barrier()
     t0 = time.perf_counter()

@@ -30,6 +30,7 @@
 // plain 2-D correlation of an n x n plane with an NA x NA kernel (NA ~ P/k + 1): 4x fewer MACs than
 // convolving at full resolution, and lanes <-> rows with an odd leading dimension is conflict free.
 #include "lcb_common.cuh"
+#include "lcb_starlet.cuh"
 #include <cooperative_groups.h>
 #include <vector>
 
@@ -1206,6 +1207,41 @@ __global__ void __cluster_dims__(DU_CTAS, 1, 1) __launch_bounds__(DU_THREADS) k_
     cl.sync();                                        // nobody leaves while its band may still be read
 }
 
+// The same term on ONE SM: the whole nu x nu background (nu = 64 or 128) with its two scratch planes and the packed sign planes
+// fits the shared memory of a single CTA (174 KB at nu = 128), so the float4 routine of the PSF fit (lcb_starlet.cuh) applies:
+// no DSMEM reads, no cluster barriers, every stencil tap one LDS.128.  Measured at cfg4: 0.13 ms for the 8-CTA DSMEM kernel --
+// the critical path of an iteration once the epochs are sharded over 8 GPUs (the epoch kernel takes 0.10 ms there) -- against
+// ~0.03 ms here.
+#ifndef LCB_SM_STARLET_THREADS
+#define LCB_SM_STARLET_THREADS 512
+#endif
+template <int NUT>
+__global__ void __launch_bounds__(NUT == 128 ? LCB_SM_STARLET_THREADS : 256) k_deconv_starlet_sm(DeconvDev D) {
+    constexpr int NTH = (NUT == 128) ? LCB_SM_STARLET_THREADS : 256;
+    constexpr int PP = NUT * NUT;
+    extern __shared__ __align__(16) float ssm[];
+    __shared__ float red[NTH / 32];
+    const int tid = threadIdx.x;
+    float* C0 = ssm;
+    float* C1 = C0 + PP;
+    float* aux = C1 + PP;                                            // [NUT][NUT/4 + 1] + [NUT][2]
+    signed char* sg = reinterpret_cast<signed char*>(aux + NUT * (NUT / 4 + 1) + 2 * NUT);   // [J][PP / 4]
+    float reg = starlet_reg_fast4<NUT, NTH>(D.h, C0, C1, sg, aux, D.W, D.lam_hf, D.lam_scales, D.J, tid);
+    for (int i = tid; i < PP / 4; i += NTH) reinterpret_cast<float4*>(D.planes)[i] = reinterpret_cast<const float4*>(C0)[i];
+    reg = warp_sum(reg);
+    if ((tid & 31) == 0) red[tid >> 5] = reg;
+    __syncthreads();
+    if (tid == 0) {
+        float s_ = 0.f;
+        for (int w = 0; w < NTH / 32; ++w) s_ += red[w];
+        D.ctl[6] = s_;
+    }
+}
+
+static size_t starlet_sm_bytes(int nu, int J) {
+    return ((size_t)2 * nu * nu + (size_t)nu * (nu / 4 + 1) + 2 * nu) * 4 + (size_t)J * nu * nu / 4;
+}
+
 // several cluster-wide sums with ONE cluster barrier
 template <int N>
 __device__ __forceinline__ void cluster_sums(float (&v)[N], float* red, float* gpart, int tid, int rank) {
@@ -1673,7 +1709,16 @@ static int launch_starlet(DeconvHandle* H) {
         const int R = (D.nu + DU_CTAS - 1) / DU_CTAS;
         const size_t dsm = (size_t)(5 + D.J) * R * D.nu * 4;
         LcbProfScope ps("k_deconv_starlet", H->st2);
-        if (dsm <= (size_t)H->max_smem && !getenv("LCB_DECONV_STARLET_L2")) {
+        const size_t one_sm = starlet_sm_bytes(D.nu, D.J);
+        if ((D.nu == 128 || D.nu == 64) && one_sm <= (size_t)H->max_smem && !getenv("LCB_DECONV_STARLET_CLUSTER")) {
+            if (!H->starlet_attr) {
+                if (D.nu == 128) LCB_CUDA(cudaFuncSetAttribute(k_deconv_starlet_sm<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)one_sm));
+                else LCB_CUDA(cudaFuncSetAttribute(k_deconv_starlet_sm<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)one_sm));
+                H->starlet_attr = true;
+            }
+            if (D.nu == 128) k_deconv_starlet_sm<128><<<1, LCB_SM_STARLET_THREADS, one_sm, H->st2>>>(D);
+            else k_deconv_starlet_sm<64><<<1, 256, one_sm, H->st2>>>(D);
+        } else if (dsm <= (size_t)H->max_smem && !getenv("LCB_DECONV_STARLET_L2")) {
             if (!H->starlet_attr) {
                 LCB_CUDA(cudaFuncSetAttribute(k_deconv_starlet_dsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
                 H->starlet_attr = true;
