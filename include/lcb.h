@@ -303,6 +303,10 @@ typedef struct {
 size_t lcb_phot_prepare_work_floats(int F, int S);
 int lcb_phot_prepare_batch(const lcb_phot_prepare_in* in, lcb_phot_prepare_out* out, float* work, void* stream);
 
+/* Pitched copy host <-> device (cudaMemcpy2DAsync on `stream`): `height` rows of `width_bytes`, row pitches in bytes.  Used by the
+ * host layer to upload a strided slice of a pinned batch array (one device's share of the stars) without a host-side gather. */
+int lcb_copy_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width_bytes, size_t height, int to_device, void* stream);
+
 /* ---------------- measurement helper ---------------------------------------------------------- */
 /* FP32 FMA micro-benchmark: runs `iters` dependent-chain FFMA loops on every SM and returns the
  * achieved TFLOP/s in *tflops (used as the measured roofline denominator by bench.py). */

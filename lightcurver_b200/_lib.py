@@ -207,6 +207,7 @@ lib.lcb_psf_fit_batch.restype = C.c_int
 lib.lcb_apply_distortion_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                            C.c_void_p, C.c_int, C.c_void_p]
 lib.lcb_apply_distortion_batch.restype = C.c_int
+lib.lcb_copy_2d.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p]
 lib.lcb_norm_medians.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
 lib.lcb_norm_scatter_work_doubles.argtypes = [C.c_int, C.c_int]
 lib.lcb_norm_scatter_matrix.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]

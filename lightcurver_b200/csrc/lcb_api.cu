@@ -337,3 +337,15 @@ extern "C" int lcb_fp32_peak(int iters, float* tflops, float* ms_out) {
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
     return LCB_OK;
 }
+
+// Strided (pitched) copy between host and device: the in-process multi-GPU fan-out hands every device a slice data[:, lo:hi]
+// of a C-contiguous pinned (F, S, n, n) array -- F rows of (hi - lo) n^2 floats with a pitch of S n^2 floats -- and this moves
+// it in ONE asynchronous 2-D copy instead of a host-side gather into pageable memory followed by a staged upload.
+extern "C" int lcb_copy_2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width_bytes, size_t height,
+                           int to_device, void* stream) {
+    LCB_REQUIRE(dst && src && dpitch >= width_bytes && spitch >= width_bytes, "lcb_copy_2d: bad arguments");
+    if (width_bytes == 0 || height == 0) return LCB_OK;
+    LCB_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width_bytes, height,
+                               to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return LCB_OK;
+}

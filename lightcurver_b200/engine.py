@@ -134,11 +134,22 @@ def apply_distortion_batch(psfs, theta, psf_index, xy, mode=1):
 
 
 def _to_device(x, dtype):
-    """numpy (pinned or pageable) / torch host or device array -> contiguous CUDA tensor of ``dtype`` on the current device."""
+    """numpy (pinned or pageable) / torch host or device array -> contiguous CUDA tensor of ``dtype`` on the current device.
+    A numpy view whose rows are contiguous blocks at a constant pitch (``batch[:, lo:hi]`` of a C-contiguous array: what the
+    in-process fan-out hands every device) goes up in ONE pitched asynchronous copy (``lcb_copy_2d``), without a host gather."""
     import torch
     if _lib.is_torch(x):
         return x.to(device='cuda', dtype=dtype, non_blocking=True).contiguous()
-    a = np.ascontiguousarray(x)
+    want = {torch.float32: np.float32, torch.uint8: None, torch.int32: np.int32}.get(dtype)
+    a = np.asarray(x)
+    if (want is not None and a.dtype == want and a.ndim >= 2 and not a.flags.c_contiguous and a[0].flags.c_contiguous
+            and a.strides[0] >= a[0].nbytes and a.shape[0] > 0 and a[0].nbytes > 0):
+        out = torch.empty(a.shape, dtype=dtype, device='cuda')
+        _lib.check(_lib.lib.lcb_copy_2d(out.data_ptr(), a[0].nbytes, a.ctypes.data, a.strides[0], a[0].nbytes, a.shape[0], 1,
+                                        C.c_void_p(torch.cuda.current_stream().cuda_stream)), 'lcb_copy_2d')
+        out._lcb_keepalive = a                     # the source must outlive the asynchronous copy
+        return out
+    a = np.ascontiguousarray(a)
     if dtype == torch.uint8:
         a = a.view(np.uint8) if a.dtype == np.bool_ else (a > 0).view(np.uint8)
     elif dtype == torch.int32:
@@ -146,6 +157,22 @@ def _to_device(x, dtype):
     elif a.dtype != np.float32:
         a = a.astype(np.float32)
     return torch.from_numpy(a).to('cuda', non_blocking=True)
+
+
+def to_host(tensors):
+    """dict of CUDA tensors -> dict of numpy arrays through PAGE-LOCKED staging (torch's caching host allocator keeps the
+    buffers for the next call): the copies run at the PCIe rate and overlap each other; one synchronisation at the end."""
+    import torch
+    staged = {}
+    for kk, v in tensors.items():
+        if not v.is_cuda:
+            staged[kk] = v
+            continue
+        h = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+        h.copy_(v, non_blocking=True)
+        staged[kk] = h
+    torch.cuda.current_stream().synchronize()
+    return {kk: h.numpy() for kk, h in staged.items()}
 
 
 GUESS_METHODS = {'center': 0, 'max': 1, 'barycenter': 2}

@@ -107,7 +107,7 @@ def build_psf_batch(images, noisemaps, subsampling_factor, masks=None, n_iter_an
         lam_scales=lam_s, lam_hf=lam_h, noise_weights=noise_propagation, mc_samples=noise_samples, mc_seed=noise_seed,
         bounds=dict(fwhm_min=cv.moffat_fwhm_min, fwhm_max=n / 2.0, beta_min=cv.moffat_beta_min, beta_max=cv.moffat_beta_max),
         want=('narrow_psf', 'full_psf', 'residuals', 'chi2', 'loss_hist', 'loss_hist_analytic', 'status'), **dist)
-    out = {kk: v.cpu().numpy() for kk, v in out.items()}            # one device -> host copy per product
+    out = engine.to_host(out)                  # one device -> host copy per product, through page-locked staging
     norms = prep['norm'].cpu().numpy().astype(np.float64)
     out['norms'] = norms
     out['star_off'] = off

@@ -192,8 +192,8 @@ def star_photometry_batch(data, noisemap, psfs, subsampling_factor, n_iter=2000,
     psf_d = engine._to_device(psfs, torch.float32)
     out = engine.phot_fit_batch(prep['data'], prep['weight'], psf_d, idx, prep['a0'], k, n_iter, lr=1e-3, schedule=True,
                                 want_residuals=want_residuals, want_loss_hist=want_loss_hist)
-    out = {kk: v.cpu().numpy() for kk, v in out.items()}
-    scale = prep['scale'].cpu().numpy()
+    out = engine.to_host(dict(out, scale=prep['scale']))
+    scale = out.pop('scale')
     res = {
         'scale': scale,
         'fluxes': out['a'].reshape(F, S) * scale[None] / cv.amplitude_per_flux(k),          # pixel-sum units
