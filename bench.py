@@ -158,19 +158,20 @@ def workload_string(F, N, n, k, cfg_name='cfg2'):
 
 def run_reference(args):
     """Reference arm: the CPU restatement of the reference's path (oracle port; STARRED itself is not installable here) on the
-    box's host cores, on OUR arm's config / metric / unit.  Every step is the same bounded sample (2 frames of the workload,
-    20 / 100 / 100 iterations of the three stages, scaled linearly to 100 / 3000 / 2000), after one untimed warm call."""
+    box's host cores, on OUR arm's config / metric / unit.  Every step is the SAME bounded sample as the `cpu_baseline` of our arm
+    (8 frames of the workload, 20 / 200 / 200 iterations of the three stages, scaled linearly to 100 / 3000 / 2000: ~17 s of CPU
+    work), after one untimed warm call; at most three timed steps so that the run ends within a few minutes."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    sample = dict(sample_frames=2, t1=20, t2=100, tphot=100)
-    cpu_baseline_run(**sample)                              # untimed warm call (thread pools, autograd graphs, scipy import)
+    sample = dict(sample_frames=8, t1=20, t2=200, tphot=200)
+    warm = dict(sample_frames=2, t1=5, t2=20, tphot=20)
+    cpu_baseline_run(**warm)                                # untimed warm call (thread pools, autograd graphs, scipy import)
     vals, secs = [], []
     r = None
-    for i in range(args.warmup + args.steps):
+    for i in range(max(1, min(args.steps, 3))):
         r = cpu_baseline_run(**sample)
-        if i >= args.warmup:
-            vals.append(r['value']); secs.append(r['seconds'])
+        vals.append(r['value']); secs.append(r['seconds'])
     v = float(np.median(vals))
     r['value'] = v
     r['spread'] = [float(np.min(vals)), float(np.max(vals))]

@@ -2,6 +2,7 @@
 // (pixel grid AdaBelief), chunked over frames so that the per-frame workspace stays bounded.
 #include "lcb_psf.cuh"
 #include <vector>
+#include <cstdlib>
 #include <mutex>
 #include <atomic>
 
@@ -106,7 +107,9 @@ static int psf_run_device(const lcb_psf_batch* in, const lcb_psf_opts* opt, lcb_
     const size_t wpf = (size_t)(J + 7) * pp + (size_t)2 * Nmax * n * n + (distort ? (size_t)2 * pp : 0);
     const bool fit_fast = !distort && lcb_psf_fit_has_fast(n, k, lcb_conv().gauss_taps) &&
                           fit_small + lcb_psf_fit_smem_fast_extra(n, nu, J) <= (size_t)maxsm;
-    const int chunk = F < 1184 ? F : 1184;                   // 8 waves of 148 CTAs
+    int chunk_max = 1184;                                    // 8 waves of 148 CTAs
+    if (const char* ce = getenv("LCB_PSF_CHUNK")) { const int c = atoi(ce); if (c >= 1) chunk_max = c; }   // tests exercise the chunk loop
+    const int chunk = F < chunk_max ? F : chunk_max;
     // grids too large for one SM: one 8-CTA cluster per frame with the planes distributed over its shared memories
     // (LCB_PSF_CLUSTER=0 / 1 forces the single-CTA / the cluster kernel: parity tests compare the two)
     const char* cl_env = getenv("LCB_PSF_CLUSTER");

@@ -346,3 +346,28 @@ def test_psf_noise_weights_monte_carlo(cuda_device):
     Wslit = run('SLIT')
     ratio = np.median((Wmc / Wslit).reshape(F, -1, nu * nu), axis=-1)
     assert (ratio[:, 0] < 0.8).all() and (ratio[:, -1] > 1.5).all()       # correlated gradient noise: less power at the finest scale
+
+
+def test_psf_fit_chunked_batches_equal_one_batch(cuda_device, monkeypatch):
+    """lcb_psf_fit_batch walks large batches in chunks of 1184 frames (bounded workspace: cfg5 needs 3.1 MB per resident
+    frame); LCB_PSF_CHUNK shrinks the chunk so that the loop, the per-chunk offsets of every in/out array and the ragged star
+    offsets are exercised: 7 frames with 2..4 stars in chunks of 3 must give bit-identical results to one chunk, on the fast
+    path (32 x 32, k = 2) and on the generic one (18 x 18, k = 3), with the noise weights and the Moffat stage inside."""
+    from lightcurver_b200 import engine
+    for n, k in ((32, 2), (18, 3)):
+        counts = [3, 2, 4, 3, 2, 4, 3]
+        F, Nmax = len(counts), max(counts)
+        d, data, nm, weight, a0, _ = _frames(F, Nmax, n, k, seed=60 + n)
+        sel = np.concatenate([np.arange(c) + f * Nmax for f, c in enumerate(counts)])
+        off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+        flat = lambda x: _flat(x)[sel]
+        moffat = np.stack([d['fwhm'], d['fwhm'], np.zeros(F), np.full(F, 2.5), np.ones(F)], -1)
+        outs = []
+        for chunk in ('3', '1000'):
+            monkeypatch.setenv('LCB_PSF_CHUNK', chunk)
+            outs.append(engine.psf_fit_batch(flat(data), flat(weight), off, k, moffat, a0.reshape(-1)[sel],
+                                             n_iter_analytic=15, n_iter_adabelief=12, lr=1e-5, noise_weights=True,
+                                             want=('narrow_psf', 'full_psf', 'residuals', 'chi2', 'loss_hist', 'loss_hist_analytic', 'status')))
+        for key in outs[0]:
+            np.testing.assert_array_equal(outs[0][key], outs[1][key], err_msg=f"{key} (n={n}, k={k})")
+        assert (outs[0]['status'] == 0).all()
