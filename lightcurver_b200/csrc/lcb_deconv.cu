@@ -59,6 +59,7 @@ struct DeconvDev {
     int E, n, k, nu, P, M, NA, A0, J, G;
     int E_total, e0;                     // epochs over all ranks, global index of the first local epoch
     int tot;                             // length of red[]
+    int tot_pad;                         // stride of a receive slot: tot rounded up to 4 floats (16-byte stores into peer memory)
     int free_h, free_mean, free_a, free_c, free_d;
     // inputs
     float *data, *weight, *S;            // [E][n][n], [E][n][n], [E][k*k][NA][NA]
@@ -758,13 +759,19 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
     const int Wn = D.cm.world, parity = seq & 1, nu2 = nu * nu;
     auto emit = [&](int i, float v) {
         if (seq == 0) D.red[i] = v;
-        else for (int r = 0; r < Wn; ++r) D.cm.slots[r][((size_t)parity * Wn + D.cm.rank) * D.tot + i] = v;
+        else for (int r = 0; r < Wn; ++r) D.cm.slots[r][((size_t)parity * Wn + D.cm.rank) * D.tot_pad + i] = v;
+    };
+    // four consecutive entries (i a multiple of 4): ONE 16-byte store per peer instead of four 4-byte stores at a 16-byte stride
+    auto emit4 = [&](int i, float4 v) {
+        if (seq == 0) *reinterpret_cast<float4*>(D.red + i) = v;
+        else for (int r = 0; r < Wn; ++r)
+            *reinterpret_cast<float4*>(D.cm.slots[r] + ((size_t)parity * Wn + D.cm.rank) * D.tot_pad + i) = v;
     };
     const int cnt = (vhi - vlo) * nu;
     // sums planes src[p * nu2 + i], p = 0 .. np_-1 (in order) over the pixels of the band.  The walk is bound by L2 latency, so
     // every thread keeps 4 quads x 4 planes (16 independent 16-byte loads) in flight; rows that are not a multiple of 4 pixels
     // fall back to scalar loads
-    auto band_sum = [&](const float* __restrict__ src, int np_, auto&& put) {
+    auto band_sum = [&](const float* __restrict__ src, int np_, auto&& put, auto&& put4) {
         if ((nu & 3) == 0) {
             const int cnt4 = cnt >> 2;
             for (int i0 = tid; i0 < cnt4; i0 += 4 * DC_THREADS) {
@@ -791,7 +798,7 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int i = i0 + q * DC_THREADS;
-                    if (i < cnt4) { const int o = vlo * nu + 4 * i; put(o, acc[q].x); put(o + 1, acc[q].y); put(o + 2, acc[q].z); put(o + 3, acc[q].w); }
+                    if (i < cnt4) put4(vlo * nu + 4 * i, acc[q]);
                 }
             }
             return;
@@ -820,8 +827,8 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
     if (D.free_h) {
         const float* src = D.Gh + (size_t)g_lo * nu2 + (size_t)vlo * nu;
         float* dst = D.Gp + (size_t)grp * nu2;
-        if (one_level) band_sum(src, g_hi - g_lo, emit);
-        else band_sum(src, g_hi - g_lo, [&](int i, float v) { dst[i] = v; });
+        if (one_level) band_sum(src, g_hi - g_lo, emit, emit4);
+        else band_sum(src, g_hi - g_lo, [&](int i, float v) { dst[i] = v; }, [&](int i, float4 v) { *reinterpret_cast<float4*>(dst + i) = v; });
     } else if (one_level) {
         for (int i = tid; i < cnt; i += DC_THREADS) emit(vlo * nu + i, 0.f);
     }
@@ -833,7 +840,7 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
         __syncthreads();
         if (!s_last) return;
         __threadfence();
-        if (D.free_h) band_sum(D.Gp + (size_t)vlo * nu, D.NG, emit);
+        if (D.free_h) band_sum(D.Gp + (size_t)vlo * nu, D.NG, emit, emit4);
         else for (int i = tid; i < cnt; i += DC_THREADS) emit(vlo * nu + i, 0.f);
     }
     if (crank == 0) {
@@ -930,7 +937,7 @@ __global__ void __launch_bounds__(256) k_deconv_reduce(DeconvDev D, int force_h,
     }
     const int W = D.cm.world, par = seq & 1;
     if (writer)
-        for (int r = 0; r < W; ++r) D.cm.slots[r][((size_t)par * W + D.cm.rank) * D.tot + i] = s;
+        for (int r = 0; r < W; ++r) D.cm.slots[r][((size_t)par * W + D.cm.rank) * D.tot_pad + i] = s;
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1297,10 +1304,10 @@ k_deconv_update(DeconvDev D, int it_arg, int n_iter, float lr0, int schedule, in
         }
         __threadfence_system();
         __syncthreads();
-        const float* sl = D.cm.slots[D.cm.rank] + (size_t)par * W * D.tot;
+        const float* sl = D.cm.slots[D.cm.rank] + (size_t)par * W * D.tot_pad;
         for (int i = gtid; i < D.tot; i += GT_ALL) {
             float s = 0.f;
-            for (int r = 0; r < W; ++r) s += __ldcg(sl + (size_t)r * D.tot + i);
+            for (int r = 0; r < W; ++r) s += __ldcg(sl + (size_t)r * D.tot_pad + i);
             D.red[i] = s;
         }
         __threadfence();
@@ -1806,6 +1813,7 @@ int lcb_deconv_create(const lcb_deconv_problem* p, int mem, void* stream, void**
     D.cm.world = 1; D.cm.rank = 0;
     D.pts_all_epochs = 1; D.fu_relative = 1;
     D.tot = D.nu * D.nu + 6 * D.M + 2;
+    D.tot_pad = (D.tot + 3) & ~3;
     D.cv = lcb_devconv();
     D.G = D.cv.G;
     LCB_REQUIRE(D.G <= 16, "gauss_taps must be <= 16");
@@ -1889,7 +1897,7 @@ int lcb_deconv_comm_init(void* handle, int rank, int world, void* ipc_handle_out
                 "lcb_deconv_comm_init: bad arguments (world <= %d)", DC_MAXW);
     LCB_REQUIRE(!H->comm_buf, "lcb_deconv_comm_init: already initialised");
     DeconvDev& D = H->D;
-    const size_t slots_bytes = ((size_t)2 * world * D.tot * 4 + 255) & ~(size_t)255;
+    const size_t slots_bytes = ((size_t)2 * world * D.tot_pad * 4 + 255) & ~(size_t)255;
     const size_t bytes = slots_bytes + (size_t)2 * world * 4 + 256;
     LCB_CUDA(cudaMalloc(&H->comm_buf, bytes));
     LCB_CUDA(cudaMemset(H->comm_buf, 0, bytes));
@@ -1912,7 +1920,7 @@ int lcb_deconv_comm_connect(void* handle, const void* all_handles) {
     DeconvHandle* H = (DeconvHandle*)handle;
     LCB_REQUIRE(H && all_handles && H->comm_buf, "lcb_deconv_comm_connect: call lcb_deconv_comm_init first");
     DeconvDev& D = H->D;
-    const size_t slots_bytes = ((size_t)2 * D.cm.world * D.tot * 4 + 255) & ~(size_t)255;
+    const size_t slots_bytes = ((size_t)2 * D.cm.world * D.tot_pad * 4 + 255) & ~(size_t)255;
     for (int r = 0; r < D.cm.world; ++r) {
         if (r == D.cm.rank) continue;
         cudaIpcMemHandle_t hd;

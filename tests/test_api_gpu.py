@@ -293,3 +293,71 @@ def test_coupled_photometry_of_many_stars_in_one_call(cuda_device, flags):
         np.testing.assert_allclose(b['loss_curve'], a['loss_curve'], rtol=1e-6)
         np.testing.assert_allclose(b['residuals'], a['residuals'], atol=1e-5 * np.abs(a['residuals']).max() + 1e-9)
         assert len(b['loss_curve']) == n_iter and np.isfinite(b['chi2'])
+
+
+def test_strided_batch_slices_go_up_in_one_pitched_copy(cuda_device):
+    """The in-process fan-out hands every device a slice ``batch[:, lo:hi]`` of the (F, S, n, n) arrays: the host layer uploads
+    it with ONE pitched copy (lcb_copy_2d) instead of gathering it on the host.  Same results as with a contiguous copy of the
+    slice (bit for bit), outputs staged through page-locked memory."""
+    from lightcurver_b200 import engine, synthetic
+    from lightcurver_b200.processes.star_photometry import star_photometry_batch
+    import torch
+    F, S, n, k = 6, 5, 16, 2
+    d = synthetic.make_phot_frames(F, S, n, k, seed=5)
+    view_d, view_n = d['data'][:, 1:4], d['noisemap'][:, 1:4]
+    assert not view_d.flags.c_contiguous
+    up = engine._to_device(view_d, torch.float32)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(up.cpu().numpy(), np.ascontiguousarray(view_d))
+    a = star_photometry_batch(view_d, view_n, d['psf'], k, n_iter=30)
+    b = star_photometry_batch(np.ascontiguousarray(view_d), np.ascontiguousarray(view_n), d['psf'], k, n_iter=30)
+    for key in ('fluxes', 'fluxes_uncertainties', 'chi2_per_frame', 'dx', 'dy', 'scale', 'loss_curve'):
+        np.testing.assert_array_equal(a[key], b[key], err_msg=key)
+    # a pinned source takes the same route
+    pinned = torch.from_numpy(d['data']).pin_memory().numpy()
+    up2 = engine._to_device(pinned[:, 2:5], torch.float32)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(up2.cpu().numpy(), d['data'][:, 2:5])
+
+
+def test_two_host_threads_with_host_buffers_and_different_conventions(cuda_device):
+    """The host layer is called from one thread per GPU by the in-process fan-out, and lightcurver may keep several handles
+    alive: LCB_MEM_HOST calls lease a staging arena per call and device, conventions are per thread.  Two threads hammer the
+    SAME device with host-buffer calls, one under the default conventions (block sum) and one under the block mean; every
+    result must equal the one obtained serially under that thread's conventions."""
+    import threading
+    from lightcurver_b200 import engine, synthetic
+    from lightcurver_b200.conventions import Conventions, apply_to_library
+    n, k, F, S = 16, 2, 4, 3
+    d = synthetic.make_phot_frames(F, S, n, k, seed=8)
+    data = d['data'].reshape(-1, n, n)
+    w = (1.0 / d['noisemap'].reshape(-1, n, n).astype(np.float64) ** 2).astype(np.float32)
+    idx = np.repeat(np.arange(F), S).astype(np.int32)
+    cvs = [Conventions(), Conventions(downsample_mean=True)]
+
+    def run(cv, reps):
+        apply_to_library(cv)                                   # this thread only
+        a0 = (data.sum((-1, -2)) * cv.amplitude_per_flux(k)).astype(np.float32)
+        outs = []
+        for _ in range(reps):
+            o = engine.phot_fit_batch(data, w, d['psf'], idx, a0, k, 25)
+            outs.append((o['a'].copy(), o['dx'].copy(), o['loss_hist'].copy()))
+        return outs
+    serial = [run(cv, 1)[0] for cv in cvs]
+    assert not np.allclose(serial[0][0], serial[1][0], rtol=1e-3)          # the two conventions give different amplitudes (x k^2)
+    results, errors = [None, None], []
+
+    def worker(i):
+        try:
+            results[i] = run(cvs[i], 12)
+        except Exception as exc:                                  # pragma: no cover
+            errors.append(exc)
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    apply_to_library(DEFAULT)
+    assert not errors, errors
+    for i in range(2):
+        for got in results[i]:
+            for x, y in zip(got, serial[i]):
+                np.testing.assert_array_equal(x, y)
