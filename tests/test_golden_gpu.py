@@ -33,3 +33,20 @@ def test_golden_psf(cuda_device):
     np.testing.assert_allclose(out['loss0'][0], g['loss'], rtol=1e-5)
     np.testing.assert_allclose(out['grad_b0'][0], g['grad_b'], rtol=1e-5, atol=1e-5 * np.abs(g['grad_b']).max())
     np.testing.assert_allclose(out['grad_s0'], g['grad_s'], rtol=2e-5, atol=1e-5 * np.abs(g['grad_s']).max())
+
+
+def test_golden_psf_with_field_distortion(cuda_device):
+    from lightcurver_b200 import engine
+    g = np.load(GOLD / 'psfdist_n16_k2.npz')
+    n, k = int(g['n']), int(g['k'])
+    N = g['data'].shape[0]
+    moffat = np.array([[3.0, 3.3, 0.3, 2.9, 1.0]])
+    out = engine.psf_fit_batch(g['data'], g['weight'], np.array([0, N], np.int32), k, moffat, g['a'], g['x0'], g['y0'],
+                               background0=g['b'][None], W=g['W'][None], n_iter_analytic=0, n_iter_adabelief=1,
+                               lam_scales=float(g['lam_scales']), lam_hf=float(g['lam_hf']),
+                               want=('loss0', 'grad_b0', 'grad_s0', 'grad_dist0'),
+                               field_distortion=1, stamp_xy=g['xy'], distortion0=g['theta'][None])
+    np.testing.assert_allclose(out['loss0'][0], g['loss'], rtol=1e-5)
+    np.testing.assert_allclose(out['grad_b0'][0], g['grad_b'], rtol=1e-5, atol=1e-5 * np.abs(g['grad_b']).max())
+    np.testing.assert_allclose(out['grad_s0'], g['grad_s'], rtol=2e-5, atol=1e-5 * np.abs(g['grad_s']).max())
+    np.testing.assert_allclose(out['grad_dist0'][0], g['grad_theta'], rtol=2e-5, atol=1e-5 * np.abs(g['grad_theta']).max())

@@ -127,6 +127,15 @@ def test_golden_vectors():
             np.testing.assert_allclose(L, g['loss'], rtol=1e-12)
             np.testing.assert_allclose(gr[0], g['grad_b'], rtol=1e-9, atol=1e-12)
             np.testing.assert_allclose(np.stack(gr[1:], -1), g['grad_s'], rtol=1e-9, atol=1e-12)
+        elif kind == 'psfdist':
+            L, gr = sm.psf_loss_grad(g['s_fixed'], g['b'], g['a'], g['x0'], g['y0'], g['data'], g['weight'], g['W'], n, k,
+                                     float(g['lam_scales']), float(g['lam_hf']), theta=g['theta'], xy=g['xy'])
+            np.testing.assert_allclose(L, g['loss'], rtol=1e-12)
+            np.testing.assert_allclose(gr[0], g['grad_b'], rtol=1e-9, atol=1e-12)
+            np.testing.assert_allclose(np.stack(gr[1:4], -1), g['grad_s'], rtol=1e-9, atol=1e-12)
+            np.testing.assert_allclose(gr[4], g['grad_theta'], rtol=1e-9, atol=1e-12)
+        else:
+            raise AssertionError(f"unknown golden vector kind {kind!r} in {f.name}")
 
 
 def test_pts_source_and_flux_uniformity_closed_forms():

@@ -71,3 +71,31 @@ def test_oracle_matches_starred_deconvolution_terms():
             ok = False
             report.append((name, want, got))
     assert ok, f"terms of the deconvolution Loss that no restated variant reproduces (STARRED value, restated variants): {report}"
+
+
+@pytest.mark.skipif(not FILES, reason="no STARRED golden vectors (run tools/dump_starred_vectors.py where STARRED is installed)")
+def test_oracle_matches_starred_field_distortion():
+    """apply_distortion of real STARRED on a fixed, non-trivial kwargs_distortion against the restated resampling, with and
+    without the determinant factor: names the Conventions.distortion_conserve_flux value that matches (or says that the
+    parametrisation itself -- keys, polynomial order -- differs from the recalled one)."""
+    import dataclasses
+    import torch
+    from oracle import starred_model as sm
+    from oracle.conventions import DEFAULT
+    f = GOLD / 'starred_distortion_n16_k2.npz'
+    if not f.exists():
+        pytest.skip("field distortion vector absent")
+    g = np.load(f)
+    keys = sorted(kk[len('distortion_'):] for kk in g.files if kk.startswith('distortion_'))
+    assert keys == ['dilation_x', 'dilation_y', 'shear'], f"STARRED's kwargs_distortion holds {keys}: restate csrc/lcb_distort.cuh"
+    assert all(g['distortion_' + kk].size == 2 for kk in keys), \
+        f"polynomial sizes {[g['distortion_' + kk].shape for kk in keys]} differ from the recalled first-order form (2 coefficients)"
+    theta = torch.full((6,), 0.03, dtype=torch.float64)
+    s = torch.tensor(g['narrow_psf'], dtype=torch.float64)
+    xy = torch.tensor(g['stamp_coordinates'], dtype=torch.float64)
+    errs = {}
+    for conserve in (True, False):
+        cv = dataclasses.replace(DEFAULT, distortion_conserve_flux=conserve)
+        got = sm.distort_psf(s, theta, xy, cv).numpy()
+        errs[conserve] = float(np.abs(got - g['distorted_probe']).max() / np.abs(g['distorted_probe']).max())
+    assert min(errs.values()) <= 1e-4, f"no variant of the restated resampling reproduces STARRED's apply_distortion: {errs}"

@@ -51,6 +51,26 @@ def main():
                         **{f'gaussian_{kk}': np.asarray(v) for kk, v in kw['kwargs_gaussian'].items()},
                         background=np.asarray(kw['kwargs_background']['background']))
 
+    # --- field distortion: build_psf(field_distortion=True, stamp_coordinates=...) (psf_modelling.py:169-170) and apply_distortion
+    #     (star_photometry.py:303) on the same frame: pins the parametrisation recalled in csrc/lcb_distort.cuh (which keys
+    #     kwargs_distortion holds, the order of its polynomial, the resampling, the determinant factor)
+    try:
+        from starred.psf.psf import apply_distortion
+        xy = np.array([[-0.3, 0.2], [0.1, -0.4], [0.4, 0.4]])
+        resd = build_psf(image=d['data'][0], noisemap=d['noisemap'][0], subsampling_factor=k, n_iter_analytic=50,
+                         n_iter_adabelief=100, masks=d['masks'][0], guess_method_star_position='center',
+                         guess_fwhm_pixels=float(d['fwhm'][0]), field_distortion=True, stamp_coordinates=xy)
+        kd = {kk: np.asarray(v) for kk, v in resd['kwargs_psf']['kwargs_distortion'].items()}
+        probe = {kk: np.full_like(v, 0.03) for kk, v in kd.items()}          # a fixed, non-trivial distortion for the resampling itself
+        np.savez_compressed(out / 'starred_distortion_n16_k2.npz', kind='starred_distortion', n=n, k=k, data=d['data'][0],
+                            noisemap=d['noisemap'][0], masks=d['masks'][0], fwhm_guess=d['fwhm'][0], stamp_coordinates=xy,
+                            narrow_psf=np.asarray(resd['narrow_psf']),
+                            distorted_fitted=np.stack([np.asarray(apply_distortion(resd['narrow_psf'], kd, p_)) for p_ in xy]),
+                            distorted_probe=np.stack([np.asarray(apply_distortion(resd['narrow_psf'], probe, p_)) for p_ in xy]),
+                            **{f'distortion_{kk}': v for kk, v in kd.items()})
+    except Exception as exc:      # pragma: no cover - depends on the installed STARRED version
+        print('field distortion vectors skipped:', exc)
+
     # --- photometry: loss and gradient of the deconvolution Loss at fixed parameters (star_photometry.py:66-111)
     F, S = 2, 3
     p = synthetic.make_phot_frames(F, S, n, k, seed=42)

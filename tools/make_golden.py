@@ -47,4 +47,25 @@ W = rng.uniform(0.5, 2.0, (4 + 1, nu, nu)).astype(np.float32)
 L, g = sm.psf_loss_grad(s_fixed, b, a, x0, y0, data, weight, W, n, k, 0.7, 1.3)
 np.savez_compressed(out / 'psf_n16_k2.npz', kind='psf', n=n, k=k, s_fixed=s_fixed, b=b, a=a, x0=x0, y0=y0, data=data,
                     weight=weight, W=W, lam_scales=0.7, lam_hf=1.3, loss=L, grad_b=g[0], grad_s=np.stack(g[1:], -1))
+
+# ---- PSF loss / gradient with field distortion (dyadic coefficients and positions: every sample position of the bilinear
+#      resampling is exactly representable, so the vector is well posed in float32 and float64 alike)
+rng2 = np.random.default_rng(20260218)
+n, k, N = 16, 2, 4
+nu = n * k
+d = synthetic.make_psf_frames(1, N, n, k, seed=44)
+sc = d['data'].max() / 100
+data = (d['data'][0] / sc).astype(np.float32)
+weight = (d['masks'][0] / (d['noisemap'][0] / sc) ** 2).astype(np.float32)
+s_fixed = sm.moffat_image(3.0, 3.3, 0.3, 2.9, n, k).numpy().astype(np.float32)
+b = (1e-4 * rng2.standard_normal((nu, nu))).astype(np.float32)
+a = ((data * d['masks'][0]).sum((-1, -2))).astype(np.float32)
+x0, y0 = rng2.uniform(-0.6, 0.6, N).astype(np.float32), rng2.uniform(-0.6, 0.6, N).astype(np.float32)
+W = rng2.uniform(0.5, 2.0, (5, nu, nu)).astype(np.float32)
+theta = (rng2.integers(-7, 8, 6) / 128.0).astype(np.float32)
+xy = (rng2.integers(-8, 9, (N, 2)) / 16.0).astype(np.float32)
+L, g = sm.psf_loss_grad(s_fixed, b, a, x0, y0, data, weight, W, n, k, 0.7, 1.3, theta=theta, xy=xy)
+np.savez_compressed(out / 'psfdist_n16_k2.npz', kind='psfdist', n=n, k=k, s_fixed=s_fixed, b=b, a=a, x0=x0, y0=y0, data=data,
+                    weight=weight, W=W, lam_scales=0.7, lam_hf=1.3, theta=theta, xy=xy, loss=L, grad_b=g[0],
+                    grad_s=np.stack(g[1:4], -1), grad_theta=g[4])
 print('wrote', sorted(p.name for p in out.glob('*.npz')))
