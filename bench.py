@@ -394,8 +394,11 @@ def deconv_section(world, rank, local, group, T, steps, warmup, comm='p2p', cpu_
     _lib.profile_enable(False)
     ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
     tt = torch.tensor([ms], device='cuda')
+    prof_ranks = None
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        prof_ranks = [None] * world                   # per-rank kernel times: shows which rank the others wait for in the update kernel
+        dist.all_gather_object(prof_ranks, {kn: round(v['ms'] / max(v['launches'], 1), 4) for kn, v in prof.items()})
     ms = float(tt.item())
     ctas = int(_lib.lib.lcb_deconv_get_cluster(jd.handle))
     jd.close()
@@ -420,6 +423,8 @@ def deconv_section(world, rank, local, group, T, steps, warmup, comm='p2p', cpu_
                         "algorithmic_flop_per_iteration": flop_it, "flop_per_iteration_survey_formula": flop_survey,
                         "note": "flops of the decimation-folded polyphase convolution the kernel executes (the restated SURVEY 8d formula: 4x fewer "
                                 "MACs than the full-resolution count, same result); per-rank share over the mean k_deconv_epoch launch time"}}
+    if prof_ranks is not None:
+        res["kernel_ms_per_launch_by_rank"] = prof_ranks
     if cpu_baseline:
         res["cpu_baseline"] = deconv_cpu_baseline(t, scale)
     return res

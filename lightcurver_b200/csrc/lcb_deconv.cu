@@ -757,18 +757,15 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
     __threadfence();
     const int seq = (D.cm.world > 1) ? ((seq_arg < 0) ? D.ictl[1] : seq_arg) : 0;
     const int Wn = D.cm.world, parity = seq & 1, nu2 = nu * nu;
-    const bool own_only = (flags & 16) != 0;      // timing experiment (LCB_DECONV_PUSH_LOCAL=1): sums go to the own slot only (WRONG results)
     auto emit = [&](int i, float v) {
         if (seq == 0) D.red[i] = v;
-        else for (int r = 0; r < Wn; ++r) { if (own_only && r != D.cm.rank) continue; D.cm.slots[r][((size_t)parity * Wn + D.cm.rank) * D.tot_pad + i] = v; }
+        else for (int r = 0; r < Wn; ++r) D.cm.slots[r][((size_t)parity * Wn + D.cm.rank) * D.tot_pad + i] = v;
     };
     // four consecutive entries (i a multiple of 4): ONE 16-byte store per peer instead of four 4-byte stores at a 16-byte stride
     auto emit4 = [&](int i, float4 v) {
         if (seq == 0) *reinterpret_cast<float4*>(D.red + i) = v;
-        else for (int r = 0; r < Wn; ++r) {
-            if (own_only && r != D.cm.rank) continue;
+        else for (int r = 0; r < Wn; ++r)
             *reinterpret_cast<float4*>(D.cm.slots[r] + ((size_t)parity * Wn + D.cm.rank) * D.tot_pad + i) = v;
-        }
     };
     const int cnt = (vhi - vlo) * nu;
     // sums planes src[p * nu2 + i], p = 0 .. np_-1 (in order) over the pixels of the band.  The walk is bound by L2 latency, so
@@ -2089,8 +2086,7 @@ struct DeconvRun {
 
 static int run_iteration(DeconvHandle* H, const lcb_fit_opts* opt, int it_arg, int seq_arg) {
     int r;
-    static const int dbg = (getenv("LCB_DECONV_PUSH_LOCAL") && getenv("LCB_DECONV_PUSH_LOCAL")[0] == '1') ? 16 : 0;
-    if ((r = launch_starlet(H)) || (r = launch_epoch(H, 4 | dbg, seq_arg)) ||
+    if ((r = launch_starlet(H)) || (r = launch_epoch(H, 4, seq_arg)) ||
         (r = launch_update(H, it_arg, opt->n_iter, opt->lr, opt->schedule, seq_arg, nullptr, nullptr, nullptr))) return r;
     return LCB_OK;
 }
