@@ -195,8 +195,9 @@ def workload_string(F, N, n, k, cfg_name='cfg2'):
 def run_reference(args):
     """Reference arm: the CPU restatement of the reference's path (oracle port; STARRED itself is not installable here) on the
     box's host cores, on OUR arm's config / metric / unit.  Every step is the SAME bounded sample as the `cpu_baseline` of our arm
-    (`cpu_baseline_parallel`: one frame of the workload per host core, one worker process per core, <= 20 / 400 / 400 iterations
-    of the three stages scaled linearly to 100 / 3000 / 2000); at most three timed steps so that the run ends within a few minutes."""
+    (`cpu_baseline_parallel`: one single-threaded worker process per host core, 8 frames of the workload batched per worker,
+    <= 20 / 200 / 200 iterations of the three stages scaled linearly to 100 / 3000 / 2000); at most three timed steps so that the
+    run ends within a few minutes."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
