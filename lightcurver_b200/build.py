@@ -67,6 +67,11 @@ if __name__ == '__main__':
     if '--timers' in sys.argv:
         p = build(extra_flags=['-DLCB_PHASE_TIMERS'], out=HERE / 'liblcb_timers.so')
         build(force=True)
+    elif '--variant' in sys.argv:
+        # python -m lightcurver_b200.build --variant NAME -DFLAG ... -> liblcb_NAME.so next to the default library (A/B timing)
+        i = sys.argv.index('--variant')
+        p = build(extra_flags=[a for a in sys.argv[i + 2:] if a.startswith('-')], out=HERE / f'liblcb_{sys.argv[i + 1]}.so')
+        build(force=True)
     else:
         p = build(verbose='-v' in sys.argv, force='-f' in sys.argv, ptxas_info='--ptxas' in sys.argv)
     print(p)

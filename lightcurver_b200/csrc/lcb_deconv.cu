@@ -301,6 +301,20 @@ __device__ __forceinline__ float block_sum(float v, float* red, int tid) {
     return s;
 }
 
+#ifdef LCB_DC_TIMERS
+// development build only (python -m lightcurver_b200.build --dc-timers): clock64 stamps of the phases of k_deconv_epoch per CTA
+#define DC_TIM_SLOTS 16
+#define DC_TIM_CTAS 2048
+__device__ long long g_dc_tim[DC_TIM_CTAS][DC_TIM_SLOTS];
+#define DC_STAMP(k) { if (tid == 0 && blockIdx.x < DC_TIM_CTAS) g_dc_tim[blockIdx.x][k] = clock64() - dc_t0; }
+extern "C" int lcb_debug_dc_timers(long long* out, int ctas) {
+    if (ctas > DC_TIM_CTAS) ctas = DC_TIM_CTAS;
+    return cudaMemcpyFromSymbol(out, g_dc_tim, (size_t)ctas * DC_TIM_SLOTS * sizeof(long long)) == cudaSuccess ? 0 : -1;
+}
+#else
+#define DC_STAMP(k)
+#endif
+
 // ---------------------------------------------------------------- per-epoch kernel (cluster of CS CTAs)
 // flags: 1 = write the model image; 2 = propagate the weights instead of the residuals (noise weights); 4 = fused reduction:
 // the LAST cluster to finish a band of rows sums that band of dL/dh over the local epochs (fixed order) into red[] -- or, with
@@ -315,6 +329,10 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
     extern __shared__ __align__(16) float sm[];
     const int tid = threadIdx.x;
     const int crank = (int)(blockIdx.x % CS);     // == cl.block_rank() for cluster dims (CS,1,1)
+#ifdef LCB_DC_TIMERS
+    const long long dc_t0 = clock64();
+    if (tid == 0 && blockIdx.x < DC_TIM_CTAS) { unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); g_dc_tim[blockIdx.x][14] = (long long)gt; }
+#endif
     const int e = blockIdx.x / CS;
     constexpr int k = K, kk = K * K;
     const int n = D.n, nu = D.nu, M = D.M, NA = D.NA, A0 = D.A0, G = D.G;
@@ -346,18 +364,34 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
     float* ep = D.ep + (size_t)e * np;
     float upd_p = 0.f, upd_mu = 0.f, upd_nv = 0.f;
     bool upd = false;
+    // every global load of the prologue is issued up front (unconditionally: one L2 round trip instead of a chain of three),
+    // the planes are cleared while the values are in flight
+    float p_in = 0.f, mu_in = 0.f, nv_in = 0.f, g_in = 0.f, pend = 0.f, c_cs = 0.f, c_lr = 0.f, c_b1 = 0.f, c_b2 = 0.f;
+    float fu_k = 0.f, fu_a = 0.f, fu_b = 0.f;
     if (tid < np) {
-        float p = ep[tid];
-        if (D.ctl[4] != 0.f && !noise) {
+        p_in = ep[tid];
+        pend = D.ctl[4]; c_cs = D.ctl[0]; c_lr = D.ctl[1]; c_b1 = D.ctl[2]; c_b2 = D.ctl[3];
+        mu_in = D.ep_mu[(size_t)e * np + tid]; nv_in = D.ep_nu[(size_t)e * np + tid]; g_in = D.ep_g[(size_t)e * np + tid];
+        if (tid < M && D.lam_fu != 0.f) { fu_k = D.fu[tid]; fu_a = D.fu[DC_MMAX + tid]; fu_b = D.fu[2 * DC_MMAX + tid]; }
+    }
+    // the folded PSF of the epoch (kk x NA x NAp floats, ~21 KB at cfg4) comes in through the TMA unit: one thread arms an
+    // mbarrier and issues ONE bulk copy; the other warps go on building f, and wait just before the forward pass
+    __shared__ __align__(8) unsigned long long s_bar;
+    if (tid == 0) lcb_mbar_init(&s_bar, 1);
+    {   // zero the planes (the gaps between rows are the halos)
+        float4* z = reinterpret_cast<float4*>(sm + L.oF);
+        for (int i = tid; i < (L.zero_end - L.oF) / 4; i += DC_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (tid < np) {
+        float p = p_in;
+        if (pend != 0.f && !noise) {
             const bool is_free = (tid < M) ? D.free_a : (tid < M + 2) ? D.free_d : D.free_mean;
             if (is_free) {
-                const BeliefCoef bc = {D.ctl[1], D.cv.b1, D.cv.b2, 1.f - D.cv.b1, 1.f - D.cv.b2, D.ctl[2], D.ctl[3],
-                                       D.cv.eps, D.cv.eps_root};
-                float mu = D.ep_mu[(size_t)e * np + tid], nv = D.ep_nu[(size_t)e * np + tid];
-                float g = D.ep_g[(size_t)e * np + tid];
+                const BeliefCoef bc = {c_lr, D.cv.b1, D.cv.b2, 1.f - D.cv.b1, 1.f - D.cv.b2, c_b1, c_b2, D.cv.eps, D.cv.eps_root};
+                float mu = mu_in, nv = nv_in, g = g_in;
                 if (tid < M && D.lam_fu != 0.f)      // flux-uniformity gradient from the global statistics of the last evaluation
-                    g += D.fu[DC_MMAX + tid] * (p - D.fu[tid]) - D.fu[2 * DC_MMAX + tid];
-                belief_update(bc, D.ctl[0] * g, p, mu, nv);
+                    g += fu_a * (p - fu_k) - fu_b;
+                belief_update(bc, c_cs * g, p, mu, nv);
                 upd = true; upd_p = p; upd_mu = mu; upd_nv = nv;
             }
         }
@@ -369,22 +403,13 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
         remr[tid] = (CS > 1) ? (float*)cl.map_shared_rank(rsm, tid) : rsm;
         remflo[tid] = bc.flo; remrlo[tid] = bc.rlo; remrhi[tid] = bc.rhi;
     }
-    // the folded PSF of the epoch (kk x NA x NAp floats, ~21 KB at cfg4) comes in through the TMA unit: one thread arms an
-    // mbarrier and issues ONE bulk copy; the other warps go on zeroing the planes and building f, and wait just before the
-    // forward pass
-    __shared__ __align__(8) unsigned long long s_bar;
-    if (tid == 0) lcb_mbar_init(&s_bar, 1);
-    __syncthreads();
+    __syncthreads();                              // (remote writes of r only start after cluster barrier #0 below)
     if (tid == 0) {
         const unsigned bytes = (unsigned)(kk * NA * NAp) * 4u;
         lcb_mbar_expect_tx(&s_bar, bytes);
         lcb_bulk_g2s(Ssm, D.S + (size_t)e * kk * NA * NAp, bytes, &s_bar);
     }
-    {   // zero the planes (the gaps between rows are the halos)
-        float4* z = reinterpret_cast<float4*>(sm + L.oF);
-        for (int i = tid; i < (L.zero_end - L.oF) / 4; i += DC_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    __syncthreads();                              // (remote writes of r only start after cluster barrier #0 below)
+    DC_STAMP(0)
 
     const int j0 = (D.P - 1) / 2;
     const float delta = 0.5f * (float)(D.P - 1) - (float)j0;
@@ -412,7 +437,8 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
     // ---- f = warp(h) + point sources in polyphase layout: every CTA builds the rows of its OWN band, then copies the
     //      other rows its forward pass reads from the CTAs that own them (distributed shared memory)
     if (!noise && own > 0) {
-        for (int i = tid; i < own * k * nu; i += DC_THREADS) {
+#pragma unroll 4
+        for (int i = tid; i < own * k * nu; i += DC_THREADS) {     // (unrolled: the L2 loads of four pixels in flight)
             const int v = Y0 * k + i / nu, u = i % nu;
             float val = 0.f;
             if (D.h != nullptr) {
@@ -439,8 +465,10 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
             __syncthreads();
         }
     }
+    DC_STAMP(1)
     if (CS > 1) {
         cl.sync();                                // #0: planes cleared and own bands of f complete in every CTA
+        DC_STAMP(2)
         if (!noise && own > 0) {
             const int nq = n / 4 + 1;             // float4 per row (the tail reads into the zero gap / shift slack)
             const int nrow = (fhi - flo) - own;
@@ -457,10 +485,12 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
         __syncthreads();
     }
 
+    DC_STAMP(3)
     // ---- forward: m = mean + 1/k^2 sum_ph corr(f_ph, S_ph);  r = w (m - d).  A task = XB outputs of one row for
     //      one slice of the NA kernel rows (SPLIT slices on adjacent lanes, summed with shuffles) so that a narrow
     //      band still gives every thread a task.
     lcb_mbar_wait(&s_bar, 0);                     // folded PSF landed in shared memory
+    DC_STAMP(4)
     const float dscale = D.cv.mean ? 1.f / (float)kk : 1.f;
     const float* dat = D.data + (size_t)e * n * n;
     const float* wgt = D.weight + (size_t)e * n * n;
@@ -470,6 +500,68 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
         for (int i = tid; i < n * n; i += DC_THREADS) {
             const int Y = i / n;
             if (Y >= rlo && Y < bd.rhi) rsm[(Y - rlo) * ld + i % n] = __ldg(wgt + i);
+        }
+    } else if (own > 0 && (own * nxb) % 32 == 0 && own * nxb < DC_THREADS && DC_THREADS % (own * nxb) == 0 &&
+               (n & 3) == 0 && ld >= n + 4 && own * (n + 4) <= 2 * DC_MMAX * 4 * DC_EXT) {
+        // Narrow band (fewer (row, x-block) tasks than threads): the NA kernel rows are split over WHOLE WARPS, so that every tap
+        // load of a warp is one broadcast wavefront (with the slices on lane groups of a warp each quarter-warp fetched its own
+        // kernel row: 96 shared-memory wavefronts per 264 FFMA, the forward pass ran at the shared-memory bandwidth).  The slices
+        // add their partial sums in slice order into a small plane (the scratch of the pts-source term, dead until later):
+        // deterministic.  The epilogue then runs on all threads, coalesced along a row, and the band of r goes to the other CTAs of
+        // the cluster as 16-byte stores (it was one 4-byte remote store per output and destination, issued by a quarter of the
+        // threads).
+        const int ntk = own * nxb, SPL = DC_THREADS / ntk;
+        const int ias = (NA + SPL - 1) / SPL;
+        const int ldm = n + 4;
+        float* msum = ext;                          // [own][n + 4]
+        const int s = tid / ntk, t2 = tid % ntk;
+        const int Y = Y0 + t2 % own, X0 = (t2 / own) * DC_XB;
+        float acc[DC_XB];
+#pragma unroll
+        for (int x = 0; x < DC_XB; ++x) acc[x] = 0.f;
+        {
+            const int ia0 = s * ias, ia1 = min(NA, ia0 + ias);
+            const int ja = max(ia0, -(Y + A0)), jb = min(ia1, n - (Y + A0));
+            for (int ph = 0; ph < kk; ++ph) {
+                const float* pl = fpl + ph * pst + X0 + A0 + (Y + A0 - flo) * ld;
+                const float* Sph = Ssm + ph * NA * NAp;
+                for (int ia = ja; ia < jb; ++ia) corr_line(pl + ia * ld, Sph + ia * NAp, NA, NA8, acc);
+            }
+        }
+        float4* mrow = reinterpret_cast<float4*>(msum + (Y - Y0) * ldm + X0);
+        for (int turn = 0; turn < SPL; ++turn) {
+            if (s == turn) {
+                float4 lo = make_float4(acc[0], acc[1], acc[2], acc[3]), hi = make_float4(acc[4], acc[5], acc[6], acc[7]);
+                if (turn > 0) {
+                    const float4 a = mrow[0], b = mrow[1];
+                    lo.x += a.x; lo.y += a.y; lo.z += a.z; lo.w += a.w; hi.x += b.x; hi.y += b.y; hi.z += b.z; hi.w += b.w;
+                }
+                mrow[0] = lo; mrow[1] = hi;
+            }
+            __syncthreads();
+        }
+        for (int i = tid; i < own * n; i += DC_THREADS) {
+            const int Yl = i / n, X = i - Yl * n, Yg = Y0 + Yl;
+            const float mval = fmaf(dscale, msum[Yl * ldm + X], mean);
+            const float d = __ldg(dat + Yg * n + X), w = __ldg(wgt + Yg * n + X);
+            const float diff = mval - d, r = w * diff;
+            rsm[(Yg - rlo) * ld + X] = r;
+            loss = fmaf(r, diff, loss);
+            gmean += r;
+            if (want_model) D.model[(size_t)e * n * n + Yg * n + X] = mval;
+        }
+        if (CS > 1) {
+            __syncthreads();
+            // rows start at a 16-byte aligned address plus the same shift in every CTA: copy whole aligned quads (the floats before
+            // and after the n values of a row are zeros of the gap on both sides)
+            const int nq = (n + L.shR + 3) / 4;
+            const float* srcb = rsm - L.shR;
+            for (int i = tid; i < (CS - 1) * own * nq; i += DC_THREADS) {
+                const int q = i % nq, Yl = (i / nq) % own, cc = i / (nq * own);
+                const int c = cc + (cc >= crank ? 1 : 0), Yg = Y0 + Yl;
+                if (Yg >= remrlo[c] && Yg < remrhi[c])
+                    reinterpret_cast<float4*>(remr[c] - L.shR + (Yg - remrlo[c]) * ld)[q] = reinterpret_cast<const float4*>(srcb + (Yg - rlo) * ld)[q];
+            }
         }
     } else {
         int SPLIT = 1;
@@ -515,8 +607,11 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
                 }
             }
         }
+    
     }
+    DC_STAMP(5)
     cl.sync();                                    // #1: r complete in every CTA; all CTAs have read the old parameters
+    DC_STAMP(6)
     if (upd && crank == 0) {
         ep[tid] = upd_p; D.ep_mu[(size_t)e * np + tid] = upd_mu; D.ep_nu[(size_t)e * np + tid] = upd_nv;
     }
@@ -538,6 +633,7 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
             if (X0 + x < n) fpl[ph * pst + (Y - flo) * ld + X0 + x] = (noise ? dscale * dscale : dscale) * acc[x];
     }
     __syncthreads();
+    DC_STAMP(7)
     const int vlo = Y0 * k, vhi = Y1 * k;         // rows of f whose dL/df lives in this CTA
     const float sc = (D.cv.half == 0.5f) ? 1.f : 2.f;
     const int warp = tid >> 5, lane = tid & 31;
@@ -567,6 +663,7 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
     // ---- shift gradient through the warp: dL/dd = sum_p dL/df[p] * grad h(q(p)) . dq/dd   (own rows)
     float gwx = 0.f, gwy = 0.f;
     if (D.free_d && !noise && D.h != nullptr) {
+#pragma unroll 4
         for (int i = tid; i < (vhi - vlo) * nu; i += DC_THREADS) {
             const int v = vlo + i / nu, u = i % nu;
             float qu, qv;
@@ -584,12 +681,19 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
             gwy = fmaf(df, -(float)k * (sa * dhu + ca * dhv), gwy);
         }
     }
-    loss = block_sum(loss, red, tid);
-    gmean = block_sum(gmean, red, tid);
-    gwx = block_sum(gwx, red, tid);
-    gwy = block_sum(gwy, red, tid);
-    if (tid == 0) { cp0[crank * 32] = loss; cp0[crank * 32 + 1] = gmean; cp0[crank * 32 + 2] = gwx; cp0[crank * 32 + 3] = gwy; }
+    {   // four block sums with one pair of barriers (warp order fixed: deterministic)
+        __shared__ float red4[(DC_THREADS / 32) * 4];
+        loss = warp_sum(loss); gmean = warp_sum(gmean); gwx = warp_sum(gwx); gwy = warp_sum(gwy);
+        if (lane == 0) { red4[warp * 4] = loss; red4[warp * 4 + 1] = gmean; red4[warp * 4 + 2] = gwx; red4[warp * 4 + 3] = gwy; }
+        __syncthreads();
+        if (tid < 4) {
+            float s4 = 0.f;
+            for (int w = 0; w < DC_THREADS / 32; ++w) s4 += red4[w * 4 + tid];
+            cp0[crank * 32 + tid] = s4;
+        }
+    }
 
+    DC_STAMP(8)
     // ---- pts-source regulariser (rank 0): lam * sum_x W_0[x] |alpha_0(p_e)[x]|, p_e = point-source channel of the
     //      epoch, alpha_0 = first starlet scale.  The Gaussians are separable, so alpha_0(g_m)(v,u) =
     //      g_y(v) g_x(u) - (B g_y)(v) (B g_x)(u) with B the edge-replicated 5-tap B3 filter; by linearity
@@ -618,12 +722,14 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
             ex[3 * DC_EXT + t] = bd;
         }
         __syncthreads();
-        if (warp < M) {
-            const int m = warp;
+        // H warps per source (H * M <= 8): warp w walks every H-th group of 32 pixels of the window of source w % M
+        const int H = (M > 0) ? (DC_THREADS / 32) / M : 0;
+        if (warp < H * M) {
+            const int m = warp % M;
             float pl = 0.f, pa[DC_MMAX], pu[DC_MMAX], pv[DC_MMAX];
 #pragma unroll
             for (int q = 0; q < DC_MMAX; ++q) pa[q] = pu[q] = pv[q] = 0.f;
-            for (int i = lane; i < GEX * GEX; i += 32) {
+            for (int i = lane + 32 * (warp / M); i < GEX * GEX; i += 32 * H) {
                 const int v = iwin[DC_MMAX + m] - 2 + i / GEX, u = iwin[m] - 2 + i % GEX;
                 if (v < 0 || v >= nu || u < 0 || u >= nu) continue;
                 bool dup = false;                  // pixel already counted by a source of lower index
@@ -657,15 +763,17 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
                 for (int q = 0; q < DC_MMAX; ++q) { pa[q] = fmaf(T, ca_[q], pa[q]); pu[q] = fmaf(T, cu_[q], pu[q]); pv[q] = fmaf(T, cv_[q], pv[q]); }
             }
             pl = warp_sum(pl);
-            if (lane == 0) ptsacc[m * 32] = pl;
+            if (lane == 0) ptsacc[warp * 32] = pl;
 #pragma unroll
             for (int q = 0; q < DC_MMAX; ++q) {
                 const float s0 = warp_sum(pa[q]), s1 = warp_sum(pu[q]), s2 = warp_sum(pv[q]);
-                if (lane == 0 && q < M) { ptsacc[m * 32 + 1 + 3 * q] = s0; ptsacc[m * 32 + 2 + 3 * q] = s1; ptsacc[m * 32 + 3 + 3 * q] = s2; }
+                if (lane == 0 && q < M) { ptsacc[warp * 32 + 1 + 3 * q] = s0; ptsacc[warp * 32 + 2 + 3 * q] = s1; ptsacc[warp * 32 + 3 + 3 * q] = s2; }
             }
         }
     }
+    DC_STAMP(9)
     cl.sync();                                    // #2: dL/df bands and partial sums complete
+    DC_STAMP(10)
     float* epg = D.ep_g + (size_t)e * np;
     if (crank == 0 && tid == 0 && !noise) {
         float ls = 0.f, gm = 0.f, wx = 0.f, wy = 0.f, ga[DC_MMAX], gu[DC_MMAX], gv[DC_MMAX];
@@ -676,11 +784,12 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
             for (int m = 0; m < M; ++m) { ga[m] += q[4 + 3 * m]; gu[m] += q[5 + 3 * m]; gv[m] += q[6 + 3 * m]; }
         }
         float ploss = 0.f;
+        const int NWP = (M > 0) ? ((DC_THREADS / 32) / M) * M : 0;   // warps that took part in the pts-source term
         float gdx = sc * wx, gdy = sc * wy;
         for (int m = 0; m < M; ++m) {
             float pa = 0.f, pu = 0.f, pv = 0.f;
             if (lam_pts != 0.f)
-                for (int w = 0; w < M; ++w) { pa += ptsacc[w * 32 + 1 + 3 * m]; pu += ptsacc[w * 32 + 2 + 3 * m]; pv += ptsacc[w * 32 + 3 + 3 * m]; }
+                for (int w = 0; w < NWP; ++w) { pa += ptsacc[w * 32 + 1 + 3 * m]; pu += ptsacc[w * 32 + 2 + 3 * m]; pv += ptsacc[w * 32 + 3 + 3 * m]; }
             const float a = par[m];
             const float GU = a * (sc * gu[m] + pu), GV = a * (sc * gv[m] + pv);
             gdx += (float)k * GU; gdy += (float)k * GV;
@@ -688,7 +797,7 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
             D.gc[(size_t)e * 2 * M + M + m] = (float)k * (-sa * GU + ca * GV);
             epg[m] = sc * ga[m] + pa;
         }
-        if (lam_pts != 0.f) for (int w = 0; w < M; ++w) ploss += ptsacc[w * 32];
+        if (lam_pts != 0.f) for (int w = 0; w < NWP; ++w) ploss += ptsacc[w * 32];
         epg[M] = gdx; epg[M + 1] = gdy; epg[M + 2] = sc * gm;
         D.eloss[e] = D.cv.half * ls + ploss;
     }
@@ -708,6 +817,7 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
             float wx1 = geo.tx - itx, wy1 = geo.ty - ity, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
             if (noise) { wx0 *= wx0; wx1 *= wx1; wy0 *= wy0; wy1 *= wy1; }
             const int iu = (int)itx, iv = (int)ity;
+#pragma unroll 4
             for (int i = tid; i < (vhi - vlo) * nu; i += DC_THREADS) {
                 const int qv_i = vlo + i / nu, qu_i = i % nu;
                 const int pv = qv_i + iv, pu = qu_i + iu;
@@ -740,7 +850,12 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
             }
         }
     }
+    DC_STAMP(11)
     cl.sync();                                    // #3: no CTA leaves while its shared memory may still be read
+    DC_STAMP(12)
+#ifdef LCB_DC_TIMERS
+    if (tid == 0 && blockIdx.x < DC_TIM_CTAS) { unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); g_dc_tim[blockIdx.x][15] = (long long)gt; g_dc_tim[blockIdx.x][13] = 0; }
+#endif
     if (!(flags & 4)) return;
 
     // ---- fused reduction over the local epochs (replaces k_deconv_reduce inside lcb_deconv_run), two levels so that no CTA
@@ -872,6 +987,7 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
             if (lane == 0) emit(i, sacc);
         }
     }
+    DC_STAMP(13)
     __threadfence_system();
     __syncthreads();
     if (tid == 0) {

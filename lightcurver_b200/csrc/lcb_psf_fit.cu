@@ -370,6 +370,16 @@ __device__ __forceinline__ float starlet_reg_fast(const float* __restrict__ Bp, 
     return reg;
 }
 
+// shared scratch of the two fast starlet routines: starlet_reg_fast keeps column / row chunk sums and the folded extras
+// ([2 GROUPS][NU] + [NU][NU/8] + [NU][2]); starlet_reg_fast4 quad sums with a padded leading dimension and the extras
+// ([NU][NU/4 + 1] + [NU][2] -- 64 floats more than the first form on the 64-wide grid: until round 2 its last 32 rows of
+// extras spilled into the first zero-halo row of the s plane, read only by the outermost Gaussian tap of a star shifted
+// by two pixels)
+__host__ __device__ constexpr int lcb_starlet_aux_floats(int nu, int nth) {
+    const int a = 2 * (nth / nu) * nu + nu * nu / 8 + 2 * nu, b = nu * (nu / 4 + 1) + 2 * nu;
+    return a > b ? a : b;
+}
+
 // ---------------------------------------------------------------- the kernel
 // NS > 0: compile-time stamp side (fast path, requires NS*K in {32, 64}); NS == 0: runtime sizes.
 // Fast path: 256-thread CTAs sized (128 registers, <= 113 KB of shared memory) so that TWO frames are resident
@@ -411,7 +421,7 @@ __global__ void __launch_bounds__(FIT_THREADS(K, NS), ((NS) > 0 ? 2 : 1)) k_psf_
     float* Vbar = rT + (n + HB) * ldt + HB * ldb;       // [HB + n + HB][ldb]
     float* aux = Vbar + (n + HB) * ldb;                 // FAST: starlet chunk sums (see starlet_reg_fast)
     const int scr_count = (int)(aux - scr);
-    float* planes = aux + (FAST ? (2 * (NT / (FAST ? NS * K : 1)) * nu + nu * nu / 8 + 2 * nu) : 0);
+    float* planes = aux + (FAST ? lcb_starlet_aux_floats(nu, NT) : 0);
     if constexpr (!FAST) {
         if (!A.planes_in_smem) planes = A.work + (size_t)f * A.work_per_frame + (size_t)J * pp;
     }
@@ -831,7 +841,7 @@ size_t lcb_psf_fit_smem_small(int n, int nu, int Nmax) {
 size_t lcb_psf_fit_smem_fast_extra(int n, int nu, int J) {
     const size_t halos = (size_t)16 * (nu + 2 * (n + 1) + (n + 1) + (nu + 1)) * 4;
     const size_t signs = (nu == 64) ? (size_t)J * nu * nu / 4 : (size_t)J * nu * nu;
-    return (size_t)3 * nu * nu * 4 + signs + (size_t)(2 * (256 / nu) * nu + nu * nu / 8 + 2 * nu) * 4 + halos;
+    return (size_t)3 * nu * nu * 4 + signs + (size_t)lcb_starlet_aux_floats(nu, 256) * 4 + halos;
 }
 
 bool lcb_psf_fit_has_fast(int n, int k, int G) {

@@ -40,7 +40,10 @@ def _problem(E, n, k, M, P_data, seed, alpha_on=True, h_sigma=2.5, h_peak=0.5):
                                                       (3, 16, 2, 2, 16, 1, True), (3, 16, 2, 2, 12, 4, False), (2, 32, 2, 3, 16, 8, True),
                                                       (2, 32, 2, 3, 16, 8, False), (3, 20, 2, 2, 12, 4, True), (2, 8, 4, 1, 8, 2, True),
                                                       # BASELINE cfg4 shape (n = 64, k = 2, P = 64, M = 4) at both cluster sizes the bench uses
-                                                      (4, 64, 2, 4, 32, 4, False), (4, 64, 2, 4, 32, 8, False), (2, 64, 2, 4, 32, 8, True)])
+                                                      (4, 64, 2, 4, 32, 4, False), (4, 64, 2, 4, 32, 8, False), (2, 64, 2, 4, 32, 8, True),
+                                                      # cluster sizes that do not divide the stamp (uneven bands, the last one shorter)
+                                                      (3, 20, 2, 2, 12, 3, True), (2, 64, 2, 4, 32, 6, True), (3, 64, 2, 4, 32, 5, False),
+                                                      (2, 64, 2, 4, 32, 7, False)])
 def test_deconv_loss_grad_parity(cuda_device, E, n, k, M, npsf, cs, alpha_on):
     """Every cluster size (CTAs per epoch) of the per-epoch kernel, rotated and purely translated epochs, all loss terms."""
     from lightcurver_b200.processes.roi_modelling import JointDeconvolution

@@ -50,6 +50,21 @@ def main():
             used = int(_lib.lib.lcb_deconv_get_cluster(jd.handle))
             parts = ' '.join(f"{kn.replace('k_deconv_', '')}={v['ms'] / max(v['launches'], 1):.3f}" for kn, v in sorted(prof.items()))
             print(f"E={E:4d} cs={cs} (used {used}) {ms:.3f} ms/it  {1e3 / ms:7.1f} it/s   [{parts}]", flush=True)
+            if hasattr(_lib.lib, 'lcb_debug_dc_timers'):     # -DLCB_DC_TIMERS build: phase stamps of the LAST launch of k_deconv_epoch
+                import ctypes
+                nc = E * used
+                buf = np.zeros((nc, 16), np.int64)
+                _lib.lib.lcb_debug_dc_timers.argtypes = [ctypes.c_void_p, ctypes.c_int]
+                _lib.lib.lcb_debug_dc_timers(buf.ctypes.data, nc)
+                names = ['zero', 'fbuild', 'cl0', 'halo', 'tma', 'fwd', 'cl1', 'adj', 'grads', 'ptsreg', 'cl2', 'warpT', 'cl3', 'tail']
+                d = np.diff(np.concatenate([np.zeros((nc, 1), np.int64), buf[:, :13]], axis=1), axis=1)
+                med, mx = np.median(d, axis=0), d.max(axis=0)
+                print('      cycles median/max: ' + ' '.join(f"{nm}={int(a)}/{int(b)}" for nm, a, b in zip(names, med, mx)))
+                tail = buf[:, 13][buf[:, 13] > 0]
+                span = (buf[:, 15].max() - buf[:, 14].min()) / 1e3
+                start_skew = (buf[:, 14].max() - buf[:, 14].min()) / 1e3
+                print(f"      end-of-body total median {int(np.median(buf[:, 12]))} max {int(buf[:, 12].max())} cycles; tail CTAs {tail.size}: "
+                      f"{[int(x) for x in np.sort(tail)[-4:]]}; grid span {span:.1f} us, start skew {start_skew:.1f} us", flush=True)
             jd.close()
 
 
