@@ -33,6 +33,7 @@
 #include "lcb_starlet.cuh"
 #include <cooperative_groups.h>
 #include <vector>
+#include <type_traits>
 
 namespace cg = cooperative_groups;
 
@@ -249,6 +250,135 @@ __device__ __forceinline__ void conv_line_T(const float* __restrict__ rr, const 
         ld8(tap, sr + NA8 - 8 - 8 * b);
         sq(tap);
         blk8<true>(acc, tap, lo, hi);
+    }
+}
+
+// ---------------------------------------------------------------- the same two lines with XB outputs per thread
+// With 8 outputs per thread a block of 8 taps costs 2 + 2 LDS.128 for 64 FFMA: the passes run at the shared-memory bandwidth
+// (window loads are 4 wavefronts each).  XB = 16 halves the loads per FFMA (2 + 2 LDS.128 for 128 FFMA): FP32-issue bound.
+// The window is a register array of XB + 8 floats that slides by 8 per block.
+template <int XB>
+__device__ __forceinline__ void ldx(float* d, const float* __restrict__ p) {
+#pragma unroll
+    for (int i = 0; i < XB / 4; ++i) {
+        const float4 a = reinterpret_cast<const float4*>(p)[i];
+        d[4 * i] = a.x; d[4 * i + 1] = a.y; d[4 * i + 2] = a.z; d[4 * i + 3] = a.w;
+    }
+}
+
+template <int XB>
+__device__ __forceinline__ void corr_line_x(const float* __restrict__ fr, const float* __restrict__ sr, int NA, int NA8, float (&acc)[XB]) {
+    float w[XB + 8], tap[8];
+    ldx<XB>(w, fr);
+#pragma unroll 1
+    for (int t0 = 0; t0 < NA8; t0 += 8) {
+        ldx<8>(w + XB, fr + t0 + XB);
+        ldx<8>(tap, sr + t0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int x = 0; x < XB; ++x) acc[x] = fmaf(tap[j], w[j + x], acc[x]);
+#pragma unroll
+        for (int i = 0; i < XB; ++i) w[i] = w[i + 8];
+    }
+    const int R = NA - NA8;                            // tail taps: aligned loads, only the real taps are multiplied
+    if (R > 0) {
+        ldx<8>(tap, sr + NA8);
+        if (R > 1) ldx<8>(w + XB, fr + NA8 + XB);
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            if (j < R) {
+#pragma unroll
+                for (int x = 0; x < XB; ++x) acc[x] = fmaf(tap[j], w[j + x], acc[x]);
+            }
+        }
+    }
+}
+
+template <int XB>
+__device__ __forceinline__ void conv_line_T_x(const float* __restrict__ rr, const float* __restrict__ sr, int NA, int NA8, float (&acc)[XB]) {
+    float w[XB + 8], tap[8];
+    const int R = NA - NA8;
+    if (R > 0) {                                       // tail taps t = NA8 + j: w[7 - j + x] of the window rr[-8 .. XB)
+        ldx<XB + 8>(w, rr - 8);
+        ldx<8>(tap, sr + NA8);
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            if (j < R) {
+#pragma unroll
+                for (int x = 0; x < XB; ++x) acc[x] = fmaf(tap[j], w[7 - j + x], acc[x]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < XB; ++i) w[i] = w[i + 8];
+    } else {
+        ldx<XB>(w, rr);
+    }
+#pragma unroll 1
+    for (int b = 0; 8 * b < NA8; ++b) {                // block b: taps NA8-8-8b .. NA8-1-8b in reverse, window rr + 8 b
+        ldx<8>(w + XB, rr + 8 * b + XB);
+        ldx<8>(tap, sr + NA8 - 8 - 8 * b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int x = 0; x < XB; ++x) acc[x] = fmaf(tap[7 - j], w[j + x], acc[x]);
+#pragma unroll
+        for (int i = 0; i < XB; ++i) w[i] = w[i + 8];
+    }
+}
+
+// NB = NA8 / 8 known at compile time: straight-line code, the window blocks are distinct registers (no rotation moves) and the
+// loads of the next block can be scheduled above the FFMAs of the current one
+template <int XB, int NB>
+__device__ __forceinline__ void corr_line_u(const float* __restrict__ fr, const float* __restrict__ sr, int R, float (&acc)[XB]) {
+    float w[XB + 8 * NB + 8], tap[8];
+    ldx<XB>(w, fr);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        ldx<8>(w + XB + 8 * b, fr + XB + 8 * b);
+        ldx<8>(tap, sr + 8 * b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int x = 0; x < XB; ++x) acc[x] = fmaf(tap[j], w[8 * b + j + x], acc[x]);
+    }
+    if (R > 0) {
+        ldx<8>(tap, sr + 8 * NB);
+        if (R > 1) ldx<8>(w + XB + 8 * NB, fr + XB + 8 * NB);
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            if (j < R) {
+#pragma unroll
+                for (int x = 0; x < XB; ++x) acc[x] = fmaf(tap[j], w[8 * NB + j + x], acc[x]);
+            }
+        }
+    }
+}
+
+template <int XB, int NB>
+__device__ __forceinline__ void conv_line_T_u(const float* __restrict__ rr, const float* __restrict__ sr, int R, float (&acc)[XB]) {
+    float w[XB + 8 * NB + 8], tap[8];                   // w[i] = rr[i - 8]
+    if (R > 0) {
+        ldx<XB + 8>(w, rr - 8);
+        ldx<8>(tap, sr + 8 * NB);
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            if (j < R) {
+#pragma unroll
+                for (int x = 0; x < XB; ++x) acc[x] = fmaf(tap[j], w[7 - j + x], acc[x]);
+            }
+        }
+    } else {
+        ldx<XB>(w + 8, rr);
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        ldx<8>(w + 8 + XB + 8 * b, rr + XB + 8 * b);
+        ldx<8>(tap, sr + 8 * (NB - 1 - b));
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int x = 0; x < XB; ++x) acc[x] = fmaf(tap[7 - j], w[8 + 8 * b + j + x], acc[x]);
     }
 }
 
@@ -496,50 +626,68 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
     const float* wgt = D.weight + (size_t)e * n * n;
     float loss = 0.f, gmean = 0.f;
     const int nxb = (n + DC_XB - 1) / DC_XB;
+    // outputs per thread of the warp-split forward pass (0 = the lane-split / unsplit form below): the (row, x-block) tasks of the
+    // band must be whole warps, divide the CTA, and the plane of partial sums must fit the scratch it borrows
+    int fwd_xb = 0;
+    {
+        auto ok = [&](int xb) {
+            const int ntk = own * ((n + xb - 1) / xb);
+            return own > 0 && ntk % 32 == 0 && ntk < DC_THREADS && DC_THREADS % ntk == 0 && (n & 3) == 0 && ld >= n + 4 &&
+                   own * (n + 4) <= 2 * DC_MMAX * 4 * DC_EXT;
+        };
+        if (!noise && !(flags & 8) && (n & 15) == 0 && ok(16)) fwd_xb = 16;
+        else if (!noise && ok(DC_XB)) fwd_xb = DC_XB;
+    }
     if (noise) {
         for (int i = tid; i < n * n; i += DC_THREADS) {
             const int Y = i / n;
             if (Y >= rlo && Y < bd.rhi) rsm[(Y - rlo) * ld + i % n] = __ldg(wgt + i);
         }
-    } else if (own > 0 && (own * nxb) % 32 == 0 && own * nxb < DC_THREADS && DC_THREADS % (own * nxb) == 0 &&
-               (n & 3) == 0 && ld >= n + 4 && own * (n + 4) <= 2 * DC_MMAX * 4 * DC_EXT) {
+    } else if (fwd_xb != 0) {
         // Narrow band (fewer (row, x-block) tasks than threads): the NA kernel rows are split over WHOLE WARPS, so that every tap
         // load of a warp is one broadcast wavefront (with the slices on lane groups of a warp each quarter-warp fetched its own
         // kernel row: 96 shared-memory wavefronts per 264 FFMA, the forward pass ran at the shared-memory bandwidth).  The slices
         // add their partial sums in slice order into a small plane (the scratch of the pts-source term, dead until later):
         // deterministic.  The epilogue then runs on all threads, coalesced along a row, and the band of r goes to the other CTAs of
         // the cluster as 16-byte stores (it was one 4-byte remote store per output and destination, issued by a quarter of the
-        // threads).
-        const int ntk = own * nxb, SPL = DC_THREADS / ntk;
-        const int ias = (NA + SPL - 1) / SPL;
+        // threads).  16 outputs per thread when the stamp side allows it (see corr_line_x).
         const int ldm = n + 4;
         float* msum = ext;                          // [own][n + 4]
-        const int s = tid / ntk, t2 = tid % ntk;
-        const int Y = Y0 + t2 % own, X0 = (t2 / own) * DC_XB;
-        float acc[DC_XB];
+        auto conv_w = [&](auto tag) {
+            constexpr int XB = decltype(tag)::value;
+            const int ntk = own * ((n + XB - 1) / XB), SPL = DC_THREADS / ntk;
+            const int ias = (NA + SPL - 1) / SPL;
+            const int s = tid / ntk, t2 = tid % ntk;
+            const int Y = Y0 + t2 % own, X0 = (t2 / own) * XB;
+            float acc[XB];
 #pragma unroll
-        for (int x = 0; x < DC_XB; ++x) acc[x] = 0.f;
-        {
-            const int ia0 = s * ias, ia1 = min(NA, ia0 + ias);
-            const int ja = max(ia0, -(Y + A0)), jb = min(ia1, n - (Y + A0));
-            for (int ph = 0; ph < kk; ++ph) {
-                const float* pl = fpl + ph * pst + X0 + A0 + (Y + A0 - flo) * ld;
-                const float* Sph = Ssm + ph * NA * NAp;
-                for (int ia = ja; ia < jb; ++ia) corr_line(pl + ia * ld, Sph + ia * NAp, NA, NA8, acc);
-            }
-        }
-        float4* mrow = reinterpret_cast<float4*>(msum + (Y - Y0) * ldm + X0);
-        for (int turn = 0; turn < SPL; ++turn) {
-            if (s == turn) {
-                float4 lo = make_float4(acc[0], acc[1], acc[2], acc[3]), hi = make_float4(acc[4], acc[5], acc[6], acc[7]);
-                if (turn > 0) {
-                    const float4 a = mrow[0], b = mrow[1];
-                    lo.x += a.x; lo.y += a.y; lo.z += a.z; lo.w += a.w; hi.x += b.x; hi.y += b.y; hi.z += b.z; hi.w += b.w;
+            for (int x = 0; x < XB; ++x) acc[x] = 0.f;
+            {
+                const int ia0 = s * ias, ia1 = min(NA, ia0 + ias);
+                const int ja = max(ia0, -(Y + A0)), jb = min(ia1, n - (Y + A0));
+                for (int ph = 0; ph < kk; ++ph) {
+                    const float* pl = fpl + ph * pst + X0 + A0 + (Y + A0 - flo) * ld;
+                    const float* Sph = Ssm + ph * NA * NAp;
+                    if constexpr (XB == DC_XB) { for (int ia = ja; ia < jb; ++ia) corr_line(pl + ia * ld, Sph + ia * NAp, NA, NA8, acc); }
+                    else if (NA8 == 32) { for (int ia = ja; ia < jb; ++ia) corr_line_u<XB, 4>(pl + ia * ld, Sph + ia * NAp, NA - NA8, acc); }
+                    else { for (int ia = ja; ia < jb; ++ia) corr_line_x<XB>(pl + ia * ld, Sph + ia * NAp, NA, NA8, acc); }
                 }
-                mrow[0] = lo; mrow[1] = hi;
             }
-            __syncthreads();
-        }
+            float4* mrow = reinterpret_cast<float4*>(msum + (Y - Y0) * ldm + X0);
+            for (int turn = 0; turn < SPL; ++turn) {
+                if (s == turn) {
+#pragma unroll
+                    for (int q4 = 0; q4 < XB / 4; ++q4) {
+                        float4 v = make_float4(acc[4 * q4], acc[4 * q4 + 1], acc[4 * q4 + 2], acc[4 * q4 + 3]);
+                        if (turn > 0) { const float4 a = mrow[q4]; v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w; }
+                        mrow[q4] = v;
+                    }
+                }
+                __syncthreads();
+            }
+        };
+        if (fwd_xb == 16) conv_w(std::integral_constant<int, 16>{});
+        else conv_w(std::integral_constant<int, DC_XB>{});
         for (int i = tid; i < own * n; i += DC_THREADS) {
             const int Yl = i / n, X = i - Yl * n, Yg = Y0 + Yl;
             const float mval = fmaf(dscale, msum[Yl * ldm + X], mean);
@@ -616,6 +764,31 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
         ep[tid] = upd_p; D.ep_mu[(size_t)e * np + tid] = upd_mu; D.ep_nu[(size_t)e * np + tid] = upd_nv;
     }
     // ---- adjoint for the own band: dL/df_ph[Y'][X'] = 1/k^2 sum S_ph[av][au] r[Y'-av][X'-au]   (overwrites f)
+    const int ntkA16 = kk * own * (n / 16);       // tasks with 16 outputs per thread
+    if (!noise && !(flags & 16) && (n & 15) == 0 && ntkA16 > 0 && ntkA16 <= DC_THREADS && ntkA16 % 32 == 0 && DC_THREADS % ntkA16 == 0) {
+        // 16 outputs per thread (conv_line_T_x); when that leaves fewer tasks than threads the NA kernel rows are split over whole
+        // warps and the slices add into the plane in slice order
+        constexpr int XB = 16;
+        const int nx16 = n / XB, SPA = DC_THREADS / ntkA16, iasA = (NA + SPA - 1) / SPA;
+        const int s = tid / ntkA16, task = tid % ntkA16;
+        const int ph = task / (own * nx16), rem = task % (own * nx16), Y = Y0 + rem % own, X0 = (rem / own) * XB;
+        float acc[XB];
+#pragma unroll
+        for (int x = 0; x < XB; ++x) acc[x] = 0.f;
+        const float* Sph = Ssm + ph * NA * NAp;
+        const float* rrow = rsm + X0 - A0 - (NA8 - 1) + (Y - A0 - rlo) * ld;
+        const int ja = max(s * iasA, Y - A0 - (n - 1)), jb = min(min(NA, (s + 1) * iasA), Y - A0 + 1);
+        if (NA8 == 32) { for (int ia = ja; ia < jb; ++ia) conv_line_T_u<XB, 4>(rrow - ia * ld, Sph + ia * NAp, NA - NA8, acc); }
+        else { for (int ia = ja; ia < jb; ++ia) conv_line_T_x<XB>(rrow - ia * ld, Sph + ia * NAp, NA, NA8, acc); }
+        float* dst = fpl + ph * pst + (Y - flo) * ld + X0;
+        for (int turn = 0; turn < SPA; ++turn) {
+            if (s == turn) {
+#pragma unroll
+                for (int x = 0; x < XB; ++x) dst[x] = (turn > 0 ? dst[x] : 0.f) + dscale * acc[x];
+            }
+            if (turn + 1 < SPA) __syncthreads();
+        }
+    } else
     for (int task = tid; task < kk * own * nxb; task += DC_THREADS) {
         const int ph = task / (own * nxb), rem = task % (own * nxb), Y = Y0 + rem % own, X0 = (rem / own) * DC_XB;
         float acc[DC_XB];
@@ -1797,6 +1970,10 @@ static int launch_epoch(DeconvHandle* H, int flags, int seq = 0) {
     at[0].val.clusterDim.x = (unsigned)H->CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     LcbProfScope ps("k_deconv_epoch", H->st);
+    {   // development switches (A/B timing): 8 outputs per thread in the forward / adjoint pass
+        static const int dev_flags = (getenv("LCB_DC_FWD8") ? 8 : 0) | (getenv("LCB_DC_ADJ8") ? 16 : 0);
+        flags |= dev_flags;
+    }
     switch (D.k) {
         case 1: LCB_CUDA(cudaLaunchKernelEx(&cfg, k_deconv_epoch<1>, D, flags, H->CS, seq)); break;
         case 2: LCB_CUDA(cudaLaunchKernelEx(&cfg, k_deconv_epoch<2>, D, flags, H->CS, seq)); break;
