@@ -566,7 +566,33 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
     }
     // ---- f = warp(h) + point sources in polyphase layout: every CTA builds the rows of its OWN band, then copies the
     //      other rows its forward pass reads from the CTAs that own them (distributed shared memory)
-    if (!noise && own > 0) {
+    // pure translation (alpha = 0, the common case): the bilinear taps sit at a constant integer offset with constant weights --
+    // f(p) = (1-fy) ((1-fx) h[v0][u0] + fx h[v0][u0+1]) + fy (...), (v0, u0) = p - (bv, bu).  (bu, fx) reproduce floor() and the
+    // fraction of the generic form at every shift, integer shifts included (fx = 0 there, so the one-sided derivative of the
+    // shift gradient stays the right-sided one).  One warp per row: no per-pixel division, coalesced loads of h.
+    const int wrp = tid >> 5, ln = tid & 31;
+    const bool transl = (al == 0.f);
+    const float t_itx = floorf(geo.tx), t_ity = floorf(geo.ty);
+    const float t_wx1 = geo.tx - t_itx, t_wy1 = geo.ty - t_ity;
+    const int t_bu = (int)t_itx + (t_wx1 > 0.f ? 1 : 0), t_bv = (int)t_ity + (t_wy1 > 0.f ? 1 : 0);
+    const float t_fx = (t_wx1 > 0.f) ? 1.f - t_wx1 : 0.f, t_fy = (t_wy1 > 0.f) ? 1.f - t_wy1 : 0.f;
+    if (!noise && own > 0 && transl && D.h != nullptr) {
+        for (int row = wrp; row < own * k; row += DC_THREADS / 32) {
+            const int v = Y0 * k + row, v0 = v - t_bv;
+            const bool okA = (v0 >= 0 && v0 < nu), okB = (v0 + 1 >= 0 && v0 + 1 < nu);
+            const float* hA = D.h + (size_t)(okA ? v0 : 0) * nu;
+            const float* hB = D.h + (size_t)(okB ? v0 + 1 : 0) * nu;
+            float* dst = fpl + ((v % k) * k) * pst + (v / k - flo) * ld;
+#pragma unroll 4
+            for (int u = ln; u < nu; u += 32) {
+                const int u0 = u - t_bu;
+                const bool in0 = (u0 >= 0 && u0 < nu), in1 = (u0 + 1 >= 0 && u0 + 1 < nu);
+                const float h00 = (okA && in0) ? __ldg(hA + u0) : 0.f, h01 = (okA && in1) ? __ldg(hA + u0 + 1) : 0.f;
+                const float h10 = (okB && in0) ? __ldg(hB + u0) : 0.f, h11 = (okB && in1) ? __ldg(hB + u0 + 1) : 0.f;
+                dst[(u % k) * pst + u / k] = (1.f - t_fy) * ((1.f - t_fx) * h00 + t_fx * h01) + t_fy * ((1.f - t_fx) * h10 + t_fx * h11);
+            }
+        }
+    } else if (!noise && own > 0) {
 #pragma unroll 4
         for (int i = tid; i < own * k * nu; i += DC_THREADS) {     // (unrolled: the L2 loads of four pixels in flight)
             const int v = Y0 * k + i / nu, u = i % nu;
@@ -835,7 +861,27 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
     }
     // ---- shift gradient through the warp: dL/dd = sum_p dL/df[p] * grad h(q(p)) . dq/dd   (own rows)
     float gwx = 0.f, gwy = 0.f;
-    if (D.free_d && !noise && D.h != nullptr) {
+    if (D.free_d && !noise && D.h != nullptr && transl) {
+        for (int row = wrp; row < vhi - vlo; row += DC_THREADS / 32) {
+            const int v = vlo + row, v0 = v - t_bv;
+            const bool okA = (v0 >= 0 && v0 < nu), okB = (v0 + 1 >= 0 && v0 + 1 < nu);
+            const float* hA = D.h + (size_t)(okA ? v0 : 0) * nu;
+            const float* hB = D.h + (size_t)(okB ? v0 + 1 : 0) * nu;
+            const float* dfrow = fpl + ((v % k) * k) * pst + (v / k - flo) * ld;
+#pragma unroll 4
+            for (int u = ln; u < nu; u += 32) {
+                const int u0 = u - t_bu;
+                const bool in0 = (u0 >= 0 && u0 < nu), in1 = (u0 + 1 >= 0 && u0 + 1 < nu);
+                const float h00 = (okA && in0) ? __ldg(hA + u0) : 0.f, h01 = (okA && in1) ? __ldg(hA + u0 + 1) : 0.f;
+                const float h10 = (okB && in0) ? __ldg(hB + u0) : 0.f, h11 = (okB && in1) ? __ldg(hB + u0 + 1) : 0.f;
+                const float dhu = (1.f - t_fy) * (h01 - h00) + t_fy * (h11 - h10);
+                const float dhv = (1.f - t_fx) * (h10 - h00) + t_fx * (h11 - h01);
+                const float df = dfrow[(u % k) * pst + u / k];
+                gwx = fmaf(df, -(float)k * dhu, gwx);      // ca = 1, sa = 0
+                gwy = fmaf(df, -(float)k * dhv, gwy);
+            }
+        }
+    } else if (D.free_d && !noise && D.h != nullptr) {
 #pragma unroll 4
         for (int i = tid; i < (vhi - vlo) * nu; i += DC_THREADS) {
             const int v = vlo + i / nu, u = i % nu;
@@ -990,12 +1036,27 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
             float wx1 = geo.tx - itx, wy1 = geo.ty - ity, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
             if (noise) { wx0 *= wx0; wx1 *= wx1; wy0 *= wy0; wy1 *= wy1; }
             const int iu = (int)itx, iv = (int)ity;
+            // one warp per row of h: the two rows of dL/df it gathers from (own band or a neighbour's, through distributed shared
+            // memory) are resolved once per row, the lanes walk the columns with shifts and masks only
+            for (int row = wrp; row < vhi - vlo; row += DC_THREADS / 32) {
+                const int qv_i = vlo + row, pv = qv_i + iv;
+                auto rowptr = [&](int pvv) -> const float* {
+                    if (pvv < 0 || pvv >= nu) return nullptr;
+                    const int Yp = pvv / k, oc = min(Yp / rpc, CS - 1);
+                    return ((oc == crank) ? (const float*)fpl : remf[oc]) + ((pvv % k) * k) * pst + (Yp - remflo[oc]) * ld;
+                };
+                const float* r0 = rowptr(pv);
+                const float* r1 = rowptr(pv + 1);
 #pragma unroll 4
-            for (int i = tid; i < (vhi - vlo) * nu; i += DC_THREADS) {
-                const int qv_i = vlo + i / nu, qu_i = i % nu;
-                const int pv = qv_i + iv, pu = qu_i + iu;
-                const float acc = wy0 * (wx0 * dfr(pv, pu) + wx1 * dfr(pv, pu + 1)) + wy1 * (wx0 * dfr(pv + 1, pu) + wx1 * dfr(pv + 1, pu + 1));
-                Gh[i + vlo * nu] = noise ? acc : sc * acc;
+                for (int qu_i = ln; qu_i < nu; qu_i += 32) {
+                    const int pu = qu_i + iu;
+                    const bool in0 = (pu >= 0 && pu < nu), in1 = (pu + 1 >= 0 && pu + 1 < nu);
+                    const int o0 = in0 ? (pu % k) * pst + pu / k : 0, o1 = in1 ? ((pu + 1) % k) * pst + (pu + 1) / k : 0;
+                    const float d00 = (r0 && in0) ? r0[o0] : 0.f, d01 = (r0 && in1) ? r0[o1] : 0.f;
+                    const float d10 = (r1 && in0) ? r1[o0] : 0.f, d11 = (r1 && in1) ? r1[o1] : 0.f;
+                    const float acc = wy0 * (wx0 * d00 + wx1 * d01) + wy1 * (wx0 * d10 + wx1 * d11);
+                    Gh[qv_i * nu + qu_i] = noise ? acc : sc * acc;
+                }
             }
         } else {
             for (int i = tid; i < (vhi - vlo) * nu; i += DC_THREADS) {
@@ -1027,7 +1088,7 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
     cl.sync();                                    // #3: no CTA leaves while its shared memory may still be read
     DC_STAMP(12)
 #ifdef LCB_DC_TIMERS
-    if (tid == 0 && blockIdx.x < DC_TIM_CTAS) { unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); g_dc_tim[blockIdx.x][15] = (long long)gt; g_dc_tim[blockIdx.x][13] = 0; }
+    if (tid == 0 && blockIdx.x < DC_TIM_CTAS) { unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); g_dc_tim[blockIdx.x][15] = (long long)gt; if (flags & 4) g_dc_tim[blockIdx.x][13] = 0; }
 #endif
     if (!(flags & 4)) return;
 
@@ -1132,17 +1193,17 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
         else for (int i = tid; i < cnt; i += DC_THREADS) emit(vlo * nu + i, 0.f);
     }
     if (crank == 0) {
-        // per-epoch scalars (every rank-0 CTA wrote its own before raising its counter): one warp per entry, lanes stride the
-        // epochs, fixed-order shuffle tree
-        const int lane = tid & 31, iflux = red_flux(D);
-        for (int i = nu2 + (tid >> 5); i < D.tot; i += DC_THREADS / 32) {
+        // per-epoch scalars (every rank-0 CTA wrote its own before raising its counter): 8 lanes per entry stride the epochs (all
+        // loads of an entry in flight at once), fixed-order shuffle tree over the 8 lanes -- one pass for up to 32 entries
+        const int sub = tid & 7, iflux = red_flux(D);
+        for (int i = nu2 + (tid >> 3); i < ((D.tot - nu2 + 31) & ~31) + nu2; i += DC_THREADS / 8) {
             float sacc = 0.f;
             if (i < nu2 + 2 * M) {
-                for (int ee = lane; ee < D.E; ee += 32) sacc += __ldcg(D.gc + (size_t)ee * 2 * M + (i - nu2));
+                for (int ee = sub; ee < D.E; ee += 8) sacc += __ldcg(D.gc + (size_t)ee * 2 * M + (i - nu2));
             } else if (i == nu2 + 2 * M) {
-                for (int ee = lane; ee < D.E; ee += 32) sacc += __ldcg(D.eloss + ee);
+                for (int ee = sub; ee < D.E; ee += 8) sacc += __ldcg(D.eloss + ee);
             } else if (i == nu2 + 2 * M + 1) {
-                for (int ee = lane; ee < D.E; ee += 32)
+                for (int ee = sub; ee < D.E; ee += 8)
                     for (int p = 0; p < np; ++p) {
                         const bool is_free = (p < M) ? D.free_a : (p < M + 2) ? D.free_d : D.free_mean;
                         const float g = __ldcg(D.ep_g + (size_t)ee * np + p);
@@ -1151,13 +1212,15 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
             } else if (i < iflux + 4 * M) {
                 const int q = (i - iflux) / M, m = (i - iflux) % M;
                 const float Kf = D.fu[m];
-                for (int ee = lane; ee < D.E; ee += 32) {
+                for (int ee = sub; ee < D.E; ee += 8) {
                     const float a = __ldcg(D.ep + (size_t)ee * np + m) - Kf, g = __ldcg(D.ep_g + (size_t)ee * np + m);
                     sacc += (q == 0) ? a : (q == 1) ? a * a : (q == 2) ? g : g * a;
                 }
             }
-            sacc = warp_sum(sacc);
-            if (lane == 0) emit(i, sacc);
+            sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+            sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+            sacc += __shfl_xor_sync(0xffffffffu, sacc, 4);
+            if (sub == 0 && i < D.tot) emit(i, sacc);
         }
     }
     DC_STAMP(13)
@@ -2128,6 +2191,12 @@ int lcb_deconv_create(const lcb_deconv_problem* p, int mem, void* stream, void**
     AL(planes, (3 + (size_t)J) * pp, true) AL(model, E * nn, true) AL(prior, 4 * (size_t)DC_MMAX, true)
     AL(band_ctr, (size_t)DC_CSMAX + 1, true) AL(ictl, 2, true)
     D.GS = 1; while (D.GS * D.GS < D.E) ++D.GS;          // ~ sqrt(E) epochs per group
+    {   // few local epochs (the 8-GPU shard of cfg4 holds 25): ONE level -- the last cluster of a band walks E planes of 8 KB, which
+        // costs less than the second round of counters, fences and L2 round trips
+        const char* ev = getenv("LCB_DC_ONELEVEL_MAX");
+        const int one_level_max = ev ? atoi(ev) : 32;
+        if (D.E <= one_level_max) D.GS = D.E;
+    }
     D.NG = (D.E + D.GS - 1) / D.GS;
     AL(grp_ctr, (size_t)D.NG * DC_CSMAX, true) AL(Gp, (size_t)D.NG * pp, true)
 #undef AL
