@@ -682,16 +682,21 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
         auto conv_w = [&](auto tag) {
             constexpr int XB = decltype(tag)::value;
             const int ntk = own * ((n + XB - 1) / XB), SPL = DC_THREADS / ntk;
-            const int ias = (NA + SPL - 1) / SPL;
             const int s = tid / ntk, t2 = tid % ntk;
             const int Y = Y0 + t2 % own, X0 = (t2 / own) * XB;
             float acc[XB];
 #pragma unroll
             for (int x = 0; x < XB; ++x) acc[x] = 0.f;
             {
-                const int ia0 = s * ias, ia1 = min(NA, ia0 + ias);
-                const int ja = max(ia0, -(Y + A0)), jb = min(ia1, n - (Y + A0));
-                for (int ph = 0; ph < kk; ++ph) {
+                // the kk * NA (phase, kernel row) units are dealt out evenly: slice s takes units [s * upw, (s + 1) * upw)
+                const int units = kk * NA, upw = (units + SPL - 1) / SPL;
+                const int un0 = s * upw, un1 = min(units, un0 + upw);
+                const int lo_ia = max(0, -(Y + A0)), hi_ia = min(NA, n - (Y + A0));   // kernel rows whose f row lies inside the stamp
+                const bool by_rows = (flags & 32) != 0;                                // development switch: slices of kernel rows, every phase
+                const int ias = (NA + SPL - 1) / SPL;
+                for (int ph = by_rows ? 0 : un0 / NA; ph < kk && (by_rows || ph * NA < un1); ++ph) {
+                    const int ja = by_rows ? max(lo_ia, s * ias) : max(lo_ia, un0 - ph * NA);
+                    const int jb = by_rows ? min(hi_ia, (s + 1) * ias) : min(hi_ia, un1 - ph * NA);
                     const float* pl = fpl + ph * pst + X0 + A0 + (Y + A0 - flo) * ld;
                     const float* Sph = Ssm + ph * NA * NAp;
                     if constexpr (XB == DC_XB) { for (int ia = ja; ia < jb; ++ia) corr_line(pl + ia * ld, Sph + ia * NAp, NA, NA8, acc); }
@@ -1123,33 +1128,40 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
     auto band_sum = [&](const float* __restrict__ src, int np_, auto&& put, auto&& put4) {
         if ((nu & 3) == 0) {
             const int cnt4 = cnt >> 2;
-            for (int i0 = tid; i0 < cnt4; i0 += 4 * DC_THREADS) {
-                float4 acc[4];
+            // NQ quads x PE planes = 16 independent 16-byte loads in flight per thread; a narrow band (two quads per thread) takes
+            // eight planes per trip instead of four.  The planes of a pixel are added in plane order either way.
+            auto walk = [&](auto nq_t, auto pe_t) {
+                constexpr int NQ = decltype(nq_t)::value, PE = decltype(pe_t)::value;
+                for (int i0 = tid; i0 < cnt4; i0 += NQ * DC_THREADS) {
+                    float4 acc[NQ];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int p0 = 0; p0 < np_; p0 += 4) {
-                    float4 v[4][4];
+                    for (int q = 0; q < NQ; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int p0 = 0; p0 < np_; p0 += PE) {
+                        float4 v[NQ][PE];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
+                        for (int q = 0; q < NQ; ++q)
 #pragma unroll
-                        for (int pe = 0; pe < 4; ++pe) {
-                            const int i = i0 + q * DC_THREADS;
-                            v[q][pe] = (i < cnt4 && p0 + pe < np_) ? __ldcg(reinterpret_cast<const float4*>(src + (size_t)(p0 + pe) * nu2) + i)
-                                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
+                            for (int pe = 0; pe < PE; ++pe) {
+                                const int i = i0 + q * DC_THREADS;
+                                v[q][pe] = (i < cnt4 && p0 + pe < np_) ? __ldcg(reinterpret_cast<const float4*>(src + (size_t)(p0 + pe) * nu2) + i)
+                                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
+                        for (int q = 0; q < NQ; ++q)
 #pragma unroll
-                        for (int pe = 0; pe < 4; ++pe) {
-                            acc[q].x += v[q][pe].x; acc[q].y += v[q][pe].y; acc[q].z += v[q][pe].z; acc[q].w += v[q][pe].w;
-                        }
+                            for (int pe = 0; pe < PE; ++pe) {
+                                acc[q].x += v[q][pe].x; acc[q].y += v[q][pe].y; acc[q].z += v[q][pe].z; acc[q].w += v[q][pe].w;
+                            }
+                    }
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) {
+                        const int i = i0 + q * DC_THREADS;
+                        if (i < cnt4) put4(vlo * nu + 4 * i, acc[q]);
+                    }
                 }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int i = i0 + q * DC_THREADS;
-                    if (i < cnt4) put4(vlo * nu + 4 * i, acc[q]);
-                }
-            }
+            };
+            if (cnt4 <= 2 * DC_THREADS) walk(std::integral_constant<int, 2>{}, std::integral_constant<int, 8>{});
+            else walk(std::integral_constant<int, 4>{}, std::integral_constant<int, 4>{});
             return;
         }
         for (int i0 = tid; i0 < cnt; i0 += 4 * DC_THREADS) {
@@ -2034,7 +2046,7 @@ static int launch_epoch(DeconvHandle* H, int flags, int seq = 0) {
     cfg.attrs = at; cfg.numAttrs = 1;
     LcbProfScope ps("k_deconv_epoch", H->st);
     {   // development switches (A/B timing): 8 outputs per thread in the forward / adjoint pass
-        static const int dev_flags = (getenv("LCB_DC_FWD8") ? 8 : 0) | (getenv("LCB_DC_ADJ8") ? 16 : 0);
+        static const int dev_flags = (getenv("LCB_DC_FWD8") ? 8 : 0) | (getenv("LCB_DC_ADJ8") ? 16 : 0) | (getenv("LCB_DC_FWDROWS") ? 32 : 0);
         flags |= dev_flags;
     }
     switch (D.k) {
