@@ -718,8 +718,10 @@ def main():
     fl = algorithmic_flops()
     kfit = prof.get('k_psf_fit', {'ms': 0.0, 'launches': 0})
     launches = sum(v['launches'] for v in prof.values())
-    fit_ms_per_launch = kfit['ms'] / max(kfit['launches'], 1)
-    achieved = fl['psf_per_frame'] * F / (fit_ms_per_launch * 1e-3) / 1e12 if fit_ms_per_launch > 0 else 0.0
+    fit_launches = max(kfit['launches'], 1)                 # more than one when the batch exceeds the 1184-frame workspace (chunks)
+    fit_ms_per_launch = kfit['ms'] / fit_launches
+    F_launch = F / fit_launches                             # frames one launch processes on average
+    achieved = fl['psf_per_frame'] * F_launch / (fit_ms_per_launch * 1e-3) / 1e12 if fit_ms_per_launch > 0 else 0.0
     hbm_peak = None
     try:
         hbm_peak = json.load(open(ROOT / 'MEASURED_PEAKS.json'))['hbm_gbs']
@@ -729,10 +731,10 @@ def main():
     try:
         if args.workload == 'psfphot':
             tj = json.load(open(ROOT / 'profiles' / 'k_psf_fit_traffic.json'))      # from the committed ncu --set full capture
-            traffic = tj['dram_bytes_per_launch'] * F / tj['frames']              # per launch of F frames
+            traffic = tj['dram_bytes_per_launch'] * F_launch / tj['frames']       # per launch
     except Exception:
         pass
-    hbm_ach = algorithmic_bytes_per_frame() * F / (fit_ms_per_launch * 1e-3) / 1e9 if fit_ms_per_launch > 0 else 0.0
+    hbm_ach = algorithmic_bytes_per_frame() * F_launch / (fit_ms_per_launch * 1e-3) / 1e9 if fit_ms_per_launch > 0 else 0.0
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step_max, "higher_is_better": True, "scaling": "weak",
@@ -748,7 +750,8 @@ def main():
         "roofline": {"bound": "fp32", "kernel": "k_psf_fit", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                      "frac": achieved / fp32_peak if fp32_peak else None, "traffic": traffic,
                      "peak_source": "lcb_fp32_peak measured live (FFMA chains on all SMs); MEASURED_PEAKS.json has no FP32 SIMT figure",
-                     "algorithmic_flop_per_launch": fl['psf_per_frame'] * F, "ms_per_launch": fit_ms_per_launch,
+                     "algorithmic_flop_per_launch": fl['psf_per_frame'] * F_launch, "ms_per_launch": fit_ms_per_launch,
+                     "launches_per_step": fit_launches,
                      "frac_executed": (achieved / fp32_peak if fp32_peak else 0.0) * fl['psf_executed_per_it'] / fl['psf_per_it'],
                      "note": "frac uses SURVEY 8d's algorithmic count (full-resolution separable passes); frac_executed is the FP32 pipe "
                              "utilisation on the flops the kernel executes after folding the k-box into the taps",

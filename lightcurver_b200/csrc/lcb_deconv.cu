@@ -1210,24 +1210,36 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
         const int sub = tid & 7, iflux = red_flux(D);
         for (int i = nu2 + (tid >> 3); i < ((D.tot - nu2 + 31) & ~31) + nu2; i += DC_THREADS / 8) {
             float sacc = 0.f;
+            auto walk = [&](auto term) {           // the terms of 4 epochs per lane are evaluated before the first add
+                for (int ee = sub; ee < D.E; ee += 32) {
+                    float t[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) t[q] = (ee + 8 * q < D.E) ? term(ee + 8 * q) : 0.f;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) sacc += t[q];
+                }
+            };
             if (i < nu2 + 2 * M) {
-                for (int ee = sub; ee < D.E; ee += 8) sacc += __ldcg(D.gc + (size_t)ee * 2 * M + (i - nu2));
+                walk([&](int ee) { return __ldcg(D.gc + (size_t)ee * 2 * M + (i - nu2)); });
             } else if (i == nu2 + 2 * M) {
-                for (int ee = sub; ee < D.E; ee += 8) sacc += __ldcg(D.eloss + ee);
+                walk([&](int ee) { return __ldcg(D.eloss + ee); });
             } else if (i == nu2 + 2 * M + 1) {
-                for (int ee = sub; ee < D.E; ee += 8)
+                walk([&](int ee) {
+                    float g2 = 0.f;
                     for (int p = 0; p < np; ++p) {
                         const bool is_free = (p < M) ? D.free_a : (p < M + 2) ? D.free_d : D.free_mean;
                         const float g = __ldcg(D.ep_g + (size_t)ee * np + p);
-                        if (is_free) sacc = fmaf(g, g, sacc);
+                        if (is_free) g2 = fmaf(g, g, g2);
                     }
+                    return g2;
+                });
             } else if (i < iflux + 4 * M) {
                 const int q = (i - iflux) / M, m = (i - iflux) % M;
                 const float Kf = D.fu[m];
-                for (int ee = sub; ee < D.E; ee += 8) {
+                walk([&](int ee) {
                     const float a = __ldcg(D.ep + (size_t)ee * np + m) - Kf, g = __ldcg(D.ep_g + (size_t)ee * np + m);
-                    sacc += (q == 0) ? a : (q == 1) ? a * a : (q == 2) ? g : g * a;
-                }
+                    return (q == 0) ? a : (q == 1) ? a * a : (q == 2) ? g : g * a;
+                });
             }
             sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
             sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
@@ -1252,10 +1264,12 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
 // seq == 0: red[] <- local sums.  seq > 0 (multi-GPU): the local sums go to slot [seq&1][my rank] of EVERY rank's
 // receive buffer (plain stores into peer memory over NVLink); the last CTA to finish raises flag [seq&1][my rank] = seq
 // on every rank (fence - atomic - fence - flag, the threadFenceReduction pattern at system scope).
-__global__ void __launch_bounds__(256) k_deconv_reduce(DeconvDev D, int force_h, int seq) {
+__global__ void __launch_bounds__(256) k_deconv_reduce(DeconvDev D, int force_h, int seq_arg) {
+    // seq_arg < 0: the sequence number is read from D.ictl[1] (CUDA-graph replay), as in k_deconv_epoch
+    const int seq = (seq_arg < 0) ? ((D.cm.world > 1) ? D.ictl[1] : 0) : seq_arg;
     // 64 entries of red[] per CTA, 4 threads per entry: thread g sums the epochs e = g, g+4, ... (independent loads in
     // flight), the four partial sums are combined in a fixed order -> deterministic
-    __shared__ float part[4][64];
+    __shared__ __align__(16) float part[4][64];
     const int nu2 = D.nu * D.nu, M = D.M, np = D.M + 3;
     const int col = threadIdx.x & 63, grp = threadIdx.x >> 6;
     const int i = blockIdx.x * 64 + col;
@@ -1263,13 +1277,16 @@ __global__ void __launch_bounds__(256) k_deconv_reduce(DeconvDev D, int force_h,
     float s = 0.f;
     if (i < nu2) {
         if (D.free_h || force_h) {
+            // 16 planes per trip, all loads issued before the first add (the walk is bound by L2 latency: four loads in flight made
+            // it 27 us at 100 local epochs); the planes of a thread are added in epoch order, absent ones add +0
             const float* src = D.Gh + i;
-            int e = grp;
-            for (; e + 12 < D.E; e += 16) {
-                const float a0 = src[(size_t)e * nu2], a1 = src[(size_t)(e + 4) * nu2], a2 = src[(size_t)(e + 8) * nu2], a3 = src[(size_t)(e + 12) * nu2];
-                s += a0; s += a1; s += a2; s += a3;
+            for (int e = grp; e < D.E; e += 64) {
+                float a[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) a[q] = (e + 4 * q < D.E) ? __ldcg(src + (size_t)(e + 4 * q) * nu2) : 0.f;
+#pragma unroll
+                for (int q = 0; q < 16; ++q) s += a[q];
             }
-            for (; e < D.E; e += 4) s += src[(size_t)e * nu2];
         }
     } else if (i < nu2 + 2 * M) {
         for (int e = grp; e < D.E; e += 4) s += D.gc[(size_t)e * 2 * M + (i - nu2)];
@@ -1300,8 +1317,16 @@ __global__ void __launch_bounds__(256) k_deconv_reduce(DeconvDev D, int force_h,
         return;
     }
     const int W = D.cm.world, par = seq & 1;
-    if (writer)
-        for (int r = 0; r < W; ++r) D.cm.slots[r][((size_t)par * W + D.cm.rank) * D.tot_pad + i] = s;
+    // the 64 sums of the CTA go to every peer as 16 stores of 16 bytes (they were 64 stores of 4 bytes): slots are 16-byte aligned,
+    // a CTA starts at a multiple of 64 entries and the slot stride tot_pad is a multiple of 4
+    __syncthreads();                                // every thread has read part[][]
+    if (grp == 0) part[0][col] = (i < D.tot) ? s : 0.f;
+    __syncthreads();
+    for (int t = threadIdx.x; t < 16 * W; t += 256) {
+        const int r = t >> 4, q = t & 15, i4 = blockIdx.x * 64 + 4 * q;
+        if (i4 + 3 < D.tot_pad)
+            *reinterpret_cast<float4*>(D.cm.slots[r] + ((size_t)par * W + D.cm.rank) * D.tot_pad + i4) = *reinterpret_cast<const float4*>(&part[0][4 * q]);
+    }
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1655,6 +1680,7 @@ k_deconv_update(DeconvDev D, int it_arg, int n_iter, float lr0, int schedule, in
     const int tid = threadIdx.x, gtid = rank * DU_THREADS + tid;
     constexpr int GT_ALL = DU_CTAS * DU_THREADS;
     const int nu = D.nu, pp = nu * nu, M = D.M;
+    const float* sl = nullptr;
     if (seq > 0) {
         const int W = D.cm.world, par = seq & 1;
         if (tid < W) {
@@ -1668,14 +1694,30 @@ k_deconv_update(DeconvDev D, int it_arg, int n_iter, float lr0, int schedule, in
         }
         __threadfence_system();
         __syncthreads();
-        const float* sl = D.cm.slots[D.cm.rank] + (size_t)par * W * D.tot_pad;
-        for (int i = gtid; i < D.tot; i += GT_ALL) {
-            float s = 0.f;
-            for (int r = 0; r < W; ++r) s += __ldcg(sl + (size_t)r * D.tot_pad + i);
-            D.red[i] = s;
+        sl = D.cm.slots[D.cm.rank] + (size_t)par * W * D.tot_pad;
+    }
+    // sum over the ranks of entry i of the exchanged buffer, in rank order (bit-identical everywhere); all loads in flight at once
+    const int Wn = D.cm.world;
+    auto rank_sum = [&](int i) -> float {
+        float v[DC_MAXW];
+#pragma unroll
+        for (int r = 0; r < DC_MAXW; ++r) v[r] = (r < Wn) ? __ldcg(sl + (size_t)r * D.tot_pad + i) : 0.f;
+        float t = 0.f;
+#pragma unroll
+        for (int r = 0; r < DC_MAXW; ++r) t += v[r];
+        return t;
+    };
+    // the scalar tail of red[] (gradients of c, loss, |g_epoch|^2, flux sums) is needed by every CTA: each one assembles its own copy
+    // in shared memory, so that no cluster barrier separates the exchange from the gradient pass
+    __shared__ float sred[6 * DC_MMAX + 2];
+    {
+        const int nsc = D.tot - pp;
+        if (tid < nsc) {
+            const float t = (seq > 0) ? rank_sum(pp + tid) : D.red[pp + tid];
+            sred[tid] = t;
+            if (seq > 0 && rank == 0) D.red[pp + tid] = t;
         }
-        __threadfence();
-        cl.sync();
+        __syncthreads();
     }
     const float* C0 = D.planes;
     float* GT = D.planes + 2 * pp;       // total gradient wrt h
@@ -1683,17 +1725,21 @@ k_deconv_update(DeconvDev D, int it_arg, int n_iter, float lr0, int schedule, in
     if (D.free_h) {
         for (int i = gtid; i < pp; i += GT_ALL) {
             const float hv = D.h[i];
-            float g = D.red[i] + (with_reg ? C0[i] : 0.f);
+            const float rs = (seq > 0) ? rank_sum(i) : D.red[i];
+            if (seq > 0) D.red[i] = rs;
+            float g = rs + (with_reg ? C0[i] : 0.f);
             if (D.lam_pos != 0.f && hv < 0.f) { g -= D.lam_pos; v4[1] -= D.lam_pos * hv; }
             GT[i] = g;
             v4[0] = fmaf(g, g, v4[0]);
             if (grad_h_out) grad_h_out[i] = g;
         }
+    } else if (seq > 0) {
+        for (int i = gtid; i < pp; i += GT_ALL) D.red[i] = rank_sum(i);
     }
     // c_x, c_y gradients (+ prior): every CTA computes them redundantly (identical), only rank 0 counts them
     __shared__ float gcs[2 * DC_MMAX];
     if (tid < 2 * M) {
-        float g = D.red[pp + tid];
+        float g = sred[tid];
         if (D.has_prior) {
             const int ax = tid / M, m = tid % M;
             const float mu = D.prior[(2 * ax) * M + m], sg = D.prior[(2 * ax + 1) * M + m];
@@ -1710,7 +1756,7 @@ k_deconv_update(DeconvDev D, int it_arg, int n_iter, float lr0, int schedule, in
     if (D.lam_fu != 0.f && tid < M) {
         const int o = red_flux(D);
         const float Et = (float)D.E_total, K = D.fu[tid];
-        const float S1 = D.red[o + tid], S2 = D.red[o + M + tid], Sg = D.red[o + 2 * M + tid], Sga = D.red[o + 3 * M + tid];
+        const float S1 = sred[o - pp + tid], S2 = sred[o - pp + M + tid], Sg = sred[o - pp + 2 * M + tid], Sga = sred[o - pp + 3 * M + tid];
         const float dm = S1 / Et, mean = K + dm;
         const float var = fmaxf(S2 / Et - dm * dm, 0.f), sd = sqrtf(var);
         float A = 0.f, B = 0.f, val = 0.f;
@@ -1733,8 +1779,8 @@ k_deconv_update(DeconvDev D, int it_arg, int n_iter, float lr0, int schedule, in
         }
     }
     cluster_sums<4>(v4, red, D.gpart, tid, rank);
-    const float gn2 = v4[0] + D.red[pp + 2 * M + 1];
-    const float L = D.red[pp + 2 * M] + (with_reg ? D.ctl[6] : 0.f) + v4[1] + v4[2] + v4[3];
+    const float gn2 = v4[0] + sred[2 * M + 1];
+    const float L = sred[2 * M] + (with_reg ? D.ctl[6] : 0.f) + v4[1] + v4[2] + v4[3];
     if (rank == 0 && D.lam_fu != 0.f && tid < M) {      // every read of D.fu above is behind the cluster barrier
         D.fu[tid] = fus[tid]; D.fu[DC_MMAX + tid] = fus[DC_MMAX + tid]; D.fu[2 * DC_MMAX + tid] = fus[2 * DC_MMAX + tid];
     }
@@ -1766,10 +1812,8 @@ k_deconv_update(DeconvDev D, int it_arg, int n_iter, float lr0, int schedule, in
         D.c[tid] = cvv; D.c_mu[tid] = mu; D.c_nu[tid] = nv;
     }
     if (gtid == 0) { D.ctl[0] = cs; D.ctl[1] = lr; D.ctl[2] = bc.inv_bc1; D.ctl[3] = bc.inv_bc2; D.ctl[4] = 1.f; }
-    if (dev_it) {
-        cl.sync();                                   // every CTA has read ictl
-        if (gtid == 0) { D.ictl[0] = it + 1; D.ictl[1] = D.ictl[1] + 1; }
-    }
+    // (every CTA read ictl before the cluster barrier of cluster_sums: no further barrier is needed before it advances)
+    if (dev_it && gtid == 0) { D.ictl[0] = it + 1; D.ictl[1] = D.ictl[1] + 1; }
 }
 
 // adds the flux-uniformity gradient to the stored per-epoch gradients (evaluation path only: lcb_deconv_loss_grad)
@@ -2458,9 +2502,26 @@ struct DeconvRun {
     int done = 0, seq0 = 0;
 };
 
+// Where the reduction over the local epochs runs: in the tail of the epoch kernel (last cluster per band, two levels above 32 epochs;
+// the sums are pushed to the peers from there) or as its own grid-wide kernel (k_deconv_reduce, which pushes as well).  Measured on
+// cfg4 shapes with CUDA-graph replays (profiles/README.md, last session of round 2): one GPU 200 epochs fused 2336 vs separate 2314
+// it/s, 100 epochs 3479-4009 vs 3676-4211, 50 epochs 6436 vs 6650, 25 epochs 10270 vs 10680; two GPUs (100 epochs per rank) fused
+// 3427 vs separate 3651; eight GPUs (25 per rank) fused 9337 vs separate 9288.  Few CTAs walking many planes at the very end of
+// the grid cost more than a kernel boundary in the middle range.  LCB_DECONV_REDUCE=fused|separate overrides the rule (A/B timing).
+static bool fused_reduction(const DeconvHandle* H) {
+    static const int forced = [] {
+        const char* e = getenv("LCB_DECONV_REDUCE");
+        return !e ? 0 : (e[0] == 'f' ? 1 : (e[0] == 's' ? 2 : 0));
+    }();
+    if (forced) return forced == 1;
+    const int E = H->D.E;
+    return E >= 128 || (H->D.cm.world > 1 && E <= 32);
+}
+
 static int run_iteration(DeconvHandle* H, const lcb_fit_opts* opt, int it_arg, int seq_arg) {
     int r;
-    if ((r = launch_starlet(H)) || (r = launch_epoch(H, 4, seq_arg)) ||
+    const bool fused = fused_reduction(H);
+    if ((r = launch_starlet(H)) || (r = launch_epoch(H, fused ? 4 : 0, seq_arg)) || (!fused && (r = launch_reduce(H, 0, seq_arg))) ||
         (r = launch_update(H, it_arg, opt->n_iter, opt->lr, opt->schedule, seq_arg, nullptr, nullptr, nullptr))) return r;
     return LCB_OK;
 }

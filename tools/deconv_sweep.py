@@ -38,6 +38,12 @@ def main():
             jd.set_reg(1.0, 1.0, 100.0, lam_pts=0.01, lam_fu=10.0)
             jd.run(10, lr=1e-4)
             torch.cuda.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            jd.run(args.iters, lr=1e-4)          # CUDA-graph replays (no per-kernel events)
+            g1.record()
+            torch.cuda.synchronize()
+            ms_graph = g0.elapsed_time(g1) / args.iters
             _lib.profile_enable(True)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -49,7 +55,7 @@ def main():
             ms = e0.elapsed_time(e1) / args.iters
             used = int(_lib.lib.lcb_deconv_get_cluster(jd.handle))
             parts = ' '.join(f"{kn.replace('k_deconv_', '')}={v['ms'] / max(v['launches'], 1):.3f}" for kn, v in sorted(prof.items()))
-            print(f"E={E:4d} cs={cs} (used {used}) {ms:.3f} ms/it  {1e3 / ms:7.1f} it/s   [{parts}]", flush=True)
+            print(f"E={E:4d} cs={cs} (used {used}) {ms:.3f} ms/it  {1e3 / ms:7.1f} it/s eager | graph {ms_graph:.3f} ms/it {1e3 / ms_graph:7.1f} it/s   [{parts}]", flush=True)
             if hasattr(_lib.lib, 'lcb_debug_dc_timers'):     # -DLCB_DC_TIMERS build: phase stamps of the LAST launch of k_deconv_epoch
                 import ctypes
                 nc = E * used
