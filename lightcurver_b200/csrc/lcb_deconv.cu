@@ -421,16 +421,6 @@ __device__ __forceinline__ float h_at(const float* __restrict__ h, int nu, int v
     return (v >= 0 && v < nu && u >= 0 && u < nu) ? __ldg(h + v * nu + u) : 0.f;
 }
 
-__device__ __forceinline__ float block_sum(float v, float* red, int tid) {
-    v = warp_sum(v);
-    __syncthreads();
-    if ((tid & 31) == 0) red[tid >> 5] = v;
-    __syncthreads();
-    float s = 0.f;
-    for (int w = 0; w < DC_THREADS / 32; ++w) s += red[w];
-    return s;
-}
-
 #ifdef LCB_DC_TIMERS
 // development build only (python -m lightcurver_b200.build --dc-timers): clock64 stamps of the phases of k_deconv_epoch per CTA
 #define DC_TIM_SLOTS 16
@@ -475,7 +465,6 @@ __global__ void __launch_bounds__(DC_THREADS, 2) k_deconv_epoch(DeconvDev D, int
     float* gx = sm + L.oG;                        // [M][16] and derivative [M][16]
     float* gy = gx + 2 * DC_MMAX * 16;
     float* par = sm + L.oPar;                     // [np]
-    float* red = sm + L.oRed;                     // [8] block_sum scratch
     float* cpart = sm + L.oCp;                    // [CS][32] (rank 0's copy is the one that is read)
     float* ptsacc = sm + L.oPts;                  // [M][32]
     float* ext = sm + L.oEx;                      // [axis][m][4][DC_EXT]
@@ -1288,24 +1277,61 @@ __global__ void __launch_bounds__(256) k_deconv_reduce(DeconvDev D, int force_h,
                 for (int q = 0; q < 16; ++q) s += a[q];
             }
         }
-    } else if (i < nu2 + 2 * M) {
-        for (int e = grp; e < D.E; e += 4) s += D.gc[(size_t)e * 2 * M + (i - nu2)];
-    } else if (i == nu2 + 2 * M) {
-        for (int e = grp; e < D.E; e += 4) s += D.eloss[e];
-    } else if (i == nu2 + 2 * M + 1) {
-        for (int e = grp; e < D.E; e += 4)
-            for (int p = 0; p < np; ++p) {
-                const bool is_free = (p < M) ? D.free_a : (p < M + 2) ? D.free_d : D.free_mean;
-                const float g = D.ep_g[(size_t)e * np + p];
-                if (is_free) s = fmaf(g, g, s);
+    }
+    // Per-epoch scalars (entries nu2 .. tot-1: gradients of c, loss, |g_epoch|^2, flux sums).  The CTA(s) that own them compute them
+    // COOPERATIVELY: thread t takes the epochs t, t + 256, ..., loads the 4M + 4 values of an epoch once (all loads in flight), forms
+    // the 6M + 2 terms, and the CTA reduces them in a fixed order (shuffle tree per warp, warps in order).  Four threads per entry
+    // walking E / 4 epochs with one L2 round trip each made this CTA the last one to finish: the kernel took 8 us + 0.9 us per 4
+    // local epochs (53 us at 200).
+    __shared__ float sc_red[8][6 * DC_MMAX + 2];
+    const int nsc = D.tot - nu2;
+    const bool owns_scalars = (int)(blockIdx.x * 64 + 63) >= nu2;      // block-uniform
+    if (owns_scalars) {
+        float t[6 * DC_MMAX + 2];
+#pragma unroll
+        for (int k = 0; k < 6 * DC_MMAX + 2; ++k) t[k] = 0.f;
+        for (int e = threadIdx.x; e < D.E; e += 256) {
+            float gcv[2 * DC_MMAX], gv[DC_MMAX + 3], av[DC_MMAX];
+#pragma unroll
+            for (int q = 0; q < 2 * DC_MMAX; ++q) gcv[q] = (q < 2 * M) ? __ldcg(D.gc + (size_t)e * 2 * M + q) : 0.f;
+#pragma unroll
+            for (int q = 0; q < DC_MMAX + 3; ++q) gv[q] = (q < np) ? __ldcg(D.ep_g + (size_t)e * np + q) : 0.f;
+#pragma unroll
+            for (int q = 0; q < DC_MMAX; ++q) av[q] = (q < M) ? __ldcg(D.ep + (size_t)e * np + q) - D.fu[q] : 0.f;
+            const float el = __ldcg(D.eloss + e);
+            float g2 = 0.f;
+#pragma unroll
+            for (int q = 0; q < DC_MMAX + 3; ++q) {
+                const bool is_free = (q < M) ? D.free_a : (q < M + 2) ? D.free_d : D.free_mean;
+                if (q < np && is_free) g2 = fmaf(gv[q], gv[q], g2);
             }
-    } else if (i < iflux + 4 * M) {
-        // flux statistics per source, shifted by the last known mean K_m: sum (a-K), sum (a-K)^2, sum g, sum g (a-K)
-        const int q = (i - iflux) / M, m = (i - iflux) % M;
-        const float K = D.fu[m];
-        for (int e = grp; e < D.E; e += 4) {
-            const float a = D.ep[(size_t)e * np + m] - K, g = D.ep_g[(size_t)e * np + m];
-            s += (q == 0) ? a : (q == 1) ? a * a : (q == 2) ? g : g * a;
+            // entry order of red[] past the pixels: gc[2M] | loss | |g|^2 | sum (a-K)[M] | sum (a-K)^2[M] | sum g[M] | sum g (a-K)[M]
+#pragma unroll
+            for (int k = 0; k < 6 * DC_MMAX + 2; ++k) {
+                float term = 0.f;
+                if (k < 2 * M) term = gcv[k < 2 * DC_MMAX ? k : 0];
+                else if (k == 2 * M) term = el;
+                else if (k == 2 * M + 1) term = g2;
+                else if (k < nsc) {
+                    const int qq = (k - 2 * M - 2) / M, m = (k - 2 * M - 2) % M;
+                    float a_ = 0.f, g_ = 0.f;
+#pragma unroll
+                    for (int q = 0; q < DC_MMAX; ++q) if (q == m) { a_ = av[q]; g_ = gv[q]; }
+                    term = (qq == 0) ? a_ : (qq == 1) ? a_ * a_ : (qq == 2) ? g_ : g_ * a_;
+                }
+                t[k] += term;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 6 * DC_MMAX + 2; ++k) {
+            const float w = warp_sum(t[k]);
+            if ((threadIdx.x & 31) == 0) sc_red[threadIdx.x >> 5][k] = w;
+        }
+        __syncthreads();
+        if (i >= nu2 && i < D.tot && grp == 0) {
+            float acc = 0.f;
+            for (int w = 0; w < 8; ++w) acc += sc_red[w][i - nu2];
+            s = acc;                                   // (the other three threads of the entry keep s = 0)
         }
     }
     part[grp][col] = s;
@@ -2502,20 +2528,20 @@ struct DeconvRun {
     int done = 0, seq0 = 0;
 };
 
-// Where the reduction over the local epochs runs: in the tail of the epoch kernel (last cluster per band, two levels above 32 epochs;
-// the sums are pushed to the peers from there) or as its own grid-wide kernel (k_deconv_reduce, which pushes as well).  Measured on
-// cfg4 shapes with CUDA-graph replays (profiles/README.md, last session of round 2): one GPU 200 epochs fused 2336 vs separate 2314
-// it/s, 100 epochs 3479-4009 vs 3676-4211, 50 epochs 6436 vs 6650, 25 epochs 10270 vs 10680; two GPUs (100 epochs per rank) fused
-// 3427 vs separate 3651; eight GPUs (25 per rank) fused 9337 vs separate 9288.  Few CTAs walking many planes at the very end of
-// the grid cost more than a kernel boundary in the middle range.  LCB_DECONV_REDUCE=fused|separate overrides the rule (A/B timing).
-static bool fused_reduction(const DeconvHandle* H) {
+// Where the reduction over the local epochs runs: as its own grid-wide kernel (k_deconv_reduce: the default) or in the tail of the
+// epoch kernel (last cluster per band, two levels above 32 epochs).  Both push the sums to the peers.  Measured on cfg4 shapes with
+// CUDA-graph replays (profiles/README.md, last session of round 2).  Before k_deconv_reduce summed its per-epoch scalars cooperatively
+// it took 8 us + 0.9 us per 4 local epochs (53 us at 200) and the routes were within a few per cent of each other: one GPU, 200 epochs,
+// fused 2336 vs separate 2314 it/s; two GPUs (100 per rank) 3427 vs 3651; eight GPUs (25 per rank) 9337 vs 9288.  With the reduce kernel
+// at 14 us for any shard size the separate route wins on one GPU at every size (200 epochs 2548 vs 2332 it/s, 100: 3711 vs 3485, 50: 6882 vs
+// 6398, 25: 10738 vs 10167): a few CTAs walking the planes at the very end of a grid cost more than a kernel boundary.
+// LCB_DECONV_REDUCE=fused|separate selects the route explicitly (A/B timing; the fused route stays tested).
+static bool fused_reduction(const DeconvHandle*) {
     static const int forced = [] {
         const char* e = getenv("LCB_DECONV_REDUCE");
         return !e ? 0 : (e[0] == 'f' ? 1 : (e[0] == 's' ? 2 : 0));
     }();
-    if (forced) return forced == 1;
-    const int E = H->D.E;
-    return E >= 128 || (H->D.cm.world > 1 && E <= 32);
+    return forced == 1;
 }
 
 static int run_iteration(DeconvHandle* H, const lcb_fit_opts* opt, int it_arg, int seq_arg) {
