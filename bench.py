@@ -416,8 +416,10 @@ def deconv_section(world, rank, local, group, T, steps, warmup, comm='p2p', cpu_
                       "collective": ("none" if world == 1 else "in-kernel all-reduce of nu^2+6M+2 floats per iteration over NVLink peer memory "
                                      "(push + flag, summed in rank order)" if comm == 'p2p' else "1 NCCL all-reduce of nu^2+6M+2 floats per iteration"),
                       "ctas_per_epoch": ctas, "loss_first_last": [float(hist[0]), float(hist[-1])]},
-           "gpu_launches": steps * (3 * T + 1), "kernels": prof, "wall_s_timed_region": wall,
-           "launch_mode": "iteration 0 eager, iterations 1.. replay one captured CUDA graph (starlet | epoch + fused reduce / NVLink push | update); "
+           # kernels per iteration: starlet, epoch, update, + the reduce kernel unless the reduction runs fused in the epoch kernel's tail
+           "gpu_launches": steps * ((4 if (comm == 'nccl' or 'k_deconv_reduce' in prof) else 3) * T + 1), "kernels": prof, "wall_s_timed_region": wall,
+           "launch_mode": "iteration 0 eager, iterations 1.. replay one captured CUDA graph (starlet | epoch | reduce + NVLink push | update; "
+                          "LCB_DECONV_REDUCE=fused folds the reduction and the push into the tail of the epoch kernel); "
                           "`kernels` comes from one extra step with per-launch CUDA events (eager launches)",
            "roofline": {"bound": "fp32", "kernel": "k_deconv_epoch", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
                         "frac": ach / fp32_peak if fp32_peak else None, "traffic": None,
