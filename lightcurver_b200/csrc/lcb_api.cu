@@ -1,5 +1,7 @@
 // lcb_api.cu -- library-wide state of liblcb: last error, conventions, staging arena, FP32 peak probe.
 #include "lcb_common.cuh"
+#include <nvtx3/nvToolsExt.h>
+#include <cstdlib>
 
 #include <mutex>
 #include <vector>
@@ -92,7 +94,14 @@ static std::vector<ProfRec> g_prof;
 static std::mutex g_prof_mu;          // launches may come from several host threads (one per GPU)
 bool lcb_profiling() { return g_prof_on; }
 
+// NVTX ranges (the reference only logs wall-clock per step): opt-in with LCB_NVTX=1, one range per library
+// call and one per kernel launch, visible to any NVTX-aware tool (nsys, ncu --nvtx)
+static const bool g_nvtx = [] { const char* e = getenv("LCB_NVTX"); return e && e[0] == '1'; }();
+LcbRange::LcbRange(const char* name) { if (g_nvtx) nvtxRangePushA(name); }
+LcbRange::~LcbRange() { if (g_nvtx) nvtxRangePop(); }
+
 LcbProfScope::LcbProfScope(const char* name, cudaStream_t s) : idx(-1), st(s) {
+    if (g_nvtx) nvtxRangePushA(name);
     if (!g_prof_on) return;
     ProfRec r; r.name = name;
     if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
@@ -102,7 +111,7 @@ LcbProfScope::LcbProfScope(const char* name, cudaStream_t s) : idx(-1), st(s) {
     g_prof.push_back(r);
     idx = (int)g_prof.size() - 1;
 }
-LcbProfScope::~LcbProfScope() { if (idx >= 0) cudaEventRecord(e1, st); }
+LcbProfScope::~LcbProfScope() { if (idx >= 0) cudaEventRecord(e1, st); if (g_nvtx) nvtxRangePop(); }
 
 extern "C" int lcb_profile_enable(int on) {
     std::lock_guard<std::mutex> lk(g_prof_mu);

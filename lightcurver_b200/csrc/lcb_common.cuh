@@ -50,6 +50,11 @@ struct LcbProfScope {
     LcbProfScope(const char* name, cudaStream_t s);
     ~LcbProfScope();
 };
+// NVTX range around a library call (LCB_NVTX=1; every LcbProfScope, i.e. every kernel launch, is a nested range as well)
+struct LcbRange {
+    LcbRange(const char* name);
+    ~LcbRange();
+};
 
 // ---------------------------------------------------------------- device side
 struct DevConv {              // conventions in the form kernels consume

@@ -2470,6 +2470,7 @@ int lcb_deconv_step_update(void* handle, int it, int n_iter, float lr, int sched
 // the host optimiser over lcb_deconv_loss_grad).  info: [0] iterations, [1] evaluations, [2] stop reason (1 ftol, 2 pgtol,
 // 3 maxiter, 4 line search stalled, 0 evaluation budget exhausted), [3] final loss, [4] |projected gradient|_inf.
 int lcb_deconv_lbfgs(void* handle, int maxiter, float a_lower, float ftol, float pgtol, float* loss_hist, float* info, int mem) {
+    LcbRange nvtx_range("lcb_deconv_lbfgs");
     DeconvHandle* H = (DeconvHandle*)handle;
     LCB_REQUIRE(H && maxiter >= 1, "lcb_deconv_lbfgs: bad arguments");
     DeconvDev& D = H->D;
@@ -2624,6 +2625,7 @@ static int run_end(DeconvHandle* H, const lcb_fit_opts* opt, DeconvRun& R, float
 }
 
 int lcb_deconv_run(void* handle, const lcb_fit_opts* opt, float* loss_hist, int mem) {
+    LcbRange nvtx_range("lcb_deconv_run");
     DeconvHandle* H = (DeconvHandle*)handle;
     LCB_REQUIRE(H && opt && opt->n_iter >= 0, "lcb_deconv_run: bad arguments");
     DeconvRun R;
@@ -2633,6 +2635,7 @@ int lcb_deconv_run(void* handle, const lcb_fit_opts* opt, float* loss_hist, int 
 }
 
 int lcb_deconv_run_many(void* const* handles, int count, const lcb_fit_opts* opt, float* const* loss_hist, int mem) {
+    LcbRange nvtx_range("lcb_deconv_run_many");
     LCB_REQUIRE(handles && count >= 0 && opt && opt->n_iter >= 0, "lcb_deconv_run_many: bad arguments");
     std::vector<DeconvRun> R((size_t)count);
     int rc = LCB_OK;
@@ -2653,6 +2656,7 @@ int lcb_deconv_run_many(void* const* handles, int count, const lcb_fit_opts* opt
 
 // loss and gradient at the current parameters (no update); collective when a communicator is connected
 int lcb_deconv_loss_grad(void* handle, lcb_deconv_grad* g, int mem) {
+    LcbRange nvtx_range("lcb_deconv_loss_grad");
     DeconvHandle* H = (DeconvHandle*)handle;
     LCB_REQUIRE(H && g, "lcb_deconv_loss_grad: NULL argument");
     DeconvDev& D = H->D;

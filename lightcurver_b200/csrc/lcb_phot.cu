@@ -210,6 +210,7 @@ static int dispatch_phot(const PhotArgs& A, size_t smem, cudaStream_t st) {
 
 extern "C" int lcb_phot_fit_batch(const lcb_phot_batch* in, const lcb_fit_opts* opt, lcb_phot_out* out,
                                   int mem, void* stream) {
+    LcbRange nvtx_range("lcb_phot_fit_batch");
     LCB_REQUIRE(in && opt && out, "lcb_phot_fit_batch: NULL argument");
     LCB_REQUIRE(in->B >= 0 && in->n >= 4 && in->k >= 1 && in->Fp >= 1, "lcb_phot_fit_batch: bad sizes B=%d n=%d k=%d Fp=%d",
                 in->B, in->n, in->k, in->Fp);

@@ -195,6 +195,7 @@ __global__ void k_phot_prep_guess(int F, int S, int n, float kk, const float* it
 extern "C" {
 
 int lcb_psf_prepare_batch(const lcb_psf_prepare_in* in, lcb_psf_prepare_out* out, void* stream) {
+    LcbRange nvtx_range("lcb_psf_prepare_batch");
     LCB_REQUIRE(in && out, "lcb_psf_prepare_batch: NULL argument");
     LCB_REQUIRE(in->F >= 0 && in->n >= 1 && in->k >= 1 && in->star_off && in->image && in->noisemap,
                 "lcb_psf_prepare_batch: bad input");
@@ -212,6 +213,7 @@ int lcb_psf_prepare_batch(const lcb_psf_prepare_in* in, lcb_psf_prepare_out* out
 size_t lcb_phot_prepare_work_floats(int F, int S) { return (size_t)4 * F * S + 16; }
 
 int lcb_phot_prepare_batch(const lcb_phot_prepare_in* in, lcb_phot_prepare_out* out, float* work, void* stream) {
+    LcbRange nvtx_range("lcb_phot_prepare_batch");
     LCB_REQUIRE(in && out && work, "lcb_phot_prepare_batch: NULL argument");
     LCB_REQUIRE(in->F >= 1 && in->S >= 1 && in->n >= 2 && in->n <= 128 && in->k >= 1 && in->data && in->noisemap,
                 "lcb_phot_prepare_batch: bad input (n <= 128)");

@@ -202,6 +202,7 @@ static int psf_run_device(const lcb_psf_batch* in, const lcb_psf_opts* opt, lcb_
 
 extern "C" int lcb_psf_fit_batch(const lcb_psf_batch* in, const lcb_psf_opts* opt, lcb_psf_out* out,
                                  int mem, void* stream) {
+    LcbRange nvtx_range("lcb_psf_fit_batch");
     LCB_REQUIRE(in && opt && out, "lcb_psf_fit_batch: NULL argument");
     LCB_REQUIRE(in->F >= 0 && in->n >= 4 && in->k >= 1, "lcb_psf_fit_batch: bad sizes F=%d n=%d k=%d", in->F, in->n, in->k);
     LCB_REQUIRE(opt->n_iter_analytic >= 0 && opt->n_iter_adabelief >= 0, "iteration counts must be >= 0");
