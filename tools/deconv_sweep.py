@@ -2,8 +2,11 @@
 
     python tools/deconv_sweep.py [--iters 100]
 
-Prints, per (E_local, cluster size), ms per iteration and the per-kernel split from lcb_profile_*.
-E_local = 200/100/50/25 are the shards of cfg4 on 1/2/4/8 GPUs."""
+Prints, per (E_local, cluster size), ms per iteration twice -- with CUDA-graph replays (what lcb_deconv_run does) and with eager
+launches under per-kernel CUDA events (lcb_profile_*), whose per-kernel split follows.  E_local = 200/100/50/25 are the shards of
+cfg4 on 1/2/4/8 GPUs.  With a -DLCB_DC_TIMERS build (python -m lightcurver_b200.build --variant dctim -DLCB_DC_TIMERS;
+LCB_LIBRARY=lightcurver_b200/liblcb_dctim.so) the clock64 stamps of the phases of k_deconv_epoch are printed as median / max cycles
+over the CTAs of the last launch.  LCB_DECONV_REDUCE=fused|separate and LCB_DECONV_CS=n select the reduction route / cluster size."""
 import argparse
 import sys
 from pathlib import Path
